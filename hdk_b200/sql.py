@@ -1,0 +1,381 @@
+"""A small SQL front end for the hot-path plan shapes.
+
+HDK parses SQL with Apache Calcite over JNI (omniscidb/Calcite, out of scope: no JVM here) and
+turns the relational algebra into a RelAlgExecutionUnit (QE/WorkUnitBuilder.cpp).  This module
+accepts the SELECT … FROM … [JOIN … ON a = b] [WHERE …] GROUP BY … [ORDER BY …] [LIMIT n] subset the
+named configs use and produces the same execution-unit shape (ir.ExecutionUnit), so that the
+parity tests can be written as SQL strings like the reference's own (`c("SELECT …", dt)`,
+omniscidb/Tests/ArrowBasedExecuteTest.cpp).  Anything else raises UnsupportedPlan.
+"""
+from __future__ import annotations
+
+import datetime
+import re
+from typing import Dict, List, Optional, Tuple
+
+from . import ir
+from .planner import UnsupportedPlan
+
+_TOKEN = re.compile(r"""
+    \s*(?:
+      (?P<num>\d+\.\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+|\d+)
+    | (?P<str>'(?:[^']|'')*')
+    | (?P<id>[A-Za-z_][A-Za-z_0-9]*|"[^"]+")
+    | (?P<op><>|!=|<=|>=|[-+*/=<>(),.])
+    )""", re.X)
+
+_KEYWORDS = {"select", "from", "where", "group", "by", "order", "limit", "join", "inner", "on", "and", "or",
+             "not", "as", "is", "null", "asc", "desc", "extract", "year", "cast", "date", "timestamp",
+             "between", "count", "sum", "min", "max", "avg"}
+
+
+def _tokenize(s: str):
+    pos, out = 0, []
+    s = s.strip().rstrip(";")
+    while pos < len(s):
+        m = _TOKEN.match(s, pos)
+        if not m or m.end() == pos:
+            raise UnsupportedPlan(f"cannot tokenize SQL at: {s[pos:pos + 20]!r}")
+        pos = m.end()
+        if m.group("num"):
+            out.append(("num", m.group("num")))
+        elif m.group("str"):
+            out.append(("str", m.group("str")[1:-1].replace("''", "'")))
+        elif m.group("id"):
+            t = m.group("id")
+            if t.startswith('"'):
+                out.append(("id", t[1:-1]))
+            elif t.lower() in _KEYWORDS:
+                out.append(("kw", t.lower()))
+            else:
+                out.append(("id", t))
+        else:
+            out.append(("op", m.group("op")))
+    out.append(("eof", ""))
+    return out
+
+
+_SQL_TYPES = {"int": ("int", 4), "integer": ("int", 4), "bigint": ("int", 8), "smallint": ("int", 2),
+              "tinyint": ("int", 1), "double": ("fp", 8), "float": ("fp", 4), "real": ("fp", 4)}
+
+
+class _Parser:
+    def __init__(self, sql: str, tables: Dict[str, object]):
+        self.toks = _tokenize(sql)
+        self.i = 0
+        self.tables = tables           # name -> storage.Table
+        self.scopes: List[Tuple[str, str, int]] = []   # (alias, table name, table index)
+
+    # -- token helpers
+    def peek(self, k=0):
+        return self.toks[self.i + k]
+
+    def eat(self, kind=None, val=None):
+        t = self.toks[self.i]
+        if (kind and t[0] != kind) or (val is not None and t[1] != val):
+            raise UnsupportedPlan(f"SQL: expected {val or kind}, got {t[1]!r}")
+        self.i += 1
+        return t
+
+    def accept(self, kind, val=None):
+        t = self.toks[self.i]
+        if t[0] == kind and (val is None or t[1] == val):
+            self.i += 1
+            return True
+        return False
+
+    # -- name resolution
+    def resolve(self, qual: Optional[str], col: str) -> ir.ColumnRef:
+        hits = []
+        for alias, tname, tidx in self.scopes:
+            if qual is not None and qual.lower() not in (alias.lower(), tname.lower()):
+                continue
+            t = self.tables[tname]
+            for cname, ci in t.columns.items():
+                if cname.lower() == col.lower():
+                    hits.append(ir.ColumnRef(tidx, cname, ci.type, ci.phys_width))
+        if len(hits) != 1:
+            raise UnsupportedPlan(f"SQL: cannot resolve column {qual + '.' if qual else ''}{col}")
+        return hits[0]
+
+    # -- expressions (precedence: or < and < not < cmp < add < mul < unary)
+    def expr(self):
+        e = self.and_expr()
+        while self.accept("kw", "or"):
+            e = ir.Logic("or", (e, self.and_expr()))
+        return e
+
+    def and_expr(self):
+        e = self.not_expr()
+        while self.accept("kw", "and"):
+            e = ir.Logic("and", (e, self.not_expr()))
+        return e
+
+    def not_expr(self):
+        if self.accept("kw", "not"):
+            return ir.Logic("not", (self.not_expr(),))
+        return self.cmp_expr()
+
+    def cmp_expr(self):
+        lhs = self.add_expr()
+        t = self.peek()
+        if t[0] == "op" and t[1] in ("<", "<=", ">", ">=", "=", "<>", "!="):
+            self.i += 1
+            rhs = self.add_expr()
+            lhs, rhs = self._coerce_temporal(lhs, rhs)
+            return ir.make_cmp("<>" if t[1] == "!=" else t[1], lhs, rhs)
+        if t == ("kw", "is"):
+            self.i += 1
+            neg = self.accept("kw", "not")
+            self.eat("kw", "null")
+            e = ir.IsNull(lhs)
+            return ir.Logic("not", (e,), ir.SqlType("bool", 1, False)) if neg else e
+        if t == ("kw", "between"):
+            self.i += 1
+            lo = self.add_expr()
+            self.eat("kw", "and")
+            hi = self.add_expr()
+            l1, lo = self._coerce_temporal(lhs, lo)
+            l2, hi = self._coerce_temporal(lhs, hi)
+            return ir.Logic("and", (ir.make_cmp(">=", l1, lo), ir.make_cmp("<=", l2, hi)))
+        return lhs
+
+    def _coerce_temporal(self, a, b):
+        """DATE/TIMESTAMP literal vs temporal column: express the literal in the column's unit."""
+        def conv(col, lit):
+            if isinstance(lit, ir.Const) and isinstance(lit.value, datetime.datetime) :
+                secs = int((lit.value - datetime.datetime(1970, 1, 1)).total_seconds())
+                ct = col.type
+                if ct.kind == "timestamp":
+                    v = secs * ct.unit
+                elif ct.kind == "date":
+                    v = secs           # date-in-days columns decode to seconds
+                else:
+                    raise UnsupportedPlan("date literal compared with a non-temporal expression")
+                return ir.Const(v, ir.SqlType("int", 8, False))
+            return lit
+        return conv(b, a), conv(a, b)
+
+    def add_expr(self):
+        e = self.mul_expr()
+        while self.peek()[0] == "op" and self.peek()[1] in "+-":
+            op = self.eat()[1]
+            e = ir.make_binop(op, e, self.mul_expr())
+        return e
+
+    def mul_expr(self):
+        e = self.unary()
+        while self.peek()[0] == "op" and self.peek()[1] in "*/":
+            op = self.eat()[1]
+            e = ir.make_binop(op, e, self.unary())
+        return e
+
+    def unary(self):
+        if self.accept("op", "-"):
+            a = self.unary()
+            if isinstance(a, ir.Const):
+                return ir.Const(-a.value, a.type)
+            return ir.UMinus(a, a.type)
+        if self.accept("op", "+"):
+            return self.unary()
+        return self.primary()
+
+    def primary(self):
+        t = self.peek()
+        if t[0] == "num":
+            self.i += 1
+            s = t[1]
+            if re.fullmatch(r"\d+", s):
+                v = int(s)
+                return ir.Const(v, ir.SqlType("int", 4 if -(1 << 31) < v < (1 << 31) else 8, False))
+            return ir.Const(float(s), ir.SqlType("fp", 8, False))
+        if t[0] == "op" and t[1] == "(":
+            self.i += 1
+            e = self.expr()
+            self.eat("op", ")")
+            return e
+        if t[0] == "kw" and t[1] in ("date", "timestamp") and self.peek(1)[0] == "str":
+            self.i += 1
+            s = self.eat("str")[1]
+            fmt = "%Y-%m-%d" if len(s) <= 10 else "%Y-%m-%d %H:%M:%S"
+            return ir.Const(datetime.datetime.strptime(s, fmt), ir.SqlType("timestamp", 8, False))
+        if t[0] == "str":
+            self.i += 1
+            return ir.Const(t[1], ir.SqlType("dict", 4, False))
+        if t[0] == "kw" and t[1] in ("count", "sum", "min", "max", "avg"):
+            self.i += 1
+            self.eat("op", "(")
+            if t[1] == "count" and self.accept("op", "*"):
+                self.eat("op", ")")
+                return ir.make_agg("count", None, self.bigint_count)
+            arg = self.expr()
+            self.eat("op", ")")
+            return ir.make_agg(t[1], arg, self.bigint_count)
+        if t == ("kw", "extract"):
+            self.i += 1
+            self.eat("op", "(")
+            self.eat("kw", "year")
+            self.eat("kw", "from")
+            arg = self.expr()
+            self.eat("op", ")")
+            if arg.type.kind not in ("timestamp", "date"):
+                raise UnsupportedPlan("EXTRACT from a non-temporal expression")
+            return ir.ExtractYear(arg, ir.SqlType("int", 8, arg.type.nullable))
+        if t == ("kw", "cast"):
+            self.i += 1
+            self.eat("op", "(")
+            arg = self.expr()
+            self.eat("kw", "as")
+            tn = self.eat()[1].lower()
+            if tn == "double" and self.peek()[1].lower() == "precision":
+                self.i += 1
+            self.eat("op", ")")
+            if tn not in _SQL_TYPES:
+                raise UnsupportedPlan(f"CAST to {tn}")
+            kind, w = _SQL_TYPES[tn]
+            return ir.cast_to(arg, ir.SqlType(kind, w, arg.type.nullable))
+        if t[0] == "id":
+            self.i += 1
+            if self.accept("op", "."):
+                col = self.eat("id")[1]
+                return self.resolve(t[1], col)
+            return self.resolve(None, t[1])
+        raise UnsupportedPlan(f"SQL: unexpected token {t[1]!r}")
+
+    # -- statement
+    def parse(self, bigint_count=False) -> ir.ExecutionUnit:
+        self.bigint_count = bigint_count
+        self.eat("kw", "select")
+        # the select list needs the FROM scopes: scan ahead for FROM at depth 0
+        depth, j = 0, self.i
+        while not (self.toks[j] == ("kw", "from") and depth == 0):
+            if self.toks[j] == ("op", "("):
+                depth += 1
+            elif self.toks[j] == ("op", ")"):
+                depth -= 1
+            elif self.toks[j][0] == "eof":
+                raise UnsupportedPlan("SQL: missing FROM")
+            j += 1
+        select_start, self.i = self.i, j + 1
+        table, alias = self._table_ref()
+        self.scopes.append((alias, table, 0))
+        joins_raw = []
+        while self.peek() in (("kw", "join"), ("kw", "inner")):
+            if self.accept("kw", "inner"):
+                pass
+            self.eat("kw", "join")
+            t2, a2 = self._table_ref()
+            self.scopes.append((a2, t2, len(joins_raw) + 1))
+            self.eat("kw", "on")
+            cond = self.expr()
+            joins_raw.append((t2, cond))
+        after_from = self.i
+        # select list
+        self.i = select_start
+        targets, names = [], []
+        while True:
+            e = self.expr()
+            name = None
+            if self.accept("kw", "as"):
+                name = self.eat()[1]
+            elif self.peek()[0] == "id":
+                name = self.eat("id")[1]
+            targets.append(e)
+            names.append(name)
+            if not self.accept("op", ","):
+                break
+        if self.peek() != ("kw", "from"):
+            raise UnsupportedPlan(f"SQL: unexpected {self.peek()[1]!r} in select list")
+        self.i = after_from
+        quals = []
+        if self.accept("kw", "where"):
+            quals = _split_conjuncts(self.expr())
+        groupby = []
+        if self.accept("kw", "group"):
+            self.eat("kw", "by")
+            while True:
+                g = self.expr()
+                if isinstance(g, ir.Const) and isinstance(g.value, int) and 1 <= g.value <= len(targets):
+                    g = targets[g.value - 1]      # GROUP BY ordinal
+                groupby.append(g)
+                if not self.accept("op", ","):
+                    break
+        order = []
+        if self.accept("kw", "order"):
+            self.eat("kw", "by")
+            while True:
+                save = self.i
+                key = None
+                if self.peek()[0] == "id" and self.peek()[1] in [n for n in names if n]:
+                    key = self.eat()[1]
+                else:
+                    self.i = save
+                    e = self.expr()
+                    if isinstance(e, ir.Const) and isinstance(e.value, int):
+                        key = e.value - 1
+                    elif e in targets:
+                        key = targets.index(e)
+                    else:
+                        raise UnsupportedPlan("ORDER BY expression must be a select item")
+                desc = False
+                if self.accept("kw", "desc"):
+                    desc = True
+                else:
+                    self.accept("kw", "asc")
+                order.append((key, desc))
+                if not self.accept("op", ","):
+                    break
+        limit = None
+        if self.accept("kw", "limit"):
+            limit = int(self.eat("num")[1])
+        self.eat("eof")
+        joins = []
+        for t2, cond in joins_raw:
+            if not (isinstance(cond, ir.Cmp) and cond.op == "="):
+                raise UnsupportedPlan("only single-column equi-joins are on the hot path")
+            lhs, rhs = cond.lhs, cond.rhs
+            strip = lambda x: x.arg if isinstance(x, ir.Cast) else x  # noqa: E731
+            lhs, rhs = strip(lhs), strip(rhs)
+            jidx = len(joins) + 1
+            if isinstance(rhs, ir.ColumnRef) and rhs.table == jidx:
+                outer, inner = lhs, rhs
+            elif isinstance(lhs, ir.ColumnRef) and lhs.table == jidx:
+                outer, inner = rhs, lhs
+            else:
+                raise UnsupportedPlan("join condition must compare an outer expression with an inner column")
+            joins.append(ir.JoinSpec(t2, outer, inner.column))
+        final_names = []
+        for i, (e, n) in enumerate(zip(targets, names)):
+            if n is None:
+                n = e.column if isinstance(e, ir.ColumnRef) else f"EXPR${i}"
+            final_names.append(n)
+        order = [(final_names.index(k) if isinstance(k, str) else k, d) for k, d in order]
+        return ir.ExecutionUnit(table, groupby, targets, final_names, quals, joins, order, limit)
+
+    def _table_ref(self):
+        name = self.eat("id")[1]
+        real = None
+        for t in self.tables:
+            if t.lower() == name.lower():
+                real = t
+        if real is None:
+            raise UnsupportedPlan(f"SQL: unknown table {name}")
+        alias = real
+        if self.accept("kw", "as"):
+            alias = self.eat("id")[1]
+        elif self.peek()[0] == "id":
+            alias = self.eat("id")[1]
+        return real, alias
+
+
+def _split_conjuncts(e: ir.Expr) -> List[ir.Expr]:
+    if isinstance(e, ir.Logic) and e.op == "and":
+        out = []
+        for a in e.args:
+            out += _split_conjuncts(a)
+        return out
+    return [e]
+
+
+def parse(sql: str, tables: Dict[str, object], bigint_count=False) -> ir.ExecutionUnit:
+    return _Parser(sql, tables).parse(bigint_count)
