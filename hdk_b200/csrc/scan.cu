@@ -1,0 +1,518 @@
+// hdk_b200/csrc/scan.cu — the fused scan → filter → join probe → group-by → aggregate kernel.
+//
+// Replaces the JIT'd multifrag_query_hoisted_literals / query_group_by_template / row_func of the
+// reference (QE/RuntimeFunctions.cpp:1692-1726, QE/QueryTemplateGenerator.cpp:488-772) and the
+// runtime it calls per row (QE/GroupByRuntime.cpp, QE/cuda_mapd_rt.cu:423-1083).
+//
+// Execution model (sm_100a):
+//   * persistent grid, a multiple of the SM count; every CTA walks tiles t = blockIdx.x, +gridDim.x
+//   * one producer warp streams each tile's column slices global → shared with 1-D TMA bulk copies
+//     (cp.async.bulk … mbarrier::complete_tx, SASS UBLKCP) through a kStages-deep mbarrier ring;
+//     unaligned heads/tails (< 16 B per column) are patched with byte copies, so any chunk pointer
+//     and any row count work on the same path
+//   * kConsumerWarps consumer warps evaluate the expression DAG per row out of shared memory and
+//     accumulate into NEUTRAL accumulators (SUM→0, MIN→+max, MAX→−max, counters) — the same
+//     representation merges across CTAs (atomics) and across GPUs (NCCL SUM/MIN/MAX):
+//       THREAD_PRIVATE : per-thread bins in shared memory, [acc][group][thread], no atomics,
+//                        bank-conflict free by construction          (few groups)
+//       CTA_SHARED     : one table per CTA in shared memory, shared atomics   (up to ~100 KB)
+//       GLOBAL         : straight into the global work table with RED atomics
+//   * a finalize kernel converts the work table into the reference's buffer encoding
+//     (finalize.cu), so the result is byte-compatible with QueryMemoryDescriptor.
+#include <algorithm>
+
+#include "common.cuh"
+#include "baseline.cuh"
+#include "device_utils.cuh"
+#include "eval.cuh"
+#include "scan.cuh"
+
+namespace hb {
+
+// Is the accumulator's argument NULL for this row?  mode 1: the argument's own sentinel; mode 2: the
+// reference's COUNT(int64) quirk (see lower.cu)
+__device__ __forceinline__ bool acc_arg_is_null(const DPlan& p, const DAcc& a, const V* vals) {
+  if (!a.arg_nullable) return false;
+  const DExpr& t = p.exprs[a.arg];
+  const V v = vals[a.arg];
+  if (t.kind == HDK_B200_FP) return v.f == fp_null_of(t.width);
+  if (v.i == int_null_of(t.width)) return true;
+  return a.arg_nullable == 2 && int32_t(v.i) == INT32_MIN;
+}
+
+__device__ __forceinline__ int64_t acc_identity(uint8_t kind) {
+  return (kind == ACC_MIN_I || kind == ACC_MIN_F) ? INT64_MAX : (kind == ACC_MAX_I || kind == ACC_MAX_F) ? INT64_MIN : 0;
+}
+
+// value contributed by this row to accumulator `a` (as an int64 cell / double bits)
+__device__ __forceinline__ int64_t acc_input(const DPlan& p, const DAcc& a, const V* vals) {
+  switch (a.kind) {
+    case ACC_CNT_ALL: case ACC_CNT_NN: return 1;
+    case ACC_SUM_I: case ACC_MIN_I: case ACC_MAX_I: return vals[a.arg].i;
+    case ACC_SUM_F: return vals[a.arg].i;  // bits of the double
+    default: return f64_order_encode(vals[a.arg].f);  // MIN_F / MAX_F
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// accumulator updates
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bin_update_private(uint8_t kind, uint8_t* bin, int64_t x) {
+  switch (kind) {
+    case ACC_CNT_ALL: case ACC_CNT_NN: *reinterpret_cast<uint32_t*>(bin) += 1u; break;
+    case ACC_SUM_I: *reinterpret_cast<int64_t*>(bin) += x; break;
+    case ACC_SUM_F: *reinterpret_cast<double*>(bin) += __longlong_as_double(x); break;
+    case ACC_MIN_I: case ACC_MIN_F: { int64_t* b = reinterpret_cast<int64_t*>(bin); *b = min(*b, x); break; }
+    default: { int64_t* b = reinterpret_cast<int64_t*>(bin); *b = max(*b, x); break; }
+  }
+}
+__device__ __forceinline__ void bin_update_shared_atomic(uint8_t kind, uint8_t* bin, int64_t x) {
+  switch (kind) {
+    case ACC_CNT_ALL: case ACC_CNT_NN: atomicAdd(reinterpret_cast<uint32_t*>(bin), 1u); break;
+    case ACC_SUM_I: atomicAdd(reinterpret_cast<unsigned long long*>(bin), static_cast<unsigned long long>(x)); break;
+    case ACC_SUM_F: atomicAdd(reinterpret_cast<double*>(bin), __longlong_as_double(x)); break;
+    case ACC_MIN_I: case ACC_MIN_F: atomicMin(reinterpret_cast<long long*>(bin), static_cast<long long>(x)); break;
+    default: atomicMax(reinterpret_cast<long long*>(bin), static_cast<long long>(x)); break;
+  }
+}
+__device__ __forceinline__ void cell_update_global(uint8_t kind, int64_t* cell, int64_t x) {
+  switch (kind) {
+    case ACC_CNT_ALL: case ACC_CNT_NN: case ACC_SUM_I:
+      atomicAdd(reinterpret_cast<unsigned long long*>(cell), static_cast<unsigned long long>(x)); break;
+    case ACC_SUM_F: atomicAdd(reinterpret_cast<double*>(cell), __longlong_as_double(x)); break;
+    case ACC_MIN_I: case ACC_MIN_F: atomicMin(reinterpret_cast<long long*>(cell), static_cast<long long>(x)); break;
+    default: atomicMax(reinterpret_cast<long long*>(cell), static_cast<long long>(x)); break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+struct StageHeader {          // written by the producer, read by consumers
+  uint32_t rows;              // rows in this tile
+  uint32_t pad;
+  uint32_t col_off[HDK_B200_MAX_COLS];  // byte offset (from dynamic smem base) of element 0 of column c
+};
+
+template <int kStrategy>
+__global__ void __launch_bounds__(kThreads, 1) scan_kernel(const __grid_constant__ ScanArgs args) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const DPlan& p = args.plan;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool is_producer = warp == kConsumerWarps;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + kStages;
+  StageHeader* hdr = reinterpret_cast<StageHeader*>(smem + 128);
+  uint32_t* tile_prefix = reinterpret_cast<uint32_t*>(smem + args.off_tile_prefix);  // [nfrag + 1]
+  uint8_t* bins = smem + args.off_bins;
+
+  // ---- prologue: barriers, tile prefix, bins
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    // inclusive scan of per-fragment tile counts, 32 fragments per step
+    uint32_t carry = 0;
+    if (lane == 0) tile_prefix[0] = 0;
+    for (uint32_t f0 = 0; f0 < args.num_fragments; f0 += 32) {
+      const uint32_t f = f0 + lane;
+      uint32_t t = 0;
+      if (f < args.num_fragments) {
+        const int64_t rows = args.num_rows[f];
+        t = rows > 0 ? uint32_t((rows + args.tile_rows - 1) / args.tile_rows) : 0;
+      }
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, t, d);
+        if (lane >= d) t += o;
+      }
+      if (f < args.num_fragments) tile_prefix[f + 1] = carry + t;
+      carry += __shfl_sync(0xffffffffu, t, 31);
+    }
+  }
+  if (!is_producer && kStrategy != HDK_B200_STRATEGY_GLOBAL && kStrategy != HDK_B200_STRATEGY_BASELINE) {
+    // initialise bins to the accumulators' identities
+    for (int a = 0; a < p.n_acc; ++a) {
+      const DAcc acc = p.accs[a];
+      uint8_t* base = bins + args.acc_bin_off[a];
+      const uint32_t n = kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE ? p.entry_count * kConsumerThreads : p.entry_count;
+      if (acc.bytes == 4) {
+        for (uint32_t i = tid; i < n; i += kConsumerThreads) reinterpret_cast<uint32_t*>(base)[i] = 0;
+      } else {
+        const int64_t id = acc_identity(acc.kind);
+        for (uint32_t i = tid; i < n; i += kConsumerThreads) reinterpret_cast<int64_t*>(base)[i] = id;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t total_tiles = tile_prefix[args.num_fragments];
+
+  if (is_producer) {
+    // =============================== producer warp ===============================
+    const uint64_t policy = policy_evict_first();
+    uint32_t it = 0;
+    uint32_t frag = 0;
+    for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const uint32_t stage = it % kStages;
+      const uint32_t round = it / kStages;
+      if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1);
+      while (tile_prefix[frag + 1] <= t) ++frag;  // tiles are visited in increasing order
+      const uint64_t row0 = uint64_t(t - tile_prefix[frag]) * args.tile_rows;
+      const uint64_t frag_rows = uint64_t(args.num_rows[frag]);
+      const uint32_t rows = uint32_t(min(uint64_t(args.tile_rows), frag_rows - row0));
+      uint8_t* stage_base = smem + args.off_stages + size_t(stage) * args.stage_bytes;
+      uint32_t tx_bytes = 0;
+      // pass 1: heads / tails by byte copies (generic proxy), header, tx byte count
+      for (int c = 0; c < p.n_cols; ++c) {
+        const uint32_t w = p.col_width[c];
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(args.col_buffers[size_t(frag) * p.n_cols + c]) + row0 * w;
+        const uint32_t bytes = rows * w;
+        const uint32_t m = uint32_t(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint32_t head = m ? min(16u - m, bytes) : 0u;
+        const uint32_t mid = (bytes - head) & ~15u;
+        const uint32_t tail = bytes - head - mid;
+        uint8_t* region = stage_base + args.col_region_off[c];
+        uint8_t* dst = region + m;
+        for (uint32_t i = lane; i < head; i += 32) dst[i] = src[i];
+        for (uint32_t i = lane; i < tail; i += 32) dst[head + mid + i] = src[head + mid + i];
+        tx_bytes += mid;
+        if (lane == 0) hdr[stage].col_off[c] = uint32_t(dst - smem);
+      }
+      if (lane == 0) hdr[stage].rows = rows;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        for (int c = 0; c < p.n_cols; ++c) {
+          const uint32_t w = p.col_width[c];
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(args.col_buffers[size_t(frag) * p.n_cols + c]) + row0 * w;
+          const uint32_t bytes = rows * w;
+          const uint32_t m = uint32_t(reinterpret_cast<uintptr_t>(src) & 15u);
+          const uint32_t head = m ? min(16u - m, bytes) : 0u;
+          const uint32_t mid = (bytes - head) & ~15u;
+          if (mid) bulk_g2s(stage_base + args.col_region_off[c] + m + head, src + head, mid, &full_bar[stage], policy);
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== consumer warps ===============================
+    V vals[HDK_B200_MAX_EXPRS];
+    int32_t my_err = 0;
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const uint32_t stage = it % kStages;
+      mbar_wait(&full_bar[stage], (it / kStages) & 1);
+      const uint32_t rows = hdr[stage].rows;
+      const uint32_t* col_off = hdr[stage].col_off;
+      for (uint32_t r = tid; r < rows; r += kConsumerThreads) {
+        int64_t rowid[HDK_B200_MAX_JOINS];
+        auto load_outer = [&](int c, int w) -> uint64_t {
+          const uint8_t* ptr = smem + col_off[c] + size_t(r) * w;
+          return w == 8 ? *reinterpret_cast<const uint64_t*>(ptr) : w == 4 ? uint64_t(*reinterpret_cast<const uint32_t*>(ptr))
+                 : w == 2 ? uint64_t(*reinterpret_cast<const uint16_t*>(ptr)) : uint64_t(*ptr);
+        };
+        auto load_inner = [&](int j, int c, int w) -> uint64_t {
+          const uint8_t* ptr = reinterpret_cast<const uint8_t*>(args.inner_col_buffers[j * HDK_B200_MAX_COLS + c]) + size_t(rowid[j]) * w;
+          return w == 8 ? __ldg(reinterpret_cast<const uint64_t*>(ptr)) : w == 4 ? uint64_t(__ldg(reinterpret_cast<const uint32_t*>(ptr)))
+                 : w == 2 ? uint64_t(__ldg(reinterpret_cast<const uint16_t*>(ptr))) : uint64_t(__ldg(ptr));
+        };
+        int32_t row_err = 0;
+        bool dropped = false;
+        // 1:N join: nodes up to the key are evaluated once, the rest once per match
+        int n_matches = 1;
+        const int32_t* match_ids = nullptr;
+        int split = p.n_exprs;
+        if (p.n_joins == 1 && p.joins[0].one_to_many) split = p.joins[0].key_expr + 1;
+        for (int n = 0; n < split && !dropped; ++n) {
+          int32_t e = 0;
+          vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
+          if (e && !row_err) row_err = e;
+          for (int j = 0; j < p.n_joins; ++j) {
+            const DJoin& jn = p.joins[j];
+            if (jn.key_expr != n) continue;
+            // hash_join_idx[_nullable] (QE/GroupByRuntime.cpp:298-329)
+            const int64_t key = vals[n].i;
+            if ((jn.key_nullable && key == jn.null_val) || key < jn.min_key || key > jn.max_key) { dropped = true; break; }
+            const int32_t* table = reinterpret_cast<const int32_t*>(args.join_hash_tables[j]);
+            const int64_t slot = key - jn.min_key;
+            if (jn.one_to_many) {
+              // offsets | counts | payload (JHT/PerfectJoinHashTable.cpp:861-886)
+              const int64_t E = p.join_entry_count[j];
+              const int32_t off = __ldg(table + slot);
+              if (off < 0) { dropped = true; break; }
+              n_matches = __ldg(table + E + slot);
+              match_ids = table + 2 * E + off;
+            } else {
+              const int32_t idx = __ldg(table + slot);
+              if (idx < 0) { dropped = true; break; }
+              rowid[j] = idx;
+            }
+          }
+        }
+        if (dropped) continue;
+        for (int mi = 0; mi < n_matches; ++mi) {
+          if (match_ids) rowid[0] = __ldg(match_ids + mi);
+          for (int n = split; n < p.n_exprs; ++n) {
+            int32_t e = 0;
+            vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
+            if (e && !row_err) row_err = e;
+          }
+          bool pass = true;
+          for (int f = 0; f < p.n_filters; ++f) pass = pass && (vals[p.filters[f]].i > 0);
+          if (!pass) continue;
+          if (row_err) { my_err = my_err > 0 ? my_err : row_err; continue; }
+          if (kStrategy == HDK_B200_STRATEGY_BASELINE) {
+            // baseline hash: find / claim the entry in the reference-encoded buffer, update slots in place
+            const DLayout& L = args.layout;
+            int8_t* buf = reinterpret_cast<int8_t*>(args.groupby_buf[0]);
+            int64_t keys[HDK_B200_MAX_KEYS];
+            for (int k = 0; k < p.n_keys; ++k) {
+              const int64_t v = vals[p.keys[k].expr].i;
+              keys[k] = L.key_width == 4 ? int64_t(int32_t(v)) : v;  // castToTypeIn(key, key_width * 8), no NULL translation
+            }
+            const uint32_t h0 = key_hash_dev(keys, p.n_keys, L.key_width) % p.entry_count;
+            const int64_t entry = L.columnar ? baseline_claim_columnar(reinterpret_cast<int64_t*>(buf), p.entry_count, keys, p.n_keys, h0)
+                                  : L.key_width == 4 ? baseline_claim_rowwise<int32_t>(buf, L.row_bytes, p.entry_count, keys, p.n_keys, h0)
+                                                     : baseline_claim_rowwise<int64_t>(buf, L.row_bytes, p.entry_count, keys, p.n_keys, h0);
+            if (entry < 0) { if (my_err <= 0) my_err = -HDK_B200_ERR_OUT_OF_SLOTS; continue; }
+            for (int s = 0; s < L.slot_count; ++s) {
+              const DSlot& sl = L.slots[s];
+              if (!sl.padded || sl.op == SLOT_KEY) continue;
+              int64_t vi = 0;
+              double vf = 0.0;
+              bool arg_null = false;
+              if (sl.arg >= 0) {
+                vi = vals[sl.arg].i;
+                vf = vals[sl.arg].f;
+                if (sl.arg_nullable) {
+                  arg_null = sl.arg_kind == HDK_B200_FP ? (vf == fp_null_of(sl.arg_width)) : (vi == int_null_of(sl.arg_width));
+                  if (sl.count_mode == 2 && int32_t(vi) == INT32_MIN) arg_null = true;
+                }
+              }
+              int8_t* ptr = L.columnar ? buf + sl.col_off + size_t(entry) * sl.padded
+                                       : buf + size_t(entry) * L.row_bytes + L.key_bytes + sl.off;
+              baseline_update_slot(sl, ptr, vi, vf, arg_null);
+            }
+            continue;
+          }
+          // perfect-hash slot: get_group_value_fast / perfect_key_hash (QE/GroupByRuntime.cpp:198-213,
+          // QE/RowFuncBuilder.cpp:748-801) incl. translate_null_key
+          uint32_t idx;
+          {
+            int64_t h = 0;
+            for (int k = 0; k < p.n_keys; ++k) {
+              const DKey& ky = p.keys[k];
+              int64_t v = vals[ky.expr].i;
+              if (ky.has_nulls && v == int_null_of(ky.width)) v = ky.null_translated;
+              h += (v - ky.min_val) * ky.mult;
+            }
+            idx = uint32_t(h);
+          }
+          if (idx >= p.entry_count) { my_err = my_err > 0 ? my_err : 1003; continue; }  // key outside the range the layout was built for
+          for (int a = 0; a < p.n_acc; ++a) {
+            const DAcc acc = p.accs[a];
+            if (acc_arg_is_null(p, acc, vals)) continue;
+            const int64_t x = acc_input(p, acc, vals);
+            if (kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE) {
+              bin_update_private(acc.kind, bins + args.acc_bin_off[a] + (size_t(idx) * kConsumerThreads + tid) * acc.bytes, x);
+            } else if (kStrategy == HDK_B200_STRATEGY_CTA_SHARED) {
+              bin_update_shared_atomic(acc.kind, bins + args.acc_bin_off[a] + size_t(idx) * acc.bytes, x);
+            } else {
+              cell_update_global(acc.kind, args.work_table + size_t(a) * p.entry_count + idx, x);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+    if (my_err) record_error(args.error_codes, my_err);
+
+    // ---- flush block partials into the global work table
+    if (kStrategy != HDK_B200_STRATEGY_GLOBAL && kStrategy != HDK_B200_STRATEGY_BASELINE) {
+      named_bar_sync(1, kConsumerThreads);
+      if (kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE) {
+        // one (acc, group) pair per warp step: lanes stride the kConsumerThreads private copies
+        const uint32_t pairs = uint32_t(p.n_acc) * p.entry_count;
+        for (uint32_t pr = warp; pr < pairs; pr += kConsumerWarps) {
+          const uint32_t a = pr / p.entry_count, g = pr % p.entry_count;
+          const DAcc acc = p.accs[a];
+          const uint8_t* base = bins + args.acc_bin_off[a] + size_t(g) * kConsumerThreads * acc.bytes;
+          int64_t x;
+          if (acc.bytes == 4) {
+            uint64_t s = 0;
+            for (int i = lane; i < kConsumerThreads; i += 32) s += reinterpret_cast<const uint32_t*>(base)[i];
+            for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            x = int64_t(s);
+          } else if (acc.kind == ACC_SUM_I) {
+            int64_t s = 0;
+            for (int i = lane; i < kConsumerThreads; i += 32) s += reinterpret_cast<const int64_t*>(base)[i];
+            for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            x = s;
+          } else if (acc.kind == ACC_SUM_F) {
+            double s = 0.0;
+            for (int i = lane; i < kConsumerThreads; i += 32) s += reinterpret_cast<const double*>(base)[i];
+            for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            x = __double_as_longlong(s);
+          } else if (acc.kind == ACC_MIN_I || acc.kind == ACC_MIN_F) {
+            int64_t s = INT64_MAX;
+            for (int i = lane; i < kConsumerThreads; i += 32) s = min(s, reinterpret_cast<const int64_t*>(base)[i]);
+            for (int d = 16; d; d >>= 1) s = min(s, __shfl_xor_sync(0xffffffffu, s, d));
+            x = s;
+          } else {
+            int64_t s = INT64_MIN;
+            for (int i = lane; i < kConsumerThreads; i += 32) s = max(s, reinterpret_cast<const int64_t*>(base)[i]);
+            for (int d = 16; d; d >>= 1) s = max(s, __shfl_xor_sync(0xffffffffu, s, d));
+            x = s;
+          }
+          if (lane == 0) {
+            if (x != acc_identity(acc.kind))
+              cell_update_global(acc.kind, args.work_table + size_t(a) * p.entry_count + g, x);
+          }
+        }
+      } else {
+        for (int a = 0; a < p.n_acc; ++a) {
+          const DAcc acc = p.accs[a];
+          const uint8_t* base = bins + args.acc_bin_off[a];
+          for (uint32_t g = tid; g < p.entry_count; g += kConsumerThreads) {
+            const int64_t x = acc.bytes == 4 ? int64_t(reinterpret_cast<const uint32_t*>(base)[g]) : reinterpret_cast<const int64_t*>(base)[g];
+            if (x != acc_identity(acc.kind)) cell_update_global(acc.kind, args.work_table + size_t(a) * p.entry_count + g, x);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// work table initialisation
+// ---------------------------------------------------------------------------------------------
+__global__ void init_work_table_kernel(int64_t* w, uint64_t E, int n_acc, const __grid_constant__ AccKinds kinds) {
+  const uint64_t n = uint64_t(n_acc) * E;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
+    w[i] = acc_identity(kinds.kind[i / E]);
+}
+
+int init_work_table(const Lowered& lw, int64_t* work_table, cudaStream_t stream) {
+  AccKinds kinds{};
+  for (int a = 0; a < lw.plan.n_acc; ++a) kinds.kind[a] = lw.plan.accs[a].kind;
+  const uint64_t n = uint64_t(lw.plan.n_acc) * lw.plan.entry_count;
+  const int block = 256;
+  const int grid = int(std::min<uint64_t>((n + block - 1) / block, uint64_t(sm_count()) * 8));
+  init_work_table_kernel<<<std::max(grid, 1), block, 0, stream>>>(work_table, lw.plan.entry_count, lw.plan.n_acc, kinds);
+  HB_LAUNCH_CHECK();
+  return HDK_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: geometry + launch
+// ---------------------------------------------------------------------------------------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
+                            int64_t* work_table, bool baseline, cudaStream_t stream, hdk_b200_launch_info* info) {
+  const DPlan& p = lw.plan;
+  if (params->num_fragments > kMaxFragments) { set_error("more than %d fragments per launch", kMaxFragments); return HDK_B200_E_UNSUPPORTED; }
+  ScanArgs a{};
+  a.plan = p;
+  a.col_buffers = params->col_buffers;
+  a.num_rows = params->num_rows;
+  a.num_fragments = uint32_t(params->num_fragments);
+  a.join_hash_tables = params->join_hash_tables;
+  a.inner_col_buffers = params->inner_col_buffers;
+  a.work_table = work_table;
+  a.error_codes = params->error_codes;
+  a.layout = lw.layout;
+  a.groupby_buf = params->groupby_buf;
+
+  int dev = 0;
+  HB_CUDA(cudaGetDevice(&dev));
+  int max_smem = 0;
+  HB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+
+  // fixed part: barriers (128 B) + stage headers + tile prefix
+  size_t off = 128 + align_up(sizeof(StageHeader) * kStages, 16);
+  a.off_tile_prefix = uint32_t(off);
+  off += align_up(size_t(a.num_fragments + 1) * 4, 16);
+
+  // accumulator bins: pick the cheapest strategy that fits
+  const size_t E = p.entry_count;
+  size_t per_group_bytes = 0;
+  for (int i = 0; i < p.n_acc; ++i) per_group_bytes += p.accs[i].bytes;
+  const size_t private_bytes = per_group_bytes * E * kConsumerThreads;
+  const size_t shared_bytes = align_up(per_group_bytes * E, 16) + 16 * size_t(p.n_acc);
+  const size_t min_stage_budget = 3 * 4096 + 2048;
+  int strategy;
+  if (off + private_bytes + min_stage_budget * 2 <= size_t(max_smem) && private_bytes <= 144 * 1024) strategy = HDK_B200_STRATEGY_THREAD_PRIVATE;
+  else if (off + shared_bytes + min_stage_budget * 2 <= size_t(max_smem)) strategy = HDK_B200_STRATEGY_CTA_SHARED;
+  else strategy = HDK_B200_STRATEGY_GLOBAL;
+  if (ko && ko->sharedMemBytes == 0xB200F001u) strategy = HDK_B200_STRATEGY_THREAD_PRIVATE;  // test hooks: force a strategy
+  if (ko && ko->sharedMemBytes == 0xB200F002u) strategy = HDK_B200_STRATEGY_CTA_SHARED;
+  if (ko && ko->sharedMemBytes == 0xB200F003u) strategy = HDK_B200_STRATEGY_GLOBAL;
+  if (baseline) strategy = HDK_B200_STRATEGY_BASELINE;
+
+  off = align_up(off, 16);
+  a.off_bins = uint32_t(off);
+  size_t bins_bytes = 0;
+  for (int i = 0; i < p.n_acc; ++i) {
+    bins_bytes = align_up(bins_bytes, 16);
+    a.acc_bin_off[i] = uint32_t(bins_bytes);
+    if (strategy == HDK_B200_STRATEGY_THREAD_PRIVATE) bins_bytes += size_t(p.accs[i].bytes) * E * kConsumerThreads;
+    else if (strategy == HDK_B200_STRATEGY_CTA_SHARED) bins_bytes += size_t(p.accs[i].bytes) * E;
+  }
+  if (strategy == HDK_B200_STRATEGY_GLOBAL || strategy == HDK_B200_STRATEGY_BASELINE) bins_bytes = 0;
+  off += align_up(bins_bytes, 128);
+  if (off + min_stage_budget > size_t(max_smem)) { set_error("forced strategy does not fit in shared memory"); return HDK_B200_E_UNSUPPORTED; }
+  a.off_stages = uint32_t(align_up(off, 128));
+
+  // stage geometry: tile_rows is a power of two ≥ kConsumerThreads, stage ≤ ~24 KB and the ring fits
+  const size_t row_bytes = std::max<size_t>(lw.stage_row_bytes, 1);
+  const size_t avail = size_t(max_smem) - a.off_stages;
+  size_t per_stage = std::min<size_t>(avail / kStages, 28 * 1024);
+  uint32_t tile_rows = 64;
+  while (size_t(tile_rows) * 2 * row_bytes + 48 * size_t(p.n_cols) <= per_stage && tile_rows < 8192) tile_rows *= 2;
+  a.tile_rows = tile_rows;
+  size_t so = 0;
+  for (int c = 0; c < p.n_cols; ++c) {
+    a.col_region_off[c] = uint32_t(so);
+    so += align_up(size_t(tile_rows) * p.col_width[c] + 32, 16);  // +16 for the alignment shift, +16 slack
+  }
+  a.stage_bytes = uint32_t(align_up(so, 128));
+  const size_t smem_bytes = a.off_stages + size_t(a.stage_bytes) * kStages;
+  if (smem_bytes > size_t(max_smem)) { set_error("stage ring does not fit in shared memory (%zu > %d)", smem_bytes, max_smem); return HDK_B200_E_UNSUPPORTED; }
+
+  int grid = sm_count();
+  if (ko && ko->gridDimX) grid = int(ko->gridDimX);
+  void (*kern)(const ScanArgs) = strategy == HDK_B200_STRATEGY_THREAD_PRIVATE ? scan_kernel<HDK_B200_STRATEGY_THREAD_PRIVATE>
+                                 : strategy == HDK_B200_STRATEGY_CTA_SHARED   ? scan_kernel<HDK_B200_STRATEGY_CTA_SHARED>
+                                 : strategy == HDK_B200_STRATEGY_GLOBAL       ? scan_kernel<HDK_B200_STRATEGY_GLOBAL>
+                                                                              : scan_kernel<HDK_B200_STRATEGY_BASELINE>;
+  HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+  kern<<<grid, kThreads, smem_bytes, stream>>>(a);
+  HB_LAUNCH_CHECK();
+  if (info) {
+    info->variant = 0;
+    info->strategy = strategy;
+    info->grid = grid;
+    info->block = kThreads;
+    info->smem_bytes = int(smem_bytes);
+    info->n_accumulators = p.n_acc;
+  }
+  return HDK_B200_OK;
+}
+
+int launch_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
+                int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info) {
+  return launch_scan_impl(lw, ko, params, work_table, false, stream, info);
+}
+int launch_baseline_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
+                         cudaStream_t stream, hdk_b200_launch_info* info) {
+  return launch_scan_impl(lw, ko, params, nullptr, true, stream, info);
+}
+
+}  // namespace hb

@@ -1,0 +1,43 @@
+// hdk_b200/csrc/scan.cuh — launch geometry and argument block of the fused scan kernel.
+#pragma once
+#include "common.cuh"
+
+namespace hb {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = kConsumerThreads + 32;  // + one TMA producer warp
+constexpr int kStages = 4;
+constexpr uint32_t kMaxFragments = 4096;
+
+struct AccKinds {
+  uint8_t kind[kMaxAcc];
+};
+
+struct ScanArgs {
+  DPlan plan;
+  DLayout layout;                     // baseline hash updates the reference-encoded buffer in place
+  const int8_t* const* col_buffers;   // [num_fragments * n_cols]
+  const int64_t* num_rows;            // [num_fragments]
+  const int64_t* join_hash_tables;    // [n_joins]
+  const int8_t* const* inner_col_buffers;
+  int64_t* work_table;                // [n_acc * entry_count]            (perfect hash)
+  int64_t* const* groupby_buf;        // GROUPBY_BUF device array, [0] used  (baseline hash)
+  int32_t* error_codes;
+  uint32_t num_fragments;
+  uint32_t tile_rows;
+  uint32_t stage_bytes;
+  uint32_t off_tile_prefix, off_bins, off_stages;   // dynamic shared memory map
+  uint32_t acc_bin_off[kMaxAcc];                    // from off_bins
+  uint32_t col_region_off[HDK_B200_MAX_COLS];       // from a stage's base
+};
+
+int init_work_table(const Lowered& lw, int64_t* work_table, cudaStream_t stream);
+int launch_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
+                int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info);
+int launch_finalize(const Lowered& lw, const int64_t* work_table, int64_t* groups_buffer, int64_t* const* groups_buffer_indirect,
+                    cudaStream_t stream);
+int launch_baseline_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
+                         cudaStream_t stream, hdk_b200_launch_info* info);
+
+}  // namespace hb

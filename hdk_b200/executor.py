@@ -1,0 +1,433 @@
+"""Executor / RelAlgExecutor / ResultSet façade over the C ABI.
+
+Mirrors the call structure of the reference for the hot path only:
+  Executor.execute_work_unit      Executor::executeWorkUnit  (QE/Execute.cpp:1736-1798): build the memory
+                                  descriptor, fetch chunks to the device, launch, collect, reduce
+  QueryExecutionContext           QE/QueryExecutionContext.cpp:238-550 (launchGpuCode): kernel params,
+                                  group-by buffer, launch, error code, copy back
+  RelAlgExecutor.execute          QE/RelAlgExecutor.cpp:158-213 + the out-of-slots → bigger table retry
+                                  ladder (:1544-1566); python/pyhdk/_sql.pyx:169-213
+  ResultSet / ExecutionResult     omniscidb/ResultSet (iteration, Arrow conversion), python/pyhdk/_sql.pyx:80-83
+PyTorch is used only as the device allocator / stream provider and for torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import pyarrow as pa
+
+from . import _lib, abi, ir, planner, sql
+from .storage import ArrowStorage, Table
+
+
+class QueryError(RuntimeError):
+    """In-band query error (QE/Execute.h:1019-1031 error codes)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"query failed with error code {code}: {msg}")
+        self.code = code
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.HdkB200Error("no CUDA device visible: hdk_b200 has no CPU fallback")
+    return torch
+
+
+class DeviceContext:
+    """Per-GPU state: chunk cache (DataMgr GPU level stand-in), scratch, stream."""
+
+    def __init__(self, device: int = 0):
+        torch = _torch()
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.index = device
+        self.scratch = None
+        self._kp_cache = {}
+
+    def stream_ptr(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def upload(self, arr: np.ndarray):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1))
+        return t.to(self.device, non_blocking=False)
+
+    def chunk(self, frag, col: str):
+        """Executor::fetchChunks (QE/ExecutionKernel.cpp:205-228): chunk → device, cached ("hot")."""
+        d = frag.device_chunks.get(col)
+        if d is None:
+            d = self.upload(frag.chunks[col])
+            frag.device_chunks[col] = d
+        return d
+
+    def get_scratch(self, nbytes: int):
+        if self.scratch is None or self.scratch.numel() < nbytes:
+            self.scratch = self.torch.empty(max(nbytes, 1 << 20), dtype=self.torch.uint8, device=self.device)
+        return self.scratch
+
+
+@dataclass
+class JoinTable:
+    """PerfectJoinHashTable (JHT/PerfectJoinHashTable.h) over a device buffer."""
+    buffer: object           # torch uint8 tensor holding int32 entries
+    hash_type: str           # "OneToOne" | "OneToMany"
+    min_key: int
+    max_key: int
+    entry_count: int
+    inner_table: Table
+    inner_columns_dev: Dict[str, object]
+
+
+class ResultSet:
+    """A group-by buffer + its descriptor, iterable like omniscidb/ResultSet/ResultSet.h."""
+
+    def __init__(self, planned: planner.PlannedQuery, buffer: np.ndarray, dictionaries=None):
+        self.planned = planned
+        self.buffer = buffer
+        self.dictionaries = dictionaries or {}
+        self._cols = None
+
+    def _decode(self):
+        """ResultSet iteration on the host (ResultSetIteration.cpp:1264-1360): numpy restatement used for
+        small results; large results go through hdk_b200_compact_result on the device."""
+        if self._cols is not None:
+            return self._cols
+        pq, q, p = self.planned, self.planned.qmd, self.planned.plan
+        E = q.entry_count
+        buf = self.buffer
+        a8 = lambda x: (x + 7) & ~7  # noqa: E731
+        # layout
+        if q.output_columnar:
+            off = 0 if q.keyless else q.key_count * a8(8 * E)
+            slot_off = []
+            for s in range(q.slot_count):
+                slot_off.append(off)
+                off += a8(q.slot_padded[s] * E)
+            row_bytes = 0
+            key_bytes = 0
+        else:
+            key_bytes = 0 if q.keyless else a8(q.key_count * q.key_width)
+            off, slot_off = 0, []
+            for s in range(q.slot_count):
+                if q.slot_padded[s] == 8:
+                    off = a8(off)
+                slot_off.append(off)
+                off += q.slot_padded[s]
+            row_bytes = a8(key_bytes + off)
+
+        def read_slot(s, width=None):
+            w = width or q.slot_padded[s]
+            dt = np.int64 if w == 8 else np.int32
+            if q.output_columnar:
+                return np.frombuffer(buf, dtype=dt, count=E, offset=slot_off[s]).astype(np.int64) if w == q.slot_padded[s] \
+                    else np.frombuffer(buf, dtype=np.int64, count=E, offset=slot_off[s]).astype(np.int32).astype(np.int64)
+            rows = np.frombuffer(buf, dtype=np.uint8).reshape(E, row_bytes)
+            raw = rows[:, key_bytes + slot_off[s]: key_bytes + slot_off[s] + w]
+            return np.ascontiguousarray(raw).view(dt).reshape(E).astype(np.int64)
+
+        def read_key(k):
+            if q.output_columnar:
+                return np.frombuffer(buf, dtype=np.int64, count=E, offset=k * a8(8 * E)).copy()
+            rows = np.frombuffer(buf, dtype=np.uint8).reshape(E, row_bytes)
+            w = q.key_width
+            raw = np.ascontiguousarray(rows[:, k * w:(k + 1) * w])
+            return raw.view(np.int64 if w == 8 else np.int32).reshape(E).astype(np.int64)
+
+        # non-empty entries (ResultSetStorage::isEmptyEntry)
+        if q.keyless:
+            s = q.target_idx_for_key
+            init = q.init_vals[s]
+            if q.slot_padded[s] == 4:
+                init = int(np.int32(init & 0xFFFFFFFF if init >= 0 else init))
+            valid = read_slot(s) != init
+        else:
+            first = read_key(0)
+            valid = first != (abi.EMPTY_KEY_32 if (q.key_width == 4 and not q.output_columnar) else abi.EMPTY_KEY_64)
+        cols = []
+        for t, ti in enumerate(pq.infos):
+            tg = p.targets[t]
+            chosen = ti.compact_type
+            if ti.agg == abi.AGG_AVG:
+                ssum = read_slot(tg.slot, 4 if ti.float_argument_input else None)
+                cnt = read_slot(tg.slot + 1)
+                if ti.float_argument_input:
+                    dividend = ssum.astype(np.int32).view(np.float32).astype(np.float64)
+                elif ti.type.is_fp:
+                    dividend = ssum.view(np.float64)
+                else:
+                    dividend = ssum.astype(np.float64)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    v = dividend / cnt.astype(np.float64)
+                col = np.ma.array(v, mask=(cnt == 0))
+            else:
+                if tg.slot >= 0 and q.slot_padded[tg.slot]:
+                    f4 = ti.float_argument_input
+                    raw = read_slot(tg.slot, 4 if f4 else None)
+                else:
+                    f4 = False
+                    raw = read_key(ti.key_index)
+                is_fp = chosen.is_fp and ti.agg != abi.AGG_COUNT
+                if is_fp:
+                    v = raw.astype(np.int32).view(np.float32).astype(np.float64) if f4 else raw.view(np.float64)
+                    null = np.float64(np.float32(abi.FLT_MIN)) if chosen.width == 4 else abi.DBL_MIN
+                    col = np.ma.array(v, mask=(v == null))
+                else:
+                    w = chosen.width
+                    trunc = raw if w == 8 else raw.astype({1: np.int8, 2: np.int16, 4: np.int32}[w]).astype(np.int64)
+                    col = np.ma.array(raw, mask=(trunc == abi.int_null(w)))
+            cols.append(col[valid])
+        self._cols = cols
+        return cols
+
+    def row_count(self):
+        cols = self._decode()
+        return len(cols[0]) if cols else 0
+
+    def to_arrow(self) -> pa.Table:
+        """ArrowResultSetConverter::convertToArrowTable (omniscidb/ResultSet/ArrowResultSetConverter.cpp)."""
+        cols = self._decode()
+        arrays, names = [], []
+        unit = self.planned.unit
+        for t, (ti, col) in enumerate(zip(self.planned.infos, cols)):
+            mask = np.ma.getmaskarray(col)
+            data = np.ma.getdata(col)
+            name = unit.target_names[t]
+            typ = ti.type
+            if not ti.is_agg and typ.kind == "dict":
+                d = self.dictionaries.get(t)
+                arr = pa.array([None if m else d[int(v)] for v, m in zip(data, mask)], type=pa.string()) if d is not None \
+                    else pa.array(data.astype(np.int32), mask=mask)
+            elif data.dtype == np.float64:
+                if ti.agg in (abi.AGG_SUM, abi.AGG_MIN, abi.AGG_MAX) and typ.is_fp and typ.width == 4:
+                    arr = pa.array(data.astype(np.float32), mask=mask)
+                else:
+                    arr = pa.array(data, mask=mask)
+            else:
+                w = 8 if ti.is_agg and ti.agg in (abi.AGG_SUM,) else typ.width
+                if not ti.is_agg and typ.kind == "timestamp":
+                    u = {1: "s", 1000: "ms", 1000000: "us", 1000000000: "ns"}[typ.unit]
+                    arr = pa.array(data, mask=mask, type=pa.int64()).cast(pa.timestamp(u))
+                elif ti.agg == abi.AGG_COUNT:
+                    arr = pa.array(data.astype(np.int32 if typ.width == 4 else np.int64), mask=mask)
+                else:
+                    arr = pa.array(data.astype({1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[w]), mask=mask)
+            arrays.append(arr)
+            names.append(name)
+        tbl = pa.table(arrays, names=names)
+        if unit.order_by:
+            tbl = tbl.sort_by([(names[i], "descending" if d else "ascending") for i, d in unit.order_by])
+        if unit.limit is not None:
+            tbl = tbl.slice(0, unit.limit)
+        return tbl
+
+
+class ExecutionResult:
+    """python/pyhdk/_sql.pyx:62-100"""
+
+    def __init__(self, result_set: ResultSet, launch_info=None):
+        self.result_set = result_set
+        self.launch_info = launch_info
+
+    def to_arrow(self):
+        return self.result_set.to_arrow()
+
+    def df(self):
+        return self.to_arrow().to_pandas()
+
+    def row_count(self):
+        return self.result_set.row_count()
+
+
+class Executor:
+    """One executor per process / GPU (Executor::getExecutor, QE/Execute.cpp:403)."""
+
+    def __init__(self, storage: ArrowStorage, config: Optional[planner.Config] = None, device: int = 0):
+        self.storage = storage
+        self.config = config or planner.Config()
+        self.ctx = DeviceContext(device)
+        self.lib = _lib.lib()
+        self.join_tables: Dict[tuple, JoinTable] = {}
+        self.last_launch_info = None
+
+    # -- join hash tables ----------------------------------------------------------------
+    def build_join_table(self, inner: Table, key_col: str) -> JoinTable:
+        """HashJoin::getInstance → PerfectJoinHashTable::reify (JHT/PerfectJoinHashTable.cpp:90-383):
+        one-to-one first; a duplicate key (err = -1) rebuilds as one-to-many (NeedsOneToManyHash)."""
+        cache_key = (inner.name, key_col)
+        if cache_key in self.join_tables:
+            return self.join_tables[cache_key]
+        torch = self.ctx.torch
+        ci = inner.columns[key_col]
+        lo, hi, has_nulls = inner.col_stats(key_col)
+        if lo is None or ci.type.is_fp:
+            raise planner.UnsupportedPlan("join key without an integer range")
+        entries = hi - lo + 1
+        if entries > (1 << 31) // 4:   # TooManyHashEntries (PerfectJoinHashTable.cpp:139-151) → baseline join: not on this path
+            raise planner.UnsupportedPlan("join key range too large for a perfect hash table")
+        chunks = (abi.JoinChunk * len(inner.fragments))()
+        keep = []
+        row = 0
+        for i, f in enumerate(inner.fragments):
+            d = self.ctx.chunk(f, key_col)
+            keep.append(d)
+            chunks[i].col_buff = d.data_ptr()
+            chunks[i].num_elems = f.num_rows
+            chunks[i].row_id = row
+            row += f.num_rows
+        host_chunks = np.frombuffer(bytes(chunks), dtype=np.uint8)
+        dchunks = self.ctx.upload(host_chunks)
+        jc = abi.JoinColumn(dchunks.data_ptr(), len(host_chunks), len(inner.fragments), row, ci.phys_width)
+        ti = abi.JoinColumnTypeInfo(ci.phys_width, lo, hi, abi.int_null(ci.phys_width), 0, 0,
+                                    abi.SMALL_DATE if ci.type.date_in_days else abi.SIGNED)
+        st = self.ctx.stream_ptr()
+        buf = torch.empty(entries * 4, dtype=torch.uint8, device=self.ctx.device)
+        err = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
+        _lib.check(self.lib.hdk_b200_init_hash_join_buff_on_device(buf.data_ptr(), entries, -1, st), "init_hash_join_buff")
+        _lib.check(self.lib.hdk_b200_fill_hash_join_buff_on_device(buf.data_ptr(), -1, 0, err.data_ptr(), C.byref(jc),
+                                                                   C.byref(ti), 1, st), "fill_hash_join_buff")
+        hash_type = "OneToOne"
+        if int(err.item()) != 0:
+            buf = torch.empty((2 * entries + row) * 4, dtype=torch.uint8, device=self.ctx.device)
+            _lib.check(self.lib.hdk_b200_fill_one_to_many_hash_table_on_device(buf.data_ptr(), entries, -1, C.byref(jc),
+                                                                               C.byref(ti), 1, st), "fill_one_to_many")
+            hash_type = "OneToMany"
+        jt = JoinTable(buf, hash_type, lo, hi, entries, inner, {})
+        self.join_tables[cache_key] = jt
+        return jt
+
+    # -- one work unit ---------------------------------------------------------------------
+    def _col_stats(self, unit: ir.ExecutionUnit):
+        tables = [self.storage.get_table(unit.table)] + [self.storage.get_table(j.inner_table) for j in unit.joins]
+        return lambda tidx, col: tables[tidx].col_stats(col)
+
+    def plan(self, unit: ir.ExecutionUnit, max_groups_buffer_entry_count=None, output_columnar=None) -> planner.PlannedQuery:
+        outer = self.storage.get_table(unit.table)
+        pq = planner.build_query(unit, self._col_stats(unit), outer.num_rows, self.config,
+                                 max_groups_buffer_entry_count=max_groups_buffer_entry_count,
+                                 output_columnar=output_columnar)
+        return pq
+
+    def _kernel_params(self, pq: planner.PlannedQuery, outer: Table, fragments, joins: List[JoinTable]):
+        torch = self.ctx.torch
+        dev = self.ctx.device
+        ncols = len(pq.columns)
+        ptrs = np.zeros(max(len(fragments) * ncols, 1), dtype=np.uint64)
+        keep = []
+        for fi, f in enumerate(fragments):
+            for ci, cname in enumerate(pq.columns):
+                d = self.ctx.chunk(f, cname)
+                keep.append(d)
+                ptrs[fi * ncols + ci] = d.data_ptr()
+        num_rows = np.array([f.num_rows for f in fragments] or [0], dtype=np.int64)
+        d_ptrs = torch.from_numpy(ptrs.view(np.int64)).to(dev)
+        d_rows = torch.from_numpy(num_rows).to(dev)
+        jt_addr = np.zeros(abi.MAX_JOINS, dtype=np.int64)
+        inner = np.zeros(abi.MAX_JOINS * abi.MAX_COLS, dtype=np.uint64)
+        for j, jt in enumerate(joins):
+            jt_addr[j] = jt.buffer.data_ptr()
+            for c, cname in enumerate(pq.inner_columns[j]):
+                if len(jt.inner_table.fragments) != 1:
+                    raise planner.UnsupportedPlan("inner table columns must be a single fragment (ColumnFetcher linearises them)")
+                d = self.ctx.chunk(jt.inner_table.fragments[0], cname)
+                keep.append(d)
+                inner[j * abi.MAX_COLS + c] = d.data_ptr()
+        d_jt = torch.from_numpy(jt_addr).to(dev)
+        d_inner = torch.from_numpy(inner.view(np.int64)).to(dev)
+        kp = abi.KernelParams()
+        kp.col_buffers = d_ptrs.data_ptr()
+        kp.num_fragments = len(fragments)
+        kp.num_rows = d_rows.data_ptr()
+        kp.num_tables = 1 + len(joins)
+        kp.join_hash_tables = d_jt.data_ptr()
+        kp.inner_col_buffers = d_inner.data_ptr()
+        keep += [d_ptrs, d_rows, d_jt, d_inner]
+        return kp, keep
+
+    def prepare(self, pq: planner.PlannedQuery, fragments=None):
+        """Everything launchGpuCode sets up before the launch: join tables, kernel params, buffers."""
+        torch = self.ctx.torch
+        unit = pq.unit
+        outer = self.storage.get_table(unit.table)
+        frags = outer.fragments if fragments is None else fragments
+        joins = []
+        for j, js in enumerate(unit.joins):
+            jt = self.build_join_table(self.storage.get_table(js.inner_table), js.inner_key_column)
+            pj = pq.plan.joins[j]
+            pj.one_to_many = int(jt.hash_type == "OneToMany")
+            pj.min_key, pj.max_key, pj.entry_count = jt.min_key, jt.max_key, jt.entry_count
+            joins.append(jt)
+        kp, keep = self._kernel_params(pq, outer, frags, joins)
+        nbytes = self.lib.hdk_b200_buffer_size_bytes(C.byref(pq.qmd))
+        out = torch.empty(nbytes, dtype=torch.uint8, device=self.ctx.device)
+        bufptr = torch.tensor([out.data_ptr()], dtype=torch.int64, device=self.ctx.device)
+        err = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
+        kp.groupby_buf = bufptr.data_ptr()
+        kp.error_codes = err.data_ptr()
+        scratch_bytes = C.c_size_t(0)
+        _lib.check(self.lib.hdk_b200_plan_check(C.byref(pq.plan), C.byref(pq.qmd), C.byref(scratch_bytes)), "plan_check")
+        scratch = self.ctx.get_scratch(scratch_bytes.value)
+        keep += [bufptr, scratch]
+        return dict(kp=kp, keep=keep, out=out, err=err, scratch=scratch, scratch_bytes=scratch_bytes.value)
+
+    def launch(self, pq: planner.PlannedQuery, prep, ko: Optional[abi.KernelOptions] = None):
+        """init buffer + fused kernel (asynchronous on the current stream)."""
+        st = self.ctx.stream_ptr()
+        info = abi.LaunchInfo()
+        if pq.qmd.hash_type == abi.BASELINE_HASH:
+            _lib.check(self.lib.hdk_b200_init_group_by_buffer(C.byref(pq.qmd), prep["out"].data_ptr(), st), "init_group_by_buffer")
+        prep["err"].zero_()
+        _lib.check(self.lib.hdk_b200_launch(C.byref(pq.plan), C.byref(pq.qmd), C.byref(ko) if ko is not None else None,
+                                            C.byref(prep["kp"]), prep["scratch"].data_ptr(), prep["scratch_bytes"], st,
+                                            C.byref(info)), "launch")
+        self.last_launch_info = info
+        return info
+
+    def execute_work_unit(self, unit: ir.ExecutionUnit, output_columnar=None, ko=None) -> ResultSet:
+        """Executor::executeWorkUnit with the out-of-slots retry of RelAlgExecutor::executeWorkUnit
+        (QE/RelAlgExecutor.cpp:1544-1566: on ERR_OUT_OF_SLOTS re-run with 2 × the cardinality estimate)."""
+        guess = None
+        outer = self.storage.get_table(unit.table)
+        for attempt in range(8):
+            pq = self.plan(unit, guess, output_columnar)
+            prep = self.prepare(pq)
+            info = self.launch(pq, prep, ko)
+            code = int(prep["err"].item())   # blocking copy of the error code = the reference's only sync
+            if code < 0 and pq.qmd.hash_type == abi.BASELINE_HASH:
+                cur = pq.qmd.entry_count
+                guess = min(max(cur * 4, 2 * min(outer.num_rows, cur * 8)), max(2 * outer.num_rows, 16))
+                if guess <= cur:
+                    raise QueryError(code, "ran out of slots in the group-by buffer")
+                continue
+            if code != 0:
+                raise QueryError(code, {1: "division by zero", 7: "overflow or underflow",
+                                        1003: "group key outside the range of the perfect-hash layout"}.get(code, "runtime error"))
+            host = prep["out"].cpu().numpy()
+            dicts = {}
+            tables = [outer] + [self.storage.get_table(j.inner_table) for j in unit.joins]
+            for t, e in enumerate(unit.target_exprs):
+                if isinstance(e, ir.ColumnRef) and e.type.kind == "dict":
+                    dicts[t] = tables[e.table].columns[e.column].dictionary
+            rs = ResultSet(pq, host, dicts)
+            rs.launch_info = info
+            return rs
+        raise QueryError(-abi.ERR_OUT_OF_SLOTS, "ran out of slots after retries")
+
+
+class RelAlgExecutor:
+    """python/pyhdk/_sql.pyx:169-213: RelAlgExecutor(executor, schema/storage, query).execute()."""
+
+    def __init__(self, executor: Executor, storage: ArrowStorage, query):
+        self.executor = executor
+        self.storage = storage
+        self.unit = query if isinstance(query, ir.ExecutionUnit) else sql.parse(query, storage.tables,
+                                                                                 executor.config.bigint_count)
+
+    def execute(self, device_type: str = "GPU", **kwargs) -> ExecutionResult:
+        if device_type != "GPU":
+            raise _lib.HdkB200Error("hdk_b200 executes on the GPU only (no CPU fallback)")
+        rs = self.executor.execute_work_unit(self.unit, output_columnar=kwargs.get("enable_columnar_output"))
+        return ExecutionResult(rs, getattr(rs, "launch_info", None))

@@ -65,6 +65,7 @@ class _Parser:
         self.i = 0
         self.tables = tables           # name -> storage.Table
         self.scopes: List[Tuple[str, str, int]] = []   # (alias, table name, table index)
+        self.aliases: Dict[str, ir.Expr] = {}
 
     # -- token helpers
     def peek(self, k=0):
@@ -85,7 +86,9 @@ class _Parser:
         return False
 
     # -- name resolution
-    def resolve(self, qual: Optional[str], col: str) -> ir.ColumnRef:
+    def resolve(self, qual: Optional[str], col: str) -> ir.Expr:
+        if qual is None and col.lower() in self.aliases:
+            return self.aliases[col.lower()]      # select-list alias used in GROUP BY / ORDER BY
         hits = []
         for alias, tname, tidx in self.scopes:
             if qual is not None and qual.lower() not in (alias.lower(), tname.lower()):
@@ -287,6 +290,9 @@ class _Parser:
         if self.peek() != ("kw", "from"):
             raise UnsupportedPlan(f"SQL: unexpected {self.peek()[1]!r} in select list")
         self.i = after_from
+        for e, n in zip(targets, names):
+            if n is not None and not isinstance(e, ir.AggExpr):
+                self.aliases[n.lower()] = e
         quals = []
         if self.accept("kw", "where"):
             quals = _split_conjuncts(self.expr())

@@ -28,6 +28,12 @@ extern "C" {
 
 #define HDK_B200_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define HDK_B200_API __attribute__((visibility("default")))
+#else
+#define HDK_B200_API
+#endif
+
 /* ---- limits of the plan POD ------------------------------------------------ */
 #define HDK_B200_MAX_EXPRS 48
 #define HDK_B200_MAX_KEYS 8
@@ -267,21 +273,21 @@ enum hdk_b200_strategy {
 
 /* Validate a plan/descriptor pair and report the scratch (device) bytes the
  * launch needs.  Host-only, no CUDA calls. */
-int hdk_b200_plan_check(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, size_t* scratch_bytes);
+HDK_B200_API int hdk_b200_plan_check(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, size_t* scratch_bytes);
 
 /* Bytes of the group-by buffer for this descriptor:
  * QueryMemoryDescriptor::getBufferSizeBytes (QueryMemoryDescriptor.cpp:457-481). */
-size_t hdk_b200_buffer_size_bytes(const hdk_b200_qmd* qmd);
+HDK_B200_API size_t hdk_b200_buffer_size_bytes(const hdk_b200_qmd* qmd);
 
 /* Fill a group-by buffer with EMPTY_KEY / init values for this descriptor.
  * Replaces QueryMemoryInitializer::initRowGroups / initColumnarGroups
  * (QE/QueryMemoryInitializer.cpp:502-687) and init_group_by_buffer_gpu /
  * init_columnar_group_by_buffer_gpu (QE/GpuInitGroups.cu:120-188). */
-int hdk_b200_init_group_by_buffer(const hdk_b200_qmd* qmd, int64_t* groups_buffer, void* stream);
+HDK_B200_API int hdk_b200_init_group_by_buffer(const hdk_b200_qmd* qmd, int64_t* groups_buffer, void* stream);
 
 /* 1:1 mirrors of the reference's host-callable initialisers, same argument meaning
  * (QE/GpuInitGroups.h:29-52); block/grid of 0 = library picks. */
-int hdk_b200_init_group_by_buffer_on_device(int64_t* groups_buffer,
+HDK_B200_API int hdk_b200_init_group_by_buffer_on_device(int64_t* groups_buffer,
                                             const int64_t* init_vals, /* DEVICE */
                                             uint32_t groups_buffer_entry_count,
                                             uint32_t key_count,
@@ -292,7 +298,7 @@ int hdk_b200_init_group_by_buffer_on_device(int64_t* groups_buffer,
                                             size_t block_size_x,
                                             size_t grid_size_x,
                                             void* stream);
-int hdk_b200_init_columnar_group_by_buffer_on_device(int64_t* groups_buffer,
+HDK_B200_API int hdk_b200_init_columnar_group_by_buffer_on_device(int64_t* groups_buffer,
                                                      const int64_t* init_vals, /* DEVICE */
                                                      uint32_t groups_buffer_entry_count,
                                                      uint32_t key_count,
@@ -310,7 +316,7 @@ int hdk_b200_init_columnar_group_by_buffer_on_device(int64_t* groups_buffer,
  * `scratch` is a device scratch area of at least the size hdk_b200_plan_check
  * reported (may be NULL when that is 0).  The result buffer is byte-compatible
  * with `qmd` so the reference's ResultSet can iterate it. */
-int hdk_b200_launch(const hdk_b200_plan* plan,
+HDK_B200_API int hdk_b200_launch(const hdk_b200_plan* plan,
                     const hdk_b200_qmd* qmd,
                     const hdk_b200_kernel_options* ko, /* may be NULL */
                     const hdk_b200_kernel_params* params,
@@ -335,18 +341,18 @@ typedef struct hdk_b200_work_table_layout {
   uint64_t max_cells;   /* last max_cells: merge with MAX */
 } hdk_b200_work_table_layout;
 
-int hdk_b200_work_table_layout_get(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
+HDK_B200_API int hdk_b200_work_table_layout_get(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
                                    hdk_b200_work_table_layout* out);
-int hdk_b200_init_work_table(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
+HDK_B200_API int hdk_b200_init_work_table(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
                              int64_t* work_table, void* stream);
-int hdk_b200_launch_partial(const hdk_b200_plan* plan,
+HDK_B200_API int hdk_b200_launch_partial(const hdk_b200_plan* plan,
                             const hdk_b200_qmd* qmd,
                             const hdk_b200_kernel_options* ko,
                             const hdk_b200_kernel_params* params, /* groupby_buf unused */
                             int64_t* work_table,
                             void* stream,
                             hdk_b200_launch_info* info);
-int hdk_b200_finalize(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
+HDK_B200_API int hdk_b200_finalize(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
                       const int64_t* work_table, int64_t* groups_buffer, void* stream);
 
 /* ResultSetReduction::reduce (QE/ResultSetReduction.cpp:174-330): merge `that`
@@ -354,7 +360,7 @@ int hdk_b200_finalize(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
  * smaller for baseline hash, :196-201).  Perfect hash: slot-wise reduceOneSlot
  * (:1234-1320).  Baseline: re-insert every non-empty entry (:696-760); running out
  * of slots sets *error_codes to a negative code (ReductionRanOutOfSlots). */
-int hdk_b200_reduce(const hdk_b200_plan* plan,
+HDK_B200_API int hdk_b200_reduce(const hdk_b200_plan* plan,
                     const hdk_b200_qmd* qmd,
                     int64_t* this_buffer,
                     const int64_t* that_buffer,
@@ -395,20 +401,20 @@ typedef struct hdk_b200_join_column_type_info {
 } hdk_b200_join_column_type_info;
 
 /* init_hash_join_buff_on_device (HashJoinRuntime.h:72-74) */
-int hdk_b200_init_hash_join_buff_on_device(int32_t* buff, int64_t entry_count,
+HDK_B200_API int hdk_b200_init_hash_join_buff_on_device(int32_t* buff, int64_t entry_count,
                                            int32_t invalid_slot_val, void* stream);
 /* fill_hash_join_buff_on_device[_bucketized] (HashJoinRuntime.h:163-183; body
  * HashJoinRuntime.cpp:198-296).  `dev_err_buff`: device int, set to -1 on a
  * duplicate key (→ NeedsOneToManyHash, JHT/Builders/PerfectHashTableBuilder.h:96-141).
  * bucket_normalization = 1 for the non-bucketized form. */
-int hdk_b200_fill_hash_join_buff_on_device(int32_t* buff, int32_t invalid_slot_val, int for_semi_join,
+HDK_B200_API int hdk_b200_fill_hash_join_buff_on_device(int32_t* buff, int32_t invalid_slot_val, int for_semi_join,
                                            int* dev_err_buff,
                                            const hdk_b200_join_column* join_column,
                                            const hdk_b200_join_column_type_info* type_info,
                                            int64_t bucket_normalization, void* stream);
 /* fill_one_to_many_hash_table_on_device[_bucketized] (HashJoinRuntime.h:236-254;
  * HashJoinRuntimeGpu.cu:134-236): buff = offsets[E] | counts[E] | payload[num_elems]. */
-int hdk_b200_fill_one_to_many_hash_table_on_device(int32_t* buff, int64_t hash_entry_count,
+HDK_B200_API int hdk_b200_fill_one_to_many_hash_table_on_device(int32_t* buff, int64_t hash_entry_count,
                                                    int32_t invalid_slot_val,
                                                    const hdk_b200_join_column* join_column,
                                                    const hdk_b200_join_column_type_info* type_info,
@@ -417,10 +423,10 @@ int hdk_b200_fill_one_to_many_hash_table_on_device(int32_t* buff, int64_t hash_e
  * body HashJoinRuntime.cpp:298-576): composite-key open addressing with MurmurHash1,
  * entry = key_component_count keys (+ one payload slot when with_val_slot).
  * key_width = 4 or 8 selects the _32 / _64 form. */
-int hdk_b200_init_baseline_hash_join_buff_on_device(int8_t* hash_join_buff, int64_t entry_count,
+HDK_B200_API int hdk_b200_init_baseline_hash_join_buff_on_device(int8_t* hash_join_buff, int64_t entry_count,
                                                     size_t key_component_count, int with_val_slot,
                                                     int32_t invalid_slot_val, int key_width, void* stream);
-int hdk_b200_fill_baseline_hash_join_buff_on_device(int8_t* hash_buff, int64_t entry_count,
+HDK_B200_API int hdk_b200_fill_baseline_hash_join_buff_on_device(int8_t* hash_buff, int64_t entry_count,
                                                     int32_t invalid_slot_val, int for_semi_join,
                                                     size_t key_component_count, int with_val_slot,
                                                     int* dev_err_buff,
@@ -429,7 +435,7 @@ int hdk_b200_fill_baseline_hash_join_buff_on_device(int8_t* hash_buff, int64_t e
                                                     int key_width, void* stream);
 /* fill_one_to_many_baseline_hash_table_on_device_{32,64} (HashJoinRuntime.h:256-300):
  * buff = offsets[E] | counts[E] | payload[num_elems] over the composite-key dictionary. */
-int hdk_b200_fill_one_to_many_baseline_hash_table_on_device(int32_t* buff, const int8_t* composite_key_dict,
+HDK_B200_API int hdk_b200_fill_one_to_many_baseline_hash_table_on_device(int32_t* buff, const int8_t* composite_key_dict,
                                                             int64_t hash_entry_count, int32_t invalid_slot_val,
                                                             size_t key_component_count,
                                                             const hdk_b200_join_column* join_columns,
@@ -439,9 +445,9 @@ int hdk_b200_fill_one_to_many_baseline_hash_table_on_device(int32_t* buff, const
  * that materialise join results): hash_join_idx (QE/GroupByRuntime.cpp:298-308) and
  * baseline_hash_join_idx_{32,64} (JHT/Runtime/JoinHashTableQueryRuntime.cpp:43-98).
  * out[i] = matching slot value / entry index or -1. */
-int hdk_b200_probe_hash_join_on_device(const int32_t* buff, const int64_t* keys, int64_t n,
+HDK_B200_API int hdk_b200_probe_hash_join_on_device(const int32_t* buff, const int64_t* keys, int64_t n,
                                        int64_t min_key, int64_t max_key, int64_t* out, void* stream);
-int hdk_b200_probe_baseline_hash_join_on_device(const int8_t* hash_buff, const int8_t* keys /* n × key_component_count × key_width */,
+HDK_B200_API int hdk_b200_probe_baseline_hash_join_on_device(const int8_t* hash_buff, const int8_t* keys /* n × key_component_count × key_width */,
                                                 int64_t n, size_t key_component_count, int key_width,
                                                 int64_t entry_count, int with_val_slot, int64_t* out, void* stream);
 
@@ -457,9 +463,9 @@ int hdk_b200_probe_baseline_hash_join_on_device(const int8_t* hash_buff, const i
  * The NCCL all-to-all between the passes' outputs is the caller's
  * (torch.distributed) job.
  * ==========================================================================*/
-int hdk_b200_shuffle_count(const hdk_b200_plan* plan, const hdk_b200_kernel_params* params,
+HDK_B200_API int hdk_b200_shuffle_count(const hdk_b200_plan* plan, const hdk_b200_kernel_params* params,
                            uint32_t n_partitions, uint64_t* counts /* DEVICE, zeroed by callee */, void* stream);
-int hdk_b200_shuffle_scatter(const hdk_b200_plan* plan, const hdk_b200_kernel_params* params,
+HDK_B200_API int hdk_b200_shuffle_scatter(const hdk_b200_plan* plan, const hdk_b200_kernel_params* params,
                              uint32_t n_partitions,
                              const uint64_t* offsets /* DEVICE [n_partitions] exclusive prefix */,
                              uint64_t* cursors /* DEVICE [n_partitions], zeroed by callee */,
@@ -473,7 +479,7 @@ int hdk_b200_shuffle_scatter(const hdk_b200_plan* plan, const hdk_b200_kernel_pa
  * pair_to_double (ResultSetBufferAccessors.h:168-195).  `row_count` is a device
  * uint64 the kernel increments.  Columns are int64 or double per target type.
  * ==========================================================================*/
-int hdk_b200_compact_result(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
+HDK_B200_API int hdk_b200_compact_result(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
                             const int64_t* groups_buffer,
                             int64_t* const* out_cols /* DEVICE array [n_targets] of int64[entry_count] */,
                             uint64_t* row_count /* DEVICE */, void* stream);
@@ -486,7 +492,7 @@ int hdk_b200_compact_result(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
  * hdk_b200_buffer_size_bytes(qmd) bytes.  Synchronous.  Returns the aggregate
  * in-band error code (>0 / <0) or 0, or HDK_B200_E_* (≤ -1000 offset) on host errors.
  * ==========================================================================*/
-int hdk_b200_query_host(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
+HDK_B200_API int hdk_b200_query_host(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
                         const int8_t* const* col_buffers, const int64_t* num_rows,
                         uint64_t num_fragments,
                         const int64_t* join_hash_tables_host /* HOST addresses of HOST int32 tables, [n_joins] or NULL */,
@@ -496,11 +502,11 @@ int hdk_b200_query_host(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
                         int8_t* out_buffer, int device, hdk_b200_launch_info* info);
 
 /* ---- misc ------------------------------------------------------------------ */
-const char* hdk_b200_last_error(void);
-int hdk_b200_abi_version(void);
-int hdk_b200_device_count(void);
+HDK_B200_API const char* hdk_b200_last_error(void);
+HDK_B200_API int hdk_b200_abi_version(void);
+HDK_B200_API int hdk_b200_device_count(void);
 /* number of kernels this library has launched in this process (bench "gpu_launches") */
-uint64_t hdk_b200_launch_count(void);
+HDK_B200_API uint64_t hdk_b200_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,494 @@
+"""Parity tests proper: the sm_100a CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bit-exact for keys, COUNT, MIN, MAX and integer SUM; 1e-9 relative for fp64 SUM/AVG
+(north_star); fp32 aggregates 1e-5 (accumulated in double on the GPU, in float by the reference)."""
+import ctypes as C
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from hdk_b200 import abi, planner
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from hdk_b200 import _lib
+    return _lib.lib()
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+def gen_tables(n=50000, seed=20240917):
+    rng = np.random.default_rng(seed)
+    i = np.arange(n)
+    t = pa.table({
+        "k": rng.integers(0, 1000, n).astype(np.int32),
+        "k_null": pa.array(rng.integers(-20, 20, n).astype(np.int32), mask=rng.random(n) < 0.03),
+        "s": rng.integers(0, 10, n).astype(np.int16),
+        "b": rng.integers(-3, 3, n).astype(np.int8),
+        "v": pa.array(rng.integers(-2**40, 2**40, n), mask=rng.random(n) < 0.01),
+        "w": pa.array(rng.integers(-1000, 1000, n).astype(np.int32), mask=rng.random(n) < 0.4),
+        "f": rng.uniform(-1e6, 1e6, n),
+        "fn": pa.array(rng.normal(0, 1e3, n), mask=rng.random(n) < 0.1),
+        "g": pa.array(rng.normal(0, 10, n).astype(np.float32), mask=rng.random(n) < 0.05),
+        "ts": pa.array((rng.integers(1230768000, 1467331200, n) * 1000).astype("datetime64[ms]")),
+        "dt": pa.array(rng.integers(8000, 11000, n).astype(np.int32), type=pa.int32()).cast(pa.date32()),
+        "d": np.minimum(rng.exponential(2.9, n), 200.0),
+        "big": rng.integers(-2**62, 2**62, n),
+        "mid": (i * 7919 % 30011).astype(np.int64) * 1000003,
+        "fk": rng.integers(-5, 1010, n).astype(np.int32),
+    })
+    m = 1000
+    pk = rng.permutation(m).astype(np.int32)
+    dim = pa.table({"pk": pk, "attr": (pk % 37).astype(np.int32), "weight": rng.uniform(0, 1, m)})
+    dim_many = pa.table({"pk": rng.integers(0, 300, m).astype(np.int32), "attr": rng.integers(0, 11, m).astype(np.int32)})
+    return {"t": t, "dim": dim, "dim_many": dim_many}
+
+
+QUERIES = [
+    # (sql, n_keys, planner kwargs)
+    ("SELECT k, COUNT(*), SUM(v), MIN(v), MAX(v) FROM t GROUP BY k", 1, {}),                     # config 1 (int64)
+    ("SELECT k, COUNT(*), SUM(f), MIN(f), MAX(f) FROM t GROUP BY k", 1, {}),                     # config 1 (fp64)
+    ("SELECT s, COUNT(*) FROM t GROUP BY s", 1, {}),                                            # taxi Q1 shape, 4-byte slots
+    ("SELECT s, AVG(f) FROM t GROUP BY s", 1, {}),                                              # taxi Q2
+    ("SELECT s, EXTRACT(YEAR FROM ts) AS y, COUNT(*) FROM t GROUP BY s, y", 2, {}),             # taxi Q3
+    ("SELECT s, EXTRACT(YEAR FROM ts) AS y, CAST(d AS INT) AS dist, COUNT(*) FROM t GROUP BY s, y, dist", 3, {}),  # taxi Q4
+    ("SELECT b, s, SUM(d), SUM(f), SUM(f * (1 - d / 200)), SUM(f * (1 - d / 200) * (1 + d / 100)), AVG(d), AVG(f), AVG(fn), COUNT(*) "
+     "FROM t WHERE dt <= DATE '1998-09-02' GROUP BY b, s", 2, {}),                                # TPC-H Q1 shape
+    ("SELECT k_null, COUNT(*), COUNT(w), SUM(w), MIN(w), MAX(w), AVG(w), MIN(fn), MAX(fn), SUM(fn) FROM t GROUP BY k_null", 1, {}),
+    ("SELECT s, SUM(g), MIN(g), MAX(g), AVG(g), COUNT(g) FROM t GROUP BY s", 1, {}),            # fp32 aggregates
+    ("SELECT k, SUM(w), COUNT(*) FROM t WHERE f > 0 AND (s < 5 OR w IS NULL) GROUP BY k", 1, {}),
+    ("SELECT k, COUNT(*), SUM(v) FROM t GROUP BY k", 1, dict(output_columnar=True)),
+    ("SELECT k_null, s, MIN(v), MAX(fn), AVG(w) FROM t GROUP BY k_null, s", 2, dict(output_columnar=True)),
+    ("SELECT big, COUNT(*), SUM(w), MIN(fn), MAX(f), AVG(v) FROM t GROUP BY big", 1, dict(max_groups_buffer_entry_count=131072)),
+    ("SELECT mid, s, COUNT(*), SUM(v), SUM(f) FROM t GROUP BY mid, s", 2, dict(max_groups_buffer_entry_count=262144)),  # config 4 shape
+    ("SELECT k, s, COUNT(*), MAX(w) FROM t GROUP BY k, s", 2, dict(cfg=planner.Config(baseline_threshold=100), max_groups_buffer_entry_count=40000)),  # 4-byte baseline keys
+    ("SELECT big, SUM(f), COUNT(w), MIN(v) FROM t GROUP BY big", 1, dict(max_groups_buffer_entry_count=131072, output_columnar=True)),
+    ("SELECT dim.attr, SUM(t.f), COUNT(*) FROM t JOIN dim ON t.fk = dim.pk GROUP BY dim.attr", 1, {}),                  # config 5 shape
+    ("SELECT dim.attr, t.s, SUM(t.f * dim.weight), MIN(t.v) FROM t JOIN dim ON t.fk = dim.pk WHERE dim.weight > 0.25 GROUP BY dim.attr, t.s", 2, {}),
+]
+
+
+@pytest.fixture(scope="module")
+def env(oracle_mod):
+    tables = gen_tables()
+    st = util.make_storage(tables, fragment_size={"t": 7001, "dim": 100000, "dim_many": 100000})
+    return tables, st
+
+
+def float_tol(pq):
+    return 1e-5 if any(ti.float_argument_input for ti in pq.infos) else 1e-9
+
+
+def check_against_oracle(oracle_mod, st, pq, gpu_buf, n_keys):
+    obuf, oerr = util.run_oracle(oracle_mod, st, pq, n_threads=4)
+    assert oerr == 0
+    exp = util.sort_rows(util.result_columns(oracle_mod, pq, obuf), n_keys)
+    got = util.sort_rows(util.result_columns(oracle_mod, pq, gpu_buf), n_keys)
+    util.assert_rows_equal(got, exp, rel=float_tol(pq))
+    has_fp_sum = any(ti.agg in (abi.AGG_SUM, abi.AGG_AVG) and ti.arg_type is not None and ti.arg_type.is_fp for ti in pq.infos)
+    if pq.qmd.hash_type == abi.PERFECT_HASH and not has_fp_sum:
+        assert np.array_equal(gpu_buf, obuf), "perfect-hash buffers without fp sums must be byte-identical"
+    return exp
+
+
+@pytest.mark.parametrize("text,nk,kw", QUERIES)
+def test_query_host_matches_oracle(oracle_mod, L, env, text, nk, kw):
+    """The reference-facing call with HOST buffers (H2D, init, launch, D2H inside the call)."""
+    tables, st = env
+    pq = util.plan_sql(st, text, **kw)
+    frs, jts, ics = util.oracle_inputs(oracle_mod, st, pq)
+    out = np.zeros(L.hdk_b200_buffer_size_bytes(C.byref(pq.qmd)), dtype=np.uint8)
+    jt_addr = np.array([t.ctypes.data for t in jts] + [0] * (abi.MAX_JOINS - len(jts)), dtype=np.int64)
+    jt_bytes = np.array([t.nbytes for t in jts] + [0] * (abi.MAX_JOINS - len(jts)), dtype=np.uint64)
+    inner_ptr = np.zeros(abi.MAX_JOINS * abi.MAX_COLS, dtype=np.uint64)
+    inner_bytes = np.zeros(abi.MAX_JOINS * abi.MAX_COLS, dtype=np.uint64)
+    for j, cols in enumerate(ics):
+        for c, a in enumerate(cols):
+            inner_ptr[j * abi.MAX_COLS + c] = a.ctypes.data
+            inner_bytes[j * abi.MAX_COLS + c] = a.nbytes
+    info = abi.LaunchInfo()
+    rc = L.hdk_b200_query_host(C.byref(pq.plan), C.byref(pq.qmd), frs.ptrs.ctypes.data, frs.num_rows.ctypes.data, frs.n_frag,
+                               jt_addr.ctypes.data, jt_bytes.ctypes.data, inner_ptr.ctypes.data, inner_bytes.ctypes.data,
+                               out.ctypes.data, 0, C.byref(info))
+    assert rc == 0, L.hdk_b200_last_error()
+    assert info.n_launches >= 1
+    check_against_oracle(oracle_mod, st, pq, out, nk)
+
+
+@pytest.mark.parametrize("strategy", [0xB200F001, 0xB200F002, 0xB200F003])
+@pytest.mark.parametrize("text,nk", [(QUERIES[2][0], 1), (QUERIES[3][0], 1), (QUERIES[4][0], 2), (QUERIES[7][0], 1), (QUERIES[8][0], 1)])
+def test_every_accumulation_strategy(oracle_mod, env, torch, strategy, text, nk):
+    """THREAD_PRIVATE / CTA_SHARED / GLOBAL must agree with the oracle on the same plan."""
+    from hdk_b200.executor import Executor
+    tables, st = env
+    ex = Executor(st)
+    from hdk_b200 import sql
+    unit = sql.parse(text, st.tables)
+    pq = ex.plan(unit)
+    prep = ex.prepare(pq)
+    ko = abi.KernelOptions()
+    ko.sharedMemBytes = strategy
+    from hdk_b200._lib import HdkB200Error
+    try:
+        info = ex.launch(pq, prep, ko)
+    except HdkB200Error as e:
+        if "does not fit" in str(e):
+            pytest.skip("forced strategy does not fit in shared memory for this plan")
+        raise
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    assert info.strategy == {0xB200F001: 0, 0xB200F002: 1, 0xB200F003: 2}[strategy]
+    check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+
+
+def test_executor_sql_end_to_end_vs_sqlite(env, torch):
+    """hdk.sql() → Arrow, against SQLite like the reference's `c()` comparator."""
+    import hdk_b200.hdk as hdkmod
+    tables, _ = env
+    h = hdkmod.init()
+    h.import_arrow(tables["t"].select(["k", "s", "v", "w", "f"]), "t", fragment_size=9000)
+    for text, nk in [("SELECT s, COUNT(*) AS c, SUM(w) AS sw, AVG(f) AS af FROM t GROUP BY s ORDER BY s", 1),
+                     ("SELECT k, MIN(v) AS mn, MAX(v) AS mx FROM t WHERE w > 10 GROUP BY k ORDER BY k", 1)]:
+        res = h.sql(text).to_arrow()
+        got = [tuple(r.values()) for r in res.to_pylist()]
+        exp = util.sqlite_rows({"t": tables["t"].select(["k", "s", "v", "w", "f"])}, text, nk)
+        util.assert_rows_equal(got, exp)
+
+
+def test_builder_api_pyhdk_vectors(torch):
+    """python/tests/test_pyhdk_api.py:457-497 through the pyhdk-shaped builder on the GPU."""
+    import hdk_b200.hdk as hdkmod
+    h = hdkmod.init()
+    ht = h.import_pydict({"a": [1, 2, 1, 2, 1, 2, 1, 2, 1, 2], "b": [1, 1, 1, 1, 1, 2, 2, 2, 2, 2], "c": list(range(1, 11))})
+    r = ht.agg(["a", "b"], c_sum="sum(c)", c_min="min(c)", count="count").sort("a", "b").run().to_arrow().to_pydict()
+    assert r == {"a": [1, 1, 2, 2], "b": [1, 2, 1, 2], "c_sum": [9, 16, 6, 24], "c_min": [1, 7, 2, 6], "count": [3, 2, 2, 3]}
+    r = ht.agg("a", bc="count(b)", cmx="max(c)", cmn="min(c)", cv="avg(c)").sort("a").run().to_arrow().to_pydict()
+    assert r == {"a": [1, 2], "bc": [5, 5], "cmx": [9, 10], "cmn": [1, 2], "cv": [5.0, 6.0]}
+    ht1 = h.import_pydict({"a": [1, 2, 3, 4, 5], "b": [5, 4, 3, 2, 1], "x": [1.1, 2.2, 3.3, 4.4, 5.5]}, "ht1")
+    ht2 = h.import_pydict({"a": [1, 2, 3, 4, 5], "bb": [1, 2, 3, 4, 5], "y": [5.5, 4.4, 3.3, 2.2, 1.1]}, "ht2")
+    r = ht1.join(ht2, "a").agg("b", sy="sum(y)", n="count").sort("b").run().to_arrow().to_pydict()
+    assert r["b"] == [1, 2, 3, 4, 5] and r["n"] == [1] * 5
+    assert np.allclose(r["sy"], [1.1, 2.2, 3.3, 4.4, 5.5])
+
+
+# ------------------------------------------------------------------------------- edge cases ---
+def test_empty_ragged_and_unaligned_inputs(oracle_mod, L, torch):
+    """Empty table, one row, fragments whose row counts are not multiples of 16, and chunk pointers that
+    are not 16-byte aligned (the TMA path patches heads/tails with byte copies)."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    rng = np.random.default_rng(5)
+    for n, frag in [(0, 10), (1, 10), (17, 5), (1000, 333), (4099, 4099), (20000, 6007)]:
+        t = pa.table({"s": rng.integers(0, 5, n).astype(np.int16), "x": rng.integers(-100, 100, n).astype(np.int8),
+                      "v": rng.integers(-2**33, 2**33, n), "f": rng.normal(0, 1, n)})
+        st = util.make_storage({"t": t}, fragment_size=frag)
+        if n == 0:
+            continue  # no statistics ⇒ the planner has no key range; HDK short-circuits empty inputs as well
+        text = "SELECT s, COUNT(*), SUM(x), MIN(v), MAX(v), SUM(f) FROM t GROUP BY s"
+        ex = Executor(st)
+        # misalign every chunk: upload into a buffer at an odd element offset
+        tab = st.get_table("t")
+        for f in tab.fragments:
+            for cname, arr in f.chunks.items():
+                w = arr.dtype.itemsize
+                raw = torch.empty(arr.nbytes + 64, dtype=torch.uint8, device="cuda")
+                off = w * 3 if w < 16 else 0
+                raw[off:off + arr.nbytes] = torch.from_numpy(arr.view(np.uint8).copy()).cuda()
+                f.device_chunks[cname] = raw[off:off + arr.nbytes]
+        pq = ex.plan(sql.parse(text, st.tables))
+        prep = ex.prepare(pq)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0
+        check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), 1)
+
+
+def test_error_codes(oracle_mod, torch):
+    """>0 persistent errors (division by zero, overflow), <0 out of slots — same codes as the oracle."""
+    from hdk_b200.executor import Executor, QueryError
+    from hdk_b200 import sql
+    t = pa.table({"k": np.arange(100, dtype=np.int32) % 4, "a": np.arange(100, dtype=np.int64), "z": (np.arange(100) % 10).astype(np.int64),
+                  "h": np.full(100, 2**62, dtype=np.int64)})
+    st = util.make_storage({"t": t}, fragment_size=64)
+    ex = Executor(st)
+    for text, code in [("SELECT k, SUM(a / z) FROM t GROUP BY k", abi.ERR_DIV_BY_ZERO),
+                       ("SELECT k, SUM(h + h) FROM t GROUP BY k", abi.ERR_OVERFLOW_OR_UNDERFLOW)]:
+        pq = ex.plan(sql.parse(text, st.tables))
+        _, oerr = util.run_oracle(oracle_mod, st, pq)
+        assert oerr == code
+        with pytest.raises(QueryError) as ei:
+            ex.execute_work_unit(sql.parse(text, st.tables))
+        assert ei.value.code == code
+    # a filter that removes the offending rows removes the error (quals short-circuit)
+    rs = ex.execute_work_unit(sql.parse("SELECT k, SUM(a / z) FROM t WHERE z <> 0 GROUP BY k", st.tables))
+    assert rs.row_count() == 4
+    # out of slots: negative code, then the retry ladder grows the table
+    t2 = pa.table({"big": np.arange(5000, dtype=np.int64) * 2**33, "v": np.ones(5000, dtype=np.int64)})
+    st2 = util.make_storage({"t": t2}, fragment_size=1024)
+    ex2 = Executor(st2)
+    pq = ex2.plan(sql.parse("SELECT big, SUM(v) FROM t GROUP BY big", st2.tables), max_groups_buffer_entry_count=1024)
+    prep = ex2.prepare(pq)
+    ex2.launch(pq, prep)
+    assert int(prep["err"].item()) < 0
+    _, oerr = util.run_oracle(oracle_mod, st2, pq, per_fragment=False)
+    assert oerr < 0
+    rs = ex2.execute_work_unit(sql.parse("SELECT big, SUM(v) FROM t GROUP BY big", st2.tables))
+    assert rs.row_count() == 5000
+
+
+# ----------------------------------------------------------------------------- join tables ---
+def _dev_join_column(torch, chunks, elem_sz):
+    keep, arr, row = [], (abi.JoinChunk * len(chunks))(), 0
+    for i, c in enumerate(chunks):
+        d = torch.from_numpy(np.ascontiguousarray(c).view(np.uint8).copy()).cuda()
+        keep.append(d)
+        arr[i].col_buff, arr[i].num_elems, arr[i].row_id = d.data_ptr(), len(c), row
+        row += len(c)
+    dchunks = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).cuda()
+    keep.append(dchunks)
+    return abi.JoinColumn(dchunks.data_ptr(), C.sizeof(arr), len(chunks), row, elem_sz), keep
+
+
+def _build_perfect_gpu(L, torch, vals, frag=None):
+    vals = np.array(vals, dtype=np.int32)
+    chunks = [vals] if frag is None else [vals[i:i + frag] for i in range(0, len(vals), frag)]
+    lo, hi = int(vals.min()), int(vals.max())
+    E = hi - lo + 1
+    jc, keep = _dev_join_column(torch, chunks, 4)
+    ti = abi.JoinColumnTypeInfo(4, lo, hi, abi.int_null(4), 0, 0, abi.SIGNED)
+    buf = torch.empty(E, dtype=torch.int32, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert L.hdk_b200_init_hash_join_buff_on_device(buf.data_ptr(), E, -1, None) == 0
+    assert L.hdk_b200_fill_hash_join_buff_on_device(buf.data_ptr(), -1, 0, err.data_ptr(), C.byref(jc), C.byref(ti), 1, None) == 0
+    torch.cuda.synchronize()
+    if int(err.item()) == 0:
+        return "OneToOne", buf.cpu().numpy(), E
+    buf = torch.empty(2 * E + len(vals), dtype=torch.int32, device="cuda")
+    assert L.hdk_b200_fill_one_to_many_hash_table_on_device(buf.data_ptr(), E, -1, C.byref(jc), C.byref(ti), 1, None) == 0
+    torch.cuda.synchronize()
+    return "OneToMany", buf.cpu().numpy(), E
+
+
+def test_join_build_golden_vectors(L, torch):
+    """omniscidb/Tests/JoinHashTableTest.cpp:133-267, 444-560 on the device builders."""
+    from tests.test_oracle_golden import decode_one_to_many
+    kind, buf, E = _build_perfect_gpu(L, torch, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+    assert kind == "OneToOne" and buf.tolist() == list(range(10))
+    kind, buf, E = _build_perfect_gpu(L, torch, [0, 1, 2, 4, 5, 6, 7, 9])
+    assert kind == "OneToOne" and buf.tolist() == [0, 1, 2, -1, 3, 4, 5, 6, -1, 7]
+    kind, buf, E = _build_perfect_gpu(L, torch, [0, 1, 2, 3, 4, 0, 1, 2, 3, 4])
+    assert kind == "OneToMany" and buf[:E].tolist() == [0, 2, 4, 6, 8] and buf[E:2 * E].tolist() == [2] * 5
+    assert decode_one_to_many(buf, E) == {0: [0, 5], 1: [1, 6], 2: [2, 7], 3: [3, 8], 4: [4, 9]}
+    kind, buf, E = _build_perfect_gpu(L, torch, [0, 2, 3, 4, 0, 2, 3, 4])
+    assert kind == "OneToMany" and buf[:E].tolist() == [0, -1, 2, 4, 6] and buf[E:2 * E].tolist() == [2, 0, 2, 2, 2]
+    assert decode_one_to_many(buf, E) == {0: [0, 4], 2: [1, 5], 3: [2, 6], 4: [3, 7]}
+    kind, buf, E = _build_perfect_gpu(L, torch, [0, 1, 2, 3, 4, 0, 1, 2, 3, 4], frag=4)
+    assert decode_one_to_many(buf, E) == {0: [0, 5], 1: [1, 6], 2: [2, 7], 3: [3, 8], 4: [4, 9]}
+
+
+def test_join_build_large_matches_oracle(oracle_mod, L, torch):
+    rng = np.random.default_rng(11)
+    from tests.test_oracle_golden import _perfect, decode_one_to_many
+    vals = rng.permutation(200000).astype(np.int32)[:150000] - 500      # one-to-one with holes
+    kind, buf, E = _build_perfect_gpu(L, torch, vals, frag=40000)
+    okind, obuf, _ = _perfect(oracle_mod, vals, frag=40000)
+    assert kind == okind == "OneToOne" and np.array_equal(buf, obuf)
+    vals = rng.integers(0, 5000, 60000).astype(np.int32)                # one-to-many
+    kind, buf, E = _build_perfect_gpu(L, torch, vals, frag=25000)
+    okind, obuf, _ = _perfect(oracle_mod, vals, frag=25000)
+    assert kind == okind == "OneToMany"
+    assert np.array_equal(buf[:2 * E], obuf[:2 * E])                    # offsets | counts are deterministic
+    assert decode_one_to_many(buf, E) == decode_one_to_many(obuf, E)    # payload order inside a bucket is not
+
+
+def test_baseline_join_keyed_vectors(oracle_mod, L, torch):
+    """Keyed tables (JoinHashTableTest.cpp:355-442): exact layout of the one-to-one table, the composite-key
+    dictionary + offsets/counts/payload of the one-to-many table, probes against the oracle."""
+    for key_width, dt in [(4, np.int32), (8, np.int64)]:
+        b = np.array([0, 1, 3], dtype=np.int32)
+        jc1, k1 = _dev_join_column(torch, [b], 4)
+        jc2, k2 = _dev_join_column(torch, [b], 4)
+        jcs = (abi.JoinColumn * 2)(jc1, jc2)
+        tis = (abi.JoinColumnTypeInfo * 2)(abi.JoinColumnTypeInfo(4, 0, 3, abi.int_null(4), 0, 0, abi.SIGNED),
+                                           abi.JoinColumnTypeInfo(4, 0, 3, abi.int_null(4), 0, 0, abi.SIGNED))
+        E = 6
+        buf = torch.empty(E * 3 * key_width, dtype=torch.uint8, device="cuda")
+        err = torch.zeros(1, dtype=torch.int32, device="cuda")
+        assert L.hdk_b200_init_baseline_hash_join_buff_on_device(buf.data_ptr(), E, 2, 1, -1, key_width, None) == 0
+        assert L.hdk_b200_fill_baseline_hash_join_buff_on_device(buf.data_ptr(), E, -1, 0, 2, 1, err.data_ptr(), jcs, tis, key_width, None) == 0
+        torch.cuda.synchronize()
+        assert int(err.item()) == 0
+        got = buf.cpu().numpy().view(dt).reshape(E, 3).tolist()
+        e = abi.EMPTY_KEY_32 if key_width == 4 else abi.EMPTY_KEY_64
+        if key_width == 4:  # | keys * (1,1,1) (3,3,2) (0,0,0) * * |
+            assert got == [[e, e, -1], [1, 1, 1], [3, 3, 2], [0, 0, 0], [e, e, -1], [e, e, -1]]
+        ob = np.empty(E * 3, dtype=dt)
+        OL = oracle_mod.lib()
+        OL.oracle_init_baseline_hash_join_buff(ob.ctypes.data, E, 2, 1, -1, key_width)
+        ojc = (abi.JoinColumn * 2)(oracle_mod.make_join_column([b], 4), oracle_mod.make_join_column([b], 4))
+        keepers = [oracle_mod.make_join_column([b], 4) for _ in range(2)]
+        ojc = (abi.JoinColumn * 2)(*keepers)
+        assert OL.oracle_fill_baseline_hash_join_buff(ob.ctypes.data, E, -1, 0, 2, 1, ojc, tis, key_width) == 0
+        assert got == ob.reshape(E, 3).tolist()
+        keys = np.array([[0, 0], [1, 1], [3, 3], [2, 2], [1, 3]], dtype=dt)
+        dkeys = torch.from_numpy(keys.view(np.uint8).copy().reshape(-1)).cuda()
+        out = torch.empty(len(keys), dtype=torch.int64, device="cuda")
+        assert L.hdk_b200_probe_baseline_hash_join_on_device(buf.data_ptr(), dkeys.data_ptr(), len(keys), 2, key_width, E, 1, out.data_ptr(), None) == 0
+        o = out.cpu().numpy()
+        assert o[:3].tolist() == [0, 1, 2] and (o[3:] < 0).all()
+        # duplicate key ⇒ err -1 (→ one-to-many): dictionary without payload + offsets | counts | payload
+        b2 = np.array([0, 1, 3, 3], dtype=np.int32)
+        jc1, k3 = _dev_join_column(torch, [b2], 4)
+        jc2, k4 = _dev_join_column(torch, [b2], 4)
+        jcs2 = (abi.JoinColumn * 2)(jc1, jc2)
+        E2 = 8
+        dic = torch.empty(E2 * 2 * key_width, dtype=torch.uint8, device="cuda")
+        assert L.hdk_b200_init_baseline_hash_join_buff_on_device(dic.data_ptr(), E2, 2, 0, -1, key_width, None) == 0
+        err.zero_()
+        assert L.hdk_b200_fill_baseline_hash_join_buff_on_device(dic.data_ptr(), E2, -1, 0, 2, 0, err.data_ptr(), jcs2, tis, key_width, None) == 0
+        otm = torch.empty(2 * E2 + 4, dtype=torch.int32, device="cuda")
+        assert L.hdk_b200_fill_one_to_many_baseline_hash_table_on_device(otm.data_ptr(), dic.data_ptr(), E2, -1, 2, jcs2, tis, key_width, None) == 0
+        torch.cuda.synchronize()
+        d = dic.cpu().numpy().view(dt).reshape(E2, 2)
+        o = otm.cpu().numpy()
+        decoded = {}
+        for i in range(E2):
+            if d[i, 0] != e:
+                decoded[int(d[i, 0])] = sorted(o[2 * E2 + o[i]: 2 * E2 + o[i] + o[E2 + i]].tolist())
+        assert decoded == {0: [0], 1: [1], 3: [2, 3]}     # JoinHashTableTest.cpp:413
+
+
+def test_fused_join_probe_one_to_many(oracle_mod, env, torch):
+    """A duplicate inner key switches the table to offsets|counts|payload and the fused kernel iterates the
+    matches (HashJoin::codegenMatchingSet); checked against pandas."""
+    import hdk_b200.hdk as hdkmod
+    tables, _ = env
+    h = hdkmod.init()
+    h.import_arrow(tables["t"].select(["fk", "f", "s"]), "t", fragment_size=12000)
+    h.import_arrow(tables["dim_many"], "dm")
+    res = h.sql("SELECT dm.attr, COUNT(*) AS n, SUM(t.f) AS sf FROM t JOIN dm ON t.fk = dm.pk GROUP BY dm.attr ORDER BY dm.attr").to_arrow().to_pandas()
+    assert h.executor.join_tables[("dm", "pk")].hash_type == "OneToMany"
+    a = tables["t"].select(["fk", "f"]).to_pandas().merge(tables["dim_many"].to_pandas(), left_on="fk", right_on="pk")
+    g = a.groupby("attr").agg(n=("f", "size"), sf=("f", "sum")).reset_index()
+    assert res["attr"].tolist() == g["attr"].tolist() and res["n"].tolist() == g["n"].tolist()
+    assert np.allclose(res["sf"].values, g["sf"].values, rtol=1e-9)
+
+
+# -------------------------------------------------------------------- reduction / compaction ---
+@pytest.mark.parametrize("idx", [0, 3, 7, 10, 12, 13, 14, 15])
+def test_reduce_on_device_matches_oracle(oracle_mod, L, env, torch, idx):
+    """ResultSetReduction on the device: two halves of the fragments aggregated separately, merged with
+    hdk_b200_reduce, against the oracle's per-fragment kernels + reduce."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    text, nk, kw = QUERIES[idx]
+    ex = Executor(st, kw.get("cfg"))
+    unit = sql.parse(text, st.tables)
+    pq = ex.plan(unit, kw.get("max_groups_buffer_entry_count"), kw.get("output_columnar"))
+    frags = st.get_table("t").fragments
+    halves = [frags[: len(frags) // 2], frags[len(frags) // 2:]]
+    bufs = []
+    for hf in halves:
+        prep = ex.prepare(pq, fragments=hf)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0
+        bufs.append(prep["out"].clone())
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = L.hdk_b200_reduce(C.byref(pq.plan), C.byref(pq.qmd), bufs[0].data_ptr(), bufs[1].data_ptr(), pq.qmd.entry_count, err.data_ptr(), None)
+    assert rc == 0, L.hdk_b200_last_error()
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    check_against_oracle(oracle_mod, st, pq, bufs[0].cpu().numpy(), nk)
+
+
+@pytest.mark.parametrize("idx", [0, 3, 7, 8, 11, 12, 13])
+def test_compact_result_matches_iteration(oracle_mod, L, env, torch, idx):
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    text, nk, kw = QUERIES[idx]
+    ex = Executor(st, kw.get("cfg"))
+    pq = ex.plan(sql.parse(text, st.tables), kw.get("max_groups_buffer_entry_count"), kw.get("output_columnar"))
+    prep = ex.prepare(pq)
+    ex.launch(pq, prep)
+    E, T = pq.qmd.entry_count, pq.plan.n_targets
+    cols = torch.zeros((T, E), dtype=torch.int64, device="cuda")
+    ptrs = torch.tensor([cols[t].data_ptr() for t in range(T)], dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert L.hdk_b200_compact_result(C.byref(pq.plan), C.byref(pq.qmd), prep["out"].data_ptr(), ptrs.data_ptr(), cnt.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    n = int(cnt.item())
+    got = cols[:, :n].cpu().numpy().T
+    vals, nulls = oracle_mod.iterate(pq, prep["out"].cpu().numpy())
+    assert n == len(vals)
+    key = lambda a: a[np.lexsort(a.T[::-1])]  # noqa: E731
+    assert np.array_equal(key(got), key(vals))
+
+
+def test_shuffle_partitions_rows_by_key(L, env, torch):
+    """hdk_b200_shuffle_count / _scatter: every row lands in exactly one partition, partition = f(key) only,
+    counts agree with the scatter, the multiset of rows is preserved."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    ex = Executor(st)
+    pq = ex.plan(sql.parse("SELECT mid, s, SUM(v) FROM t GROUP BY mid, s", st.tables), 262144)
+    prep = ex.prepare(pq)
+    P = 8
+    counts = torch.zeros(P, dtype=torch.int64, device="cuda")
+    assert L.hdk_b200_shuffle_count(C.byref(pq.plan), C.byref(prep["kp"]), P, counts.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    c = counts.cpu().numpy()
+    n = tables["t"].num_rows
+    assert c.sum() == n and (c > 0).all()
+    offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(c)[:-1]]).astype(np.int64)).cuda()
+    cursors = torch.zeros(P, dtype=torch.int64, device="cuda")
+    tab = st.get_table("t")
+    outs = [torch.zeros(n * tab.columns[cn].phys_width, dtype=torch.uint8, device="cuda") for cn in pq.columns]
+    ptrs = torch.tensor([o.data_ptr() for o in outs], dtype=torch.int64, device="cuda")
+    assert L.hdk_b200_shuffle_scatter(C.byref(pq.plan), C.byref(prep["kp"]), P, offsets.data_ptr(), cursors.data_ptr(), ptrs.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(cursors.cpu().numpy(), c)
+    cols = {cn: outs[i].cpu().numpy().view(tab.columns[cn].np_dtype) for i, cn in enumerate(pq.columns)}
+    src = {cn: np.concatenate([f.chunks[cn] for f in tab.fragments]) for cn in pq.columns}
+    order = lambda d: np.lexsort([d[cn] for cn in pq.columns])  # noqa: E731
+    for cn in pq.columns:
+        assert np.array_equal(cols[cn][order(cols)], src[cn][order(src)])
+    part_of = {}
+    bounds = np.concatenate([[0], np.cumsum(c)])
+    for p in range(P):
+        seg = slice(bounds[p], bounds[p + 1])
+        for key in set(zip(cols["mid"][seg].tolist(), cols["s"][seg].tolist())):
+            assert part_of.setdefault(key, p) == p
+
+
+def test_init_group_by_buffer_mirrors(L, torch):
+    """hdk_b200_init_group_by_buffer_on_device / _columnar_ with the reference's argument meaning
+    (QE/GpuInitGroups.cu:120-188)."""
+    init = torch.tensor([0, -5, 7], dtype=torch.int64, device="cuda")
+    buf = torch.zeros(10 * 5, dtype=torch.int64, device="cuda")
+    assert L.hdk_b200_init_group_by_buffer_on_device(buf.data_ptr(), init.data_ptr(), 10, 2, 8, 5, 0, 1, 0, 0, None) == 0
+    torch.cuda.synchronize()
+    rows = buf.cpu().numpy().reshape(10, 5)
+    assert (rows[:, :2] == abi.EMPTY_KEY_64).all() and (rows[:, 2:] == [0, -5, 7]).all()
+    buf.zero_()
+    assert L.hdk_b200_init_group_by_buffer_on_device(buf.data_ptr(), init.data_ptr(), 10, 0, 8, 3, 1, 1, 0, 0, None) == 0
+    torch.cuda.synchronize()
+    assert (buf.cpu().numpy()[:30].reshape(10, 3) == [0, -5, 7]).all()
+    sizes = torch.tensor([8, 4, 8], dtype=torch.int8, device="cuda")
+    cbuf = torch.zeros(8 * 10 + 8 * 10 + 40 + 80, dtype=torch.uint8, device="cuda")
+    assert L.hdk_b200_init_columnar_group_by_buffer_on_device(cbuf.data_ptr(), init.data_ptr(), 10, 1, 3, sizes.data_ptr(), 1, 0, 8, 0, 0, None) == 0
+    torch.cuda.synchronize()
+    raw = cbuf.cpu().numpy()
+    assert (raw[:80].view(np.int64) == abi.EMPTY_KEY_64).all() and (raw[80:160].view(np.int64) == 0).all()
+    assert (raw[160:200].view(np.int32) == -5).all() and (raw[200:280].view(np.int64) == 7).all()

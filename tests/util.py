@@ -1,0 +1,100 @@
+"""Shared helpers of the test-suite: build tables, plan queries, run the CPU oracle, compare."""
+import ctypes as C
+import sqlite3
+
+import numpy as np
+import pyarrow as pa
+
+from hdk_b200 import abi, planner, sql, storage
+
+
+def make_storage(tables, fragment_size=1000):
+    st = storage.ArrowStorage()
+    for name, t in tables.items():
+        fs = fragment_size[name] if isinstance(fragment_size, dict) else fragment_size
+        st.import_arrow_table(t, name, fragment_size=fs)
+    return st
+
+
+def plan_sql(st, text, cfg=None, **kw):
+    unit = sql.parse(text, st.tables)
+    tabs = [st.get_table(unit.table)] + [st.get_table(j.inner_table) for j in unit.joins]
+    return planner.build_query(unit, lambda ti, c: tabs[ti].col_stats(c), tabs[0].num_rows, cfg or planner.Config(), **kw)
+
+
+def oracle_inputs(oracle, st, pq):
+    """Fragments + host-built join tables / inner columns for the oracle (and query_host)."""
+    outer = st.get_table(pq.unit.table)
+    frs = oracle.Fragments([[fr.chunks[c] for c in pq.columns] for fr in outer.fragments])
+    join_tables, inner_cols = [], []
+    for j, js in enumerate(pq.unit.joins):
+        inner = st.get_table(js.inner_table)
+        lo, hi, _ = inner.col_stats(js.inner_key_column)
+        ci = inner.columns[js.inner_key_column]
+        E = hi - lo + 1
+        chunks = [f.chunks[js.inner_key_column] for f in inner.fragments]
+        jc = oracle.make_join_column(chunks, ci.phys_width)
+        ti = oracle.make_type_info(ci.phys_width, lo, hi, abi.int_null(ci.phys_width))
+        L = oracle.lib()
+        buf = np.empty(E, dtype=np.int32)
+        L.oracle_init_hash_join_buff(buf.ctypes.data, E, -1)
+        rc = L.oracle_fill_hash_join_buff(buf.ctypes.data, -1, 0, C.byref(jc), C.byref(ti), 1)
+        assert rc == 0, "oracle join tables in these tests are one-to-one"
+        pj = pq.plan.joins[j]
+        pj.one_to_many, pj.min_key, pj.max_key, pj.entry_count = 0, lo, hi, E
+        join_tables.append(buf)
+        inner_cols.append([np.concatenate([f.chunks[c] for f in inner.fragments]) for c in pq.inner_columns[j]])
+    return frs, join_tables, inner_cols
+
+
+def run_oracle(oracle, st, pq, kind="port", n_threads=2, per_fragment=True):
+    frs, jt, ic = oracle_inputs(oracle, st, pq)
+    buf, err = oracle.run_query(pq, frs, jt, ic, n_threads=n_threads, kind=kind, per_fragment=per_fragment)
+    return buf, err
+
+
+def result_columns(oracle, pq, buf):
+    vals, nulls = oracle.iterate(pq, buf)
+    return oracle.rows_to_columns(pq, vals, nulls)
+
+
+def sort_rows(cols, n_keys):
+    """rows sorted by the first n_keys columns (NULLs first) → list of tuples with None for NULL"""
+    n = len(cols[0]) if cols else 0
+    rows = []
+    for i in range(n):
+        row = []
+        for c in cols:
+            m = np.ma.getmaskarray(c)[i]
+            v = np.ma.getdata(c)[i]
+            row.append(None if m else (float(v) if np.issubdtype(np.asarray(v).dtype, np.floating) else int(v)))
+        rows.append(tuple(row))
+    keyf = lambda r: tuple((0, 0) if x is None else (1, x) for x in r[:n_keys])  # noqa: E731
+    return sorted(rows, key=keyf)
+
+
+def assert_rows_equal(got, exp, rel=1e-9, float_cols=()):
+    assert len(got) == len(exp), f"row count {len(got)} != {len(exp)}"
+    for r, (g, e) in enumerate(zip(got, exp)):
+        assert len(g) == len(e)
+        for c, (a, b) in enumerate(zip(g, e)):
+            if a is None or b is None:
+                assert a is None and b is None, f"row {r} col {c}: {a} vs {b}"
+            elif isinstance(a, float) or isinstance(b, float) or c in float_cols:
+                assert abs(float(a) - float(b)) <= rel * max(abs(float(b)), 1e-300) + 1e-300, f"row {r} col {c}: {a} vs {b}"
+            else:
+                assert a == b, f"row {r} col {c}: {a} vs {b}"
+
+
+def sqlite_rows(tables, text, n_keys):
+    """The reference's own differential oracle: the same SQL on SQLite
+    (omniscidb/Tests/ArrowSQLRunner/SQLiteComparator.cpp:66-170)."""
+    con = sqlite3.connect(":memory:")
+    for name, t in tables.items():
+        cols = t.column_names
+        con.execute(f"CREATE TABLE {name} ({', '.join(cols)})")
+        data = list(zip(*[t.column(c).to_pylist() for c in cols]))
+        con.executemany(f"INSERT INTO {name} VALUES ({', '.join('?' * len(cols))})", data)
+    rows = [tuple(r) for r in con.execute(text).fetchall()]
+    keyf = lambda r: tuple((0, 0) if x is None else (1, x) for x in r[:n_keys])  # noqa: E731
+    return sorted(rows, key=keyf)
