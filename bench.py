@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path: NYC-taxi-shaped synthetic table, taxi benchmark
+Q1–Q4 (omniscidb/Benchmarks/taxi/taxi_full_bench.cpp:300-355), 1.1 B rows per GPU resident in HBM.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N … bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference …      # the reference's CPU path (oracle/_ref) on the host cores
+
+A step = one pass of Q1, Q2, Q3 and Q4 over this rank's fragments: per query the fused scan kernel
+fills a neutral work table, ranks merge it with NCCL all-reduce (N > 1), a finalize kernel writes the
+reference-encoded group-by buffer.  value = rows scanned per second over all ranks
+(4 queries × rows per GPU × N ÷ max-over-ranks device time).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rows/s (taxi Q1-Q4 scan+group-by, rows scanned per second)"
+UNIT = "rows/s"
+NOMINAL_HBM_GBS = 8000.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy read+write)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU execution shape on the host cores (oracle/_ref, else the port)
+# ------------------------------------------------------------------------------------------------
+def cpu_taxi(sample_rows, threads, repeats=1):
+    """Q1–Q4 over a host-resident taxi sample: one kernel per fragment with a private buffer on `threads`
+    workers, then ResultSetReduction.  Returns (rows/s over the four queries, kind, seconds)."""
+    import numpy as np
+    import benchdata
+    from hdk_b200 import planner, sql, storage
+    from oracle import oracle
+    kind = "reference" if oracle.ref_available() else "port"
+    st = storage.ArrowStorage()
+    rng = np.random.default_rng(benchdata.SEED)
+    n = sample_rows
+    import pyarrow as pa
+    lo, hi = benchdata._epoch_ms(2009, 1, 1), benchdata._epoch_ms(2016, 7, 1)
+    t = pa.table({
+        "cab_type": pa.array((rng.random(n) < 0.08).astype(np.int32)),
+        "passenger_count": pa.array(rng.choice(10, n, p=np.array(benchdata.PASSENGER_PMF) / sum(benchdata.PASSENGER_PMF)).astype(np.int16)),
+        "pickup_datetime": pa.array(rng.integers(lo, hi, n).astype("datetime64[ms]")),
+        "total_amount": pa.array(np.abs(rng.normal(14, 10, n))),
+        "trip_distance": pa.array(np.minimum(rng.exponential(2.9, n), 200.0)),
+    })
+    frag = max(1, (n + threads * 2 - 1) // (threads * 2))
+    tab = st.import_arrow_table(t, "trips", fragment_size=frag)
+    total = 0.0
+    for _ in range(repeats):
+        for q in ("q1", "q2", "q3", "q4"):
+            unit = sql.parse(benchdata.TAXI_QUERIES[q], st.tables)
+            pq = planner.build_query(unit, lambda ti, c: tab.col_stats(c), tab.num_rows)
+            frs = oracle.Fragments([[fr.chunks[c] for c in pq.columns] for fr in tab.fragments])
+            t0 = time.perf_counter()
+            buf, err = oracle.run_query(pq, frs, n_threads=threads, kind=kind)
+            total += time.perf_counter() - t0
+            assert err == 0
+    return 4.0 * n * repeats / total, kind, total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample_rows
+    cpu_taxi(min(sample, 2_000_000), threads)   # warm the page cache / allocator
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_taxi(sample, threads)
+    t0 = time.perf_counter()
+    vals = [cpu_taxi(sample, threads) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    value = sum(v[0] for v in vals) / len(vals)
+    kind = vals[0][1]
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(v[2] for v in vals) / len(vals), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic",
+        "config": {"workload": "taxi Q1-Q4, NYC-taxi-shaped synthetic rows (bounded CPU sample of the 1.1B-row config)",
+                   "rows_per_step": sample, "queries": 4},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{sample} rows x 4 queries per step, one kernel per fragment on {threads} threads + reduce; "
+                                   "per-row runtime = the reference's RuntimeFunctions.cpp compiled -O3 into the driver, row loop interpreted from the plan "
+                                   "(the LLVM JIT cannot be built here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=1_100_000_000, help="rows per GPU (weak scaling)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000)
+    ap.add_argument("--e2e-rows", type=int, default=128_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import benchdata
+    from hdk_b200 import _lib, abi, distributed as D, sql
+    from hdk_b200.executor import Executor
+    from hdk_b200.storage import ArrowStorage
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    L = _lib.lib()
+
+    # ---- data: this rank's shard, generated on the device, resident in HBM before timing
+    st = ArrowStorage()
+    t_gen = time.perf_counter()
+    benchdata.make_taxi(st, device, args.rows, rank=rank)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t_gen
+    ex = Executor(st, device=local_rank)
+    qnames = ["q1", "q2", "q3", "q4"]
+    plans = {}
+    for q in qnames:
+        plans[q] = sql.parse(benchdata.TAXI_QUERIES[q], st.tables)
+    # global statistics so that all ranks agree on the perfect-hash ranges
+    if world > 1:
+        tab = st.get_table("trips")
+        for cname, ci in tab.columns.items():
+            lo, hi, hn = tab.col_stats(cname)
+            tt = torch.tensor([float(lo), -float(hi)], dtype=torch.float64, device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+            glo, ghi = tt[0].item(), -tt[1].item()
+            for f in tab.fragments:
+                f.stats[cname].min = glo if ci.type.is_fp else int(glo)
+                f.stats[cname].max = ghi if ci.type.is_fp else int(ghi)
+    pqs, preps, layouts = {}, {}, {}
+    for q in qnames:
+        pq = ex.plan(plans[q])
+        assert pq.qmd.hash_type == abi.PERFECT_HASH
+        pqs[q] = pq
+        preps[q] = ex.prepare(pq)
+        preps[q]["scratch"] = torch.empty(max(preps[q]["scratch_bytes"], 8), dtype=torch.uint8, device=device)  # one work table per query
+        layouts[q] = ex.work_table_layout(pq)
+    stream_ptr = ex.ctx.stream_ptr()
+
+    def run_query(q, ev=None):
+        pq, prep = pqs[q], preps[q]
+        prep["err"].zero_()
+        _lib.check(L.hdk_b200_init_work_table(C.byref(pq.plan), C.byref(pq.qmd), prep["scratch"].data_ptr(), stream_ptr), "init_work_table")
+        if ev is not None:
+            ev[0].record()
+        info = abi.LaunchInfo()
+        _lib.check(L.hdk_b200_launch_partial(C.byref(pq.plan), C.byref(pq.qmd), None, C.byref(prep["kp"]), prep["scratch"].data_ptr(),
+                                             stream_ptr, C.byref(info)), "launch_partial")
+        if ev is not None:
+            ev[1].record()
+        wl = layouts[q]
+        D.allreduce_work_table(prep["scratch"], wl.n_cells, wl.sum_i64_cells, wl.sum_cells, wl.min_cells, wl.max_cells)
+        ex.finalize(pq, prep)
+        return info
+
+    def step(evs=None):
+        infos = {}
+        for q in qnames:
+            infos[q] = run_query(q, evs[q] if evs else None)
+        return infos
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        infos = step()
+    barrier()
+    for q in qnames:
+        assert int(preps[q]["err"].item()) == 0, f"{q}: in-band error"
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    kernel_events = [{q: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for q in qnames}
+                     for _ in range(args.steps)]
+    launches0 = L.hdk_b200_launch_count()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e_start.record()
+    for s in range(args.steps):
+        step(kernel_events[s])
+    e_end.record()
+    barrier()
+    launches = L.hdk_b200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = e_start.elapsed_time(e_end)
+    tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    elapsed_ms = tt.item()
+    rows_rank = st.get_table("trips").num_rows
+    value = 4.0 * rows_rank * world * args.steps / (elapsed_ms * 1e-3)
+
+    # per-query scan-kernel durations (CUDA events on the launching stream, inside the timed region)
+    peak, peak_src = measured_peak()
+    per_query = {}
+    for q in qnames:
+        ms = sum(kernel_events[s][q][0].elapsed_time(kernel_events[s][q][1]) for s in range(args.steps)) / args.steps
+        bytes_alg = benchdata.TAXI_BYTES_PER_ROW[q] * rows_rank
+        gbs = bytes_alg / (ms * 1e-3) / 1e9
+        per_query[q] = {"scan_kernel_ms": ms, "rows_per_s": rows_rank / (ms * 1e-3), "bytes_per_row": benchdata.TAXI_BYTES_PER_ROW[q],
+                        "achieved_gbs": gbs, "frac_of_measured_peak": gbs / peak, "frac_of_nominal_8TBs": gbs / NOMINAL_HBM_GBS,
+                        "strategy": int(infos[q].strategy), "entry_count": int(pqs[q].qmd.entry_count),
+                        "grid": int(infos[q].grid), "smem_bytes": int(infos[q].smem_bytes)}
+    dominant = max(qnames, key=lambda q: per_query[q]["scan_kernel_ms"])
+    dq = per_query[dominant]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dominant)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": f"scan_kernel (taxi {dominant})", "achieved": dq["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dq["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": benchdata.TAXI_BYTES_PER_ROW[dominant] * rows_rank,
+                "kernel_ms": dq["scan_kernel_ms"],
+                "step_frac": sum(benchdata.TAXI_BYTES_PER_ROW[q] for q in qnames) * rows_rank / 1e9 /
+                (sum(per_query[q]["scan_kernel_ms"] for q in qnames) * 1e-3) / peak}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64/f64", "data": "synthetic",
+        "config": {"workload": "NYC-taxi-shaped synthetic table, taxi benchmark Q1-Q4 (BASELINE.json configs[1])",
+                   "rows_per_gpu": rows_rank, "total_rows": rows_rank * world, "fragment_rows": benchdata.FRAGMENT_ROWS,
+                   "queries": 4, "parallelism": f"fragments sharded per GPU x{world}; perfect-hash partials merged by NCCL all-reduce",
+                   "l2": "inputs (4.4-19.8 GB per query) are larger than the 126 MB L2", "data_gen_s": gen_s},
+        "roofline": roofline, "per_query": per_query, "gpu_launches": int(launches),
+    }
+    if rank == 0:
+        out["clocks"] = clocks
+
+    # ---- e2e: the public API (Executor.execute_work_unit = what hdk.sql() runs) with HOST-resident chunks:
+    #      every query copies its columns from pinned host memory, launches, reads the result back and decodes it
+    if not args.no_e2e:
+        e2e_rows = min(args.e2e_rows, rows_rank)
+        tab = st.get_table("trips")
+        n_frag = max(1, (e2e_rows + benchdata.FRAGMENT_ROWS - 1) // benchdata.FRAGMENT_ROWS)
+        st2 = ArrowStorage()
+        from hdk_b200.storage import Fragment
+        frs = []
+        for f in tab.fragments[:n_frag]:
+            pinned = {c: torch.empty(d.numel(), dtype=torch.uint8).pin_memory() for c, d in f.device_chunks.items()}
+            for c, d in f.device_chunks.items():
+                pinned[c].copy_(d)
+            nf = Fragment(f.frag_id, f.num_rows, f.row_offset, 0, {}, f.stats, {})
+            nf.pinned = pinned
+            frs.append(nf)
+        torch.cuda.synchronize()
+        st2.add_device_table("trips", tab.columns, frs)
+        ex2 = Executor(st2, device=local_rank, hot_data=False)
+        units = {q: sql.parse(benchdata.TAXI_QUERIES[q], st2.tables) for q in qnames}
+        e2e_rows = sum(f.num_rows for f in frs)
+
+        def e2e_step():
+            d2h = 0
+            for q in qnames:
+                rs = ex2.execute_work_unit(units[q])
+                rs.row_count()
+                d2h += rs.buffer.nbytes + 4
+            return d2h
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        ex2.ctx.h2d_bytes = 0
+        k = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(k):
+            d2h = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        out["e2e"] = {"value": 4.0 * e2e_rows * world * k / tt.item(), "unit": UNIT, "h2d_bytes_per_step": ex2.ctx.h2d_bytes // k,
+                      "d2h_bytes_per_step": int(d2h), "rows_per_gpu": e2e_rows, "steps": k,
+                      "path": "Executor.execute_work_unit (hdk.sql): pinned host chunks -> H2D -> init+scan+finalize -> D2H buffer + error code -> ResultSet decode"}
+        del ex2, st2, frs
+
+    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        try:
+            v, kind, secs = cpu_taxi(args.cpu_sample_rows, threads)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                                   "sample": f"{args.cpu_sample_rows} rows x Q1-Q4 ({secs:.1f} s of CPU work), one kernel per fragment on {threads} "
+                                             "threads + reduce; per-row runtime = the reference's own RuntimeFunctions.cpp (oracle/_ref), row loop "
+                                             "interpreted from the plan because the LLVM JIT cannot be built here"}
+        except Exception as e:  # the oracle is a reported baseline, never a dependency of the product path
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

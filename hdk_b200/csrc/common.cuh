@@ -138,6 +138,7 @@ struct Lowered {
 };
 
 int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, Lowered* out);
+uint64_t plan_signature(const DPlan& p);
 
 // ---------------------------------------------------------------------------------------
 // small device helpers

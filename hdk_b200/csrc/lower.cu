@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <string>
 
 #include "common.cuh"
 
@@ -302,9 +303,64 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
   return HDK_B200_OK;
 }
 
+// Structural signature of a lowered plan: everything the scan kernel's control flow depends on, nothing
+// that is data (literals, key ranges, entry counts).  Pre-compiled shapes are matched by it.
+uint64_t plan_signature(const DPlan& p) {
+  uint64_t h = 1469598103934665603ULL;
+  auto mix = [&](uint64_t v) { for (int i = 0; i < 8; ++i) { h ^= (v >> (8 * i)) & 0xff; h *= 1099511628211ULL; } };
+  mix(p.n_exprs); mix(p.n_filters); mix(p.n_keys); mix(p.n_joins); mix(p.n_acc); mix(p.n_cols); mix(p.hash_type);
+  for (int i = 0; i < p.n_exprs; ++i) {
+    const DExpr& e = p.exprs[i];
+    mix(e.op); mix(uint8_t(e.a)); mix(uint8_t(e.b)); mix(e.aux); mix(e.kind); mix(e.width); mix(e.nullable);
+    if (e.op == HDK_B200_OP_COL || e.op == HDK_B200_OP_EXTRACT_YEAR) mix(uint64_t(e.imm.i));
+  }
+  for (int i = 0; i < p.n_filters; ++i) mix(uint8_t(p.filters[i]));
+  for (int i = 0; i < p.n_keys; ++i) { mix(p.keys[i].expr); mix(p.keys[i].has_nulls); mix(p.keys[i].width); }
+  for (int i = 0; i < p.n_joins; ++i) { mix(p.joins[i].key_expr); mix(p.joins[i].key_nullable); mix(p.joins[i].one_to_many); }
+  for (int i = 0; i < p.n_acc; ++i) { mix(p.accs[i].kind); mix(uint8_t(p.accs[i].arg)); mix(p.accs[i].arg_nullable); mix(p.accs[i].bytes); }
+  for (int i = 0; i < p.n_cols; ++i) mix(p.col_width[i]);
+  return h;
+}
+
+// C++ aggregate initialiser of the structural part of a DPlan (consumed by static_shapes.inc)
+static int dump_shape(const DPlan& p, char* out, size_t cap) {
+  std::string s = "{";
+  auto add = [&](const char* fmt, ...) { char b[256]; va_list ap; va_start(ap, fmt); vsnprintf(b, sizeof(b), fmt, ap); va_end(ap); s += b; };
+  add("%d, %d, %d, %d, %d, %d, 0u, %d,\n  {", p.n_exprs, p.n_filters, p.n_keys, p.n_joins, p.n_acc, p.n_cols, p.hash_type);
+  for (int i = 0; i < p.n_exprs; ++i) {
+    const DExpr& e = p.exprs[i];
+    const long long imm = (e.op == HDK_B200_OP_COL || e.op == HDK_B200_OP_EXTRACT_YEAR) ? (long long)e.imm.i : 0;
+    add("{%d, %d, %d, %d, %d, %d, %d, 0, {%lldLL}}%s", e.op, e.a, e.b, e.aux, e.kind, e.width, e.nullable, imm, i + 1 < p.n_exprs ? ", " : "");
+  }
+  s += "},\n  {";
+  for (int i = 0; i < HDK_B200_MAX_FILTERS; ++i) add("%d%s", i < p.n_filters ? p.filters[i] : 0, i + 1 < HDK_B200_MAX_FILTERS ? ", " : "");
+  s += "},\n  {";
+  for (int i = 0; i < p.n_keys; ++i) add("{0, 0, 0, 0, %d, %d, %d, 0, 0}%s", p.keys[i].expr, p.keys[i].has_nulls, p.keys[i].width, i + 1 < p.n_keys ? ", " : "");
+  s += "},\n  {";
+  for (int i = 0; i < p.n_joins; ++i) add("{0, 0, 0, %d, %d, %d, 0, 0}%s", p.joins[i].key_expr, p.joins[i].key_nullable, p.joins[i].one_to_many, i + 1 < p.n_joins ? ", " : "");
+  s += "},\n  {";
+  for (int i = 0; i < p.n_acc; ++i) add("{%d, %d, %d, %d}%s", p.accs[i].kind, p.accs[i].arg, p.accs[i].arg_nullable, p.accs[i].bytes, i + 1 < p.n_acc ? ", " : "");
+  s += "},\n  {";
+  for (int i = 0; i < HDK_B200_MAX_COLS; ++i) add("%d%s", i < p.n_cols ? p.col_width[i] : 0, i + 1 < HDK_B200_MAX_COLS ? ", " : "");
+  s += "},\n  {0, 0, 0, 0}}";
+  if (s.size() + 1 > cap) return -1;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return int(s.size());
+}
+
 }  // namespace hb
 
 extern "C" {
+// build-time helper of tools/gen_static_shapes.py (not part of the public header): signature + initialiser text
+__attribute__((visibility("default"))) int hdk_b200_internal_dump_shape(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd,
+                                                                        uint64_t* sig, int* n_exprs, char* out, size_t cap) {
+  hb::Lowered lw;
+  if (int rc = hb::lower_plan(plan, qmd, &lw)) return rc;
+  if (sig) *sig = hb::plan_signature(lw.plan);
+  if (n_exprs) *n_exprs = lw.plan.n_exprs;
+  return hb::dump_shape(lw.plan, out, cap) < 0 ? HDK_B200_E_NOMEM : HDK_B200_OK;
+}
+
 const char* hdk_b200_last_error(void) { return hb::last_error(); }
 int hdk_b200_abi_version(void) { return HDK_B200_ABI_VERSION; }
 uint64_t hdk_b200_launch_count(void) { return hb::g_launch_count; }

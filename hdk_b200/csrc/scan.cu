@@ -94,7 +94,221 @@ struct StageHeader {          // written by the producer, read by consumers
   uint32_t col_off[HDK_B200_MAX_COLS];  // byte offset (from dynamic smem base) of element 0 of column c
 };
 
+// ---- plan shapes -----------------------------------------------------------------------------
+// The generic kernel interprets the device plan at run time.  For the plan shapes listed in
+// static_shapes.inc (generated at build time from the named configs by tools/gen_static_shapes.py)
+// the SAME row code is instantiated with the plan's structure as a compile-time constant, so the
+// expression switch, type checks and accumulator dispatch fold away and `vals[]` lives in registers.
+// Literal values, key ranges and entry counts stay run-time parameters in both cases.
+struct GenericShape {
+  static constexpr bool is_static = false;
+  static constexpr int rows_per_iter = 1;
+  __host__ __device__ static constexpr DPlan get() { return DPlan{}; }
+};
+template <int ID>
+struct StaticShape;
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+__device__ __forceinline__ uint64_t lds_elem(const uint8_t* ptr, int w) {
+  return w == 8 ? *reinterpret_cast<const uint64_t*>(ptr) : w == 4 ? uint64_t(*reinterpret_cast<const uint32_t*>(ptr))
+         : w == 2 ? uint64_t(*reinterpret_cast<const uint16_t*>(ptr)) : uint64_t(*ptr);
+}
+__device__ __forceinline__ uint64_t ldg_elem(const uint8_t* ptr, int w) {
+  return w == 8 ? __ldg(reinterpret_cast<const uint64_t*>(ptr)) : w == 4 ? uint64_t(__ldg(reinterpret_cast<const uint32_t*>(ptr)))
+         : w == 2 ? uint64_t(__ldg(reinterpret_cast<const uint16_t*>(ptr))) : uint64_t(__ldg(ptr));
+}
+
+// group slot of a row (perfect hash): get_group_value_fast / perfect_key_hash incl. translate_null_key
+// (QE/GroupByRuntime.cpp:198-213, QE/RowFuncBuilder.cpp:748-801)
 template <int kStrategy>
+__device__ __forceinline__ void accumulate_one(const ScanArgs& args, uint8_t* bins, int tid, int a, const DAcc acc, uint32_t idx,
+                                               int64_t x) {
+  if (kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE) {
+    bin_update_private(acc.kind, bins + args.acc_bin_off[a] + (size_t(idx) * kConsumerThreads + tid) * acc.bytes, x);
+  } else if (kStrategy == HDK_B200_STRATEGY_CTA_SHARED) {
+    bin_update_shared_atomic(acc.kind, bins + args.acc_bin_off[a] + size_t(idx) * acc.bytes, x);
+  } else {
+    cell_update_global(acc.kind, args.work_table + size_t(a) * args.plan.entry_count + idx, x);
+  }
+}
+
+// baseline hash: find / claim the entry in the reference-encoded buffer, update slots in place
+__device__ __forceinline__ void baseline_row(const ScanArgs& args, const DPlan& p, const V* vals, int32_t& my_err) {
+  const DLayout& L = args.layout;
+  int8_t* buf = reinterpret_cast<int8_t*>(args.groupby_buf[0]);
+  int64_t keys[HDK_B200_MAX_KEYS];
+  for (int k = 0; k < p.n_keys; ++k) {
+    const int64_t v = vals[p.keys[k].expr].i;
+    keys[k] = L.key_width == 4 ? int64_t(int32_t(v)) : v;  // castToTypeIn(key, key_width * 8), no NULL translation
+  }
+  const uint32_t h0 = key_hash_dev(keys, p.n_keys, L.key_width) % p.entry_count;
+  const int64_t entry = L.columnar ? baseline_claim_columnar(reinterpret_cast<int64_t*>(buf), p.entry_count, keys, p.n_keys, h0)
+                        : L.key_width == 4 ? baseline_claim_rowwise<int32_t>(buf, L.row_bytes, p.entry_count, keys, p.n_keys, h0)
+                                           : baseline_claim_rowwise<int64_t>(buf, L.row_bytes, p.entry_count, keys, p.n_keys, h0);
+  if (entry < 0) { if (my_err <= 0) my_err = -HDK_B200_ERR_OUT_OF_SLOTS; return; }
+  for (int s = 0; s < L.slot_count; ++s) {
+    const DSlot& sl = L.slots[s];
+    if (!sl.padded || sl.op == SLOT_KEY) continue;
+    int64_t vi = 0;
+    double vf = 0.0;
+    bool arg_null = false;
+    if (sl.arg >= 0) {
+      vi = vals[sl.arg].i;
+      vf = vals[sl.arg].f;
+      if (sl.arg_nullable) {
+        arg_null = sl.arg_kind == HDK_B200_FP ? (vf == fp_null_of(sl.arg_width)) : (vi == int_null_of(sl.arg_width));
+        if (sl.count_mode == 2 && int32_t(vi) == INT32_MIN) arg_null = true;
+      }
+    }
+    int8_t* ptr = L.columnar ? buf + sl.col_off + size_t(entry) * sl.padded : buf + size_t(entry) * L.row_bytes + L.key_bytes + sl.off;
+    baseline_update_slot(sl, ptr, vi, vf, arg_null);
+  }
+}
+
+// ---- one row, run-time plan --------------------------------------------------------------------
+template <int kStrategy>
+__device__ __forceinline__ void process_row_generic(const ScanArgs& args, const uint8_t* smem, const uint32_t* col_off, uint32_t r,
+                                                    uint8_t* bins, int tid, V* vals, int32_t& my_err) {
+  const DPlan& p = args.plan;
+  int64_t rowid[HDK_B200_MAX_JOINS];
+  auto load_outer = [&](int c, int w) -> uint64_t { return lds_elem(smem + col_off[c] + size_t(r) * w, w); };
+  auto load_inner = [&](int j, int c, int w) -> uint64_t {
+    return ldg_elem(reinterpret_cast<const uint8_t*>(args.inner_col_buffers[j * HDK_B200_MAX_COLS + c]) + size_t(rowid[j]) * w, w);
+  };
+  int32_t row_err = 0;
+  bool dropped = false;
+  // 1:N join: nodes up to the key are evaluated once, the rest once per match
+  int n_matches = 1;
+  const int32_t* match_ids = nullptr;
+  int split = p.n_exprs;
+  if (p.n_joins == 1 && p.joins[0].one_to_many) split = p.joins[0].key_expr + 1;
+  for (int n = 0; n < split && !dropped; ++n) {
+    int32_t e = 0;
+    vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
+    if (e && !row_err) row_err = e;
+    for (int j = 0; j < p.n_joins; ++j) {
+      const DJoin& jn = p.joins[j];
+      if (jn.key_expr != n) continue;
+      // hash_join_idx[_nullable] (QE/GroupByRuntime.cpp:298-329)
+      const int64_t key = vals[n].i;
+      if ((jn.key_nullable && key == jn.null_val) || key < jn.min_key || key > jn.max_key) { dropped = true; break; }
+      const int32_t* table = reinterpret_cast<const int32_t*>(args.join_hash_tables[j]);
+      const int64_t slot = key - jn.min_key;
+      if (jn.one_to_many) {
+        // offsets | counts | payload (JHT/PerfectJoinHashTable.cpp:861-886)
+        const int64_t E = p.join_entry_count[j];
+        const int32_t off = __ldg(table + slot);
+        if (off < 0) { dropped = true; break; }
+        n_matches = __ldg(table + E + slot);
+        match_ids = table + 2 * E + off;
+      } else {
+        const int32_t idx = __ldg(table + slot);
+        if (idx < 0) { dropped = true; break; }
+        rowid[j] = idx;
+      }
+    }
+  }
+  if (dropped) return;
+  for (int mi = 0; mi < n_matches; ++mi) {
+    if (match_ids) rowid[0] = __ldg(match_ids + mi);
+    for (int n = split; n < p.n_exprs; ++n) {
+      int32_t e = 0;
+      vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
+      if (e && !row_err) row_err = e;
+    }
+    bool pass = true;
+    for (int f = 0; f < p.n_filters; ++f) pass = pass && (vals[p.filters[f]].i > 0);
+    if (!pass) continue;
+    if (row_err) { my_err = my_err > 0 ? my_err : row_err; continue; }
+    if (kStrategy == HDK_B200_STRATEGY_BASELINE) { baseline_row(args, p, vals, my_err); continue; }
+    int64_t h = 0;
+    for (int k = 0; k < p.n_keys; ++k) {
+      const DKey& ky = p.keys[k];
+      int64_t v = vals[ky.expr].i;
+      if (ky.has_nulls && v == int_null_of(ky.width)) v = ky.null_translated;
+      h += (v - ky.min_val) * ky.mult;
+    }
+    const uint32_t idx = uint32_t(h);
+    if (idx >= p.entry_count) { my_err = my_err > 0 ? my_err : 1003; continue; }  // key outside the range the layout was built for
+    for (int a = 0; a < p.n_acc; ++a) {
+      const DAcc acc = p.accs[a];
+      if (acc_arg_is_null(p, acc, vals)) continue;
+      accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(p, acc, vals));
+    }
+  }
+}
+
+// ---- one row, compile-time plan structure ------------------------------------------------------
+// `raw` holds the row's column elements already fetched from the staged tile (see the tile loop).
+template <class Shape, int kStrategy>
+__device__ __forceinline__ void process_row_static(const ScanArgs& args, const uint64_t* raw, uint8_t* bins, int tid, int32_t& my_err) {
+  constexpr DPlan sp = Shape::get();
+  const DPlan& rp = args.plan;  // literals, key ranges, entry count
+  V vals[sp.n_exprs > 0 ? sp.n_exprs : 1];
+  int64_t rowid[HDK_B200_MAX_JOINS];
+  int32_t row_err = 0;
+  bool alive = true;
+  auto load_outer = [&](int c, int) -> uint64_t { return raw[c]; };
+  auto load_inner = [&](int j, int c, int w) -> uint64_t {
+    return alive ? ldg_elem(reinterpret_cast<const uint8_t*>(args.inner_col_buffers[j * HDK_B200_MAX_COLS + c]) + size_t(rowid[j]) * w, w) : 0;
+  };
+  static_for<0, sp.n_exprs>([&](auto I) {
+    constexpr int n = decltype(I)::value;
+    constexpr DPlan sp = Shape::get();  // (a captured constexpr object is not a constant expression inside the lambda)
+    DExpr e = sp.exprs[n];
+    if constexpr (sp.exprs[n].op == HDK_B200_OP_CONST) e.imm = rp.exprs[n].imm;  // literals are run-time; widths / units are structure
+    int32_t err = 0;
+    vals[n] = eval_node(sp, e, vals, err, load_outer, load_inner);
+    if (err && !row_err) row_err = err;
+    static_for<0, sp.n_joins>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      constexpr DPlan sp = Shape::get();
+      if constexpr (sp.joins[j].key_expr == n) {
+        const DJoin& jn = rp.joins[j];
+        const int64_t key = vals[n].i;
+        bool hit = alive && !((sp.joins[j].key_nullable && key == jn.null_val) || key < jn.min_key || key > jn.max_key);
+        int32_t idx = -1;
+        if (hit) idx = __ldg(reinterpret_cast<const int32_t*>(args.join_hash_tables[j]) + (key - jn.min_key));
+        alive = hit && idx >= 0;
+        rowid[j] = idx;
+      }
+    });
+  });
+  if (!alive) return;
+  bool pass = true;
+  static_for<0, sp.n_filters>([&](auto F) {
+    constexpr DPlan sp = Shape::get();
+    pass = pass && (vals[sp.filters[decltype(F)::value]].i > 0);
+  });
+  if (!pass) return;
+  if (row_err) { my_err = my_err > 0 ? my_err : row_err; return; }
+  int64_t h = 0;
+  static_for<0, sp.n_keys>([&](auto K) {
+    constexpr int k = decltype(K)::value;
+    constexpr DPlan sp = Shape::get();
+    const DKey& ky = rp.keys[k];
+    int64_t v = vals[sp.keys[k].expr].i;
+    if (sp.keys[k].has_nulls && v == int_null_of(sp.keys[k].width)) v = ky.null_translated;
+    if constexpr (k == 0) h = v - ky.min_val; else h += (v - ky.min_val) * ky.mult;
+  });
+  const uint32_t idx = uint32_t(h);
+  if (idx >= rp.entry_count) { my_err = my_err > 0 ? my_err : 1003; return; }
+  static_for<0, sp.n_acc>([&](auto A) {
+    constexpr int a = decltype(A)::value;
+    constexpr DPlan sp = Shape::get();
+    constexpr DAcc acc = sp.accs[a];
+    if (!acc_arg_is_null(sp, acc, vals)) accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(sp, acc, vals));
+  });
+}
+
+template <int kStrategy, class Shape>
 __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const __grid_constant__ ScanArgs args) {
   extern __shared__ __align__(128) uint8_t smem[];
   const DPlan& p = args.plan;
@@ -201,132 +415,37 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const __grid_constant
     }
   } else {
     // =============================== consumer warps ===============================
-    V vals[HDK_B200_MAX_EXPRS];
     int32_t my_err = 0;
     uint32_t it = 0;
     for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const uint32_t stage = it % kStages;
       mbar_wait(&full_bar[stage], (it / kStages) & 1);
       const uint32_t rows = hdr[stage].rows;
-      const uint32_t* col_off = hdr[stage].col_off;
-      for (uint32_t r = tid; r < rows; r += kConsumerThreads) {
-        int64_t rowid[HDK_B200_MAX_JOINS];
-        auto load_outer = [&](int c, int w) -> uint64_t {
-          const uint8_t* ptr = smem + col_off[c] + size_t(r) * w;
-          return w == 8 ? *reinterpret_cast<const uint64_t*>(ptr) : w == 4 ? uint64_t(*reinterpret_cast<const uint32_t*>(ptr))
-                 : w == 2 ? uint64_t(*reinterpret_cast<const uint16_t*>(ptr)) : uint64_t(*ptr);
-        };
-        auto load_inner = [&](int j, int c, int w) -> uint64_t {
-          const uint8_t* ptr = reinterpret_cast<const uint8_t*>(args.inner_col_buffers[j * HDK_B200_MAX_COLS + c]) + size_t(rowid[j]) * w;
-          return w == 8 ? __ldg(reinterpret_cast<const uint64_t*>(ptr)) : w == 4 ? uint64_t(__ldg(reinterpret_cast<const uint32_t*>(ptr)))
-                 : w == 2 ? uint64_t(__ldg(reinterpret_cast<const uint16_t*>(ptr))) : uint64_t(__ldg(ptr));
-        };
-        int32_t row_err = 0;
-        bool dropped = false;
-        // 1:N join: nodes up to the key are evaluated once, the rest once per match
-        int n_matches = 1;
-        const int32_t* match_ids = nullptr;
-        int split = p.n_exprs;
-        if (p.n_joins == 1 && p.joins[0].one_to_many) split = p.joins[0].key_expr + 1;
-        for (int n = 0; n < split && !dropped; ++n) {
-          int32_t e = 0;
-          vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
-          if (e && !row_err) row_err = e;
-          for (int j = 0; j < p.n_joins; ++j) {
-            const DJoin& jn = p.joins[j];
-            if (jn.key_expr != n) continue;
-            // hash_join_idx[_nullable] (QE/GroupByRuntime.cpp:298-329)
-            const int64_t key = vals[n].i;
-            if ((jn.key_nullable && key == jn.null_val) || key < jn.min_key || key > jn.max_key) { dropped = true; break; }
-            const int32_t* table = reinterpret_cast<const int32_t*>(args.join_hash_tables[j]);
-            const int64_t slot = key - jn.min_key;
-            if (jn.one_to_many) {
-              // offsets | counts | payload (JHT/PerfectJoinHashTable.cpp:861-886)
-              const int64_t E = p.join_entry_count[j];
-              const int32_t off = __ldg(table + slot);
-              if (off < 0) { dropped = true; break; }
-              n_matches = __ldg(table + E + slot);
-              match_ids = table + 2 * E + off;
-            } else {
-              const int32_t idx = __ldg(table + slot);
-              if (idx < 0) { dropped = true; break; }
-              rowid[j] = idx;
-            }
+      if constexpr (Shape::is_static) {
+        constexpr DPlan sp = Shape::get();
+        constexpr int R = Shape::rows_per_iter;
+        const uint8_t* cbase[sp.n_cols > 0 ? sp.n_cols : 1];
+        static_for<0, sp.n_cols>([&](auto Cc) { cbase[decltype(Cc)::value] = smem + hdr[stage].col_off[decltype(Cc)::value]; });
+        for (uint32_t r0 = tid; r0 < rows; r0 += kConsumerThreads * R) {
+          uint64_t raw[R][sp.n_cols > 0 ? sp.n_cols : 1];
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            const uint32_t r = r0 + u * kConsumerThreads;
+            static_for<0, sp.n_cols>([&](auto Cc) {
+              constexpr int c = decltype(Cc)::value;
+              constexpr DPlan sp = Shape::get();
+              constexpr int w = sp.col_width[c];
+              raw[u][c] = r < rows ? lds_elem(cbase[c] + size_t(r) * w, w) : 0;
+            });
           }
+#pragma unroll
+          for (int u = 0; u < R; ++u)
+            if (r0 + u * kConsumerThreads < rows) process_row_static<Shape, kStrategy>(args, raw[u], bins, tid, my_err);
         }
-        if (dropped) continue;
-        for (int mi = 0; mi < n_matches; ++mi) {
-          if (match_ids) rowid[0] = __ldg(match_ids + mi);
-          for (int n = split; n < p.n_exprs; ++n) {
-            int32_t e = 0;
-            vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
-            if (e && !row_err) row_err = e;
-          }
-          bool pass = true;
-          for (int f = 0; f < p.n_filters; ++f) pass = pass && (vals[p.filters[f]].i > 0);
-          if (!pass) continue;
-          if (row_err) { my_err = my_err > 0 ? my_err : row_err; continue; }
-          if (kStrategy == HDK_B200_STRATEGY_BASELINE) {
-            // baseline hash: find / claim the entry in the reference-encoded buffer, update slots in place
-            const DLayout& L = args.layout;
-            int8_t* buf = reinterpret_cast<int8_t*>(args.groupby_buf[0]);
-            int64_t keys[HDK_B200_MAX_KEYS];
-            for (int k = 0; k < p.n_keys; ++k) {
-              const int64_t v = vals[p.keys[k].expr].i;
-              keys[k] = L.key_width == 4 ? int64_t(int32_t(v)) : v;  // castToTypeIn(key, key_width * 8), no NULL translation
-            }
-            const uint32_t h0 = key_hash_dev(keys, p.n_keys, L.key_width) % p.entry_count;
-            const int64_t entry = L.columnar ? baseline_claim_columnar(reinterpret_cast<int64_t*>(buf), p.entry_count, keys, p.n_keys, h0)
-                                  : L.key_width == 4 ? baseline_claim_rowwise<int32_t>(buf, L.row_bytes, p.entry_count, keys, p.n_keys, h0)
-                                                     : baseline_claim_rowwise<int64_t>(buf, L.row_bytes, p.entry_count, keys, p.n_keys, h0);
-            if (entry < 0) { if (my_err <= 0) my_err = -HDK_B200_ERR_OUT_OF_SLOTS; continue; }
-            for (int s = 0; s < L.slot_count; ++s) {
-              const DSlot& sl = L.slots[s];
-              if (!sl.padded || sl.op == SLOT_KEY) continue;
-              int64_t vi = 0;
-              double vf = 0.0;
-              bool arg_null = false;
-              if (sl.arg >= 0) {
-                vi = vals[sl.arg].i;
-                vf = vals[sl.arg].f;
-                if (sl.arg_nullable) {
-                  arg_null = sl.arg_kind == HDK_B200_FP ? (vf == fp_null_of(sl.arg_width)) : (vi == int_null_of(sl.arg_width));
-                  if (sl.count_mode == 2 && int32_t(vi) == INT32_MIN) arg_null = true;
-                }
-              }
-              int8_t* ptr = L.columnar ? buf + sl.col_off + size_t(entry) * sl.padded
-                                       : buf + size_t(entry) * L.row_bytes + L.key_bytes + sl.off;
-              baseline_update_slot(sl, ptr, vi, vf, arg_null);
-            }
-            continue;
-          }
-          // perfect-hash slot: get_group_value_fast / perfect_key_hash (QE/GroupByRuntime.cpp:198-213,
-          // QE/RowFuncBuilder.cpp:748-801) incl. translate_null_key
-          uint32_t idx;
-          {
-            int64_t h = 0;
-            for (int k = 0; k < p.n_keys; ++k) {
-              const DKey& ky = p.keys[k];
-              int64_t v = vals[ky.expr].i;
-              if (ky.has_nulls && v == int_null_of(ky.width)) v = ky.null_translated;
-              h += (v - ky.min_val) * ky.mult;
-            }
-            idx = uint32_t(h);
-          }
-          if (idx >= p.entry_count) { my_err = my_err > 0 ? my_err : 1003; continue; }  // key outside the range the layout was built for
-          for (int a = 0; a < p.n_acc; ++a) {
-            const DAcc acc = p.accs[a];
-            if (acc_arg_is_null(p, acc, vals)) continue;
-            const int64_t x = acc_input(p, acc, vals);
-            if (kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE) {
-              bin_update_private(acc.kind, bins + args.acc_bin_off[a] + (size_t(idx) * kConsumerThreads + tid) * acc.bytes, x);
-            } else if (kStrategy == HDK_B200_STRATEGY_CTA_SHARED) {
-              bin_update_shared_atomic(acc.kind, bins + args.acc_bin_off[a] + size_t(idx) * acc.bytes, x);
-            } else {
-              cell_update_global(acc.kind, args.work_table + size_t(a) * p.entry_count + idx, x);
-            }
-          }
-        }
+      } else {
+        V vals[HDK_B200_MAX_EXPRS];
+        const uint32_t* col_off = hdr[stage].col_off;
+        for (uint32_t r = tid; r < rows; r += kConsumerThreads) process_row_generic<kStrategy>(args, smem, col_off, r, bins, tid, vals, my_err);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -388,6 +507,32 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const __grid_constant
     }
   }
 }
+
+// ---- pre-compiled plan shapes ------------------------------------------------------------------
+#define HB_STATIC_SHAPE(ID, SIG, NAME, RPI, ...)                                 \
+  template <>                                                                    \
+  struct StaticShape<ID> {                                                       \
+    static constexpr bool is_static = true;                                      \
+    static constexpr int rows_per_iter = RPI;                                    \
+    __host__ __device__ static constexpr DPlan get() { return DPlan __VA_ARGS__; } \
+  };
+#include "static_shapes.inc"
+#undef HB_STATIC_SHAPE
+
+typedef void (*ScanKernelFn)(const ScanArgs);
+struct StaticEntry {
+  uint64_t sig;
+  const char* name;
+  ScanKernelFn fn[3];  // THREAD_PRIVATE, CTA_SHARED, GLOBAL
+};
+#define HB_STATIC_SHAPE(ID, SIG, NAME, RPI, ...)                                                             \
+  {SIG, NAME, {scan_kernel<HDK_B200_STRATEGY_THREAD_PRIVATE, StaticShape<ID>>,                               \
+               scan_kernel<HDK_B200_STRATEGY_CTA_SHARED, StaticShape<ID>>,                                   \
+               scan_kernel<HDK_B200_STRATEGY_GLOBAL, StaticShape<ID>>}},
+static const StaticEntry kStaticShapes[] = {
+#include "static_shapes.inc"
+    {0, nullptr, {nullptr, nullptr, nullptr}}};
+#undef HB_STATIC_SHAPE
 
 // ---------------------------------------------------------------------------------------------
 // work table initialisation
@@ -488,15 +633,21 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
 
   int grid = sm_count();
   if (ko && ko->gridDimX) grid = int(ko->gridDimX);
-  void (*kern)(const ScanArgs) = strategy == HDK_B200_STRATEGY_THREAD_PRIVATE ? scan_kernel<HDK_B200_STRATEGY_THREAD_PRIVATE>
-                                 : strategy == HDK_B200_STRATEGY_CTA_SHARED   ? scan_kernel<HDK_B200_STRATEGY_CTA_SHARED>
-                                 : strategy == HDK_B200_STRATEGY_GLOBAL       ? scan_kernel<HDK_B200_STRATEGY_GLOBAL>
-                                                                              : scan_kernel<HDK_B200_STRATEGY_BASELINE>;
+  ScanKernelFn kern = strategy == HDK_B200_STRATEGY_THREAD_PRIVATE ? scan_kernel<HDK_B200_STRATEGY_THREAD_PRIVATE, GenericShape>
+                      : strategy == HDK_B200_STRATEGY_CTA_SHARED   ? scan_kernel<HDK_B200_STRATEGY_CTA_SHARED, GenericShape>
+                      : strategy == HDK_B200_STRATEGY_GLOBAL       ? scan_kernel<HDK_B200_STRATEGY_GLOBAL, GenericShape>
+                                                                   : scan_kernel<HDK_B200_STRATEGY_BASELINE, GenericShape>;
+  int variant = 0;
+  if (strategy != HDK_B200_STRATEGY_BASELINE && !(ko && ko->literalsOffset == 0xB200F0FFu)) {  // test hook: force the generic kernel
+    const uint64_t sig = plan_signature(p);
+    for (int i = 0; kStaticShapes[i].name; ++i)
+      if (kStaticShapes[i].sig == sig) { kern = kStaticShapes[i].fn[strategy]; variant = i + 1; break; }
+  }
   HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
   kern<<<grid, kThreads, smem_bytes, stream>>>(a);
   HB_LAUNCH_CHECK();
   if (info) {
-    info->variant = 0;
+    info->variant = variant;
     info->strategy = strategy;
     info->grid = grid;
     info->block = kThreads;

@@ -1,0 +1,91 @@
+"""Multi-GPU layer of the hot path: one process per GPU, torch.distributed (NCCL over NVLink 5 /
+NVSwitch; gloo on CPU for the host-logic tests).  HDK itself has none of this — fragments are all
+stamped with device 0 (omniscidb/ArrowStorage/ArrowStorage.cpp:365-367) and multi-device results
+are merged on the host (QE/Execute.cpp:1224-1336).  Three exchange patterns:
+
+  * perfect-hash group-by  : every rank scans its fragments into a NEUTRAL work table
+                             (hdk_b200_launch_partial) → all-reduce per merge class
+                             (int64 SUM | fp64 SUM | MIN | MAX) → hdk_b200_finalize
+  * baseline-hash group-by : rows are re-partitioned by MurmurHash64A(key) % world
+                             (hdk_b200_shuffle_count / _scatter, model: QE/RelAlgExecutor.cpp:691-838)
+                             → all-to-all → local aggregate; results are disjoint, no merge
+  * small join build side  : built once on rank 0, broadcast (table + inner columns)
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def is_dist() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def world() -> int:
+    return dist.get_world_size() if is_dist() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if is_dist() else 0
+
+
+def shard_fragments(n_fragments: int, r: Optional[int] = None, w: Optional[int] = None) -> List[int]:
+    """fragment i → rank i mod world (what upstream intended with Fragment::deviceIds)."""
+    r = rank() if r is None else r
+    w = world() if w is None else w
+    return [i for i in range(n_fragments) if i % w == r]
+
+
+def allreduce_work_table(work: torch.Tensor, n_cells: int, sum_i64_cells: int, sum_cells: int, min_cells: int,
+                         max_cells: int, group=None) -> None:
+    """In-place merge of a neutral work table (int64 view of the scratch buffer) across ranks.
+    Layout (hdk_b200_work_table_layout): [0, sum_i64) int64 SUM | [sum_i64, sum) fp64 SUM |
+    next min_cells int64 MIN (fp MIN is stored order-encoded) | last max_cells int64 MAX."""
+    if not is_dist() or world() == 1:
+        return
+    w = work.view(torch.int64)[:n_cells]
+    if sum_i64_cells:
+        dist.all_reduce(w[:sum_i64_cells], op=dist.ReduceOp.SUM, group=group)
+    if sum_cells > sum_i64_cells:
+        dist.all_reduce(w[sum_i64_cells:sum_cells].view(torch.float64), op=dist.ReduceOp.SUM, group=group)
+    if min_cells:
+        dist.all_reduce(w[sum_cells:sum_cells + min_cells], op=dist.ReduceOp.MIN, group=group)
+    if max_cells:
+        dist.all_reduce(w[sum_cells + min_cells:sum_cells + min_cells + max_cells], op=dist.ReduceOp.MAX, group=group)
+
+
+def all_to_all_rows(cols: List[torch.Tensor], send_counts: torch.Tensor, widths: List[int], group=None):
+    """Exchange partition-contiguous column buffers (output of hdk_b200_shuffle_scatter).
+    cols[c] is a uint8 tensor holding rows grouped by destination rank; send_counts[r] rows go to rank r.
+    Returns (received columns, rows received)."""
+    w = world()
+    send = send_counts.to(torch.int64)
+    recv = torch.empty_like(send)
+    if w > 1:
+        dist.all_to_all_single(recv, send, group=group)
+    else:
+        recv.copy_(send)
+    send_l, recv_l = send.tolist(), recv.tolist()
+    n_recv = int(sum(recv_l))
+    out = []
+    for c, width in zip(cols, widths):
+        dst = torch.empty(max(n_recv, 1) * width, dtype=torch.uint8, device=c.device)
+        if w > 1:
+            dist.all_to_all_single(dst[: n_recv * width], c[: int(sum(send_l)) * width],
+                                   output_split_sizes=[x * width for x in recv_l],
+                                   input_split_sizes=[x * width for x in send_l], group=group)
+        else:
+            dst[: n_recv * width].copy_(c[: n_recv * width])
+        out.append(dst)
+    return out, n_recv
+
+
+def broadcast_tensor(t: Optional[torch.Tensor], nbytes: int, device, src: int = 0, group=None) -> torch.Tensor:
+    """Broadcast a byte buffer (join hash table / dimension column) from `src` to every rank."""
+    if rank() != src or t is None:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    if is_dist() and world() > 1:
+        dist.broadcast(t, src=src, group=group)
+    return t

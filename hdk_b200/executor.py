@@ -41,13 +41,15 @@ def _torch():
 class DeviceContext:
     """Per-GPU state: chunk cache (DataMgr GPU level stand-in), scratch, stream."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, hot_data: bool = True):
         torch = _torch()
         self.torch = torch
         self.device = torch.device("cuda", device)
         self.index = device
         self.scratch = None
-        self._kp_cache = {}
+        self.hot_data = hot_data        # keep chunks resident between queries (USE_HOT_DATA in the reference's taxi bench)
+        self.h2d_bytes = 0              # bytes copied host → device by fetches (e2e accounting)
+        self._staging = {}
 
     def stream_ptr(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -57,12 +59,27 @@ class DeviceContext:
         return t.to(self.device, non_blocking=False)
 
     def chunk(self, frag, col: str):
-        """Executor::fetchChunks (QE/ExecutionKernel.cpp:205-228): chunk → device, cached ("hot")."""
+        """Executor::fetchChunks (QE/ExecutionKernel.cpp:205-228): chunk → device.  hot_data keeps the device
+        copy; otherwise every query copies the chunk again from (pinned) host memory into a reusable staging
+        buffer, like a cold DataMgr GPU level."""
         d = frag.device_chunks.get(col)
-        if d is None:
+        if d is not None:
+            return d
+        if self.hot_data:
             d = self.upload(frag.chunks[col])
             frag.device_chunks[col] = d
-        return d
+            return d
+        src = frag.pinned.get(col) if getattr(frag, "pinned", None) else None
+        if src is None:
+            src = self.torch.from_numpy(np.ascontiguousarray(frag.chunks[col]).view(np.uint8).reshape(-1).copy())
+        key = (frag.frag_id, col)
+        dst = self._staging.get(key)
+        if dst is None or dst.numel() != src.numel():
+            dst = self.torch.empty(src.numel(), dtype=self.torch.uint8, device=self.device)
+            self._staging[key] = dst
+        dst.copy_(src, non_blocking=True)
+        self.h2d_bytes += src.numel()
+        return dst
 
     def get_scratch(self, nbytes: int):
         if self.scratch is None or self.scratch.numel() < nbytes:
@@ -245,10 +262,11 @@ class ExecutionResult:
 class Executor:
     """One executor per process / GPU (Executor::getExecutor, QE/Execute.cpp:403)."""
 
-    def __init__(self, storage: ArrowStorage, config: Optional[planner.Config] = None, device: int = 0):
+    def __init__(self, storage: ArrowStorage, config: Optional[planner.Config] = None, device: int = 0,
+                 hot_data: bool = True):
         self.storage = storage
         self.config = config or planner.Config()
-        self.ctx = DeviceContext(device)
+        self.ctx = DeviceContext(device, hot_data)
         self.lib = _lib.lib()
         self.join_tables: Dict[tuple, JoinTable] = {}
         self.last_launch_info = None
@@ -384,6 +402,39 @@ class Executor:
                                             C.byref(prep["kp"]), prep["scratch"].data_ptr(), prep["scratch_bytes"], st,
                                             C.byref(info)), "launch")
         self.last_launch_info = info
+        return info
+
+    # -- multi-GPU split of the perfect-hash launch ------------------------------------
+    def work_table_layout(self, pq: planner.PlannedQuery) -> abi.WorkTableLayout:
+        wl = abi.WorkTableLayout()
+        _lib.check(self.lib.hdk_b200_work_table_layout_get(C.byref(pq.plan), C.byref(pq.qmd), C.byref(wl)), "work_table_layout")
+        return wl
+
+    def launch_partial(self, pq: planner.PlannedQuery, prep, ko: Optional[abi.KernelOptions] = None):
+        """scan this rank's fragments into the neutral work table (asynchronous)."""
+        st = self.ctx.stream_ptr()
+        info = abi.LaunchInfo()
+        prep["err"].zero_()
+        _lib.check(self.lib.hdk_b200_init_work_table(C.byref(pq.plan), C.byref(pq.qmd), prep["scratch"].data_ptr(), st), "init_work_table")
+        _lib.check(self.lib.hdk_b200_launch_partial(C.byref(pq.plan), C.byref(pq.qmd), C.byref(ko) if ko is not None else None,
+                                                    C.byref(prep["kp"]), prep["scratch"].data_ptr(), st, C.byref(info)), "launch_partial")
+        self.last_launch_info = info
+        return info
+
+    def finalize(self, pq: planner.PlannedQuery, prep):
+        _lib.check(self.lib.hdk_b200_finalize(C.byref(pq.plan), C.byref(pq.qmd), prep["scratch"].data_ptr(),
+                                              prep["out"].data_ptr(), self.ctx.stream_ptr()), "finalize")
+
+    def execute_sharded(self, pq: planner.PlannedQuery, prep, group=None):
+        """perfect hash across ranks: partial scan → NCCL all-reduce per merge class → finalize."""
+        from . import distributed as D
+        info = self.launch_partial(pq, prep)
+        wl = self.work_table_layout(pq)
+        D.allreduce_work_table(prep["scratch"], wl.n_cells, wl.sum_i64_cells, wl.sum_cells, wl.min_cells, wl.max_cells, group)
+        if D.is_dist() and D.world() > 1:
+            import torch.distributed as dist
+            dist.all_reduce(prep["err"], op=dist.ReduceOp.MAX, group=group)   # a positive (persistent) code wins
+        self.finalize(pq, prep)
         return info
 
     def execute_work_unit(self, unit: ir.ExecutionUnit, output_columnar=None, ko=None) -> ResultSet:

@@ -1,0 +1,67 @@
+"""The pre-compiled plan shapes (static_shapes.inc) on the benchmark's own generators at reduced size:
+every named config must (a) dispatch to its pre-compiled kernel, (b) match the CPU oracle, (c) match the
+generic (interpreting) kernel bit for bit on integer results."""
+import numpy as np
+import pytest
+
+from hdk_b200 import abi
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_frs(oracle, st, pq):
+    return util.oracle_inputs(oracle, st, pq)
+
+
+CASES = [
+    ("taxi_q1", "taxi", "q1", 1), ("taxi_q2", "taxi", "q2", 1), ("taxi_q3", "taxi", "q3", 2), ("taxi_q4", "taxi", "q4", 3),
+    ("c1_int64", "c1", "int", 1), ("c1_fp64", "c1", "fp", 1), ("tpch_q1", "lineitem", None, 2), ("star_join_sum", "star", None, 1),
+]
+
+
+@pytest.mark.parametrize("name,kind,sub,nk", CASES)
+def test_static_shape_parity(oracle_mod, name, kind, sub, nk):
+    import torch
+    import benchdata
+    from hdk_b200 import sql
+    from hdk_b200.executor import Executor
+    from hdk_b200.storage import ArrowStorage
+    dev = torch.device("cuda", 0)
+    st = ArrowStorage()
+    if kind == "taxi":
+        benchdata.make_taxi(st, dev, 300_007, fragment_rows=70_001, keep_host=True)
+        text = benchdata.TAXI_QUERIES[sub].split(" ORDER BY")[0]
+    elif kind == "c1":
+        benchdata.make_c1(st, dev, rows=250_003, fragment_rows=62_501, keep_host=True)
+        text = benchdata.C1_QUERY if sub == "int" else benchdata.C1_QUERY_F
+    elif kind == "lineitem":
+        benchdata.make_lineitem(st, dev, 200_003, fragment_rows=50_001, keep_host=True)
+        text = benchdata.TPCH_Q1
+    else:
+        benchdata.make_star(st, dev, 300_007, 5_000, fragment_rows=70_001, keep_host=True)
+        text = benchdata.C5_QUERY
+    ex = Executor(st)
+    unit = sql.parse(text, st.tables)
+    pq = ex.plan(unit)
+    prep = ex.prepare(pq)
+    info = ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    assert info.variant > 0, f"{name}: expected a pre-compiled kernel, ran the generic one"
+    got = prep["out"].cpu().numpy().copy()
+    # the same plan on the generic kernel
+    ko = abi.KernelOptions()
+    ko.literalsOffset = 0xB200F0FF
+    info2 = ex.launch(pq, prep, ko)
+    torch.cuda.synchronize()
+    assert info2.variant == 0
+    gen = prep["out"].cpu().numpy().copy()
+    obuf, oerr = util.run_oracle(oracle_mod, st, pq, n_threads=4)
+    assert oerr == 0
+    exp = util.sort_rows(util.result_columns(oracle_mod, pq, obuf), nk)
+    util.assert_rows_equal(util.sort_rows(util.result_columns(oracle_mod, pq, got), nk), exp)
+    util.assert_rows_equal(util.sort_rows(util.result_columns(oracle_mod, pq, gen), nk), exp)
+    has_fp_sum = any(ti.agg in (abi.AGG_SUM, abi.AGG_AVG) and ti.arg_type is not None and ti.arg_type.is_fp for ti in pq.infos)
+    if not has_fp_sum:
+        assert np.array_equal(got, obuf) and np.array_equal(gen, obuf)
