@@ -120,6 +120,36 @@ __device__ __forceinline__ uint64_t lds_elem(const uint8_t* ptr, int w) {
   return w == 8 ? *reinterpret_cast<const uint64_t*>(ptr) : w == 4 ? uint64_t(*reinterpret_cast<const uint32_t*>(ptr))
          : w == 2 ? uint64_t(*reinterpret_cast<const uint16_t*>(ptr)) : uint64_t(*ptr);
 }
+// one <= 16-byte shared-memory load holding several consecutive elements of a column, and element extraction
+template <int BYTES>
+__device__ __forceinline__ void lds_vec(const uint8_t* p, uint32_t* words) {
+  if constexpr (BYTES == 16) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    words[0] = t.x; words[1] = t.y; words[2] = t.z; words[3] = t.w;
+  } else if constexpr (BYTES == 8) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    words[0] = t.x; words[1] = t.y;
+  } else if constexpr (BYTES == 4) {
+    words[0] = *reinterpret_cast<const uint32_t*>(p);
+  } else if constexpr (BYTES == 2) {
+    words[0] = *reinterpret_cast<const uint16_t*>(p);
+  } else {
+    words[0] = *p;
+  }
+}
+template <int W>
+__device__ __forceinline__ uint64_t vec_elem(const uint32_t* words, int v) {
+  if constexpr (W == 8) return uint64_t(words[2 * v]) | (uint64_t(words[2 * v + 1]) << 32);
+  else if constexpr (W == 4) return words[v];
+  else if constexpr (W == 2) return (words[v / 2] >> (16 * (v % 2))) & 0xffffu;
+  else return (words[v / 4] >> (8 * (v % 4))) & 0xffu;
+}
+__host__ __device__ constexpr int shape_max_width(const DPlan& p) {
+  int m = 1;
+  for (int c = 0; c < p.n_cols; ++c) m = p.col_width[c] > m ? p.col_width[c] : m;
+  return m;
+}
+
 __device__ __forceinline__ uint64_t ldg_elem(const uint8_t* ptr, int w) {
   return w == 8 ? __ldg(reinterpret_cast<const uint64_t*>(ptr)) : w == 4 ? uint64_t(__ldg(reinterpret_cast<const uint32_t*>(ptr)))
          : w == 2 ? uint64_t(__ldg(reinterpret_cast<const uint16_t*>(ptr))) : uint64_t(__ldg(ptr));
@@ -239,7 +269,10 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
     if (idx >= p.entry_count) { my_err = my_err > 0 ? my_err : 1003; continue; }  // key outside the range the layout was built for
     for (int a = 0; a < p.n_acc; ++a) {
       const DAcc acc = p.accs[a];
-      if (acc_arg_is_null(p, acc, vals)) continue;
+      // shared-memory bins of a CNT_NN accumulator count the NULL rows (rare) instead of the non-NULL ones;
+      // the flush converts: non-null = rows - nulls.  The global work table always holds non-null counts.
+      const bool count_nulls = acc.kind == ACC_CNT_NN && kStrategy != HDK_B200_STRATEGY_GLOBAL;
+      if (acc_arg_is_null(p, acc, vals) != count_nulls) continue;
       accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(p, acc, vals));
     }
   }
@@ -304,12 +337,13 @@ __device__ __forceinline__ void process_row_static(const ScanArgs& args, const u
     constexpr int a = decltype(A)::value;
     constexpr DPlan sp = Shape::get();
     constexpr DAcc acc = sp.accs[a];
-    if (!acc_arg_is_null(sp, acc, vals)) accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(sp, acc, vals));
+    constexpr bool count_nulls = acc.kind == ACC_CNT_NN && kStrategy != HDK_B200_STRATEGY_GLOBAL;
+    if (acc_arg_is_null(sp, acc, vals) == count_nulls) accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(sp, acc, vals));
   });
 }
 
 template <int kStrategy, class Shape>
-__global__ void __launch_bounds__(kThreads, 1) scan_kernel(const __grid_constant__ ScanArgs args) {
+__global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant__ ScanArgs args) {
   extern __shared__ __align__(128) uint8_t smem[];
   const DPlan& p = args.plan;
   const int tid = threadIdx.x;
@@ -324,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const __grid_constant
 
   // ---- prologue: barriers, tile prefix, bins
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {  // (all kStages barriers are initialised; args.n_stages of them are used)
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kConsumerWarps);
     }
@@ -368,79 +402,118 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const __grid_constant
 
   if (is_producer) {
     // =============================== producer warp ===============================
+    // Lane c owns column c: it keeps the current fragment's chunk pointer in a register (re-read only when
+    // the tile walk enters a new fragment), patches its own head / tail bytes and issues its own bulk copy,
+    // so a tile costs one short pass without dependent global loads.
     const uint64_t policy = policy_evict_first();
-    uint32_t it = 0;
-    uint32_t frag = 0;
+    const int c = lane;
+    const bool has_col = c < p.n_cols;
+    const uint32_t w = has_col ? p.col_width[c] : 0;
+    const uint32_t region_off = has_col ? args.col_region_off[c] : 0;
+    uint32_t it = 0, frag = 0, cur_frag = 0xffffffffu;
+    const uint8_t* col_base = nullptr;
+    uint64_t frag_rows = 0;
     for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const uint32_t stage = it % kStages;
-      const uint32_t round = it / kStages;
+      const uint32_t stage = it % args.n_stages;
+      const uint32_t round = it / args.n_stages;
       if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1);
       while (tile_prefix[frag + 1] <= t) ++frag;  // tiles are visited in increasing order
+      if (frag != cur_frag) {
+        cur_frag = frag;
+        frag_rows = uint64_t(args.num_rows[frag]);
+        if (has_col) col_base = reinterpret_cast<const uint8_t*>(args.col_buffers[size_t(frag) * p.n_cols + c]);
+      }
       const uint64_t row0 = uint64_t(t - tile_prefix[frag]) * args.tile_rows;
-      const uint64_t frag_rows = uint64_t(args.num_rows[frag]);
       const uint32_t rows = uint32_t(min(uint64_t(args.tile_rows), frag_rows - row0));
       uint8_t* stage_base = smem + args.off_stages + size_t(stage) * args.stage_bytes;
-      uint32_t tx_bytes = 0;
-      // pass 1: heads / tails by byte copies (generic proxy), header, tx byte count
-      for (int c = 0; c < p.n_cols; ++c) {
-        const uint32_t w = p.col_width[c];
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(args.col_buffers[size_t(frag) * p.n_cols + c]) + row0 * w;
+      uint32_t mid = 0, head = 0, m = 0;
+      const uint8_t* src = nullptr;
+      if (has_col) {
+        src = col_base + row0 * w;
         const uint32_t bytes = rows * w;
-        const uint32_t m = uint32_t(reinterpret_cast<uintptr_t>(src) & 15u);
-        const uint32_t head = m ? min(16u - m, bytes) : 0u;
-        const uint32_t mid = (bytes - head) & ~15u;
+        m = uint32_t(reinterpret_cast<uintptr_t>(src) & 15u);
+        head = m ? min(16u - m, bytes) : 0u;
+        mid = (bytes - head) & ~15u;
         const uint32_t tail = bytes - head - mid;
-        uint8_t* region = stage_base + args.col_region_off[c];
-        uint8_t* dst = region + m;
-        for (uint32_t i = lane; i < head; i += 32) dst[i] = src[i];
-        for (uint32_t i = lane; i < tail; i += 32) dst[head + mid + i] = src[head + mid + i];
-        tx_bytes += mid;
-        if (lane == 0) hdr[stage].col_off[c] = uint32_t(dst - smem);
+        uint8_t* dst = stage_base + region_off + m;
+        for (uint32_t i = 0; i < head; ++i) dst[i] = src[i];                          // generic-proxy byte patches
+        for (uint32_t i = 0; i < tail; ++i) dst[head + mid + i] = src[head + mid + i];
+        hdr[stage].col_off[c] = uint32_t(dst - smem);
       }
+      uint32_t tx_bytes = mid;
+      for (int d = 16; d; d >>= 1) tx_bytes += __shfl_xor_sync(0xffffffffu, tx_bytes, d);
       if (lane == 0) hdr[stage].rows = rows;
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-        for (int c = 0; c < p.n_cols; ++c) {
-          const uint32_t w = p.col_width[c];
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(args.col_buffers[size_t(frag) * p.n_cols + c]) + row0 * w;
-          const uint32_t bytes = rows * w;
-          const uint32_t m = uint32_t(reinterpret_cast<uintptr_t>(src) & 15u);
-          const uint32_t head = m ? min(16u - m, bytes) : 0u;
-          const uint32_t mid = (bytes - head) & ~15u;
-          if (mid) bulk_g2s(stage_base + args.col_region_off[c] + m + head, src + head, mid, &full_bar[stage], policy);
-        }
-      }
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
       __syncwarp();
+      if (mid) bulk_g2s(stage_base + region_off + m + head, src + head, mid, &full_bar[stage], policy);
     }
   } else {
     // =============================== consumer warps ===============================
     int32_t my_err = 0;
     uint32_t it = 0;
     for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const uint32_t stage = it % kStages;
-      mbar_wait(&full_bar[stage], (it / kStages) & 1);
+      const uint32_t stage = it % args.n_stages;
+      mbar_wait(&full_bar[stage], (it / args.n_stages) & 1);
       const uint32_t rows = hdr[stage].rows;
       if constexpr (Shape::is_static) {
         constexpr DPlan sp = Shape::get();
         constexpr int R = Shape::rows_per_iter;
-        const uint8_t* cbase[sp.n_cols > 0 ? sp.n_cols : 1];
-        static_for<0, sp.n_cols>([&](auto Cc) { cbase[decltype(Cc)::value] = smem + hdr[stage].col_off[decltype(Cc)::value]; });
-        for (uint32_t r0 = tid; r0 < rows; r0 += kConsumerThreads * R) {
-          uint64_t raw[R][sp.n_cols > 0 ? sp.n_cols : 1];
+        constexpr int VW = 16 / shape_max_width(sp);      // consecutive rows a lane takes with one <= 16-byte load per column
+        constexpr int U = R / VW > 0 ? R / VW : 1;        // vector groups per thread per iteration
+        constexpr int NC = sp.n_cols > 0 ? sp.n_cols : 1;
+        const uint8_t* cbase[NC];
+        bool vec_ok = (rows % VW) == 0;
+        static_for<0, sp.n_cols>([&](auto Cc) {
+          constexpr int c = decltype(Cc)::value;
+          constexpr DPlan sp = Shape::get();
+          const uint32_t off = hdr[stage].col_off[c];
+          cbase[c] = smem + off;
+          vec_ok = vec_ok && (off % (VW * sp.col_width[c])) == 0;
+        });
+        if (vec_ok) {
+          // fast path (every tile but a fragment's last, 16-byte aligned chunks): vector loads, no per-row bounds checks
+          const uint32_t n_groups = rows / VW;
+          for (uint32_t g0 = tid; g0 < n_groups; g0 += kConsumerThreads * U) {
+            uint32_t words[U][NC][4];
 #pragma unroll
-          for (int u = 0; u < R; ++u) {
-            const uint32_t r = r0 + u * kConsumerThreads;
+            for (int u = 0; u < U; ++u) {
+              const uint32_t g = g0 + u * kConsumerThreads;
+              if (g < n_groups)
+                static_for<0, sp.n_cols>([&](auto Cc) {
+                  constexpr int c = decltype(Cc)::value;
+                  constexpr DPlan sp = Shape::get();
+                  constexpr int w = sp.col_width[c];
+                  lds_vec<VW * w>(cbase[c] + size_t(g) * (VW * w), words[u][c]);
+                });
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (g0 + u * kConsumerThreads < n_groups) {
+#pragma unroll
+                for (int v = 0; v < VW; ++v) {
+                  uint64_t raw[NC];
+                  static_for<0, sp.n_cols>([&](auto Cc) {
+                    constexpr int c = decltype(Cc)::value;
+                    constexpr DPlan sp = Shape::get();
+                    raw[c] = vec_elem<sp.col_width[c]>(words[u][c], v);
+                  });
+                  process_row_static<Shape, kStrategy>(args, raw, bins, tid, my_err);
+                }
+              }
+            }
+          }
+        } else {
+          for (uint32_t r = tid; r < rows; r += kConsumerThreads) {
+            uint64_t raw[NC];
             static_for<0, sp.n_cols>([&](auto Cc) {
               constexpr int c = decltype(Cc)::value;
               constexpr DPlan sp = Shape::get();
               constexpr int w = sp.col_width[c];
-              raw[u][c] = r < rows ? lds_elem(cbase[c] + size_t(r) * w, w) : 0;
+              raw[c] = lds_elem(cbase[c] + size_t(r) * w, w);
             });
+            process_row_static<Shape, kStrategy>(args, raw, bins, tid, my_err);
           }
-#pragma unroll
-          for (int u = 0; u < R; ++u)
-            if (r0 + u * kConsumerThreads < rows) process_row_static<Shape, kStrategy>(args, raw[u], bins, tid, my_err);
         }
       } else {
         V vals[HDK_B200_MAX_EXPRS];
@@ -466,6 +539,12 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const __grid_constant
           if (acc.bytes == 4) {
             uint64_t s = 0;
             for (int i = lane; i < kConsumerThreads; i += 32) s += reinterpret_cast<const uint32_t*>(base)[i];
+            if (acc.kind == ACC_CNT_NN) {  // bins hold NULL counts: non-null = rows (accumulator 0) - nulls
+              const uint8_t* rows_base = bins + args.acc_bin_off[0] + size_t(g) * kConsumerThreads * 4;
+              uint64_t rws = 0;
+              for (int i = lane; i < kConsumerThreads; i += 32) rws += reinterpret_cast<const uint32_t*>(rows_base)[i];
+              s = rws - s;
+            }
             for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
             x = int64_t(s);
           } else if (acc.kind == ACC_SUM_I) {
@@ -499,7 +578,8 @@ __global__ void __launch_bounds__(kThreads, 1) scan_kernel(const __grid_constant
           const DAcc acc = p.accs[a];
           const uint8_t* base = bins + args.acc_bin_off[a];
           for (uint32_t g = tid; g < p.entry_count; g += kConsumerThreads) {
-            const int64_t x = acc.bytes == 4 ? int64_t(reinterpret_cast<const uint32_t*>(base)[g]) : reinterpret_cast<const int64_t*>(base)[g];
+            int64_t x = acc.bytes == 4 ? int64_t(reinterpret_cast<const uint32_t*>(base)[g]) : reinterpret_cast<const int64_t*>(base)[g];
+            if (acc.kind == ACC_CNT_NN) x = int64_t(reinterpret_cast<const uint32_t*>(bins + args.acc_bin_off[0])[g]) - x;
             if (x != acc_identity(acc.kind)) cell_update_global(acc.kind, args.work_table + size_t(a) * p.entry_count + g, x);
           }
         }
@@ -584,25 +664,33 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   size_t off = 128 + align_up(sizeof(StageHeader) * kStages, 16);
   a.off_tile_prefix = uint32_t(off);
   off += align_up(size_t(a.num_fragments + 1) * 4, 16);
+  const size_t fixed_bytes = align_up(off, 16);
 
-  // accumulator bins: pick the cheapest strategy that fits
+  // accumulator bins: pick the cheapest strategy that fits.  THREAD_PRIVATE needs one copy per consumer
+  // thread; CTA_SHARED one copy per CTA (native shared atomics for counters, CAS loops for 64-bit ops).
   const size_t E = p.entry_count;
   size_t per_group_bytes = 0;
-  for (int i = 0; i < p.n_acc; ++i) per_group_bytes += p.accs[i].bytes;
-  const size_t private_bytes = per_group_bytes * E * kConsumerThreads;
+  bool counters_only = true;
+  for (int i = 0; i < p.n_acc; ++i) {
+    per_group_bytes += p.accs[i].bytes;
+    counters_only = counters_only && p.accs[i].bytes == 4;
+  }
+  const size_t private_bytes = per_group_bytes * E * kConsumerThreads + 16 * size_t(p.n_acc);
   const size_t shared_bytes = align_up(per_group_bytes * E, 16) + 16 * size_t(p.n_acc);
-  const size_t min_stage_budget = 3 * 4096 + 2048;
+  const size_t row_bytes = std::max<size_t>(lw.stage_row_bytes, 1);
+  const size_t min_ring = kStages * (size_t(kConsumerThreads) * row_bytes + 48 * size_t(p.n_cols) + 128);  // one row per thread per tile
+  const size_t half_sm = (size_t(max_smem) - 2048) / 2;   // budget that still lets two CTAs share an SM
   int strategy;
-  if (off + private_bytes + min_stage_budget * 2 <= size_t(max_smem) && private_bytes <= 144 * 1024) strategy = HDK_B200_STRATEGY_THREAD_PRIVATE;
-  else if (off + shared_bytes + min_stage_budget * 2 <= size_t(max_smem)) strategy = HDK_B200_STRATEGY_CTA_SHARED;
-  else strategy = HDK_B200_STRATEGY_GLOBAL;
-  if (ko && ko->sharedMemBytes == 0xB200F001u) strategy = HDK_B200_STRATEGY_THREAD_PRIVATE;  // test hooks: force a strategy
-  if (ko && ko->sharedMemBytes == 0xB200F002u) strategy = HDK_B200_STRATEGY_CTA_SHARED;
-  if (ko && ko->sharedMemBytes == 0xB200F003u) strategy = HDK_B200_STRATEGY_GLOBAL;
   if (baseline) strategy = HDK_B200_STRATEGY_BASELINE;
+  else if (counters_only && E >= 32 && fixed_bytes + shared_bytes + 4 * min_ring <= half_sm) strategy = HDK_B200_STRATEGY_CTA_SHARED;
+  else if (fixed_bytes + private_bytes + min_ring <= size_t(max_smem)) strategy = HDK_B200_STRATEGY_THREAD_PRIVATE;
+  else if (fixed_bytes + shared_bytes + min_ring <= size_t(max_smem)) strategy = HDK_B200_STRATEGY_CTA_SHARED;
+  else strategy = HDK_B200_STRATEGY_GLOBAL;
+  if (!baseline && ko && ko->sharedMemBytes == 0xB200F001u) strategy = HDK_B200_STRATEGY_THREAD_PRIVATE;  // test hooks: force a strategy
+  if (!baseline && ko && ko->sharedMemBytes == 0xB200F002u) strategy = HDK_B200_STRATEGY_CTA_SHARED;
+  if (!baseline && ko && ko->sharedMemBytes == 0xB200F003u) strategy = HDK_B200_STRATEGY_GLOBAL;
 
-  off = align_up(off, 16);
-  a.off_bins = uint32_t(off);
+  a.off_bins = uint32_t(fixed_bytes);
   size_t bins_bytes = 0;
   for (int i = 0; i < p.n_acc; ++i) {
     bins_bytes = align_up(bins_bytes, 16);
@@ -611,16 +699,32 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
     else if (strategy == HDK_B200_STRATEGY_CTA_SHARED) bins_bytes += size_t(p.accs[i].bytes) * E;
   }
   if (strategy == HDK_B200_STRATEGY_GLOBAL || strategy == HDK_B200_STRATEGY_BASELINE) bins_bytes = 0;
-  off += align_up(bins_bytes, 128);
-  if (off + min_stage_budget > size_t(max_smem)) { set_error("forced strategy does not fit in shared memory"); return HDK_B200_E_UNSUPPORTED; }
-  a.off_stages = uint32_t(align_up(off, 128));
+  a.off_stages = uint32_t(align_up(fixed_bytes + bins_bytes, 128));
+  if (a.off_stages + min_ring > size_t(max_smem)) { set_error("forced strategy does not fit in shared memory"); return HDK_B200_E_UNSUPPORTED; }
 
-  // stage geometry: tile_rows is a power of two ≥ kConsumerThreads, stage ≤ ~24 KB and the ring fits
-  const size_t row_bytes = std::max<size_t>(lw.stage_row_bytes, 1);
-  const size_t avail = size_t(max_smem) - a.off_stages;
-  size_t per_stage = std::min<size_t>(avail / kStages, 28 * 1024);
-  uint32_t tile_rows = 64;
-  while (size_t(tile_rows) * 2 * row_bytes + 48 * size_t(p.n_cols) <= per_stage && tile_rows < 8192) tile_rows *= 2;
+  // stage geometry: search (CTAs per SM, ring depth) for the configuration with the most resident warps
+  // that still gives every consumer thread >= 4 (then >= 2, then >= 1) rows per tile.  tile_rows is a
+  // power of two; a stage holds at most 32 KB.
+  auto max_tile = [&](size_t budget, int stages) -> uint32_t {
+    const size_t avail = budget > a.off_stages ? budget - a.off_stages : 0;
+    const size_t per_stage = std::min<size_t>(avail / stages, 32 * 1024);
+    uint32_t tr = 0;
+    for (uint32_t cand = kConsumerThreads; cand <= 16384; cand *= 2)
+      if (align_up(size_t(cand) * row_bytes + 48 * size_t(p.n_cols), 128) <= per_stage) tr = cand;
+    return tr;
+  };
+  uint32_t tile_rows = 0;
+  int ctas_per_sm = 1, n_stages = kStages;
+  auto try_cfg = [&](int ctas, int want) {
+    for (int stages = kStages; stages >= 3 && !tile_rows; --stages) {
+      const uint32_t tr = max_tile(ctas == 2 ? half_sm : size_t(max_smem), stages);
+      if (tr >= uint32_t(kConsumerThreads) * want) { tile_rows = tr; ctas_per_sm = ctas; n_stages = stages; }
+    }
+  };
+  const int order[6][2] = {{2, 4}, {2, 2}, {1, 4}, {1, 2}, {2, 1}, {1, 1}};
+  for (int i = 0; i < 6 && !tile_rows; ++i) try_cfg(order[i][0], order[i][1]);
+  if (!tile_rows) { set_error("stage ring does not fit in shared memory"); return HDK_B200_E_UNSUPPORTED; }
+  a.n_stages = uint32_t(n_stages);
   a.tile_rows = tile_rows;
   size_t so = 0;
   for (int c = 0; c < p.n_cols; ++c) {
@@ -628,10 +732,10 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
     so += align_up(size_t(tile_rows) * p.col_width[c] + 32, 16);  // +16 for the alignment shift, +16 slack
   }
   a.stage_bytes = uint32_t(align_up(so, 128));
-  const size_t smem_bytes = a.off_stages + size_t(a.stage_bytes) * kStages;
+  const size_t smem_bytes = a.off_stages + size_t(a.stage_bytes) * n_stages;
   if (smem_bytes > size_t(max_smem)) { set_error("stage ring does not fit in shared memory (%zu > %d)", smem_bytes, max_smem); return HDK_B200_E_UNSUPPORTED; }
 
-  int grid = sm_count();
+  int grid = sm_count() * ctas_per_sm;
   if (ko && ko->gridDimX) grid = int(ko->gridDimX);
   ScanKernelFn kern = strategy == HDK_B200_STRATEGY_THREAD_PRIVATE ? scan_kernel<HDK_B200_STRATEGY_THREAD_PRIVATE, GenericShape>
                       : strategy == HDK_B200_STRATEGY_CTA_SHARED   ? scan_kernel<HDK_B200_STRATEGY_CTA_SHARED, GenericShape>

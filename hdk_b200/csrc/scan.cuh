@@ -4,7 +4,7 @@
 
 namespace hb {
 
-constexpr int kConsumerWarps = 8;
+constexpr int kConsumerWarps = 16;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;  // + one TMA producer warp
 constexpr int kStages = 4;
@@ -27,6 +27,7 @@ struct ScanArgs {
   uint32_t num_fragments;
   uint32_t tile_rows;
   uint32_t stage_bytes;
+  uint32_t n_stages;                  // ring depth actually used (<= kStages)
   uint32_t off_tile_prefix, off_bins, off_stages;   // dynamic shared memory map
   uint32_t acc_bin_off[kMaxAcc];                    // from off_bins
   uint32_t col_region_off[HDK_B200_MAX_COLS];       // from a stage's base
