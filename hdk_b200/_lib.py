@@ -7,7 +7,7 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libhdk_b200.so")
+LIB_PATH = os.environ.get("HDK_B200_LIB") or os.path.join(_HERE, "csrc", "libhdk_b200.so")   # (override: A/B builds while tuning)
 _lib = None
 
 

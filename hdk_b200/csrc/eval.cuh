@@ -126,7 +126,19 @@ __device__ __forceinline__ V eval_node(const DPlan& p, const DExpr& e, const V* 
       const DExpr& ta = p.exprs[e.a];
       int64_t t = vals[e.a].i;
       if (ta.nullable && t == int_null_of(ta.width)) { r = v_null(e); break; }
-      if (e.imm.i > 1) t = ta.nullable ? ((t < 0 ? t - (e.imm.i - 1) : t) / e.imm.i) : t / e.imm.i;  // QE/DateTimeIR.cpp:314-320
+      const int64_t units = e.imm.i;
+      // Fast path: the whole computation in 32 bits when the time lies in extract_year's own fast range
+      // [0, 2^32 - 2208988800) s (ExtractFromTime.cpp:262).  For second / millisecond units the division by
+      // `units` is done in fp64: t < 2^41 is exact, the quotient's fractional part is a multiple of 1/units
+      // >= 1e-3, and the product's error is < 1e-6, so adding half a step and truncating is exact.
+      if (units <= 1000 && t >= 0 && t < int64_t(2085978496) * units) {
+        const uint32_t secs = units == 1 ? uint32_t(t) : uint32_t(__double2uint_rz(fma(double(t), 1.0 / double(units), 0.5 / double(units))));
+        const uint32_t s1900 = secs + 2208988800u;
+        const uint32_t leap = (s1900 - 5097600u) / 126230400u;
+        r.i = (s1900 - leap * 86400u) / 31536000u + 1900;
+        break;
+      }
+      if (units > 1) t = ta.nullable ? ((t < 0 ? t - (units - 1) : t) / units) : t / units;  // QE/DateTimeIR.cpp:314-320
       r.i = dev_extract_year(t);
       break;
     }

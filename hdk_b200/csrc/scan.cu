@@ -161,7 +161,7 @@ template <int kStrategy>
 __device__ __forceinline__ void accumulate_one(const ScanArgs& args, uint8_t* bins, int tid, int a, const DAcc acc, uint32_t idx,
                                                int64_t x) {
   if (kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE) {
-    bin_update_private(acc.kind, bins + args.acc_bin_off[a] + (size_t(idx) * kConsumerThreads + tid) * acc.bytes, x);
+    bin_update_private(acc.kind, bins + args.acc_bin_off[a] + (idx * args.consumer_threads + uint32_t(tid)) * acc.bytes, x);
   } else if (kStrategy == HDK_B200_STRATEGY_CTA_SHARED) {
     bin_update_shared_atomic(acc.kind, bins + args.acc_bin_off[a] + size_t(idx) * acc.bytes, x);
   } else {
@@ -279,12 +279,13 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
 }
 
 // ---- one row, compile-time plan structure ------------------------------------------------------
-// `raw` holds the row's column elements already fetched from the staged tile (see the tile loop).
-template <class Shape, int kStrategy>
-__device__ __forceinline__ void process_row_static(const ScanArgs& args, const uint64_t* raw, uint8_t* bins, int tid, int32_t& my_err) {
+// Split in two phases so that a thread can evaluate several rows (independent load / probe chains in
+// flight together) before it touches the accumulators.  `raw` holds the row's column elements already
+// fetched from the staged tile.  Returns false when the row is dropped (join miss / filter / error).
+template <class Shape>
+__device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint64_t* raw, V* vals, uint32_t& idx, int32_t& my_err) {
   constexpr DPlan sp = Shape::get();
   const DPlan& rp = args.plan;  // literals, key ranges, entry count
-  V vals[sp.n_exprs > 0 ? sp.n_exprs : 1];
   int64_t rowid[HDK_B200_MAX_JOINS];
   int32_t row_err = 0;
   bool alive = true;
@@ -307,39 +308,52 @@ __device__ __forceinline__ void process_row_static(const ScanArgs& args, const u
         const DJoin& jn = rp.joins[j];
         const int64_t key = vals[n].i;
         bool hit = alive && !((sp.joins[j].key_nullable && key == jn.null_val) || key < jn.min_key || key > jn.max_key);
-        int32_t idx = -1;
-        if (hit) idx = __ldg(reinterpret_cast<const int32_t*>(args.join_hash_tables[j]) + (key - jn.min_key));
-        alive = hit && idx >= 0;
-        rowid[j] = idx;
+        int32_t ridx = -1;
+        if (hit) ridx = __ldg(reinterpret_cast<const int32_t*>(args.join_hash_tables[j]) + (key - jn.min_key));
+        alive = hit && ridx >= 0;
+        rowid[j] = ridx;
       }
     });
   });
-  if (!alive) return;
+  if (!alive) return false;
   bool pass = true;
   static_for<0, sp.n_filters>([&](auto F) {
     constexpr DPlan sp = Shape::get();
     pass = pass && (vals[sp.filters[decltype(F)::value]].i > 0);
   });
-  if (!pass) return;
-  if (row_err) { my_err = my_err > 0 ? my_err : row_err; return; }
-  int64_t h = 0;
-  static_for<0, sp.n_keys>([&](auto K) {
-    constexpr int k = decltype(K)::value;
-    constexpr DPlan sp = Shape::get();
-    const DKey& ky = rp.keys[k];
-    int64_t v = vals[sp.keys[k].expr].i;
-    if (sp.keys[k].has_nulls && v == int_null_of(sp.keys[k].width)) v = ky.null_translated;
-    if constexpr (k == 0) h = v - ky.min_val; else h += (v - ky.min_val) * ky.mult;
-  });
-  const uint32_t idx = uint32_t(h);
-  if (idx >= rp.entry_count) { my_err = my_err > 0 ? my_err : 1003; return; }
-  static_for<0, sp.n_acc>([&](auto A) {
-    constexpr int a = decltype(A)::value;
-    constexpr DPlan sp = Shape::get();
-    constexpr DAcc acc = sp.accs[a];
-    constexpr bool count_nulls = acc.kind == ACC_CNT_NN && kStrategy != HDK_B200_STRATEGY_GLOBAL;
-    if (acc_arg_is_null(sp, acc, vals) == count_nulls) accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(sp, acc, vals));
-  });
+  if (!pass) return false;
+  if (row_err) { my_err = my_err > 0 ? my_err : row_err; return false; }
+  if constexpr (sp.hash_type == HDK_B200_PERFECT_HASH) {
+    int64_t h = 0;
+    static_for<0, sp.n_keys>([&](auto K) {
+      constexpr int k = decltype(K)::value;
+      constexpr DPlan sp = Shape::get();
+      const DKey& ky = rp.keys[k];
+      int64_t v = vals[sp.keys[k].expr].i;
+      if (sp.keys[k].has_nulls && v == int_null_of(sp.keys[k].width)) v = ky.null_translated;
+      if constexpr (k == 0) h = v - ky.min_val; else h += (v - ky.min_val) * ky.mult;
+    });
+    idx = uint32_t(h);
+    if (idx >= rp.entry_count) { my_err = my_err > 0 ? my_err : 1003; return false; }
+  }
+  return true;
+}
+
+template <class Shape, int kStrategy>
+__device__ __forceinline__ void accumulate_row_static(const ScanArgs& args, const V* vals, uint32_t idx, uint8_t* bins, int tid,
+                                                      int32_t& my_err) {
+  constexpr DPlan sp = Shape::get();
+  if constexpr (kStrategy == HDK_B200_STRATEGY_BASELINE) {
+    baseline_row(args, args.plan, vals, my_err);
+  } else {
+    static_for<0, sp.n_acc>([&](auto A) {
+      constexpr int a = decltype(A)::value;
+      constexpr DPlan sp = Shape::get();
+      constexpr DAcc acc = sp.accs[a];
+      constexpr bool count_nulls = acc.kind == ACC_CNT_NN && kStrategy != HDK_B200_STRATEGY_GLOBAL;
+      if (acc_arg_is_null(sp, acc, vals) == count_nulls) accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(sp, acc, vals));
+    });
+  }
 }
 
 template <int kStrategy, class Shape>
@@ -348,7 +362,9 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
   const DPlan& p = args.plan;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const bool is_producer = warp == kConsumerWarps;
+  const int nct = int(args.consumer_threads);   // consumer threads (multiple of 32); the warp after them is the producer
+  const int ncw = nct >> 5;
+  const bool is_producer = warp == ncw;
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + kStages;
@@ -360,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {  // (all kStages barriers are initialised; args.n_stages of them are used)
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kConsumerWarps);
+      mbar_init(&empty_bar[s], ncw);
     }
     mbar_fence_init();
   }
@@ -388,12 +404,12 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     for (int a = 0; a < p.n_acc; ++a) {
       const DAcc acc = p.accs[a];
       uint8_t* base = bins + args.acc_bin_off[a];
-      const uint32_t n = kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE ? p.entry_count * kConsumerThreads : p.entry_count;
+      const uint32_t n = kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE ? p.entry_count * nct : p.entry_count;
       if (acc.bytes == 4) {
-        for (uint32_t i = tid; i < n; i += kConsumerThreads) reinterpret_cast<uint32_t*>(base)[i] = 0;
+        for (uint32_t i = tid; i < n; i += nct) reinterpret_cast<uint32_t*>(base)[i] = 0;
       } else {
         const int64_t id = acc_identity(acc.kind);
-        for (uint32_t i = tid; i < n; i += kConsumerThreads) reinterpret_cast<int64_t*>(base)[i] = id;
+        for (uint32_t i = tid; i < n; i += nct) reinterpret_cast<int64_t*>(base)[i] = id;
       }
     }
   }
@@ -471,14 +487,16 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
           cbase[c] = smem + off;
           vec_ok = vec_ok && (off % (VW * sp.col_width[c])) == 0;
         });
+        constexpr int NE = sp.n_exprs > 0 ? sp.n_exprs : 1;
         if (vec_ok) {
-          // fast path (every tile but a fragment's last, 16-byte aligned chunks): vector loads, no per-row bounds checks
+          // fast path (every tile but a fragment's last, 16-byte aligned chunks): vector loads, no per-row bounds
+          // checks; phase 1 evaluates all U*VW rows of the iteration, phase 2 accumulates them
           const uint32_t n_groups = rows / VW;
-          for (uint32_t g0 = tid; g0 < n_groups; g0 += kConsumerThreads * U) {
+          for (uint32_t g0 = tid; g0 < n_groups; g0 += uint32_t(nct) * U) {
             uint32_t words[U][NC][4];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              const uint32_t g = g0 + u * kConsumerThreads;
+              const uint32_t g = g0 + u * nct;
               if (g < n_groups)
                 static_for<0, sp.n_cols>([&](auto Cc) {
                   constexpr int c = decltype(Cc)::value;
@@ -487,24 +505,34 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                   lds_vec<VW * w>(cbase[c] + size_t(g) * (VW * w), words[u][c]);
                 });
             }
+            V vals[U * VW][NE];
+            uint32_t idx[U * VW];
+            bool ok[U * VW];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              if (g0 + u * kConsumerThreads < n_groups) {
 #pragma unroll
-                for (int v = 0; v < VW; ++v) {
-                  uint64_t raw[NC];
-                  static_for<0, sp.n_cols>([&](auto Cc) {
-                    constexpr int c = decltype(Cc)::value;
-                    constexpr DPlan sp = Shape::get();
-                    raw[c] = vec_elem<sp.col_width[c]>(words[u][c], v);
-                  });
-                  process_row_static<Shape, kStrategy>(args, raw, bins, tid, my_err);
-                }
+              for (int v = 0; v < VW; ++v) {
+                uint64_t raw[NC];
+                static_for<0, sp.n_cols>([&](auto Cc) {
+                  constexpr int c = decltype(Cc)::value;
+                  constexpr DPlan sp = Shape::get();
+                  raw[c] = vec_elem<sp.col_width[c]>(words[u][c], v);
+                });
+                idx[u * VW + v] = 0;
+                ok[u * VW + v] = (g0 + u * nct < n_groups) && eval_row_static<Shape>(args, raw, vals[u * VW + v], idx[u * VW + v], my_err);
+#if !HB_PHASED
+                if (ok[u * VW + v]) accumulate_row_static<Shape, kStrategy>(args, vals[u * VW + v], idx[u * VW + v], bins, tid, my_err);
+#endif
               }
             }
+#if HB_PHASED
+#pragma unroll
+            for (int i = 0; i < U * VW; ++i)
+              if (ok[i]) accumulate_row_static<Shape, kStrategy>(args, vals[i], idx[i], bins, tid, my_err);
+#endif
           }
         } else {
-          for (uint32_t r = tid; r < rows; r += kConsumerThreads) {
+          for (uint32_t r = tid; r < rows; r += nct) {
             uint64_t raw[NC];
             static_for<0, sp.n_cols>([&](auto Cc) {
               constexpr int c = decltype(Cc)::value;
@@ -512,13 +540,15 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
               constexpr int w = sp.col_width[c];
               raw[c] = lds_elem(cbase[c] + size_t(r) * w, w);
             });
-            process_row_static<Shape, kStrategy>(args, raw, bins, tid, my_err);
+            V vals[NE];
+            uint32_t idx = 0;
+            if (eval_row_static<Shape>(args, raw, vals, idx, my_err)) accumulate_row_static<Shape, kStrategy>(args, vals, idx, bins, tid, my_err);
           }
         }
       } else {
         V vals[HDK_B200_MAX_EXPRS];
         const uint32_t* col_off = hdr[stage].col_off;
-        for (uint32_t r = tid; r < rows; r += kConsumerThreads) process_row_generic<kStrategy>(args, smem, col_off, r, bins, tid, vals, my_err);
+        for (uint32_t r = tid; r < rows; r += nct) process_row_generic<kStrategy>(args, smem, col_off, r, bins, tid, vals, my_err);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -527,44 +557,44 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
 
     // ---- flush block partials into the global work table
     if (kStrategy != HDK_B200_STRATEGY_GLOBAL && kStrategy != HDK_B200_STRATEGY_BASELINE) {
-      named_bar_sync(1, kConsumerThreads);
+      named_bar_sync(1, nct);
       if (kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE) {
-        // one (acc, group) pair per warp step: lanes stride the kConsumerThreads private copies
+        // one (acc, group) pair per warp step: lanes stride the private copies
         const uint32_t pairs = uint32_t(p.n_acc) * p.entry_count;
-        for (uint32_t pr = warp; pr < pairs; pr += kConsumerWarps) {
+        for (uint32_t pr = warp; pr < pairs; pr += ncw) {
           const uint32_t a = pr / p.entry_count, g = pr % p.entry_count;
           const DAcc acc = p.accs[a];
-          const uint8_t* base = bins + args.acc_bin_off[a] + size_t(g) * kConsumerThreads * acc.bytes;
+          const uint8_t* base = bins + args.acc_bin_off[a] + size_t(g) * nct * acc.bytes;
           int64_t x;
           if (acc.bytes == 4) {
             uint64_t s = 0;
-            for (int i = lane; i < kConsumerThreads; i += 32) s += reinterpret_cast<const uint32_t*>(base)[i];
+            for (int i = lane; i < nct; i += 32) s += reinterpret_cast<const uint32_t*>(base)[i];
             if (acc.kind == ACC_CNT_NN) {  // bins hold NULL counts: non-null = rows (accumulator 0) - nulls
-              const uint8_t* rows_base = bins + args.acc_bin_off[0] + size_t(g) * kConsumerThreads * 4;
+              const uint8_t* rows_base = bins + args.acc_bin_off[0] + size_t(g) * nct * 4;
               uint64_t rws = 0;
-              for (int i = lane; i < kConsumerThreads; i += 32) rws += reinterpret_cast<const uint32_t*>(rows_base)[i];
+              for (int i = lane; i < nct; i += 32) rws += reinterpret_cast<const uint32_t*>(rows_base)[i];
               s = rws - s;
             }
             for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
             x = int64_t(s);
           } else if (acc.kind == ACC_SUM_I) {
             int64_t s = 0;
-            for (int i = lane; i < kConsumerThreads; i += 32) s += reinterpret_cast<const int64_t*>(base)[i];
+            for (int i = lane; i < nct; i += 32) s += reinterpret_cast<const int64_t*>(base)[i];
             for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
             x = s;
           } else if (acc.kind == ACC_SUM_F) {
             double s = 0.0;
-            for (int i = lane; i < kConsumerThreads; i += 32) s += reinterpret_cast<const double*>(base)[i];
+            for (int i = lane; i < nct; i += 32) s += reinterpret_cast<const double*>(base)[i];
             for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
             x = __double_as_longlong(s);
           } else if (acc.kind == ACC_MIN_I || acc.kind == ACC_MIN_F) {
             int64_t s = INT64_MAX;
-            for (int i = lane; i < kConsumerThreads; i += 32) s = min(s, reinterpret_cast<const int64_t*>(base)[i]);
+            for (int i = lane; i < nct; i += 32) s = min(s, reinterpret_cast<const int64_t*>(base)[i]);
             for (int d = 16; d; d >>= 1) s = min(s, __shfl_xor_sync(0xffffffffu, s, d));
             x = s;
           } else {
             int64_t s = INT64_MIN;
-            for (int i = lane; i < kConsumerThreads; i += 32) s = max(s, reinterpret_cast<const int64_t*>(base)[i]);
+            for (int i = lane; i < nct; i += 32) s = max(s, reinterpret_cast<const int64_t*>(base)[i]);
             for (int d = 16; d; d >>= 1) s = max(s, __shfl_xor_sync(0xffffffffu, s, d));
             x = s;
           }
@@ -577,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         for (int a = 0; a < p.n_acc; ++a) {
           const DAcc acc = p.accs[a];
           const uint8_t* base = bins + args.acc_bin_off[a];
-          for (uint32_t g = tid; g < p.entry_count; g += kConsumerThreads) {
+          for (uint32_t g = tid; g < p.entry_count; g += nct) {
             int64_t x = acc.bytes == 4 ? int64_t(reinterpret_cast<const uint32_t*>(base)[g]) : reinterpret_cast<const int64_t*>(base)[g];
             if (acc.kind == ACC_CNT_NN) x = int64_t(reinterpret_cast<const uint32_t*>(bins + args.acc_bin_off[0])[g]) - x;
             if (x != acc_identity(acc.kind)) cell_update_global(acc.kind, args.work_table + size_t(a) * p.entry_count + g, x);
@@ -603,15 +633,22 @@ typedef void (*ScanKernelFn)(const ScanArgs);
 struct StaticEntry {
   uint64_t sig;
   const char* name;
-  ScanKernelFn fn[3];  // THREAD_PRIVATE, CTA_SHARED, GLOBAL
+  ScanKernelFn fn[4];  // THREAD_PRIVATE, CTA_SHARED, GLOBAL, BASELINE
 };
-#define HB_STATIC_SHAPE(ID, SIG, NAME, RPI, ...)                                                             \
-  {SIG, NAME, {scan_kernel<HDK_B200_STRATEGY_THREAD_PRIVATE, StaticShape<ID>>,                               \
-               scan_kernel<HDK_B200_STRATEGY_CTA_SHARED, StaticShape<ID>>,                                   \
-               scan_kernel<HDK_B200_STRATEGY_GLOBAL, StaticShape<ID>>}},
+// perfect-hash shapes get the three accumulation strategies, baseline-hash shapes the in-place one
+template <int ID, int S>
+constexpr ScanKernelFn pick_kernel() {
+  if constexpr ((StaticShape<ID>::get().hash_type == HDK_B200_BASELINE_HASH) == (S == HDK_B200_STRATEGY_BASELINE))
+    return scan_kernel<S, StaticShape<ID>>;
+  else
+    return nullptr;
+}
+#define HB_STATIC_SHAPE(ID, SIG, NAME, RPI, ...)                                                              \
+  {SIG, NAME, {pick_kernel<ID, HDK_B200_STRATEGY_THREAD_PRIVATE>(), pick_kernel<ID, HDK_B200_STRATEGY_CTA_SHARED>(), \
+               pick_kernel<ID, HDK_B200_STRATEGY_GLOBAL>(), pick_kernel<ID, HDK_B200_STRATEGY_BASELINE>()}},
 static const StaticEntry kStaticShapes[] = {
 #include "static_shapes.inc"
-    {0, nullptr, {nullptr, nullptr, nullptr}}};
+    {0, nullptr, {nullptr, nullptr, nullptr, nullptr}}};
 #undef HB_STATIC_SHAPE
 
 // ---------------------------------------------------------------------------------------------
@@ -660,101 +697,124 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   int max_smem = 0;
   HB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 
+  // ---- shared-memory map and launch geometry ---------------------------------------------------
   // fixed part: barriers (128 B) + stage headers + tile prefix
   size_t off = 128 + align_up(sizeof(StageHeader) * kStages, 16);
   a.off_tile_prefix = uint32_t(off);
   off += align_up(size_t(a.num_fragments + 1) * 4, 16);
   const size_t fixed_bytes = align_up(off, 16);
-
-  // accumulator bins: pick the cheapest strategy that fits.  THREAD_PRIVATE needs one copy per consumer
-  // thread; CTA_SHARED one copy per CTA (native shared atomics for counters, CAS loops for 64-bit ops).
   const size_t E = p.entry_count;
-  size_t per_group_bytes = 0;
-  bool counters_only = true;
-  for (int i = 0; i < p.n_acc; ++i) {
-    per_group_bytes += p.accs[i].bytes;
-    counters_only = counters_only && p.accs[i].bytes == 4;
-  }
-  const size_t private_bytes = per_group_bytes * E * kConsumerThreads + 16 * size_t(p.n_acc);
-  const size_t shared_bytes = align_up(per_group_bytes * E, 16) + 16 * size_t(p.n_acc);
   const size_t row_bytes = std::max<size_t>(lw.stage_row_bytes, 1);
-  const size_t min_ring = kStages * (size_t(kConsumerThreads) * row_bytes + 48 * size_t(p.n_cols) + 128);  // one row per thread per tile
   const size_t half_sm = (size_t(max_smem) - 2048) / 2;   // budget that still lets two CTAs share an SM
-  int strategy;
-  if (baseline) strategy = HDK_B200_STRATEGY_BASELINE;
-  else if (counters_only && E >= 32 && fixed_bytes + shared_bytes + 4 * min_ring <= half_sm) strategy = HDK_B200_STRATEGY_CTA_SHARED;
-  else if (fixed_bytes + private_bytes + min_ring <= size_t(max_smem)) strategy = HDK_B200_STRATEGY_THREAD_PRIVATE;
-  else if (fixed_bytes + shared_bytes + min_ring <= size_t(max_smem)) strategy = HDK_B200_STRATEGY_CTA_SHARED;
-  else strategy = HDK_B200_STRATEGY_GLOBAL;
-  if (!baseline && ko && ko->sharedMemBytes == 0xB200F001u) strategy = HDK_B200_STRATEGY_THREAD_PRIVATE;  // test hooks: force a strategy
-  if (!baseline && ko && ko->sharedMemBytes == 0xB200F002u) strategy = HDK_B200_STRATEGY_CTA_SHARED;
-  if (!baseline && ko && ko->sharedMemBytes == 0xB200F003u) strategy = HDK_B200_STRATEGY_GLOBAL;
+  bool counters_only = true;
+  for (int i = 0; i < p.n_acc; ++i) counters_only = counters_only && p.accs[i].bytes == 4;
 
-  a.off_bins = uint32_t(fixed_bytes);
-  size_t bins_bytes = 0;
-  for (int i = 0; i < p.n_acc; ++i) {
-    bins_bytes = align_up(bins_bytes, 16);
-    a.acc_bin_off[i] = uint32_t(bins_bytes);
-    if (strategy == HDK_B200_STRATEGY_THREAD_PRIVATE) bins_bytes += size_t(p.accs[i].bytes) * E * kConsumerThreads;
-    else if (strategy == HDK_B200_STRATEGY_CTA_SHARED) bins_bytes += size_t(p.accs[i].bytes) * E;
-  }
-  if (strategy == HDK_B200_STRATEGY_GLOBAL || strategy == HDK_B200_STRATEGY_BASELINE) bins_bytes = 0;
-  a.off_stages = uint32_t(align_up(fixed_bytes + bins_bytes, 128));
-  if (a.off_stages + min_ring > size_t(max_smem)) { set_error("forced strategy does not fit in shared memory"); return HDK_B200_E_UNSUPPORTED; }
-
-  // stage geometry: search (CTAs per SM, ring depth) for the configuration with the most resident warps
-  // that still gives every consumer thread >= 4 (then >= 2, then >= 1) rows per tile.  tile_rows is a
-  // power of two; a stage holds at most 32 KB.
-  auto max_tile = [&](size_t budget, int stages) -> uint32_t {
-    const size_t avail = budget > a.off_stages ? budget - a.off_stages : 0;
-    const size_t per_stage = std::min<size_t>(avail / stages, 32 * 1024);
-    uint32_t tr = 0;
-    for (uint32_t cand = kConsumerThreads; cand <= 16384; cand *= 2)
-      if (align_up(size_t(cand) * row_bytes + 48 * size_t(p.n_cols), 128) <= per_stage) tr = cand;
-    return tr;
+  struct Geo {
+    int strategy, nct, ctas, stages;
+    uint32_t tile_rows;
+    size_t off_stages;
   };
-  uint32_t tile_rows = 0;
-  int ctas_per_sm = 1, n_stages = kStages;
-  auto try_cfg = [&](int ctas, int want) {
-    for (int stages = kStages; stages >= 3 && !tile_rows; --stages) {
-      const uint32_t tr = max_tile(ctas == 2 ? half_sm : size_t(max_smem), stages);
-      if (tr >= uint32_t(kConsumerThreads) * want) { tile_rows = tr; ctas_per_sm = ctas; n_stages = stages; }
+  // does (strategy, consumer threads, CTAs per SM) fit with >= min_rows rows per thread per tile?
+  auto fit = [&](int strategy, int nct, int ctas, int min_rows, Geo* g) -> bool {
+    size_t bins = 0;
+    for (int i = 0; i < p.n_acc; ++i) {
+      bins = align_up(bins, 16);
+      if (strategy == HDK_B200_STRATEGY_THREAD_PRIVATE) bins += size_t(p.accs[i].bytes) * E * nct;
+      else if (strategy == HDK_B200_STRATEGY_CTA_SHARED) bins += size_t(p.accs[i].bytes) * E;
     }
+    const size_t off_stages = align_up(fixed_bytes + bins, 128);
+    const size_t budget = ctas == 2 ? half_sm : size_t(max_smem);
+    if (off_stages >= budget) return false;
+    for (int stages = kStages; stages >= 3; --stages) {
+      const size_t per_stage = std::min<size_t>((budget - off_stages) / stages, 32 * 1024);
+      uint32_t tr = 0;
+      for (uint32_t cand = 32; cand <= 16384; cand *= 2)
+        if (align_up(size_t(cand) * row_bytes + 48 * size_t(p.n_cols), 128) <= per_stage) tr = cand;
+      if (tr >= uint32_t(nct) * min_rows) {
+        *g = Geo{strategy, nct, ctas, stages, tr, off_stages};
+        return true;
+      }
+    }
+    return false;
   };
-  const int order[6][2] = {{2, 4}, {2, 2}, {1, 4}, {1, 2}, {2, 1}, {1, 1}};
-  for (int i = 0; i < 6 && !tile_rows; ++i) try_cfg(order[i][0], order[i][1]);
-  if (!tile_rows) { set_error("stage ring does not fit in shared memory"); return HDK_B200_E_UNSUPPORTED; }
-  a.n_stages = uint32_t(n_stages);
-  a.tile_rows = tile_rows;
+  // most resident consumer threads first; then rows per thread per tile
+  auto best = [&](int strategy, Geo* out) -> bool {
+    const int ncts[4] = {512, 384, 256, 128};
+    long best_score = -1;
+    for (int min_rows = 4; min_rows >= 1; min_rows >>= 1) {
+      for (int ctas = 2; ctas >= 1; --ctas)
+        for (int i = 0; i < 4; ++i) {
+          Geo g;
+          if (!fit(strategy, ncts[i], ctas, min_rows, &g)) continue;
+          const long score = long(ctas) * ncts[i] * 64 + (min_rows >= 2 ? 32 : 0) + (ctas == 1 ? 1 : 0);
+          if (score > best_score) { best_score = score; *out = g; }
+        }
+      if (best_score >= 0 && min_rows == 2) break;   // do not trade resident threads for 1-row tiles
+    }
+    return best_score >= 0;
+  };
+  Geo geo{};
+  bool have = false;
+  int forced = -1;
+  if (!baseline && ko && ko->sharedMemBytes == 0xB200F001u) forced = HDK_B200_STRATEGY_THREAD_PRIVATE;  // test hooks
+  if (!baseline && ko && ko->sharedMemBytes == 0xB200F002u) forced = HDK_B200_STRATEGY_CTA_SHARED;
+  if (!baseline && ko && ko->sharedMemBytes == 0xB200F003u) forced = HDK_B200_STRATEGY_GLOBAL;
+  if (baseline) have = best(HDK_B200_STRATEGY_BASELINE, &geo);
+  else if (forced >= 0) have = best(forced, &geo);
+  else {
+    Geo g;
+    // counters only and enough groups to spread the native shared atomics: one table per CTA
+    if (counters_only && E >= 32 && best(HDK_B200_STRATEGY_CTA_SHARED, &g) && g.ctas * g.nct >= 1024) { geo = g; have = true; }
+    if (!have && best(HDK_B200_STRATEGY_THREAD_PRIVATE, &g) && g.ctas * g.nct >= 256) { geo = g; have = true; }
+    if (!have && best(HDK_B200_STRATEGY_CTA_SHARED, &g)) { geo = g; have = true; }
+    if (!have) have = best(HDK_B200_STRATEGY_GLOBAL, &geo);
+  }
+  if (!have) { set_error(forced >= 0 ? "forced strategy does not fit in shared memory" : "stage ring does not fit in shared memory"); return HDK_B200_E_UNSUPPORTED; }
+  const int strategy = geo.strategy;
+  a.consumer_threads = uint32_t(geo.nct);
+  a.n_stages = uint32_t(geo.stages);
+  a.tile_rows = geo.tile_rows;
+  a.off_bins = uint32_t(fixed_bytes);
+  a.off_stages = uint32_t(geo.off_stages);
+  {
+    size_t bins = 0;
+    for (int i = 0; i < p.n_acc; ++i) {
+      bins = align_up(bins, 16);
+      a.acc_bin_off[i] = uint32_t(bins);
+      if (strategy == HDK_B200_STRATEGY_THREAD_PRIVATE) bins += size_t(p.accs[i].bytes) * E * geo.nct;
+      else if (strategy == HDK_B200_STRATEGY_CTA_SHARED) bins += size_t(p.accs[i].bytes) * E;
+    }
+  }
   size_t so = 0;
   for (int c = 0; c < p.n_cols; ++c) {
     a.col_region_off[c] = uint32_t(so);
-    so += align_up(size_t(tile_rows) * p.col_width[c] + 32, 16);  // +16 for the alignment shift, +16 slack
+    so += align_up(size_t(geo.tile_rows) * p.col_width[c] + 32, 16);  // +16 for the alignment shift, +16 slack
   }
   a.stage_bytes = uint32_t(align_up(so, 128));
-  const size_t smem_bytes = a.off_stages + size_t(a.stage_bytes) * n_stages;
+  const size_t smem_bytes = a.off_stages + size_t(a.stage_bytes) * geo.stages;
   if (smem_bytes > size_t(max_smem)) { set_error("stage ring does not fit in shared memory (%zu > %d)", smem_bytes, max_smem); return HDK_B200_E_UNSUPPORTED; }
-
-  int grid = sm_count() * ctas_per_sm;
+  const int block = geo.nct + 32;
+  int grid = sm_count() * geo.ctas;
   if (ko && ko->gridDimX) grid = int(ko->gridDimX);
+
   ScanKernelFn kern = strategy == HDK_B200_STRATEGY_THREAD_PRIVATE ? scan_kernel<HDK_B200_STRATEGY_THREAD_PRIVATE, GenericShape>
                       : strategy == HDK_B200_STRATEGY_CTA_SHARED   ? scan_kernel<HDK_B200_STRATEGY_CTA_SHARED, GenericShape>
                       : strategy == HDK_B200_STRATEGY_GLOBAL       ? scan_kernel<HDK_B200_STRATEGY_GLOBAL, GenericShape>
                                                                    : scan_kernel<HDK_B200_STRATEGY_BASELINE, GenericShape>;
   int variant = 0;
-  if (strategy != HDK_B200_STRATEGY_BASELINE && !(ko && ko->literalsOffset == 0xB200F0FFu)) {  // test hook: force the generic kernel
+  if (!(ko && ko->literalsOffset == 0xB200F0FFu)) {  // test hook: force the generic kernel
     const uint64_t sig = plan_signature(p);
     for (int i = 0; kStaticShapes[i].name; ++i)
-      if (kStaticShapes[i].sig == sig) { kern = kStaticShapes[i].fn[strategy]; variant = i + 1; break; }
+      if (kStaticShapes[i].sig == sig && kStaticShapes[i].fn[strategy]) { kern = kStaticShapes[i].fn[strategy]; variant = i + 1; break; }
   }
   HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
-  kern<<<grid, kThreads, smem_bytes, stream>>>(a);
+  kern<<<grid, block, smem_bytes, stream>>>(a);
   HB_LAUNCH_CHECK();
   if (info) {
     info->variant = variant;
     info->strategy = strategy;
     info->grid = grid;
-    info->block = kThreads;
+    info->block = block;
     info->smem_bytes = int(smem_bytes);
     info->n_accumulators = p.n_acc;
   }

@@ -28,6 +28,7 @@ struct ScanArgs {
   uint32_t tile_rows;
   uint32_t stage_bytes;
   uint32_t n_stages;                  // ring depth actually used (<= kStages)
+  uint32_t consumer_threads;          // consumer threads per CTA (multiple of 32, <= kConsumerThreads); blockDim = that + 32
   uint32_t off_tile_prefix, off_bins, off_stages;   // dynamic shared memory map
   uint32_t acc_bin_off[kMaxAcc];                    // from off_bins
   uint32_t col_region_off[HDK_B200_MAX_COLS];       // from a stage's base

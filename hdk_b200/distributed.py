@@ -64,7 +64,9 @@ def all_to_all_rows(cols: List[torch.Tensor], send_counts: torch.Tensor, widths:
     send = send_counts.to(torch.int64)
     recv = torch.empty_like(send)
     if w > 1:
-        dist.all_to_all_single(recv, send, group=group)
+        gathered = [torch.empty_like(send) for _ in range(w)]
+        dist.all_gather(gathered, send, group=group)     # counts matrix: recv[r] = send_of_rank_r[me]
+        recv = torch.stack([g[rank()] for g in gathered])
     else:
         recv.copy_(send)
     send_l, recv_l = send.tolist(), recv.tolist()
@@ -73,13 +75,33 @@ def all_to_all_rows(cols: List[torch.Tensor], send_counts: torch.Tensor, widths:
     for c, width in zip(cols, widths):
         dst = torch.empty(max(n_recv, 1) * width, dtype=torch.uint8, device=c.device)
         if w > 1:
-            dist.all_to_all_single(dst[: n_recv * width], c[: int(sum(send_l)) * width],
-                                   output_split_sizes=[x * width for x in recv_l],
-                                   input_split_sizes=[x * width for x in send_l], group=group)
+            _all_to_all_bytes(dst[: n_recv * width], c[: int(sum(send_l)) * width], [x * width for x in recv_l],
+                              [x * width for x in send_l], group)
         else:
             dst[: n_recv * width].copy_(c[: n_recv * width])
         out.append(dst)
     return out, n_recv
+
+
+def _all_to_all_bytes(dst, src, recv_sizes, send_sizes, group=None):
+    """all_to_all_single over NCCL; gloo has no all-to-all, so the CPU tests fall back to isend / irecv pairs."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(dst, src, output_split_sizes=recv_sizes, input_split_sizes=send_sizes, group=group)
+        return
+    r, ops, so, ro = rank(), [], 0, 0
+    for peer in range(world()):
+        s_chunk, r_chunk = src[so:so + send_sizes[peer]], dst[ro:ro + recv_sizes[peer]]
+        so += send_sizes[peer]
+        ro += recv_sizes[peer]
+        if peer == r:
+            r_chunk.copy_(s_chunk)
+            continue
+        if send_sizes[peer]:
+            ops.append(dist.isend(s_chunk.contiguous(), peer, group=group))
+        if recv_sizes[peer]:
+            ops.append(dist.irecv(r_chunk, peer, group=group))
+    for o in ops:
+        o.wait()
 
 
 def broadcast_tensor(t: Optional[torch.Tensor], nbytes: int, device, src: int = 0, group=None) -> torch.Tensor:

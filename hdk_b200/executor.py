@@ -437,6 +437,46 @@ class Executor:
         self.finalize(pq, prep)
         return info
 
+    def execute_partitioned(self, unit: ir.ExecutionUnit, max_groups_buffer_entry_count: int, group=None):
+        """baseline hash across ranks (model: QE/RelAlgExecutor.cpp:691-838): partition this rank's
+        rows by MurmurHash64A(key) % world on the device (count → scatter), exchange the partitions with an
+        NCCL all-to-all, aggregate the received rows locally.  Every key lives on exactly one rank afterwards,
+        so there is no merge: the result is the concatenation of the ranks' ResultSets.
+        Returns (ResultSet of this rank's key partition, rows received)."""
+        from . import distributed as D
+        torch = self.ctx.torch
+        dev = self.ctx.device
+        W = D.world()
+        pq = self.plan(unit, max_groups_buffer_entry_count)
+        if pq.qmd.hash_type != abi.BASELINE_HASH:
+            raise planner.UnsupportedPlan("execute_partitioned is for baseline-hash group-by")
+        if unit.joins:
+            raise planner.UnsupportedPlan("partitioned aggregation of joined plans is not supported")
+        prep = self.prepare(pq)
+        outer = self.storage.get_table(unit.table)
+        st = self.ctx.stream_ptr()
+        counts = torch.zeros(W, dtype=torch.int64, device=dev)
+        _lib.check(self.lib.hdk_b200_shuffle_count(C.byref(pq.plan), C.byref(prep["kp"]), W, counts.data_ptr(), st), "shuffle_count")
+        n_local = int(counts.sum().item())
+        offsets = torch.cumsum(counts, 0) - counts
+        cursors = torch.zeros(W, dtype=torch.int64, device=dev)
+        widths = [outer.columns[c].phys_width for c in pq.columns]
+        send_cols = [torch.empty(max(n_local, 1) * w, dtype=torch.uint8, device=dev) for w in widths]
+        ptrs = torch.tensor([t.data_ptr() for t in send_cols], dtype=torch.int64, device=dev)
+        _lib.check(self.lib.hdk_b200_shuffle_scatter(C.byref(pq.plan), C.byref(prep["kp"]), W, offsets.data_ptr(), cursors.data_ptr(),
+                                                     ptrs.data_ptr(), st), "shuffle_scatter")
+        recv_cols, n_recv = D.all_to_all_rows(send_cols, counts, widths, group)
+        # local aggregate over the received rows: one device-resident fragment, filters already applied
+        from .storage import ChunkStats, Fragment
+        frag = Fragment(0, n_recv, 0, 0, {}, {c: ChunkStats(None, None, False) for c in pq.columns},
+                        {c: t[: n_recv * w] for c, t, w in zip(pq.columns, recv_cols, widths)})
+        prep2 = self.prepare(pq, fragments=[frag])
+        self.launch(pq, prep2)
+        code = int(prep2["err"].item())
+        if code != 0:
+            raise QueryError(code, "ran out of slots in the group-by buffer" if code < 0 else "runtime error")
+        return ResultSet(pq, prep2["out"].cpu().numpy()), n_recv
+
     def execute_work_unit(self, unit: ir.ExecutionUnit, output_columnar=None, ko=None) -> ResultSet:
         """Executor::executeWorkUnit with the out-of-slots retry of RelAlgExecutor::executeWorkUnit
         (QE/RelAlgExecutor.cpp:1544-1566: on ERR_OUT_OF_SLOTS re-run with 2 × the cardinality estimate)."""

@@ -38,16 +38,20 @@ def test_static_shape_parity(oracle_mod, name, kind, sub, nk):
     elif kind == "lineitem":
         benchdata.make_lineitem(st, dev, 200_003, fragment_rows=50_001, keep_host=True)
         text = benchdata.TPCH_Q1
+    elif kind == "c4":
+        benchdata.make_c4(st, dev, 200_003, 30_000, fragment_rows=50_001, keep_host=True)
+        text = benchdata.C4_QUERY
     else:
         benchdata.make_star(st, dev, 300_007, 5_000, fragment_rows=70_001, keep_host=True)
         text = benchdata.C5_QUERY
     ex = Executor(st)
     unit = sql.parse(text, st.tables)
-    pq = ex.plan(unit)
+    pq = ex.plan(unit, 65536 if kind == "c4" else None)
     prep = ex.prepare(pq)
     info = ex.launch(pq, prep)
     torch.cuda.synchronize()
     assert int(prep["err"].item()) == 0
+    assert (pq.qmd.hash_type == abi.BASELINE_HASH) == (kind == "c4")
     assert info.variant > 0, f"{name}: expected a pre-compiled kernel, ran the generic one"
     got = prep["out"].cpu().numpy().copy()
     # the same plan on the generic kernel

@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Device-time measurements of the other named configs (BASELINE.json configs[0], [2], [3], [4]) on one GPU:
+scan-kernel time by CUDA events, algorithmic GB/s and fraction of the measured HBM peak.  Not the bench
+contract (bench.py is); used to guide optimisation and quoted in DESIGN.md / profiles/.
+
+    python tools/bench_configs.py [--scale 1.0] [--only c1,tpch,c4,c5]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import benchdata  # noqa: E402
+from hdk_b200 import _lib, abi, sql  # noqa: E402
+from hdk_b200.executor import Executor  # noqa: E402
+from hdk_b200.storage import ArrowStorage  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label=""):
+    unit = sql.parse(text, ex.storage.tables)
+    pq = ex.plan(unit, guess)
+    prep = ex.prepare(pq)
+    L = ex.lib
+    st = ex.ctx.stream_ptr()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    times, tot = [], []
+    info = None
+    for i in range(reps + 2):
+        torch.cuda.synchronize()
+        e0.record()
+        if pq.qmd.hash_type == abi.BASELINE_HASH:
+            _lib.check(L.hdk_b200_init_group_by_buffer(C.byref(pq.qmd), prep["out"].data_ptr(), st), "init")
+        prep["err"].zero_()
+        e1.record()
+        info = ex.launch(pq, prep)
+        e2.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(e1.elapsed_time(e2))
+            tot.append(e0.elapsed_time(e2))
+    err = int(prep["err"].item())
+    ms = sum(times) / len(times)
+    gbs = bytes_per_row * rows / (ms * 1e-3) / 1e9
+    res = {"config": label, "rows": rows, "ms": round(ms, 3), "ms_with_init": round(sum(tot) / len(tot), 3), "rows_per_s": rows / (ms * 1e-3),
+           "gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak(), 3), "hash": int(pq.qmd.hash_type), "entries": int(pq.qmd.entry_count),
+           "strategy": int(info.strategy), "variant": int(info.variant), "grid": int(info.grid), "smem": int(info.smem_bytes), "err": err,
+           "buffer_mb": round(prep["out"].numel() / 1e6, 1)}
+    print(json.dumps(res), flush=True)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--only", default="c1,tpch,c5,c4")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    only = args.only.split(",")
+    out = []
+    if "c1" in only:
+        st = ArrowStorage()
+        benchdata.make_c1(st, dev)
+        ex = Executor(st)
+        out.append(time_query(ex, benchdata.C1_QUERY, 12, 10_000_000, reps=20, label="c1 int64 (10M rows, 1K groups)"))
+        out.append(time_query(ex, benchdata.C1_QUERY_F, 12, 10_000_000, reps=20, label="c1 fp64"))
+        del ex, st
+        torch.cuda.empty_cache()
+    if "tpch" in only:
+        rows = int(600_037_902 * args.scale)
+        st = ArrowStorage()
+        benchdata.make_lineitem(st, dev, rows)
+        ex = Executor(st)
+        out.append(time_query(ex, benchdata.TPCH_Q1, benchdata.TPCH_Q1_BYTES_PER_ROW, rows, label="tpch q1 SF100 lineitem"))
+        del ex, st
+        torch.cuda.empty_cache()
+    if "c5" in only:
+        rows = int(2_000_000_000 * args.scale)
+        st = ArrowStorage()
+        benchdata.make_star(st, dev, rows, 10_000_000)
+        ex = Executor(st)
+        t0 = time.perf_counter()
+        ex.build_join_table(st.get_table("dim"), "pk")
+        torch.cuda.synchronize()
+        print(json.dumps({"config": "c5 join build (10M rows)", "ms_first_call": round((time.perf_counter() - t0) * 1e3, 2)}), flush=True)
+        out.append(time_query(ex, benchdata.C5_QUERY, benchdata.C5_BYTES_PER_ROW, rows, label="c5 star join 2B x 10M + group-by SUM"))
+        del ex, st
+        torch.cuda.empty_cache()
+    if "c4" in only:
+        rows = int(1_000_000_000 * args.scale)
+        distinct = int(100_000_000 * args.scale)
+        st = ArrowStorage()
+        benchdata.make_c4(st, dev, rows, distinct)
+        ex = Executor(st)
+        out.append(time_query(ex, benchdata.C4_QUERY, benchdata.C4_BYTES_PER_ROW, rows, reps=3, guess=2 * distinct,
+                              label="c4 baseline hash 1B rows / 100M groups"))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
