@@ -125,19 +125,20 @@ __device__ __forceinline__ V eval_node(const DPlan& p, const DExpr& e, const V* 
     case HDK_B200_OP_EXTRACT_YEAR: {
       const DExpr& ta = p.exprs[e.a];
       int64_t t = vals[e.a].i;
-      if (ta.nullable && t == int_null_of(ta.width)) { r = v_null(e); break; }
       const int64_t units = e.imm.i;
-      // Fast path: the whole computation in 32 bits when the time lies in extract_year's own fast range
-      // [0, 2^32 - 2208988800) s (ExtractFromTime.cpp:262).  For second / millisecond units the division by
-      // `units` is done in fp64: t < 2^41 is exact, the quotient's fractional part is a multiple of 1/units
-      // >= 1e-3, and the product's error is < 1e-6, so adding half a step and truncating is exact.
-      if (units <= 1000 && t >= 0 && t < int64_t(2085978496) * units) {
-        const uint32_t secs = units == 1 ? uint32_t(t) : uint32_t(__double2uint_rz(fma(double(t), 1.0 / double(units), 0.5 / double(units))));
-        const uint32_t s1900 = secs + 2208988800u;
-        const uint32_t leap = (s1900 - 5097600u) / 126230400u;
-        r.i = (s1900 - leap * 86400u) / 31536000u + 1900;
+      // Fast path for times inside extract_year's own fast range [0, 2^32 - 2208988800) s (ExtractFromTime.cpp:262),
+      // which also excludes NULL (every sentinel is negative).  Days since the epoch come from one fp64 fma:
+      // t < 2^41 is exact, (t + 1/2) / D is at least 1/(2 D) > 5e-9 away from an integer and the rounding error is
+      // < 1e-11, so truncation is exact; between 1901 and 2099 every fourth year is leap, so
+      // year = 1970 + (4 days + 2) / 1461.  Checked against the reference formula for every second of the range
+      // and every day boundary in ms (tests/test_gpu_parity.py::test_extract_year_boundaries).
+      if (units <= 1000 && uint64_t(t) < uint64_t(2085978496) * uint64_t(units)) {
+        const double inv = 1.0 / (86400.0 * double(units));
+        const uint32_t days = __double2uint_rz(fma(double(t), inv, 0.5 * inv));
+        r.i = 1970 + (4u * days + 2u) / 1461u;
         break;
       }
+      if (ta.nullable && t == int_null_of(ta.width)) { r = v_null(e); break; }
       if (units > 1) t = ta.nullable ? ((t < 0 ? t - (units - 1) : t) / units) : t / units;  // QE/DateTimeIR.cpp:314-320
       r.i = dev_extract_year(t);
       break;

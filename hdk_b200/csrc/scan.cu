@@ -20,6 +20,8 @@
 //   * a finalize kernel converts the work table into the reference's buffer encoding
 //     (finalize.cu), so the result is byte-compatible with QueryMemoryDescriptor.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "baseline.cuh"
@@ -90,7 +92,7 @@ __device__ __forceinline__ void cell_update_global(uint8_t kind, int64_t* cell, 
 // ---------------------------------------------------------------------------------------------
 struct StageHeader {          // written by the producer, read by consumers
   uint32_t rows;              // rows in this tile
-  uint32_t pad;
+  uint32_t aligned;           // every column slice of the tile starts on a 16-byte boundary (vector loads allowed)
   uint32_t col_off[HDK_B200_MAX_COLS];  // byte offset (from dynamic smem base) of element 0 of column c
 };
 
@@ -148,6 +150,13 @@ __host__ __device__ constexpr int shape_max_width(const DPlan& p) {
   int m = 1;
   for (int c = 0; c < p.n_cols; ++c) m = p.col_width[c] > m ? p.col_width[c] : m;
   return m;
+}
+__host__ __device__ constexpr int shape_vec_rows(const DPlan& p) { return 16 / shape_max_width(p); }
+// rows a consumer thread handles per iteration of the full-tile loop: a multiple of the vector group
+template <class Shape>
+__host__ __device__ constexpr int shape_iter_rows() {
+  constexpr int vw = shape_vec_rows(Shape::get());
+  return Shape::rows_per_iter > vw ? Shape::rows_per_iter / vw * vw : vw;
 }
 
 __device__ __forceinline__ uint64_t ldg_elem(const uint8_t* ptr, int w) {
@@ -283,7 +292,8 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
 // flight together) before it touches the accumulators.  `raw` holds the row's column elements already
 // fetched from the staged tile.  Returns false when the row is dropped (join miss / filter / error).
 template <class Shape>
-__device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint64_t* raw, V* vals, uint32_t& idx, int32_t& my_err) {
+__device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint64_t* raw, V* vals, uint32_t& idx, uint32_t& max_idx,
+                                                int32_t& my_err) {
   constexpr DPlan sp = Shape::get();
   const DPlan& rp = args.plan;  // literals, key ranges, entry count
   int64_t rowid[HDK_B200_MAX_JOINS];
@@ -334,7 +344,8 @@ __device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint
       if constexpr (k == 0) h = v - ky.min_val; else h += (v - ky.min_val) * ky.mult;
     });
     idx = uint32_t(h);
-    if (idx >= rp.entry_count) { my_err = my_err > 0 ? my_err : 1003; return false; }
+    max_idx = max(max_idx, idx);   // a key outside the range the layout was built for is reported once per tile (error 1003)
+    if (idx >= rp.entry_count) return false;
   }
   return true;
 }
@@ -426,13 +437,12 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     const bool has_col = c < p.n_cols;
     const uint32_t w = has_col ? p.col_width[c] : 0;
     const uint32_t region_off = has_col ? args.col_region_off[c] : 0;
-    uint32_t it = 0, frag = 0, cur_frag = 0xffffffffu;
+    uint32_t stage = 0, phase = 0, frag = 0, cur_frag = 0xffffffffu;   // phase: parity of the ring round being filled
+    bool first_round = true;
     const uint8_t* col_base = nullptr;
     uint64_t frag_rows = 0;
-    for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const uint32_t stage = it % args.n_stages;
-      const uint32_t round = it / args.n_stages;
-      if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1);
+    for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      if (!first_round) mbar_wait(&empty_bar[stage], phase ^ 1);
       while (tile_prefix[frag + 1] <= t) ++frag;  // tiles are visited in increasing order
       if (frag != cur_frag) {
         cur_frag = frag;
@@ -458,53 +468,50 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
       }
       uint32_t tx_bytes = mid;
       for (int d = 16; d; d >>= 1) tx_bytes += __shfl_xor_sync(0xffffffffu, tx_bytes, d);
-      if (lane == 0) hdr[stage].rows = rows;
+      const bool aligned = __ballot_sync(0xffffffffu, m != 0) == 0;   // every column slice starts on a 16-byte boundary
+      if (lane == 0) {
+        hdr[stage].rows = rows;
+        hdr[stage].aligned = aligned ? 1u : 0u;
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
       __syncwarp();
       if (mid) bulk_g2s(stage_base + region_off + m + head, src + head, mid, &full_bar[stage], policy);
+      if (++stage == args.n_stages) { stage = 0; phase ^= 1; first_round = false; }
     }
   } else {
     // =============================== consumer warps ===============================
     int32_t my_err = 0;
-    uint32_t it = 0;
-    for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const uint32_t stage = it % args.n_stages;
-      mbar_wait(&full_bar[stage], (it / args.n_stages) & 1);
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait(&full_bar[stage], phase);
       const uint32_t rows = hdr[stage].rows;
       if constexpr (Shape::is_static) {
         constexpr DPlan sp = Shape::get();
-        constexpr int R = Shape::rows_per_iter;
-        constexpr int VW = 16 / shape_max_width(sp);      // consecutive rows a lane takes with one <= 16-byte load per column
-        constexpr int U = R / VW > 0 ? R / VW : 1;        // vector groups per thread per iteration
+        constexpr int VW = shape_vec_rows(sp);            // consecutive rows a lane takes with one <= 16-byte load per column
+        constexpr int U = shape_iter_rows<Shape>() / VW;  // vector groups per thread per iteration
         constexpr int NC = sp.n_cols > 0 ? sp.n_cols : 1;
-        const uint8_t* cbase[NC];
-        bool vec_ok = (rows % VW) == 0;
-        static_for<0, sp.n_cols>([&](auto Cc) {
-          constexpr int c = decltype(Cc)::value;
-          constexpr DPlan sp = Shape::get();
-          const uint32_t off = hdr[stage].col_off[c];
-          cbase[c] = smem + off;
-          vec_ok = vec_ok && (off % (VW * sp.col_width[c])) == 0;
-        });
         constexpr int NE = sp.n_exprs > 0 ? sp.n_exprs : 1;
-        if (vec_ok) {
-          // fast path (every tile but a fragment's last, 16-byte aligned chunks): vector loads, no per-row bounds
-          // checks; phase 1 evaluates all U*VW rows of the iteration, phase 2 accumulates them
-          const uint32_t n_groups = rows / VW;
-          for (uint32_t g0 = tid; g0 < n_groups; g0 += uint32_t(nct) * U) {
+        uint32_t max_idx = 0;
+        if (rows == args.tile_rows && hdr[stage].aligned && args.full_iters) {
+          // full tile (all but a fragment's last, 16-byte aligned chunks): every thread runs the same number of
+          // iterations; per iteration U vector loads per column, then U*VW rows evaluated, then accumulated
+          const uint8_t* cptr[NC];
+          static_for<0, sp.n_cols>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value;
+            constexpr DPlan sp = Shape::get();
+            cptr[c] = smem + args.off_stages + stage * args.stage_bytes + args.col_region_off[c] + uint32_t(tid) * (VW * sp.col_width[c]);
+          });
+          for (uint32_t i = 0; i < args.full_iters; ++i) {
             uint32_t words[U][NC][4];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const uint32_t g = g0 + u * nct;
-              if (g < n_groups)
-                static_for<0, sp.n_cols>([&](auto Cc) {
-                  constexpr int c = decltype(Cc)::value;
-                  constexpr DPlan sp = Shape::get();
-                  constexpr int w = sp.col_width[c];
-                  lds_vec<VW * w>(cbase[c] + size_t(g) * (VW * w), words[u][c]);
-                });
-            }
+            for (int u = 0; u < U; ++u)
+              static_for<0, sp.n_cols>([&](auto Cc) {
+                constexpr int c = decltype(Cc)::value;
+                constexpr DPlan sp = Shape::get();
+                constexpr int gw = VW * sp.col_width[c];
+                lds_vec<gw>(cptr[c] + size_t(i * U + u) * nct * gw, words[u][c]);
+              });
             V vals[U * VW][NE];
             uint32_t idx[U * VW];
             bool ok[U * VW];
@@ -519,19 +526,19 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                   raw[c] = vec_elem<sp.col_width[c]>(words[u][c], v);
                 });
                 idx[u * VW + v] = 0;
-                ok[u * VW + v] = (g0 + u * nct < n_groups) && eval_row_static<Shape>(args, raw, vals[u * VW + v], idx[u * VW + v], my_err);
-#if !HB_PHASED
-                if (ok[u * VW + v]) accumulate_row_static<Shape, kStrategy>(args, vals[u * VW + v], idx[u * VW + v], bins, tid, my_err);
-#endif
+                ok[u * VW + v] = eval_row_static<Shape>(args, raw, vals[u * VW + v], idx[u * VW + v], max_idx, my_err);
               }
             }
-#if HB_PHASED
 #pragma unroll
-            for (int i = 0; i < U * VW; ++i)
-              if (ok[i]) accumulate_row_static<Shape, kStrategy>(args, vals[i], idx[i], bins, tid, my_err);
-#endif
+            for (int r = 0; r < U * VW; ++r)
+              if (ok[r]) accumulate_row_static<Shape, kStrategy>(args, vals[r], idx[r], bins, tid, my_err);
           }
         } else {
+          const uint8_t* cbase[NC];
+          static_for<0, sp.n_cols>([&](auto Cc) {
+            constexpr int c = decltype(Cc)::value;
+            cbase[c] = smem + hdr[stage].col_off[c];
+          });
           for (uint32_t r = tid; r < rows; r += nct) {
             uint64_t raw[NC];
             static_for<0, sp.n_cols>([&](auto Cc) {
@@ -542,9 +549,10 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
             });
             V vals[NE];
             uint32_t idx = 0;
-            if (eval_row_static<Shape>(args, raw, vals, idx, my_err)) accumulate_row_static<Shape, kStrategy>(args, vals, idx, bins, tid, my_err);
+            if (eval_row_static<Shape>(args, raw, vals, idx, max_idx, my_err)) accumulate_row_static<Shape, kStrategy>(args, vals, idx, bins, tid, my_err);
           }
         }
+        if (sp.hash_type == HDK_B200_PERFECT_HASH && max_idx >= p.entry_count && my_err <= 0) my_err = 1003;
       } else {
         V vals[HDK_B200_MAX_EXPRS];
         const uint32_t* col_off = hdr[stage].col_off;
@@ -552,6 +560,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == args.n_stages) { stage = 0; phase ^= 1; }
     }
     if (my_err) record_error(args.error_codes, my_err);
 
@@ -633,6 +642,7 @@ typedef void (*ScanKernelFn)(const ScanArgs);
 struct StaticEntry {
   uint64_t sig;
   const char* name;
+  int iter_rows;       // rows per consumer thread per iteration of the full-tile loop
   ScanKernelFn fn[4];  // THREAD_PRIVATE, CTA_SHARED, GLOBAL, BASELINE
 };
 // perfect-hash shapes get the three accumulation strategies, baseline-hash shapes the in-place one
@@ -644,11 +654,11 @@ constexpr ScanKernelFn pick_kernel() {
     return nullptr;
 }
 #define HB_STATIC_SHAPE(ID, SIG, NAME, RPI, ...)                                                              \
-  {SIG, NAME, {pick_kernel<ID, HDK_B200_STRATEGY_THREAD_PRIVATE>(), pick_kernel<ID, HDK_B200_STRATEGY_CTA_SHARED>(), \
+  {SIG, NAME, shape_iter_rows<StaticShape<ID>>(), {pick_kernel<ID, HDK_B200_STRATEGY_THREAD_PRIVATE>(), pick_kernel<ID, HDK_B200_STRATEGY_CTA_SHARED>(), \
                pick_kernel<ID, HDK_B200_STRATEGY_GLOBAL>(), pick_kernel<ID, HDK_B200_STRATEGY_BASELINE>()}},
 static const StaticEntry kStaticShapes[] = {
 #include "static_shapes.inc"
-    {0, nullptr, {nullptr, nullptr, nullptr, nullptr}}};
+    {0, nullptr, 0, {nullptr, nullptr, nullptr, nullptr}}};
 #undef HB_STATIC_SHAPE
 
 // ---------------------------------------------------------------------------------------------
@@ -709,6 +719,15 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   bool counters_only = true;
   for (int i = 0; i < p.n_acc; ++i) counters_only = counters_only && p.accs[i].bytes == 4;
 
+  // pre-compiled shape for this plan?  (its iteration granularity shapes the tile size)
+  const StaticEntry* stat = nullptr;
+  if (!(ko && ko->literalsOffset == 0xB200F0FFu)) {  // test hook: force the generic kernel
+    const uint64_t sig = plan_signature(p);
+    for (int i = 0; kStaticShapes[i].name; ++i)
+      if (kStaticShapes[i].sig == sig) { stat = &kStaticShapes[i]; break; }
+  }
+  const int iter_rows = stat ? stat->iter_rows : 1;
+
   struct Geo {
     int strategy, nct, ctas, stages;
     uint32_t tile_rows;
@@ -725,11 +744,16 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
     const size_t off_stages = align_up(fixed_bytes + bins, 128);
     const size_t budget = ctas == 2 ? half_sm : size_t(max_smem);
     if (off_stages >= budget) return false;
-    for (int stages = kStages; stages >= 3; --stages) {
+    for (int stages = 4; stages >= 3; --stages) {
       const size_t per_stage = std::min<size_t>((budget - off_stages) / stages, 32 * 1024);
+      // a whole number of full-tile iterations (nct * iter_rows rows each), every column slice a multiple of 16 bytes
+      const uint32_t quantum = uint32_t(nct) * uint32_t(iter_rows);
       uint32_t tr = 0;
-      for (uint32_t cand = 32; cand <= 16384; cand *= 2)
+      for (uint32_t cand = quantum; cand <= 32768; cand += quantum)
         if (align_up(size_t(cand) * row_bytes + 48 * size_t(p.n_cols), 128) <= per_stage) tr = cand;
+      if (tr == 0)   // tiles smaller than one iteration quantum: scalar path only
+        for (uint32_t cand = 32; cand < quantum; cand *= 2)
+          if (align_up(size_t(cand) * row_bytes + 48 * size_t(p.n_cols), 128) <= per_stage) tr = cand;
       if (tr >= uint32_t(nct) * min_rows) {
         *g = Geo{strategy, nct, ctas, stages, tr, off_stages};
         return true;
@@ -769,6 +793,21 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
     if (!have && best(HDK_B200_STRATEGY_CTA_SHARED, &g)) { geo = g; have = true; }
     if (!have) have = best(HDK_B200_STRATEGY_GLOBAL, &geo);
   }
+  // tuning hook (tools/sweep_geo.py): HDK_B200_GEO="strategy,consumer_threads,ctas_per_sm,stages,tile_rows" overrides the search
+  if (const char* env = getenv("HDK_B200_GEO")) {
+    int es = 0, en = 0, ec = 0, est = 0, et = 0;
+    if (!baseline && sscanf(env, "%d,%d,%d,%d,%d", &es, &en, &ec, &est, &et) == 5 && en >= 32 && en <= kConsumerWarps * 32 && en % 32 == 0 &&
+        est >= 1 && est <= kStages && et >= 32 && es >= 0 && es <= HDK_B200_STRATEGY_GLOBAL) {
+      size_t bins = 0;
+      for (int i = 0; i < p.n_acc; ++i) {
+        bins = align_up(bins, 16);
+        if (es == HDK_B200_STRATEGY_THREAD_PRIVATE) bins += size_t(p.accs[i].bytes) * E * en;
+        else if (es == HDK_B200_STRATEGY_CTA_SHARED) bins += size_t(p.accs[i].bytes) * E;
+      }
+      geo = Geo{es, en, ec, est, uint32_t(et), align_up(fixed_bytes + bins, 128)};
+      have = true;
+    }
+  }
   if (!have) { set_error(forced >= 0 ? "forced strategy does not fit in shared memory" : "stage ring does not fit in shared memory"); return HDK_B200_E_UNSUPPORTED; }
   const int strategy = geo.strategy;
   a.consumer_threads = uint32_t(geo.nct);
@@ -802,10 +841,11 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
                       : strategy == HDK_B200_STRATEGY_GLOBAL       ? scan_kernel<HDK_B200_STRATEGY_GLOBAL, GenericShape>
                                                                    : scan_kernel<HDK_B200_STRATEGY_BASELINE, GenericShape>;
   int variant = 0;
-  if (!(ko && ko->literalsOffset == 0xB200F0FFu)) {  // test hook: force the generic kernel
-    const uint64_t sig = plan_signature(p);
-    for (int i = 0; kStaticShapes[i].name; ++i)
-      if (kStaticShapes[i].sig == sig && kStaticShapes[i].fn[strategy]) { kern = kStaticShapes[i].fn[strategy]; variant = i + 1; break; }
+  if (stat && stat->fn[strategy]) {
+    kern = stat->fn[strategy];
+    variant = int(stat - kStaticShapes) + 1;
+    const uint32_t per_iter = uint32_t(geo.nct) * uint32_t(stat->iter_rows);
+    a.full_iters = (geo.tile_rows % per_iter == 0 && geo.tile_rows % 16 == 0) ? geo.tile_rows / per_iter : 0;
   }
   HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
   kern<<<grid, block, smem_bytes, stream>>>(a);

@@ -7,7 +7,7 @@ namespace hb {
 constexpr int kConsumerWarps = 16;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;  // + one TMA producer warp
-constexpr int kStages = 4;
+constexpr int kStages = 8;   // ring depth limit (the geometry search uses 3-4)
 constexpr uint32_t kMaxFragments = 4096;
 
 struct AccKinds {
@@ -28,6 +28,7 @@ struct ScanArgs {
   uint32_t tile_rows;
   uint32_t stage_bytes;
   uint32_t n_stages;                  // ring depth actually used (<= kStages)
+  uint32_t full_iters;                // static shapes: iterations of the full-tile loop (tile_rows / (consumer_threads * iter rows)); 0 = off
   uint32_t consumer_threads;          // consumer threads per CTA (multiple of 32, <= kConsumerThreads); blockDim = that + 32
   uint32_t off_tile_prefix, off_bins, off_stages;   // dynamic shared memory map
   uint32_t acc_bin_off[kMaxAcc];                    // from off_bins
