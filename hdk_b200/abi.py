@@ -9,7 +9,7 @@ MAX_SLOTS = 32
 MAX_FILTERS = 8
 MAX_JOINS = 4
 MAX_COLS = 32
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EMPTY_KEY_64 = 9223372036854775807
 EMPTY_KEY_32 = 2147483647
@@ -71,7 +71,7 @@ class Key(C.Structure):
 
 class Join(C.Structure):
     _fields_ = [("key_expr", C.c_int32), ("one_to_many", C.c_int32), ("min_key", C.c_int64),
-                ("max_key", C.c_int64), ("null_val", C.c_int64), ("key_nullable", C.c_int32), ("pad", C.c_int32),
+                ("max_key", C.c_int64), ("null_val", C.c_int64), ("key_nullable", C.c_int32), ("payload_by_slot", C.c_int32),
                 ("entry_count", C.c_int64)]
 
 
@@ -87,7 +87,7 @@ class KernelParams(C.Structure):
                 ("num_rows", C.c_void_p), ("frag_row_offsets", C.c_void_p), ("max_matched", C.c_int32),
                 ("total_matched", C.c_void_p), ("init_agg_vals", C.c_void_p), ("groupby_buf", C.c_void_p),
                 ("error_codes", C.c_void_p), ("num_tables", C.c_uint32), ("join_hash_tables", C.c_void_p),
-                ("inner_col_buffers", C.c_void_p)]
+                ("inner_col_buffers", C.c_void_p), ("total_rows_hint", C.c_uint64)]
 
 
 class KernelOptions(C.Structure):
@@ -98,7 +98,7 @@ class KernelOptions(C.Structure):
 
 class LaunchInfo(C.Structure):
     _fields_ = [("variant", C.c_int32), ("strategy", C.c_int32), ("n_launches", C.c_int32), ("grid", C.c_int32),
-                ("block", C.c_int32), ("smem_bytes", C.c_int32), ("n_accumulators", C.c_int32), ("pad", C.c_int32)]
+                ("block", C.c_int32), ("smem_bytes", C.c_int32), ("n_accumulators", C.c_int32), ("tile_rows", C.c_int32)]
 
 
 class WorkTableLayout(C.Structure):

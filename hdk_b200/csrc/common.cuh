@@ -73,7 +73,7 @@ struct DKey {           // 40 bytes
 struct DJoin {          // 32 bytes
   int64_t min_key, max_key, null_val;
   int32_t key_expr;
-  uint8_t key_nullable, one_to_many, pad0, pad1;
+  uint8_t key_nullable, one_to_many, by_slot, pad1;   // by_slot: presence bitmap + slot-ordered inner columns (run-time, not structure)
 };
 
 constexpr int kMaxAcc = 28;

@@ -366,11 +366,42 @@ static int make_cols(const hdk_b200_join_column* jcs, const hdk_b200_join_column
   return HDK_B200_OK;
 }
 
+// slot-ordered copy of one inner column + presence bitmap (one warp per 32 slots → one bitmap word)
+template <typename T>
+__global__ void gather_payload_kernel(const int32_t* __restrict__ table, int64_t entries, const T* __restrict__ col,
+                                      T* __restrict__ out, uint32_t* __restrict__ bitmap) {
+  const int64_t words = (entries + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  for (int64_t w = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5; w < words; w += (int64_t(gridDim.x) * blockDim.x) >> 5) {
+    const int64_t slot = w * 32 + lane;
+    const int32_t rid = slot < entries ? table[slot] : -1;
+    if (slot < entries) out[slot] = rid >= 0 ? col[rid] : T(0);
+    const uint32_t bits = __ballot_sync(0xffffffffu, rid >= 0);
+    if (bitmap && lane == 0) bitmap[w] = bits;
+  }
+}
+
 }  // namespace hb
 
 using namespace hb;
 
 extern "C" {
+
+int hdk_b200_gather_join_payload_on_device(const int32_t* hash_table, int64_t entry_count, const int8_t* inner_col, int elem_width,
+                                           int8_t* out_by_slot, uint32_t* present_bitmap, void* stream) {
+  if (!hash_table || !inner_col || !out_by_slot || entry_count < 0) { set_error("bad argument"); return HDK_B200_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for_join(uint64_t(entry_count), 256);
+  switch (elem_width) {
+    case 1: gather_payload_kernel<uint8_t><<<grid, 256, 0, st>>>(hash_table, entry_count, reinterpret_cast<const uint8_t*>(inner_col), reinterpret_cast<uint8_t*>(out_by_slot), present_bitmap); break;
+    case 2: gather_payload_kernel<uint16_t><<<grid, 256, 0, st>>>(hash_table, entry_count, reinterpret_cast<const uint16_t*>(inner_col), reinterpret_cast<uint16_t*>(out_by_slot), present_bitmap); break;
+    case 4: gather_payload_kernel<uint32_t><<<grid, 256, 0, st>>>(hash_table, entry_count, reinterpret_cast<const uint32_t*>(inner_col), reinterpret_cast<uint32_t*>(out_by_slot), present_bitmap); break;
+    case 8: gather_payload_kernel<uint64_t><<<grid, 256, 0, st>>>(hash_table, entry_count, reinterpret_cast<const uint64_t*>(inner_col), reinterpret_cast<uint64_t*>(out_by_slot), present_bitmap); break;
+    default: set_error("element width %d", elem_width); return HDK_B200_E_INVALID;
+  }
+  HB_LAUNCH_CHECK();
+  return HDK_B200_OK;
+}
 
 int hdk_b200_init_hash_join_buff_on_device(int32_t* buff, int64_t entry_count, int32_t invalid_slot_val, void* stream) {
   if (!buff || entry_count < 0) { set_error("bad argument"); return HDK_B200_E_INVALID; }

@@ -73,8 +73,13 @@ __device__ __forceinline__ void bin_update_shared_atomic(uint8_t kind, uint8_t* 
     case ACC_CNT_ALL: case ACC_CNT_NN: atomicAdd(reinterpret_cast<uint32_t*>(bin), 1u); break;
     case ACC_SUM_I: atomicAdd(reinterpret_cast<unsigned long long*>(bin), static_cast<unsigned long long>(x)); break;
     case ACC_SUM_F: atomicAdd(reinterpret_cast<double*>(bin), __longlong_as_double(x)); break;
-    case ACC_MIN_I: case ACC_MIN_F: atomicMin(reinterpret_cast<long long*>(bin), static_cast<long long>(x)); break;
-    default: atomicMax(reinterpret_cast<long long*>(bin), static_cast<long long>(x)); break;
+    // 64-bit shared atomics are CAS loops (SASS ATOMS.CAST.SPIN.64): look first, a bin only ever moves towards x
+    case ACC_MIN_I: case ACC_MIN_F:
+      if (x < *reinterpret_cast<volatile int64_t*>(bin)) atomicMin(reinterpret_cast<long long*>(bin), static_cast<long long>(x));
+      break;
+    default:
+      if (x > *reinterpret_cast<volatile int64_t*>(bin)) atomicMax(reinterpret_cast<long long*>(bin), static_cast<long long>(x));
+      break;
   }
 }
 __device__ __forceinline__ void cell_update_global(uint8_t kind, int64_t* cell, int64_t x) {
@@ -247,6 +252,10 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
         if (off < 0) { dropped = true; break; }
         n_matches = __ldg(table + E + slot);
         match_ids = table + 2 * E + off;
+      } else if (jn.by_slot) {
+        // presence bitmap + slot-ordered inner columns (hdk_b200_gather_join_payload_on_device)
+        if (!((__ldg(reinterpret_cast<const uint32_t*>(table) + (slot >> 5)) >> (slot & 31)) & 1u)) { dropped = true; break; }
+        rowid[j] = slot;
       } else {
         const int32_t idx = __ldg(table + slot);
         if (idx < 0) { dropped = true; break; }
@@ -318,8 +327,16 @@ __device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint
         const DJoin& jn = rp.joins[j];
         const int64_t key = vals[n].i;
         bool hit = alive && !((sp.joins[j].key_nullable && key == jn.null_val) || key < jn.min_key || key > jn.max_key);
-        int32_t ridx = -1;
-        if (hit) ridx = __ldg(reinterpret_cast<const int32_t*>(args.join_hash_tables[j]) + (key - jn.min_key));
+        int64_t ridx = -1;
+        if (hit) {
+          const int64_t slot = key - jn.min_key;
+          if (jn.by_slot) {   // presence bitmap + slot-ordered inner columns: the row id is the slot
+            const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(args.join_hash_tables[j]) + (slot >> 5));
+            ridx = ((word >> (slot & 31)) & 1u) ? slot : -1;
+          } else {
+            ridx = __ldg(reinterpret_cast<const int32_t*>(args.join_hash_tables[j]) + slot);
+          }
+        }
         alive = hit && ridx >= 0;
         rowid[j] = ridx;
       }
@@ -350,12 +367,46 @@ __device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint
   return true;
 }
 
+__host__ __device__ constexpr bool shape_has_wide_acc(const DPlan& p) {
+  for (int a = 0; a < p.n_acc; ++a)
+    if (p.accs[a].bytes == 8) return true;
+  return false;
+}
+
 template <class Shape, int kStrategy>
 __device__ __forceinline__ void accumulate_row_static(const ScanArgs& args, const V* vals, uint32_t idx, uint8_t* bins, int tid,
                                                       int32_t& my_err) {
   constexpr DPlan sp = Shape::get();
   if constexpr (kStrategy == HDK_B200_STRATEGY_BASELINE) {
     baseline_row(args, args.plan, vals, my_err);
+  } else if constexpr (kStrategy == HDK_B200_STRATEGY_CTA_SHARED && shape_has_wide_acc(sp)) {
+    // Counters use the native 32-bit shared atomics.  The 64-bit ones are CAS loops that collapse when lanes of one
+    // warp hit the same bin, so lanes holding the same group take turns: round r updates the r-th lane of each group.
+    static_for<0, sp.n_acc>([&](auto A) {
+      constexpr int a = decltype(A)::value;
+      constexpr DPlan sp = Shape::get();
+      constexpr DAcc acc = sp.accs[a];
+      if constexpr (acc.bytes == 4) {
+        constexpr bool count_nulls = acc.kind == ACC_CNT_NN;
+        if (acc_arg_is_null(sp, acc, vals) == count_nulls) accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(sp, acc, vals));
+      }
+    });
+    const uint32_t active = __activemask();
+    const uint32_t peers = __match_any_sync(active, idx);
+    const uint32_t rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+    const uint32_t rounds = __reduce_max_sync(active, rank);
+    for (uint32_t r = 0; r <= rounds; ++r) {
+      if (rank == r) {
+        static_for<0, sp.n_acc>([&](auto A) {
+          constexpr int a = decltype(A)::value;
+          constexpr DPlan sp = Shape::get();
+          constexpr DAcc acc = sp.accs[a];
+          if constexpr (acc.bytes == 8) {
+            if (!acc_arg_is_null(sp, acc, vals)) accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(sp, acc, vals));
+          }
+        });
+      }
+    }
   } else {
     static_for<0, sp.n_acc>([&](auto A) {
       constexpr int a = decltype(A)::value;
@@ -715,7 +766,6 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   const size_t fixed_bytes = align_up(off, 16);
   const size_t E = p.entry_count;
   const size_t row_bytes = std::max<size_t>(lw.stage_row_bytes, 1);
-  const size_t half_sm = (size_t(max_smem) - 2048) / 2;   // budget that still lets two CTAs share an SM
   bool counters_only = true;
   for (int i = 0; i < p.n_acc; ++i) counters_only = counters_only && p.accs[i].bytes == 4;
 
@@ -733,8 +783,11 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
     uint32_t tile_rows;
     size_t off_stages;
   };
-  // does (strategy, consumer threads, CTAs per SM) fit with >= min_rows rows per thread per tile?
-  auto fit = [&](int strategy, int nct, int ctas, int min_rows, Geo* g) -> bool {
+  int sm_smem = 0;
+  HB_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+  // Largest tile for (strategy, consumer threads, CTAs per SM, ring depth); false if nothing fits.
+  auto fit = [&](int strategy, int nct, int ctas, int stages, Geo* g) -> bool {
+    if (ctas * (nct + 32) > 2048) return false;
     size_t bins = 0;
     for (int i = 0; i < p.n_acc; ++i) {
       bins = align_up(bins, 16);
@@ -742,40 +795,47 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
       else if (strategy == HDK_B200_STRATEGY_CTA_SHARED) bins += size_t(p.accs[i].bytes) * E;
     }
     const size_t off_stages = align_up(fixed_bytes + bins, 128);
-    const size_t budget = ctas == 2 ? half_sm : size_t(max_smem);
+    // each resident CTA costs its dynamic shared memory + 1 KB reserved by the driver
+    const size_t budget = std::min<size_t>(size_t(sm_smem) / ctas - 1024, size_t(max_smem));
     if (off_stages >= budget) return false;
-    for (int stages = 4; stages >= 3; --stages) {
-      const size_t per_stage = std::min<size_t>((budget - off_stages) / stages, 32 * 1024);
-      // a whole number of full-tile iterations (nct * iter_rows rows each), every column slice a multiple of 16 bytes
-      const uint32_t quantum = uint32_t(nct) * uint32_t(iter_rows);
-      uint32_t tr = 0;
-      for (uint32_t cand = quantum; cand <= 32768; cand += quantum)
-        if (align_up(size_t(cand) * row_bytes + 48 * size_t(p.n_cols), 128) <= per_stage) tr = cand;
-      if (tr == 0)   // tiles smaller than one iteration quantum: scalar path only
-        for (uint32_t cand = 32; cand < quantum; cand *= 2)
-          if (align_up(size_t(cand) * row_bytes + 48 * size_t(p.n_cols), 128) <= per_stage) tr = cand;
-      if (tr >= uint32_t(nct) * min_rows) {
-        *g = Geo{strategy, nct, ctas, stages, tr, off_stages};
-        return true;
-      }
+    const size_t per_stage = std::min<size_t>((budget - off_stages) / stages, 48 * 1024);
+    // a whole number of full-tile iterations (nct * iter_rows rows each); every column slice is then a multiple of 16 bytes
+    const uint32_t quantum = uint32_t(nct) * uint32_t(iter_rows);
+    auto fits = [&](uint32_t rows) { return align_up(size_t(rows) * row_bytes + 48 * size_t(p.n_cols), 128) <= per_stage; };
+    // small inputs: keep >= 8 tiles per resident CTA when the caller told us the row count
+    uint32_t cap = 32768;
+    if (params->total_rows_hint) {
+      const uint64_t want = params->total_rows_hint / (uint64_t(sm_count()) * ctas * 8);
+      cap = uint32_t(std::min<uint64_t>(cap, std::max<uint64_t>(want, quantum)));
     }
-    return false;
+    uint32_t tr = 0;
+    for (uint32_t cand = quantum; cand <= cap && fits(cand); cand += quantum) tr = cand;
+    if (tr == 0)   // tiles smaller than one iteration quantum: scalar path only
+      for (uint32_t cand = 32; cand < quantum && fits(cand); cand *= 2) tr = cand;
+    if (tr == 0) return false;
+    *g = Geo{strategy, nct, ctas, stages, tr, off_stages};
+    return true;
   };
-  // most resident consumer threads first; then rows per thread per tile
+  // Score fitted to tools/sweep_geo.py runs on the taxi shapes (profiles/r1_geometry_sweep.md): ~768 consumer
+  // threads per SM is the sweet spot (three 256-thread CTAs, each with its own ring, beat two 512-thread CTAs by
+  // 5-15 %), more rows per thread per tile amortise the per-tile barrier work (~2 rows' worth), and a 2-deep ring
+  // only pays off when its tiles are large enough to cover the refill latency (~0.7 rows per thread).
   auto best = [&](int strategy, Geo* out) -> bool {
-    const int ncts[4] = {512, 384, 256, 128};
-    long best_score = -1;
-    for (int min_rows = 4; min_rows >= 1; min_rows >>= 1) {
-      for (int ctas = 2; ctas >= 1; --ctas)
-        for (int i = 0; i < 4; ++i) {
+    static const int ncts[] = {256, 384, 192, 512, 128, 64, 32};
+    double best_score = -1.0;
+    for (int nct : ncts)
+      for (int ctas = 1; ctas <= 6; ++ctas)
+        for (int stages = 2; stages <= 3; ++stages) {
           Geo g;
-          if (!fit(strategy, ncts[i], ctas, min_rows, &g)) continue;
-          const long score = long(ctas) * ncts[i] * 64 + (min_rows >= 2 ? 32 : 0) + (ctas == 1 ? 1 : 0);
+          if (!fit(strategy, nct, ctas, stages, &g)) continue;
+          const double T = double(nct) * ctas;
+          const double teff = T <= 768.0 ? T : 768.0 - 0.5 * (T - 768.0);
+          const double rpt = double(g.tile_rows) / nct;
+          const bool full = g.tile_rows % (uint32_t(nct) * uint32_t(iter_rows)) == 0;
+          const double score = teff * (rpt / (rpt + 2.0)) * (full ? 1.0 : 0.5) * (stages == 2 ? rpt / (rpt + 0.7) : 1.0);
           if (score > best_score) { best_score = score; *out = g; }
         }
-      if (best_score >= 0 && min_rows == 2) break;   // do not trade resident threads for 1-row tiles
-    }
-    return best_score >= 0;
+    return best_score >= 0.0;
   };
   Geo geo{};
   bool have = false;
@@ -788,8 +848,10 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   else {
     Geo g;
     // counters only and enough groups to spread the native shared atomics: one table per CTA
-    if (counters_only && E >= 32 && best(HDK_B200_STRATEGY_CTA_SHARED, &g) && g.ctas * g.nct >= 1024) { geo = g; have = true; }
-    if (!have && best(HDK_B200_STRATEGY_THREAD_PRIVATE, &g) && g.ctas * g.nct >= 256) { geo = g; have = true; }
+    if (counters_only && E >= 32 && best(HDK_B200_STRATEGY_CTA_SHARED, &g) && g.ctas * g.nct >= 512) { geo = g; have = true; }
+    // private bins: no atomics at all.  With few groups a shared table would serialise on its hot bins, so take
+    // private bins even when only a few warps fit.
+    if (!have && best(HDK_B200_STRATEGY_THREAD_PRIVATE, &g) && (g.ctas * g.nct >= 256 || E < 64)) { geo = g; have = true; }
     if (!have && best(HDK_B200_STRATEGY_CTA_SHARED, &g)) { geo = g; have = true; }
     if (!have) have = best(HDK_B200_STRATEGY_GLOBAL, &geo);
   }
@@ -848,6 +910,11 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
     a.full_iters = (geo.tile_rows % per_iter == 0 && geo.tile_rows % 16 == 0) ? geo.tile_rows / per_iter : 0;
   }
   HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+  if (!(ko && ko->gridDimX)) {   // persistent grid = what is actually resident (registers can allow fewer CTAs than planned)
+    int occ = 0;
+    HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem_bytes));
+    grid = sm_count() * std::max(1, std::min(occ, geo.ctas));
+  }
   kern<<<grid, block, smem_bytes, stream>>>(a);
   HB_LAUNCH_CHECK();
   if (info) {
@@ -857,6 +924,7 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
     info->block = block;
     info->smem_bytes = int(smem_bytes);
     info->n_accumulators = p.n_acc;
+    info->tile_rows = int(geo.tile_rows);
   }
   return HDK_B200_OK;
 }

@@ -97,6 +97,8 @@ class JoinTable:
     entry_count: int
     inner_table: Table
     inner_columns_dev: Dict[str, object]
+    bitmap: object = None    # presence bitmap (uint32 words) once a slot-ordered column has been made
+    by_slot: Dict[str, object] = None   # inner column name -> copy ordered by hash slot
 
 
 class ResultSet:
@@ -317,6 +319,27 @@ class Executor:
         self.join_tables[cache_key] = jt
         return jt
 
+    def _slot_ordered_column(self, jt: JoinTable, cname: str):
+        """hdk_b200_gather_join_payload_on_device: copy of an inner column ordered by hash slot (+ presence bitmap),
+        made once per (join table, column) and cached with the table."""
+        if jt.by_slot is None:
+            jt.by_slot = {}
+        if cname in jt.by_slot:
+            return jt.by_slot[cname]
+        torch = self.ctx.torch
+        if len(jt.inner_table.fragments) != 1:
+            raise planner.UnsupportedPlan("inner table columns must be a single fragment (ColumnFetcher linearises them)")
+        src = self.ctx.chunk(jt.inner_table.fragments[0], cname)
+        width = jt.inner_table.columns[cname].phys_width
+        out = torch.empty(max(jt.entry_count, 1) * width, dtype=torch.uint8, device=self.ctx.device)
+        if jt.bitmap is None:
+            jt.bitmap = torch.empty((jt.entry_count + 31) // 32 + 1, dtype=torch.int32, device=self.ctx.device)
+        _lib.check(self.lib.hdk_b200_gather_join_payload_on_device(jt.buffer.data_ptr(), jt.entry_count, src.data_ptr(), width,
+                                                                   out.data_ptr(), jt.bitmap.data_ptr(), self.ctx.stream_ptr()),
+                   "gather_join_payload")
+        jt.by_slot[cname] = out
+        return out
+
     # -- one work unit ---------------------------------------------------------------------
     def _col_stats(self, unit: ir.ExecutionUnit):
         tables = [self.storage.get_table(unit.table)] + [self.storage.get_table(j.inner_table) for j in unit.joins]
@@ -346,8 +369,12 @@ class Executor:
         jt_addr = np.zeros(abi.MAX_JOINS, dtype=np.int64)
         inner = np.zeros(abi.MAX_JOINS * abi.MAX_COLS, dtype=np.uint64)
         for j, jt in enumerate(joins):
-            jt_addr[j] = jt.buffer.data_ptr()
+            by_slot = bool(pq.plan.joins[j].payload_by_slot)
+            jt_addr[j] = jt.bitmap.data_ptr() if by_slot else jt.buffer.data_ptr()
             for c, cname in enumerate(pq.inner_columns[j]):
+                if by_slot:
+                    inner[j * abi.MAX_COLS + c] = jt.by_slot[cname].data_ptr()
+                    continue
                 if len(jt.inner_table.fragments) != 1:
                     raise planner.UnsupportedPlan("inner table columns must be a single fragment (ColumnFetcher linearises them)")
                 d = self.ctx.chunk(jt.inner_table.fragments[0], cname)
@@ -362,6 +389,7 @@ class Executor:
         kp.num_tables = 1 + len(joins)
         kp.join_hash_tables = d_jt.data_ptr()
         kp.inner_col_buffers = d_inner.data_ptr()
+        kp.total_rows_hint = int(num_rows.sum())
         keep += [d_ptrs, d_rows, d_jt, d_inner]
         return kp, keep
 
@@ -377,6 +405,10 @@ class Executor:
             pj = pq.plan.joins[j]
             pj.one_to_many = int(jt.hash_type == "OneToMany")
             pj.min_key, pj.max_key, pj.entry_count = jt.min_key, jt.max_key, jt.entry_count
+            pj.payload_by_slot = int(self.config.join_payload_by_slot and jt.hash_type == "OneToOne")
+            if pj.payload_by_slot:
+                for cname in pq.inner_columns[j]:
+                    self._slot_ordered_column(jt, cname)
             joins.append(jt)
         kp, keep = self._kernel_params(pq, outer, frags, joins)
         nbytes = self.lib.hdk_b200_buffer_size_bytes(C.byref(pq.qmd))

@@ -29,6 +29,8 @@ class Config:
     big_group_threshold: int = 16384
     baseline_threshold: int = 1000000
     enable_columnar_output: bool = False
+    # hdk_b200 extension: probe OneToOne joins through a presence bitmap + slot-ordered inner columns
+    join_payload_by_slot: bool = True
 
 
 class UnsupportedPlan(Exception):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HDK_B200_ABI_VERSION 1
+#define HDK_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define HDK_B200_API __attribute__((visibility("default")))
@@ -198,7 +198,10 @@ typedef struct hdk_b200_join {
   int64_t max_key;
   int64_t null_val;      /* outer key null sentinel; used when key nullable */
   int32_t key_nullable;
-  int32_t pad;
+  /* extension (OneToOne only).  1: JOIN_HASH_TABLES[j] is the presence bitmap and inner_col_buffers[j][*] are the
+   * slot-ordered copies made by hdk_b200_gather_join_payload_on_device, so a probe costs one random access per
+   * referenced column instead of table + column; results are identical. */
+  int32_t payload_by_slot;
   int64_t entry_count;   /* hash entries (for one_to_many buffer offsets) */
 } hdk_b200_join;
 
@@ -241,6 +244,10 @@ typedef struct hdk_b200_kernel_params {
   const int64_t* join_hash_tables;  /* JOIN_HASH_TABLES: device array [n_joins] of table addresses */
   /* -- extension: inner-table columns for joins, device array [n_joins * HDK_B200_MAX_COLS] */
   const int8_t* const* inner_col_buffers;
+  /* -- extension: sum of NUM_ROWS when the host knows it (the reference fills NUM_ROWS from a host vector,
+   *    QE/QueryExecutionContext.cpp:789-964), 0 = unknown.  Only sizes tiles so that small inputs still give
+   *    every resident CTA several tiles; results never depend on it. */
+  uint64_t total_rows_hint;
 } hdk_b200_kernel_params;
 
 /* KernelOptions, QE/DeviceKernel.h:33-43.  grid/block of 0 = library picks
@@ -261,7 +268,7 @@ typedef struct hdk_b200_launch_info {
   int32_t n_launches;    /* kernels enqueued by this call */
   int32_t grid, block, smem_bytes;
   int32_t n_accumulators;
-  int32_t pad;
+  int32_t tile_rows;     /* rows per staged tile */
 } hdk_b200_launch_info;
 
 enum hdk_b200_strategy {
@@ -447,6 +454,16 @@ HDK_B200_API int hdk_b200_fill_one_to_many_baseline_hash_table_on_device(int32_t
  * out[i] = matching slot value / entry index or -1. */
 HDK_B200_API int hdk_b200_probe_hash_join_on_device(const int32_t* buff, const int64_t* keys, int64_t n,
                                        int64_t min_key, int64_t max_key, int64_t* out, void* stream);
+
+/* Extension: re-order one inner-table column by hash slot for a OneToOne perfect table (the layout the reference's
+ * fill_hash_join_buff_on_device produces, JHT/Runtime/HashJoinRuntime.cpp fill_hash_join_buff):
+ *   out_by_slot[slot] = table[slot] >= 0 ? inner_col[table[slot]] : 0      (elem_width 1, 2, 4 or 8 bytes)
+ *   present_bitmap bit slot = table[slot] >= 0                            (uint32 words, may be NULL)
+ * The probe of a plan whose join has payload_by_slot = 1 then reads the bitmap (entry_count / 8 bytes, cache
+ * resident) and one element of each referenced column per row. */
+HDK_B200_API int hdk_b200_gather_join_payload_on_device(const int32_t* hash_table, int64_t entry_count, const int8_t* inner_col,
+                                                        int elem_width, int8_t* out_by_slot, uint32_t* present_bitmap,
+                                                        void* stream);
 HDK_B200_API int hdk_b200_probe_baseline_hash_join_on_device(const int8_t* hash_buff, const int8_t* keys /* n × key_component_count × key_width */,
                                                 int64_t n, size_t key_component_count, int key_width,
                                                 int64_t entry_count, int with_val_slot, int64_t* out, void* stream);

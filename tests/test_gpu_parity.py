@@ -149,6 +149,47 @@ def test_every_accumulation_strategy(oracle_mod, env, torch, strategy, text, nk)
     check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
 
 
+@pytest.mark.parametrize("by_slot", [False, True])
+@pytest.mark.parametrize("text,nk", [(QUERIES[16][0], 1), (QUERIES[17][0], 2)])
+def test_join_probe_table_vs_slot_ordered_payload(oracle_mod, env, torch, by_slot, text, nk):
+    """OneToOne probe through the reference-layout table and through the presence bitmap + slot-ordered inner
+    columns (hdk_b200_gather_join_payload_on_device) must both match the oracle."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    ex = Executor(st, planner.Config(join_payload_by_slot=by_slot))
+    pq = ex.plan(sql.parse(text, st.tables))
+    prep = ex.prepare(pq)
+    assert bool(pq.plan.joins[0].payload_by_slot) == by_slot
+    ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+
+
+def test_gather_join_payload_kernel(L, torch):
+    """out[slot] = col[table[slot]] for present slots, 0 otherwise; bitmap bit = present — for every element width."""
+    rng = np.random.default_rng(11)
+    for E, width in [(1, 4), (31, 1), (32, 2), (33, 8), (100003, 4), (65536, 8)]:
+        n_inner = max(E // 2, 1)
+        table = np.full(E, -1, dtype=np.int32)
+        slots = rng.permutation(E)[:n_inner]
+        table[slots] = rng.permutation(n_inner).astype(np.int32)
+        col = rng.integers(1, 2**(8 * width - 1) - 1, n_inner).astype({1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[width])
+        d_table, d_col = torch.from_numpy(table).cuda(), torch.from_numpy(col.view(np.uint8)).cuda()
+        d_out = torch.full((E * width,), 0xAB, dtype=torch.uint8, device="cuda")
+        d_bits = torch.zeros((E + 31) // 32, dtype=torch.int32, device="cuda")
+        assert L.hdk_b200_gather_join_payload_on_device(d_table.data_ptr(), E, d_col.data_ptr(), width, d_out.data_ptr(),
+                                                        d_bits.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy().view(col.dtype)
+        exp = np.where(table >= 0, col[np.maximum(table, 0)], 0).astype(col.dtype)
+        assert np.array_equal(out, exp)
+        bits = np.unpackbits(d_bits.cpu().numpy().view(np.uint8), bitorder="little")[:E]
+        assert np.array_equal(bits.astype(bool), table >= 0)
+    assert L.hdk_b200_gather_join_payload_on_device(0, 4, 0, 4, 0, 0, None) != 0
+
+
 def test_executor_sql_end_to_end_vs_sqlite(env, torch):
     """hdk.sql() → Arrow, against SQLite like the reference's `c()` comparator."""
     import hdk_b200.hdk as hdkmod

@@ -27,7 +27,7 @@ def peak():
     return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
 
 
-def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label=""):
+def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label="", force=None):
     unit = sql.parse(text, ex.storage.tables)
     pq = ex.plan(unit, guess)
     prep = ex.prepare(pq)
@@ -36,6 +36,11 @@ def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label=""):
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     times, tot = [], []
     info = None
+    ko = None
+    if force is not None:   # test hook of hdk_b200_launch: force an accumulation strategy
+        ko = abi.KernelOptions()
+        ko.sharedMemBytes = 0xB200F001 + force
+        label += f" [forced strategy {force}]"
     for i in range(reps + 2):
         torch.cuda.synchronize()
         e0.record()
@@ -43,7 +48,7 @@ def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label=""):
             _lib.check(L.hdk_b200_init_group_by_buffer(C.byref(pq.qmd), prep["out"].data_ptr(), st), "init")
         prep["err"].zero_()
         e1.record()
-        info = ex.launch(pq, prep)
+        info = ex.launch(pq, prep, ko)
         e2.record()
         torch.cuda.synchronize()
         if i >= 2:
@@ -54,7 +59,7 @@ def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label=""):
     gbs = bytes_per_row * rows / (ms * 1e-3) / 1e9
     res = {"config": label, "rows": rows, "ms": round(ms, 3), "ms_with_init": round(sum(tot) / len(tot), 3), "rows_per_s": rows / (ms * 1e-3),
            "gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak(), 3), "hash": int(pq.qmd.hash_type), "entries": int(pq.qmd.entry_count),
-           "strategy": int(info.strategy), "variant": int(info.variant), "grid": int(info.grid), "smem": int(info.smem_bytes), "err": err,
+           "strategy": int(info.strategy), "variant": int(info.variant), "grid": int(info.grid), "smem": int(info.smem_bytes), "block": int(info.block), "tile_rows": int(info.tile_rows), "err": err,
            "buffer_mb": round(prep["out"].numel() / 1e6, 1)}
     print(json.dumps(res), flush=True)
     return res
@@ -64,6 +69,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--only", default="c1,tpch,c5,c4")
+    ap.add_argument("--force", action="store_true", help="also time the GLOBAL strategy where it is an alternative")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     only = args.only.split(",")
@@ -74,6 +80,8 @@ def main():
         ex = Executor(st)
         out.append(time_query(ex, benchdata.C1_QUERY, 12, 10_000_000, reps=20, label="c1 int64 (10M rows, 1K groups)"))
         out.append(time_query(ex, benchdata.C1_QUERY_F, 12, 10_000_000, reps=20, label="c1 fp64"))
+        if args.force:
+            out.append(time_query(ex, benchdata.C1_QUERY, 12, 10_000_000, reps=20, label="c1 int64", force=2))
         del ex, st
         torch.cuda.empty_cache()
     if "tpch" in only:
@@ -94,6 +102,8 @@ def main():
         torch.cuda.synchronize()
         print(json.dumps({"config": "c5 join build (10M rows)", "ms_first_call": round((time.perf_counter() - t0) * 1e3, 2)}), flush=True)
         out.append(time_query(ex, benchdata.C5_QUERY, benchdata.C5_BYTES_PER_ROW, rows, label="c5 star join 2B x 10M + group-by SUM"))
+        if args.force:
+            out.append(time_query(ex, benchdata.C5_QUERY, benchdata.C5_BYTES_PER_ROW, rows, label="c5", force=2))
         del ex, st
         torch.cuda.empty_cache()
     if "c4" in only:

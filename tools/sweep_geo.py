@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--rows", type=int, default=400_000_000)
     ap.add_argument("--only", default="q1,q2,q3,q4")
     ap.add_argument("--reps", type=int, default=4)
+    ap.add_argument("--fine", action="store_true", help="finer grid around the library's own strategy")
     ap.add_argument("--geos", default="", help="semicolon-separated explicit geometries; default: a built-in grid")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -58,10 +59,13 @@ def main():
         bpr = benchdata.TAXI_BYTES_PER_ROW[q]
         os.environ.pop("HDK_B200_GEO", None)
         ms, info, err = time_scan(ex, pq, prep, args.reps)
-        print(f"{q} default: strategy={info.strategy} block={info.block} grid={info.grid} smem={info.smem_bytes} "
+        print(f"{q} default: strategy={info.strategy} block={info.block} grid={info.grid} smem={info.smem_bytes} tile_rows={info.tile_rows} "
               f"ms={ms:.3f} frac={bpr * args.rows / ms / 1e6 / peak:.3f} err={err}", flush=True)
         if args.geos:
             cands = [tuple(int(x) for x in g.split(",")) for g in args.geos.split(";")]
+        elif args.fine:
+            cands = [(info.strategy, n, c, stg, n * 4 * k) for n in (128, 192, 256, 320, 384, 512) for c in (1, 2, 3, 4, 5, 6)
+                     for stg in (2, 3, 4) for k in (1, 2, 3, 4, 6, 8)]
         else:
             cands = [(s, n, c, stg, tr) for s in (0, 1) for n in (128, 256, 384, 512) for c in (1, 2, 3, 4) for stg in (3, 4, 6, 8)
                      for tr in (512, 1024, 2048, 4096, 8192)]
