@@ -142,7 +142,8 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
     d.min_key = s.min_key; d.max_key = s.max_key; d.null_val = s.null_val;
     d.key_expr = s.key_expr; d.key_nullable = uint8_t(s.key_nullable); d.one_to_many = uint8_t(s.one_to_many);
     if (s.payload_by_slot && s.one_to_many) { set_error("payload_by_slot needs a one-to-one table"); return HDK_B200_E_INVALID; }
-    d.by_slot = uint8_t(s.payload_by_slot != 0);
+    if (s.payload_by_slot < 0 || s.payload_by_slot > 2) { set_error("payload_by_slot must be 0, 1 or 2"); return HDK_B200_E_INVALID; }
+    d.by_slot = uint8_t(s.payload_by_slot);
     p.join_entry_count[j] = s.entry_count;
     // every inner-table column of join j must come after the join's key node
     for (int i = 0; i <= s.key_expr; ++i)

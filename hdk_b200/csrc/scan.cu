@@ -254,8 +254,8 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
         match_ids = table + 2 * E + off;
       } else if (jn.by_slot) {
         // presence bitmap + slot-ordered inner columns (hdk_b200_gather_join_payload_on_device)
-        if (!((__ldg(reinterpret_cast<const uint32_t*>(table) + (slot >> 5)) >> (slot & 31)) & 1u)) { dropped = true; break; }
-        rowid[j] = slot;
+        if (jn.by_slot == 1 && !((__ldg(reinterpret_cast<const uint32_t*>(table) + (slot >> 5)) >> (slot & 31)) & 1u)) { dropped = true; break; }
+        rowid[j] = slot;   // (by_slot == 2: every slot of [min_key, max_key] is occupied, no bitmap)
       } else {
         const int32_t idx = __ldg(table + slot);
         if (idx < 0) { dropped = true; break; }
@@ -330,7 +330,9 @@ __device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint
         int64_t ridx = -1;
         if (hit) {
           const int64_t slot = key - jn.min_key;
-          if (jn.by_slot) {   // presence bitmap + slot-ordered inner columns: the row id is the slot
+          if (jn.by_slot == 2) {        // slot-ordered inner columns, every slot occupied
+            ridx = slot;
+          } else if (jn.by_slot == 1) { // presence bitmap + slot-ordered inner columns: the row id is the slot
             const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(args.join_hash_tables[j]) + (slot >> 5));
             ridx = ((word >> (slot & 31)) & 1u) ? slot : -1;
           } else {

@@ -99,6 +99,7 @@ class JoinTable:
     inner_columns_dev: Dict[str, object]
     bitmap: object = None    # presence bitmap (uint32 words) once a slot-ordered column has been made
     by_slot: Dict[str, object] = None   # inner column name -> copy ordered by hash slot
+    dense: bool = False      # OneToOne and every slot occupied
 
 
 class ResultSet:
@@ -316,6 +317,7 @@ class Executor:
                                                                                C.byref(ti), 1, st), "fill_one_to_many")
             hash_type = "OneToMany"
         jt = JoinTable(buf, hash_type, lo, hi, entries, inner, {})
+        jt.dense = hash_type == "OneToOne" and not has_nulls and row == entries
         self.join_tables[cache_key] = jt
         return jt
 
@@ -405,7 +407,10 @@ class Executor:
             pj = pq.plan.joins[j]
             pj.one_to_many = int(jt.hash_type == "OneToMany")
             pj.min_key, pj.max_key, pj.entry_count = jt.min_key, jt.max_key, jt.entry_count
-            pj.payload_by_slot = int(self.config.join_payload_by_slot and jt.hash_type == "OneToOne")
+            pj.payload_by_slot = 0
+            if self.config.join_payload_by_slot and jt.hash_type == "OneToOne":
+                # a one-to-one table has no duplicate keys: as many non-NULL keys as entries ⇒ every slot is occupied
+                pj.payload_by_slot = 2 if jt.dense else 1
             if pj.payload_by_slot:
                 for cname in pq.inner_columns[j]:
                     self._slot_ordered_column(jt, cname)

@@ -200,7 +200,8 @@ typedef struct hdk_b200_join {
   int32_t key_nullable;
   /* extension (OneToOne only).  1: JOIN_HASH_TABLES[j] is the presence bitmap and inner_col_buffers[j][*] are the
    * slot-ordered copies made by hdk_b200_gather_join_payload_on_device, so a probe costs one random access per
-   * referenced column instead of table + column; results are identical. */
+   * referenced column instead of table + column; results are identical.  2: as 1, and the caller knows that every
+   * slot of [min_key, max_key] is occupied (as many distinct non-NULL keys as entries), so the bitmap is not read. */
   int32_t payload_by_slot;
   int64_t entry_count;   /* hash entries (for one_to_many buffer offsets) */
 } hdk_b200_join;

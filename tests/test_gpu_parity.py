@@ -160,11 +160,32 @@ def test_join_probe_table_vs_slot_ordered_payload(oracle_mod, env, torch, by_slo
     ex = Executor(st, planner.Config(join_payload_by_slot=by_slot))
     pq = ex.plan(sql.parse(text, st.tables))
     prep = ex.prepare(pq)
-    assert bool(pq.plan.joins[0].payload_by_slot) == by_slot
+    assert pq.plan.joins[0].payload_by_slot == (2 if by_slot else 0)   # dim.pk is a permutation: every slot occupied
     ex.launch(pq, prep)
     torch.cuda.synchronize()
     assert int(prep["err"].item()) == 0
     check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+
+
+def test_join_probe_sparse_dimension_uses_bitmap(oracle_mod, torch):
+    """A dimension whose keys leave holes in [min, max]: the slot-ordered probe has to consult the presence bitmap."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    rng = np.random.default_rng(3)
+    pk = rng.permutation(5000)[:1700].astype(np.int32)
+    dim = pa.table({"pk": pk, "attr": (pk % 23).astype(np.int16), "w": rng.uniform(0, 1, len(pk))})
+    n = 30011
+    t = pa.table({"fk": pa.array(rng.integers(-10, 5100, n).astype(np.int32), mask=rng.random(n) < 0.02), "x": rng.integers(-50, 50, n)})
+    st = util.make_storage({"t": t, "dim": dim}, fragment_size={"t": 4001, "dim": 100000})
+    for by_slot in (True, False):
+        ex = Executor(st, planner.Config(join_payload_by_slot=by_slot))
+        pq = ex.plan(sql.parse("SELECT dim.attr, COUNT(*), SUM(t.x), SUM(dim.w) FROM t JOIN dim ON t.fk = dim.pk GROUP BY dim.attr", st.tables))
+        prep = ex.prepare(pq)
+        assert pq.plan.joins[0].payload_by_slot == (1 if by_slot else 0)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0
+        check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), 1)
 
 
 def test_gather_join_payload_kernel(L, torch):
