@@ -420,8 +420,112 @@ __device__ __forceinline__ void accumulate_row_static(const ScanArgs& args, cons
   }
 }
 
-template <int kStrategy, class Shape>
-__global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant__ ScanArgs args) {
+// ---- REGISTER strategy: few groups, many aggregates (TPC-H Q1) ------------------------------------
+// Every consumer thread keeps the accumulators of all G (<= 8) groups in registers: a row updates group g's set
+// under the predicate idx == g.  No shared-memory traffic per row; the price is G predicated updates per
+// accumulator, which the integer / fp64 pipes absorb while the kernel waits for HBM.  COUNT(arg) counts the (rare)
+// NULL rows in a small per-CTA table instead of spending G registers: non-null = rows - nulls.
+constexpr int kRegGroups = 8;
+constexpr int kRegThreads = 384 + 32;   // most consumer threads + producer warp of a REGISTER-strategy CTA
+
+template <class Shape, int G>
+struct RegAcc {
+  static constexpr int NA = Shape::get().n_acc > 0 ? Shape::get().n_acc : 1;
+  int64_t wide[G][NA];     // SUM / MIN / MAX cells (fp64 as bits); entries of other accumulators are dead and cost nothing
+  uint32_t cnt[G];         // rows of the group (accumulator 0 is always CNT_ALL, see lower.cu)
+};
+
+template <class Shape, int G>
+__device__ __forceinline__ void reg_init(RegAcc<Shape, G>& r) {
+  constexpr DPlan sp = Shape::get();
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    r.cnt[g] = 0;
+    static_for<0, sp.n_acc>([&](auto A) {
+      constexpr int a = decltype(A)::value;
+      constexpr DPlan sp = Shape::get();
+      r.wide[g][a] = acc_identity(sp.accs[a].kind);
+    });
+  }
+}
+
+template <class Shape, int G>
+__device__ __forceinline__ void reg_accumulate(RegAcc<Shape, G>& r, uint32_t* null_bins, bool ok, const V* vals, uint32_t idx) {
+  constexpr DPlan sp = Shape::get();
+  // inputs masked to the accumulator's identity when the row is dropped or the argument is NULL, so that the
+  // per-group update needs the single predicate idx == g
+  int64_t x[RegAcc<Shape, G>::NA];
+  static_for<0, sp.n_acc>([&](auto A) {
+    constexpr int a = decltype(A)::value;
+    constexpr DPlan sp = Shape::get();
+    constexpr DAcc acc = sp.accs[a];
+    const bool is_null = acc_arg_is_null(sp, acc, vals);
+    if constexpr (acc.kind == ACC_CNT_NN) {
+      if (ok && is_null) atomicAdd(&null_bins[idx * sp.n_acc + a], 1u);
+    } else if constexpr (acc.kind == ACC_SUM_F) {
+      x[a] = (ok && !is_null) ? acc_input(sp, acc, vals) : int64_t(0x8000000000000000ULL);   // -0.0: s + (-0.0) == s for every s
+    } else if constexpr (acc.kind != ACC_CNT_ALL) {
+      x[a] = (ok && !is_null) ? acc_input(sp, acc, vals) : acc_identity(acc.kind);
+    }
+  });
+  if (!ok) idx = 0xffffffffu;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (idx == uint32_t(g)) {
+      r.cnt[g] += 1u;
+      static_for<0, sp.n_acc>([&](auto A) {
+        constexpr int a = decltype(A)::value;
+        constexpr DPlan sp = Shape::get();
+        constexpr DAcc acc = sp.accs[a];
+        if constexpr (acc.kind == ACC_SUM_I) r.wide[g][a] += x[a];
+        else if constexpr (acc.kind == ACC_SUM_F) r.wide[g][a] = __double_as_longlong(__longlong_as_double(r.wide[g][a]) + __longlong_as_double(x[a]));
+        else if constexpr (acc.kind == ACC_MIN_I || acc.kind == ACC_MIN_F) r.wide[g][a] = min(r.wide[g][a], x[a]);
+        else if constexpr (acc.kind == ACC_MAX_I || acc.kind == ACC_MAX_F) r.wide[g][a] = max(r.wide[g][a], x[a]);
+      });
+    }
+  }
+}
+
+// warp-reduce every (group, accumulator) pair and merge lane 0's result into the global work table
+template <class Shape, int G>
+__device__ __forceinline__ void reg_flush(const ScanArgs& args, RegAcc<Shape, G>& r, const uint32_t* null_bins, int warp, int lane) {
+  constexpr DPlan sp = Shape::get();
+  const uint32_t E = args.plan.entry_count;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (uint32_t(g) >= E) break;
+    const int64_t rows = int64_t(__reduce_add_sync(0xffffffffu, r.cnt[g]));   // (a thread sees < 2^32 rows per launch)
+    static_for<0, sp.n_acc>([&](auto A) {
+      constexpr int a = decltype(A)::value;
+      constexpr DPlan sp = Shape::get();
+      constexpr DAcc acc = sp.accs[a];
+      int64_t x;
+      if constexpr (acc.kind == ACC_CNT_ALL) {
+        x = rows;
+      } else if constexpr (acc.kind == ACC_CNT_NN) {
+        x = rows - (warp == 0 ? int64_t(null_bins[g * sp.n_acc + a]) : 0);   // the CTA's NULL rows are subtracted once
+      } else if constexpr (acc.kind == ACC_SUM_I) {
+        x = r.wide[g][a];
+        for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+      } else if constexpr (acc.kind == ACC_SUM_F) {
+        double s = __longlong_as_double(r.wide[g][a]);
+        for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        x = __double_as_longlong(s);
+      } else if constexpr (acc.kind == ACC_MIN_I || acc.kind == ACC_MIN_F) {
+        x = r.wide[g][a];
+        for (int d = 16; d; d >>= 1) x = min(x, __shfl_xor_sync(0xffffffffu, x, d));
+      } else {
+        x = r.wide[g][a];
+        for (int d = 16; d; d >>= 1) x = max(x, __shfl_xor_sync(0xffffffffu, x, d));
+      }
+      if (lane == 0 && x != acc_identity(acc.kind)) cell_update_global(acc.kind, args.work_table + size_t(a) * E + g, x);
+    });
+  }
+}
+
+template <int kStrategy, class Shape, int G = kRegGroups>
+__global__ void __launch_bounds__(kStrategy == HDK_B200_STRATEGY_REGISTER ? kRegThreads : kThreads, kStrategy == HDK_B200_STRATEGY_REGISTER ? 1 : 2)
+scan_kernel(const __grid_constant__ ScanArgs args) {
   extern __shared__ __align__(128) uint8_t smem[];
   const DPlan& p = args.plan;
   const int tid = threadIdx.x;
@@ -463,7 +567,10 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
       carry += __shfl_sync(0xffffffffu, t, 31);
     }
   }
-  if (!is_producer && kStrategy != HDK_B200_STRATEGY_GLOBAL && kStrategy != HDK_B200_STRATEGY_BASELINE) {
+  if (kStrategy == HDK_B200_STRATEGY_REGISTER && !is_producer) {
+    for (uint32_t i = tid; i < uint32_t(G) * kMaxAcc; i += nct) reinterpret_cast<uint32_t*>(bins)[i] = 0;
+  }
+  if (!is_producer && (kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE || kStrategy == HDK_B200_STRATEGY_CTA_SHARED)) {
     // initialise bins to the accumulators' identities
     for (int a = 0; a < p.n_acc; ++a) {
       const DAcc acc = p.accs[a];
@@ -536,6 +643,9 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     // =============================== consumer warps ===============================
     int32_t my_err = 0;
     uint32_t stage = 0, phase = 0;
+    RegAcc<Shape, G> racc;   // REGISTER strategy only (dead otherwise)
+    uint32_t* null_bins = reinterpret_cast<uint32_t*>(bins);   // REGISTER: [G][n_acc] NULL-row counters of COUNT(arg)
+    if constexpr (kStrategy == HDK_B200_STRATEGY_REGISTER && Shape::is_static) reg_init<Shape, G>(racc);
     for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       mbar_wait(&full_bar[stage], phase);
       const uint32_t rows = hdr[stage].rows;
@@ -583,8 +693,10 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
               }
             }
 #pragma unroll
-            for (int r = 0; r < U * VW; ++r)
-              if (ok[r]) accumulate_row_static<Shape, kStrategy>(args, vals[r], idx[r], bins, tid, my_err);
+            for (int r = 0; r < U * VW; ++r) {
+              if constexpr (kStrategy == HDK_B200_STRATEGY_REGISTER) reg_accumulate<Shape, G>(racc, null_bins, ok[r], vals[r], idx[r]);
+              else if (ok[r]) accumulate_row_static<Shape, kStrategy>(args, vals[r], idx[r], bins, tid, my_err);
+            }
           }
         } else {
           const uint8_t* cbase[NC];
@@ -602,7 +714,9 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
             });
             V vals[NE];
             uint32_t idx = 0;
-            if (eval_row_static<Shape>(args, raw, vals, idx, max_idx, my_err)) accumulate_row_static<Shape, kStrategy>(args, vals, idx, bins, tid, my_err);
+            const bool ok = eval_row_static<Shape>(args, raw, vals, idx, max_idx, my_err);
+            if constexpr (kStrategy == HDK_B200_STRATEGY_REGISTER) reg_accumulate<Shape, G>(racc, null_bins, ok, vals, idx);
+            else if (ok) accumulate_row_static<Shape, kStrategy>(args, vals, idx, bins, tid, my_err);
           }
         }
         if (sp.hash_type == HDK_B200_PERFECT_HASH && max_idx >= p.entry_count && my_err <= 0) my_err = 1003;
@@ -618,7 +732,11 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     if (my_err) record_error(args.error_codes, my_err);
 
     // ---- flush block partials into the global work table
-    if (kStrategy != HDK_B200_STRATEGY_GLOBAL && kStrategy != HDK_B200_STRATEGY_BASELINE) {
+    if constexpr (kStrategy == HDK_B200_STRATEGY_REGISTER) {
+      named_bar_sync(1, nct);   // every consumer's NULL counts are in
+      if constexpr (Shape::is_static) reg_flush<Shape, G>(args, racc, null_bins, warp, lane);
+    }
+    if (kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE || kStrategy == HDK_B200_STRATEGY_CTA_SHARED) {
       named_bar_sync(1, nct);
       if (kStrategy == HDK_B200_STRATEGY_THREAD_PRIVATE) {
         // one (acc, group) pair per warp step: lanes stride the private copies
@@ -696,22 +814,37 @@ struct StaticEntry {
   uint64_t sig;
   const char* name;
   int iter_rows;       // rows per consumer thread per iteration of the full-tile loop
-  ScanKernelFn fn[4];  // THREAD_PRIVATE, CTA_SHARED, GLOBAL, BASELINE
+  ScanKernelFn fn[5];  // THREAD_PRIVATE, CTA_SHARED, GLOBAL, BASELINE, REGISTER (8 groups)
+  ScanKernelFn reg_fn[4];  // REGISTER kernels for <= 2, 4, 6, 8 groups
 };
 // perfect-hash shapes get the three accumulation strategies, baseline-hash shapes the in-place one
-template <int ID, int S>
+// REGISTER only where it can win: several wide accumulators (it replaces n_acc shared-memory updates per row by
+// kRegGroups predicated register updates per accumulator) and a register budget that fits
+__host__ __device__ constexpr bool shape_wants_registers(const DPlan& p) {
+  int wide = 0;
+  for (int a = 0; a < p.n_acc; ++a) wide += p.accs[a].bytes == 8;
+  return p.hash_type == HDK_B200_PERFECT_HASH && p.n_joins == 0 && wide >= 3 && wide * 2 + (p.n_acc - wide) <= 18;
+}
+template <int ID, int S, int G = kRegGroups>
 constexpr ScanKernelFn pick_kernel() {
-  if constexpr ((StaticShape<ID>::get().hash_type == HDK_B200_BASELINE_HASH) == (S == HDK_B200_STRATEGY_BASELINE))
+  if constexpr (S == HDK_B200_STRATEGY_REGISTER) {
+    if constexpr (shape_wants_registers(StaticShape<ID>::get())) return scan_kernel<S, StaticShape<ID>, G>;
+    else return nullptr;
+  } else if constexpr ((StaticShape<ID>::get().hash_type == HDK_B200_BASELINE_HASH) == (S == HDK_B200_STRATEGY_BASELINE)) {
     return scan_kernel<S, StaticShape<ID>>;
-  else
+  } else {
     return nullptr;
+  }
 }
 #define HB_STATIC_SHAPE(ID, SIG, NAME, RPI, ...)                                                              \
   {SIG, NAME, shape_iter_rows<StaticShape<ID>>(), {pick_kernel<ID, HDK_B200_STRATEGY_THREAD_PRIVATE>(), pick_kernel<ID, HDK_B200_STRATEGY_CTA_SHARED>(), \
-               pick_kernel<ID, HDK_B200_STRATEGY_GLOBAL>(), pick_kernel<ID, HDK_B200_STRATEGY_BASELINE>()}},
+               pick_kernel<ID, HDK_B200_STRATEGY_GLOBAL>(), pick_kernel<ID, HDK_B200_STRATEGY_BASELINE>(), \
+               pick_kernel<ID, HDK_B200_STRATEGY_REGISTER>()},                                                    \
+   {pick_kernel<ID, HDK_B200_STRATEGY_REGISTER, 2>(), pick_kernel<ID, HDK_B200_STRATEGY_REGISTER, 4>(),                 \
+    pick_kernel<ID, HDK_B200_STRATEGY_REGISTER, 6>(), pick_kernel<ID, HDK_B200_STRATEGY_REGISTER, 8>()}},
 static const StaticEntry kStaticShapes[] = {
 #include "static_shapes.inc"
-    {0, nullptr, 0, {nullptr, nullptr, nullptr, nullptr}}};
+    {0, nullptr, 0, {nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}}};
 #undef HB_STATIC_SHAPE
 
 // ---------------------------------------------------------------------------------------------
@@ -796,11 +929,12 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
       if (strategy == HDK_B200_STRATEGY_THREAD_PRIVATE) bins += size_t(p.accs[i].bytes) * E * nct;
       else if (strategy == HDK_B200_STRATEGY_CTA_SHARED) bins += size_t(p.accs[i].bytes) * E;
     }
+    if (strategy == HDK_B200_STRATEGY_REGISTER) bins = size_t(kRegGroups) * kMaxAcc * 4;   // NULL-row counters of COUNT(arg)
     const size_t off_stages = align_up(fixed_bytes + bins, 128);
     // each resident CTA costs its dynamic shared memory + 1 KB reserved by the driver
     const size_t budget = std::min<size_t>(size_t(sm_smem) / ctas - 1024, size_t(max_smem));
     if (off_stages >= budget) return false;
-    const size_t per_stage = std::min<size_t>((budget - off_stages) / stages, 48 * 1024);
+    const size_t per_stage = std::min<size_t>((budget - off_stages) / stages, 72 * 1024);
     // a whole number of full-tile iterations (nct * iter_rows rows each); every column slice is then a multiple of 16 bytes
     const uint32_t quantum = uint32_t(nct) * uint32_t(iter_rows);
     auto fits = [&](uint32_t rows) { return align_up(size_t(rows) * row_bytes + 48 * size_t(p.n_cols), 128) <= per_stage; };
@@ -829,7 +963,19 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
       for (int ctas = 1; ctas <= 6; ++ctas)
         for (int stages = 2; stages <= 3; ++stages) {
           Geo g;
+          // REGISTER kernels are compiled for <= 256 consumer threads and a large register file share
+          if (strategy == HDK_B200_STRATEGY_REGISTER && (nct + 32 > kRegThreads || ctas > 2)) continue;
           if (!fit(strategy, nct, ctas, stages, &g)) continue;
+          if (strategy == HDK_B200_STRATEGY_REGISTER) {   // the register file decides how many of these CTAs are resident
+            ScanKernelFn k = stat->reg_fn[E <= 2 ? 0 : E <= 4 ? 1 : E <= 6 ? 2 : 3];
+            const size_t smem_need = g.off_stages + size_t(stages) * align_up(size_t(g.tile_rows) * row_bytes + 48 * size_t(p.n_cols), 128);
+            int occ = 0;
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::min<size_t>(smem_need + 4096, size_t(max_smem)))) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, nct + 32, smem_need) != cudaSuccess || occ < ctas) {
+              cudaGetLastError();
+              continue;
+            }
+          }
           const double T = double(nct) * ctas;
           const double teff = T <= 768.0 ? T : 768.0 - 0.5 * (T - 768.0);
           const double rpt = double(g.tile_rows) / nct;
@@ -845,12 +991,16 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   if (!baseline && ko && ko->sharedMemBytes == 0xB200F001u) forced = HDK_B200_STRATEGY_THREAD_PRIVATE;  // test hooks
   if (!baseline && ko && ko->sharedMemBytes == 0xB200F002u) forced = HDK_B200_STRATEGY_CTA_SHARED;
   if (!baseline && ko && ko->sharedMemBytes == 0xB200F003u) forced = HDK_B200_STRATEGY_GLOBAL;
+  if (!baseline && ko && ko->sharedMemBytes == 0xB200F005u) forced = HDK_B200_STRATEGY_REGISTER;
   if (baseline) have = best(HDK_B200_STRATEGY_BASELINE, &geo);
+  else if (forced == HDK_B200_STRATEGY_REGISTER && !(stat && stat->fn[forced] && E <= size_t(kRegGroups))) have = false;
   else if (forced >= 0) have = best(forced, &geo);
   else {
     Geo g;
+    // few groups, several wide aggregates, pre-compiled shape: accumulators live in registers
+    if (stat && stat->fn[HDK_B200_STRATEGY_REGISTER] && E <= size_t(kRegGroups) && best(HDK_B200_STRATEGY_REGISTER, &g)) { geo = g; have = true; }
     // counters only and enough groups to spread the native shared atomics: one table per CTA
-    if (counters_only && E >= 32 && best(HDK_B200_STRATEGY_CTA_SHARED, &g) && g.ctas * g.nct >= 512) { geo = g; have = true; }
+    if (!have && counters_only && E >= 32 && best(HDK_B200_STRATEGY_CTA_SHARED, &g) && g.ctas * g.nct >= 512) { geo = g; have = true; }
     // private bins: no atomics at all.  With few groups a shared table would serialise on its hot bins, so take
     // private bins even when only a few warps fit.
     if (!have && best(HDK_B200_STRATEGY_THREAD_PRIVATE, &g) && (g.ctas * g.nct >= 256 || E < 64)) { geo = g; have = true; }
@@ -861,13 +1011,14 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   if (const char* env = getenv("HDK_B200_GEO")) {
     int es = 0, en = 0, ec = 0, est = 0, et = 0;
     if (!baseline && sscanf(env, "%d,%d,%d,%d,%d", &es, &en, &ec, &est, &et) == 5 && en >= 32 && en <= kConsumerWarps * 32 && en % 32 == 0 &&
-        est >= 1 && est <= kStages && et >= 32 && es >= 0 && es <= HDK_B200_STRATEGY_GLOBAL) {
+        est >= 1 && est <= kStages && et >= 32 && es >= 0 && es <= HDK_B200_STRATEGY_REGISTER && es != HDK_B200_STRATEGY_BASELINE) {
       size_t bins = 0;
       for (int i = 0; i < p.n_acc; ++i) {
         bins = align_up(bins, 16);
         if (es == HDK_B200_STRATEGY_THREAD_PRIVATE) bins += size_t(p.accs[i].bytes) * E * en;
         else if (es == HDK_B200_STRATEGY_CTA_SHARED) bins += size_t(p.accs[i].bytes) * E;
       }
+      if (es == HDK_B200_STRATEGY_REGISTER) bins = size_t(kRegGroups) * kMaxAcc * 4;
       geo = Geo{es, en, ec, est, uint32_t(et), align_up(fixed_bytes + bins, 128)};
       have = true;
     }
@@ -900,6 +1051,7 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   int grid = sm_count() * geo.ctas;
   if (ko && ko->gridDimX) grid = int(ko->gridDimX);
 
+  if (strategy == HDK_B200_STRATEGY_REGISTER && !(stat && stat->fn[strategy])) { set_error("REGISTER strategy needs a pre-compiled shape"); return HDK_B200_E_UNSUPPORTED; }
   ScanKernelFn kern = strategy == HDK_B200_STRATEGY_THREAD_PRIVATE ? scan_kernel<HDK_B200_STRATEGY_THREAD_PRIVATE, GenericShape>
                       : strategy == HDK_B200_STRATEGY_CTA_SHARED   ? scan_kernel<HDK_B200_STRATEGY_CTA_SHARED, GenericShape>
                       : strategy == HDK_B200_STRATEGY_GLOBAL       ? scan_kernel<HDK_B200_STRATEGY_GLOBAL, GenericShape>
@@ -907,6 +1059,7 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   int variant = 0;
   if (stat && stat->fn[strategy]) {
     kern = stat->fn[strategy];
+    if (strategy == HDK_B200_STRATEGY_REGISTER) kern = stat->reg_fn[E <= 2 ? 0 : E <= 4 ? 1 : E <= 6 ? 2 : 3];
     variant = int(stat - kStaticShapes) + 1;
     const uint32_t per_iter = uint32_t(geo.nct) * uint32_t(stat->iter_rows);
     a.full_iters = (geo.tile_rows % per_iter == 0 && geo.tile_rows % 16 == 0) ? geo.tile_rows / per_iter : 0;

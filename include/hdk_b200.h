@@ -276,7 +276,8 @@ enum hdk_b200_strategy {
   HDK_B200_STRATEGY_THREAD_PRIVATE = 0, /* per-thread bins in shared memory, no atomics */
   HDK_B200_STRATEGY_CTA_SHARED = 1,     /* per-CTA table in shared memory, shared atomics */
   HDK_B200_STRATEGY_GLOBAL = 2,         /* perfect hash straight into the global work table */
-  HDK_B200_STRATEGY_BASELINE = 3        /* open addressing in the global group-by buffer */
+  HDK_B200_STRATEGY_BASELINE = 3,       /* open addressing in the global group-by buffer */
+  HDK_B200_STRATEGY_REGISTER = 4        /* <= 8 groups, pre-compiled shapes: every thread keeps all groups' accumulators in registers */
 };
 
 /* Validate a plan/descriptor pair and report the scratch (device) bytes the

@@ -53,6 +53,8 @@ def test_static_shape_parity(oracle_mod, name, kind, sub, nk):
     assert int(prep["err"].item()) == 0
     assert (pq.qmd.hash_type == abi.BASELINE_HASH) == (kind == "c4")
     assert info.variant > 0, f"{name}: expected a pre-compiled kernel, ran the generic one"
+    if name == "tpch_q1":
+        assert info.strategy == 4, "TPC-H Q1 (6 groups, 11 accumulators) should keep its accumulators in registers"
     got = prep["out"].cpu().numpy().copy()
     # the same plan on the generic kernel
     ko = abi.KernelOptions()
@@ -69,3 +71,42 @@ def test_static_shape_parity(oracle_mod, name, kind, sub, nk):
     has_fp_sum = any(ti.agg in (abi.AGG_SUM, abi.AGG_AVG) and ti.arg_type is not None and ti.arg_type.is_fp for ti in pq.infos)
     if not has_fp_sum:
         assert np.array_equal(got, obuf) and np.array_equal(gen, obuf)
+
+
+@pytest.mark.parametrize("sub", ["int", "fp"])
+def test_register_strategy_few_groups(oracle_mod, sub):
+    """<= 8 groups and several wide aggregates: the REGISTER strategy (per-thread register accumulators) must match
+    the oracle and the shared-memory strategies, NULL arguments, MIN/MAX and empty groups included."""
+    import pyarrow as pa
+    import torch
+    from hdk_b200 import sql
+    from hdk_b200.executor import Executor
+    rng = np.random.default_rng(21)
+    n = 150_011
+    k = rng.choice([0, 1, 2, 4, 5], n, p=[0.5, 0.3, 0.15, 0.04, 0.01]).astype(np.int32)      # group 3 stays empty
+    t = pa.table({"k": k,   # (no NULL keys: the pre-compiled c1 shapes have a NULL-free key)
+                  "v": pa.array(rng.integers(-2**40, 2**40, n), mask=rng.random(n) < 0.02),
+                  "f": pa.array(rng.uniform(-1e6, 1e6, n), mask=rng.random(n) < 0.02)})
+    st = util.make_storage({"c1": t}, fragment_size=40_009)
+    col = "v" if sub == "int" else "f"
+    text = f"SELECT k, COUNT(*), SUM({col}), MIN({col}), MAX({col}) FROM c1 GROUP BY k"
+    ex = Executor(st)
+    pq = ex.plan(sql.parse(text, st.tables))
+    prep = ex.prepare(pq)
+    info = ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0 and info.variant > 0 and info.strategy == 4
+    got = prep["out"].cpu().numpy().copy()
+    obuf, oerr = util.run_oracle(oracle_mod, st, pq, n_threads=2)
+    assert oerr == 0
+    exp = util.sort_rows(util.result_columns(oracle_mod, pq, obuf), 1)
+    util.assert_rows_equal(util.sort_rows(util.result_columns(oracle_mod, pq, got), 1), exp)
+    if sub == "int":
+        assert np.array_equal(got, obuf)
+    for hook in (0xB200F001, 0xB200F002, 0xB200F005):
+        ko = abi.KernelOptions()
+        ko.sharedMemBytes = hook
+        i2 = ex.launch(pq, prep, ko)
+        torch.cuda.synchronize()
+        assert i2.strategy == {0xB200F001: 0, 0xB200F002: 1, 0xB200F005: 4}[hook]
+        util.assert_rows_equal(util.sort_rows(util.result_columns(oracle_mod, pq, prep["out"].cpu().numpy()), 1), exp)
