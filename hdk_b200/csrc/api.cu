@@ -47,16 +47,20 @@ int hdk_b200_launch(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, const hd
   if (!params || !params->groupby_buf || !params->error_codes) { hb::set_error("null kernel params"); return HDK_B200_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (info) memset(info, 0, sizeof(*info));
-  if (qmd->hash_type == HDK_B200_BASELINE_HASH) {
-    if (int rc = hb::launch_baseline_scan(lw, ko, params, st, info)) return rc;
-    if (info) info->n_launches = 1;
-    return HDK_B200_OK;
-  }
   if (scratch_bytes < lw.work_table_bytes || !scratch) {
     hb::set_error("scratch too small: need %zu bytes, got %zu", lw.work_table_bytes, scratch_bytes);
     return HDK_B200_E_INVALID;
   }
   int64_t* work = static_cast<int64_t*>(scratch);
+  if (qmd->hash_type == HDK_B200_BASELINE_HASH) {
+    // keys are claimed in the caller-initialised buffer, aggregates accumulate in the entry-major work table,
+    // finalize encodes the slots of the claimed entries
+    if (int rc = hb::init_work_table(lw, work, st)) return rc;
+    if (int rc = hb::launch_baseline_scan(lw, ko, params, work, st, info)) return rc;
+    if (int rc = hb::launch_finalize(lw, work, nullptr, params->groupby_buf, st)) return rc;
+    if (info) info->n_launches = 3;
+    return HDK_B200_OK;
+  }
   // GROUPBY_BUF is a device array of pointers: finalize dereferences it on the device, no host sync
   if (int rc = hb::init_work_table(lw, work, st)) return rc;
   if (int rc = hb::launch_scan(lw, ko, params, work, st, info)) return rc;

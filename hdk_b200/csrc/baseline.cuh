@@ -1,11 +1,10 @@
 // hdk_b200/csrc/baseline.cuh — device side of baseline-hash group-by: open-addressing probe / claim in
-// the reference-encoded global buffer and in-place, null-aware slot updates.
+// the reference-encoded global buffer.  (Aggregates accumulate in a neutral work table, scan.cu / finalize.cu.)
 //
 //   hash           key_hash = MurmurHash3_x86_32 over the key bytes, seed 0  (QE/GroupByRuntime.cpp:24-29)
 //   probe          h % E, linear probing, NULL ⇒ out of slots                (QE/GroupByRuntime.cpp:31-54, 90-112)
 //   claim          CAS on the first key component; the winner publishes the rest; others wait until
 //                  the rest is published, then compare                      (QE/cuda_mapd_rt.cu:176-236, 240-321)
-//   slot updates   agg_*_shared / agg_*_skip_val_shared                      (QE/cuda_mapd_rt.cu:423-1083)
 #pragma once
 #include "common.cuh"
 
@@ -121,94 +120,6 @@ __device__ __forceinline__ int64_t baseline_claim_columnar(int64_t* buf64, uint3
     h = h + 1 == E ? 0 : h + 1;
   } while (h != h0);
   return -1;
-}
-
-// ---- in-place slot updates in the reference encoding -------------------------------------------
-template <class F>
-__device__ __forceinline__ void cas_loop64(int64_t* p, F f) {
-  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p);
-  for (;;) {
-    const unsigned long long neu = (unsigned long long)f(int64_t(old));
-    if (neu == old) return;
-    const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(p), old, neu);
-    if (prev == old) return;
-    old = prev;
-  }
-}
-template <class F>
-__device__ __forceinline__ void cas_loop32(int32_t* p, F f) {
-  unsigned int old = *reinterpret_cast<volatile unsigned int*>(p);
-  for (;;) {
-    const unsigned int neu = (unsigned int)f(int32_t(old));
-    if (neu == old) return;
-    const unsigned int prev = atomicCAS(reinterpret_cast<unsigned int*>(p), old, neu);
-    if (prev == old) return;
-    old = prev;
-  }
-}
-
-// v: the argument as int64 (ints) or double bits (fp; float arguments arrive widened to double)
-__device__ __forceinline__ void baseline_update_slot(const DSlot& s, int8_t* p, int64_t vi, double vf, bool arg_null) {
-  const bool skip = s.skip_null != 0;
-  switch (s.op) {
-    case SLOT_COUNT:
-      if (skip && arg_null) return;
-      if (s.bytes == 4) atomicAdd(reinterpret_cast<unsigned int*>(p), 1u);
-      else atomicAdd(reinterpret_cast<unsigned long long*>(p), 1ull);
-      return;
-    case SLOT_SUM:
-      if (skip && arg_null) return;
-      if (s.is_fp) {
-        if (s.bytes == 4) {
-          const float v = float(vf);
-          if (!skip || s.is_avg_sum) { atomicAdd(reinterpret_cast<float*>(p), v); return; }
-          const int32_t nul = int32_t(s.init_val);
-          cas_loop32(reinterpret_cast<int32_t*>(p), [&](int32_t o) { return o == nul ? __float_as_int(v) : __float_as_int(__int_as_float(o) + v); });
-        } else {
-          if (!skip || s.is_avg_sum) { atomicAdd(reinterpret_cast<double*>(p), vf); return; }
-          const int64_t nul = s.init_val;
-          cas_loop64(reinterpret_cast<int64_t*>(p), [&](int64_t o) { return o == nul ? __double_as_longlong(vf) : __double_as_longlong(__longlong_as_double(o) + vf); });
-        }
-      } else {
-        if (!skip || s.is_avg_sum) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)vi); return; }
-        const int64_t nul = s.init_val;
-        cas_loop64(reinterpret_cast<int64_t*>(p), [&](int64_t o) { return o == nul ? vi : int64_t(uint64_t(o) + uint64_t(vi)); });
-      }
-      return;
-    case SLOT_MIN:
-    case SLOT_MAX: {
-      if (skip && arg_null) return;
-      const bool is_min = s.op == SLOT_MIN;
-      if (s.is_fp) {
-        if (s.bytes == 4) {
-          const float v = float(vf);
-          const int32_t nul = int32_t(s.init_val);
-          cas_loop32(reinterpret_cast<int32_t*>(p), [&](int32_t o) {
-            if (skip && o == nul) return __float_as_int(v);
-            const float of = __int_as_float(o);
-            return __float_as_int(is_min ? (v < of ? v : of) : (v > of ? v : of));
-          });
-        } else {
-          const int64_t nul = s.init_val;
-          cas_loop64(reinterpret_cast<int64_t*>(p), [&](int64_t o) {
-            if (skip && o == nul) return __double_as_longlong(vf);
-            const double of = __longlong_as_double(o);
-            return __double_as_longlong(is_min ? (vf < of ? vf : of) : (vf > of ? vf : of));
-          });
-        }
-      } else {
-        if (!skip) {
-          if (is_min) atomicMin(reinterpret_cast<long long*>(p), (long long)vi);
-          else atomicMax(reinterpret_cast<long long*>(p), (long long)vi);
-          return;
-        }
-        const int64_t nul = s.init_val;
-        cas_loop64(reinterpret_cast<int64_t*>(p), [&](int64_t o) { return o == nul ? vi : (is_min ? min(o, vi) : max(o, vi)); });
-      }
-      return;
-    }
-    default: return;
-  }
 }
 
 }  // namespace hb

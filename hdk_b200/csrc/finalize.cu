@@ -165,6 +165,8 @@ struct FinalizeArgs {
   int32_t n_keys;
   uint32_t entry_count;
   const int64_t* work;
+  uint64_t acc_stride, entry_stride;   // cell (acc, e) = work[acc * acc_stride + e * entry_stride]
+  int32_t baseline;                // baseline hash: keys were written by the scan's claim; empty entries keep the caller's init
   int8_t* buf;                     // direct pointer, or
   int64_t* const* buf_indirect;    // GROUPBY_BUF-style device array of pointers ([0] is used)
 };
@@ -184,13 +186,15 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
   const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
   int8_t* const buf = a.buf ? a.buf : reinterpret_cast<int8_t*>(a.buf_indirect[0]);
   for (uint64_t e = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; e < E; e += step) {
-    const int64_t rows = a.work[e];  // accumulator 0 = rows in the group
+    const int64_t rows = a.work[e * a.entry_stride];  // accumulator 0 = rows in the group
     const bool empty = rows == 0;
+    if (a.baseline && empty) continue;
     int8_t* row = L.columnar ? nullptr : buf + e * L.row_bytes;
     // group keys: the (NULL-translated) key value, or EMPTY_KEY
     int64_t comp[HDK_B200_MAX_KEYS];
-    for (int k = 0; k < a.n_keys; ++k) comp[k] = a.n_keys == 1 ? int64_t(e) : int64_t((e / uint64_t(a.keys[k].mult)) % uint64_t(a.keys[k].card));
-    if (!L.keyless) {
+    if (!a.baseline)
+      for (int k = 0; k < a.n_keys; ++k) comp[k] = a.n_keys == 1 ? int64_t(e) : int64_t((e / uint64_t(a.keys[k].mult)) % uint64_t(a.keys[k].card));
+    if (!L.keyless && !a.baseline) {
       for (int k = 0; k < a.n_keys; ++k) {
         const int64_t kv = empty ? HDK_B200_EMPTY_KEY_64 : a.keys[k].min_val + comp[k];
         if (L.columnar) reinterpret_cast<int64_t*>(buf + size_t(k) * ((8 * E + 7) & ~uint64_t(7)))[e] = kv;
@@ -199,7 +203,7 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
     }
     for (int s = 0; s < L.slot_count; ++s) {
       const DSlot& sl = L.slots[s];
-      if (!sl.padded) continue;
+      if (!sl.padded || (a.baseline && sl.op == SLOT_KEY)) continue;
       int8_t* p = L.columnar ? buf + sl.col_off + e * sl.padded : row + L.key_bytes + sl.off;
       int64_t v = sl.init_val;
       if (!empty) {
@@ -210,11 +214,11 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
             v = is_null ? int_null_of(sl.key_width) : ky.min_val + comp[sl.key_index];
             break;
           }
-          case SLOT_COUNT: v = a.work[uint64_t(sl.acc) * E + e]; break;
+          case SLOT_COUNT: v = a.work[uint64_t(sl.acc) * a.acc_stride + e * a.entry_stride]; break;
           default: {
-            const bool any = !sl.skip_null || a.work[uint64_t(sl.acc_cnt) * E + e] != 0;
+            const bool any = !sl.skip_null || a.work[uint64_t(sl.acc_cnt) * a.acc_stride + e * a.entry_stride] != 0;
             if (any || sl.is_avg_sum) {
-              const int64_t cell = a.work[uint64_t(sl.acc) * E + e];
+              const int64_t cell = a.work[uint64_t(sl.acc) * a.acc_stride + e * a.entry_stride];
               if (sl.is_fp) {
                 const double d = sl.op == SLOT_SUM ? __longlong_as_double(cell) : f64_order_decode(cell);
                 v = sl.bytes == 4 ? int64_t(__float_as_uint(float(d))) : __double_as_longlong(d);
@@ -228,7 +232,7 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
       }
       store_slot(p, sl.bytes, sl.padded, v);
     }
-    if (!L.columnar) {
+    if (!L.columnar && !a.baseline) {
       // zero alignment padding inside the row (keys part with 4-byte keys, tail) for deterministic bytes
       // — nothing to do: perfect-hash rows consist of 8-byte keys and 4/8-byte slots; a trailing 4-byte
       // pad exists only when the slot area has an odd number of 4-byte slots.
@@ -248,6 +252,9 @@ int launch_finalize(const Lowered& lw, const int64_t* work_table, int64_t* group
   a.n_keys = lw.plan.n_keys;
   a.entry_count = lw.plan.entry_count;
   a.work = work_table;
+  a.baseline = lw.plan.hash_type == HDK_B200_BASELINE_HASH;
+  a.acc_stride = a.baseline ? 1 : a.entry_count;
+  a.entry_stride = a.baseline ? uint64_t(lw.plan.n_acc) : 1;
   a.buf = reinterpret_cast<int8_t*>(groups_buffer);
   finalize_kernel<<<grid_for(a.entry_count, 128), 128, 0, stream>>>(a);
   HB_LAUNCH_CHECK();

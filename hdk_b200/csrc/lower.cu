@@ -302,7 +302,7 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
     }
     out->n_sum_i = counts[0]; out->n_sum_f = counts[1]; out->n_min = counts[2]; out->n_max = counts[3];
   }
-  out->work_table_bytes = q->hash_type == HDK_B200_PERFECT_HASH ? size_t(p.n_acc) * E * 8 : 0;
+  out->work_table_bytes = size_t(p.n_acc) * E * 8;   // perfect: [n_acc][E]; baseline: [E][n_acc]
   return HDK_B200_OK;
 }
 

@@ -41,6 +41,6 @@ int launch_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_
 int launch_finalize(const Lowered& lw, const int64_t* work_table, int64_t* groups_buffer, int64_t* const* groups_buffer_indirect,
                     cudaStream_t stream);
 int launch_baseline_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
-                         cudaStream_t stream, hdk_b200_launch_info* info);
+                         int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info);
 
 }  // namespace hb
