@@ -178,9 +178,17 @@ __global__ void compact_kernel(const __grid_constant__ CompactArgs a) {
   const DLayout& L = a.layout;
   const uint64_t E = L.entry_count;
   const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
-  for (uint64_t e = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; e < E; e += step) {
-    if (entry_is_empty(L, a.buf, E, e)) continue;
-    const unsigned long long r = atomicAdd(a.row_count, 1ull);
+  const int lane = threadIdx.x & 31;
+  for (uint64_t base = blockIdx.x * uint64_t(blockDim.x); base < E; base += step) {   // whole warps iterate together
+    const uint64_t e = base + threadIdx.x;
+    const bool keep = e < E && !entry_is_empty(L, a.buf, E, e);
+    // one reservation per warp: output positions = warp base + rank among the warp's non-empty entries
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    unsigned long long wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(a.row_count, (unsigned long long)__popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (!keep) continue;
+    const unsigned long long r = wbase + __popc(m & ((1u << lane) - 1u));
     for (int t = 0; t < a.n_targets; ++t) {
       int64_t cell;
       if (a.agg[t] == HDK_B200_AGG_AVG) {

@@ -220,6 +220,27 @@ class ResultSet:
         self._cols = cols
         return cols
 
+    @classmethod
+    def from_compact(cls, planned: planner.PlannedQuery, cells: np.ndarray, dictionaries=None) -> "ResultSet":
+        """Result set over the output of hdk_b200_compact_result: cells[t] holds one 8-byte cell per non-empty
+        entry (integers with NULL normalised to the target type's sentinel, doubles as bits, AVG finalised)."""
+        rs = cls(planned, np.zeros(0, dtype=np.uint8), dictionaries)
+        cols = []
+        for t, ti in enumerate(planned.infos):
+            c = np.ascontiguousarray(cells[t])
+            chosen = ti.compact_type
+            if ti.agg == abi.AGG_AVG:
+                v = c.view(np.float64)
+                cols.append(np.ma.array(v, mask=(v == abi.DBL_MIN)))
+            elif chosen.is_fp and ti.agg != abi.AGG_COUNT:
+                v = c.view(np.float64)
+                null = np.float64(np.float32(abi.FLT_MIN)) if (ti.float_argument_input or chosen.width == 4) else abi.DBL_MIN
+                cols.append(np.ma.array(v, mask=(v == null)))
+            else:
+                cols.append(np.ma.array(c, mask=(c == abi.int_null(ti.type.width))))
+        rs._cols = cols
+        return rs
+
     def row_count(self):
         cols = self._decode()
         return len(cols[0]) if cols else 0
@@ -287,6 +308,7 @@ class Executor:
         self.storage = storage
         self.config = config or planner.Config()
         self.ctx = DeviceContext(device, hot_data)
+        self.compact_threshold_bytes = 64 << 20   # larger group-by buffers are iterated on the device (hdk_b200_compact_result)
         self.lib = _lib.lib()
         self.join_tables: Dict[tuple, JoinTable] = {}
         self.last_launch_info = None
@@ -531,6 +553,18 @@ class Executor:
             raise QueryError(code, "ran out of slots in the group-by buffer" if code < 0 else "runtime error")
         return ResultSet(pq, prep2["out"].cpu().numpy()), n_recv
 
+    def compact_on_device(self, pq: planner.PlannedQuery, out) -> np.ndarray:
+        """hdk_b200_compact_result (ResultSet iteration on the device): [n_targets, rows] int64 cells on the host."""
+        torch = self.ctx.torch
+        E, T = pq.qmd.entry_count, pq.plan.n_targets
+        cols = torch.empty((T, E), dtype=torch.int64, device=self.ctx.device)
+        ptrs = torch.tensor([cols[t].data_ptr() for t in range(T)], dtype=torch.int64, device=self.ctx.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.ctx.device)
+        _lib.check(self.lib.hdk_b200_compact_result(C.byref(pq.plan), C.byref(pq.qmd), out.data_ptr(), ptrs.data_ptr(),
+                                                    cnt.data_ptr(), self.ctx.stream_ptr()), "compact_result")
+        n = int(cnt.item())
+        return cols[:, :n].cpu().numpy()
+
     def execute_work_unit(self, unit: ir.ExecutionUnit, output_columnar=None, ko=None) -> ResultSet:
         """Executor::executeWorkUnit with the out-of-slots retry of RelAlgExecutor::executeWorkUnit
         (QE/RelAlgExecutor.cpp:1544-1566: on ERR_OUT_OF_SLOTS re-run with 2 × the cardinality estimate)."""
@@ -550,13 +584,16 @@ class Executor:
             if code != 0:
                 raise QueryError(code, {1: "division by zero", 7: "overflow or underflow",
                                         1003: "group key outside the range of the perfect-hash layout"}.get(code, "runtime error"))
-            host = prep["out"].cpu().numpy()
             dicts = {}
             tables = [outer] + [self.storage.get_table(j.inner_table) for j in unit.joins]
             for t, e in enumerate(unit.target_exprs):
                 if isinstance(e, ir.ColumnRef) and e.type.kind == "dict":
                     dicts[t] = tables[e.table].columns[e.column].dictionary
-            rs = ResultSet(pq, host, dicts)
+            if prep["out"].numel() > self.compact_threshold_bytes:
+                # large (baseline-hash) buffers: drop the empty entries and finalise AVG on the device, copy rows only
+                rs = ResultSet.from_compact(pq, self.compact_on_device(pq, prep["out"]), dicts)
+            else:
+                rs = ResultSet(pq, prep["out"].cpu().numpy(), dicts)
             rs.launch_info = info
             return rs
         raise QueryError(-abi.ERR_OUT_OF_SLOTS, "ran out of slots after retries")

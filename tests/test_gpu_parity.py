@@ -497,6 +497,30 @@ def test_compact_result_matches_iteration(oracle_mod, L, env, torch, idx):
     assert np.array_equal(key(got), key(vals))
 
 
+def test_executor_iterates_large_buffers_on_device(env, torch):
+    """execute_work_unit switches to device-side compaction above a buffer-size threshold; the Arrow result must
+    not depend on which side iterated the buffer (same buffer decoded both ways, bit for bit)."""
+    from hdk_b200.executor import Executor, ResultSet
+    from hdk_b200 import sql
+    tables, st = env
+    for text in ("SELECT mid, s, COUNT(*) AS n, SUM(v) AS sv, AVG(w) AS aw, MIN(fn) AS mf, MAX(g) AS mg FROM t GROUP BY mid, s",
+                 "SELECT k_null, COUNT(w) AS cw, AVG(g) AS ag, SUM(fn) AS sf FROM t GROUP BY k_null"):
+        ex = Executor(st)
+        pq = ex.plan(sql.parse(text, st.tables), 262144)
+        prep = ex.prepare(pq)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0
+        host_side = ResultSet(pq, prep["out"].cpu().numpy()).to_arrow()
+        dev_side = ResultSet.from_compact(pq, ex.compact_on_device(pq, prep["out"])).to_arrow()
+        order = [(c, "ascending") for c in host_side.column_names[:2]]
+        assert host_side.num_rows == dev_side.num_rows and host_side.num_rows > 0
+        assert host_side.sort_by(order).equals(dev_side.sort_by(order)), text
+        # and the switch itself
+        ex.compact_threshold_bytes = 0
+        assert ex.execute_work_unit(sql.parse(text, st.tables)).row_count() == host_side.num_rows
+
+
 def test_shuffle_partitions_rows_by_key(L, env, torch):
     """hdk_b200_shuffle_count / _scatter: every row lands in exactly one partition, partition = f(key) only,
     counts agree with the scatter, the multiset of rows is preserved."""
