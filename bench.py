@@ -331,6 +331,10 @@ def main():
                 "frac": dq["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": benchdata.TAXI_BYTES_PER_ROW[dominant] * rows_rank,
                 "kernel_ms": dq["scan_kernel_ms"],
+                "kernel_share_of_step": dq["scan_kernel_ms"] / (elapsed_ms / args.steps),
+                "scan_kernels_share_of_step": sum(per_query[q]["scan_kernel_ms"] for q in qnames) / (elapsed_ms / args.steps),
+                "note": "achieved = algorithmic bytes / CUDA-event time of the kernel inside the timed step; the measured peak is a "
+                        "read+write copy, a read-only stream can exceed it (nominal HBM3e: 8000 GB/s)",
                 "step_frac": sum(benchdata.TAXI_BYTES_PER_ROW[q] for q in qnames) * rows_rank / 1e9 /
                 (sum(per_query[q]["scan_kernel_ms"] for q in qnames) * 1e-3) / peak}
 
