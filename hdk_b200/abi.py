@@ -101,6 +101,11 @@ class LaunchInfo(C.Structure):
                 ("block", C.c_int32), ("smem_bytes", C.c_int32), ("n_accumulators", C.c_int32), ("tile_rows", C.c_int32)]
 
 
+class ChunkStatsPOD(C.Structure):
+    _fields_ = [("min_i", C.c_int64), ("max_i", C.c_int64), ("min_f_enc", C.c_int64), ("max_f_enc", C.c_int64),
+                ("null_count", C.c_uint64), ("row_count", C.c_uint64)]
+
+
 class WorkTableLayout(C.Structure):
     _fields_ = [("n_cells", C.c_uint64), ("sum_cells", C.c_uint64), ("sum_i64_cells", C.c_uint64),
                 ("min_cells", C.c_uint64), ("max_cells", C.c_uint64)]

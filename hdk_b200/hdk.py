@@ -126,9 +126,16 @@ class HDK:
         return self._executor
 
     def import_arrow(self, at: pa.Table, table_name: Optional[str] = None, fragment_size: Optional[int] = None,
-                     shard=None) -> QueryNode:
+                     shard=None, on_device: bool = False) -> QueryNode:
+        """on_device: copy the raw Arrow buffers to the GPU and convert them there (NULL sentinels + chunk
+        statistics, hdk_b200_materialize_nulls_on_device) instead of materialising on the host first."""
         name = table_name or f"tab_{len(self.storage.tables) + 1}"
-        self.storage.import_arrow_table(at, name, fragment_size or DEFAULT_FRAGMENT_SIZE, shard=shard)
+        if on_device:
+            import torch
+            self.storage.import_arrow_table_to_device(at, name, torch.device("cuda", self._device), fragment_size or DEFAULT_FRAGMENT_SIZE,
+                                                      shard=shard)
+        else:
+            self.storage.import_arrow_table(at, name, fragment_size or DEFAULT_FRAGMENT_SIZE, shard=shard)
         return QueryNode(self, name)
 
     def import_pydict(self, values: Dict[str, list], table_name: Optional[str] = None, **kw) -> QueryNode:

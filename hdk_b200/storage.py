@@ -192,6 +192,83 @@ class ArrowStorage:
         self.tables[name] = t
         return t
 
+    def import_arrow_table_to_device(self, at: pa.Table, name: str, device, fragment_size: int = DEFAULT_FRAGMENT_SIZE,
+                                     shard: Optional[tuple] = None) -> Table:
+        """importArrowTable with the format conversion on the GPU: the raw Arrow value and validity
+        buffers of every fixed-width column are copied to the device as they are; hdk_b200_materialize_nulls_on_device
+        writes the NULL sentinels in place and reduces the chunk statistics in the same pass.  Dictionary / string
+        and boolean columns (bit-packed or variable-width in Arrow) take the host path.  Fragments keep no host copy."""
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+        L = _lib.lib()
+        if name in self.tables:
+            raise ValueError(f"table {name} already exists")
+        host_side = [f.name for f in at.schema if pa.types.is_boolean(f.type) or pa.types.is_dictionary(f.type)
+                     or pa.types.is_string(f.type) or pa.types.is_large_string(f.type)]
+        host_tab = self.import_arrow_table(at.select(host_side), name + ".__host", fragment_size, shard) if host_side else None
+        self.tables.pop(name + ".__host", None)
+        cols: Dict[str, ColumnInfo] = {}
+        for f in at.schema:
+            if f.name in host_side:
+                cols[f.name] = host_tab.columns[f.name]
+            else:
+                sql_t, dt = _arrow_type_to_sql(f.type, f.nullable)
+                cols[f.name] = ColumnInfo(f.name, sql_t, dt.itemsize, dt, None)
+        n = at.num_rows
+        frags: List[Fragment] = []
+        stats_dev = torch.zeros(6, dtype=torch.int64, device=device)
+        fid = kept = 0
+        for off in range(0, max(n, 1), fragment_size):
+            rows = min(fragment_size, n - off)
+            if rows <= 0 and n > 0:
+                break
+            if shard is None or (fid % shard[1] == shard[0]):
+                sl = at.slice(off, rows)
+                fr = Fragment(fid, rows, off, fid % self.n_devices, {}, {})
+                for cname, ci in cols.items():
+                    if cname in host_side:
+                        hf = host_tab.fragments[kept]
+                        fr.device_chunks[cname] = torch.from_numpy(hf.chunks[cname].view(np.uint8).reshape(-1)).to(device)
+                        fr.stats[cname] = hf.stats[cname]
+                        continue
+                    w = ci.phys_width
+                    dst = torch.empty(max(rows, 1) * w, dtype=torch.uint8, device=device)
+                    _lib.check(L.hdk_b200_init_chunk_stats_on_device(stats_dev.data_ptr(), None), "init_chunk_stats")
+                    pos = 0
+                    for piece in sl.column(cname).chunks:
+                        m = len(piece)
+                        if m == 0:
+                            continue
+                        validity, data = piece.buffers()[0], piece.buffers()[1]
+                        raw = np.frombuffer(data, dtype=np.uint8)[piece.offset * w:(piece.offset + m) * w]
+                        dst[pos * w:(pos + m) * w].copy_(torch.from_numpy(raw.copy() if not raw.flags.writeable else raw))
+                        dv, bit0 = None, 0
+                        if validity is not None and piece.null_count:
+                            b0, b1 = piece.offset // 8, (piece.offset + m + 7) // 8
+                            dv = torch.from_numpy(np.frombuffer(validity, dtype=np.uint8)[b0:b1].copy()).to(device)
+                            bit0 = piece.offset - 8 * b0
+                        _lib.check(L.hdk_b200_materialize_nulls_on_device(dst.data_ptr() + pos * w, w, int(ci.type.is_fp),
+                                                                          dv.data_ptr() if dv is not None else None, bit0, m,
+                                                                          stats_dev.data_ptr(), None), "materialize_nulls")
+                        pos += m
+                    fr.device_chunks[cname] = dst
+                    s = stats_dev.cpu().numpy()
+                    if ci.type.is_fp:
+                        dec = lambda e: float(np.int64(e ^ ((e >> 63) & 0x7FFFFFFFFFFFFFFF)).view(np.float64))  # noqa: E731
+                        lo, hi = (dec(int(s[2])), dec(int(s[3]))) if int(s[2]) != abi.EMPTY_KEY_64 else (None, None)
+                    else:
+                        lo, hi = (int(s[0]), int(s[1])) if int(s[0]) != abi.EMPTY_KEY_64 else (None, None)
+                    fr.stats[cname] = ChunkStats(lo, hi, bool(s[4]))
+                frags.append(fr)
+                kept += 1
+            fid += 1
+        t = Table(name, cols, frags, sum(f.num_rows for f in frags))
+        self.tables[name] = t
+        return t
+
     def add_device_table(self, name: str, columns: Dict[str, ColumnInfo], fragments: List[Fragment]) -> Table:
         """Register fragments whose chunks already live on the device (synthetic benchmarks)."""
         t = Table(name, columns, fragments, sum(f.num_rows for f in fragments))

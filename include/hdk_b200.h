@@ -504,6 +504,29 @@ HDK_B200_API int hdk_b200_compact_result(const hdk_b200_plan* plan, const hdk_b2
                             uint64_t* row_count /* DEVICE */, void* stream);
 
 /* ============================================================================
+ * Storage-side helper on the device ("next" row: ArrowStorage -> device residency).
+ * Arrow fixed-width column data + validity bitmap, already copied to the device,
+ * become the chunk format of the hot path in place: slots whose validity bit is 0
+ * receive the in-band NULL sentinel (omniscidb/ArrowStorage/ArrowStorageUtils.cpp:100-170:
+ * INTn_MIN for integers / timestamps / date32 days, FLT_MIN / DBL_MIN for floating point), and the
+ * chunk statistics the planner needs (min, max, has_nulls — ArrowStorage.cpp:1000-1040
+ * ChunkStats; they decide perfect vs baseline hash) are reduced in the same pass.
+ * `stats` lives on the device and ACCUMULATES over calls (one call per Arrow chunk of a
+ * fragment's column); initialise it with hdk_b200_init_chunk_stats_on_device.
+ * `validity` may be NULL (no NULLs); bit i of the column is bit (bit_offset + i), LSB first.
+ * ==========================================================================*/
+typedef struct hdk_b200_chunk_stats {
+  int64_t min_i, max_i;         /* integer columns: over the non-NULL values (INT64_MAX / INT64_MIN when none) */
+  int64_t min_f_enc, max_f_enc; /* floating point: order-preserving int64 image of the double, b ^ ((b >> 63) & INT64_MAX) */
+  uint64_t null_count;          /* values equal to the sentinel after materialisation */
+  uint64_t row_count;
+} hdk_b200_chunk_stats;
+HDK_B200_API int hdk_b200_init_chunk_stats_on_device(hdk_b200_chunk_stats* stats, void* stream);
+HDK_B200_API int hdk_b200_materialize_nulls_on_device(int8_t* values, int elem_width /* 1, 2, 4, 8 */, int is_fp,
+                                                      const uint8_t* validity, int64_t bit_offset, int64_t num_elems,
+                                                      hdk_b200_chunk_stats* stats, void* stream);
+
+/* ============================================================================
  * Host-buffer convenience wrapper = what the reference-facing plugin call does
  * end to end (H2D of the chunks, init, launch, D2H of the group-by buffer and the
  * error code; QE/QueryExecutionContext.cpp:238-550).  All pointers are HOST

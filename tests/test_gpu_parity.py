@@ -211,6 +211,41 @@ def test_gather_join_payload_kernel(L, torch):
     assert L.hdk_b200_gather_join_payload_on_device(0, 4, 0, 4, 0, 0, None) != 0
 
 
+def test_arrow_import_on_device_matches_host_import(env, L, torch):
+    """raw Arrow buffers converted on the GPU (hdk_b200_materialize_nulls_on_device) must give the
+    same chunk bytes (NULL sentinels included) and the same chunk statistics as the host-side import, for every
+    column type of the test table, sliced fragments (non-zero Arrow offsets, bit offsets not multiples of 8) and
+    multi-chunk columns."""
+    from hdk_b200.storage import ArrowStorage
+    import hdk_b200.hdk as hdkmod
+    tables, _ = env
+    t = tables["t"]
+    t2 = pa.concat_tables([t.slice(0, 1234), t.slice(1234, 4321), t.slice(5555)])   # three Arrow chunks per column
+    host = ArrowStorage().import_arrow_table(t2, "t", fragment_size=3001)
+    dev = ArrowStorage().import_arrow_table_to_device(t2, "t", torch.device("cuda", 0), fragment_size=3001)
+    assert len(host.fragments) == len(dev.fragments) and host.num_rows == dev.num_rows
+    for hf, df in zip(host.fragments, dev.fragments):
+        assert hf.num_rows == df.num_rows
+        for cname in host.columns:
+            got = df.device_chunks[cname].cpu().numpy()
+            exp = hf.chunks[cname].view(np.uint8).reshape(-1)
+            assert np.array_equal(got[: exp.size], exp), cname
+            hs, ds = hf.stats[cname], df.stats[cname]
+            assert (hs.min, hs.max, hs.has_nulls) == (ds.min, ds.max, ds.has_nulls), (cname, hs, ds)
+    # and the same answers through the façade
+    res = []
+    for on_device in (False, True):
+        h = hdkmod.init()
+        h.import_arrow(t2.select(["k_null", "s", "v", "w", "fn", "g", "ts"]), "t", fragment_size=3001, on_device=on_device)
+        res.append(h.sql("SELECT k_null, COUNT(*) AS n, SUM(v) AS sv, MIN(w) AS mw, MAX(g) AS mg, COUNT(fn) AS cf FROM t GROUP BY k_null ORDER BY k_null").to_arrow())
+    assert res[0].equals(res[1])
+    # argument errors
+    assert L.hdk_b200_materialize_nulls_on_device(0, 4, 0, 0, 0, 10, 0, None) != 0
+    st = torch.zeros(6, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    assert L.hdk_b200_materialize_nulls_on_device(buf.data_ptr(), 3, 0, 0, 0, 10, st.data_ptr(), None) != 0
+
+
 def test_executor_sql_end_to_end_vs_sqlite(env, torch):
     """hdk.sql() → Arrow, against SQLite like the reference's `c()` comparator."""
     import hdk_b200.hdk as hdkmod
