@@ -39,12 +39,30 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+    NVML polling thread (5 ms period; nvidia-smi -lms needs ~100 ms to start, longer than a short timed region);
+    `mark()` brackets the timed region so that only samples taken inside it are reported.  Falls back to
+    `nvidia-smi -lms 20` when pynvml is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.samples = index, None, [], []
+        self.t0 = self.t1 = None
+        self._stop = threading.Event()
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -55,11 +73,40 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self, begin: bool):
+        if begin:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
+
+    def _poll(self):
+        n = self.nvml
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append((time.perf_counter(), float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)),
+                                     n.nvmlDeviceGetPowerUsage(self.h) / 1000.0, int(reasons_fn(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            inside = [s for s in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= s[0] <= self.t1]
+            use = inside or self.samples[-3:]
+            sm = sorted(s[1] for s in use)
+            mask = 0
+            for s in use:
+                mask |= s[3]
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm,
+                    "power_w_max": max((s[2] for s in use), default=None), "samples": len(inside),
+                    "reasons": sorted(v for k, v in self.REASONS.items() if mask & k), "source": "nvml, 5 ms period, samples inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -82,7 +129,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -292,11 +339,13 @@ def main():
     launches0 = L.hdk_b200_launch_count()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark(True)
     e_start.record()
     for s in range(args.steps):
         step(kernel_events[s])
     e_end.record()
     barrier()
+    sampler.mark(False)
     launches = L.hdk_b200_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = e_start.elapsed_time(e_end)
