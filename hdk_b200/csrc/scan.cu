@@ -498,7 +498,8 @@ __device__ __forceinline__ void reg_flush(const ScanArgs& args, RegAcc<Shape, G>
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     if (uint32_t(g) >= E) break;
-    const int64_t rows = int64_t(__reduce_add_sync(0xffffffffu, r.cnt[g]));   // (a thread sees < 2^32 rows per launch)
+    int64_t rows = int64_t(r.cnt[g]);   // (a thread sees < 2^32 rows per launch; the warp total is summed in 64 bits)
+    for (int d = 16; d; d >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, d);
     static_for<0, sp.n_acc>([&](auto A) {
       constexpr int a = decltype(A)::value;
       constexpr DPlan sp = Shape::get();
@@ -984,10 +985,16 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
             }
           }
           const double T = double(nct) * ctas;
-          const double teff = T <= 768.0 ? T : 768.0 - 0.5 * (T - 768.0);
+          // plans that gather through a join table wait on L2 / DRAM latency per row: they want more resident warps
+          // (config 5: 4.8 ms at 768 threads per SM, 2.7 ms at 1152)
+          const double t_best = p.n_joins ? 1152.0 : 768.0;
+          const double teff = T <= t_best ? T : t_best - 0.5 * (T - t_best);
           const double rpt = double(g.tile_rows) / nct;
           const bool full = g.tile_rows % (uint32_t(nct) * uint32_t(iter_rows)) == 0;
-          const double score = teff * (rpt / (rpt + 2.0)) * (full ? 1.0 : 0.5) * (stages == 2 ? rpt / (rpt + 0.7) : 1.0);
+          // (gathering plans also want the L1 the ring would take: config 5 with 3 x 384 threads, 2.7 ms with a 2-deep
+          //  ring, 4.2 ms with a 3-deep one)
+          const double ring = p.n_joins ? (stages == 2 ? 1.0 : 0.7) : (stages == 2 ? rpt / (rpt + 0.7) : 1.0);
+          const double score = teff * (rpt / (rpt + 2.0)) * (full ? 1.0 : 0.5) * ring;
           if (score > best_score) { best_score = score; *out = g; }
         }
     return best_score >= 0.0;
