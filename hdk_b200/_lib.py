@@ -25,7 +25,8 @@ EXPORTS = [
     "hdk_b200_fill_one_to_many_baseline_hash_table_on_device", "hdk_b200_probe_hash_join_on_device",
     "hdk_b200_probe_baseline_hash_join_on_device", "hdk_b200_gather_join_payload_on_device", "hdk_b200_shuffle_count", "hdk_b200_shuffle_scatter",
     "hdk_b200_compact_result", "hdk_b200_init_chunk_stats_on_device",
-    "hdk_b200_materialize_nulls_on_device", "hdk_b200_query_host", "hdk_b200_last_error", "hdk_b200_abi_version",
+    "hdk_b200_materialize_nulls_on_device", "hdk_b200_peer_alloc", "hdk_b200_peer_open", "hdk_b200_peer_close",
+    "hdk_b200_peer_free", "hdk_b200_exchange_bytes", "hdk_b200_exchange_init", "hdk_b200_launch_exchange", "hdk_b200_query_host", "hdk_b200_last_error", "hdk_b200_abi_version",
     "hdk_b200_device_count", "hdk_b200_launch_count",
 ]
 
@@ -61,6 +62,13 @@ def _bind(lib):
         "hdk_b200_compact_result": (ci, [P, Q, vp, vp, vp, vp]),
         "hdk_b200_init_chunk_stats_on_device": (ci, [vp, vp]),
         "hdk_b200_materialize_nulls_on_device": (ci, [vp, ci, ci, vp, i64, i64, vp, vp]),
+        "hdk_b200_peer_alloc": (ci, [sz, C.POINTER(vp), vp]),
+        "hdk_b200_peer_open": (ci, [vp, C.POINTER(vp)]),
+        "hdk_b200_peer_close": (ci, [vp]),
+        "hdk_b200_peer_free": (ci, [vp]),
+        "hdk_b200_exchange_bytes": (ci, [P, Q, ci, C.POINTER(sz)]),
+        "hdk_b200_exchange_init": (ci, [vp, vp]),
+        "hdk_b200_launch_exchange": (ci, [P, Q, KO, KP, vp, sz, C.POINTER(vp), ci, ci, u64, vp, LI]),
         "hdk_b200_query_host": (ci, [P, Q, vp, vp, u64, vp, vp, vp, vp, vp, ci, LI]),
         "hdk_b200_last_error": (C.c_char_p, []),
         "hdk_b200_abi_version": (ci, []),

@@ -167,6 +167,13 @@ struct FinalizeArgs {
   const int64_t* work;
   uint64_t acc_stride, entry_stride;   // cell (acc, e) = work[acc * acc_stride + e * entry_stride]
   int32_t baseline;                // baseline hash: keys were written by the scan's claim; empty entries keep the caller's init
+  // multi-GPU exchange: `work` points at n_peers slots of `slot_cells` cells (one partial table per rank)
+  uint32_t n_peers;
+  uint64_t slot_cells;
+  uint64_t epoch;
+  const unsigned long long* flags; // [n_peers] flags of this epoch's parity
+  int32_t* error_codes;
+  AccKinds kinds;
   int8_t* buf;                     // direct pointer, or
   int64_t* const* buf_indirect;    // GROUPBY_BUF-style device array of pointers ([0] is used)
 };
@@ -180,13 +187,47 @@ __device__ __forceinline__ void store_slot(int8_t* p, int bytes, int padded, int
   }
 }
 
+// merge of one accumulator cell over the ranks' partial tables (kMerged) or the plain work-table cell
+template <bool kMerged>
+__device__ __forceinline__ int64_t work_cell(const FinalizeArgs& a, int acc, uint64_t e) {
+  const uint64_t i = uint64_t(acc) * a.acc_stride + e * a.entry_stride;
+  if (!kMerged) return a.work[i];
+  const uint8_t kind = a.kinds.kind[acc];
+  int64_t x = __ldcg(a.work + i);
+  for (uint32_t r = 1; r < a.n_peers; ++r) {
+    const int64_t y = __ldcg(a.work + uint64_t(r) * a.slot_cells + i);
+    if (kind == ACC_SUM_F) x = __double_as_longlong(__longlong_as_double(x) + __longlong_as_double(y));
+    else if (kind == ACC_MIN_I || kind == ACC_MIN_F) x = min(x, y);
+    else if (kind == ACC_MAX_I || kind == ACC_MAX_F) x = max(x, y);
+    else x += y;   // counters, int64 SUM
+  }
+  return x;
+}
+
+template <bool kMerged>
 __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
   const DLayout& L = a.layout;
   const uint64_t E = a.entry_count;
   const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
   int8_t* const buf = a.buf ? a.buf : reinterpret_cast<int8_t*>(a.buf_indirect[0]);
+  if (kMerged) {
+    // wait until every rank has published its table of this epoch (flags are written after a system-wide fence)
+    if (threadIdx.x == 0) {
+      bool ok = true;
+      for (uint32_t r = 0; r < a.n_peers && ok; ++r) {
+        uint64_t spins = 0;
+        while (*reinterpret_cast<const volatile unsigned long long*>(a.flags + r) < a.epoch) {
+          if (++spins > (1ull << 22)) { ok = false; break; }   // a few seconds: a peer died or never launched — report, do not hang
+          __nanosleep(100);
+        }
+      }
+      if (!ok) record_error(a.error_codes, HDK_B200_ERR_PEER_TIMEOUT);
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
   for (uint64_t e = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; e < E; e += step) {
-    const int64_t rows = a.work[e * a.entry_stride];  // accumulator 0 = rows in the group
+    const int64_t rows = work_cell<kMerged>(a, 0, e);  // accumulator 0 = rows in the group
     const bool empty = rows == 0;
     if (a.baseline && empty) continue;
     int8_t* row = L.columnar ? nullptr : buf + e * L.row_bytes;
@@ -214,11 +255,11 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
             v = is_null ? int_null_of(sl.key_width) : ky.min_val + comp[sl.key_index];
             break;
           }
-          case SLOT_COUNT: v = a.work[uint64_t(sl.acc) * a.acc_stride + e * a.entry_stride]; break;
+          case SLOT_COUNT: v = work_cell<kMerged>(a, sl.acc, e); break;
           default: {
-            const bool any = !sl.skip_null || a.work[uint64_t(sl.acc_cnt) * a.acc_stride + e * a.entry_stride] != 0;
+            const bool any = !sl.skip_null || work_cell<kMerged>(a, sl.acc_cnt, e) != 0;
             if (any || sl.is_avg_sum) {
-              const int64_t cell = a.work[uint64_t(sl.acc) * a.acc_stride + e * a.entry_stride];
+              const int64_t cell = work_cell<kMerged>(a, sl.acc, e);
               if (sl.is_fp) {
                 const double d = sl.op == SLOT_SUM ? __longlong_as_double(cell) : f64_order_decode(cell);
                 v = sl.bytes == 4 ? int64_t(__float_as_uint(float(d))) : __double_as_longlong(d);
@@ -256,7 +297,31 @@ int launch_finalize(const Lowered& lw, const int64_t* work_table, int64_t* group
   a.acc_stride = a.baseline ? 1 : a.entry_count;
   a.entry_stride = a.baseline ? uint64_t(lw.plan.n_acc) : 1;
   a.buf = reinterpret_cast<int8_t*>(groups_buffer);
-  finalize_kernel<<<grid_for(a.entry_count, 128), 128, 0, stream>>>(a);
+  finalize_kernel<false><<<grid_for(a.entry_count, 128), 128, 0, stream>>>(a);
+  HB_LAUNCH_CHECK();
+  return HDK_B200_OK;
+}
+
+int launch_finalize_exchange(const Lowered& lw, const int64_t* slots, const unsigned long long* flags, uint32_t n_peers, uint64_t epoch,
+                             int32_t* error_codes, int64_t* const* groups_buffer_indirect, cudaStream_t stream) {
+  FinalizeArgs a{};
+  a.buf_indirect = groups_buffer_indirect;
+  a.layout = lw.layout;
+  for (int k = 0; k < lw.plan.n_keys; ++k) a.keys[k] = lw.plan.keys[k];
+  a.n_keys = lw.plan.n_keys;
+  a.entry_count = lw.plan.entry_count;
+  a.work = slots;
+  a.baseline = 0;
+  a.acc_stride = a.entry_count;
+  a.entry_stride = 1;
+  a.n_peers = n_peers;
+  a.slot_cells = (uint64_t(lw.plan.n_acc) * lw.plan.entry_count + 1) & ~uint64_t(1);
+  a.epoch = epoch;
+  a.flags = flags;
+  a.error_codes = error_codes;
+  for (int i = 0; i < lw.plan.n_acc; ++i) a.kinds.kind[i] = lw.plan.accs[i].kind;
+  // few CTAs: each one spins on the flags first
+  finalize_kernel<true><<<std::min(grid_for(a.entry_count, 128), sm_count()), 128, 0, stream>>>(a);
   HB_LAUNCH_CHECK();
   return HDK_B200_OK;
 }

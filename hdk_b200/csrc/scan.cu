@@ -801,6 +801,28 @@ scan_kernel(const __grid_constant__ ScanArgs args) {
       }
     }
   }
+
+  // ---- multi-GPU exchange: the last CTA to finish publishes this GPU's partial table to every peer ----
+  if (args.n_peers) {
+    __shared__ bool is_last;
+    __threadfence();     // this thread's atomics on the local work table are visible device-wide
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(args.ticket, 1ull) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const uint64_t n2 = args.n_cells / 2;   // 16-byte pieces (the table is 16-byte aligned)
+      for (uint32_t pr = 0; pr < args.n_peers; ++pr) {
+        longlong2* dst = reinterpret_cast<longlong2*>(args.peer_slot[pr]);
+        const longlong2* src = reinterpret_cast<const longlong2*>(args.work_table);
+        for (uint64_t i = tid; i < n2; i += blockDim.x) dst[i] = __ldcg(src + i);
+        if ((args.n_cells & 1) && tid == 0) args.peer_slot[pr][args.n_cells - 1] = __ldcg(args.work_table + args.n_cells - 1);
+      }
+      __threadfence_system();   // the copies are visible on the peers before the flags
+      __syncthreads();
+      if (uint32_t(tid) < args.n_peers) *reinterpret_cast<volatile unsigned long long*>(args.peer_flag[tid]) = args.epoch;
+    }
+  }
 }
 
 // ---- pre-compiled plan shapes ------------------------------------------------------------------
@@ -881,7 +903,8 @@ int init_work_table(const Lowered& lw, int64_t* work_table, cudaStream_t stream)
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
-                            int64_t* work_table, bool baseline, cudaStream_t stream, hdk_b200_launch_info* info) {
+                            int64_t* work_table, bool baseline, cudaStream_t stream, hdk_b200_launch_info* info,
+                            const ExchangeTargets* xchg = nullptr) {
   const DPlan& p = lw.plan;
   if (params->num_fragments > kMaxFragments) { set_error("more than %d fragments per launch", kMaxFragments); return HDK_B200_E_UNSUPPORTED; }
   ScanArgs a{};
@@ -895,6 +918,13 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   a.error_codes = params->error_codes;
   a.layout = lw.layout;
   a.groupby_buf = params->groupby_buf;
+  if (xchg) {
+    a.n_peers = xchg->n_peers;
+    a.n_cells = uint64_t(p.n_acc) * p.entry_count;
+    a.epoch = xchg->epoch;
+    a.ticket = xchg->ticket;
+    for (uint32_t i = 0; i < xchg->n_peers; ++i) { a.peer_slot[i] = xchg->peer_slot[i]; a.peer_flag[i] = xchg->peer_flag[i]; }
+  }
 
   int dev = 0;
   HB_CUDA(cudaGetDevice(&dev));
@@ -1101,6 +1131,10 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
 int launch_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
                 int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info) {
   return launch_scan_impl(lw, ko, params, work_table, false, stream, info);
+}
+int launch_scan_exchange(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
+                         int64_t* work_table, const ExchangeTargets& x, cudaStream_t stream, hdk_b200_launch_info* info) {
+  return launch_scan_impl(lw, ko, params, work_table, false, stream, info, &x);
 }
 int launch_baseline_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
                          int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info) {

@@ -31,6 +31,13 @@ struct ScanArgs {
   uint32_t full_iters;                // static shapes: iterations of the full-tile loop (tile_rows / (consumer_threads * iter rows)); 0 = off
   uint32_t consumer_threads;          // consumer threads per CTA (multiple of 32, <= kConsumerThreads); blockDim = that + 32
   uint32_t off_tile_prefix, off_bins, off_stages;   // dynamic shared memory map
+  // multi-GPU exchange (hdk_b200_launch_exchange): the last CTA publishes the work table to every peer
+  uint32_t n_peers;                   // 0 = single-GPU launch
+  uint64_t n_cells;                   // n_acc * entry_count
+  uint64_t epoch;
+  unsigned long long* ticket;         // CTAs-done counter behind the work table, zeroed with it
+  int64_t* peer_slot[HDK_B200_MAX_PEERS];              // slot `my_rank` of peer p's exchange buffer (this epoch's parity)
+  unsigned long long* peer_flag[HDK_B200_MAX_PEERS];   // flag `my_rank` of peer p
   uint32_t acc_bin_off[kMaxAcc];                    // from off_bins
   uint32_t col_region_off[HDK_B200_MAX_COLS];       // from a stage's base
 };
@@ -40,6 +47,18 @@ int launch_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_
                 int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info);
 int launch_finalize(const Lowered& lw, const int64_t* work_table, int64_t* groups_buffer, int64_t* const* groups_buffer_indirect,
                     cudaStream_t stream);
+// exchange variants (peer.cu)
+struct ExchangeTargets {
+  uint32_t n_peers;
+  uint64_t epoch;
+  unsigned long long* ticket;
+  int64_t* peer_slot[HDK_B200_MAX_PEERS];
+  unsigned long long* peer_flag[HDK_B200_MAX_PEERS];
+};
+int launch_scan_exchange(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
+                         int64_t* work_table, const ExchangeTargets& x, cudaStream_t stream, hdk_b200_launch_info* info);
+int launch_finalize_exchange(const Lowered& lw, const int64_t* slots, const unsigned long long* flags, uint32_t n_peers, uint64_t epoch,
+                             int32_t* error_codes, int64_t* const* groups_buffer_indirect, cudaStream_t stream);
 int launch_baseline_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
                          int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info);
 

@@ -10,6 +10,11 @@ are merged on the host (QE/Execute.cpp:1224-1336).  Three exchange patterns (SUR
                              (hdk_b200_shuffle_count / _scatter, model: QE/RelAlgExecutor.cpp:691-838)
                              → all-to-all → local aggregate; results are disjoint, no merge
   * small join build side  : built once on rank 0, broadcast (table + inner columns)
+
+`PeerExchange` replaces the all-reduce of the first pattern by the library's own exchange over peer memory
+(hdk_b200_launch_exchange: the scan kernel's last CTA stores this GPU's partial table into every peer's exchange
+buffer through NVLink and raises a flag; every finalize kernel waits for the flags and merges) — NCCL then only
+carries the one-time IPC handle exchange.
 """
 from __future__ import annotations
 
@@ -111,3 +116,54 @@ def broadcast_tensor(t: Optional[torch.Tensor], nbytes: int, device, src: int = 
     if is_dist() and world() > 1:
         dist.broadcast(t, src=src, group=group)
     return t
+
+
+class PeerExchange:
+    """Peer-visible exchange buffers of one plan (hdk_b200_peer_alloc + CUDA IPC handles gathered through the process
+    group).  `ptrs()` is the host array hdk_b200_launch_exchange wants; `next_epoch()` the per-launch counter."""
+
+    def __init__(self, lib, plan, qmd, device, group=None):
+        import ctypes as C
+
+        from . import _lib
+        self.lib, self.rank, self.world = lib, rank(), world()
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.hdk_b200_exchange_bytes(C.byref(plan), C.byref(qmd), self.world, C.byref(nbytes)), "exchange_bytes")
+        self.nbytes = nbytes.value
+        self.local = C.c_void_p(0)
+        handle = (C.c_uint8 * 64)()
+        _lib.check(lib.hdk_b200_peer_alloc(self.nbytes, C.byref(self.local), handle), "peer_alloc")
+        _lib.check(lib.hdk_b200_exchange_init(self.local, None), "exchange_init")
+        torch.cuda.synchronize(device)
+        self.opened = []
+        self._ptrs = (C.c_void_p * self.world)()
+        self._ptrs[self.rank] = self.local.value
+        if self.world > 1:
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=device)
+            gathered = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(gathered, mine, group=group)
+            for r, g in enumerate(gathered):
+                if r == self.rank:
+                    continue
+                hb = (C.c_uint8 * 64)(*g.cpu().tolist())
+                p = C.c_void_p(0)
+                _lib.check(lib.hdk_b200_peer_open(hb, C.byref(p)), f"peer_open(rank {r})")
+                self.opened.append(p)
+                self._ptrs[r] = p.value
+            dist.barrier(group=group)    # every rank's flags are zeroed and mapped before the first launch
+        self.epoch = 0
+
+    def ptrs(self):
+        return self._ptrs
+
+    def next_epoch(self) -> int:
+        self.epoch += 1
+        return self.epoch
+
+    def close(self):
+        for p in self.opened:
+            self.lib.hdk_b200_peer_close(p)
+        self.opened = []
+        if self.local:
+            self.lib.hdk_b200_peer_free(self.local)
+            self.local = None

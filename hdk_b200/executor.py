@@ -486,6 +486,20 @@ class Executor:
         _lib.check(self.lib.hdk_b200_work_table_layout_get(C.byref(pq.plan), C.byref(pq.qmd), C.byref(wl)), "work_table_layout")
         return wl
 
+    def launch_exchange(self, pq: planner.PlannedQuery, prep, xchg, ko: Optional[abi.KernelOptions] = None):
+        """Multi-GPU perfect-hash launch with the merge over peer memory (hdk_b200_launch_exchange): init + scan +
+        publish to every rank + wait / merge / finalize, no NCCL call.  `xchg`: distributed.PeerExchange of this plan."""
+        st = self.ctx.stream_ptr()
+        info = abi.LaunchInfo()
+        need = prep["scratch_bytes"] + 80
+        if prep["scratch"].numel() < need:
+            prep["scratch"] = self.ctx.get_scratch(need)
+        _lib.check(self.lib.hdk_b200_launch_exchange(C.byref(pq.plan), C.byref(pq.qmd), C.byref(ko) if ko is not None else None,
+                                                     C.byref(prep["kp"]), prep["scratch"].data_ptr(), prep["scratch"].numel(),
+                                                     xchg.ptrs(), xchg.world, xchg.rank, xchg.next_epoch(), st, C.byref(info)),
+                   "launch_exchange")
+        return info
+
     def launch_partial(self, pq: planner.PlannedQuery, prep, ko: Optional[abi.KernelOptions] = None):
         """scan this rank's fragments into the neutral work table (asynchronous)."""
         st = self.ctx.stream_ptr()

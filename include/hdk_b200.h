@@ -491,6 +491,40 @@ HDK_B200_API int hdk_b200_shuffle_scatter(const hdk_b200_plan* plan, const hdk_b
                              int8_t* const* out_cols /* DEVICE array [n_cols] */, void* stream);
 
 /* ============================================================================
+ * Multi-GPU merge of perfect-hash partials over peer memory (NVLink / NVSwitch), one process per GPU.
+ * The reference merges per-device result sets on the host (Executor::reduceMultiDeviceResultSets,
+ * QE/Execute.cpp:1224-1336); here the scan kernel itself publishes this GPU's neutral partial table:
+ * the last CTA to finish copies it into slot `my_rank` of EVERY peer's exchange buffer with plain
+ * 16-byte stores over NVLink and raises a flag there; the finalize kernel of each GPU waits for the
+ * n_peers flags of the current epoch, merges the slots (SUM / MIN / MAX per accumulator) and writes
+ * the reference-encoded buffer.  No NCCL call and no host synchronisation on the data path.
+ *
+ *   exchange buffer (one per rank and plan, peer-visible):
+ *     flags[2][HDK_B200_MAX_PEERS] uint64 | parity 0: n_peers slots x cells int64 | parity 1: the same
+ *   `epoch` (1, 2, 3, ...) is the caller's launch counter for this plan, equal on all ranks; its parity
+ *   selects the half, so a fast rank can publish epoch e+1 while a slow one still merges epoch e.
+ *
+ * hdk_b200_peer_* wrap cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle so that the buffers can be
+ * shared between the per-GPU processes (handles travel through the host-side process group).
+ * ==========================================================================*/
+#define HDK_B200_MAX_PEERS 16
+#define HDK_B200_IPC_HANDLE_BYTES 64
+#define HDK_B200_ERR_PEER_TIMEOUT 1004 /* a peer's flag did not arrive (in-band error code, positive = persistent) */
+HDK_B200_API int hdk_b200_peer_alloc(size_t bytes, void** dev_ptr, uint8_t handle[HDK_B200_IPC_HANDLE_BYTES]);
+HDK_B200_API int hdk_b200_peer_open(const uint8_t handle[HDK_B200_IPC_HANDLE_BYTES], void** dev_ptr);
+HDK_B200_API int hdk_b200_peer_close(void* dev_ptr);
+HDK_B200_API int hdk_b200_peer_free(void* dev_ptr);
+HDK_B200_API int hdk_b200_exchange_bytes(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, int n_peers, size_t* bytes);
+/* zero the flags of a local exchange buffer (once per buffer; barrier across ranks before the first launch) */
+HDK_B200_API int hdk_b200_exchange_init(void* local_exchange, void* stream);
+/* init work table + scan (+ publish to peers) + wait / merge / finalize.  scratch: hdk_b200_plan_check bytes + 64.
+ * peer_exchange: HOST array [n_peers] of DEVICE pointers, entry r = rank r's exchange buffer as mapped here. */
+HDK_B200_API int hdk_b200_launch_exchange(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, const hdk_b200_kernel_options* ko,
+                                          const hdk_b200_kernel_params* params, void* scratch, size_t scratch_bytes,
+                                          void* const* peer_exchange, int n_peers, int my_rank, uint64_t epoch, void* stream,
+                                          hdk_b200_launch_info* info);
+
+/* ============================================================================
  * Result-set side helpers on the device ("next" row: ResultSet → Arrow).
  * Compact the non-empty entries (ResultSetStorage::isEmptyEntry,
  * omniscidb/ResultSet/ResultSetStorage.cpp:439-525) of a group-by buffer into

@@ -532,6 +532,87 @@ def test_compact_result_matches_iteration(oracle_mod, L, env, torch, idx):
     assert np.array_equal(key(got), key(vals))
 
 
+def _alloc_exchange(L, pq, n_peers):
+    nbytes = C.c_size_t(0)
+    assert L.hdk_b200_exchange_bytes(C.byref(pq.plan), C.byref(pq.qmd), n_peers, C.byref(nbytes)) == 0
+    ptr, handle = C.c_void_p(0), (C.c_uint8 * 64)()
+    assert L.hdk_b200_peer_alloc(nbytes.value, C.byref(ptr), handle) == 0, L.hdk_b200_last_error()
+    assert L.hdk_b200_exchange_init(ptr, None) == 0
+    return ptr
+
+
+@pytest.mark.parametrize("idx", [0, 1, 3, 5, 6, 7, 16])
+def test_peer_exchange_single_rank(oracle_mod, L, env, torch, idx):
+    """hdk_b200_launch_exchange with one rank: ticket, publish into the own slot, flag, wait + merge + finalize —
+    several epochs through both parities — must equal the plain launch."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    text, nk, kw = QUERIES[idx]
+    ex = Executor(st, kw.get("cfg"))
+    pq = ex.plan(sql.parse(text, st.tables), kw.get("max_groups_buffer_entry_count"), kw.get("output_columnar"))
+    prep = ex.prepare(pq)
+    xp = _alloc_exchange(L, pq, 1)
+    torch.cuda.synchronize()
+    ptrs = (C.c_void_p * 1)(xp.value)
+    scratch = torch.empty(prep["scratch_bytes"] + 128, dtype=torch.uint8, device="cuda")
+    try:
+        for epoch in (1, 2, 3):
+            prep["out"].zero_()
+            info = abi.LaunchInfo()
+            rc = L.hdk_b200_launch_exchange(C.byref(pq.plan), C.byref(pq.qmd), None, C.byref(prep["kp"]), scratch.data_ptr(), scratch.numel(),
+                                            ptrs, 1, 0, epoch, None, C.byref(info))
+            assert rc == 0, L.hdk_b200_last_error()
+            torch.cuda.synchronize()
+            assert int(prep["err"].item()) == 0
+            check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+        assert L.hdk_b200_launch_exchange(C.byref(pq.plan), C.byref(pq.qmd), None, C.byref(prep["kp"]), scratch.data_ptr(), scratch.numel(),
+                                          ptrs, 1, 0, 0, None, None) != 0       # epoch 0 is reserved
+        assert L.hdk_b200_launch_exchange(C.byref(pq.plan), C.byref(pq.qmd), None, C.byref(prep["kp"]), scratch.data_ptr(), 8,
+                                          ptrs, 1, 0, 4, None, None) != 0       # scratch too small
+    finally:
+        torch.cuda.synchronize()
+        L.hdk_b200_peer_free(xp)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 6, 7])
+def test_peer_exchange_two_ranks_on_one_gpu(oracle_mod, L, env, torch, idx):
+    """The exchange protocol with two "ranks" sharing this GPU: each owns half of the fragments, its own stream,
+    scratch, output buffer and exchange buffer; each publishes into both exchange buffers.  Both outputs must be the
+    result over ALL fragments (bit-exact for integers), for several epochs."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    text, nk, kw = QUERIES[idx]
+    ex = Executor(st, kw.get("cfg"))
+    pq = ex.plan(sql.parse(text, st.tables), kw.get("max_groups_buffer_entry_count"), kw.get("output_columnar"))
+    frags = st.get_table("t").fragments
+    halves = [frags[0::2], frags[1::2]]
+    preps = [ex.prepare(pq, fragments=h) for h in halves]
+    xs = [_alloc_exchange(L, pq, 2) for _ in range(2)]
+    ptrs = (C.c_void_p * 2)(xs[0].value, xs[1].value)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    scr = [torch.empty(preps[0]["scratch_bytes"] + 128, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    try:
+        for epoch in (1, 2, 3, 4):
+            for r in (0, 1):
+                preps[r]["out"].zero_()
+            torch.cuda.synchronize()
+            for r in ((0, 1) if epoch % 2 else (1, 0)):       # alternate who goes first
+                rc = L.hdk_b200_launch_exchange(C.byref(pq.plan), C.byref(pq.qmd), None, C.byref(preps[r]["kp"]), scr[r].data_ptr(),
+                                                scr[r].numel(), ptrs, 2, r, epoch, streams[r].cuda_stream, None)
+                assert rc == 0, L.hdk_b200_last_error()
+            torch.cuda.synchronize()
+            for r in (0, 1):
+                assert int(preps[r]["err"].item()) == 0
+                check_against_oracle(oracle_mod, st, pq, preps[r]["out"].cpu().numpy(), nk)
+    finally:
+        torch.cuda.synchronize()
+        for x in xs:
+            L.hdk_b200_peer_free(x)
+
+
 def test_executor_iterates_large_buffers_on_device(env, torch):
     """execute_work_unit switches to device-side compaction above a buffer-size threshold; the Arrow result must
     not depend on which side iterated the buffer (same buffer decoded both ways, bit for bit)."""
