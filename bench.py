@@ -241,6 +241,8 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=128_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--merge", choices=["p2p", "nccl"], default="p2p",
+                    help="N > 1: merge partial tables inside the kernels over peer memory (default) or with NCCL all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -298,9 +300,33 @@ def main():
         layouts[q] = ex.work_table_layout(pq)
     stream_ptr = ex.ctx.stream_ptr()
 
+    # multi-GPU merge of the partial tables: the library's own exchange over peer memory (NVLink stores + flags inside
+    # the scan / finalize kernels, hdk_b200_launch_exchange) or, as the fallback / comparison, NCCL all-reduce
+    merge = args.merge if world > 1 else "none"
+    xchg = {}
+    if merge == "p2p":
+        ok = 1
+        try:
+            for q in qnames:
+                preps[q]["scratch"] = torch.empty(preps[q]["scratch_bytes"] + 128, dtype=torch.uint8, device=device)
+                xchg[q] = D.PeerExchange(L, pqs[q].plan, pqs[q].qmd, device)
+        except Exception as e:   # no peer access on this box: every rank must take the same path
+            print(f"[bench] peer exchange unavailable on rank {rank}: {e}", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            merge = "nccl"
+
     def run_query(q, ev=None):
         pq, prep = pqs[q], preps[q]
-        prep["err"].zero_()
+        if merge == "p2p":
+            if ev is not None:
+                ev[0].record()
+            info = ex.launch_exchange(pq, prep, xchg[q])
+            if ev is not None:
+                ev[1].record()
+            return info
         _lib.check(L.hdk_b200_init_work_table(C.byref(pq.plan), C.byref(pq.qmd), prep["scratch"].data_ptr(), stream_ptr), "init_work_table")
         if ev is not None:
             ev[0].record()
@@ -328,6 +354,18 @@ def main():
     for _ in range(max(args.warmup, 3)):
         infos = step()
     barrier()
+    if merge == "p2p":
+        # a peer flag that never arrived is reported in band (1004): fall back to NCCL on every rank rather than fail
+        bad = torch.tensor([max(int(preps[q]["err"].item()) for q in qnames)], dtype=torch.int32, device=device)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()) != 0:
+            print(f"[bench] peer exchange reported {int(bad.item())}; using NCCL all-reduce", file=sys.stderr)
+            merge = "nccl"
+            for q in qnames:
+                preps[q]["err"].zero_()
+            for _ in range(max(args.warmup, 3)):
+                infos = step()
+            barrier()
     for q in qnames:
         assert int(preps[q]["err"].item()) == 0, f"{q}: in-band error"
 
@@ -347,6 +385,8 @@ def main():
     barrier()
     sampler.mark(False)
     launches = L.hdk_b200_launch_count() - launches0
+    for q in qnames:
+        assert int(preps[q]["err"].item()) == 0, f"{q}: in-band error {int(preps[q]['err'].item())} inside the timed region"
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = e_start.elapsed_time(e_end)
     tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
@@ -393,7 +433,10 @@ def main():
         "dtype": "int64/f64", "data": "synthetic",
         "config": {"workload": "NYC-taxi-shaped synthetic table, taxi benchmark Q1-Q4 (BASELINE.json configs[1])",
                    "rows_per_gpu": rows_rank, "total_rows": rows_rank * world, "fragment_rows": benchdata.FRAGMENT_ROWS,
-                   "queries": 4, "parallelism": f"fragments sharded per GPU x{world}; perfect-hash partials merged by NCCL all-reduce",
+                   "queries": 4, "parallelism": f"fragments sharded per GPU x{world}; perfect-hash partials merged " +
+                   ({"p2p": "inside the scan / finalize kernels over peer memory (NVLink stores + flags, no NCCL on the data path)",
+                     "nccl": "by NCCL all-reduce", "none": "locally (one GPU)"}[merge]),
+                   "merge": merge,
                    "l2": "inputs (4.4-19.8 GB per query) are larger than the 126 MB L2", "data_gen_s": gen_s},
         "roofline": roofline, "per_query": per_query, "gpu_launches": int(launches),
     }

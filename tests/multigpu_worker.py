@@ -53,6 +53,25 @@ def main():
         obuf, oerr = util.run_oracle(oracle, full, pq_full)
         exp = util.sort_rows(util.result_columns(oracle, pq_full, obuf), nk)
         util.assert_rows_equal(got, exp)
+    # (1b) the same plans with the merge over peer memory (hdk_b200_launch_exchange) instead of NCCL, three epochs each
+    for text, nk in [("SELECT s, COUNT(*), SUM(v), MIN(v), MAX(v), AVG(f) FROM t GROUP BY s", 1),
+                     ("SELECT k, s, COUNT(v), SUM(f), MIN(f) FROM t WHERE f > -50 GROUP BY k, s", 2),
+                     ("SELECT dim.attr, SUM(t.f), COUNT(*) FROM t JOIN dim ON t.fk = dim.pk GROUP BY dim.attr", 1)]:
+        pq = ex.plan(sql.parse(text, st.tables))
+        prep = ex.prepare(pq)
+        xchg = D.PeerExchange(ex.lib, pq.plan, pq.qmd, torch.device("cuda", local))
+        pq_full = util.plan_sql(full, text)
+        obuf, oerr = util.run_oracle(oracle, full, pq_full)
+        exp = util.sort_rows(util.result_columns(oracle, pq_full, obuf), nk)
+        for _ in range(3):
+            prep["out"].zero_()
+            ex.launch_exchange(pq, prep, xchg)
+            torch.cuda.synchronize()
+            assert int(prep["err"].item()) == 0, f"in-band error {int(prep['err'].item())}"
+            got = util.sort_rows(util.result_columns(oracle, pq, prep["out"].cpu().numpy()), nk)
+            util.assert_rows_equal(got, exp)
+        dist.barrier()
+        xchg.close()
     # (2) baseline hash: shuffle by key hash → all-to-all → local aggregate; union of ranks = full result
     text = "SELECT big, s, SUM(v), COUNT(*), SUM(f) FROM t GROUP BY big, s"
     rs, n_recv = ex.execute_partitioned(sql.parse(text, st.tables), 262144)
