@@ -72,7 +72,8 @@ class Key(C.Structure):
 class Join(C.Structure):
     _fields_ = [("key_expr", C.c_int32), ("one_to_many", C.c_int32), ("min_key", C.c_int64),
                 ("max_key", C.c_int64), ("null_val", C.c_int64), ("key_nullable", C.c_int32), ("payload_by_slot", C.c_int32),
-                ("entry_count", C.c_int64)]
+                ("entry_count", C.c_int64), ("n_key_exprs", C.c_int32), ("key_width", C.c_int32),
+                ("key_exprs", C.c_int32 * MAX_KEYS)]
 
 
 class Plan(C.Structure):

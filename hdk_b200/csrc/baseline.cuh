@@ -6,6 +6,8 @@
 //   claim          CAS on the first key component; the winner publishes the rest; others wait until
 //                  the rest is published, then compare                      (QE/cuda_mapd_rt.cu:176-236, 240-321)
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace hb {
@@ -120,6 +122,69 @@ __device__ __forceinline__ int64_t baseline_claim_columnar(int64_t* buf64, uint3
     h = h + 1 == E ? 0 : h + 1;
   } while (h != h0);
   return -1;
+}
+
+// ---- baseline JOIN tables (JHT/BaselineJoinHashTable.cpp): E x (key components ‖ payload), MurmurHash1 ----------
+__device__ __forceinline__ uint32_t murmur1_dev(const void* key, int len) {
+  // MurmurHash1 (QE/MurmurHash1Inl.h), seed 0; len is a multiple of 4 here
+  const unsigned int m = 0xc6a4a793u;
+  unsigned int h = 0u ^ (unsigned(len) * m);
+  const unsigned int* d = static_cast<const unsigned int*>(key);
+  for (int i = 0; i < len / 4; ++i) {
+    h += d[i];
+    h *= m;
+    h ^= h >> 16;
+  }
+  h *= m;
+  h ^= h >> 10;
+  h *= m;
+  h ^= h >> 17;
+  return h;
+}
+
+// claim-or-find the entry of `key`: CAS the first component, publish the rest, wait for the rest
+// (get_matching_baseline_hash_slot_at, HashJoinRuntime.cpp:359-394)
+template <typename T>
+__device__ __forceinline__ T* baseline_slot(int8_t* hash_buff, int64_t E, const T* key, int kc, size_t entry_sz, bool insert) {
+  using U = typename std::conditional<sizeof(T) == 4, unsigned int, unsigned long long>::type;
+  const T empty = sizeof(T) == 4 ? T(HDK_B200_EMPTY_KEY_32) : T(HDK_B200_EMPTY_KEY_64);
+  const uint32_t h0 = murmur1_dev(key, kc * int(sizeof(T))) % uint32_t(E);
+  uint32_t h = h0;
+  do {
+    T* row = reinterpret_cast<T*>(hash_buff + size_t(h) * entry_sz);
+    T first = *reinterpret_cast<volatile T*>(row);
+    if (first == empty) {
+      if (!insert) return nullptr;
+      first = T(atomicCAS(reinterpret_cast<U*>(row), U(empty), U(key[0])));
+      if (first == empty) {
+        for (int i = 1; i < kc; ++i) atomicExch(reinterpret_cast<U*>(row + i), U(key[i]));
+        return row + kc;
+      }
+    }
+    if (first == key[0]) {
+      bool match = true;
+      for (int i = 1; i < kc && match; ++i) {
+        T v;
+        while ((v = *reinterpret_cast<volatile T*>(row + i)) == empty) {
+        }
+        match = v == key[i];
+      }
+      if (match) return row + kc;
+    }
+    h = h + 1 == uint32_t(E) ? 0 : h + 1;
+  } while (h != h0);
+  return nullptr;
+}
+
+
+// probe of the one-to-one layout from the fused scan kernel: row id of the matching inner row, or -1
+// (baseline_hash_join_idx_{32,64}, JHT/Runtime/JoinHashTableQueryRuntime.cpp:43-98)
+template <typename T>
+__device__ __forceinline__ int64_t baseline_join_probe(const int8_t* table, int64_t E, const int64_t* key64, int kc) {
+  T key[HDK_B200_MAX_KEYS];
+  for (int i = 0; i < kc; ++i) key[i] = T(key64[i]);
+  const T* slot = baseline_slot<T>(const_cast<int8_t*>(table), E, key, kc, size_t(kc + 1) * sizeof(T), false);
+  return slot ? int64_t(*slot) : -1;
 }
 
 }  // namespace hb

@@ -70,10 +70,14 @@ struct DKey {           // 40 bytes
   uint8_t has_nulls, width, pad0, pad1;
 };
 
-struct DJoin {          // 32 bytes
+struct DJoin {          // 48 bytes
   int64_t min_key, max_key, null_val;
-  int32_t key_expr;
+  int32_t key_expr;     // perfect: the key node; baseline: the last component in node order (probe point)
   uint8_t key_nullable, one_to_many, by_slot, pad1;   // by_slot: presence bitmap + slot-ordered inner columns (run-time, not structure)
+  // baseline join table (composite / wide-range keys): n_key_exprs > 0
+  uint8_t n_key_exprs, key_width, pad2, pad3;
+  int8_t key_exprs[HDK_B200_MAX_KEYS];
+  int32_t pad4;
 };
 
 constexpr int kMaxAcc = 28;

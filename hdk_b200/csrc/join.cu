@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "baseline.cuh"
 #include "common.cuh"
 
 namespace hb {
@@ -204,23 +205,6 @@ struct JoinCols {
   int n;
 };
 
-__device__ __forceinline__ uint32_t murmur1_dev(const void* key, int len) {
-  // MurmurHash1 (QE/MurmurHash1Inl.h), seed 0; len is a multiple of 4 here
-  const unsigned int m = 0xc6a4a793u;
-  unsigned int h = 0u ^ (unsigned(len) * m);
-  const unsigned int* d = static_cast<const unsigned int*>(key);
-  for (int i = 0; i < len / 4; ++i) {
-    h += d[i];
-    h *= m;
-    h ^= h >> 16;
-  }
-  h *= m;
-  h ^= h >> 10;
-  h *= m;
-  h ^= h >> 17;
-  return h;
-}
-
 template <typename T>
 __global__ void init_baseline_kernel(int8_t* buff, int64_t E, int kc, bool with_val, int32_t invalid) {
   const T empty = sizeof(T) == 4 ? T(HDK_B200_EMPTY_KEY_32) : T(HDK_B200_EMPTY_KEY_64);
@@ -248,40 +232,6 @@ __device__ __forceinline__ bool composite_key(const JoinCols& cs, uint64_t row, 
     key[k] = T(elem);
   }
   return true;
-}
-
-// claim-or-find the entry of `key`: CAS the first component, publish the rest, wait for the rest
-// (get_matching_baseline_hash_slot_at, HashJoinRuntime.cpp:359-394)
-template <typename T>
-__device__ __forceinline__ T* baseline_slot(int8_t* hash_buff, int64_t E, const T* key, int kc, size_t entry_sz, bool insert) {
-  using U = typename std::conditional<sizeof(T) == 4, unsigned int, unsigned long long>::type;
-  const T empty = sizeof(T) == 4 ? T(HDK_B200_EMPTY_KEY_32) : T(HDK_B200_EMPTY_KEY_64);
-  const uint32_t h0 = murmur1_dev(key, kc * int(sizeof(T))) % uint32_t(E);
-  uint32_t h = h0;
-  do {
-    T* row = reinterpret_cast<T*>(hash_buff + size_t(h) * entry_sz);
-    T first = *reinterpret_cast<volatile T*>(row);
-    if (first == empty) {
-      if (!insert) return nullptr;
-      first = T(atomicCAS(reinterpret_cast<U*>(row), U(empty), U(key[0])));
-      if (first == empty) {
-        for (int i = 1; i < kc; ++i) atomicExch(reinterpret_cast<U*>(row + i), U(key[i]));
-        return row + kc;
-      }
-    }
-    if (first == key[0]) {
-      bool match = true;
-      for (int i = 1; i < kc && match; ++i) {
-        T v;
-        while ((v = *reinterpret_cast<volatile T*>(row + i)) == empty) {
-        }
-        match = v == key[i];
-      }
-      if (match) return row + kc;
-    }
-    h = h + 1 == uint32_t(E) ? 0 : h + 1;
-  } while (h != h0);
-  return nullptr;
 }
 
 template <typename T>

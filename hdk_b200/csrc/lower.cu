@@ -145,6 +145,18 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
     if (s.payload_by_slot < 0 || s.payload_by_slot > 2) { set_error("payload_by_slot must be 0, 1 or 2"); return HDK_B200_E_INVALID; }
     d.by_slot = uint8_t(s.payload_by_slot);
     p.join_entry_count[j] = s.entry_count;
+    if (s.n_key_exprs < 0 || s.n_key_exprs > HDK_B200_MAX_KEYS) { set_error("join %d: bad n_key_exprs", j); return HDK_B200_E_INVALID; }
+    if (s.n_key_exprs > 0) {
+      if (s.one_to_many || s.payload_by_slot) { set_error("join %d: the fused baseline probe is one-to-one", j); return HDK_B200_E_UNSUPPORTED; }
+      if (s.key_width != 4 && s.key_width != 8) { set_error("join %d: key_width must be 4 or 8", j); return HDK_B200_E_INVALID; }
+      d.n_key_exprs = uint8_t(s.n_key_exprs);
+      d.key_width = uint8_t(s.key_width);
+      for (int i = 0; i < s.n_key_exprs; ++i) {
+        if (s.key_exprs[i] < 0 || s.key_exprs[i] > s.key_expr) { set_error("join %d: component %d must not come after key_expr", j, i); return HDK_B200_E_INVALID; }
+        if (plan->exprs[s.key_exprs[i]].type.kind != HDK_B200_INT) { set_error("join %d: floating-point join keys are not supported", j); return HDK_B200_E_UNSUPPORTED; }
+        d.key_exprs[i] = int8_t(s.key_exprs[i]);
+      }
+    }
     // every inner-table column of join j must come after the join's key node
     for (int i = 0; i <= s.key_expr; ++i)
       if (plan->exprs[i].op == HDK_B200_OP_COL && plan->exprs[i].a == j + 1) { set_error("inner column of join %d precedes its key node", j); return HDK_B200_E_INVALID; }
@@ -319,7 +331,10 @@ uint64_t plan_signature(const DPlan& p) {
   }
   for (int i = 0; i < p.n_filters; ++i) mix(uint8_t(p.filters[i]));
   for (int i = 0; i < p.n_keys; ++i) { mix(p.keys[i].expr); mix(p.keys[i].has_nulls); mix(p.keys[i].width); }
-  for (int i = 0; i < p.n_joins; ++i) { mix(p.joins[i].key_expr); mix(p.joins[i].key_nullable); mix(p.joins[i].one_to_many); }
+  for (int i = 0; i < p.n_joins; ++i) {
+    mix(p.joins[i].key_expr); mix(p.joins[i].key_nullable); mix(p.joins[i].one_to_many); mix(p.joins[i].n_key_exprs);
+    for (int k = 0; k < p.joins[i].n_key_exprs; ++k) mix(uint8_t(p.joins[i].key_exprs[k]));
+  }
   for (int i = 0; i < p.n_acc; ++i) { mix(p.accs[i].kind); mix(uint8_t(p.accs[i].arg)); mix(p.accs[i].arg_nullable); mix(p.accs[i].bytes); }
   for (int i = 0; i < p.n_cols; ++i) mix(p.col_width[i]);
   return h;

@@ -231,6 +231,16 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
     for (int j = 0; j < p.n_joins; ++j) {
       const DJoin& jn = p.joins[j];
       if (jn.key_expr != n) continue;
+      if (jn.n_key_exprs) {   // composite / wide-range key: baseline join table, one-to-one layout
+        int64_t k64[HDK_B200_MAX_KEYS];
+        for (int i = 0; i < jn.n_key_exprs; ++i) k64[i] = vals[jn.key_exprs[i]].i;
+        const int8_t* tbl = reinterpret_cast<const int8_t*>(args.join_hash_tables[j]);
+        const int64_t rid = jn.key_width == 4 ? baseline_join_probe<int32_t>(tbl, p.join_entry_count[j], k64, jn.n_key_exprs)
+                                              : baseline_join_probe<int64_t>(tbl, p.join_entry_count[j], k64, jn.n_key_exprs);
+        if (rid < 0) { dropped = true; break; }
+        rowid[j] = rid;
+        continue;
+      }
       // hash_join_idx[_nullable] (QE/GroupByRuntime.cpp:298-329)
       const int64_t key = vals[n].i;
       if ((jn.key_nullable && key == jn.null_val) || key < jn.min_key || key > jn.max_key) { dropped = true; break; }
@@ -320,7 +330,21 @@ __device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint
     static_for<0, sp.n_joins>([&](auto J) {
       constexpr int j = decltype(J)::value;
       constexpr DPlan sp = Shape::get();
-      if constexpr (sp.joins[j].key_expr == n) {
+      if constexpr (sp.joins[j].key_expr == n && sp.joins[j].n_key_exprs > 0) {
+        int64_t k64[HDK_B200_MAX_KEYS];
+        static_for<0, sp.joins[j].n_key_exprs>([&](auto Kc) {
+          constexpr DPlan sp = Shape::get();
+          k64[decltype(Kc)::value] = vals[sp.joins[j].key_exprs[decltype(Kc)::value]].i;
+        });
+        int64_t ridx = -1;
+        if (alive) {
+          const int8_t* tbl = reinterpret_cast<const int8_t*>(args.join_hash_tables[j]);
+          ridx = rp.joins[j].key_width == 4 ? baseline_join_probe<int32_t>(tbl, rp.join_entry_count[j], k64, sp.joins[j].n_key_exprs)
+                                            : baseline_join_probe<int64_t>(tbl, rp.join_entry_count[j], k64, sp.joins[j].n_key_exprs);
+        }
+        alive = alive && ridx >= 0;
+        rowid[j] = ridx;
+      } else if constexpr (sp.joins[j].key_expr == n) {
         const DJoin& jn = rp.joins[j];
         const int64_t key = vals[n].i;
         bool hit = alive && !((sp.joins[j].key_nullable && key == jn.null_val) || key < jn.min_key || key > jn.max_key);

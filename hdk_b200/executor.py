@@ -117,6 +117,8 @@ class JoinTable:
     bitmap: object = None    # presence bitmap (uint32 words) once a slot-ordered column has been made
     by_slot: Dict[str, object] = None   # inner column name -> copy ordered by hash slot
     dense: bool = False      # OneToOne and every slot occupied
+    key_width: int = 0       # baseline join tables ("Baseline*"): bytes per key component / payload cell
+    n_keys: int = 1
 
 
 class ResultSet:
@@ -314,9 +316,66 @@ class Executor:
         self.last_launch_info = None
 
     # -- join hash tables ----------------------------------------------------------------
+    def _join_columns(self, inner: Table, key_cols, key_width=None):
+        """JoinColumn / JoinColumnTypeInfo PODs over the inner table's (device) key chunks."""
+        n = len(key_cols)
+        jcs, tis, keep = (abi.JoinColumn * n)(), (abi.JoinColumnTypeInfo * n)(), []
+        rows = 0
+        for k, key_col in enumerate(key_cols):
+            ci = inner.columns[key_col]
+            lo, hi, _ = inner.col_stats(key_col)
+            if lo is None or ci.type.is_fp:
+                raise planner.UnsupportedPlan("join key without an integer range")
+            chunks = (abi.JoinChunk * len(inner.fragments))()
+            row = 0
+            for i, f in enumerate(inner.fragments):
+                d = self.ctx.chunk(f, key_col)
+                keep.append(d)
+                chunks[i].col_buff = d.data_ptr()
+                chunks[i].num_elems = f.num_rows
+                chunks[i].row_id = row
+                row += f.num_rows
+            rows = row
+            host_chunks = np.frombuffer(bytes(chunks), dtype=np.uint8)
+            dchunks = self.ctx.upload(host_chunks)
+            keep.append(dchunks)
+            jcs[k] = abi.JoinColumn(dchunks.data_ptr(), len(host_chunks), len(inner.fragments), row, ci.phys_width)
+            tis[k] = abi.JoinColumnTypeInfo(ci.phys_width, lo, hi, abi.int_null(ci.phys_width), 0, 0,
+                                            abi.SMALL_DATE if ci.type.date_in_days else abi.SIGNED)
+        return jcs, tis, rows, keep
+
+    def build_baseline_join_table(self, inner: Table, key_cols, key_width: int) -> JoinTable:
+        """BaselineJoinHashTable::reify (JHT/BaselineJoinHashTable.cpp:256-259: 2 x tuples entries) in the one-to-one
+        layout E x (components ‖ row id).  A duplicate composite key would need the one-to-many layout, which the fused
+        probe does not read: UnsupportedPlan, never a silent wrong answer."""
+        cache_key = (inner.name, tuple(key_cols), key_width)
+        if cache_key in self.join_tables:
+            return self.join_tables[cache_key]
+        torch = self.ctx.torch
+        jcs, tis, rows, keep = self._join_columns(inner, key_cols)
+        entries = 2 * max(rows, 1)
+        n = len(key_cols)
+        buf = torch.empty(entries * (n + 1) * key_width, dtype=torch.uint8, device=self.ctx.device)
+        err = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)
+        st = self.ctx.stream_ptr()
+        _lib.check(self.lib.hdk_b200_init_baseline_hash_join_buff_on_device(buf.data_ptr(), entries, n, 1, -1, key_width, st),
+                   "init_baseline_hash_join_buff")
+        _lib.check(self.lib.hdk_b200_fill_baseline_hash_join_buff_on_device(buf.data_ptr(), entries, -1, 0, n, 1, err.data_ptr(), jcs, tis,
+                                                                            key_width, st), "fill_baseline_hash_join_buff")
+        code = int(err.item())
+        if code == -1:
+            raise planner.UnsupportedPlan("duplicate composite join keys: the one-to-many baseline table is not read by the fused probe")
+        if code != 0:
+            raise QueryError(code, "baseline join table build failed")
+        jt = JoinTable(buf, "BaselineOneToOne", 0, 0, entries, inner, {})
+        jt.key_width, jt.n_keys = key_width, n
+        self.join_tables[cache_key] = jt
+        return jt
+
     def build_join_table(self, inner: Table, key_col: str) -> JoinTable:
         """HashJoin::getInstance → PerfectJoinHashTable::reify (JHT/PerfectJoinHashTable.cpp:90-383):
-        one-to-one first; a duplicate key (err = -1) rebuilds as one-to-many (NeedsOneToManyHash)."""
+        one-to-one first; a duplicate key (err = -1) rebuilds as one-to-many (NeedsOneToManyHash); a key range too wide
+        for a perfect table (TooManyHashEntries, :139-151) falls back to the baseline table like HashJoin::getInstance."""
         cache_key = (inner.name, key_col)
         if cache_key in self.join_tables:
             return self.join_tables[cache_key]
@@ -326,8 +385,8 @@ class Executor:
         if lo is None or ci.type.is_fp:
             raise planner.UnsupportedPlan("join key without an integer range")
         entries = hi - lo + 1
-        if entries > (1 << 31) // 4:   # TooManyHashEntries (PerfectJoinHashTable.cpp:139-151) → baseline join: not on this path
-            raise planner.UnsupportedPlan("join key range too large for a perfect hash table")
+        if entries > self.config.max_perfect_join_entries:
+            raise planner.UnsupportedPlan("join key range too large for a perfect hash table (the planner picks the baseline table)")
         chunks = (abi.JoinChunk * len(inner.fragments))()
         keep = []
         row = 0
@@ -442,8 +501,14 @@ class Executor:
         frags = outer.fragments if fragments is None else fragments
         joins = []
         for j, js in enumerate(unit.joins):
-            jt = self.build_join_table(self.storage.get_table(js.inner_table), js.inner_key_column)
             pj = pq.plan.joins[j]
+            inner_t = self.storage.get_table(js.inner_table)
+            if pj.n_key_exprs >= 1:     # the planner chose a baseline join table (composite or wide-range key)
+                jt = self.build_baseline_join_table(inner_t, js.inner_key_columns[:pj.n_key_exprs], pj.key_width)
+                pj.one_to_many, pj.payload_by_slot, pj.entry_count = 0, 0, jt.entry_count
+                joins.append(jt)
+                continue
+            jt = self.build_join_table(inner_t, js.inner_key_column)
             pj.one_to_many = int(jt.hash_type == "OneToMany")
             pj.min_key, pj.max_key, pj.entry_count = jt.min_key, jt.max_key, jt.entry_count
             pj.payload_by_slot = 0

@@ -53,9 +53,10 @@ class QueryNode:
             raise planner.UnsupportedPlan("only inner equi-joins are on the hot path")
         lhs_cols = [lhs_cols] if isinstance(lhs_cols, str) else list(lhs_cols)
         rhs_cols = lhs_cols if rhs_cols is None else ([rhs_cols] if isinstance(rhs_cols, str) else list(rhs_cols))
-        if len(lhs_cols) != 1 or len(rhs_cols) != 1:
-            raise planner.UnsupportedPlan("multi-column joins need the baseline join table (not on the fused path)")
-        spec = ir.JoinSpec(rhs.table_name, self.ref(lhs_cols[0]), rhs_cols[0])
+        if len(lhs_cols) != len(rhs_cols) or not lhs_cols:
+            raise ValueError("join: left and right key lists differ in length")
+        spec = ir.JoinSpec(rhs.table_name, self.ref(lhs_cols[0]), rhs_cols[0],
+                           [(self.ref(lc), rc) for lc, rc in zip(lhs_cols[1:], rhs_cols[1:])])   # > 1 column: baseline join table
         return QueryNode(self._hdk, self.table_name, self._quals, self._joins + [spec])
 
     def _parse_expr(self, text: str) -> ir.Expr:

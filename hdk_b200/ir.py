@@ -300,11 +300,22 @@ def expr_range(e: Expr, col_stats) -> Range:
 # ---------------------------------------------------------------------------------------------
 @dataclass
 class JoinSpec:
-    """Equi-join of the outer table with one inner table on a single integer key
-    (JoinCondition / buildHashTableForQualifier, QE/Execute.cpp:3692)."""
+    """Inner equi-join of the outer table with one inner table (JoinCondition / buildHashTableForQualifier,
+    QE/Execute.cpp:3692).  One integer key → perfect join table when its range allows; several key columns (or a
+    range too wide for a perfect table) → baseline join table.  `outer_key` / `inner_key_column` are the first pair;
+    `more_keys` holds the remaining (outer expression, inner column) pairs of a composite key."""
     inner_table: str
     outer_key: Expr
     inner_key_column: str
+    more_keys: List[tuple] = field(default_factory=list)
+
+    @property
+    def outer_keys(self):
+        return [self.outer_key] + [o for o, _ in self.more_keys]
+
+    @property
+    def inner_key_columns(self):
+        return [self.inner_key_column] + [c for _, c in self.more_keys]
 
 
 @dataclass

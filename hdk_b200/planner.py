@@ -31,6 +31,8 @@ class Config:
     enable_columnar_output: bool = False
     # hdk_b200 extension: probe OneToOne joins through a presence bitmap + slot-ordered inner columns
     join_payload_by_slot: bool = True
+    # perfect join tables up to this many entries (PerfectJoinHashTable.cpp:139-151); beyond: baseline join table
+    max_perfect_join_entries: int = (1 << 31) // 4
 
 
 class UnsupportedPlan(Exception):
@@ -430,9 +432,24 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
         raise UnsupportedPlan("too many joins")
     p.n_joins = len(unit.joins)
     for j, js in enumerate(unit.joins):
-        p.joins[j].key_expr = lower(js.outer_key)
+        nodes = [lower(k) for k in js.outer_keys]
+        p.joins[j].key_expr = max(nodes)        # the probe point: every component has been evaluated by then
         p.joins[j].key_nullable = int(js.outer_key.type.nullable)
         p.joins[j].null_val = abi.int_null(js.outer_key.type.width)
+        wide = False
+        if len(nodes) == 1:
+            lo, hi, _ = col_stats(j + 1, js.inner_key_column)
+            wide = lo is not None and (hi - lo + 1) > cfg.max_perfect_join_entries
+        if len(nodes) > 1 or wide:
+            # composite key, or a single key whose range is too wide for a perfect table (TooManyHashEntries,
+            # JHT/PerfectJoinHashTable.cpp:139-151) → baseline join table (JHT/BaselineJoinHashTable.cpp)
+            if len(nodes) > abi.MAX_KEYS:
+                raise UnsupportedPlan("too many join key components")
+            p.joins[j].n_key_exprs = len(nodes)
+            for i, nd in enumerate(nodes):
+                p.joins[j].key_exprs[i] = nd
+            # getKeyComponentWidth: 8 as soon as one component is wider than 4 bytes
+            p.joins[j].key_width = 8 if any(k.type.width > 4 for k in js.outer_keys) else 4
     if len(unit.quals) > abi.MAX_FILTERS:
         raise UnsupportedPlan("too many filters")
     p.n_filters = len(unit.quals)

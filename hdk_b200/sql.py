@@ -336,20 +336,30 @@ class _Parser:
             limit = int(self.eat("num")[1])
         self.eat("eof")
         joins = []
+        def conjuncts(c):
+            if isinstance(c, ir.Logic) and c.op == "and":
+                out = []
+                for x in c.args:
+                    out += conjuncts(x)
+                return out
+            return [c]
+
         for t2, cond in joins_raw:
-            if not (isinstance(cond, ir.Cmp) and cond.op == "="):
-                raise UnsupportedPlan("only single-column equi-joins are on the hot path")
-            lhs, rhs = cond.lhs, cond.rhs
-            strip = lambda x: x.arg if isinstance(x, ir.Cast) else x  # noqa: E731
-            lhs, rhs = strip(lhs), strip(rhs)
             jidx = len(joins) + 1
-            if isinstance(rhs, ir.ColumnRef) and rhs.table == jidx:
-                outer, inner = lhs, rhs
-            elif isinstance(lhs, ir.ColumnRef) and lhs.table == jidx:
-                outer, inner = rhs, lhs
-            else:
-                raise UnsupportedPlan("join condition must compare an outer expression with an inner column")
-            joins.append(ir.JoinSpec(t2, outer, inner.column))
+            pairs = []
+            for c in conjuncts(cond):
+                if not (isinstance(c, ir.Cmp) and c.op == "="):
+                    raise UnsupportedPlan("only (conjunctions of) equi-join conditions are on the hot path")
+                strip = lambda x: x.arg if isinstance(x, ir.Cast) else x  # noqa: E731
+                lhs, rhs = strip(c.lhs), strip(c.rhs)
+                if isinstance(rhs, ir.ColumnRef) and rhs.table == jidx:
+                    outer, inner = lhs, rhs
+                elif isinstance(lhs, ir.ColumnRef) and lhs.table == jidx:
+                    outer, inner = rhs, lhs
+                else:
+                    raise UnsupportedPlan("join condition must compare an outer expression with an inner column")
+                pairs.append((outer, inner.column))
+            joins.append(ir.JoinSpec(t2, pairs[0][0], pairs[0][1], pairs[1:]))
         final_names = []
         for i, (e, n) in enumerate(zip(targets, names)):
             if n is None:

@@ -203,7 +203,17 @@ typedef struct hdk_b200_join {
    * referenced column instead of table + column; results are identical.  2: as 1, and the caller knows that every
    * slot of [min_key, max_key] is occupied (as many distinct non-NULL keys as entries), so the bitmap is not read. */
   int32_t payload_by_slot;
-  int64_t entry_count;   /* hash entries (for one_to_many buffer offsets) */
+  int64_t entry_count;   /* hash entries (for one_to_many buffer offsets; baseline: entries of the table) */
+  /* Composite / wide-range equi-joins probe a BASELINE join table (JHT/BaselineJoinHashTable.cpp) in its one-to-one
+   * layout E x (key components ‖ payload row id), every cell key_width (4 or 8) bytes, MurmurHash1 + linear probing
+   * (write_baseline_hash_slot, JHT/Runtime/HashJoinRuntime.cpp:438-471; probe baseline_hash_join_idx_{32,64},
+   * JHT/Runtime/JoinHashTableQueryRuntime.cpp:43-98).  n_key_exprs = 0: perfect table on `key_expr` (above).
+   * n_key_exprs >= 1: `key_exprs` are the outer-side component nodes in key order and `key_expr` is the LAST of them
+   * in node order (the probe happens once it has been evaluated); min_key / max_key / null_val are unused — rows with
+   * a NULL component were never inserted by the build, so they simply miss. */
+  int32_t n_key_exprs;
+  int32_t key_width;
+  int32_t key_exprs[HDK_B200_MAX_KEYS];
 } hdk_b200_join;
 
 typedef struct hdk_b200_plan {

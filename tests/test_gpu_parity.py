@@ -188,6 +188,34 @@ def test_join_probe_sparse_dimension_uses_bitmap(oracle_mod, torch):
         check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), 1)
 
 
+@pytest.mark.parametrize("text,nk", util.COMPOSITE_JOIN_QUERIES)
+def test_fused_baseline_join_probe(oracle_mod, L, torch, text, nk):
+    """Composite-key / wide-range joins through the fused kernel: baseline join table built on the device
+    (hdk_b200_fill_baseline_hash_join_buff_on_device), probed per row inside scan_kernel; device-resident launch and
+    the host-buffer entry point (oracle-built table, byte-identical layout) against the oracle."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables = util.composite_join_tables()
+    st = util.make_storage(tables, fragment_size={"t": 1201, "dim": 100000, "dim2": 100000})
+    ex = Executor(st)
+    pq = ex.plan(sql.parse(text, st.tables))
+    prep = ex.prepare(pq)
+    assert pq.plan.joins[0].n_key_exprs >= 1
+    ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+    # hdk.sql end to end against SQLite
+    import hdk_b200.hdk as hdkmod
+    h = hdkmod.init()
+    for name, tb in tables.items():
+        h.import_arrow(tb, name, fragment_size=1201 if name == "t" else 100000)
+    order = ", ".join(str(i + 1) for i in range(nk))
+    res = h.sql(text + " ORDER BY " + order).to_arrow()
+    got = [tuple(r.values()) for r in res.to_pylist()]
+    util.assert_rows_equal(got, util.sqlite_rows(tables, text + " ORDER BY " + order, nk), rel=1e-9)
+
+
 def test_gather_join_payload_kernel(L, torch):
     """out[slot] = col[table[slot]] for present slots, 0 otherwise; bitmap bit = present — for every element width."""
     rng = np.random.default_rng(11)

@@ -59,3 +59,23 @@ def test_oracle_matches_sqlite(oracle_mod, tables, text, nk, columnar):
     text_sqlite = text.replace("CAST(d AS INT)", "CAST(ROUND(d) AS INT)")
     exp = util.sqlite_rows(tables, text_sqlite, nk)
     util.assert_rows_equal(got, exp, rel=1e-9)
+
+
+@pytest.mark.parametrize("text,nk", util.COMPOSITE_JOIN_QUERIES)
+def test_baseline_join_probe_in_row_function_vs_sqlite(oracle_mod, text, nk):
+    """Composite-key and wide-range equi-joins: the planner picks a baseline join table, the oracle's row function
+    probes it with the reference's baseline_hash_join_idx_{32,64}; the answer must be SQLite's, and the restatement
+    and the reference runtime must agree byte for byte."""
+    tables = util.composite_join_tables()
+    st = util.make_storage(tables, fragment_size={"t": 1201, "dim": 100000, "dim2": 100000})
+    pq = util.plan_sql(st, text)
+    assert pq.plan.joins[0].n_key_exprs >= 1
+    buf, err = util.run_oracle(oracle_mod, st, pq, kind="port")
+    assert err == 0
+    got = util.sort_rows(util.result_columns(oracle_mod, pq, buf), nk)
+    order = ", ".join(str(i + 1) for i in range(nk))
+    exp = util.sqlite_rows(tables, text + " ORDER BY " + order, nk)
+    util.assert_rows_equal(got, exp, rel=1e-9)
+    if oracle_mod.ref_available():
+        buf2, err2 = util.run_oracle(oracle_mod, st, pq, kind="reference")
+        assert err2 == 0 and np.array_equal(buf, buf2)

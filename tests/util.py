@@ -22,6 +22,9 @@ def plan_sql(st, text, cfg=None, **kw):
     return planner.build_query(unit, lambda ti, c: tabs[ti].col_stats(c), tabs[0].num_rows, cfg or planner.Config(), **kw)
 
 
+_KEEP = []   # ctypes temporaries referenced by JoinColumn structs
+
+
 def oracle_inputs(oracle, st, pq):
     """Fragments + host-built join tables / inner columns for the oracle (and query_host)."""
     outer = st.get_table(pq.unit.table)
@@ -29,6 +32,33 @@ def oracle_inputs(oracle, st, pq):
     join_tables, inner_cols = [], []
     for j, js in enumerate(pq.unit.joins):
         inner = st.get_table(js.inner_table)
+        pj = pq.plan.joins[j]
+        if pj.n_key_exprs > 0:
+            # baseline join table built by the oracle's own builder (one-to-one layout, 2 x rows entries)
+            kc, kw = pj.n_key_exprs, pj.key_width
+            key_cols = js.inner_key_columns[:kc]
+            rows = sum(f.num_rows for f in inner.fragments)
+            E = 2 * max(rows, 1)
+            jcs = (abi.JoinColumn * kc)()
+            tis = (abi.JoinColumnTypeInfo * kc)()
+            keep = []
+            for k, kcname in enumerate(key_cols):
+                ci = inner.columns[kcname]
+                lo, hi, _ = inner.col_stats(kcname)
+                jc = oracle.make_join_column([f.chunks[kcname] for f in inner.fragments], ci.phys_width)
+                keep.append(jc)
+                jcs[k] = jc
+                tis[k] = oracle.make_type_info(ci.phys_width, lo, hi, abi.int_null(ci.phys_width))
+            L = oracle.lib()
+            buf = np.empty(E * (kc + 1) * kw, dtype=np.uint8)
+            L.oracle_init_baseline_hash_join_buff(buf.ctypes.data, E, kc, 1, -1, kw)
+            rc = L.oracle_fill_baseline_hash_join_buff(buf.ctypes.data, E, -1, 0, kc, 1, jcs, tis, kw)
+            assert rc == 0, "oracle baseline join tables in these tests are one-to-one"
+            pj.entry_count = E
+            join_tables.append(buf)
+            inner_cols.append([np.concatenate([f.chunks[c] for f in inner.fragments]) for c in pq.inner_columns[j]])
+            _KEEP.append(keep)
+            continue
         lo, hi, _ = inner.col_stats(js.inner_key_column)
         ci = inner.columns[js.inner_key_column]
         E = hi - lo + 1
@@ -98,3 +128,27 @@ def sqlite_rows(tables, text, n_keys):
     rows = [tuple(r) for r in con.execute(text).fetchall()]
     keyf = lambda r: tuple((0, 0) if x is None else (1, x) for x in r[:n_keys])  # noqa: E731
     return sorted(rows, key=keyf)
+
+
+def composite_join_tables(seed=1, n=5000):
+    """Fact table + a dimension keyed by (a, b) with unique pairs + a dimension keyed by a 2^40-spaced int64
+    (range too wide for a perfect table): inputs of the baseline-join tests."""
+    rng = np.random.default_rng(seed)
+    t = pa.table({"a": rng.integers(0, 40, n).astype(np.int32),
+                  "b": pa.array(rng.integers(0, 30, n).astype(np.int16), mask=rng.random(n) < 0.02),
+                  "x": rng.integers(-100, 100, n), "f": rng.integers(-10**6, 10**6, n) / 128.0,
+                  "big": pa.array(rng.integers(0, 300, n) * (2**40), mask=rng.random(n) < 0.01)})
+    m = 700
+    pairs = rng.permutation(40 * 30)[:m]
+    dim = pa.table({"a": (pairs // 30).astype(np.int32), "b": (pairs % 30).astype(np.int16),
+                    "attr": rng.integers(0, 9, m).astype(np.int32), "w": rng.integers(0, 1000, m)})
+    dim2 = pa.table({"big": rng.permutation(300)[:200] * (2**40), "g": rng.integers(0, 5, 200).astype(np.int32),
+                     "u": rng.integers(0, 50, 200) / 8.0})
+    return {"t": t, "dim": dim, "dim2": dim2}
+
+
+COMPOSITE_JOIN_QUERIES = [
+    ("SELECT dim.attr, COUNT(*), SUM(t.x), SUM(dim.w) FROM t JOIN dim ON t.a = dim.a AND t.b = dim.b GROUP BY dim.attr", 1),
+    ("SELECT dim.attr, t.a, MIN(t.f), MAX(dim.w), AVG(t.x) FROM t JOIN dim ON t.a = dim.a AND t.b = dim.b WHERE dim.w > 100 GROUP BY dim.attr, t.a", 2),
+    ("SELECT dim2.g, COUNT(*), SUM(t.f * dim2.u), SUM(t.x) FROM t JOIN dim2 ON t.big = dim2.big GROUP BY dim2.g", 1),
+]
