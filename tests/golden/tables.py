@@ -31,10 +31,14 @@ def golden_tables():
     })
     pk = rng.permutation(1000).astype(np.int32)
     dim = pa.table({"pk": pk, "attr": (pk % 37).astype(np.int32), "weight": rng.integers(0, 1024, 1000).astype(np.float64) / 1024.0})
-    return {"t": t, "dim": dim}
+    # dimension keyed by the pair (s, b): 10 x 6 combinations, 48 of them present
+    combos = rng.permutation(60)[:48]
+    dim2k = pa.table({"s": (combos // 6).astype(np.int16), "b": (combos % 6 - 3).astype(np.int8),
+                      "attr": rng.integers(0, 5, 48).astype(np.int32), "w": rng.integers(0, 1000, 48)})
+    return {"t": t, "dim": dim, "dim2k": dim2k}
 
 
-FRAGMENT_SIZE = {"t": 1501, "dim": 100000}
+FRAGMENT_SIZE = {"t": 1501, "dim": 100000, "dim2k": 100000}
 
 # (name, sql, number of key columns, planner kwargs)
 QUERIES = [
@@ -53,5 +57,7 @@ QUERIES = [
     ("baseline_1key", "SELECT big, COUNT(*), SUM(w), MIN(fn), MAX(f), AVG(v) FROM t GROUP BY big", 1, dict(max_groups_buffer_entry_count=16384)),
     ("baseline_2key", "SELECT mid, s, COUNT(*), SUM(v), SUM(f) FROM t GROUP BY mid, s", 2, dict(max_groups_buffer_entry_count=32768)),
     ("star_join", "SELECT dim.attr, SUM(t.f), COUNT(*) FROM t JOIN dim ON t.fk = dim.pk GROUP BY dim.attr", 1, {}),
+    ("composite_join", "SELECT dim2k.attr, COUNT(*), SUM(t.f), SUM(dim2k.w), MIN(t.v) FROM t JOIN dim2k ON t.s = dim2k.s AND t.b = dim2k.b "
+                       "GROUP BY dim2k.attr", 1, {}),
     ("join_filter", "SELECT dim.attr, t.s, SUM(t.f * dim.weight), MIN(t.v) FROM t JOIN dim ON t.fk = dim.pk WHERE dim.weight > 0.25 GROUP BY dim.attr, t.s", 2, {}),
 ]
