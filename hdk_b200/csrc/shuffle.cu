@@ -7,6 +7,7 @@
 //   pass 1 (COUNT)      per-partition histogram, reduced over kernels (QE/Execute.cpp:1365-1435)
 //   pass 2 (scatter)    rows copied into pre-sized per-partition columnar buffers (QE/Execute.cpp:1933-2018)
 #include <algorithm>
+#include <cstdlib>
 
 #include "baseline.cuh"
 #include "common.cuh"
@@ -15,6 +16,15 @@
 namespace hb {
 
 constexpr uint32_t kMaxPartitions = 1024;
+constexpr uint32_t kMaxFragments = 4096;
+
+// h % n for a 64-bit hash and n <= 1024 partitions with 32-bit arithmetic only (a 64-bit modulo by a run-time value
+// costs ~100 instructions): (hi * 2^32 + lo) mod n = ((hi mod n) * (2^32 mod n) + lo mod n) mod n, every term < 2^32
+__device__ __forceinline__ uint32_t mod_partitions(uint64_t h, uint32_t n) {
+  const uint32_t hi = uint32_t(h >> 32) % n, lo = uint32_t(h) % n;
+  const uint32_t two32 = uint32_t((1ull << 32) % n);
+  return (hi * two32 + lo) % n;
+}
 
 struct ShuffleArgs {
   DPlan plan;
@@ -26,7 +36,25 @@ struct ShuffleArgs {
   const uint64_t* offsets;         // pass 2
   unsigned long long* cursors;     // pass 2
   int8_t* const* out_cols;         // pass 2
+  // fast path: no filters and every group key is a plain outer column → keys are read directly, no interpreter
+  int32_t direct;
+  int8_t key_col[HDK_B200_MAX_KEYS];
+  uint8_t key_w[HDK_B200_MAX_KEYS];
+  uint8_t key_days[HDK_B200_MAX_KEYS];   // date column stored as days (decoded to seconds like fixed_width_small_date_decode)
 };
+
+__device__ __forceinline__ int row_partition_direct(const ShuffleArgs& a, const int8_t* const* cols, uint64_t pos) {
+  int64_t keys[HDK_B200_MAX_KEYS];
+  for (int k = 0; k < a.plan.n_keys; ++k) {
+    const int w = a.key_w[k];
+    const int8_t* ptr = cols[a.key_col[k]] + pos * w;
+    int64_t v = w == 8 ? *reinterpret_cast<const int64_t*>(ptr) : w == 4 ? int64_t(*reinterpret_cast<const int32_t*>(ptr))
+                : w == 2 ? int64_t(*reinterpret_cast<const int16_t*>(ptr)) : int64_t(*ptr);
+    if (a.key_days[k]) v = (v == int_null_of(w)) ? INT64_MIN : v * 86400;
+    keys[k] = v;
+  }
+  return int(mod_partitions(murmur64a_keys(keys, a.plan.n_keys), a.n_partitions));
+}
 
 // partition of one row, or -1 when the row is filtered out
 __device__ __forceinline__ int row_partition(const ShuffleArgs& a, const int8_t* const* cols, uint64_t pos, V* vals) {
@@ -43,7 +71,7 @@ __device__ __forceinline__ int row_partition(const ShuffleArgs& a, const int8_t*
     if (!(vals[p.filters[f]].i > 0)) return -1;
   int64_t keys[HDK_B200_MAX_KEYS];
   for (int k = 0; k < p.n_keys; ++k) keys[k] = vals[p.keys[k].expr].i;
-  return int(murmur64a_keys(keys, p.n_keys) % a.n_partitions);
+  return int(mod_partitions(murmur64a_keys(keys, p.n_keys), a.n_partitions));
 }
 
 __global__ void shuffle_count_kernel(const __grid_constant__ ShuffleArgs a) {
@@ -100,6 +128,176 @@ __global__ void shuffle_scatter_kernel(const __grid_constant__ ShuffleArgs a) {
   }
 }
 
+// ---- tile-based passes -------------------------------------------------------------------------
+// A CTA takes tiles of kTileRows rows; partition ids of a thread's rows stay in registers.  Counting: a shared
+// histogram per CTA (warp-aggregated), flushed once.  Scattering: histogram of the tile → one global reservation per
+// partition and tile → every row's position = reservation + its rank inside the tile (warp prefix via match / popc +
+// per-warp offsets), so consecutive rows of a partition land next to each other (coalesced, also over NVLink).
+constexpr int kShufThreads = 256;
+constexpr int kShufRowsPerThread = 8;
+constexpr int kTileRows = kShufThreads * kShufRowsPerThread;
+
+struct ScatterToArgs {
+  ShuffleArgs base;
+  int8_t* const* dest_cols;        // [n_partitions * n_cols]
+  const uint64_t* dest_offsets;    // [n_partitions]
+};
+
+__device__ __forceinline__ void tile_of(const ShuffleArgs& a, uint64_t tile, const uint32_t* frag_tile_prefix, uint32_t& frag, uint64_t& row0) {
+  // fragment holding this tile (few fragments: linear search over the prefix in shared memory)
+  frag = 0;
+  while (frag + 1 < a.num_fragments && frag_tile_prefix[frag + 1] <= tile) ++frag;
+  row0 = (tile - frag_tile_prefix[frag]) * uint64_t(kTileRows);
+}
+
+// kStaged (few partitions, narrow rows): the tile's rows are first regrouped by partition in shared memory, then every
+// partition's run is copied out with consecutive threads writing consecutive elements — whole 128-byte lines per warp
+// instead of a handful of elements per destination, which is what NVLink wants when the destinations are peers.
+constexpr uint32_t kStagedMaxPartitions = 32;
+
+template <bool kScatter, bool kStaged = false>
+__global__ void __launch_bounds__(kShufThreads) shuffle_tile_kernel(const __grid_constant__ ScatterToArgs sa) {
+  const ShuffleArgs& a = sa.base;
+  const DPlan& p = a.plan;
+  extern __shared__ __align__(16) uint8_t staging[];      // kStaged: column-major copy of the tile, rows grouped by partition
+  __shared__ unsigned int run_start[kStagedMaxPartitions + 1];
+  __shared__ uint32_t stage_col_off[HDK_B200_MAX_COLS];
+  __shared__ uint32_t frag_tile_prefix[kMaxFragments + 1];
+  __shared__ unsigned int hist[kMaxPartitions];          // rows of the tile (scatter) / of the CTA (count) per partition
+  __shared__ unsigned long long base[kMaxPartitions];    // scatter: reserved start per partition
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    uint32_t acc = 0;
+    frag_tile_prefix[0] = 0;
+    for (uint32_t f = 0; f < a.num_fragments; ++f) {
+      const int64_t rows = a.num_rows[f];
+      acc += rows > 0 ? uint32_t((rows + kTileRows - 1) / kTileRows) : 0;
+      frag_tile_prefix[f + 1] = acc;
+    }
+  }
+  for (uint32_t i = tid; i < a.n_partitions; i += kShufThreads) hist[i] = 0;
+  __syncthreads();
+  const uint32_t total_tiles = frag_tile_prefix[a.num_fragments];
+  V vals[HDK_B200_MAX_EXPRS];
+  for (uint64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t frag;
+    uint64_t row0;
+    tile_of(a, tile, frag_tile_prefix, frag, row0);
+    const int8_t* const* cols = a.col_buffers + size_t(frag) * p.n_cols;
+    const uint64_t rows = uint64_t(a.num_rows[frag]);
+    int part[kShufRowsPerThread];
+#pragma unroll
+    for (int r = 0; r < kShufRowsPerThread; ++r) {
+      const uint64_t pos = row0 + uint64_t(r) * kShufThreads + tid;      // coalesced: consecutive threads, consecutive rows
+      part[r] = pos < rows ? (a.direct ? row_partition_direct(a, cols, pos) : row_partition(a, cols, pos, vals)) : -1;
+      // warp-aggregated histogram update
+      const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+      if (part[r] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[part[r]], (unsigned)__popc(peers));
+    }
+    if (!kScatter) continue;
+    __syncthreads();
+    // one reservation per partition and tile
+    if (kStaged && tid == 0) {   // where each partition's run starts inside the tile (<= 32 partitions)
+      unsigned int acc = 0;
+      for (uint32_t i = 0; i < a.n_partitions; ++i) { run_start[i] = acc; acc += hist[i]; }
+      run_start[a.n_partitions] = acc;
+      uint32_t off = 0;
+      for (int c = 0; c < p.n_cols; ++c) { stage_col_off[c] = off; off += uint32_t(kTileRows) * p.col_width[c]; }
+    }
+    for (uint32_t i = tid; i < a.n_partitions; i += kShufThreads) {
+      base[i] = hist[i] ? sa.dest_offsets[i] + atomicAdd(a.cursors + i, (unsigned long long)hist[i]) : 0;
+      hist[i] = 0;   // becomes the running position inside the reservation
+    }
+    __syncthreads();
+    if (kStaged) {
+#pragma unroll
+      for (int r = 0; r < kShufRowsPerThread; ++r) {
+        const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+        if (part[r] < 0) continue;
+        const int leader = __ffs(peers) - 1;
+        unsigned int start = 0;
+        if (lane == leader) start = atomicAdd(&hist[part[r]], (unsigned)__popc(peers));
+        start = __shfl_sync(peers, start, leader);
+        const uint32_t lp = run_start[part[r]] + start + __popc(peers & ((1u << lane) - 1u));   // position inside the tile
+        const uint64_t pos = row0 + uint64_t(r) * kShufThreads + tid;
+        for (int c = 0; c < p.n_cols; ++c) {
+          const int w = p.col_width[c];
+          const int8_t* src = cols[c] + pos * w;
+          uint8_t* o = staging + stage_col_off[c] + size_t(lp) * w;
+          if (w == 8) *reinterpret_cast<uint64_t*>(o) = *reinterpret_cast<const uint64_t*>(src);
+          else if (w == 4) *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(src);
+          else if (w == 2) *reinterpret_cast<uint16_t*>(o) = *reinterpret_cast<const uint16_t*>(src);
+          else *o = uint8_t(*src);
+        }
+      }
+      __syncthreads();
+      // copy the runs out: consecutive threads, consecutive elements of one partition's run
+      for (int c = 0; c < p.n_cols; ++c) {
+        const int w = p.col_width[c];
+        const uint8_t* sc = staging + stage_col_off[c];
+        for (uint32_t pr = 0; pr < a.n_partitions; ++pr) {
+          const uint32_t n = run_start[pr + 1] - run_start[pr];
+          if (!n) continue;
+          int8_t* out = sa.dest_cols[size_t(pr) * p.n_cols + c] + base[pr] * w;
+          const uint8_t* src = sc + size_t(run_start[pr]) * w;
+          if (w == 8) { for (uint32_t i = tid; i < n; i += kShufThreads) reinterpret_cast<uint64_t*>(out)[i] = reinterpret_cast<const uint64_t*>(src)[i]; }
+          else if (w == 4) { for (uint32_t i = tid; i < n; i += kShufThreads) reinterpret_cast<uint32_t*>(out)[i] = reinterpret_cast<const uint32_t*>(src)[i]; }
+          else if (w == 2) { for (uint32_t i = tid; i < n; i += kShufThreads) reinterpret_cast<uint16_t*>(out)[i] = reinterpret_cast<const uint16_t*>(src)[i]; }
+          else { for (uint32_t i = tid; i < n; i += kShufThreads) out[i] = int8_t(src[i]); }
+        }
+      }
+      __syncthreads();
+      for (uint32_t i = tid; i < a.n_partitions; i += kShufThreads) hist[i] = 0;
+      __syncthreads();
+      continue;
+    }
+#pragma unroll
+    for (int r = 0; r < kShufRowsPerThread; ++r) {
+      const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+      if (part[r] < 0) continue;
+      const int leader = __ffs(peers) - 1;
+      unsigned int start = 0;
+      if (lane == leader) start = atomicAdd(&hist[part[r]], (unsigned)__popc(peers));   // shared-memory atomic, per warp and partition
+      start = __shfl_sync(peers, start, leader);
+      const uint64_t dst = base[part[r]] + start + __popc(peers & ((1u << lane) - 1u));
+      const uint64_t pos = row0 + uint64_t(r) * kShufThreads + tid;
+      int8_t* const* out = sa.dest_cols + size_t(part[r]) * p.n_cols;
+      for (int c = 0; c < p.n_cols; ++c) {
+        const int w = p.col_width[c];
+        const int8_t* src = cols[c] + pos * w;
+        int8_t* o = out[c] + dst * w;
+        if (w == 8) *reinterpret_cast<uint64_t*>(o) = *reinterpret_cast<const uint64_t*>(src);
+        else if (w == 4) *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(src);
+        else if (w == 2) *reinterpret_cast<uint16_t*>(o) = *reinterpret_cast<const uint16_t*>(src);
+        else *o = *src;
+      }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < a.n_partitions; i += kShufThreads) hist[i] = 0;
+    __syncthreads();
+  }
+  if (!kScatter) {
+    __syncthreads();
+    for (uint32_t i = tid; i < a.n_partitions; i += kShufThreads)
+      if (hist[i]) atomicAdd(a.counts + i, (unsigned long long)hist[i]);
+  } else {
+    __threadfence_system();   // rows written to peer memory are visible before the host-side barrier that follows
+  }
+}
+
+static void detect_direct_keys(const DPlan& p, ShuffleArgs* a) {
+  a->direct = 0;
+  if (p.n_filters) return;
+  for (int k = 0; k < p.n_keys; ++k) {
+    const DExpr& e = p.exprs[p.keys[k].expr];
+    if (e.op != HDK_B200_OP_COL || e.a != 0 || e.kind != HDK_B200_INT) return;
+    a->key_col[k] = e.b;
+    a->key_w[k] = uint8_t(e.imm.i);
+    a->key_days[k] = uint8_t(e.aux == 1);
+  }
+  a->direct = 1;
+}
+
 // a plan without layout information: lower only what the shuffle needs
 static int lower_for_shuffle(const hdk_b200_plan* plan, Lowered* lw) {
   hdk_b200_qmd q{};
@@ -141,7 +339,43 @@ int hdk_b200_shuffle_count(const hdk_b200_plan* plan, const hdk_b200_kernel_para
   a.counts = reinterpret_cast<unsigned long long*>(counts);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   HB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * n_partitions, st));
-  shuffle_count_kernel<<<sm_count() * 4, 256, 0, st>>>(a);
+  if (a.num_fragments > kMaxFragments) { set_error("more than %u fragments", kMaxFragments); return HDK_B200_E_UNSUPPORTED; }
+  ScatterToArgs sa{};
+  sa.base = a;
+  detect_direct_keys(lw.plan, &sa.base);
+  shuffle_tile_kernel<false><<<sm_count() * 4, kShufThreads, 0, st>>>(sa);
+  HB_LAUNCH_CHECK();
+  return HDK_B200_OK;
+}
+
+int hdk_b200_shuffle_scatter_to(const hdk_b200_plan* plan, const hdk_b200_kernel_params* params, uint32_t n_partitions,
+                                int8_t* const* dest_cols, const uint64_t* dest_offsets, uint64_t* cursors, void* stream) {
+  if (!plan || !params || !dest_cols || !dest_offsets || !cursors || n_partitions == 0 || n_partitions > kMaxPartitions) { set_error("bad argument"); return HDK_B200_E_INVALID; }
+  if (plan->n_joins) { set_error("shuffle of joined plans is not supported"); return HDK_B200_E_UNSUPPORTED; }
+  if (params->num_fragments > kMaxFragments) { set_error("more than %u fragments", kMaxFragments); return HDK_B200_E_UNSUPPORTED; }
+  Lowered lw;
+  if (int rc = lower_for_shuffle(plan, &lw)) return rc;
+  ScatterToArgs sa{};
+  sa.base.plan = lw.plan;
+  sa.base.col_buffers = params->col_buffers;
+  sa.base.num_rows = params->num_rows;
+  sa.base.num_fragments = uint32_t(params->num_fragments);
+  sa.base.n_partitions = n_partitions;
+  sa.base.cursors = reinterpret_cast<unsigned long long*>(cursors);
+  sa.dest_cols = dest_cols;
+  sa.dest_offsets = dest_offsets;
+  detect_direct_keys(lw.plan, &sa.base);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HB_CUDA(cudaMemsetAsync(cursors, 0, sizeof(uint64_t) * n_partitions, st));
+  const size_t staging = size_t(kTileRows) * lw.stage_row_bytes;
+  bool staged = n_partitions >= 4 && n_partitions <= kStagedMaxPartitions && staging <= 96 * 1024;
+  if (const char* env = getenv("HDK_B200_SCATTER_STAGED")) staged = env[0] == '1' && n_partitions <= kStagedMaxPartitions && staging <= 96 * 1024;   // tuning hook
+  if (staged) {
+    HB_CUDA(cudaFuncSetAttribute(shuffle_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(staging)));
+    shuffle_tile_kernel<true, true><<<sm_count() * 3, kShufThreads, staging, st>>>(sa);
+  } else {
+    shuffle_tile_kernel<true><<<sm_count() * 4, kShufThreads, 0, st>>>(sa);
+  }
   HB_LAUNCH_CHECK();
   return HDK_B200_OK;
 }

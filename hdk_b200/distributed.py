@@ -167,3 +167,59 @@ class PeerExchange:
         if self.local:
             self.lib.hdk_b200_peer_free(self.local)
             self.local = None
+
+
+class _DevMem:
+    """zero-copy torch view of raw device memory (cudaMalloc through the library)"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerRows:
+    """Peer-visible receive buffers of a partitioned aggregation, one per plan column, `capacity_rows` rows each.
+    hdk_b200_shuffle_scatter_to writes every partition straight into its owner's buffers through NVLink — the
+    scatter kernel is the all-to-all; only the per-partition counts travel through the process group."""
+
+    def __init__(self, lib, widths, capacity_rows: int, device, group=None):
+        import ctypes as C
+
+        from . import _lib
+        self.lib, self.widths, self.capacity, self.device, self.group = lib, list(widths), int(capacity_rows), device, group
+        self.rank, self.world = rank(), world()
+        n = len(self.widths)
+        self.local_ptrs, handles = [], []
+        for w in self.widths:
+            p, h = C.c_void_p(0), (C.c_uint8 * 64)()
+            _lib.check(lib.hdk_b200_peer_alloc(max(self.capacity, 1) * w, C.byref(p), h), "peer_alloc")
+            self.local_ptrs.append(p)
+            handles.append(bytes(h))
+        self.opened = []
+        table = [[0] * n for _ in range(self.world)]
+        table[self.rank] = [p.value for p in self.local_ptrs]
+        if self.world > 1:
+            mine = torch.tensor(list(b"".join(handles)), dtype=torch.uint8, device=device)
+            gathered = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(gathered, mine, group=group)
+            for r, g in enumerate(gathered):
+                if r == self.rank:
+                    continue
+                raw = bytes(g.cpu().tolist())
+                for c in range(n):
+                    hb = (C.c_uint8 * 64)(*raw[64 * c: 64 * (c + 1)])
+                    p = C.c_void_p(0)
+                    _lib.check(lib.hdk_b200_peer_open(hb, C.byref(p)), f"peer_open(rank {r}, column {c})")
+                    self.opened.append(p)
+                    table[r][c] = p.value
+            dist.barrier(group=group)
+        self.dest = torch.tensor([x for row in table for x in row], dtype=torch.int64, device=device)   # [world * n_cols]
+
+    def local_column(self, c: int, rows: int):
+        return torch.as_tensor(_DevMem(self.local_ptrs[c].value, max(rows, 1) * self.widths[c]), device=self.device)[: rows * self.widths[c]]
+
+    def close(self):
+        for p in self.opened:
+            self.lib.hdk_b200_peer_close(p)
+        for p in self.local_ptrs:
+            self.lib.hdk_b200_peer_free(p)
+        self.opened, self.local_ptrs = [], []

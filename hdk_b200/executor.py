@@ -311,6 +311,8 @@ class Executor:
         self.config = config or planner.Config()
         self.ctx = DeviceContext(device, hot_data)
         self.compact_threshold_bytes = 64 << 20   # larger group-by buffers are iterated on the device (hdk_b200_compact_result)
+        self.partition_over_peer_memory = True    # execute_partitioned: scatter straight into the owners' buffers (else NCCL all-to-all)
+        self._peer_rows = {}
         self.lib = _lib.lib()
         self.join_tables: Dict[tuple, JoinTable] = {}
         self.last_launch_info = None
@@ -612,6 +614,15 @@ class Executor:
         st = self.ctx.stream_ptr()
         counts = torch.zeros(W, dtype=torch.int64, device=dev)
         _lib.check(self.lib.hdk_b200_shuffle_count(C.byref(pq.plan), C.byref(prep["kp"]), W, counts.data_ptr(), st), "shuffle_count")
+        widths = [outer.columns[c].phys_width for c in pq.columns]
+        if self.partition_over_peer_memory and D.is_dist():
+            frag, n_recv = self._exchange_rows_over_peer_memory(pq, prep, counts, widths, group)
+            prep2 = self.prepare(pq, fragments=[frag])
+            self.launch(pq, prep2)
+            code = int(prep2["err"].item())
+            if code != 0:
+                raise QueryError(code, "ran out of slots in the group-by buffer" if code < 0 else "runtime error")
+            return ResultSet(pq, prep2["out"].cpu().numpy()), n_recv
         n_local = int(counts.sum().item())
         offsets = torch.cumsum(counts, 0) - counts
         cursors = torch.zeros(W, dtype=torch.int64, device=dev)
@@ -631,6 +642,45 @@ class Executor:
         if code != 0:
             raise QueryError(code, "ran out of slots in the group-by buffer" if code < 0 else "runtime error")
         return ResultSet(pq, prep2["out"].cpu().numpy()), n_recv
+
+    def _exchange_rows_over_peer_memory(self, pq, prep, counts, widths, group=None):
+        """The all-to-all of execute_partitioned fused into the scatter kernel: counts are all-gathered (W x W int64),
+        every rank derives where its rows start in each owner's receive buffer, hdk_b200_shuffle_scatter_to writes them
+        there through NVLink.  Returns (fragment over this rank's received rows, rows received)."""
+        import torch.distributed as dist
+
+        from . import distributed as D
+        from .storage import ChunkStats, Fragment
+        torch = self.ctx.torch
+        dev = self.ctx.device
+        W, me = D.world(), D.rank()
+        gathered = [torch.empty_like(counts) for _ in range(W)]
+        if W > 1:
+            dist.all_gather(gathered, counts, group=group)
+        else:
+            gathered = [counts]
+        M = torch.stack(gathered).cpu()                     # M[r][d]: rows rank r sends to rank d
+        recv_total = [int(M[:, d].sum()) for d in range(W)]
+        need = max(recv_total)
+        pr = self._peer_rows.get(tuple(widths))
+        if pr is None or pr.capacity < need:                # collective decision: every rank sees the same M
+            if pr is not None:
+                pr.close()
+            pr = D.PeerRows(self.lib, widths, int(need * 1.25) + 1024, dev, group)
+            self._peer_rows[tuple(widths)] = pr
+        offsets = torch.tensor([int(M[:me, d].sum()) for d in range(W)], dtype=torch.int64, device=dev)
+        cursors = torch.zeros(W, dtype=torch.int64, device=dev)
+        if W > 1:
+            dist.barrier(group=group)                       # every owner is done with the previous contents of its buffers
+        _lib.check(self.lib.hdk_b200_shuffle_scatter_to(C.byref(pq.plan), C.byref(prep["kp"]), W, pr.dest.data_ptr(), offsets.data_ptr(),
+                                                        cursors.data_ptr(), self.ctx.stream_ptr()), "shuffle_scatter_to")
+        torch.cuda.synchronize(dev)
+        if W > 1:
+            dist.barrier(group=group)                       # all rows have landed
+        n_recv = recv_total[me]
+        frag = Fragment(0, n_recv, 0, 0, {}, {c: ChunkStats(None, None, False) for c in pq.columns},
+                        {c: pr.local_column(i, n_recv) for i, c in enumerate(pq.columns)})
+        return frag, n_recv
 
     def compact_on_device(self, pq: planner.PlannedQuery, out) -> np.ndarray:
         """hdk_b200_compact_result (ResultSet iteration on the device): [n_targets, rows] int64 cells on the host."""

@@ -499,6 +499,16 @@ HDK_B200_API int hdk_b200_shuffle_scatter(const hdk_b200_plan* plan, const hdk_b
                              const uint64_t* offsets /* DEVICE [n_partitions] exclusive prefix */,
                              uint64_t* cursors /* DEVICE [n_partitions], zeroed by callee */,
                              int8_t* const* out_cols /* DEVICE array [n_cols] */, void* stream);
+/* pass 2 with one destination per partition: partition p's rows go to dest_cols[p * n_cols + c] (DEVICE array of DEVICE
+ * pointers) starting at row dest_offsets[p].  The pointers may address PEER memory (hdk_b200_peer_alloc / _open): the
+ * scatter kernel then IS the all-to-all — each GPU writes its rows straight into the owners' receive buffers through
+ * NVLink, no staging copy and no collective for the payload (counts are exchanged beforehand to derive the offsets;
+ * a barrier after the kernels makes the rows visible to the owners). */
+HDK_B200_API int hdk_b200_shuffle_scatter_to(const hdk_b200_plan* plan, const hdk_b200_kernel_params* params, uint32_t n_partitions,
+                                             int8_t* const* dest_cols /* DEVICE [n_partitions * n_cols] */,
+                                             const uint64_t* dest_offsets /* DEVICE [n_partitions] */,
+                                             uint64_t* cursors /* DEVICE [n_partitions], zeroed by callee */, void* stream);
+
 
 /* ============================================================================
  * Multi-GPU merge of perfect-hash partials over peer memory (NVLink / NVSwitch), one process per GPU.

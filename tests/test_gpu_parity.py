@@ -665,6 +665,53 @@ def test_executor_iterates_large_buffers_on_device(env, torch):
         assert ex.execute_work_unit(sql.parse(text, st.tables)).row_count() == host_side.num_rows
 
 
+@pytest.mark.parametrize("P", [1, 5, 40])
+def test_shuffle_scatter_to_per_partition_destinations(L, env, torch, P):
+    """hdk_b200_shuffle_scatter_to: every partition into its own destination buffers at its own row offset (the shape
+    the fused all-to-all uses, here all on one GPU): the multiset of rows per partition must equal the one the
+    column-major scatter produces, and the counts pass must agree."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    ex = Executor(st)
+    pq = ex.plan(sql.parse("SELECT mid, s, SUM(v) FROM t GROUP BY mid, s", st.tables), 262144)
+    prep = ex.prepare(pq)      # (P <= 32: rows regrouped in shared memory first; P = 40: direct scatter)
+    counts = torch.zeros(P, dtype=torch.int64, device="cuda")
+    assert L.hdk_b200_shuffle_count(C.byref(pq.plan), C.byref(prep["kp"]), P, counts.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    c = counts.cpu().numpy()
+    n = tables["t"].num_rows
+    assert c.sum() == n
+    widths = [st.get_table("t").columns[x].phys_width for x in pq.columns]
+    # reference: column-major scatter
+    offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(c)[:-1]]).astype(np.int64)).cuda()
+    cursors = torch.zeros(P, dtype=torch.int64, device="cuda")
+    ref_cols = [torch.zeros(n * w, dtype=torch.uint8, device="cuda") for w in widths]
+    ptrs = torch.tensor([x.data_ptr() for x in ref_cols], dtype=torch.int64, device="cuda")
+    assert L.hdk_b200_shuffle_scatter(C.byref(pq.plan), C.byref(prep["kp"]), P, offsets.data_ptr(), cursors.data_ptr(), ptrs.data_ptr(), None) == 0
+    # per-partition destinations, each with 3 rows of headroom in front
+    pad = 3
+    dest = [[torch.full(((int(c[p]) + pad) * w,), 0xEE, dtype=torch.uint8, device="cuda") for w in widths] for p in range(P)]
+    dptr = torch.tensor([x.data_ptr() for row in dest for x in row], dtype=torch.int64, device="cuda")
+    doff = torch.full((P,), pad, dtype=torch.int64, device="cuda")
+    cur2 = torch.zeros(P, dtype=torch.int64, device="cuda")
+    assert L.hdk_b200_shuffle_scatter_to(C.byref(pq.plan), C.byref(prep["kp"]), P, dptr.data_ptr(), doff.data_ptr(), cur2.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(cur2.cpu().numpy(), c)
+    off = offsets.cpu().numpy()
+    for p in range(P):
+        rows_ref, rows_got = [], []
+        for ci, w in enumerate(widths):
+            dt = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[w]
+            rows_ref.append(ref_cols[ci].cpu().numpy().view(dt)[off[p]: off[p] + c[p]].astype(np.int64))
+            g = dest[p][ci].cpu().numpy()
+            assert (g[: pad * w] == 0xEE).all()                         # headroom untouched
+            rows_got.append(g.view(dt)[pad: pad + c[p]].astype(np.int64))
+        a, b = np.stack(rows_ref, 1), np.stack(rows_got, 1)
+        key = lambda m: m[np.lexsort(m.T[::-1])]  # noqa: E731
+        assert np.array_equal(key(a), key(b)), f"partition {p}"
+
+
 def test_shuffle_partitions_rows_by_key(L, env, torch):
     """hdk_b200_shuffle_count / _scatter: every row lands in exactly one partition, partition = f(key) only,
     counts agree with the scatter, the multiset of rows is preserved."""
