@@ -138,6 +138,11 @@ class ClockSampler:
 _CPU_CACHE = {}
 
 
+def oracle_mod():
+    from oracle import oracle
+    return oracle
+
+
 def cpu_taxi(sample_rows, threads, repeats=1, min_seconds=0.0):
     """Q1–Q4 over a host-resident taxi sample: one kernel per fragment with a private buffer on `threads`
     workers, then ResultSetReduction.  Returns (rows/s over the four queries, kind, seconds)."""
@@ -193,6 +198,12 @@ def run_reference(args):
     wall = time.perf_counter() - t0
     value = sum(v[0] for v in vals) / len(vals)
     kind = vals[0][1]
+    try:   # context: what this box's RAM can deliver to the same threads (ceiling of any CPU scan over host-resident columns)
+        host_gbs = float(oracle_mod().lib(kind).oracle_host_read_gbs(1 << 29, threads, 2))
+    except Exception:
+        host_gbs = None
+    if host_gbs is None:
+        host_gbs = 0.0
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(v[2] for v in vals) / len(vals), "higher_is_better": True,
@@ -202,7 +213,9 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"{sample} rows x 4 queries per step, one kernel per fragment on {threads} threads + reduce; "
                                    "per-row runtime = the reference's RuntimeFunctions.cpp compiled -O3 into the driver, row loop interpreted from the plan "
-                                   "(the LLVM JIT cannot be built here)"},
+                                   "(the LLVM JIT cannot be built here)",
+                         "host_read_gbs": host_gbs,
+                         "host_memory_bound_rows_per_s": host_gbs * 1e9 / 10.5},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
@@ -499,7 +512,13 @@ def main():
             cpu_taxi(args.cpu_sample_rows, threads)   # warm-up pass (page faults of the private buffers)
             v, kind, secs = cpu_taxi(args.cpu_sample_rows, threads, repeats=max(args.cpu_repeats, 1),
                                      min_seconds=0.0 if args.cpu_repeats else 10.0)
+            host_gbs = float(oracle_mod().lib(kind).oracle_host_read_gbs(1 << 30, threads, 3))
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                                   "host_read_gbs": host_gbs,
+                                   "host_memory_bound_rows_per_s": host_gbs * 1e9 / (sum(benchdata.TAXI_BYTES_PER_ROW.values()) / 4.0),
+                                   "note": "host_read_gbs = measured read bandwidth of this box's RAM with the same threads; "
+                                           "host_memory_bound_rows_per_s = that / 10.5 B per scanned row = ceiling of ANY CPU implementation "
+                                           "over host-resident columns (a JIT-compiled row loop would sit between `value` and it)",
                                    "sample": f"{args.cpu_sample_rows} rows x Q1-Q4 ({secs:.1f} s of CPU work), one kernel per fragment on {threads} "
                                              "threads + reduce; per-row runtime = the reference's own RuntimeFunctions.cpp (oracle/_ref), row loop "
                                              "interpreted from the plan because the LLVM JIT cannot be built here"}

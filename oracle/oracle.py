@@ -63,6 +63,8 @@ def _bind(lib):
     lib.oracle_extract_year.argtypes = [i64]
     lib.oracle_get_group_value.restype = vp
     lib.oracle_get_group_value.argtypes = [vp, u32, vp, u32, u32, u32]
+    lib.oracle_host_read_gbs.restype = C.c_double
+    lib.oracle_host_read_gbs.argtypes = [C.c_size_t, C.c_int, C.c_int]
     lib.oracle_key_hash.restype = u32
     lib.oracle_key_hash.argtypes = [vp, u32, u32]
     return lib
