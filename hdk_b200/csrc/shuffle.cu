@@ -3,7 +3,7 @@
 //
 // Model: the reference's CPU-only partitioned aggregation (QE/RelAlgExecutor.cpp:691-838):
 //   partition function  MurmurHash64A over the 64-bit-widened key components (QE/RowFuncBuilder.cpp:516-577);
-//                       the reference masks with (P-1), here `% n_partitions` so any GPU count works
+//                       the reference masks with (P-1), here multiply-shift range reduction so any GPU count works
 //   pass 1 (COUNT)      per-partition histogram, reduced over kernels (QE/Execute.cpp:1365-1435)
 //   pass 2 (scatter)    rows copied into pre-sized per-partition columnar buffers (QE/Execute.cpp:1933-2018)
 #include <algorithm>
@@ -18,13 +18,10 @@ namespace hb {
 constexpr uint32_t kMaxPartitions = 1024;
 constexpr uint32_t kMaxFragments = 4096;
 
-// h % n for a 64-bit hash and n <= 1024 partitions with 32-bit arithmetic only (a 64-bit modulo by a run-time value
-// costs ~100 instructions): (hi * 2^32 + lo) mod n = ((hi mod n) * (2^32 mod n) + lo mod n) mod n, every term < 2^32
-__device__ __forceinline__ uint32_t mod_partitions(uint64_t h, uint32_t n) {
-  const uint32_t hi = uint32_t(h >> 32) % n, lo = uint32_t(h) % n;
-  const uint32_t two32 = uint32_t((1ull << 32) % n);
-  return (hi * two32 + lo) % n;
-}
+// partition of a 64-bit key hash: multiply-shift range reduction of its upper half, floor(h_hi * n / 2^32) — one
+// multiply instead of a modulo by a run-time value (~100 instructions for 64 bits).  Any deterministic function of
+// the key serves (the reference masks MurmurHash64A with P - 1, QE/RowFuncBuilder.cpp:516-577).
+__device__ __forceinline__ uint32_t mod_partitions(uint64_t h, uint32_t n) { return __umulhi(uint32_t(h >> 32), n); }
 
 struct ShuffleArgs {
   DPlan plan;
@@ -41,7 +38,21 @@ struct ShuffleArgs {
   int8_t key_col[HDK_B200_MAX_KEYS];
   uint8_t key_w[HDK_B200_MAX_KEYS];
   uint8_t key_days[HDK_B200_MAX_KEYS];   // date column stored as days (decoded to seconds like fixed_width_small_date_decode)
+  // region mode (hdk_b200_region_*): partition = region of the baseline group-by table the row's key hashes into
+  uint32_t region_mode, entry_count, key_width, region_mul;   // region = min(umulhi(slot, region_mul), n_partitions - 1)
 };
+
+// partition id from the (64-bit widened) group keys
+__device__ __forceinline__ int partition_of_keys(const ShuffleArgs& a, int64_t* keys, int n_keys) {
+  if (a.region_mode) {
+    // the slot the baseline probe starts at: key_hash (MurmurHash3 over the key bytes at key_width) % entry_count
+    if (a.key_width == 4)
+      for (int k = 0; k < n_keys; ++k) keys[k] = int64_t(int32_t(keys[k]));
+    const uint32_t slot = key_hash_dev(keys, n_keys, int(a.key_width)) % a.entry_count;
+    return int(min(__umulhi(slot, a.region_mul), a.n_partitions - 1));
+  }
+  return int(mod_partitions(murmur64a_keys(keys, n_keys), a.n_partitions));
+}
 
 __device__ __forceinline__ int row_partition_direct(const ShuffleArgs& a, const int8_t* const* cols, uint64_t pos) {
   int64_t keys[HDK_B200_MAX_KEYS];
@@ -53,7 +64,7 @@ __device__ __forceinline__ int row_partition_direct(const ShuffleArgs& a, const 
     if (a.key_days[k]) v = (v == int_null_of(w)) ? INT64_MIN : v * 86400;
     keys[k] = v;
   }
-  return int(mod_partitions(murmur64a_keys(keys, a.plan.n_keys), a.n_partitions));
+  return partition_of_keys(a, keys, a.plan.n_keys);
 }
 
 // partition of one row, or -1 when the row is filtered out
@@ -71,7 +82,7 @@ __device__ __forceinline__ int row_partition(const ShuffleArgs& a, const int8_t*
     if (!(vals[p.filters[f]].i > 0)) return -1;
   int64_t keys[HDK_B200_MAX_KEYS];
   for (int k = 0; k < p.n_keys; ++k) keys[k] = vals[p.keys[k].expr].i;
-  return int(mod_partitions(murmur64a_keys(keys, p.n_keys), a.n_partitions));
+  return partition_of_keys(a, keys, p.n_keys);
 }
 
 __global__ void shuffle_count_kernel(const __grid_constant__ ShuffleArgs a) {
@@ -344,6 +355,63 @@ int hdk_b200_shuffle_count(const hdk_b200_plan* plan, const hdk_b200_kernel_para
   sa.base = a;
   detect_direct_keys(lw.plan, &sa.base);
   shuffle_tile_kernel<false><<<sm_count() * 4, kShufThreads, 0, st>>>(sa);
+  HB_LAUNCH_CHECK();
+  return HDK_B200_OK;
+}
+
+static int region_setup(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, const hdk_b200_kernel_params* params, uint32_t n_regions,
+                        Lowered* lw, ScatterToArgs* sa) {
+  if (!plan || !qmd || !params || n_regions == 0 || n_regions > kMaxPartitions) { set_error("bad argument"); return HDK_B200_E_INVALID; }
+  if (qmd->hash_type != HDK_B200_BASELINE_HASH) { set_error("region partitioning is for baseline-hash plans"); return HDK_B200_E_UNSUPPORTED; }
+  if (plan->n_joins) { set_error("region partitioning of joined plans is not supported"); return HDK_B200_E_UNSUPPORTED; }
+  if (params->num_fragments > kMaxFragments) { set_error("more than %u fragments", kMaxFragments); return HDK_B200_E_UNSUPPORTED; }
+  if (int rc = lower_plan(plan, qmd, lw)) return rc;
+  sa->base.plan = lw->plan;
+  sa->base.col_buffers = params->col_buffers;
+  sa->base.num_rows = params->num_rows;
+  sa->base.num_fragments = uint32_t(params->num_fragments);
+  sa->base.n_partitions = n_regions;
+  sa->base.region_mode = 1;
+  sa->base.entry_count = qmd->entry_count;
+  sa->base.key_width = uint32_t(qmd->key_width);
+  // region = floor(slot * n_regions / E) up to rounding: monotone in the slot, which is all that matters
+  sa->base.region_mul = uint32_t(std::min<uint64_t>(((uint64_t(n_regions) << 32) + qmd->entry_count - 1) / qmd->entry_count, 0xffffffffull));
+  detect_direct_keys(lw->plan, &sa->base);
+  return HDK_B200_OK;
+}
+
+int hdk_b200_region_count(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, const hdk_b200_kernel_params* params, uint32_t n_regions,
+                          uint64_t* counts, void* stream) {
+  Lowered lw;
+  ScatterToArgs sa{};
+  if (int rc = region_setup(plan, qmd, params, n_regions, &lw, &sa)) return rc;
+  if (!counts) { set_error("null counts"); return HDK_B200_E_INVALID; }
+  sa.base.counts = reinterpret_cast<unsigned long long*>(counts);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * n_regions, st));
+  shuffle_tile_kernel<false><<<sm_count() * 4, kShufThreads, 0, st>>>(sa);
+  HB_LAUNCH_CHECK();
+  return HDK_B200_OK;
+}
+
+int hdk_b200_region_scatter_to(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, const hdk_b200_kernel_params* params,
+                               uint32_t n_regions, int8_t* const* dest_cols, const uint64_t* dest_offsets, uint64_t* cursors, void* stream) {
+  Lowered lw;
+  ScatterToArgs sa{};
+  if (int rc = region_setup(plan, qmd, params, n_regions, &lw, &sa)) return rc;
+  if (!dest_cols || !dest_offsets || !cursors) { set_error("null argument"); return HDK_B200_E_INVALID; }
+  sa.base.cursors = reinterpret_cast<unsigned long long*>(cursors);
+  sa.dest_cols = dest_cols;
+  sa.dest_offsets = dest_offsets;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HB_CUDA(cudaMemsetAsync(cursors, 0, sizeof(uint64_t) * n_regions, st));
+  const size_t staging = size_t(kTileRows) * lw.stage_row_bytes;
+  if (n_regions <= kStagedMaxPartitions && staging <= 96 * 1024) {
+    HB_CUDA(cudaFuncSetAttribute(shuffle_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(staging)));
+    shuffle_tile_kernel<true, true><<<sm_count() * 3, kShufThreads, staging, st>>>(sa);
+  } else {
+    shuffle_tile_kernel<true><<<sm_count() * 4, kShufThreads, 0, st>>>(sa);
+  }
   HB_LAUNCH_CHECK();
   return HDK_B200_OK;
 }

@@ -6,7 +6,7 @@ are merged on the host (QE/Execute.cpp:1224-1336).  Three exchange patterns (SUR
   * perfect-hash group-by  : every rank scans its fragments into a NEUTRAL work table
                              (hdk_b200_launch_partial) → all-reduce per merge class
                              (int64 SUM | fp64 SUM | MIN | MAX) → hdk_b200_finalize
-  * baseline-hash group-by : rows are re-partitioned by MurmurHash64A(key) % world
+  * baseline-hash group-by : rows are re-partitioned by floor(hi32(MurmurHash64A(key)) * world / 2^32)
                              (hdk_b200_shuffle_count / _scatter, model: QE/RelAlgExecutor.cpp:691-838)
                              → all-to-all → local aggregate; results are disjoint, no merge
   * small join build side  : built once on rank 0, broadcast (table + inner columns)

@@ -311,6 +311,11 @@ class Executor:
         self.config = config or planner.Config()
         self.ctx = DeviceContext(device, hot_data)
         self.compact_threshold_bytes = 64 << 20   # larger group-by buffers are iterated on the device (hdk_b200_compact_result)
+        # Baseline-hash tables beyond this many bytes get their rows regrouped by table region first (0 = never).
+        # Off by default: measured on config 4 (250 M rows, 25 M groups, 134 regions) the two extra passes cost more
+        # than the L2-resident aggregate saves with the current direct scatter (39 ms vs 27 ms) — see DESIGN.md §3.
+        self.region_pass_threshold_bytes = 0
+        self.region_bytes = 12 << 20                   # target size of one region (a fraction of L2)
         self.partition_over_peer_memory = True    # execute_partitioned: scatter straight into the owners' buffers (else NCCL all-to-all)
         self._peer_rows = {}
         self.lib = _lib.lib()
@@ -538,14 +543,58 @@ class Executor:
         """init buffer + fused kernel (asynchronous on the current stream)."""
         st = self.ctx.stream_ptr()
         info = abi.LaunchInfo()
+        kp = prep["kp"]
         if pq.qmd.hash_type == abi.BASELINE_HASH:
             _lib.check(self.lib.hdk_b200_init_group_by_buffer(C.byref(pq.qmd), prep["out"].data_ptr(), st), "init_group_by_buffer")
+            if self._wants_region_pass(pq, prep):
+                kp = self._regroup_by_table_region(pq, prep)
         prep["err"].zero_()
         _lib.check(self.lib.hdk_b200_launch(C.byref(pq.plan), C.byref(pq.qmd), C.byref(ko) if ko is not None else None,
-                                            C.byref(prep["kp"]), prep["scratch"].data_ptr(), prep["scratch_bytes"], st,
+                                            C.byref(kp), prep["scratch"].data_ptr(), prep["scratch_bytes"], st,
                                             C.byref(info)), "launch")
         self.last_launch_info = info
         return info
+
+    # -- locality pass for large baseline-hash tables ----------------------------------------------------------
+    def _table_bytes(self, pq):
+        return int(pq.qmd.entry_count) * 8 * (int(pq.plan.n_targets) + int(pq.qmd.key_count) + 2)   # buffer rows + work cells, roughly
+
+    def _wants_region_pass(self, pq, prep) -> bool:
+        """Worth regrouping the rows by table region?  Only when the table is far larger than L2 (random DRAM sectors per
+        row otherwise) and the plan has no joins (the passes re-read plain outer columns)."""
+        if not self.region_pass_threshold_bytes or pq.unit.joins:
+            return False
+        return self._table_bytes(pq) >= self.region_pass_threshold_bytes and int(prep["kp"].total_rows_hint) > 0
+
+    def _regroup_by_table_region(self, pq, prep):
+        """hdk_b200_region_count → exclusive scan → hdk_b200_region_scatter_to into one buffer per column, regions in
+        order; returns kernel params over that single regrouped fragment.  Everything stays on the stream."""
+        torch = self.ctx.torch
+        dev = self.ctx.device
+        st = self.ctx.stream_ptr()
+        outer = self.storage.get_table(pq.unit.table)
+        widths = [outer.columns[c].phys_width for c in pq.columns]
+        n_regions = int(min(1024, max(2, -(-self._table_bytes(pq) // self.region_bytes))))
+        total = int(prep["kp"].total_rows_hint)
+        counts = torch.zeros(n_regions, dtype=torch.int64, device=dev)
+        _lib.check(self.lib.hdk_b200_region_count(C.byref(pq.plan), C.byref(pq.qmd), C.byref(prep["kp"]), n_regions, counts.data_ptr(), st),
+                   "region_count")
+        offsets = torch.cumsum(counts, 0) - counts
+        cursors = torch.zeros(n_regions, dtype=torch.int64, device=dev)
+        cols = [torch.empty(max(total, 1) * w, dtype=torch.uint8, device=dev) for w in widths]
+        dest = torch.tensor([t.data_ptr() for t in cols] * n_regions, dtype=torch.int64, device=dev)
+        _lib.check(self.lib.hdk_b200_region_scatter_to(C.byref(pq.plan), C.byref(pq.qmd), C.byref(prep["kp"]), n_regions, dest.data_ptr(),
+                                                       offsets.data_ptr(), cursors.data_ptr(), st), "region_scatter_to")
+        ptrs = torch.tensor([t.data_ptr() for t in cols], dtype=torch.int64, device=dev)
+        n_rows = counts.sum().reshape(1)                    # rows that passed the filters: stays on the device
+        old = prep["kp"]
+        kp = abi.KernelParams()
+        C.memmove(C.byref(kp), C.byref(old), C.sizeof(kp))
+        kp.col_buffers = ptrs.data_ptr()
+        kp.num_fragments = 1
+        kp.num_rows = n_rows.data_ptr()
+        prep["keep"] += [cols, dest, ptrs, n_rows, counts, offsets, cursors]
+        return kp
 
     # -- multi-GPU split of the perfect-hash launch (SURVEY §8e) ------------------------------------
     def work_table_layout(self, pq: planner.PlannedQuery) -> abi.WorkTableLayout:
@@ -596,7 +645,7 @@ class Executor:
 
     def execute_partitioned(self, unit: ir.ExecutionUnit, max_groups_buffer_entry_count: int, group=None):
         """baseline hash across ranks (model: QE/RelAlgExecutor.cpp:691-838): partition this rank's
-        rows by MurmurHash64A(key) % world on the device (count → scatter), exchange the partitions with an
+        rows by the upper half of MurmurHash64A(key), range-reduced to world, on the device (count → scatter), exchange the partitions with an
         NCCL all-to-all, aggregate the received rows locally.  Every key lives on exactly one rank afterwards,
         so there is no merge: the result is the concatenation of the ranks' ResultSets.
         Returns (ResultSet of this rank's key partition, rows received)."""

@@ -483,8 +483,8 @@ HDK_B200_API int hdk_b200_probe_baseline_hash_join_on_device(const int8_t* hash_
 /* ============================================================================
  * Partitioned aggregation shuffle (model: QE/RelAlgExecutor.cpp:691-838,
  * partition function MurmurHash64A over 64-bit-widened keys & (P-1)…
- * QE/RowFuncBuilder.cpp:516-577; here modulo n_partitions so that any GPU count
- * works).  Two passes over the fragments of one device:
+ * QE/RowFuncBuilder.cpp:516-577; here floor(upper 32 bits * n_partitions / 2^32) so that
+ * any GPU count works without a modulo).  Two passes over the fragments of one device:
  *   pass 1: hdk_b200_shuffle_count  → counts[n_partitions] (device uint64)
  *   pass 2: hdk_b200_shuffle_scatter → rows written partition-contiguous into
  *           `out_cols[c]` (one device array per plan column, outer table only)
@@ -499,6 +499,18 @@ HDK_B200_API int hdk_b200_shuffle_scatter(const hdk_b200_plan* plan, const hdk_b
                              const uint64_t* offsets /* DEVICE [n_partitions] exclusive prefix */,
                              uint64_t* cursors /* DEVICE [n_partitions], zeroed by callee */,
                              int8_t* const* out_cols /* DEVICE array [n_cols] */, void* stream);
+/* Locality pass for large baseline-hash group-bys on ONE GPU (same two passes, different partition function): rows are
+ * regrouped by the REGION of the group-by table their key hashes into (region = floor(slot * n_regions / entry_count),
+ * slot = key_hash % entry_count as in get_group_value, QE/GroupByRuntime.cpp:31-54).  Aggregating the regrouped rows in
+ * order then touches one L2-sized region of the table at a time instead of a random 32-byte sector of a multi-GB table
+ * per row.  Results are unchanged (same hash, same probing, same table).  Filters are applied by the passes. */
+HDK_B200_API int hdk_b200_region_count(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, const hdk_b200_kernel_params* params,
+                                       uint32_t n_regions, uint64_t* counts /* DEVICE [n_regions] */, void* stream);
+HDK_B200_API int hdk_b200_region_scatter_to(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, const hdk_b200_kernel_params* params,
+                                            uint32_t n_regions, int8_t* const* dest_cols /* DEVICE [n_regions * n_cols] */,
+                                            const uint64_t* dest_offsets /* DEVICE [n_regions] */,
+                                            uint64_t* cursors /* DEVICE [n_regions], zeroed by callee */, void* stream);
+
 /* pass 2 with one destination per partition: partition p's rows go to dest_cols[p * n_cols + c] (DEVICE array of DEVICE
  * pointers) starting at row dest_offsets[p].  The pointers may address PEER memory (hdk_b200_peer_alloc / _open): the
  * scatter kernel then IS the all-to-all — each GPU writes its rows straight into the owners' receive buffers through

@@ -665,6 +665,28 @@ def test_executor_iterates_large_buffers_on_device(env, torch):
         assert ex.execute_work_unit(sql.parse(text, st.tables)).row_count() == host_side.num_rows
 
 
+@pytest.mark.parametrize("idx", [12, 13, 14, 15])
+def test_baseline_region_pass_does_not_change_results(oracle_mod, env, torch, idx):
+    """Regrouping the rows by table region (hdk_b200_region_count / _scatter_to) before a baseline-hash aggregate is a
+    pure locality optimisation: forced on for the small test tables (several region counts, staged and direct scatter),
+    the result must still equal the oracle's, filters and 4-byte / columnar key layouts included."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    text, nk, kw = QUERIES[idx]
+    for region_bytes in (1 << 20, 64 << 10, 4 << 10):
+        ex = Executor(st, kw.get("cfg"))
+        ex.region_pass_threshold_bytes, ex.region_bytes = 1, region_bytes
+        pq = ex.plan(sql.parse(text, st.tables), kw.get("max_groups_buffer_entry_count"), kw.get("output_columnar"))
+        assert pq.qmd.hash_type == abi.BASELINE_HASH
+        prep = ex.prepare(pq)
+        assert ex._wants_region_pass(pq, prep)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0
+        check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+
+
 @pytest.mark.parametrize("P", [1, 5, 40])
 def test_shuffle_scatter_to_per_partition_destinations(L, env, torch, P):
     """hdk_b200_shuffle_scatter_to: every partition into its own destination buffers at its own row offset (the shape
