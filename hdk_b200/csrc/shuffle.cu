@@ -42,23 +42,46 @@ struct ShuffleArgs {
   uint32_t region_mode, entry_count, key_width, region_mul;   // region = min(umulhi(slot, region_mul), n_partitions - 1)
 };
 
-// partition id from the (64-bit widened) group keys
-__device__ __forceinline__ int partition_of_keys(const ShuffleArgs& a, int64_t* keys, int n_keys) {
+// partition id from the (64-bit widened) group keys.  The loops are unrolled over the maximum key count with an early
+// exit so that keys[] is only ever indexed by constants and stays in registers.
+__device__ __forceinline__ int partition_of_keys(const ShuffleArgs& a, const int64_t* keys, int n_keys) {
   if (a.region_mode) {
     // the slot the baseline probe starts at: key_hash (MurmurHash3 over the key bytes at key_width) % entry_count
-    if (a.key_width == 4)
-      for (int k = 0; k < n_keys; ++k) keys[k] = int64_t(int32_t(keys[k]));
-    const uint32_t slot = key_hash_dev(keys, n_keys, int(a.key_width)) % a.entry_count;
+    uint32_t h = 0;
+#pragma unroll
+    for (int k = 0; k < HDK_B200_MAX_KEYS; ++k) {
+      if (k >= n_keys) break;
+      h = mm3_block(h, uint32_t(uint64_t(keys[k])));
+      if (a.key_width == 8) h = mm3_block(h, uint32_t(uint64_t(keys[k]) >> 32));
+    }
+    const uint32_t slot = mm3_final(h, uint32_t(n_keys) * a.key_width) % a.entry_count;
     return int(min(__umulhi(slot, a.region_mul), a.n_partitions - 1));
   }
-  return int(mod_partitions(murmur64a_keys(keys, n_keys), a.n_partitions));
+  const uint64_t m = 0xc6a4a7935bd1e995ULL;   // MurmurHash64A over the 64-bit widened keys, seed 0 (baseline.cuh)
+  uint64_t h = uint64_t(n_keys) * 8 * m;
+#pragma unroll
+  for (int k = 0; k < HDK_B200_MAX_KEYS; ++k) {
+    if (k >= n_keys) break;
+    uint64_t x = uint64_t(keys[k]) * m;
+    x ^= x >> 47;
+    x *= m;
+    h ^= x;
+    h *= m;
+  }
+  h ^= h >> 47;
+  h *= m;
+  h ^= h >> 47;
+  return int(mod_partitions(h, a.n_partitions));
 }
 
-__device__ __forceinline__ int row_partition_direct(const ShuffleArgs& a, const int8_t* const* cols, uint64_t pos) {
+// kbase[k]: the tile's fragment base of key column k, loaded once per tile (no pointer → data chain per row)
+__device__ __forceinline__ int row_partition_direct(const ShuffleArgs& a, const int8_t* const* kbase, uint64_t pos) {
   int64_t keys[HDK_B200_MAX_KEYS];
-  for (int k = 0; k < a.plan.n_keys; ++k) {
+#pragma unroll
+  for (int k = 0; k < HDK_B200_MAX_KEYS; ++k) {
+    if (k >= a.plan.n_keys) break;
     const int w = a.key_w[k];
-    const int8_t* ptr = cols[a.key_col[k]] + pos * w;
+    const int8_t* ptr = kbase[k] + pos * w;
     int64_t v = w == 8 ? *reinterpret_cast<const int64_t*>(ptr) : w == 4 ? int64_t(*reinterpret_cast<const int32_t*>(ptr))
                 : w == 2 ? int64_t(*reinterpret_cast<const int16_t*>(ptr)) : int64_t(*ptr);
     if (a.key_days[k]) v = (v == int_null_of(w)) ? INT64_MIN : v * 86400;
@@ -161,13 +184,20 @@ __device__ __forceinline__ void tile_of(const ShuffleArgs& a, uint64_t tile, con
   row0 = (tile - frag_tile_prefix[frag]) * uint64_t(kTileRows);
 }
 
+__device__ __forceinline__ void copy_elem(void* o, const void* src, int w) {
+  if (w == 8) *reinterpret_cast<uint64_t*>(o) = *reinterpret_cast<const uint64_t*>(src);
+  else if (w == 4) *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(src);
+  else if (w == 2) *reinterpret_cast<uint16_t*>(o) = *reinterpret_cast<const uint16_t*>(src);
+  else *reinterpret_cast<uint8_t*>(o) = *reinterpret_cast<const uint8_t*>(src);
+}
+
 // kStaged (few partitions, narrow rows): the tile's rows are first regrouped by partition in shared memory, then every
 // partition's run is copied out with consecutive threads writing consecutive elements — whole 128-byte lines per warp
 // instead of a handful of elements per destination, which is what NVLink wants when the destinations are peers.
 constexpr uint32_t kStagedMaxPartitions = 32;
 
 template <bool kScatter, bool kStaged = false>
-__global__ void __launch_bounds__(kShufThreads) shuffle_tile_kernel(const __grid_constant__ ScatterToArgs sa) {
+__global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __grid_constant__ ScatterToArgs sa) {
   const ShuffleArgs& a = sa.base;
   const DPlan& p = a.plan;
   extern __shared__ __align__(16) uint8_t staging[];      // kStaged: column-major copy of the tile, rows grouped by partition
@@ -196,11 +226,22 @@ __global__ void __launch_bounds__(kShufThreads) shuffle_tile_kernel(const __grid
     tile_of(a, tile, frag_tile_prefix, frag, row0);
     const int8_t* const* cols = a.col_buffers + size_t(frag) * p.n_cols;
     const uint64_t rows = uint64_t(a.num_rows[frag]);
+    const int8_t* kbase[HDK_B200_MAX_KEYS];
+    if (a.direct) {
+#pragma unroll
+      for (int k = 0; k < HDK_B200_MAX_KEYS; ++k) kbase[k] = k < p.n_keys ? cols[a.key_col[k]] : nullptr;
+    }
+    constexpr int kHoist = 8;                 // column bases kept in registers for the copies (more columns: re-read)
+    const int8_t* cbase[kHoist];
+    if (kScatter) {
+#pragma unroll
+      for (int c = 0; c < kHoist; ++c) cbase[c] = c < p.n_cols ? cols[c] : nullptr;
+    }
     int part[kShufRowsPerThread];
 #pragma unroll
     for (int r = 0; r < kShufRowsPerThread; ++r) {
       const uint64_t pos = row0 + uint64_t(r) * kShufThreads + tid;      // coalesced: consecutive threads, consecutive rows
-      part[r] = pos < rows ? (a.direct ? row_partition_direct(a, cols, pos) : row_partition(a, cols, pos, vals)) : -1;
+      part[r] = pos < rows ? (a.direct ? row_partition_direct(a, kbase, pos) : row_partition(a, cols, pos, vals)) : -1;
       // warp-aggregated histogram update
       const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
       if (part[r] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[part[r]], (unsigned)__popc(peers));
@@ -231,14 +272,15 @@ __global__ void __launch_bounds__(kShufThreads) shuffle_tile_kernel(const __grid
         start = __shfl_sync(peers, start, leader);
         const uint32_t lp = run_start[part[r]] + start + __popc(peers & ((1u << lane) - 1u));   // position inside the tile
         const uint64_t pos = row0 + uint64_t(r) * kShufThreads + tid;
-        for (int c = 0; c < p.n_cols; ++c) {
+#pragma unroll
+        for (int c = 0; c < kHoist; ++c) {
+          if (c >= p.n_cols) break;
           const int w = p.col_width[c];
-          const int8_t* src = cols[c] + pos * w;
-          uint8_t* o = staging + stage_col_off[c] + size_t(lp) * w;
-          if (w == 8) *reinterpret_cast<uint64_t*>(o) = *reinterpret_cast<const uint64_t*>(src);
-          else if (w == 4) *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(src);
-          else if (w == 2) *reinterpret_cast<uint16_t*>(o) = *reinterpret_cast<const uint16_t*>(src);
-          else *o = uint8_t(*src);
+          copy_elem(staging + stage_col_off[c] + size_t(lp) * w, cbase[c] + pos * w, w);
+        }
+        for (int c = kHoist; c < p.n_cols; ++c) {
+          const int w = p.col_width[c];
+          copy_elem(staging + stage_col_off[c] + size_t(lp) * w, cols[c] + pos * w, w);
         }
       }
       __syncthreads();
@@ -273,14 +315,15 @@ __global__ void __launch_bounds__(kShufThreads) shuffle_tile_kernel(const __grid
       const uint64_t dst = base[part[r]] + start + __popc(peers & ((1u << lane) - 1u));
       const uint64_t pos = row0 + uint64_t(r) * kShufThreads + tid;
       int8_t* const* out = sa.dest_cols + size_t(part[r]) * p.n_cols;
-      for (int c = 0; c < p.n_cols; ++c) {
+#pragma unroll
+      for (int c = 0; c < kHoist; ++c) {
+        if (c >= p.n_cols) break;
         const int w = p.col_width[c];
-        const int8_t* src = cols[c] + pos * w;
-        int8_t* o = out[c] + dst * w;
-        if (w == 8) *reinterpret_cast<uint64_t*>(o) = *reinterpret_cast<const uint64_t*>(src);
-        else if (w == 4) *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(src);
-        else if (w == 2) *reinterpret_cast<uint16_t*>(o) = *reinterpret_cast<const uint16_t*>(src);
-        else *o = *src;
+        copy_elem(out[c] + dst * w, cbase[c] + pos * w, w);
+      }
+      for (int c = kHoist; c < p.n_cols; ++c) {
+        const int w = p.col_width[c];
+        copy_elem(out[c] + dst * w, cols[c] + pos * w, w);
       }
     }
     __syncthreads();
