@@ -108,26 +108,6 @@ __device__ __forceinline__ int row_partition(const ShuffleArgs& a, const int8_t*
   return partition_of_keys(a, keys, p.n_keys);
 }
 
-__global__ void shuffle_count_kernel(const __grid_constant__ ShuffleArgs a) {
-  __shared__ unsigned int hist[kMaxPartitions];
-  for (uint32_t i = threadIdx.x; i < a.n_partitions; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
-  V vals[HDK_B200_MAX_EXPRS];
-  const uint64_t start = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-  const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
-  for (uint32_t f = 0; f < a.num_fragments; ++f) {
-    const int8_t* const* cols = a.col_buffers + size_t(f) * a.plan.n_cols;
-    const uint64_t rows = uint64_t(a.num_rows[f]);
-    for (uint64_t pos = start; pos < rows; pos += step) {
-      const int part = row_partition(a, cols, pos, vals);
-      if (part >= 0) atomicAdd(&hist[part], 1u);
-    }
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < a.n_partitions; i += blockDim.x)
-    if (hist[i]) atomicAdd(a.counts + i, (unsigned long long)hist[i]);
-}
-
 __global__ void shuffle_scatter_kernel(const __grid_constant__ ShuffleArgs a) {
   V vals[HDK_B200_MAX_EXPRS];
   const DPlan& p = a.plan;
