@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __g
       hist[i] = 0;   // becomes the running position inside the reservation
     }
     __syncthreads();
-    if (kStaged) {
+    if constexpr (kStaged) {
 #pragma unroll
       for (int r = 0; r < kShufRowsPerThread; ++r) {
         const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
@@ -280,10 +280,7 @@ __global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __g
         }
       }
       __syncthreads();
-      for (uint32_t i = tid; i < a.n_partitions; i += kShufThreads) hist[i] = 0;
-      __syncthreads();
-      continue;
-    }
+    } else {
 #pragma unroll
     for (int r = 0; r < kShufRowsPerThread; ++r) {
       const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
@@ -305,6 +302,7 @@ __global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __g
         const int w = p.col_width[c];
         copy_elem(out[c] + dst * w, cols[c] + pos * w, w);
       }
+    }
     }
     __syncthreads();
     for (uint32_t i = tid; i < a.n_partitions; i += kShufThreads) hist[i] = 0;

@@ -426,6 +426,16 @@ class Executor:
         self.join_tables[cache_key] = jt
         return jt
 
+    def _linear_inner_column(self, jt: JoinTable, cname: str):
+        """Inner-table column addressed by the join's row ids: the fragments' chunks back to back, like
+        ColumnFetcher::linearizeColumnFragments (QE/ColumnFetcher.cpp) — the single chunk itself when there is only one."""
+        frs = jt.inner_table.fragments
+        if len(frs) == 1:
+            return self.ctx.chunk(frs[0], cname)
+        if cname not in jt.inner_columns_dev:
+            jt.inner_columns_dev[cname] = self.ctx.torch.cat([self.ctx.chunk(f, cname) for f in frs])
+        return jt.inner_columns_dev[cname]
+
     def _slot_ordered_column(self, jt: JoinTable, cname: str):
         """hdk_b200_gather_join_payload_on_device: copy of an inner column ordered by hash slot (+ presence bitmap),
         made once per (join table, column) and cached with the table."""
@@ -434,9 +444,7 @@ class Executor:
         if cname in jt.by_slot:
             return jt.by_slot[cname]
         torch = self.ctx.torch
-        if len(jt.inner_table.fragments) != 1:
-            raise planner.UnsupportedPlan("inner table columns must be a single fragment (ColumnFetcher linearises them)")
-        src = self.ctx.chunk(jt.inner_table.fragments[0], cname)
+        src = self._linear_inner_column(jt, cname)
         width = jt.inner_table.columns[cname].phys_width
         out = torch.empty(max(jt.entry_count, 1) * width, dtype=torch.uint8, device=self.ctx.device)
         if jt.bitmap is None:
@@ -482,9 +490,7 @@ class Executor:
                 if by_slot:
                     inner[j * abi.MAX_COLS + c] = jt.by_slot[cname].data_ptr()
                     continue
-                if len(jt.inner_table.fragments) != 1:
-                    raise planner.UnsupportedPlan("inner table columns must be a single fragment (ColumnFetcher linearises them)")
-                d = self.ctx.chunk(jt.inner_table.fragments[0], cname)
+                d = self._linear_inner_column(jt, cname)
                 keep.append(d)
                 inner[j * abi.MAX_COLS + c] = d.data_ptr()
         d_jt = torch.from_numpy(jt_addr).to(dev)

@@ -167,6 +167,34 @@ def test_join_probe_table_vs_slot_ordered_payload(oracle_mod, env, torch, by_slo
     check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
 
 
+def test_join_inner_table_with_several_fragments(oracle_mod, env, torch):
+    """Inner-table columns are linearised across fragments (row ids of the join table are table-wide), for the table
+    probe, the slot-ordered payload and the baseline (composite-key) probe."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, _ = env
+    st = util.make_storage({"t": tables["t"], "dim": tables["dim"]}, fragment_size={"t": 7001, "dim": 137})
+    assert len(st.get_table("dim").fragments) > 5
+    for by_slot in (True, False):
+        ex = Executor(st, planner.Config(join_payload_by_slot=by_slot))
+        pq = ex.plan(sql.parse(QUERIES[17][0], st.tables))
+        prep = ex.prepare(pq)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0
+        check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), 2)
+    ct = util.composite_join_tables()
+    st2 = util.make_storage(ct, fragment_size={"t": 1201, "dim": 97, "dim2": 100000})
+    ex = Executor(st2)
+    text, nk = util.COMPOSITE_JOIN_QUERIES[1]
+    pq = ex.plan(sql.parse(text, st2.tables))
+    prep = ex.prepare(pq)
+    ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    check_against_oracle(oracle_mod, st2, pq, prep["out"].cpu().numpy(), nk)
+
+
 def test_join_probe_sparse_dimension_uses_bitmap(oracle_mod, torch):
     """A dimension whose keys leave holes in [min, max]: the slot-ordered probe has to consult the presence bitmap."""
     from hdk_b200.executor import Executor
