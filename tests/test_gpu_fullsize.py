@@ -104,3 +104,60 @@ def test_full_size_taxi_properties(oracle_mod, taxi):
                                      err.data_ptr(), None) == 0
             torch.cuda.synchronize()
             assert int(err.item()) == 0 and torch.equal(bufs[0], whole["out"]), q
+
+
+def test_reduce_and_launch_with_buffers_beyond_4_gib(oracle_mod):
+    """ResultSetTest.cpp ReduceLargeBuffers.*Overflow32: group-by buffers larger than 2^32 bytes (150 M baseline entries
+    x 32 B = 4.8 GB).  Launch, finalize, reduce and compaction must address them with 64-bit offsets: split invariance
+    (whole == reduce of two halves) as decoded rows, entries must exist beyond the 4 GiB offset, and the decoded rows
+    must equal the oracle's on a normally sized table."""
+    import pyarrow as pa
+    import torch
+    from hdk_b200 import sql
+    from hdk_b200.executor import Executor, ResultSet
+    free, _ = torch.cuda.mem_get_info()
+    if free < 24 << 30:
+        pytest.skip("needs ~24 GB of device memory")
+    rng = np.random.default_rng(9)
+    n = 40_000
+    t = pa.table({"big": rng.integers(-2**62, 2**62, n), "s": rng.integers(0, 7, n).astype(np.int16),
+                  "v": pa.array(rng.integers(-2**40, 2**40, n), mask=rng.random(n) < 0.02)})
+    st = util.make_storage({"t": t}, fragment_size=10_000)
+    text = "SELECT big, s, COUNT(*), SUM(v), MIN(v) FROM t GROUP BY big, s"
+    E = 150_000_000
+    ex = Executor(st)
+    ex.compact_threshold_bytes = 1 << 62
+    pq = ex.plan(sql.parse(text, st.tables), E)
+    assert pq.qmd.hash_type == abi.BASELINE_HASH and ex.lib.hdk_b200_buffer_size_bytes(C.byref(pq.qmd)) > (1 << 32)
+    frags = st.get_table("t").fragments
+    whole = ex.prepare(pq)
+    ex.launch(pq, whole)
+    torch.cuda.synchronize()
+    assert int(whole["err"].item()) == 0
+    parts = []
+    for part in (frags[:2], frags[2:]):
+        pp = ex.prepare(pq, fragments=part)
+        ex.launch(pq, pp)
+        torch.cuda.synchronize()
+        assert int(pp["err"].item()) == 0
+        parts.append(pp)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert ex.lib.hdk_b200_reduce(C.byref(pq.plan), C.byref(pq.qmd), parts[0]["out"].data_ptr(), parts[1]["out"].data_ptr(), E,
+                                  err.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    # entries beyond the 4 GiB offset exist in the whole-table buffer (keys are spread uniformly)
+    row_bytes = whole["out"].numel() // E
+    first_key = whole["out"].view(torch.int64)[:: row_bytes // 8]
+    far = first_key[(1 << 32) // row_bytes + 1:]
+    assert int((far != abi.EMPTY_KEY_64).sum().item()) > 100
+    # decoded rows: whole == reduced halves == oracle over a small table of the same plan
+    rows_whole = ResultSet.from_compact(pq, ex.compact_on_device(pq, whole["out"])).to_arrow().sort_by([("big", "ascending"), ("s", "ascending")])
+    rows_red = ResultSet.from_compact(pq, ex.compact_on_device(pq, parts[0]["out"])).to_arrow().sort_by([("big", "ascending"), ("s", "ascending")])
+    assert rows_whole.equals(rows_red) and rows_whole.num_rows > 30_000
+    pq_small = util.plan_sql(st, text, max_groups_buffer_entry_count=131072)
+    obuf, oerr = util.run_oracle(oracle_mod, st, pq_small)
+    assert oerr == 0
+    exp = util.sort_rows(util.result_columns(oracle_mod, pq_small, obuf), 2)
+    got = [tuple(r.values()) for r in rows_whole.to_pylist()]
+    util.assert_rows_equal(got, exp)
