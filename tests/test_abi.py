@@ -39,7 +39,7 @@ def test_struct_sizes_match_header():
                "hdk_b200_kernel_params": abi.KernelParams, "hdk_b200_kernel_options": abi.KernelOptions,
                "hdk_b200_launch_info": abi.LaunchInfo, "hdk_b200_work_table_layout": abi.WorkTableLayout,
                "hdk_b200_join_chunk": abi.JoinChunk, "hdk_b200_join_column": abi.JoinColumn,
-               "hdk_b200_join_column_type_info": abi.JoinColumnTypeInfo}
+               "hdk_b200_join_column_type_info": abi.JoinColumnTypeInfo, "hdk_b200_chunk_stats": abi.ChunkStatsPOD}
     prog = '#include <stdio.h>\n#include "hdk_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in structs) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:
