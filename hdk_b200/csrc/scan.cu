@@ -1080,8 +1080,9 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   // tuning hook (tools/sweep_geo.py): HDK_B200_GEO="strategy,consumer_threads,ctas_per_sm,stages,tile_rows" overrides the search
   if (const char* env = getenv("HDK_B200_GEO")) {
     int es = 0, en = 0, ec = 0, est = 0, et = 0;
-    if (!baseline && sscanf(env, "%d,%d,%d,%d,%d", &es, &en, &ec, &est, &et) == 5 && en >= 32 && en <= kConsumerWarps * 32 && en % 32 == 0 &&
-        est >= 1 && est <= kStages && et >= 32 && es >= 0 && es <= HDK_B200_STRATEGY_REGISTER && es != HDK_B200_STRATEGY_BASELINE) {
+    if (sscanf(env, "%d,%d,%d,%d,%d", &es, &en, &ec, &est, &et) == 5 && en >= 32 && en <= kConsumerWarps * 32 && en % 32 == 0 &&
+        est >= 1 && est <= kStages && et >= 32 && es >= 0 && es <= HDK_B200_STRATEGY_REGISTER &&
+        (es == HDK_B200_STRATEGY_BASELINE) == baseline) {
       size_t bins = 0;
       for (int i = 0; i < p.n_acc; ++i) {
         bins = align_up(bins, 16);
