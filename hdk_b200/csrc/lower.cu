@@ -61,7 +61,7 @@ static int acc_class(uint8_t kind) {  // 0 sum_i, 1 sum_f, 2 min, 3 max
 int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
   if (!plan || !q || !out) { set_error("null plan/qmd"); return HDK_B200_E_INVALID; }
   if (plan->abi_version != HDK_B200_ABI_VERSION) { set_error("plan ABI version %d != %d", plan->abi_version, HDK_B200_ABI_VERSION); return HDK_B200_E_INVALID; }
-  if (plan->n_exprs < 0 || plan->n_exprs > HDK_B200_MAX_EXPRS || plan->n_keys < 1 || plan->n_keys > HDK_B200_MAX_KEYS ||
+  if (plan->n_exprs < 0 || plan->n_exprs > HDK_B200_MAX_EXPRS || plan->n_keys < 0 || plan->n_keys > HDK_B200_MAX_KEYS ||
       plan->n_targets < 1 || plan->n_targets > HDK_B200_MAX_TARGETS || plan->n_filters < 0 ||
       plan->n_filters > HDK_B200_MAX_FILTERS || plan->n_joins < 0 || plan->n_joins > HDK_B200_MAX_JOINS ||
       plan->n_cols < 0 || plan->n_cols > HDK_B200_MAX_COLS) {
@@ -180,6 +180,11 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
       if (s.cardinality <= 0) { set_error("key %d: bad cardinality", k); return HDK_B200_E_INVALID; }
       mult *= s.cardinality;
     }
+  }
+  if (plan->n_keys == 0 && !(q->hash_type == HDK_B200_PERFECT_HASH && q->keyless && q->entry_count == 1 && !q->output_columnar)) {
+    // non-grouped aggregate (QueryDescriptionType::NonGroupedAggregate): zero keys = one keyless row-wise entry
+    set_error("a plan without group keys needs a keyless perfect-hash descriptor with one entry");
+    return HDK_B200_E_INVALID;
   }
   if (q->hash_type == HDK_B200_PERFECT_HASH) {
     if (plan->n_keys == 1) {

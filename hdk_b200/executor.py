@@ -177,7 +177,9 @@ class ResultSet:
             return raw.view(np.int64 if w == 8 else np.int32).reshape(E).astype(np.int64)
 
         # non-empty entries (ResultSetStorage::isEmptyEntry)
-        if q.keyless:
+        if q.key_count == 0:
+            valid = np.ones(E, dtype=bool)     # non-grouped aggregate: the single row is always returned (COUNT 0 / NULL sums)
+        elif q.keyless:
             s = q.target_idx_for_key
             init = q.init_vals[s]
             if q.slot_padded[s] == 4:

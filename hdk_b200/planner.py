@@ -281,8 +281,11 @@ class PlannedQuery:
 def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, cfg: Config = Config(),
                 max_groups_buffer_entry_count: Optional[int] = None, force_hash_type: Optional[int] = None,
                 output_columnar: Optional[bool] = None) -> PlannedQuery:
-    if not unit.groupby_exprs:
-        raise UnsupportedPlan("non-grouped aggregates are outside the hot path")
+    # Non-grouped aggregates (SELECT COUNT(*), SUM(x) ... without GROUP BY; the reference's
+    # QueryDescriptionType::NonGroupedAggregate) run as the degenerate group-by: zero keys, one keyless entry.
+    non_grouped = not unit.groupby_exprs
+    if non_grouped and any(not isinstance(t, ir.AggExpr) for t in unit.target_exprs):
+        raise UnsupportedPlan("a query without GROUP BY may only select aggregates")
     if len(unit.groupby_exprs) > abi.MAX_KEYS:
         raise UnsupportedPlan("too many group keys")
     for g in unit.groupby_exprs:
@@ -311,13 +314,20 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
     if cri.hash_type == abi.PERFECT_HASH:
         keyless, tidx = get_keyless_info(infos, col_stats)
         q.keyless = int(keyless and not cri.bucket)
+        if non_grouped:
+            q.keyless, columnar = 1, False      # one entry, nothing to key; the row is always part of the result
+            q.output_columnar = 0
+            tidx = tidx if keyless else 0
         if columnar and q.keyless:
             # keyless + columnar drives get_columnar_group_bin_offset over a slot column in the
             # reference (QE/RowFuncBuilder.cpp:604-607); we keep keys in that case.
             q.keyless = 0
         q.target_idx_for_key = tidx
         q.key_width = 8
-        if len(unit.groupby_exprs) > 1:
+        if non_grouped:
+            q.entry_count = 1
+            q.min_val = q.max_val = q.bucket = q.has_nulls = 0
+        elif len(unit.groupby_exprs) > 1:
             q.entry_count = cri.max
             q.min_val, q.max_val, q.bucket, q.has_nulls = 0, cri.max, 0, int(cri.has_nulls)
         else:

@@ -244,6 +244,33 @@ def test_fused_baseline_join_probe(oracle_mod, L, torch, text, nk):
     util.assert_rows_equal(got, util.sqlite_rows(tables, text + " ORDER BY " + order, nk), rel=1e-9)
 
 
+@pytest.mark.parametrize("text", util.NON_GROUPED_QUERIES)
+def test_non_grouped_aggregates(oracle_mod, torch, text):
+    """Aggregates without GROUP BY on the GPU: buffer byte-identical to the oracle's where there is no fp sum, one row
+    out, SQLite agrees (through hdk.sql)."""
+    import hdk_b200.hdk as hdkmod
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables = util.composite_join_tables()
+    st = util.make_storage(tables, fragment_size={"t": 1201, "dim": 100000, "dim2": 100000})
+    ex = Executor(st)
+    pq = ex.plan(sql.parse(text, st.tables))
+    prep = ex.prepare(pq)
+    ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    obuf, oerr = util.run_oracle(oracle_mod, st, pq)
+    assert oerr == 0
+    if not any(ti.arg_type is not None and ti.arg_type.is_fp and ti.agg in (abi.AGG_SUM, abi.AGG_AVG) for ti in pq.infos):
+        assert np.array_equal(prep["out"].cpu().numpy(), obuf)
+    h = hdkmod.init()
+    for name, tb in tables.items():
+        h.import_arrow(tb, name, fragment_size=1201 if name == "t" else 100000)
+    got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+    assert len(got) == 1
+    util.assert_rows_equal(got, util.sqlite_rows(tables, text, 0), rel=1e-9)
+
+
 def test_gather_join_payload_kernel(L, torch):
     """out[slot] = col[table[slot]] for present slots, 0 otherwise; bitmap bit = present — for every element width."""
     rng = np.random.default_rng(11)

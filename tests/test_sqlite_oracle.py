@@ -79,3 +79,19 @@ def test_baseline_join_probe_in_row_function_vs_sqlite(oracle_mod, text, nk):
     if oracle_mod.ref_available():
         buf2, err2 = util.run_oracle(oracle_mod, st, pq, kind="reference")
         assert err2 == 0 and np.array_equal(buf, buf2)
+
+
+@pytest.mark.parametrize("text", util.NON_GROUPED_QUERIES)
+def test_non_grouped_aggregates_vs_sqlite(oracle_mod, text):
+    """Aggregates without GROUP BY (the reference's NonGroupedAggregate) run as the degenerate group-by — zero keys,
+    one keyless entry — and always return one row, NULL / 0 when no row passes the filter."""
+    from hdk_b200.executor import ResultSet
+    tables = util.composite_join_tables()
+    st = util.make_storage(tables, fragment_size={"t": 1201, "dim": 100000, "dim2": 100000})
+    pq = util.plan_sql(st, text)
+    assert pq.qmd.key_count == 0 and pq.qmd.entry_count == 1 and pq.qmd.keyless == 1
+    buf, err = util.run_oracle(oracle_mod, st, pq, kind="port")
+    assert err == 0
+    got = [tuple(r.values()) for r in ResultSet(pq, buf).to_arrow().to_pylist()]
+    assert len(got) == 1
+    util.assert_rows_equal(got, util.sqlite_rows(tables, text, 0), rel=1e-9)

@@ -152,3 +152,11 @@ COMPOSITE_JOIN_QUERIES = [
     ("SELECT dim.attr, t.a, MIN(t.f), MAX(dim.w), AVG(t.x) FROM t JOIN dim ON t.a = dim.a AND t.b = dim.b WHERE dim.w > 100 GROUP BY dim.attr, t.a", 2),
     ("SELECT dim2.g, COUNT(*), SUM(t.f * dim2.u), SUM(t.x) FROM t JOIN dim2 ON t.big = dim2.big GROUP BY dim2.g", 1),
 ]
+
+
+NON_GROUPED_QUERIES = [
+    "SELECT COUNT(*), SUM(x), AVG(f), MIN(x), COUNT(x) FROM t WHERE a < 20",
+    "SELECT SUM(x), MAX(f), COUNT(*) FROM t WHERE a > 1000",                     # no row passes: NULL, NULL, 0
+    "SELECT SUM(f * (1 - f)), MIN(f), MAX(x) FROM t",
+    "SELECT SUM(t.x), COUNT(*) FROM t JOIN dim ON t.a = dim.a AND t.b = dim.b WHERE dim.w > 500",
+]
