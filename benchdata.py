@@ -136,6 +136,11 @@ TPCH_Q1 = ("SELECT l_returnflag, l_linestatus, sum(l_quantity) AS sum_qty, sum(l
 TPCH_Q1_BYTES_PER_ROW = 44
 
 
+TPCH_Q6 = ("SELECT sum(l_extendedprice * l_discount) FROM lineitem WHERE l_shipdate >= DATE '1994-01-01' AND l_shipdate < DATE '1995-01-01' "
+           "AND l_discount >= 0.05 AND l_discount <= 0.07 AND l_quantity < 24")
+TPCH_Q6_BYTES_PER_ROW = 8 + 8 + 8 + 4   # l_extendedprice, l_discount, l_quantity fp64; l_shipdate date32
+
+
 def make_lineitem(storage, device, rows, fragment_rows=FRAGMENT_ROWS, keep_host=False, rank=0):
     d0 = (datetime.date(1992, 1, 2) - datetime.date(1970, 1, 1)).days
     d1 = (datetime.date(1998, 12, 1) - datetime.date(1970, 1, 1)).days

@@ -17,6 +17,7 @@ def _oracle_frs(oracle, st, pq):
 CASES = [
     ("taxi_q1", "taxi", "q1", 1), ("taxi_q2", "taxi", "q2", 1), ("taxi_q3", "taxi", "q3", 2), ("taxi_q4", "taxi", "q4", 3),
     ("c1_int64", "c1", "int", 1), ("c1_fp64", "c1", "fp", 1), ("tpch_q1", "lineitem", None, 2), ("star_join_sum", "star", None, 1),
+    ("tpch_q6", "lineitem", "q6", 0),
 ]
 
 
@@ -37,7 +38,7 @@ def test_static_shape_parity(oracle_mod, name, kind, sub, nk):
         text = benchdata.C1_QUERY if sub == "int" else benchdata.C1_QUERY_F
     elif kind == "lineitem":
         benchdata.make_lineitem(st, dev, 200_003, fragment_rows=50_001, keep_host=True)
-        text = benchdata.TPCH_Q1
+        text = benchdata.TPCH_Q6 if sub == "q6" else benchdata.TPCH_Q1
     elif kind == "c4":
         benchdata.make_c4(st, dev, 200_003, 30_000, fragment_rows=50_001, keep_host=True)
         text = benchdata.C4_QUERY

@@ -90,6 +90,7 @@ def main():
         benchdata.make_lineitem(st, dev, rows)
         ex = Executor(st)
         out.append(time_query(ex, benchdata.TPCH_Q1, benchdata.TPCH_Q1_BYTES_PER_ROW, rows, label="tpch q1 SF100 lineitem"))
+        out.append(time_query(ex, benchdata.TPCH_Q6, benchdata.TPCH_Q6_BYTES_PER_ROW, rows, label="tpch q6 (non-grouped aggregate)"))
         del ex, st
         torch.cuda.empty_cache()
     if "c5" in only:
