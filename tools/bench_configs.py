@@ -65,11 +65,33 @@ def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label="", forc
     return res
 
 
+def cpu_reference(make, text, rows, guess=None, label=""):
+    """The reference's CPU execution shape on a host-resident slice of the same generator (oracle/_ref when present):
+    one kernel per fragment with a private buffer on all host cores + reduce.  Reported beside the GPU number."""
+    from oracle import oracle
+    from tests import util
+    st = ArrowStorage()
+    make(st, rows)
+    pq = util.plan_sql(st, text, **({"max_groups_buffer_entry_count": guess} if guess else {}))
+    kind = "reference" if oracle.ref_available() else "port"
+    threads = os.cpu_count() or 1
+    frs, jt, ic = util.oracle_inputs(oracle, st, pq)
+    oracle.run_query(pq, frs, jt, ic, n_threads=threads, kind=kind)        # warm-up (page faults)
+    t0 = time.perf_counter()
+    _, err = oracle.run_query(pq, frs, jt, ic, n_threads=threads, kind=kind)
+    dt = time.perf_counter() - t0
+    res = {"config": label + " [CPU " + kind + "]", "rows": rows, "ms": round(dt * 1e3, 1), "rows_per_s": rows / dt, "cores": threads, "err": int(err)}
+    print(json.dumps(res), flush=True)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--only", default="c1,tpch,c5,c4")
     ap.add_argument("--force", action="store_true", help="also time the GLOBAL strategy where it is an alternative")
+    ap.add_argument("--cpu", action="store_true", help="also time the reference's CPU path (oracle/_ref) on a host slice of each config")
+    ap.add_argument("--cpu-rows", type=int, default=8_000_000)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     only = args.only.split(",")
@@ -80,6 +102,8 @@ def main():
         ex = Executor(st)
         out.append(time_query(ex, benchdata.C1_QUERY, 12, 10_000_000, reps=20, label="c1 int64 (10M rows, 1K groups)"))
         out.append(time_query(ex, benchdata.C1_QUERY_F, 12, 10_000_000, reps=20, label="c1 fp64"))
+        if args.cpu:
+            cpu_reference(lambda s, n: benchdata.make_c1(s, dev, rows=10_000_000, keep_host=True), benchdata.C1_QUERY, 10_000_000, label="c1 int64")
         if args.force:
             out.append(time_query(ex, benchdata.C1_QUERY, 12, 10_000_000, reps=20, label="c1 int64", force=2))
         del ex, st
@@ -91,6 +115,10 @@ def main():
         ex = Executor(st)
         out.append(time_query(ex, benchdata.TPCH_Q1, benchdata.TPCH_Q1_BYTES_PER_ROW, rows, label="tpch q1 SF100 lineitem"))
         out.append(time_query(ex, benchdata.TPCH_Q6, benchdata.TPCH_Q6_BYTES_PER_ROW, rows, label="tpch q6 (non-grouped aggregate)"))
+        if args.cpu:
+            mk = lambda s, n: benchdata.make_lineitem(s, dev, n, fragment_rows=1_000_000, keep_host=True)  # noqa: E731
+            cpu_reference(mk, benchdata.TPCH_Q1, args.cpu_rows, label="tpch q1")
+            cpu_reference(mk, benchdata.TPCH_Q6, args.cpu_rows, label="tpch q6")
         del ex, st
         torch.cuda.empty_cache()
     if "c5" in only:
@@ -105,6 +133,9 @@ def main():
         out.append(time_query(ex, benchdata.C5_QUERY, benchdata.C5_BYTES_PER_ROW, rows, label="c5 star join 2B x 10M + group-by SUM"))
         if args.force:
             out.append(time_query(ex, benchdata.C5_QUERY, benchdata.C5_BYTES_PER_ROW, rows, label="c5", force=2))
+        if args.cpu:
+            cpu_reference(lambda s, n: benchdata.make_star(s, dev, n, 10_000_000, fragment_rows=1_000_000, keep_host=True), benchdata.C5_QUERY,
+                          args.cpu_rows, label="c5 star join")
         del ex, st
         torch.cuda.empty_cache()
     if "c4" in only:
@@ -115,6 +146,9 @@ def main():
         ex = Executor(st)
         out.append(time_query(ex, benchdata.C4_QUERY, benchdata.C4_BYTES_PER_ROW, rows, reps=3, guess=2 * distinct,
                               label="c4 baseline hash 1B rows / 100M groups"))
+        if args.cpu:
+            cpu_reference(lambda s, n: benchdata.make_c4(s, dev, n, n // 10, fragment_rows=1_000_000, keep_host=True), benchdata.C4_QUERY,
+                          args.cpu_rows, guess=2 * (args.cpu_rows // 10), label="c4 baseline hash")
     return 0
 
 
