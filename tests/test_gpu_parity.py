@@ -123,6 +123,27 @@ def test_query_host_matches_oracle(oracle_mod, L, env, text, nk, kw):
     check_against_oracle(oracle_mod, st, pq, out, nk)
 
 
+@pytest.mark.parametrize("idx", list(range(len(QUERIES))))
+def test_every_query_with_columnar_output(oracle_mod, env, torch, idx):
+    """The reference re-runs its whole SQL suite with --enable-columnar-output (Tests/CMakeLists.txt:155): every query of
+    the list with a columnar group-by buffer, device-resident launch, against the oracle on the same descriptor."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    text, nk, kw = QUERIES[idx]
+    ex = Executor(st, kw.get("cfg"))
+    try:
+        pq = ex.plan(sql.parse(text, st.tables), kw.get("max_groups_buffer_entry_count"), True)
+    except planner.UnsupportedPlan as e:
+        pytest.skip(f"columnar layout not produced for this plan: {e}")
+    assert pq.qmd.output_columnar == 1
+    prep = ex.prepare(pq)
+    ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+
+
 @pytest.mark.parametrize("strategy", [0xB200F001, 0xB200F002, 0xB200F003])
 @pytest.mark.parametrize("text,nk", [(QUERIES[2][0], 1), (QUERIES[3][0], 1), (QUERIES[4][0], 2), (QUERIES[7][0], 1), (QUERIES[8][0], 1)])
 def test_every_accumulation_strategy(oracle_mod, env, torch, strategy, text, nk):
