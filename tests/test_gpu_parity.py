@@ -350,6 +350,30 @@ def test_arrow_import_on_device_matches_host_import(env, L, torch):
     assert L.hdk_b200_materialize_nulls_on_device(buf.data_ptr(), 3, 0, 0, 0, 10, st.data_ptr(), None) != 0
 
 
+def test_group_by_boundaries_and_null_on_gpu(oracle_mod, torch):
+    """GroupByBoundariesAndNull (ArrowBasedExecuteTest.cpp:2845-2866) on the device: keys at INT32_MAX / 127 / 32767 / 2^62
+    with NULL keys, single and composite, buffers byte-identical to the oracle's."""
+    from tests.test_sqlite_oracle import BOUNDARY_QUERIES, boundary_tables
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    st = util.make_storage(boundary_tables(), fragment_size=17)
+    for text in BOUNDARY_QUERIES:
+        ex = Executor(st)
+        pq = ex.plan(sql.parse(text, st.tables))
+        prep = ex.prepare(pq)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0, text
+        obuf, oerr = util.run_oracle(oracle_mod, st, pq)
+        assert oerr == 0
+        if pq.qmd.hash_type == abi.PERFECT_HASH:
+            assert np.array_equal(prep["out"].cpu().numpy(), obuf), text
+        else:
+            nk = pq.plan.n_keys
+            util.assert_rows_equal(util.sort_rows(util.result_columns(oracle_mod, pq, prep["out"].cpu().numpy()), nk),
+                                   util.sort_rows(util.result_columns(oracle_mod, pq, obuf), nk))
+
+
 def test_executor_sql_end_to_end_vs_sqlite(env, torch):
     """hdk.sql() → Arrow, against SQLite like the reference's `c()` comparator."""
     import hdk_b200.hdk as hdkmod

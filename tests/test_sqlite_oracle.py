@@ -95,3 +95,35 @@ def test_non_grouped_aggregates_vs_sqlite(oracle_mod, text):
     got = [tuple(r.values()) for r in ResultSet(pq, buf).to_arrow().to_pylist()]
     assert len(got) == 1
     util.assert_rows_equal(got, util.sqlite_rows(tables, text, 0), rel=1e-9)
+
+
+def boundary_tables():
+    """ArrowBasedExecuteTest.cpp:2845-2866 GroupByBoundariesAndNull: group keys at the top of their type's range
+    together with NULL keys (the NULL bin is max + 1 in 64-bit arithmetic)."""
+    n = 64
+    x = np.arange(n) % 9
+    return {"test": pa.table({
+        "x": x.astype(np.int32),
+        "k32": pa.array(np.where(x == 7, 2147483647, 0).astype(np.int32), mask=(x != 7)),
+        "k8": pa.array(np.where(x == 7, 127, 0).astype(np.int8), mask=(x != 7)),
+        "k16": pa.array(np.where(x % 3 == 0, 32767, -32767).astype(np.int16), mask=(x % 4 == 1)),
+        "k64": pa.array(np.where(x % 2 == 0, 2**62, -2**62), mask=(x == 3)),
+        "v": np.arange(n).astype(np.int64)})}
+
+
+BOUNDARY_QUERIES = ["SELECT k32, COUNT(*) FROM test GROUP BY k32", "SELECT k8, COUNT(*), SUM(v) FROM test GROUP BY k8",
+                    "SELECT k16, COUNT(*), MIN(v) FROM test GROUP BY k16", "SELECT k64, COUNT(*), MAX(v) FROM test GROUP BY k64",
+                    "SELECT k8, k16, COUNT(*) FROM test GROUP BY k8, k16"]
+
+
+@pytest.mark.parametrize("text", BOUNDARY_QUERIES)
+def test_group_by_boundaries_and_null(oracle_mod, text):
+    tables = boundary_tables()
+    st = util.make_storage(tables, fragment_size=17)
+    nk = text.split(" FROM ")[0].count(",") + 1 - sum(text.count(a) for a in ("COUNT(", "SUM(", "MIN(", "MAX("))
+    pq = util.plan_sql(st, text)
+    buf, err = util.run_oracle(oracle_mod, st, pq, kind="port")
+    assert err == 0
+    got = util.sort_rows(util.result_columns(oracle_mod, pq, buf), nk)
+    order = ", ".join(str(i + 1) for i in range(nk))
+    util.assert_rows_equal(got, util.sqlite_rows(tables, text + " ORDER BY " + order, nk))
