@@ -350,6 +350,25 @@ def test_arrow_import_on_device_matches_host_import(env, L, torch):
     assert L.hdk_b200_materialize_nulls_on_device(buf.data_ptr(), 3, 0, 0, 0, 10, st.data_ptr(), None) != 0
 
 
+def test_filter_and_group_by_on_gpu(oracle_mod, torch):
+    """Select.FilterAndGroupBy (ArrowBasedExecuteTest.cpp:2787-2843), the queries inside the supported subset: expression
+    group keys, keys that are not projected, filters on expressions, nullable aggregates — GPU buffer vs the oracle's."""
+    from tests.test_sqlite_oracle import FILTER_GROUP_BY_QUERIES, filter_group_by_tables
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    st = util.make_storage(filter_group_by_tables(), fragment_size=101)
+    for text, nk in FILTER_GROUP_BY_QUERIES:
+        if nk is None:
+            continue
+        ex = Executor(st)
+        pq = ex.plan(sql.parse(text, st.tables))
+        prep = ex.prepare(pq)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0, text
+        check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), pq.plan.n_keys)
+
+
 def test_group_by_boundaries_and_null_on_gpu(oracle_mod, torch):
     """GroupByBoundariesAndNull (ArrowBasedExecuteTest.cpp:2845-2866) on the device: keys at INT32_MAX / 127 / 32767 / 2^62
     with NULL keys, single and composite, buffers byte-identical to the oracle's."""
