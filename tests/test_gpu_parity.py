@@ -123,6 +123,25 @@ def test_query_host_matches_oracle(oracle_mod, L, env, text, nk, kw):
     check_against_oracle(oracle_mod, st, pq, out, nk)
 
 
+@pytest.mark.parametrize("idx", [0, 2, 4, 6, 7, 9, 12, 13, 16])
+def test_queries_with_bigint_count(oracle_mod, env, torch, idx):
+    """Select.GroupByPerfectHash runs twice, the second time with config.exec.group_by.bigint_count (COUNT becomes a
+    64-bit aggregate: wider slots, different compaction): same here, against the oracle on the same descriptor."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    text, nk, kw = QUERIES[idx]
+    cfg = planner.Config(bigint_count=True)
+    ex = Executor(st, cfg)
+    pq = ex.plan(sql.parse(text, st.tables, True), kw.get("max_groups_buffer_entry_count"), kw.get("output_columnar"))
+    assert any(ti.agg == abi.AGG_COUNT and ti.type.width == 8 for ti in pq.infos)
+    prep = ex.prepare(pq)
+    ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+
+
 @pytest.mark.parametrize("idx", list(range(len(QUERIES))))
 def test_every_query_with_columnar_output(oracle_mod, env, torch, idx):
     """The reference re-runs its whole SQL suite with --enable-columnar-output (Tests/CMakeLists.txt:155): every query of
