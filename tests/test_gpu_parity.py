@@ -437,6 +437,9 @@ def test_builder_api_pyhdk_vectors(torch):
     assert r == {"a": [1, 2], "bc": [5, 5], "cmx": [9, 10], "cmn": [1, 2], "cv": [5.0, 6.0]}
     ht1 = h.import_pydict({"a": [1, 2, 3, 4, 5], "b": [5, 4, 3, 2, 1], "x": [1.1, 2.2, 3.3, 4.4, 5.5]}, "ht1")
     ht2 = h.import_pydict({"a": [1, 2, 3, 4, 5], "bb": [1, 2, 3, 4, 5], "y": [5.5, 4.4, 3.3, 2.2, 1.1]}, "ht2")
+    # python/tests/test_pyhdk_calcite_json.py:47-168 (filter a > 1 AND a < 3, COUNT(*) without GROUP BY → 1)
+    ht3 = h.import_pydict({"a": [1, 2, 3], "b": [10, 20, 30]}, "test3")
+    assert ht3.filter("a > 1 AND a < 3").agg([], n="count", sb="sum(b)").run().to_arrow().to_pydict() == {"n": [1], "sb": [20]}
     r = ht1.join(ht2, "a").agg("b", sy="sum(y)", n="count").sort("b").run().to_arrow().to_pydict()
     assert r["b"] == [1, 2, 3, 4, 5] and r["n"] == [1] * 5
     assert np.allclose(r["sy"], [1.1, 2.2, 3.3, 4.4, 5.5])
