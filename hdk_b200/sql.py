@@ -26,7 +26,9 @@ _TOKEN = re.compile(r"""
 
 _KEYWORDS = {"select", "from", "where", "group", "by", "order", "limit", "join", "inner", "on", "and", "or",
              "not", "as", "is", "null", "asc", "desc", "extract", "year", "cast", "date", "timestamp",
-             "between", "count", "sum", "min", "max", "avg"}
+             "between", "count", "sum", "min", "max", "avg",
+             # recognised only to be rejected: they must never be taken for a table alias or a column name
+             "left", "right", "full", "outer", "cross", "natural", "having", "distinct", "over", "union", "using"}
 
 
 def _tokenize(s: str):

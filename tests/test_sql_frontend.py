@@ -1,0 +1,59 @@
+"""The SQL subset of the façade (hdk_b200/sql.py): what parses into which ExecutionUnit, and what is rejected loudly
+(never silently approximated)."""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from hdk_b200 import abi, ir, planner, sql
+from tests import util
+
+
+@pytest.fixture(scope="module")
+def st():
+    n = 50
+    t = pa.table({"a": np.arange(n, dtype=np.int32) % 5, "b": np.arange(n, dtype=np.int16) % 3, "x": np.arange(n, dtype=np.int64),
+                  "f": np.linspace(0, 1, n), "ts": pa.array((np.arange(n) * 86400000).astype("datetime64[ms]")), "s": pa.array(["u", "v"] * (n // 2))})
+    d = pa.table({"a": np.arange(5, dtype=np.int32), "b": np.zeros(5, dtype=np.int16), "w": np.arange(5, dtype=np.int64)})
+    return util.make_storage({"t": t, "d": d}, fragment_size=20)
+
+
+def test_select_aliases_group_by_order_limit(st):
+    u = sql.parse("SELECT a AS k, EXTRACT(YEAR FROM ts) AS y, COUNT(*) AS n, AVG(f) FROM t WHERE x >= 3 AND f < 0.9 "
+                  "GROUP BY k, y ORDER BY n DESC, k LIMIT 7", st.tables)
+    assert u.table == "t" and u.target_names == ["k", "y", "n", "EXPR$3"] and u.limit == 7
+    assert len(u.groupby_exprs) == 2 and isinstance(u.groupby_exprs[1], ir.ExtractYear if hasattr(ir, "ExtractYear") else object)
+    assert u.order_by == [(2, True), (0, False)]
+    assert len(u.quals) >= 1
+
+
+def test_join_conditions(st):
+    u = sql.parse("SELECT d.w, SUM(t.x) FROM t JOIN d ON t.a = d.a GROUP BY d.w", st.tables)
+    assert len(u.joins) == 1 and u.joins[0].inner_table == "d" and u.joins[0].inner_key_column == "a" and not u.joins[0].more_keys
+    u = sql.parse("SELECT d.w, SUM(t.x) FROM t INNER JOIN d ON d.a = t.a AND t.b = d.b GROUP BY d.w", st.tables)
+    assert u.joins[0].inner_key_columns == ["a", "b"] and [k.column for k in u.joins[0].outer_keys] == ["a", "b"]
+    pq = util.plan_sql(st, "SELECT d.w, SUM(t.x) FROM t JOIN d ON t.a = d.a AND t.b = d.b GROUP BY d.w")
+    assert pq.plan.joins[0].n_key_exprs == 2 and pq.plan.joins[0].key_width == 4
+    pq = util.plan_sql(st, "SELECT d.w, SUM(t.x) FROM t JOIN d ON t.a = d.a GROUP BY d.w")
+    assert pq.plan.joins[0].n_key_exprs == 0                                   # perfect table
+    pq = util.plan_sql(st, "SELECT d.w, SUM(t.x) FROM t JOIN d ON t.a = d.a GROUP BY d.w", cfg=planner.Config(max_perfect_join_entries=2))
+    assert pq.plan.joins[0].n_key_exprs == 1                                   # range too wide for the configured limit
+
+
+def test_non_grouped_aggregate_plans_as_one_keyless_entry(st):
+    pq = util.plan_sql(st, "SELECT COUNT(*), SUM(x), MIN(f) FROM t WHERE a = 2")
+    assert pq.plan.n_keys == 0 and pq.qmd.entry_count == 1 and pq.qmd.keyless == 1 and pq.qmd.hash_type == abi.PERFECT_HASH
+
+
+@pytest.mark.parametrize("text", [
+    "SELECT a, COUNT(*) FROM t GROUP BY a HAVING COUNT(*) > 1",          # HAVING
+    "SELECT a, COUNT(DISTINCT b) FROM t GROUP BY a",                    # count distinct
+    "SELECT a FROM t",                                                  # projection without aggregation
+    "SELECT a, x FROM t GROUP BY a",                                    # non-key, non-aggregate target
+    "SELECT f, COUNT(*) FROM t GROUP BY f",                             # floating-point group key
+    "SELECT d.w, COUNT(*) FROM t LEFT JOIN d ON t.a = d.a GROUP BY d.w",  # outer join
+    "SELECT d.w, COUNT(*) FROM t JOIN d ON t.a < d.a GROUP BY d.w",     # non-equi join
+    "SELECT a, SUM(x) OVER (PARTITION BY a) FROM t",                    # window function
+])
+def test_unsupported_sql_is_rejected(st, text):
+    with pytest.raises((planner.UnsupportedPlan, SyntaxError, KeyError, ValueError)):
+        util.plan_sql(st, text)
