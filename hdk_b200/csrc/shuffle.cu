@@ -222,9 +222,12 @@ __global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __g
     for (int r = 0; r < kShufRowsPerThread; ++r) {
       const uint64_t pos = row0 + uint64_t(r) * kShufThreads + tid;      // coalesced: consecutive threads, consecutive rows
       part[r] = pos < rows ? (a.direct ? row_partition_direct(a, kbase, pos) : row_partition(a, cols, pos, vals)) : -1;
-      // warp-aggregated histogram update
-      const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
-      if (part[r] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[part[r]], (unsigned)__popc(peers));
+      if (a.n_partitions > 32) {   // many partitions: lanes rarely meet, MATCH.ANY would cost one round per distinct value
+        if (part[r] >= 0) atomicAdd(&hist[part[r]], 1u);
+      } else {                     // warp-aggregated histogram update
+        const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+        if (part[r] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[part[r]], (unsigned)__popc(peers));
+      }
     }
     if (!kScatter) continue;
     __syncthreads();
@@ -330,6 +333,164 @@ static void detect_direct_keys(const DPlan& p, ShuffleArgs* a) {
   a->direct = 1;
 }
 
+// ---- large-tile scatter ----------------------------------------------------------------------------------------------
+// Up to 1024 partitions: a CTA regroups a tile of up to 8192 rows by partition in shared memory (column-major staging
+// + the partition of every staged position), reserves one run per partition and tile with a single global atomic, and
+// copies the staged tile out position by position — consecutive threads write consecutive elements of a partition's run
+// (hundreds of bytes even with > 100 partitions), where the direct scatter writes a handful of elements per destination.
+constexpr int kBigThreads = 512;
+constexpr int kBigMaxRpt = 16;
+
+struct BigScatterArgs {
+  ScatterToArgs s;
+  uint32_t tile_rows, rpt;                       // rows per tile (multiple of kBigThreads), rows per thread
+  uint32_t off_part, off_hist, off_run, off_base, off_prefix;   // dynamic shared-memory map (staging at 0)
+  uint32_t stage_off[HDK_B200_MAX_COLS];
+};
+
+__global__ void __launch_bounds__(kBigThreads, 1) scatter_big_tile_kernel(const __grid_constant__ BigScatterArgs ba) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const ShuffleArgs& a = ba.s.base;
+  const DPlan& p = a.plan;
+  uint16_t* part_of_pos = reinterpret_cast<uint16_t*>(sm + ba.off_part);
+  unsigned int* hist = reinterpret_cast<unsigned int*>(sm + ba.off_hist);
+  unsigned int* run_start = reinterpret_cast<unsigned int*>(sm + ba.off_run);
+  unsigned long long* base = reinterpret_cast<unsigned long long*>(sm + ba.off_base);
+  uint32_t* frag_tile_prefix = reinterpret_cast<uint32_t*>(sm + ba.off_prefix);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t P = a.n_partitions;
+  const bool many = P > 32;
+  if (tid == 0) {
+    uint32_t acc = 0;
+    frag_tile_prefix[0] = 0;
+    for (uint32_t f = 0; f < a.num_fragments; ++f) {
+      const int64_t rows = a.num_rows[f];
+      acc += rows > 0 ? uint32_t((rows + ba.tile_rows - 1) / ba.tile_rows) : 0;
+      frag_tile_prefix[f + 1] = acc;
+    }
+  }
+  __syncthreads();
+  const uint32_t total_tiles = frag_tile_prefix[a.num_fragments];
+  V vals[HDK_B200_MAX_EXPRS];
+  for (uint64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t frag = 0;
+    while (frag + 1 < a.num_fragments && frag_tile_prefix[frag + 1] <= tile) ++frag;
+    const uint64_t row0 = (tile - frag_tile_prefix[frag]) * uint64_t(ba.tile_rows);
+    const int8_t* const* cols = a.col_buffers + size_t(frag) * p.n_cols;
+    const uint64_t rows = uint64_t(a.num_rows[frag]);
+    const int8_t* kbase[HDK_B200_MAX_KEYS];
+    if (a.direct) {
+#pragma unroll
+      for (int k = 0; k < HDK_B200_MAX_KEYS; ++k) kbase[k] = k < p.n_keys ? cols[a.key_col[k]] : nullptr;
+    }
+    for (uint32_t i = tid; i < P; i += kBigThreads) hist[i] = 0;
+    __syncthreads();
+    int part[kBigMaxRpt];
+#pragma unroll
+    for (int r = 0; r < kBigMaxRpt; ++r) {
+      part[r] = -1;
+      if (uint32_t(r) < ba.rpt) {
+        const uint64_t pos = row0 + uint64_t(r) * kBigThreads + tid;
+        if (pos < rows) part[r] = a.direct ? row_partition_direct(a, kbase, pos) : row_partition(a, cols, pos, vals);
+        if (many) {   // many partitions: lanes rarely meet, MATCH.ANY would cost one round per distinct value
+          if (part[r] >= 0) atomicAdd(&hist[part[r]], 1u);
+        } else {
+          const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+          if (part[r] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[part[r]], (unsigned)__popc(peers));
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of the histogram: lane l owns a contiguous chunk of ceil(P / 32) partitions
+      const uint32_t chunk = (P + 31) / 32, lo = min(uint32_t(lane) * chunk, P), hi = min(lo + chunk, P);
+      unsigned int sum = 0;
+      for (uint32_t i = lo; i < hi; ++i) sum += hist[i];
+      unsigned int incl = sum;
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      unsigned int run = incl - sum;
+      for (uint32_t i = lo; i < hi; ++i) { run_start[i] = run; run += hist[i]; }
+      if (lane == 31) run_start[P] = incl;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < P; i += kBigThreads) {
+      base[i] = hist[i] ? ba.s.dest_offsets[i] + atomicAdd(a.cursors + i, (unsigned long long)hist[i]) : 0;
+      hist[i] = 0;   // becomes the running position inside the run
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kBigMaxRpt; ++r) {
+      if (uint32_t(r) < ba.rpt) {
+        uint32_t lp = 0;
+        if (many) {
+          if (part[r] >= 0) lp = run_start[part[r]] + atomicAdd(&hist[part[r]], 1u);
+        } else {
+          const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+          if (part[r] >= 0) {
+            const int leader = __ffs(peers) - 1;
+            unsigned int start = 0;
+            if (lane == leader) start = atomicAdd(&hist[part[r]], (unsigned)__popc(peers));
+            start = __shfl_sync(peers, start, leader);
+            lp = run_start[part[r]] + start + __popc(peers & ((1u << lane) - 1u));
+          }
+        }
+        if (part[r] >= 0) {
+          const uint64_t pos = row0 + uint64_t(r) * kBigThreads + tid;
+          part_of_pos[lp] = uint16_t(part[r]);
+          for (int c = 0; c < p.n_cols; ++c) {
+            const int w = p.col_width[c];
+            copy_elem(sm + ba.stage_off[c] + size_t(lp) * w, cols[c] + pos * w, w);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t n_tile = run_start[P];
+    for (int c = 0; c < p.n_cols; ++c) {
+      const int w = p.col_width[c];
+      const uint8_t* sc = sm + ba.stage_off[c];
+      for (uint32_t i = tid; i < n_tile; i += kBigThreads) {
+        const uint32_t pr = part_of_pos[i];
+        int8_t* out = ba.s.dest_cols[size_t(pr) * p.n_cols + c] + (base[pr] + (i - run_start[pr])) * w;
+        copy_elem(out, sc + size_t(i) * w, w);
+      }
+    }
+    __syncthreads();
+  }
+  __threadfence_system();
+}
+
+// launch the large-tile scatter when its shared-memory plan fits; false = use the small-tile kernels
+static bool launch_big_scatter(const ScatterToArgs& sa, const Lowered& lw, uint32_t n_partitions, cudaStream_t st, int* rc) {
+  *rc = HDK_B200_OK;
+  const size_t row_bytes = std::max<size_t>(lw.stage_row_bytes, 1);
+  int dev = 0, max_smem = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+  const size_t fixed = size_t(n_partitions) * (4 + 4 + 8) + 64 + (size_t(sa.base.num_fragments) + 1) * 4 + 64;
+  uint32_t rpt = kBigMaxRpt;
+  while (rpt >= 4 && size_t(rpt) * kBigThreads * (row_bytes + 2) + fixed + 256 > size_t(max_smem)) --rpt;
+  if (rpt < 4 || lw.plan.n_cols > HDK_B200_MAX_COLS) return false;
+  BigScatterArgs ba{};
+  ba.s = sa;
+  ba.rpt = rpt;
+  ba.tile_rows = rpt * kBigThreads;
+  size_t off = 0;
+  for (int c = 0; c < lw.plan.n_cols; ++c) { ba.stage_off[c] = uint32_t(off); off += size_t(ba.tile_rows) * lw.plan.col_width[c]; off = (off + 15) & ~size_t(15); }
+  ba.off_part = uint32_t(off); off += size_t(ba.tile_rows) * 2; off = (off + 15) & ~size_t(15);
+  ba.off_hist = uint32_t(off); off += size_t(n_partitions) * 4; off = (off + 15) & ~size_t(15);
+  ba.off_run = uint32_t(off); off += (size_t(n_partitions) + 1) * 4; off = (off + 15) & ~size_t(15);
+  ba.off_base = uint32_t(off); off += size_t(n_partitions) * 8; off = (off + 15) & ~size_t(15);
+  ba.off_prefix = uint32_t(off); off += (size_t(sa.base.num_fragments) + 1) * 4;
+  if (off > size_t(max_smem)) return false;
+  if (cudaFuncSetAttribute(scatter_big_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(off)) != cudaSuccess) { cudaGetLastError(); return false; }
+  scatter_big_tile_kernel<<<sm_count(), kBigThreads, off, st>>>(ba);
+  ++g_launch_count;
+  if (cudaGetLastError() != cudaSuccess) { set_error("large-tile scatter launch failed"); *rc = HDK_B200_E_CUDA; }
+  return true;
+}
+
 // a plan without layout information: lower only what the shuffle needs
 static int lower_for_shuffle(const hdk_b200_plan* plan, Lowered* lw) {
   hdk_b200_qmd q{};
@@ -426,6 +587,11 @@ int hdk_b200_region_scatter_to(const hdk_b200_plan* plan, const hdk_b200_qmd* qm
   sa.dest_offsets = dest_offsets;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   HB_CUDA(cudaMemsetAsync(cursors, 0, sizeof(uint64_t) * n_regions, st));
+  const char* big_env = getenv("HDK_B200_SCATTER_BIG");   // tuning hook: 0 = never use the large-tile kernel
+  if (n_regions >= 4 && !(big_env && big_env[0] == '0')) {
+    int rc = HDK_B200_OK;
+    if (launch_big_scatter(sa, lw, n_regions, st, &rc)) return rc;
+  }
   const size_t staging = size_t(kTileRows) * lw.stage_row_bytes;
   if (n_regions <= kStagedMaxPartitions && staging <= 96 * 1024) {
     HB_CUDA(cudaFuncSetAttribute(shuffle_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(staging)));
@@ -456,6 +622,11 @@ int hdk_b200_shuffle_scatter_to(const hdk_b200_plan* plan, const hdk_b200_kernel
   detect_direct_keys(lw.plan, &sa.base);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   HB_CUDA(cudaMemsetAsync(cursors, 0, sizeof(uint64_t) * n_partitions, st));
+  const char* big_env = getenv("HDK_B200_SCATTER_BIG");   // tuning hook: 0 = never, 1 = also for few partitions
+  if ((n_partitions > kStagedMaxPartitions || (big_env && big_env[0] == '1')) && !(big_env && big_env[0] == '0')) {
+    int rc = HDK_B200_OK;
+    if (launch_big_scatter(sa, lw, n_partitions, st, &rc)) return rc;
+  }
   const size_t staging = size_t(kTileRows) * lw.stage_row_bytes;
   bool staged = n_partitions >= 4 && n_partitions <= kStagedMaxPartitions && staging <= 96 * 1024;
   if (const char* env = getenv("HDK_B200_SCATTER_STAGED")) staged = env[0] == '1' && n_partitions <= kStagedMaxPartitions && staging <= 96 * 1024;   // tuning hook
