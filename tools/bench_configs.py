@@ -67,7 +67,9 @@ def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label="", forc
 
 def cpu_reference(make, text, rows, guess=None, label=""):
     """The reference's CPU execution shape on a host-resident slice of the same generator (oracle/_ref when present):
-    one kernel per fragment with a private buffer on all host cores + reduce.  Reported beside the GPU number."""
+    one kernel per fragment with a private buffer on all host cores + reduce.  Reported beside the GPU number.
+    (Same role as bench.py's cpu_baseline leg: the oracle is the thing timed as the CPU baseline, never part of the
+    GPU path being measured.)"""
     from oracle import oracle
     from tests import util
     st = ArrowStorage()
