@@ -24,7 +24,7 @@ ERR_OVERFLOW_OR_UNDERFLOW = 7
 INT, FP = 0, 1
 
 (OP_COL, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_CAST, OP_EXTRACT_YEAR, OP_LT, OP_LE, OP_GT, OP_GE,
- OP_EQ, OP_NE, OP_AND, OP_OR, OP_NOT, OP_IS_NULL, OP_UMINUS) = range(19)
+ OP_EQ, OP_NE, OP_AND, OP_OR, OP_NOT, OP_IS_NULL, OP_UMINUS, OP_CASE) = range(20)
 
 AGG_NONE, AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX, AGG_AVG = range(6)
 PERFECT_HASH, BASELINE_HASH = 0, 1
@@ -47,7 +47,7 @@ class Type(C.Structure):
 
 class Expr(C.Structure):
     _fields_ = [("op", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("aux", C.c_int32), ("type", Type),
-                ("pad", C.c_int32), ("ival", C.c_int64), ("fval", C.c_double)]
+                ("guard", C.c_int32), ("ival", C.c_int64), ("fval", C.c_double)]
 
 
 class Target(C.Structure):

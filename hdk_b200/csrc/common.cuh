@@ -36,7 +36,7 @@ struct DExpr {          // 16 bytes
   int8_t a, b;          // operand nodes (OP_COL: table, column)
   uint8_t aux;
   uint8_t kind, width, nullable;  // result type
-  uint8_t pad;
+  uint8_t guard;        // 0, or 1 + the node that must be true for this one to be evaluated (inside a CASE arm)
   union {
     int64_t i;
     double f;

@@ -47,6 +47,7 @@ __device__ __forceinline__ V eval_node(const DPlan& p, const DExpr& e, const V* 
                                        LoadOuter&& load_outer, LoadInner&& load_inner) {
   V r;
   r.i = 0;
+  if (e.guard && !(vals[e.guard - 1].i > 0)) return r;  // inside a CASE arm this row does not take (QE/CaseIR.cpp:66-93)
   switch (e.op) {
     case HDK_B200_OP_COL: {
       // fixed_width_{int,float,double,small_date}_decode (QE/DecodersImpl.h:31-161)
@@ -180,6 +181,9 @@ __device__ __forceinline__ V eval_node(const DPlan& p, const DExpr& e, const V* 
       r.i = v_is_null(t, vals[e.a]);
       break;
     }
+    case HDK_B200_OP_CASE:  // toBool(when) ? then : else, QE/CaseIR.cpp:68-111; both arms already have the node's type
+      r = vals[e.a].i > 0 ? vals[e.b] : vals[int(e.imm.i)];
+      break;
     default: err = 1000; break;
   }
   return r;

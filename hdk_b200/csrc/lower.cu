@@ -100,6 +100,8 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
     if ((unary || binary) && (e.a < 0 || e.a >= i)) { set_error("expr %d: operand a=%d not topologically earlier", i, e.a); return HDK_B200_E_INVALID; }
     if (binary && (e.b < 0 || e.b >= i)) { set_error("expr %d: operand b=%d not topologically earlier", i, e.b); return HDK_B200_E_INVALID; }
     if (e.type.width != 1 && e.type.width != 2 && e.type.width != 4 && e.type.width != 8) { set_error("expr %d: bad width", i); return HDK_B200_E_INVALID; }
+    if (e.guard < 0 || e.guard > i) { set_error("expr %d: guard %d not topologically earlier", i, e.guard); return HDK_B200_E_INVALID; }
+    d.guard = uint8_t(e.guard);
     switch (e.op) {
       case HDK_B200_OP_COL: {
         if (e.a < 0 || e.a > plan->n_joins || e.b < 0 || e.b >= HDK_B200_MAX_COLS) { set_error("expr %d: bad column ref", i); return HDK_B200_E_INVALID; }
@@ -119,6 +121,14 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
         break;
       case HDK_B200_OP_EXTRACT_YEAR:
         d.imm.i = e.ival > 0 ? e.ival : 1;
+        break;
+      case HDK_B200_OP_CASE:
+        if (e.a < 0 || e.a >= i || e.b < 0 || e.b >= i || e.ival < 0 || e.ival >= i) { set_error("expr %d: CASE operand not topologically earlier", i); return HDK_B200_E_INVALID; }
+        for (int arm : {e.b, int(e.ival)})
+          if (plan->exprs[arm].type.kind != e.type.kind || plan->exprs[arm].type.width != e.type.width) {
+            set_error("expr %d: CASE arm %d does not have the node's type", i, arm); return HDK_B200_E_INVALID;
+          }
+        d.imm.i = e.ival;
         break;
       default:
         if (!(unary || binary)) { set_error("expr %d: unknown op %d", i, e.op); return HDK_B200_E_UNSUPPORTED; }
@@ -331,8 +341,8 @@ uint64_t plan_signature(const DPlan& p) {
   mix(p.n_exprs); mix(p.n_filters); mix(p.n_keys); mix(p.n_joins); mix(p.n_acc); mix(p.n_cols); mix(p.hash_type);
   for (int i = 0; i < p.n_exprs; ++i) {
     const DExpr& e = p.exprs[i];
-    mix(e.op); mix(uint8_t(e.a)); mix(uint8_t(e.b)); mix(e.aux); mix(e.kind); mix(e.width); mix(e.nullable);
-    if (e.op == HDK_B200_OP_COL || e.op == HDK_B200_OP_EXTRACT_YEAR) mix(uint64_t(e.imm.i));
+    mix(e.op); mix(uint8_t(e.a)); mix(uint8_t(e.b)); mix(e.aux); mix(e.kind); mix(e.width); mix(e.nullable); mix(e.guard);
+    if (e.op == HDK_B200_OP_COL || e.op == HDK_B200_OP_EXTRACT_YEAR || e.op == HDK_B200_OP_CASE) mix(uint64_t(e.imm.i));
   }
   for (int i = 0; i < p.n_filters; ++i) mix(uint8_t(p.filters[i]));
   for (int i = 0; i < p.n_keys; ++i) { mix(p.keys[i].expr); mix(p.keys[i].has_nulls); mix(p.keys[i].width); }
@@ -352,8 +362,8 @@ static int dump_shape(const DPlan& p, char* out, size_t cap) {
   add("%d, %d, %d, %d, %d, %d, 0u, %d,\n  {", p.n_exprs, p.n_filters, p.n_keys, p.n_joins, p.n_acc, p.n_cols, p.hash_type);
   for (int i = 0; i < p.n_exprs; ++i) {
     const DExpr& e = p.exprs[i];
-    const long long imm = (e.op == HDK_B200_OP_COL || e.op == HDK_B200_OP_EXTRACT_YEAR) ? (long long)e.imm.i : 0;
-    add("{%d, %d, %d, %d, %d, %d, %d, 0, {%lldLL}}%s", e.op, e.a, e.b, e.aux, e.kind, e.width, e.nullable, imm, i + 1 < p.n_exprs ? ", " : "");
+    const long long imm = (e.op == HDK_B200_OP_COL || e.op == HDK_B200_OP_EXTRACT_YEAR || e.op == HDK_B200_OP_CASE) ? (long long)e.imm.i : 0;
+    add("{%d, %d, %d, %d, %d, %d, %d, %d, {%lldLL}}%s", e.op, e.a, e.b, e.aux, e.kind, e.width, e.nullable, e.guard, imm, i + 1 < p.n_exprs ? ", " : "");
   }
   s += "},\n  {";
   for (int i = 0; i < HDK_B200_MAX_FILTERS; ++i) add("%d%s", i < p.n_filters ? p.filters[i] : 0, i + 1 < HDK_B200_MAX_FILTERS ? ", " : "");

@@ -114,7 +114,6 @@ __global__ void reduce_perfect_kernel(const __grid_constant__ ReduceArgs a) {
 
 __global__ void reduce_baseline_kernel(const __grid_constant__ ReduceArgs a) {
   const DLayout& L = a.layout;
-  DLayout TL = L;  // `that` has the same row layout but its own entry count (columnar offsets differ)
   const uint64_t TE = a.that_entry_count;
   const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t e = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; e < TE; e += step) {
@@ -156,7 +155,6 @@ __global__ void reduce_baseline_kernel(const __grid_constant__ ReduceArgs a) {
       reduce_slot(sl, slot_ptr(L, a.this_buf, uint64_t(dst), sl), src);
     }
   }
-  (void)TL;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -153,6 +153,17 @@ class IsNull(Expr):
 
 
 @dataclass(frozen=True)
+class Case(Expr):
+    """CASE WHEN c1 THEN v1 [WHEN c2 THEN v2 …] ELSE ve END (hdk::ir::CaseExpr).  Every value already has `type`."""
+    arms: tuple         # ((when, then), …)
+    else_: Expr
+    type: SqlType
+
+    def children(self):
+        return tuple(x for arm in self.arms for x in arm) + (self.else_,)
+
+
+@dataclass(frozen=True)
 class AggExpr(Expr):
     agg: str            # count sum min max avg
     arg: Optional[Expr]
@@ -184,6 +195,33 @@ def cast_to(e: Expr, t: SqlType) -> Expr:
             return Const(None, t)
         return Const(float(v) if t.is_fp else int(v), t.with_nullable(False))
     return Cast(e, t.with_nullable(e.type.nullable))
+
+
+def make_case(arms, else_: Optional[Expr]) -> Expr:
+    """The arms unify to their common numeric type; no ELSE means ELSE NULL, and then (or with any nullable arm) the
+    result is nullable — what the reference's CASE normalisation produces (omniscidb/IR/Expr.cpp, CaseExpr typing)."""
+    values = [v for _, v in arms] + ([else_] if else_ is not None else [])
+    typed = [v for v in values if not (isinstance(v, Const) and v.value is None)]
+    if not typed:
+        raise NotImplementedError("CASE with only NULL values")
+    for c, _ in arms:
+        if c.type.kind != "bool":
+            raise NotImplementedError("CASE condition must be boolean")
+    t = typed[0].type
+    if all(v.type.kind == "int" or v.type.is_fp for v in typed):
+        for v in typed[1:]:
+            t = common_numeric_type(t, v.type)
+    elif any((v.type.kind, v.type.width, getattr(v.type, "unit", 0)) != (t.kind, t.width, getattr(t, "unit", 0)) for v in typed) \
+            or t.kind in ("dict", "bool"):
+        raise NotImplementedError("CASE over non-numeric values of different types")
+    t = t.with_nullable(len(typed) < len(values) or else_ is None or any(v.type.nullable for v in typed))
+
+    def conv(v):
+        if isinstance(v, Const) and v.value is None:
+            return Const(None, t)
+        v = cast_to(v, t)
+        return v
+    return Case(tuple((c, conv(v)) for c, v in arms), conv(else_) if else_ is not None else Const(None, t), t)
 
 
 def make_binop(op: str, lhs: Expr, rhs: Expr) -> Expr:
@@ -292,6 +330,28 @@ def expr_range(e: Expr, col_stats) -> Range:
             c = [a.lo * b.lo, a.lo * b.hi, a.hi * b.lo, a.hi * b.hi]
             return Range(kind, min(c), max(c), hn)
         return Range("invalid")
+    if isinstance(e, Case):
+        # the union of the arms' ranges; a NULL arm only adds has_nulls (getExpressionRange(CaseExpr), ExpressionRange.cpp)
+        out = None
+        for v in [v for _, v in e.arms] + [e.else_]:
+            if isinstance(v, Const) and v.value is None:
+                r = None
+            else:
+                r = expr_range(v, col_stats)
+                if r.kind == "invalid":
+                    return r
+            if r is None:
+                if out is not None:
+                    out.has_nulls = True
+                else:
+                    out = Range("null", has_nulls=True)
+            elif out is None or out.kind == "null":
+                out = Range(r.kind, r.lo, r.hi, r.has_nulls or out is not None)
+            else:
+                if out.kind != r.kind:
+                    return Range("invalid")
+                out = Range(r.kind, min(out.lo, r.lo), max(out.hi, r.hi), out.has_nulls or r.has_nulls)
+        return out if out is not None and out.kind != "null" else Range("invalid")
     return Range("invalid")
 
 

@@ -378,18 +378,39 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
     inner_columns: List[List[str]] = [[] for _ in unit.joins]
     node_of = {}
 
-    def emit(op, a=0, b=0, aux=0, t=None, ival=0, fval=0.0):
+    def emit(op, a=0, b=0, aux=0, t=None, ival=0, fval=0.0, guard=0):
         n = p.n_exprs
         if n >= abi.MAX_EXPRS:
             raise UnsupportedPlan("expression too large")
         e = p.exprs[n]
-        e.op, e.a, e.b, e.aux, e.type, e.ival, e.fval = op, a, b, aux, t.abi(), int(ival), float(fval)
+        e.op, e.a, e.b, e.aux, e.type, e.ival, e.fval, e.guard = op, a, b, aux, t.abi(), int(ival), float(fval), guard
         p.n_exprs = n + 1
         return n
 
-    def lower(e: ir.Expr) -> int:
-        if e in node_of:
-            return node_of[e]
+    raises_memo = {}
+
+    def can_raise(e: ir.Expr) -> bool:
+        """Does evaluating e possibly raise a row error (division by zero, checked integer overflow)?"""
+        if e not in raises_memo:
+            own = isinstance(e, ir.BinOp) and (e.op == "/" or (e.overflow_check and not e.type.is_fp))
+            raises_memo[e] = own or any(can_raise(c) for c in e.children())
+        return raises_memo[e]
+
+    BOOL_NN, BOOL_N = ir.SqlType("bool", 1, False), ir.SqlType("bool", 1, True)
+
+    def both(g: Optional[int], c: int) -> int:
+        return c if g is None else emit(abi.OP_AND, g, c, t=BOOL_N)
+
+    def lower(e: ir.Expr, guard: Optional[int] = None) -> int:
+        """guard: the node that is true for the rows where the reference would execute e at all (the CASE arm it sits
+        in, QE/CaseIR.cpp:66-93).  Only nodes that can raise carry it — everything else is pure and evaluated for every
+        row — so a sub-expression shared between an arm and the rest of the query is one node unless it can raise."""
+        if not can_raise(e):
+            guard = None
+        memo_key = (e, guard)
+        if memo_key in node_of:
+            return node_of[memo_key]
+        g = 0 if guard is None else guard + 1
         if isinstance(e, ir.ColumnRef):
             if e.table == 0:
                 if e.column not in columns:
@@ -402,39 +423,59 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
                 idx = cl.index(e.column)
             n = emit(abi.OP_COL, e.table, idx, 1 if e.type.date_in_days else 0, e.type, ival=e.phys_width)
         elif isinstance(e, ir.Const):
-            if e.value is None:
-                raise UnsupportedPlan("NULL literal")
-            n = emit(abi.OP_CONST, t=e.type.with_nullable(False),
-                     ival=0 if e.type.is_fp else int(e.value), fval=float(e.value))
+            if e.value is None:       # the NULL arm of a CASE: the type's sentinel
+                t = e.type.with_nullable(True)
+                n = emit(abi.OP_CONST, t=t, ival=0 if t.is_fp else abi.int_null(t.width),
+                         fval=abi.fp_null(t.width) if t.is_fp else 0.0)
+            else:
+                n = emit(abi.OP_CONST, t=e.type.with_nullable(False),
+                         ival=0 if e.type.is_fp else int(e.value), fval=float(e.value))
         elif isinstance(e, ir.BinOp):
-            a, b = lower(e.lhs), lower(e.rhs)
+            a, b = lower(e.lhs, guard), lower(e.rhs, guard)
             op = {"+": abi.OP_ADD, "-": abi.OP_SUB, "*": abi.OP_MUL, "/": abi.OP_DIV}[e.op]
-            n = emit(op, a, b, 1 if (e.overflow_check and not e.type.is_fp) else 0, e.type)
+            n = emit(op, a, b, 1 if (e.overflow_check and not e.type.is_fp) else 0, e.type, guard=g)
         elif isinstance(e, ir.UMinus):
-            n = emit(abi.OP_UMINUS, lower(e.arg), t=e.type)
+            n = emit(abi.OP_UMINUS, lower(e.arg, guard), t=e.type)
         elif isinstance(e, ir.Cast):
-            n = emit(abi.OP_CAST, lower(e.arg), t=e.type)
+            n = emit(abi.OP_CAST, lower(e.arg, guard), t=e.type)
         elif isinstance(e, ir.ExtractYear):
             at = e.arg.type
             units = at.unit if at.kind == "timestamp" else 1
-            n = emit(abi.OP_EXTRACT_YEAR, lower(e.arg), t=e.type.with_nullable(at.nullable), ival=units)
+            n = emit(abi.OP_EXTRACT_YEAR, lower(e.arg, guard), t=e.type.with_nullable(at.nullable), ival=units)
+        elif isinstance(e, ir.Case):
+            # WHEN i is reached when no earlier WHEN was true; THEN i additionally needs WHEN i; the arms nest from the
+            # last one outwards: CASE(c1, v1, CASE(c2, v2, else))
+            reach, conds, thens = guard, [], []
+            pieces = [x for arm in e.arms for x in arm] + [e.else_]
+            for i, (c, v) in enumerate(e.arms):
+                cn = lower(c, reach)
+                conds.append(cn)
+                thens.append(lower(v, both(reach, cn) if can_raise(v) else None))
+                if any(can_raise(x) for x in pieces[2 * i + 2:]):      # what follows needs "no WHEN so far was true"
+                    nt = emit(abi.OP_NOT, cn, t=c.type)
+                    if c.type.nullable:
+                        nt = emit(abi.OP_OR, emit(abi.OP_IS_NULL, cn, t=BOOL_NN), nt, t=BOOL_NN)
+                    reach = both(reach, nt)
+            n = lower(e.else_, reach)
+            for cn, tn in reversed(list(zip(conds, thens))):
+                n = emit(abi.OP_CASE, cn, tn, t=e.type, ival=n)
         elif isinstance(e, ir.Cmp):
-            a, b = lower(e.lhs), lower(e.rhs)
+            a, b = lower(e.lhs, guard), lower(e.rhs, guard)
             op = {"<": abi.OP_LT, "<=": abi.OP_LE, ">": abi.OP_GT, ">=": abi.OP_GE, "=": abi.OP_EQ,
                   "<>": abi.OP_NE}[e.op]
             n = emit(op, a, b, t=e.type)
         elif isinstance(e, ir.Logic):
             if e.op == "not":
-                n = emit(abi.OP_NOT, lower(e.args[0]), t=e.type)
+                n = emit(abi.OP_NOT, lower(e.args[0], guard), t=e.type)
             else:
-                n = lower(e.args[0])
+                n = lower(e.args[0], guard)
                 for x in e.args[1:]:
-                    n = emit(abi.OP_AND if e.op == "and" else abi.OP_OR, n, lower(x), t=e.type)
+                    n = emit(abi.OP_AND if e.op == "and" else abi.OP_OR, n, lower(x, guard), t=e.type)
         elif isinstance(e, ir.IsNull):
-            n = emit(abi.OP_IS_NULL, lower(e.arg), t=e.type)
+            n = emit(abi.OP_IS_NULL, lower(e.arg, guard), t=e.type)
         else:
             raise UnsupportedPlan(f"expression {type(e).__name__}")
-        node_of[e] = n
+        node_of[memo_key] = n
         return n
 
     # joins first so that a join's key node precedes every inner-table column

@@ -26,9 +26,9 @@ _TOKEN = re.compile(r"""
 
 _KEYWORDS = {"select", "from", "where", "group", "by", "order", "limit", "join", "inner", "on", "and", "or",
              "not", "as", "is", "null", "asc", "desc", "extract", "year", "cast", "date", "timestamp",
-             "between", "count", "sum", "min", "max", "avg",
+             "between", "count", "sum", "min", "max", "avg", "case", "when", "then", "else", "end",
              # recognised only to be rejected: they must never be taken for a table alias or a column name
-             "left", "right", "full", "outer", "cross", "natural", "having", "distinct", "over", "union", "using"}
+             "in", "left", "right", "full", "outer", "cross", "natural", "having", "distinct", "over", "union", "using"}
 
 
 def _tokenize(s: str):
@@ -121,14 +121,46 @@ class _Parser:
             return ir.Logic("not", (self.not_expr(),))
         return self.cmp_expr()
 
+    def _coerce_dict_literal(self, a, b, op):
+        """'literal' vs a dictionary-encoded column: the literal becomes its dictionary id (ids are table-wide,
+        ArrowStorage keeps one dictionary per column).  A string that is not in the dictionary gets an id no row has."""
+        def conv(col, lit):
+            if isinstance(lit, ir.Const) and isinstance(lit.value, str):
+                if not (isinstance(col, ir.ColumnRef) and col.type.kind == "dict"):
+                    raise UnsupportedPlan("string literal compared with a non-dictionary expression")
+                if op not in ("=", "<>"):
+                    raise UnsupportedPlan("only = and <> are defined between a dictionary column and a string literal")
+                tname = [tn for _, tn, tidx in self.scopes if tidx == col.table][0]
+                d = self.tables[tname].columns[col.column].dictionary or []
+                return ir.Const(d.index(lit.value) if lit.value in d else len(d), ir.SqlType("int", 4, False))
+            return lit
+        return conv(b, a), conv(a, b)
+
+    def _equals(self, op, lhs, rhs):
+        lhs, rhs = self._coerce_temporal(lhs, rhs)
+        lhs, rhs = self._coerce_dict_literal(lhs, rhs, op)
+        return ir.make_cmp(op, lhs, rhs)
+
     def cmp_expr(self):
         lhs = self.add_expr()
         t = self.peek()
         if t[0] == "op" and t[1] in ("<", "<=", ">", ">=", "=", "<>", "!="):
             self.i += 1
             rhs = self.add_expr()
-            lhs, rhs = self._coerce_temporal(lhs, rhs)
-            return ir.make_cmp("<>" if t[1] == "!=" else t[1], lhs, rhs)
+            return self._equals("<>" if t[1] == "!=" else t[1], lhs, rhs)
+        neg_in = t == ("kw", "not") and self.peek(1) == ("kw", "in")
+        if t == ("kw", "in") or neg_in:
+            # x [NOT] IN (a, b, ...): a disjunction of equalities (three-valued: a NULL x stays NULL and is filtered)
+            self.i += 2 if neg_in else 1
+            self.eat("op", "(")
+            e = None
+            while True:
+                c = self._equals("=", lhs, self.add_expr())
+                e = c if e is None else ir.Logic("or", (e, c))
+                if not self.accept("op", ","):
+                    break
+            self.eat("op", ")")
+            return ir.Logic("not", (e,)) if neg_in else e
         if t == ("kw", "is"):
             self.i += 1
             neg = self.accept("kw", "not")
@@ -216,6 +248,29 @@ class _Parser:
             arg = self.expr()
             self.eat("op", ")")
             return ir.make_agg(t[1], arg, self.bigint_count)
+        if t == ("kw", "null"):
+            self.i += 1
+            return ir.Const(None, ir.SqlType("int", 4, True))       # only meaningful as a CASE value, which retypes it
+        if t == ("kw", "case"):
+            # searched CASE, or simple CASE x WHEN v … (rewritten to x = v)
+            self.i += 1
+            subject = None if self.peek() == ("kw", "when") else self.expr()
+            arms, else_ = [], None
+            while self.accept("kw", "when"):
+                c = self.expr()
+                if subject is not None:
+                    c = self._equals("=", subject, c)
+                self.eat("kw", "then")
+                arms.append((c, self.expr()))
+            if not arms:
+                raise SyntaxError("CASE without WHEN")
+            if self.accept("kw", "else"):
+                else_ = self.expr()
+            self.eat("kw", "end")
+            try:
+                return ir.make_case(arms, else_)
+            except NotImplementedError as ex:
+                raise UnsupportedPlan(str(ex))
         if t == ("kw", "extract"):
             self.i += 1
             self.eat("op", "(")

@@ -110,7 +110,10 @@ enum hdk_b200_op {
   HDK_B200_OP_OR = 15,
   HDK_B200_OP_NOT = 16,
   HDK_B200_OP_IS_NULL = 17,
-  HDK_B200_OP_UMINUS = 18
+  HDK_B200_OP_UMINUS = 18,
+  HDK_B200_OP_CASE = 19    /* a = WHEN condition, b = THEN value, ival = ELSE value node: b if a is true (> 0, a NULL */
+                           /* condition is not), else the ELSE node — CodeGenerator::codegenCase, QE/CaseIR.cpp:51-113. */
+                           /* Both values already carry the node's type; further WHEN arms nest in the ELSE node.     */
 };
 
 typedef struct hdk_b200_expr {
@@ -119,7 +122,10 @@ typedef struct hdk_b200_expr {
   int32_t b;    /* operand node index, or column index for OP_COL */
   int32_t aux;
   hdk_b200_type type; /* result type */
-  int32_t pad;
+  int32_t guard; /* 0 = always evaluated.  g > 0: the node sits inside a CASE arm and is evaluated only for rows where
+                  * node g-1 is true; elsewhere it raises no error and its value is never selected.  The reference gets
+                  * this from the basic blocks codegenCase emits (QE/CaseIR.cpp:66-93): a division in a THEN arm cannot
+                  * fail for rows that take another arm. */
   int64_t ival;
   double fval;
 } hdk_b200_expr;

@@ -388,6 +388,31 @@ def test_filter_and_group_by_on_gpu(oracle_mod, torch):
         check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), pq.plan.n_keys)
 
 
+def test_case_expressions_on_gpu(oracle_mod, torch):
+    """CASE arms (QE/CaseIR.cpp:51-113): value selection, ELSE NULL, CASE as group key / in the filter, and guarded arms —
+    a division or checked addition inside an arm raises only for the rows that take the arm.  GPU buffer vs the oracle's,
+    and the error code when the arm is taken."""
+    from tests.test_sqlite_oracle import CASE_ERROR_QUERIES, CASE_QUERIES, case_tables
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    st = util.make_storage(case_tables(), fragment_size=101)
+    for text, nk in CASE_QUERIES:
+        ex = Executor(st)
+        pq = ex.plan(sql.parse(text, st.tables))
+        prep = ex.prepare(pq)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0, text
+        check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), pq.plan.n_keys)
+    for text, code in CASE_ERROR_QUERIES:
+        ex = Executor(st)
+        pq = ex.plan(sql.parse(text, st.tables))
+        prep = ex.prepare(pq)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == code, text
+
+
 def test_group_by_boundaries_and_null_on_gpu(oracle_mod, torch):
     """GroupByBoundariesAndNull (ArrowBasedExecuteTest.cpp:2845-2866) on the device: keys at INT32_MAX / 127 / 32767 / 2^62
     with NULL keys, single and composite, buffers byte-identical to the oracle's."""

@@ -44,7 +44,48 @@ def test_non_grouped_aggregate_plans_as_one_keyless_entry(st):
     assert pq.plan.n_keys == 0 and pq.qmd.entry_count == 1 and pq.qmd.keyless == 1 and pq.qmd.hash_type == abi.PERFECT_HASH
 
 
+def test_in_lists_and_dictionary_literals(st):
+    u = sql.parse("SELECT a, COUNT(*) FROM t WHERE b IN (0, 2) GROUP BY a", st.tables)
+    q = u.quals[0]
+    assert isinstance(q, ir.Logic) and q.op == "or" and all(isinstance(c, ir.Cmp) for c in q.args)
+    u = sql.parse("SELECT a, COUNT(*) FROM t WHERE b NOT IN (0, 2) GROUP BY a", st.tables)
+    assert u.quals[0].op == "not" and u.quals[0].args[0].op == "or"
+    d = st.get_table("t").columns["s"].dictionary
+    u = sql.parse("SELECT a, COUNT(*) FROM t WHERE s = 'v' GROUP BY a", st.tables)
+    assert isinstance(u.quals[0].rhs, ir.Const) and u.quals[0].rhs.value == d.index("v")
+    u = sql.parse("SELECT a, COUNT(*) FROM t WHERE 'zz' = s GROUP BY a", st.tables)       # not in the dictionary: an id no row carries
+    assert u.quals[0].lhs.value == len(d)
+
+
+def test_case_lowering_guards_only_what_can_raise(st):
+    pq = util.plan_sql(st, "SELECT a, SUM(CASE WHEN b > 0 THEN x ELSE 0 END) FROM t GROUP BY a")
+    nodes = [pq.plan.exprs[i] for i in range(pq.plan.n_exprs)]
+    assert sum(n.op == abi.OP_CASE for n in nodes) == 1 and all(n.guard == 0 for n in nodes)   # pure arms: no guards
+    pq = util.plan_sql(st, "SELECT a, SUM(CASE WHEN b <> 0 THEN x / b WHEN b = 0 THEN 1 ELSE x / (b - 1) END) FROM t GROUP BY a")
+    nodes = [pq.plan.exprs[i] for i in range(pq.plan.n_exprs)]
+    divs = [n for n in nodes if n.op == abi.OP_DIV]
+    assert len(divs) == 2 and all(d.guard > 0 for d in divs) and divs[0].guard != divs[1].guard
+    first = nodes[divs[0].guard - 1]
+    assert first.op == abi.OP_NE                                            # THEN 1 runs where WHEN 1 is true
+    assert nodes[divs[1].guard - 1].op == abi.OP_AND                        # ELSE runs where neither WHEN was
+    case = [n for n in nodes if n.op == abi.OP_CASE]
+    assert len(case) == 2 and case[1].a == divs[0].guard - 1 and nodes[case[1].ival] is case[0]   # nested from the last arm outwards
+    pq = util.plan_sql(st, "SELECT a, COUNT(CASE WHEN b > 0 THEN 1 END) FROM t GROUP BY a")       # implicit ELSE NULL
+    case = [pq.plan.exprs[i] for i in range(pq.plan.n_exprs) if pq.plan.exprs[i].op == abi.OP_CASE]
+    assert case[0].type.nullable == 1 and pq.plan.exprs[case[0].ival].ival == abi.int_null(4)
+    # the same division inside and outside an arm: two nodes, only one of them guarded
+    pq = util.plan_sql(st, "SELECT a, SUM(CASE WHEN b <> 0 THEN x / b ELSE 0 END), SUM(x / b) FROM t GROUP BY a")
+    divs = [pq.plan.exprs[i] for i in range(pq.plan.n_exprs) if pq.plan.exprs[i].op == abi.OP_DIV]
+    assert sorted(d.guard > 0 for d in divs) == [False, True]
+
+
 @pytest.mark.parametrize("text", [
+    "SELECT a, COUNT(*) FROM t WHERE CASE WHEN b > 0 THEN s ELSE s END = 'u' GROUP BY a",   # CASE over dictionary values
+    "SELECT a, SUM(CASE WHEN b THEN 1 ELSE 0 END) FROM t GROUP BY a",    # non-boolean WHEN
+    "SELECT a, SUM(CASE WHEN b > 0 THEN NULL END) FROM t GROUP BY a",    # only NULL values
+    "SELECT a, COUNT(*) FROM t WHERE s < 'v' GROUP BY a",                # ordering on dictionary ids is not string ordering
+    "SELECT a, COUNT(*) FROM t WHERE a = 'u' GROUP BY a",                # string literal against a number
+    "SELECT a, COUNT(*) FROM t WHERE a IN () GROUP BY a",                # empty IN list
     "SELECT a, COUNT(*) FROM t GROUP BY a HAVING COUNT(*) > 1",          # HAVING
     "SELECT a, COUNT(DISTINCT b) FROM t GROUP BY a",                    # count distinct
     "SELECT a FROM t",                                                  # projection without aggregation

@@ -152,6 +152,14 @@ FILTER_GROUP_BY_QUERIES = [
     ("SELECT x, COUNT(u) FROM test GROUP BY x", 1),
     ("SELECT CAST((dd - 0.5) * 2.0 AS int) AS key0, COUNT(*) AS val FROM test WHERE (dd >= 100.0 AND dd < 400.0) GROUP BY key0", 1),
     ("SELECT x * 2 AS x2, COUNT(*) AS n FROM test GROUP BY x2", 1),
+    # IN lists and dictionary literals (Select.InValues :2554, Select.Strings :4593 — the equality forms)
+    ("SELECT x, COUNT(*) FROM test WHERE y IN (42, 44, 99) GROUP BY x", 1),
+    ("SELECT x, COUNT(*), SUM(z) FROM test WHERE z NOT IN (100, 102) GROUP BY x", 1),
+    ("SELECT x, COUNT(*) FROM test WHERE str = 'foo' GROUP BY x", 1),
+    ("SELECT x, COUNT(*) FROM test WHERE str <> 'bar' AND str <> 'not there' GROUP BY x", 1),
+    ("SELECT str, COUNT(*), MIN(y) FROM test WHERE str IN ('foo', 'baz', 'qux') GROUP BY str", 1),
+    ("SELECT x, COUNT(*) FROM test WHERE str = 'not there' GROUP BY x", 1),
+    ("SELECT COUNT(*) FROM test WHERE str NOT IN ('foo') AND y IN (43)", 0),
 ]
 
 
@@ -174,3 +182,62 @@ def test_filter_and_group_by_vs_sqlite(oracle_mod, text, nk):
     exp = util.sqlite_rows(tables, text, nk)
     keyf = lambda r: tuple((0, 0) if x is None else (1, x) for x in r)   # noqa: E731
     util.assert_rows_equal(sorted(got, key=keyf), sorted(exp, key=keyf), rel=1e-6)
+
+
+def case_tables():
+    tables = filter_group_by_tables()
+    rng = np.random.default_rng(9)
+    n = tables["test"].num_rows
+    t = tables["test"].append_column("q", pa.array(rng.integers(0, 3, n).astype(np.int32)))
+    tables["test"] = t.append_column("big", pa.array(rng.integers(2**62, 2**63 - 1, n)))
+    return tables
+
+
+# CASE expressions (Select.Case, ArrowBasedExecuteTest.cpp:4244-4460; codegen QE/CaseIR.cpp): value selection, the implicit
+# ELSE NULL, CASE as a group key and inside a filter, and arms that would raise for the rows that do not take them
+CASE_QUERIES = [
+    ("SELECT x, SUM(CASE WHEN y > 43 THEN z ELSE 0 END), COUNT(*) FROM test GROUP BY x", 1),
+    ("SELECT x, SUM(CASE WHEN y = 42 THEN 1 WHEN y = 43 THEN 10 ELSE 100 END) FROM test GROUP BY x", 1),
+    ("SELECT x, COUNT(CASE WHEN z > 100 THEN 1 END), MIN(CASE WHEN u > 2.5 THEN u END) FROM test GROUP BY x", 1),
+    ("SELECT CASE WHEN y < 44 THEN 0 ELSE 1 END AS k, COUNT(*), SUM(dd) FROM test GROUP BY k", 1),
+    ("SELECT x, SUM(CASE WHEN q <> 0 THEN y / q ELSE -1 END) FROM test GROUP BY x", 1),
+    ("SELECT x, SUM(CASE WHEN q = 0 THEN 0 WHEN y / q > 30 THEN 1 ELSE z / q END) FROM test GROUP BY x", 1),
+    ("SELECT x, AVG(CASE WHEN z IS NULL THEN 0.5 ELSE dd * 2 END) FROM test GROUP BY x", 1),
+    ("SELECT x, SUM(CASE y WHEN 42 THEN 2 WHEN 44 THEN 3 ELSE 0 END) FROM test GROUP BY x", 1),
+    ("SELECT x, COUNT(*) FROM test WHERE CASE WHEN q = 0 THEN 0 ELSE y / q END > 30 GROUP BY x", 1),
+    ("SELECT x, SUM(CASE WHEN y > 43 THEN big + big ELSE 1 END) FROM test WHERE y <= 43 GROUP BY x", 1),
+    ("SELECT SUM(CASE WHEN str = 'foo' THEN dd ELSE 0.0 END), SUM(dd) FROM test", 0),
+    ("SELECT x, SUM(CASE WHEN q > 0 THEN CASE WHEN q > 1 THEN 100 / (q - 1) ELSE 100 / q END ELSE 100 / (q + 5) END) "
+     "FROM test GROUP BY x", 1),
+    ("SELECT x, SUM(CASE WHEN z > 100 THEN 1 / q WHEN z IS NULL THEN 7 ELSE 2 END) FROM test WHERE q > 0 OR z IS NULL OR z <= 100 "
+     "GROUP BY x", 1),
+]
+# the arm IS taken by rows that make it fail: the error must come through (Execute.h:156-157)
+CASE_ERROR_QUERIES = [
+    ("SELECT x, SUM(CASE WHEN q <> 1 THEN y / q ELSE -1 END) FROM test GROUP BY x", 1),            # ERR_DIV_BY_ZERO
+    ("SELECT x, SUM(CASE WHEN y > 43 THEN big + big ELSE 1 END) FROM test GROUP BY x", 7),           # ERR_OVERFLOW_OR_UNDERFLOW
+    ("SELECT x, SUM(CASE WHEN 10 / q > 3 THEN 1 ELSE 0 END) FROM test GROUP BY x", 1),               # the WHEN itself
+]
+
+
+@pytest.mark.parametrize("text,nk", CASE_QUERIES)
+@pytest.mark.parametrize("kind", ["port", "reference"])
+def test_case_expressions_vs_sqlite(oracle_mod, text, nk, kind):
+    from hdk_b200.executor import ResultSet
+    tables = case_tables()
+    st = util.make_storage(tables, fragment_size=101)
+    pq = util.plan_sql(st, text)
+    buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
+    assert err == 0
+    got = [tuple(r.values()) for r in ResultSet(pq, buf, {}).to_arrow().to_pylist()]
+    exp = util.sqlite_rows(tables, text, nk)
+    keyf = lambda r: tuple((0, 0) if x is None else (1, x) for x in r)   # noqa: E731
+    util.assert_rows_equal(sorted(got, key=keyf), sorted(exp, key=keyf), rel=1e-9)
+
+
+@pytest.mark.parametrize("text,code", CASE_ERROR_QUERIES)
+def test_case_arm_errors_reach_the_caller(oracle_mod, text, code):
+    st = util.make_storage(case_tables(), fragment_size=101)
+    pq = util.plan_sql(st, text)
+    _, err = util.run_oracle(oracle_mod, st, pq, kind="port")
+    assert err == code
