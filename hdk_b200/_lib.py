@@ -24,7 +24,8 @@ EXPORTS = [
     "hdk_b200_init_baseline_hash_join_buff_on_device", "hdk_b200_fill_baseline_hash_join_buff_on_device",
     "hdk_b200_fill_one_to_many_baseline_hash_table_on_device", "hdk_b200_probe_hash_join_on_device",
     "hdk_b200_probe_baseline_hash_join_on_device", "hdk_b200_gather_join_payload_on_device", "hdk_b200_shuffle_count", "hdk_b200_shuffle_scatter", "hdk_b200_shuffle_scatter_to", "hdk_b200_region_count", "hdk_b200_region_scatter_to",
-    "hdk_b200_compact_result", "hdk_b200_init_chunk_stats_on_device",
+    "hdk_b200_compact_result", "hdk_b200_sort_scratch_bytes", "hdk_b200_sort_permutation", "hdk_b200_gather_rows",
+    "hdk_b200_init_chunk_stats_on_device",
     "hdk_b200_materialize_nulls_on_device", "hdk_b200_peer_alloc", "hdk_b200_peer_open", "hdk_b200_peer_close",
     "hdk_b200_peer_free", "hdk_b200_exchange_bytes", "hdk_b200_exchange_init", "hdk_b200_launch_exchange", "hdk_b200_query_host", "hdk_b200_last_error", "hdk_b200_abi_version",
     "hdk_b200_device_count", "hdk_b200_launch_count",
@@ -63,6 +64,9 @@ def _bind(lib):
         "hdk_b200_region_count": (ci, [P, Q, KP, u32, vp, vp]),
         "hdk_b200_region_scatter_to": (ci, [P, Q, KP, u32, vp, vp, vp, vp]),
         "hdk_b200_compact_result": (ci, [P, Q, vp, vp, vp, vp]),
+        "hdk_b200_sort_scratch_bytes": (sz, [u64]),
+        "hdk_b200_sort_permutation": (ci, [C.POINTER(vp), C.POINTER(abi.OrderEntry), ci, u64, vp, vp, sz, vp]),
+        "hdk_b200_gather_rows": (ci, [C.POINTER(vp), C.POINTER(vp), ci, vp, u64, vp]),
         "hdk_b200_init_chunk_stats_on_device": (ci, [vp, vp]),
         "hdk_b200_materialize_nulls_on_device": (ci, [vp, ci, ci, vp, i64, i64, vp, vp]),
         "hdk_b200_peer_alloc": (ci, [sz, C.POINTER(vp), vp]),

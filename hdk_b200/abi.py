@@ -102,6 +102,11 @@ class LaunchInfo(C.Structure):
                 ("block", C.c_int32), ("smem_bytes", C.c_int32), ("n_accumulators", C.c_int32), ("tile_rows", C.c_int32)]
 
 
+class OrderEntry(C.Structure):
+    _fields_ = [("column", C.c_int32), ("is_fp", C.c_int32), ("type_width", C.c_int32), ("nullable", C.c_int32),
+                ("is_desc", C.c_int32), ("nulls_first", C.c_int32), ("dict_rank", C.c_void_p), ("dict_size", C.c_int64)]
+
+
 class ChunkStatsPOD(C.Structure):
     _fields_ = [("min_i", C.c_int64), ("max_i", C.c_int64), ("min_f_enc", C.c_int64), ("max_f_enc", C.c_int64),
                 ("null_count", C.c_uint64), ("row_count", C.c_uint64)]

@@ -1,0 +1,308 @@
+// hdk_b200/csrc/sort.cu — ORDER BY / LIMIT over an aggregated result, on the device.
+//
+// The reference sorts a ResultSet by building a permutation of its non-empty entries with a comparator over the
+// ORDER BY targets (sortResultSet, QE/ResultSetSort.cpp:752-851; ResultSetComparator::operator(), :333-470: per order
+// entry NULL placement by `nulls_first`, then `(lhs < rhs) != is_desc`, dictionary targets by string), with
+// std::partial_sort for LIMIT (topPermutation, :504-520) — host work proportional to the number of groups, which
+// for a baseline-hash result (1e8 groups) dwarfs the aggregation itself.
+//
+// Here every ORDER BY target becomes one 64-bit key whose unsigned order IS the comparator's order, and the
+// permutation comes from a stable LSD radix sort (8-bit digits) of (key, row id) pairs, last ORDER BY target first.
+// Input: the dense 8-byte result columns hdk_b200_compact_result produces.  HBM-bound: per pass one read of the keys
+// for the histogram, one read + one write of the pairs for the scatter; digits on which all keys agree (known from
+// the OR / AND of the keys, reduced while they are generated) cost nothing, so a COUNT column below 2^24 takes three
+// passes, not eight.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace hb {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortItems = 8;                                  // elements per thread per chunk
+constexpr int kSortChunk = kSortThreads * kSortItems;          // 2048
+constexpr int kSortMaxCtas = 148 * 4;
+
+struct SortState {
+  unsigned long long key_or, key_and;   // over all keys of the current ORDER BY target
+};
+
+struct SortBufs {
+  uint64_t* keys[2];
+  uint32_t* idx[2];      // idx[0] = the caller's permutation buffer
+  uint32_t* hist;        // [256][n_ctas], digit-major
+  SortState* state;
+  uint64_t n;
+  uint32_t n_ctas;
+  uint64_t per_cta;      // elements per CTA range, a multiple of kSortChunk
+};
+
+// digit p is constant over all keys ⇔ OR and AND agree on its bits
+__device__ __forceinline__ bool digit_varies(const SortState* s, int p) { return (((s->key_or ^ s->key_and) >> (8 * p)) & 0xff) != 0; }
+// which of the two buffers holds the data before pass p: every pass that ran flipped it
+__device__ __forceinline__ int cur_before(const SortState* s, int p) {
+  int c = 0;
+  for (int q = 0; q < p; ++q) c ^= int(digit_varies(s, q));
+  return c;
+}
+
+// --------------------------------------------------------------------------------------------- keys
+struct KeyArgs {
+  const int64_t* col;
+  const int32_t* dict_rank;
+  int64_t dict_size;
+  int32_t is_fp, type_width, nullable, is_desc, nulls_first;
+};
+
+// unsigned key whose ascending order is the comparator's order (QE/ResultSetSort.cpp:410-470)
+__device__ __forceinline__ uint64_t order_key(const KeyArgs& k, int64_t cell) {
+  bool is_null;
+  uint64_t u;
+  if (k.is_fp) {
+    const double d = __longlong_as_double(cell);
+    is_null = k.nullable && d == (k.type_width == 4 ? double(1.17549435e-38f) : 2.2250738585072014e-308);
+    const uint64_t b = d == 0.0 ? 0ull : uint64_t(cell);   // -0.0 and +0.0 compare equal
+    u = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+  } else {
+    is_null = k.nullable && cell == int_null_of(k.type_width);
+    if (k.dict_rank && !is_null) cell = (cell >= 0 && cell < k.dict_size) ? int64_t(k.dict_rank[cell]) : cell;
+    u = uint64_t(cell) ^ 0x8000000000000000ull;
+  }
+  if (!k.nullable) return k.is_desc ? ~u : u;
+  if (is_null) return k.nulls_first ? 0ull : ~0ull;
+  // one code at the NULL end is kept free: an integer's sentinel is its type minimum, so non-NULL u >= 1
+  // (fp: the extreme codes are NaN payloads no arithmetic produces)
+  uint64_t r = k.is_desc ? ~u : (k.is_fp ? u : u - 1);            // ints: [0, 2^64 - 2] either way
+  if (k.is_fp) r = min(max(r, uint64_t(1)), ~uint64_t(1)) - 1;    // clamp into [0, 2^64 - 3]
+  return k.nulls_first ? r + 1 : r;
+}
+
+__global__ void __launch_bounds__(256) sort_keys_kernel(const KeyArgs k, SortBufs b, int first) {
+  unsigned long long o = 0, a = ~0ull;
+  const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < b.n; i += step) {
+    uint32_t row;
+    if (first) { row = uint32_t(i); b.idx[0][i] = row; } else row = b.idx[0][i];
+    const uint64_t key = order_key(k, k.col[row]);
+    b.keys[0][i] = key;
+    o |= key;
+    a &= key;
+  }
+  for (int d = 16; d; d >>= 1) {
+    o |= __shfl_xor_sync(0xffffffffu, o, d);
+    a &= __shfl_xor_sync(0xffffffffu, a, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicOr(&b.state->key_or, o);
+    atomicAnd(&b.state->key_and, a);
+  }
+}
+
+// --------------------------------------------------------------------------------------------- one radix pass
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(SortBufs b, int pass) {
+  if (!digit_varies(b.state, pass)) return;
+  __shared__ uint32_t bins[256];
+  bins[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t* src = b.keys[cur_before(b.state, pass)];
+  const uint64_t lo = blockIdx.x * b.per_cta, hi = min(b.n, lo + b.per_cta);
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += kSortThreads) atomicAdd(&bins[(src[i] >> (8 * pass)) & 0xff], 1u);
+  __syncthreads();
+  b.hist[uint64_t(threadIdx.x) * b.n_ctas + blockIdx.x] = bins[threadIdx.x];
+}
+
+// exclusive scan of the digit-major histogram: entry [d][cta] becomes the first output position of CTA cta's digit d
+__global__ void __launch_bounds__(1024) sort_scan_kernel(SortBufs b, int pass) {
+  if (!digit_varies(b.state, pass)) return;
+  __shared__ uint32_t part[1024];
+  const uint32_t total = 256u * b.n_ctas;
+  const uint32_t per = (total + 1023u) / 1024u;
+  const uint32_t lo = min(total, threadIdx.x * per), hi = min(total, lo + per);
+  uint32_t s = 0;
+  for (uint32_t i = lo; i < hi; ++i) s += b.hist[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {           // Hillis-Steele inclusive scan of the 1024 partial sums
+    const uint32_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - s;
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t c = b.hist[i];
+    b.hist[i] = run;
+    run += c;
+  }
+}
+
+// Stable scatter.  A CTA owns a contiguous range and walks it chunk by chunk; inside a chunk warp w owns the
+// elements [w*256, (w+1)*256) in (item, lane) order.  Rank of an element = CTA's running offset of its digit
+// + elements of the same digit in earlier warps of the chunk + earlier elements of the same digit in its own warp.
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortBufs b, int pass) {
+  if (!digit_varies(b.state, pass)) return;
+  __shared__ uint32_t cnt[kSortWarps][257];     // [.][256] collects the out-of-range lanes of the last chunk
+  __shared__ uint32_t off[256];
+  const int cur = cur_before(b.state, pass);
+  const uint64_t* __restrict__ ksrc = b.keys[cur];
+  const uint32_t* __restrict__ isrc = b.idx[cur];
+  uint64_t* __restrict__ kdst = b.keys[cur ^ 1];
+  uint32_t* __restrict__ idst = b.idx[cur ^ 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  off[threadIdx.x] = b.hist[uint64_t(threadIdx.x) * b.n_ctas + blockIdx.x];
+  const uint64_t lo = blockIdx.x * b.per_cta, hi = min(b.n, lo + b.per_cta);
+  for (uint64_t base = lo; base < hi; base += kSortChunk) {
+    for (int i = threadIdx.x; i < kSortWarps * 257; i += kSortThreads) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    uint64_t key[kSortItems];
+    uint32_t row[kSortItems], rank[kSortItems];
+    int dig[kSortItems];
+    const uint64_t wbase = base + uint64_t(warp) * (32 * kSortItems) + lane;
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      const uint64_t i = wbase + uint64_t(j) * 32;
+      const bool ok = i < hi;
+      key[j] = ok ? ksrc[i] : 0;
+      row[j] = ok ? isrc[i] : 0;
+      dig[j] = ok ? int((key[j] >> (8 * pass)) & 0xff) : 256;
+    }
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      const unsigned peers = __match_any_sync(0xffffffffu, dig[j]);
+      rank[j] = cnt[warp][dig[j]] + __popc(peers & lt);
+      __syncwarp();
+      if ((peers & lt) == 0) cnt[warp][dig[j]] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    {
+      const int d = threadIdx.x;     // 256 threads = 256 digits
+      uint32_t run = off[d];
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t c = cnt[w][d];
+        cnt[w][d] = run;
+        run += c;
+      }
+      off[d] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+      if (dig[j] < 256) {
+        const uint32_t pos = cnt[warp][dig[j]] + rank[j];
+        kdst[pos] = key[j];
+        idst[pos] = row[j];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// after the last pass of a target: bring the permutation back to idx[0] if an odd number of passes ran
+__global__ void __launch_bounds__(256) sort_settle_kernel(SortBufs b) {
+  if (cur_before(b.state, 8) == 0) return;
+  const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < b.n; i += step) b.idx[0][i] = b.idx[1][i];
+}
+
+struct GatherArgs {
+  const int64_t* in[HDK_B200_MAX_TARGETS];
+  int64_t* out[HDK_B200_MAX_TARGETS];
+  int32_t n_cols;
+  const uint32_t* perm;
+  uint64_t n_out;
+};
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant__ GatherArgs a) {
+  const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < a.n_out; i += step) {
+    const uint32_t r = a.perm[i];
+    for (int c = 0; c < a.n_cols; ++c) a.out[c][i] = a.in[c][r];
+  }
+}
+
+static inline uint32_t sort_ctas(uint64_t n) { return uint32_t(std::min<uint64_t>(kSortMaxCtas, (n + kSortChunk - 1) / kSortChunk)); }
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" {
+
+size_t hdk_b200_sort_scratch_bytes(uint64_t n_rows) {
+  if (n_rows == 0) return 256;
+  return align256(n_rows * 8) * 2 + align256(n_rows * 4) + align256(size_t(256) * sort_ctas(n_rows) * 4) + 256;
+}
+
+int hdk_b200_sort_permutation(const int64_t* const* cols, const hdk_b200_order_entry* order, int n_order, uint64_t n_rows,
+                              uint32_t* permutation, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!order || n_order < 1 || n_order > HDK_B200_MAX_TARGETS) { set_error("sort: bad order entry count"); return HDK_B200_E_INVALID; }
+  if (n_rows >> 32) { set_error("sort: more than 2^32 rows"); return HDK_B200_E_UNSUPPORTED; }   // RowSortException, ResultSetSort.cpp:785-787
+  if (n_rows == 0) return HDK_B200_OK;
+  if (!cols || !permutation || !scratch) { set_error("sort: null argument"); return HDK_B200_E_INVALID; }
+  if (scratch_bytes < hdk_b200_sort_scratch_bytes(n_rows)) { set_error("sort: scratch too small"); return HDK_B200_E_NOMEM; }
+  for (int i = 0; i < n_order; ++i) {
+    const hdk_b200_order_entry& oe = order[i];
+    if (oe.column < 0 || oe.column >= HDK_B200_MAX_TARGETS || !cols[oe.column]) { set_error("sort: bad order column"); return HDK_B200_E_INVALID; }
+    if (oe.type_width != 1 && oe.type_width != 2 && oe.type_width != 4 && oe.type_width != 8) { set_error("sort: bad type width"); return HDK_B200_E_INVALID; }
+    if (oe.is_fp && oe.dict_rank) { set_error("sort: dictionary rank on a floating-point target"); return HDK_B200_E_INVALID; }
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SortBufs b{};
+  uint8_t* p = static_cast<uint8_t*>(scratch);
+  b.keys[0] = reinterpret_cast<uint64_t*>(p); p += align256(n_rows * 8);
+  b.keys[1] = reinterpret_cast<uint64_t*>(p); p += align256(n_rows * 8);
+  b.idx[0] = permutation;
+  b.idx[1] = reinterpret_cast<uint32_t*>(p); p += align256(n_rows * 4);
+  b.n_ctas = sort_ctas(n_rows);
+  b.hist = reinterpret_cast<uint32_t*>(p); p += align256(size_t(256) * b.n_ctas * 4);
+  b.state = reinterpret_cast<SortState*>(p);
+  b.n = n_rows;
+  const uint64_t chunks = (n_rows + kSortChunk - 1) / kSortChunk;
+  b.per_cta = (chunks + b.n_ctas - 1) / b.n_ctas * kSortChunk;
+  const int flat_grid = int(std::min<uint64_t>(148 * 8, (n_rows + 255) / 256));
+  for (int o = n_order - 1; o >= 0; --o) {       // LSD over the ORDER BY list: least significant target first
+    const hdk_b200_order_entry& oe = order[o];
+    KeyArgs k{cols[oe.column], oe.dict_rank, oe.dict_size, oe.is_fp, oe.type_width, oe.nullable, oe.is_desc, oe.nulls_first};
+    HB_CUDA(cudaMemsetAsync(&b.state->key_or, 0x00, 8, st));
+    HB_CUDA(cudaMemsetAsync(&b.state->key_and, 0xff, 8, st));
+    sort_keys_kernel<<<flat_grid, 256, 0, st>>>(k, b, o == n_order - 1);
+    HB_LAUNCH_CHECK();
+    for (int pass = 0; pass < 8; ++pass) {
+      sort_hist_kernel<<<b.n_ctas, kSortThreads, 0, st>>>(b, pass);
+      HB_LAUNCH_CHECK();
+      sort_scan_kernel<<<1, 1024, 0, st>>>(b, pass);
+      HB_LAUNCH_CHECK();
+      sort_scatter_kernel<<<b.n_ctas, kSortThreads, 0, st>>>(b, pass);
+      HB_LAUNCH_CHECK();
+    }
+    sort_settle_kernel<<<flat_grid, 256, 0, st>>>(b);
+    HB_LAUNCH_CHECK();
+  }
+  return HDK_B200_OK;
+}
+
+int hdk_b200_gather_rows(const int64_t* const* cols_in, int64_t* const* cols_out, int n_cols, const uint32_t* permutation,
+                         uint64_t n_out, void* stream) {
+  if (n_cols < 1 || n_cols > HDK_B200_MAX_TARGETS) { set_error("gather: bad column count"); return HDK_B200_E_INVALID; }
+  if (n_out == 0) return HDK_B200_OK;
+  if (!cols_in || !cols_out || !permutation) { set_error("gather: null argument"); return HDK_B200_E_INVALID; }
+  GatherArgs a{};
+  for (int c = 0; c < n_cols; ++c) {
+    if (!cols_in[c] || !cols_out[c]) { set_error("gather: null column"); return HDK_B200_E_INVALID; }
+    a.in[c] = cols_in[c];
+    a.out[c] = cols_out[c];
+  }
+  a.n_cols = n_cols;
+  a.perm = permutation;
+  a.n_out = n_out;
+  gather_rows_kernel<<<int(std::min<uint64_t>(148 * 8, (n_out + 255) / 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  HB_LAUNCH_CHECK();
+  return HDK_B200_OK;
+}
+
+}  // extern "C"

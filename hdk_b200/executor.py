@@ -129,6 +129,7 @@ class ResultSet:
         self.buffer = buffer
         self.dictionaries = dictionaries or {}
         self._cols = None
+        self.sorted_on_device = False     # ORDER BY / LIMIT already applied by hdk_b200_sort_permutation + gather_rows
 
     def _decode(self):
         """ResultSet iteration on the host (ResultSetIteration.cpp:1264-1360): numpy restatement used for
@@ -245,6 +246,25 @@ class ResultSet:
         rs._cols = cols
         return rs
 
+    def order_entries(self) -> list:
+        """One dict per ORDER BY item, typed the way the compacted 8-byte cells are (and the way `from_compact` reads them)."""
+        out = []
+        for entry in self.planned.unit.order_by:
+            t, desc, nulls_first = (tuple(entry) + (False,))[:3]
+            ti = self.planned.infos[t]
+            chosen = ti.compact_type
+            is_fp = ti.agg == abi.AGG_AVG or (chosen.is_fp and ti.agg != abi.AGG_COUNT)
+            if ti.agg == abi.AGG_AVG:
+                width = 8
+            elif is_fp:
+                width = 4 if (ti.float_argument_input or chosen.width == 4) else 8
+            else:
+                width = ti.type.width
+            d = self.dictionaries.get(t) if (not ti.is_agg and ti.type.kind == "dict") else None
+            out.append(dict(column=t, is_fp=int(is_fp), type_width=width, nullable=1, is_desc=int(bool(desc)),
+                            nulls_first=int(bool(nulls_first)), dictionary=d))
+        return out
+
     def row_count(self):
         cols = self._decode()
         return len(cols[0]) if cols else 0
@@ -280,8 +300,15 @@ class ResultSet:
             arrays.append(arr)
             names.append(name)
         tbl = pa.table(arrays, names=names)
-        if unit.order_by:
-            tbl = tbl.sort_by([(names[i], "descending" if d else "ascending") for i, d in unit.order_by])
+        if unit.order_by and not self.sorted_on_device:
+            # only result sets that did not come through Executor.execute_work_unit (tests decoding an oracle buffer):
+            # stable single-key sorts, last key first, each with its own NULL placement
+            import pyarrow.compute as pc
+            for entry in reversed(unit.order_by):
+                i, d, nf = (tuple(entry) + (False,))[:3]
+                idx = pc.sort_indices(tbl, sort_keys=[(names[i], "descending" if d else "ascending")],
+                                      null_placement="at_start" if nf else "at_end")
+                tbl = tbl.take(idx)
         if unit.limit is not None:
             tbl = tbl.slice(0, unit.limit)
         return tbl
@@ -739,8 +766,9 @@ class Executor:
                         {c: pr.local_column(i, n_recv) for i, c in enumerate(pq.columns)})
         return frag, n_recv
 
-    def compact_on_device(self, pq: planner.PlannedQuery, out) -> np.ndarray:
-        """hdk_b200_compact_result (ResultSet iteration on the device): [n_targets, rows] int64 cells on the host."""
+    def compact_on_device(self, pq: planner.PlannedQuery, out, to_host=True):
+        """hdk_b200_compact_result (ResultSet iteration on the device): [n_targets, rows] int64 cells (on the host, or
+        the device tensor and the row count with to_host=False)."""
         torch = self.ctx.torch
         E, T = pq.qmd.entry_count, pq.plan.n_targets
         cols = torch.empty((T, E), dtype=torch.int64, device=self.ctx.device)
@@ -749,7 +777,39 @@ class Executor:
         _lib.check(self.lib.hdk_b200_compact_result(C.byref(pq.plan), C.byref(pq.qmd), out.data_ptr(), ptrs.data_ptr(),
                                                     cnt.data_ptr(), self.ctx.stream_ptr()), "compact_result")
         n = int(cnt.item())
-        return cols[:, :n].cpu().numpy()
+        return cols[:, :n].cpu().numpy() if to_host else (cols, n)
+
+    def sort_on_device(self, cols, n_rows: int, order: list, limit=None):
+        """ORDER BY [LIMIT] over compacted result columns (sortResultSet, QE/ResultSetSort.cpp:752-851):
+        hdk_b200_sort_permutation, then hdk_b200_gather_rows of the first `limit` rows.  cols: device int64 [T, >= n_rows];
+        order: ResultSet.order_entries().  Returns a device tensor [T, min(limit, n_rows)]."""
+        torch = self.ctx.torch
+        T = cols.shape[0]
+        n_out = n_rows if limit is None else min(int(limit), n_rows)
+        out = torch.empty((T, n_out), dtype=torch.int64, device=self.ctx.device)
+        if n_rows == 0 or n_out == 0:
+            return out
+        entries = (abi.OrderEntry * len(order))()
+        keep = []
+        for e, oe in zip(entries, order):
+            e.column, e.is_fp, e.type_width, e.nullable = oe["column"], oe["is_fp"], oe["type_width"], oe["nullable"]
+            e.is_desc, e.nulls_first = oe["is_desc"], oe["nulls_first"]
+            if oe.get("dictionary") is not None:
+                d = oe["dictionary"]
+                rank = np.empty(len(d), dtype=np.int32)
+                rank[np.array(sorted(range(len(d)), key=d.__getitem__), dtype=np.int64)] = np.arange(len(d), dtype=np.int32)
+                rk = torch.from_numpy(rank).to(self.ctx.device)
+                keep.append(rk)
+                e.dict_rank, e.dict_size = rk.data_ptr(), len(d)
+        perm = torch.empty(n_rows, dtype=torch.int32, device=self.ctx.device)
+        sb = self.lib.hdk_b200_sort_scratch_bytes(n_rows)
+        scratch = torch.empty(sb, dtype=torch.uint8, device=self.ctx.device)
+        in_ptrs = (C.c_void_p * abi.MAX_TARGETS)(*[cols[t].data_ptr() for t in range(T)])
+        _lib.check(self.lib.hdk_b200_sort_permutation(in_ptrs, entries, len(order), n_rows, perm.data_ptr(), scratch.data_ptr(), sb,
+                                                      self.ctx.stream_ptr()), "sort_permutation")
+        out_ptrs = (C.c_void_p * T)(*[out[t].data_ptr() for t in range(T)])
+        _lib.check(self.lib.hdk_b200_gather_rows(in_ptrs, out_ptrs, T, perm.data_ptr(), n_out, self.ctx.stream_ptr()), "gather_rows")
+        return out
 
     def execute_work_unit(self, unit: ir.ExecutionUnit, output_columnar=None, ko=None) -> ResultSet:
         """Executor::executeWorkUnit with the out-of-slots retry of RelAlgExecutor::executeWorkUnit
@@ -775,7 +835,14 @@ class Executor:
             for t, e in enumerate(unit.target_exprs):
                 if isinstance(e, ir.ColumnRef) and e.type.kind == "dict":
                     dicts[t] = tables[e.table].columns[e.column].dictionary
-            if prep["out"].numel() > self.compact_threshold_bytes:
+            if unit.order_by:
+                # ORDER BY [LIMIT]: compact, sort and cut on the device; only the rows of the answer travel
+                cols, n = self.compact_on_device(pq, prep["out"], to_host=False)
+                order = ResultSet(pq, np.zeros(0, dtype=np.uint8), dicts).order_entries()
+                cells = self.sort_on_device(cols, n, order, unit.limit).cpu().numpy()
+                rs = ResultSet.from_compact(pq, cells, dicts)
+                rs.sorted_on_device = True
+            elif prep["out"].numel() > self.compact_threshold_bytes:
                 # large (baseline-hash) buffers: drop the empty entries and finalise AVG on the device, copy rows only
                 rs = ResultSet.from_compact(pq, self.compact_on_device(pq, prep["out"]), dicts)
             else:

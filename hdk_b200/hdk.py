@@ -100,9 +100,11 @@ class AggNode:
 
     def sort(self, *fields) -> "AggNode":
         order = []
-        for f in fields:
-            name, desc = (f, False) if isinstance(f, str) else (f[0], str(f[1]).lower().startswith("desc"))
-            order.append((self.unit.target_names.index(name), desc))
+        for f in fields:   # "x" | ("x", "asc" | "desc"[, "first" | "last"]); NULLs last by default (python/pyhdk/hdk.py:1687-1689)
+            f = (f,) if isinstance(f, str) else tuple(f)
+            desc = len(f) > 1 and str(f[1]).lower().startswith("desc")
+            nulls_first = len(f) > 2 and str(f[2]).lower() == "first"
+            order.append((self.unit.target_names.index(f[0]), desc, nulls_first))
         u = self.unit
         return AggNode(self._hdk, ir.ExecutionUnit(u.table, u.groupby_exprs, u.target_exprs, u.target_names, u.quals,
                                                    u.joins, order, u.limit))

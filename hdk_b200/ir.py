@@ -386,5 +386,5 @@ class ExecutionUnit:
     target_names: List[str]
     quals: List[Expr] = field(default_factory=list)
     joins: List[JoinSpec] = field(default_factory=list)
-    order_by: List[tuple] = field(default_factory=list)   # (name, desc)
+    order_by: List[tuple] = field(default_factory=list)   # (target index, is_desc, nulls_first) — hdk::ir::OrderEntry
     limit: Optional[int] = None

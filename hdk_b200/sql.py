@@ -26,7 +26,7 @@ _TOKEN = re.compile(r"""
 
 _KEYWORDS = {"select", "from", "where", "group", "by", "order", "limit", "join", "inner", "on", "and", "or",
              "not", "as", "is", "null", "asc", "desc", "extract", "year", "cast", "date", "timestamp",
-             "between", "count", "sum", "min", "max", "avg", "case", "when", "then", "else", "end",
+             "between", "count", "sum", "min", "max", "avg", "case", "when", "then", "else", "end", "nulls", "first", "last",
              # recognised only to be rejected: they must never be taken for a table alias or a column name
              "in", "left", "right", "full", "outer", "cross", "natural", "having", "distinct", "over", "union", "using"}
 
@@ -385,7 +385,15 @@ class _Parser:
                     desc = True
                 else:
                     self.accept("kw", "asc")
-                order.append((key, desc))
+                # Calcite's default (RelFieldCollation): NULLs sort high — last when ascending, first when descending
+                nulls_first = desc
+                if self.accept("kw", "nulls"):
+                    if self.accept("kw", "last"):
+                        nulls_first = False
+                    else:
+                        self.eat("kw", "first")
+                        nulls_first = True
+                order.append((key, desc, nulls_first))
                 if not self.accept("op", ","):
                     break
         limit = None
@@ -422,7 +430,7 @@ class _Parser:
             if n is None:
                 n = e.column if isinstance(e, ir.ColumnRef) else f"EXPR${i}"
             final_names.append(n)
-        order = [(final_names.index(k) if isinstance(k, str) else k, d) for k, d in order]
+        order = [(final_names.index(k) if isinstance(k, str) else k, d, nf) for k, d, nf in order]
         return ir.ExecutionUnit(table, groupby, targets, final_names, quals, joins, order, limit)
 
     def _table_ref(self):

@@ -576,6 +576,37 @@ HDK_B200_API int hdk_b200_compact_result(const hdk_b200_plan* plan, const hdk_b2
                             uint64_t* row_count /* DEVICE */, void* stream);
 
 /* ============================================================================
+ * ORDER BY / LIMIT over the compacted result, on the device ("next" row: top-k / ORDER BY over aggregated results).
+ * Replaces sortResultSet (QE/ResultSetSort.cpp:752-851): the permutation it leaves in the ResultSet
+ * (ResultSet::setPermutationBuffer) is computed here, over the dense rows hdk_b200_compact_result wrote.
+ * Order of one entry = ResultSetComparator::operator() (:333-470): NULLs before or after every value according to
+ * `nulls_first` whatever the direction, then (lhs < rhs) != is_desc; rows equal on every entry come in unspecified
+ * order (the reference uses std::sort / std::partial_sort).  Dictionary-encoded targets compare by string: pass the
+ * rank of each dictionary id in string order.  LIMIT n = the first n entries of the permutation
+ * (topPermutation, :504-520); hdk_b200_gather_rows then materialises those rows only.
+ * ==========================================================================*/
+typedef struct hdk_b200_order_entry {
+  int32_t column;       /* index into cols[] = tle_no - 1 (hdk::ir::OrderEntry) */
+  int32_t is_fp;        /* the cells are doubles (bits), else int64 */
+  int32_t type_width;   /* logical width of the target's type: selects the NULL sentinel compact_result wrote */
+  int32_t nullable;
+  int32_t is_desc;
+  int32_t nulls_first;
+  const int32_t* dict_rank; /* DEVICE int32[dict_size] or NULL */
+  int64_t dict_size;
+} hdk_b200_order_entry;
+
+HDK_B200_API size_t hdk_b200_sort_scratch_bytes(uint64_t n_rows);
+/* cols: HOST array [HDK_B200_MAX_TARGETS or fewer, indexed by order[i].column] of DEVICE int64[n_rows];
+ * permutation: DEVICE uint32[n_rows], receives the row ids in result order. */
+HDK_B200_API int hdk_b200_sort_permutation(const int64_t* const* cols, const hdk_b200_order_entry* order, int n_order,
+                                           uint64_t n_rows, uint32_t* permutation, void* scratch, size_t scratch_bytes,
+                                           void* stream);
+/* cols_out[c][i] = cols_in[c][permutation[i]] for i < n_out; cols_in / cols_out: HOST arrays [n_cols] of DEVICE pointers */
+HDK_B200_API int hdk_b200_gather_rows(const int64_t* const* cols_in, int64_t* const* cols_out, int n_cols,
+                                      const uint32_t* permutation, uint64_t n_out, void* stream);
+
+/* ============================================================================
  * Storage-side helper on the device ("next" row: ArrowStorage -> device residency).
  * Arrow fixed-width column data + validity bitmap, already copied to the device,
  * become the chunk format of the hot path in place: slots whose validity bit is 0

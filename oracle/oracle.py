@@ -181,3 +181,41 @@ def make_type_info(elem_sz, min_val, max_val, null_val, uses_bw_eq=False, transl
     ti.elem_sz, ti.min_val, ti.max_val, ti.null_val = elem_sz, min_val, max_val, null_val
     ti.uses_bw_eq, ti.translated_null_val, ti.column_type = int(uses_bw_eq), translated_null_val, column_type
     return ti
+
+
+# ---------------------------------------------------------------------------------------------
+# ORDER BY / LIMIT over decoded result rows (test infrastructure, like everything in this file)
+# ---------------------------------------------------------------------------------------------
+def result_set_less(order, cols, lhs, rhs):
+    """ResultSetComparator::operator() (QE/ResultSetSort.cpp:333-470) over decoded 8-byte result cells.
+    order: list of dicts {column, is_fp, type_width, nullable, is_desc, nulls_first, dictionary (list of str | None)};
+    cols[c][row] = int (NULL = the type's sentinel) or float (NULL = DBL_MIN / float(FLT_MIN))."""
+    import struct
+    for oe in order:
+        l, r = cols[oe["column"]][lhs], cols[oe["column"]][rhs]
+        if oe["is_fp"]:
+            null = struct.unpack("<f", struct.pack("<I", 0x00800000))[0] if oe["type_width"] == 4 else 2.2250738585072014e-308
+        else:
+            null = -(1 << (8 * oe["type_width"] - 1))
+        ln, rn = bool(oe["nullable"]) and l == null, bool(oe["nullable"]) and r == null
+        if ln and rn:                       # :410-413
+            continue
+        if ln:                              # :414-417
+            return bool(oe["nulls_first"])
+        if rn:                              # :418-421
+            return not oe["nulls_first"]
+        if oe.get("dictionary") is not None:  # :425-438: dictionary targets compare by string
+            l, r = oe["dictionary"][int(l)], oe["dictionary"][int(r)]
+        if l == r:                          # :440-442
+            continue
+        return (l < r) != bool(oe["is_desc"])   # :443-456
+    return False
+
+
+def sort_permutation(cols, n_rows, order, top_n=0):
+    """sortResultSet's generic path (QE/ResultSetSort.cpp:836-849): the permutation of all rows sorted with the
+    comparator, cut to top_n (topPermutation, :504-520).  Pure Python: small cases only."""
+    import functools
+    cmp = lambda a, b: -1 if result_set_less(order, cols, a, b) else (1 if result_set_less(order, cols, b, a) else 0)  # noqa: E731
+    perm = sorted(range(n_rows), key=functools.cmp_to_key(cmp))
+    return perm[:top_n] if top_n else perm

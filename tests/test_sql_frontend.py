@@ -22,7 +22,7 @@ def test_select_aliases_group_by_order_limit(st):
                   "GROUP BY k, y ORDER BY n DESC, k LIMIT 7", st.tables)
     assert u.table == "t" and u.target_names == ["k", "y", "n", "EXPR$3"] and u.limit == 7
     assert len(u.groupby_exprs) == 2 and isinstance(u.groupby_exprs[1], ir.ExtractYear if hasattr(ir, "ExtractYear") else object)
-    assert u.order_by == [(2, True), (0, False)]
+    assert u.order_by == [(2, True, True), (0, False, False)]    # Calcite default: NULLs high
     assert len(u.quals) >= 1
 
 
