@@ -65,7 +65,7 @@ def _bind(lib):
         "hdk_b200_region_scatter_to": (ci, [P, Q, KP, u32, vp, vp, vp, vp]),
         "hdk_b200_compact_result": (ci, [P, Q, vp, vp, vp, vp]),
         "hdk_b200_sort_scratch_bytes": (sz, [u64]),
-        "hdk_b200_sort_permutation": (ci, [C.POINTER(vp), C.POINTER(abi.OrderEntry), ci, u64, vp, vp, sz, vp]),
+        "hdk_b200_sort_permutation": (ci, [C.POINTER(vp), C.POINTER(abi.OrderEntry), ci, u64, u64, vp, C.POINTER(u64), vp, sz, vp]),
         "hdk_b200_gather_rows": (ci, [C.POINTER(vp), C.POINTER(vp), ci, vp, u64, vp]),
         "hdk_b200_init_chunk_stats_on_device": (ci, [vp, vp]),
         "hdk_b200_materialize_nulls_on_device": (ci, [vp, ci, ci, vp, i64, i64, vp, vp]),

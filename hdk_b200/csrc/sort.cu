@@ -208,6 +208,78 @@ __global__ void __launch_bounds__(256) sort_settle_kernel(SortBufs b) {
   for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < b.n; i += step) b.idx[0][i] = b.idx[1][i];
 }
 
+// --------------------------------------------------------------------------------------------- LIMIT prefilter
+// ORDER BY … LIMIT k over n >> k rows: only rows whose PRIMARY key is among the k smallest can be in the answer
+// (topPermutation keeps the k least rows, QE/ResultSetSort.cpp:504-520).  An MSD radix select finds the bucket that
+// holds the k-th smallest primary key — one histogram pass over the keys per digit, stopping as soon as the rows up to and
+// including that bucket are few — and the rows with key <= the bucket's upper bound (every tie included, the later
+// ORDER BY targets still decide among them) are compacted into the candidate list the LSD sort then runs on.
+struct SelectState {
+  unsigned long long prefix, mask;   // the digits fixed so far
+  unsigned long long k;              // rank still to find inside the current bucket (1-based)
+  unsigned long long threshold;      // result: candidates are the rows with key <= threshold
+  unsigned long long n_candidates;
+  unsigned int done;
+  unsigned int hist[256];
+};
+
+__global__ void __launch_bounds__(256) select_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n, const SortState* ss,
+                                                          SelectState* s, int pass) {
+  if (s->done || !digit_varies(ss, pass)) return;
+  __shared__ uint32_t bins[256];
+  bins[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned long long prefix = s->prefix, mask = s->mask;
+  const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += step) {
+    const uint64_t key = keys[i];
+    if ((key & mask) == prefix) atomicAdd(&bins[(key >> (8 * pass)) & 0xff], 1u);
+  }
+  __syncthreads();
+  if (bins[threadIdx.x]) atomicAdd(&s->hist[threadIdx.x], bins[threadIdx.x]);
+}
+
+__global__ void select_pick_kernel(const SortState* ss, SelectState* s, int pass, unsigned long long top_n, unsigned long long stop_at) {
+  if (threadIdx.x || s->done) return;
+  const unsigned long long digit_mask = 0xffull << (8 * pass);
+  if (!digit_varies(ss, pass)) {             // every key has the same digit here: it joins the prefix
+    s->prefix |= ss->key_or & digit_mask;
+    s->mask |= digit_mask;
+  } else {
+    unsigned long long cum = 0;
+    int d = 0;
+    for (; d < 255; ++d) {
+      if (cum + s->hist[d] >= s->k) break;
+      cum += s->hist[d];
+    }
+    const unsigned long long in_bucket = s->hist[d];
+    s->k -= cum;
+    s->prefix |= (unsigned long long)d << (8 * pass);
+    s->mask |= digit_mask;
+    for (int i = 0; i < 256; ++i) s->hist[i] = 0;
+    // rows before this bucket = top_n - k; stop refining once [everything up to and including the bucket] is small
+    if ((top_n - s->k) + in_bucket <= stop_at) s->done = 1;
+  }
+  if (pass == 0) s->done = 1;
+  if (s->done) s->threshold = s->prefix | ~s->mask;    // upper bound of the bucket
+}
+
+__global__ void __launch_bounds__(256) select_compact_kernel(const uint64_t* __restrict__ keys, uint64_t n, SelectState* s,
+                                                             uint32_t* __restrict__ rows_out) {
+  const unsigned long long thr = s->threshold;
+  const int lane = threadIdx.x & 31;
+  const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t base = blockIdx.x * uint64_t(blockDim.x); base < n; base += step) {   // whole warps iterate together
+    const uint64_t i = base + threadIdx.x;
+    const bool keep = i < n && keys[i] <= thr;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    unsigned long long wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(&s->n_candidates, (unsigned long long)__popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (keep) rows_out[wbase + __popc(m & ((1u << lane) - 1u))] = uint32_t(i);
+  }
+}
+
 struct GatherArgs {
   const int64_t* in[HDK_B200_MAX_TARGETS];
   int64_t* out[HDK_B200_MAX_TARGETS];
@@ -235,11 +307,42 @@ extern "C" {
 
 size_t hdk_b200_sort_scratch_bytes(uint64_t n_rows) {
   if (n_rows == 0) return 256;
-  return align256(n_rows * 8) * 2 + align256(n_rows * 4) + align256(size_t(256) * sort_ctas(n_rows) * 4) + 256;
+  return align256(n_rows * 8) * 2 + align256(n_rows * 4) + align256(size_t(256) * sort_ctas(n_rows) * 4) + 256 +
+         align256(sizeof(SelectState));
+}
+
+// the LSD sort of the rows listed in b.idx[0] (or of all rows, identity, when `identity`)
+static int sort_rows_lsd(SortBufs b, const int64_t* const* cols, const hdk_b200_order_entry* order, int n_order, bool identity,
+                         cudaStream_t st) {
+  const uint64_t chunks = (b.n + kSortChunk - 1) / kSortChunk;
+  b.n_ctas = sort_ctas(b.n);
+  b.per_cta = (chunks + b.n_ctas - 1) / b.n_ctas * kSortChunk;
+  const int flat_grid = int(std::min<uint64_t>(148 * 8, (b.n + 255) / 256));
+  for (int o = n_order - 1; o >= 0; --o) {       // LSD over the ORDER BY list: least significant target first
+    const hdk_b200_order_entry& oe = order[o];
+    KeyArgs k{cols[oe.column], oe.dict_rank, oe.dict_size, oe.is_fp, oe.type_width, oe.nullable, oe.is_desc, oe.nulls_first};
+    HB_CUDA(cudaMemsetAsync(&b.state->key_or, 0x00, 8, st));
+    HB_CUDA(cudaMemsetAsync(&b.state->key_and, 0xff, 8, st));
+    sort_keys_kernel<<<flat_grid, 256, 0, st>>>(k, b, identity && o == n_order - 1);
+    HB_LAUNCH_CHECK();
+    for (int pass = 0; pass < 8; ++pass) {
+      sort_hist_kernel<<<b.n_ctas, kSortThreads, 0, st>>>(b, pass);
+      HB_LAUNCH_CHECK();
+      sort_scan_kernel<<<1, 1024, 0, st>>>(b, pass);
+      HB_LAUNCH_CHECK();
+      sort_scatter_kernel<<<b.n_ctas, kSortThreads, 0, st>>>(b, pass);
+      HB_LAUNCH_CHECK();
+    }
+    sort_settle_kernel<<<flat_grid, 256, 0, st>>>(b);
+    HB_LAUNCH_CHECK();
+  }
+  return HDK_B200_OK;
 }
 
 int hdk_b200_sort_permutation(const int64_t* const* cols, const hdk_b200_order_entry* order, int n_order, uint64_t n_rows,
-                              uint32_t* permutation, void* scratch, size_t scratch_bytes, void* stream) {
+                              uint64_t top_n, uint32_t* permutation, uint64_t* n_sorted, void* scratch, size_t scratch_bytes,
+                              void* stream) {
+  if (n_sorted) *n_sorted = n_rows;
   if (!order || n_order < 1 || n_order > HDK_B200_MAX_TARGETS) { set_error("sort: bad order entry count"); return HDK_B200_E_INVALID; }
   if (n_rows >> 32) { set_error("sort: more than 2^32 rows"); return HDK_B200_E_UNSUPPORTED; }   // RowSortException, ResultSetSort.cpp:785-787
   if (n_rows == 0) return HDK_B200_OK;
@@ -258,32 +361,40 @@ int hdk_b200_sort_permutation(const int64_t* const* cols, const hdk_b200_order_e
   b.keys[1] = reinterpret_cast<uint64_t*>(p); p += align256(n_rows * 8);
   b.idx[0] = permutation;
   b.idx[1] = reinterpret_cast<uint32_t*>(p); p += align256(n_rows * 4);
-  b.n_ctas = sort_ctas(n_rows);
-  b.hist = reinterpret_cast<uint32_t*>(p); p += align256(size_t(256) * b.n_ctas * 4);
-  b.state = reinterpret_cast<SortState*>(p);
+  b.hist = reinterpret_cast<uint32_t*>(p); p += align256(size_t(256) * sort_ctas(n_rows) * 4);
+  b.state = reinterpret_cast<SortState*>(p); p += 256;
+  SelectState* sel = reinterpret_cast<SelectState*>(p);
   b.n = n_rows;
-  const uint64_t chunks = (n_rows + kSortChunk - 1) / kSortChunk;
-  b.per_cta = (chunks + b.n_ctas - 1) / b.n_ctas * kSortChunk;
-  const int flat_grid = int(std::min<uint64_t>(148 * 8, (n_rows + 255) / 256));
-  for (int o = n_order - 1; o >= 0; --o) {       // LSD over the ORDER BY list: least significant target first
-    const hdk_b200_order_entry& oe = order[o];
+  bool identity = true;
+  if (top_n && top_n <= n_rows / 8 && n_rows >= (1u << 16)) {
+    // LIMIT prefilter on the primary target: keys → radix select → candidate rows in idx[0]
+    const hdk_b200_order_entry& oe = order[0];
     KeyArgs k{cols[oe.column], oe.dict_rank, oe.dict_size, oe.is_fp, oe.type_width, oe.nullable, oe.is_desc, oe.nulls_first};
+    const int flat_grid = int(std::min<uint64_t>(148 * 8, (n_rows + 255) / 256));
     HB_CUDA(cudaMemsetAsync(&b.state->key_or, 0x00, 8, st));
     HB_CUDA(cudaMemsetAsync(&b.state->key_and, 0xff, 8, st));
-    sort_keys_kernel<<<flat_grid, 256, 0, st>>>(k, b, o == n_order - 1);
+    HB_CUDA(cudaMemsetAsync(sel, 0, sizeof(SelectState), st));
+    HB_CUDA(cudaMemcpyAsync(&sel->k, &top_n, 8, cudaMemcpyHostToDevice, st));
+    sort_keys_kernel<<<flat_grid, 256, 0, st>>>(k, b, 1);
     HB_LAUNCH_CHECK();
-    for (int pass = 0; pass < 8; ++pass) {
-      sort_hist_kernel<<<b.n_ctas, kSortThreads, 0, st>>>(b, pass);
+    const unsigned long long stop_at = std::max<unsigned long long>(4 * top_n, 1u << 15);
+    for (int pass = 7; pass >= 0; --pass) {
+      select_hist_kernel<<<flat_grid, 256, 0, st>>>(b.keys[0], n_rows, b.state, sel, pass);
       HB_LAUNCH_CHECK();
-      sort_scan_kernel<<<1, 1024, 0, st>>>(b, pass);
-      HB_LAUNCH_CHECK();
-      sort_scatter_kernel<<<b.n_ctas, kSortThreads, 0, st>>>(b, pass);
+      select_pick_kernel<<<1, 32, 0, st>>>(b.state, sel, pass, top_n, stop_at);
       HB_LAUNCH_CHECK();
     }
-    sort_settle_kernel<<<flat_grid, 256, 0, st>>>(b);
+    select_compact_kernel<<<flat_grid, 256, 0, st>>>(b.keys[0], n_rows, sel, b.idx[0]);
     HB_LAUNCH_CHECK();
+    unsigned long long m = 0;   // the candidate count sizes the sort's grids: the one synchronisation of this call
+    HB_CUDA(cudaMemcpyAsync(&m, &sel->n_candidates, 8, cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaStreamSynchronize(st));
+    if (m < top_n || m > n_rows) { set_error("sort: LIMIT prefilter kept %llu of %llu rows for LIMIT %llu", m, (unsigned long long)n_rows, (unsigned long long)top_n); return HDK_B200_E_CUDA; }
+    b.n = m;
+    identity = false;
+    if (n_sorted) *n_sorted = m;
   }
-  return HDK_B200_OK;
+  return sort_rows_lsd(b, cols, order, n_order, identity, st);
 }
 
 int hdk_b200_gather_rows(const int64_t* const* cols_in, int64_t* const* cols_out, int n_cols, const uint32_t* permutation,

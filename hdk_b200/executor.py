@@ -805,8 +805,9 @@ class Executor:
         sb = self.lib.hdk_b200_sort_scratch_bytes(n_rows)
         scratch = torch.empty(sb, dtype=torch.uint8, device=self.ctx.device)
         in_ptrs = (C.c_void_p * abi.MAX_TARGETS)(*[cols[t].data_ptr() for t in range(T)])
-        _lib.check(self.lib.hdk_b200_sort_permutation(in_ptrs, entries, len(order), n_rows, perm.data_ptr(), scratch.data_ptr(), sb,
-                                                      self.ctx.stream_ptr()), "sort_permutation")
+        _lib.check(self.lib.hdk_b200_sort_permutation(in_ptrs, entries, len(order), n_rows, 0 if limit is None else n_out,
+                                                      perm.data_ptr(), None, scratch.data_ptr(), sb, self.ctx.stream_ptr()),
+                   "sort_permutation")
         out_ptrs = (C.c_void_p * T)(*[out[t].data_ptr() for t in range(T)])
         _lib.check(self.lib.hdk_b200_gather_rows(in_ptrs, out_ptrs, T, perm.data_ptr(), n_out, self.ctx.stream_ptr()), "gather_rows")
         return out

@@ -598,10 +598,14 @@ typedef struct hdk_b200_order_entry {
 
 HDK_B200_API size_t hdk_b200_sort_scratch_bytes(uint64_t n_rows);
 /* cols: HOST array [HDK_B200_MAX_TARGETS or fewer, indexed by order[i].column] of DEVICE int64[n_rows];
- * permutation: DEVICE uint32[n_rows], receives the row ids in result order. */
+ * permutation: DEVICE uint32[n_rows], receives the row ids in result order.
+ * top_n: 0 = order all rows.  > 0 = the caller will use the first top_n entries only (LIMIT): when top_n << n_rows the rows
+ * that cannot be among them are dropped before sorting (radix select on the first ORDER BY target, every tie kept), and
+ * *n_sorted (HOST, optional) receives how many leading entries of `permutation` are valid (top_n <= *n_sorted <= n_rows).
+ * That path reads one counter back and therefore synchronises `stream`; without it the call is asynchronous. */
 HDK_B200_API int hdk_b200_sort_permutation(const int64_t* const* cols, const hdk_b200_order_entry* order, int n_order,
-                                           uint64_t n_rows, uint32_t* permutation, void* scratch, size_t scratch_bytes,
-                                           void* stream);
+                                           uint64_t n_rows, uint64_t top_n, uint32_t* permutation, uint64_t* n_sorted,
+                                           void* scratch, size_t scratch_bytes, void* stream);
 /* cols_out[c][i] = cols_in[c][permutation[i]] for i < n_out; cols_in / cols_out: HOST arrays [n_cols] of DEVICE pointers */
 HDK_B200_API int hdk_b200_gather_rows(const int64_t* const* cols_in, int64_t* const* cols_out, int n_cols,
                                       const uint32_t* permutation, uint64_t n_out, void* stream);

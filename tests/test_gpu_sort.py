@@ -12,7 +12,7 @@ from tests.test_sort import DBL_NULL, ORDERS, key_rows, order_entries, sort_case
 pytestmark = pytest.mark.gpu
 
 
-def device_sort(torch, cols, entries, n, limit=None):
+def device_sort(torch, cols, entries, n, limit=None, top_n=0):
     L = _lib.lib()
     dev = torch.device("cuda", 0)
     dcols = [torch.from_numpy(np.ascontiguousarray(c).view(np.int64)).to(dev) for c in cols]
@@ -31,10 +31,13 @@ def device_sort(torch, cols, entries, n, limit=None):
     sb = L.hdk_b200_sort_scratch_bytes(n)
     scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
     ptrs = (C.c_void_p * abi.MAX_TARGETS)(*[c.data_ptr() for c in dcols])
-    _lib.check(L.hdk_b200_sort_permutation(ptrs, oes, len(entries), n, perm.data_ptr(), scratch.data_ptr(), sb, None), "sort")
+    n_sorted = C.c_uint64(0)
+    _lib.check(L.hdk_b200_sort_permutation(ptrs, oes, len(entries), n, top_n, perm.data_ptr(), C.byref(n_sorted), scratch.data_ptr(), sb,
+                                           None), "sort")
     torch.cuda.synchronize()
+    assert max(top_n, 0) <= n_sorted.value <= n and (top_n or n_sorted.value == n)
     if limit is None:
-        return perm[:n], dcols
+        return perm[:n_sorted.value], dcols
     n_out = min(limit, n)
     out = [torch.empty(n_out, dtype=torch.int64, device=dev) for _ in dcols]
     optrs = (C.c_void_p * len(dcols))(*[o.data_ptr() for o in out])
@@ -125,10 +128,20 @@ def test_device_sort_large_sortedness_and_permutation():
     ptrs = (C.c_void_p * abi.MAX_TARGETS)(col.data_ptr())
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    _lib.check(L.hdk_b200_sort_permutation(ptrs, oe, 1, n, perm.data_ptr(), scratch.data_ptr(), sb, None), "sort")
+    _lib.check(L.hdk_b200_sort_permutation(ptrs, oe, 1, n, 0, perm.data_ptr(), None, scratch.data_ptr(), sb, None), "sort")
     t1.record()
     torch.cuda.synchronize()
     print(f"sorted {n} rows in {t0.elapsed_time(t1):.2f} ms")
+    # LIMIT 100 of the same order through the prefilter: same leading rows (the keys are distinct w.h.p., ties compare equal)
+    top = torch.empty(n, dtype=torch.int32, device=dev)
+    n_sorted = C.c_uint64(0)
+    t0.record()
+    _lib.check(L.hdk_b200_sort_permutation(ptrs, oe, 1, n, 100, top.data_ptr(), C.byref(n_sorted), scratch.data_ptr(), sb, None), "top")
+    t1.record()
+    torch.cuda.synchronize()
+    print(f"top-100 of {n} rows in {t0.elapsed_time(t1):.2f} ms ({n_sorted.value} candidates)")
+    assert 100 <= n_sorted.value < n // 8
+    assert torch.equal(col[top[:100].long()], col[perm[:100].long()])
     del scratch
     s = col[perm.long()]
     assert bool((s[:-1] >= s[1:]).all())                                           # descending
@@ -141,7 +154,7 @@ def test_device_sort_large_sortedness_and_permutation():
 def test_order_by_limit_through_the_facade_vs_sqlite(oracle_mod):
     """hdk.sql with ORDER BY … [NULLS FIRST|LAST] LIMIT: compact → sort → gather on the device; rows vs SQLite in order."""
     import pyarrow as pa
-    import hdk_b200
+    import hdk_b200.hdk as hdk_mod
     from tests import util
     rng = np.random.default_rng(12)
     n = 20_000
@@ -149,7 +162,7 @@ def test_order_by_limit_through_the_facade_vs_sqlite(oracle_mod):
                   "g": rng.integers(0, 5, n).astype(np.int16),
                   "v": pa.array(rng.integers(-50, 50, n).astype(np.int64), mask=rng.random(n) < 0.3),
                   "s": pa.array(rng.choice(["kiwi", "apple", "fig", "banana"], n))})
-    hdk = hdk_b200.init()
+    hdk = hdk_mod.init()
     hdk.import_arrow(t, "t", fragment_size=3000)
     queries = [
         "SELECT k, COUNT(*) AS n, SUM(v) AS sv FROM t GROUP BY k ORDER BY n DESC, k ASC NULLS FIRST LIMIT 17",
@@ -163,3 +176,19 @@ def test_order_by_limit_through_the_facade_vs_sqlite(oracle_mod):
         got = [tuple(r.values()) for r in res.to_arrow().to_pylist()]
         exp = util.sqlite_rows({"t": t}, q, 0)
         util.assert_rows_equal(got, exp, rel=1e-9)
+
+
+@pytest.mark.parametrize("order", [ORDERS[1], ORDERS[5], ORDERS[9], ORDERS[13], ORDERS[14]])
+@pytest.mark.parametrize("top_n", [1, 10, 5000])
+def test_limit_prefilter_keeps_every_row_of_the_answer(oracle_mod, order, top_n):
+    """LIMIT through the radix-select prefilter (n >= 65536, top_n <= n / 8): the first top_n ORDER BY tuples equal the
+    full sort's, with heavy ties on the primary target (|values| ~ 11, NULLs) so the threshold bucket holds many rows."""
+    import torch
+    cols, meta = sort_case(n=100_000, seed=21)
+    n = len(cols[0])
+    entries = order_entries(order, meta)
+    full, _ = device_sort(torch, cols, entries, n)
+    part, _ = device_sort(torch, cols, entries, n, top_n=top_n)
+    full, part = full.cpu().numpy().astype(np.int64), part.cpu().numpy().astype(np.int64)
+    assert len(np.unique(part)) == len(part)
+    assert key_rows(cols, meta, order, part[:top_n]) == key_rows(cols, meta, order, full[:top_n])
