@@ -13,6 +13,7 @@
 // the OR / AND of the keys, reduced while they are generated) cost nothing, so a COUNT column below 2^24 takes three
 // passes, not eight.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -26,12 +27,13 @@ constexpr int kSortMaxCtas = 148 * 4;
 
 struct SortState {
   unsigned long long key_or, key_and;   // over all keys of the current ORDER BY target
+  unsigned int totals[8][256];          // per radix pass: rows per digit over all CTAs
 };
 
 struct SortBufs {
   uint64_t* keys[2];
   uint32_t* idx[2];      // idx[0] = the caller's permutation buffer
-  uint32_t* hist;        // [256][n_ctas], digit-major
+  uint32_t* hist;        // [n_ctas][256]
   SortState* state;
   uint64_t n;
   uint32_t n_ctas;
@@ -100,61 +102,73 @@ __global__ void __launch_bounds__(256) sort_keys_kernel(const KeyArgs k, SortBuf
 }
 
 // --------------------------------------------------------------------------------------------- one radix pass
+// rows per digit of this CTA's range → hist[cta][digit]; and, summed over the CTAs, → state->totals[pass][digit]
 __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(SortBufs b, int pass) {
   if (!digit_varies(b.state, pass)) return;
   __shared__ uint32_t bins[256];
   bins[threadIdx.x] = 0;
   __syncthreads();
-  const uint64_t* src = b.keys[cur_before(b.state, pass)];
+  const uint64_t* __restrict__ src = cur_before(b.state, pass) ? b.keys[1] : b.keys[0];
   const uint64_t lo = blockIdx.x * b.per_cta, hi = min(b.n, lo + b.per_cta);
-  for (uint64_t i = lo + threadIdx.x; i < hi; i += kSortThreads) atomicAdd(&bins[(src[i] >> (8 * pass)) & 0xff], 1u);
-  __syncthreads();
-  b.hist[uint64_t(threadIdx.x) * b.n_ctas + blockIdx.x] = bins[threadIdx.x];
-}
-
-// exclusive scan of the digit-major histogram: entry [d][cta] becomes the first output position of CTA cta's digit d
-__global__ void __launch_bounds__(1024) sort_scan_kernel(SortBufs b, int pass) {
-  if (!digit_varies(b.state, pass)) return;
-  __shared__ uint32_t part[1024];
-  const uint32_t total = 256u * b.n_ctas;
-  const uint32_t per = (total + 1023u) / 1024u;
-  const uint32_t lo = min(total, threadIdx.x * per), hi = min(total, lo + per);
-  uint32_t s = 0;
-  for (uint32_t i = lo; i < hi; ++i) s += b.hist[i];
-  part[threadIdx.x] = s;
-  __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {           // Hillis-Steele inclusive scan of the 1024 partial sums
-    const uint32_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
-    __syncthreads();
-    part[threadIdx.x] += v;
-    __syncthreads();
+  const int sh = 8 * pass;
+  uint64_t i = lo + threadIdx.x;
+  for (; i + 3 * kSortThreads < hi; i += 4 * kSortThreads) {      // four independent loads in flight per thread
+    const uint64_t k0 = src[i], k1 = src[i + kSortThreads], k2 = src[i + 2 * kSortThreads], k3 = src[i + 3 * kSortThreads];
+    atomicAdd(&bins[(k0 >> sh) & 0xff], 1u);
+    atomicAdd(&bins[(k1 >> sh) & 0xff], 1u);
+    atomicAdd(&bins[(k2 >> sh) & 0xff], 1u);
+    atomicAdd(&bins[(k3 >> sh) & 0xff], 1u);
   }
-  uint32_t run = part[threadIdx.x] - s;
-  for (uint32_t i = lo; i < hi; ++i) {
-    const uint32_t c = b.hist[i];
-    b.hist[i] = run;
-    run += c;
-  }
+  for (; i < hi; i += kSortThreads) atomicAdd(&bins[(src[i] >> sh) & 0xff], 1u);
+  __syncthreads();
+  const uint32_t c = bins[threadIdx.x];
+  b.hist[uint64_t(blockIdx.x) * 256 + threadIdx.x] = c;
+  if (c) atomicAdd(&b.state->totals[pass][threadIdx.x], c);
 }
 
 // Stable scatter.  A CTA owns a contiguous range and walks it chunk by chunk; inside a chunk warp w owns the
-// elements [w*256, (w+1)*256) in (item, lane) order.  Rank of an element = CTA's running offset of its digit
-// + elements of the same digit in earlier warps of the chunk + earlier elements of the same digit in its own warp.
+// elements [w*256, (w+1)*256) in (item, lane) order.  Output position of an element = rows of smaller digits (all
+// CTAs) + rows of its digit in earlier CTAs + in earlier chunks of this CTA + in earlier warps of the chunk + earlier
+// elements of the same digit in its own warp (lanes with equal digits found with one ballot per digit bit).
+// kStaged: the chunk is first regrouped by digit in shared memory and written out run by run, so that neighbouring
+// threads write neighbouring addresses instead of 8-byte pieces of 256 different streams.
+template <bool kStaged>
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortBufs b, int pass) {
   if (!digit_varies(b.state, pass)) return;
   __shared__ uint32_t cnt[kSortWarps][257];     // [.][256] collects the out-of-range lanes of the last chunk
-  __shared__ uint32_t off[256];
+  __shared__ uint32_t off[256];                 // next output position of each digit for this CTA
+  __shared__ uint32_t scan[256];
+  __shared__ uint64_t skey[kStaged ? kSortChunk : 1];
+  __shared__ uint32_t srow[kStaged ? kSortChunk : 1];
   const int cur = cur_before(b.state, pass);
-  const uint64_t* __restrict__ ksrc = b.keys[cur];
-  const uint32_t* __restrict__ isrc = b.idx[cur];
-  uint64_t* __restrict__ kdst = b.keys[cur ^ 1];
-  uint32_t* __restrict__ idst = b.idx[cur ^ 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t* __restrict__ ksrc = cur ? b.keys[1] : b.keys[0];
+  const uint32_t* __restrict__ isrc = cur ? b.idx[1] : b.idx[0];
+  uint64_t* __restrict__ kdst = cur ? b.keys[0] : b.keys[1];
+  uint32_t* __restrict__ idst = cur ? b.idx[0] : b.idx[1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned lt = (1u << lane) - 1u;
-  off[threadIdx.x] = b.hist[uint64_t(threadIdx.x) * b.n_ctas + blockIdx.x];
+  const int sh = 8 * pass;
+  {
+    uint32_t before = 0;                        // rows of digit `tid` in the CTAs ahead of this one (coalesced rows of 1 KB)
+    uint32_t c = 0;
+    for (; c + 4 <= blockIdx.x; c += 4)
+      before += b.hist[uint64_t(c) * 256 + tid] + b.hist[uint64_t(c + 1) * 256 + tid] + b.hist[uint64_t(c + 2) * 256 + tid] +
+                b.hist[uint64_t(c + 3) * 256 + tid];
+    for (; c < blockIdx.x; ++c) before += b.hist[uint64_t(c) * 256 + tid];
+    const uint32_t total = b.state->totals[pass][tid];
+    scan[tid] = total;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {         // inclusive scan over the digits
+      const uint32_t v = tid >= d ? scan[tid - d] : 0;
+      __syncthreads();
+      scan[tid] += v;
+      __syncthreads();
+    }
+    off[tid] = scan[tid] - total + before;
+  }
   const uint64_t lo = blockIdx.x * b.per_cta, hi = min(b.n, lo + b.per_cta);
   for (uint64_t base = lo; base < hi; base += kSortChunk) {
-    for (int i = threadIdx.x; i < kSortWarps * 257; i += kSortThreads) (&cnt[0][0])[i] = 0;
+    for (int i = tid; i < kSortWarps * 257; i += kSortThreads) (&cnt[0][0])[i] = 0;
     __syncthreads();
     uint64_t key[kSortItems];
     uint32_t row[kSortItems], rank[kSortItems];
@@ -166,38 +180,89 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortBufs b, 
       const bool ok = i < hi;
       key[j] = ok ? ksrc[i] : 0;
       row[j] = ok ? isrc[i] : 0;
-      dig[j] = ok ? int((key[j] >> (8 * pass)) & 0xff) : 256;
+      dig[j] = ok ? int((key[j] >> sh) & 0xff) : 256;
     }
 #pragma unroll
     for (int j = 0; j < kSortItems; ++j) {
-      const unsigned peers = __match_any_sync(0xffffffffu, dig[j]);
-      rank[j] = cnt[warp][dig[j]] + __popc(peers & lt);
-      __syncwarp();
-      if ((peers & lt) == 0) cnt[warp][dig[j]] += __popc(peers);
+      const int d = dig[j];
+      unsigned peers = __ballot_sync(0xffffffffu, d < 256);
+      if (d >= 256) peers = ~peers;
+#pragma unroll
+      for (int bit = 0; bit < 8; ++bit) {
+        const unsigned m = __ballot_sync(0xffffffffu, (d >> bit) & 1);
+        peers &= ((d >> bit) & 1) ? m : ~m;
+      }
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader) {
+        old = cnt[warp][d];
+        cnt[warp][d] = old + __popc(peers);
+      }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      rank[j] = old + __popc(peers & lt);
       __syncwarp();
     }
     __syncthreads();
-    {
-      const int d = threadIdx.x;     // 256 threads = 256 digits
-      uint32_t run = off[d];
+    if constexpr (!kStaged) {
+      uint32_t run = off[tid];                  // 256 threads = 256 digits
 #pragma unroll
       for (int w = 0; w < kSortWarps; ++w) {
-        const uint32_t c = cnt[w][d];
-        cnt[w][d] = run;
+        const uint32_t c = cnt[w][tid];
+        cnt[w][tid] = run;
         run += c;
       }
-      off[d] = run;
-    }
-    __syncthreads();
+      off[tid] = run;
+      __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kSortItems; ++j) {
-      if (dig[j] < 256) {
-        const uint32_t pos = cnt[warp][dig[j]] + rank[j];
-        kdst[pos] = key[j];
-        idst[pos] = row[j];
+      for (int j = 0; j < kSortItems; ++j) {
+        if (dig[j] < 256) {
+          const uint32_t pos = cnt[warp][dig[j]] + rank[j];
+          kdst[pos] = key[j];
+          idst[pos] = row[j];
+        }
       }
+      __syncthreads();
+    } else {
+      // positions inside the chunk: digits in order, inside a digit warps in order
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t c = cnt[w][tid];
+        cnt[w][tid] = run;                      // rows of digit tid in earlier warps of the chunk
+        run += c;
+      }
+      scan[tid] = run;                          // rows of digit tid in the chunk
+      __syncthreads();
+      for (int d = 1; d < 256; d <<= 1) {
+        const uint32_t v = tid >= d ? scan[tid - d] : 0;
+        __syncthreads();
+        scan[tid] += v;
+        __syncthreads();
+      }
+      const uint32_t first = scan[tid] - run;   // chunk slot of digit tid's first row
+      __syncthreads();
+      scan[tid] = first;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kSortItems; ++j) {
+        if (dig[j] < 256) {
+          const uint32_t slot = scan[dig[j]] + cnt[warp][dig[j]] + rank[j];
+          skey[slot] = key[j];
+          srow[slot] = row[j];
+        }
+      }
+      __syncthreads();
+      const uint32_t in_chunk = uint32_t(min(uint64_t(kSortChunk), hi - base));
+      for (uint32_t slot = tid; slot < in_chunk; slot += kSortThreads) {
+        const uint64_t k = skey[slot];
+        const int d = int((k >> sh) & 0xff);
+        const uint32_t pos = off[d] + (slot - scan[d]);
+        kdst[pos] = k;
+        idst[pos] = srow[slot];
+      }
+      __syncthreads();
+      off[tid] += run;
     }
-    __syncthreads();
   }
 }
 
@@ -307,8 +372,8 @@ extern "C" {
 
 size_t hdk_b200_sort_scratch_bytes(uint64_t n_rows) {
   if (n_rows == 0) return 256;
-  return align256(n_rows * 8) * 2 + align256(n_rows * 4) + align256(size_t(256) * sort_ctas(n_rows) * 4) + 256 +
-         align256(sizeof(SelectState));
+  return align256(n_rows * 8) * 2 + align256(n_rows * 4) + align256(size_t(256) * sort_ctas(n_rows) * 4) +
+         align256(sizeof(SortState)) + align256(sizeof(SelectState));
 }
 
 // the LSD sort of the rows listed in b.idx[0] (or of all rows, identity, when `identity`)
@@ -318,19 +383,19 @@ static int sort_rows_lsd(SortBufs b, const int64_t* const* cols, const hdk_b200_
   b.n_ctas = sort_ctas(b.n);
   b.per_cta = (chunks + b.n_ctas - 1) / b.n_ctas * kSortChunk;
   const int flat_grid = int(std::min<uint64_t>(148 * 8, (b.n + 255) / 256));
+  static const bool staged = [] { const char* e = getenv("HDK_B200_SORT_STAGED"); return e ? atoi(e) != 0 : true; }();   // tuning hook
   for (int o = n_order - 1; o >= 0; --o) {       // LSD over the ORDER BY list: least significant target first
     const hdk_b200_order_entry& oe = order[o];
     KeyArgs k{cols[oe.column], oe.dict_rank, oe.dict_size, oe.is_fp, oe.type_width, oe.nullable, oe.is_desc, oe.nulls_first};
-    HB_CUDA(cudaMemsetAsync(&b.state->key_or, 0x00, 8, st));
+    HB_CUDA(cudaMemsetAsync(b.state, 0x00, sizeof(SortState), st));
     HB_CUDA(cudaMemsetAsync(&b.state->key_and, 0xff, 8, st));
     sort_keys_kernel<<<flat_grid, 256, 0, st>>>(k, b, identity && o == n_order - 1);
     HB_LAUNCH_CHECK();
     for (int pass = 0; pass < 8; ++pass) {
       sort_hist_kernel<<<b.n_ctas, kSortThreads, 0, st>>>(b, pass);
       HB_LAUNCH_CHECK();
-      sort_scan_kernel<<<1, 1024, 0, st>>>(b, pass);
-      HB_LAUNCH_CHECK();
-      sort_scatter_kernel<<<b.n_ctas, kSortThreads, 0, st>>>(b, pass);
+      if (staged) sort_scatter_kernel<true><<<b.n_ctas, kSortThreads, 0, st>>>(b, pass);
+      else sort_scatter_kernel<false><<<b.n_ctas, kSortThreads, 0, st>>>(b, pass);
       HB_LAUNCH_CHECK();
     }
     sort_settle_kernel<<<flat_grid, 256, 0, st>>>(b);
@@ -362,7 +427,7 @@ int hdk_b200_sort_permutation(const int64_t* const* cols, const hdk_b200_order_e
   b.idx[0] = permutation;
   b.idx[1] = reinterpret_cast<uint32_t*>(p); p += align256(n_rows * 4);
   b.hist = reinterpret_cast<uint32_t*>(p); p += align256(size_t(256) * sort_ctas(n_rows) * 4);
-  b.state = reinterpret_cast<SortState*>(p); p += 256;
+  b.state = reinterpret_cast<SortState*>(p); p += align256(sizeof(SortState));
   SelectState* sel = reinterpret_cast<SelectState*>(p);
   b.n = n_rows;
   bool identity = true;
