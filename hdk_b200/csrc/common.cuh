@@ -31,10 +31,12 @@ int sm_count();
 // ---------------------------------------------------------------------------------------
 // device plan: the C-ABI plan lowered to a compact, kernel-parameter-sized form
 // ---------------------------------------------------------------------------------------
+constexpr uint8_t kAuxInQual = 0x80;   // errors of such a node are raised whether or not the row passes the filter
+
 struct DExpr {          // 16 bytes
   uint8_t op;           // hdk_b200_op
   int8_t a, b;          // operand nodes (OP_COL: table, column)
-  uint8_t aux;
+  uint8_t aux;          // bit 0: the ABI's aux (date-in-days column / checked arithmetic); bit 7 (kAuxInQual): part of a filter qual
   uint8_t kind, width, nullable;  // result type
   uint8_t guard;        // 0, or 1 + the node that must be true for this one to be evaluated (inside a CASE arm)
   union {

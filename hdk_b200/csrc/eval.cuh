@@ -57,7 +57,7 @@ __device__ __forceinline__ V eval_node(const DPlan& p, const DExpr& e, const V* 
         r.f = pw == 4 ? double(__uint_as_float(uint32_t(raw))) : __longlong_as_double(int64_t(raw));
       } else {
         int64_t v = pw == 1 ? int64_t(int8_t(raw)) : pw == 2 ? int64_t(int16_t(raw)) : pw == 4 ? int64_t(int32_t(raw)) : int64_t(raw);
-        if (e.aux == 1) v = (v == int_null_of(pw)) ? int_null_of(e.width) : v * 86400;
+        if (e.aux & 1) v = (v == int_null_of(pw)) ? int_null_of(e.width) : v * 86400;
         r.i = v;
       }
       break;
@@ -104,7 +104,10 @@ __device__ __forceinline__ V eval_node(const DPlan& p, const DExpr& e, const V* 
     case HDK_B200_OP_UMINUS: {
       const DExpr& ta = p.exprs[e.a];
       if (v_is_null(ta, vals[e.a])) { r = v_null(e); break; }
-      if (e.kind == HDK_B200_FP) r.f = -vals[e.a].f; else r.i = resize_int(-vals[e.a].i, e.width);
+      if (e.kind == HDK_B200_FP) { r.f = -vals[e.a].f; break; }
+      // operand == type minimum raises (codegenUMinus, QE/ArithmeticIR.cpp:782-811); a nullable minimum was NULL above
+      if (vals[e.a].i == int_null_of(e.width)) { err = HDK_B200_ERR_OVERFLOW_OR_UNDERFLOW; break; }
+      r.i = resize_int(-vals[e.a].i, e.width);
       break;
     }
     case HDK_B200_OP_CAST: {
@@ -119,6 +122,11 @@ __device__ __forceinline__ V eval_node(const DPlan& p, const DExpr& e, const V* 
       } else if (e.kind == HDK_B200_FP) {
         r.f = e.width == 4 ? double(float(a.f)) : a.f;
       } else {
+        // narrowing integer cast: v > max or v <= min (= the NULL sentinel) of the target raises (QE/CastIR.cpp:405-462)
+        if (ta.width > e.width) {
+          const int64_t mx = (int64_t(1) << (8 * e.width - 1)) - 1;
+          if (a.i > mx || a.i <= -mx - 1) { err = HDK_B200_ERR_OVERFLOW_OR_UNDERFLOW; break; }
+        }
         r.i = resize_int(a.i, e.width);
       }
       break;

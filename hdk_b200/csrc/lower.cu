@@ -142,6 +142,21 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
   for (int i = 0; i < plan->n_filters; ++i) {
     if (plan->filters[i] < 0 || plan->filters[i] >= plan->n_exprs) { set_error("bad filter node"); return HDK_B200_E_INVALID; }
     p.filters[i] = int8_t(plan->filters[i]);
+    p.exprs[p.filters[i]].aux |= kAuxInQual;
+  }
+  // Everything a qual is made of: the reference generates the quals ahead of the filter branch and a failed check returns
+  // from the row function at once (ArithmeticIR.cpp `CreateRet(ERR_…)`), so those errors do not depend on the row passing;
+  // keys and targets live inside the filter-true block (QE/RowFuncBuilder.cpp:400-513).
+  for (int i = plan->n_exprs - 1; i >= 0; --i) {
+    const DExpr& d = p.exprs[i];
+    if (!(d.aux & kAuxInQual)) continue;
+    if (d.guard) p.exprs[d.guard - 1].aux |= kAuxInQual;
+    if (d.op == HDK_B200_OP_COL || d.op == HDK_B200_OP_CONST) continue;
+    p.exprs[d.a].aux |= kAuxInQual;
+    const bool unary = d.op == HDK_B200_OP_CAST || d.op == HDK_B200_OP_EXTRACT_YEAR || d.op == HDK_B200_OP_NOT ||
+                       d.op == HDK_B200_OP_IS_NULL || d.op == HDK_B200_OP_UMINUS;
+    if (!unary) p.exprs[d.b].aux |= kAuxInQual;
+    if (d.op == HDK_B200_OP_CASE) p.exprs[int(d.imm.i)].aux |= kAuxInQual;
   }
   // ---- joins
   for (int j = 0; j < plan->n_joins; ++j) {

@@ -217,7 +217,7 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
   auto load_inner = [&](int j, int c, int w) -> uint64_t {
     return ldg_elem(reinterpret_cast<const uint8_t*>(args.inner_col_buffers[j * HDK_B200_MAX_COLS + c]) + size_t(rowid[j]) * w, w);
   };
-  int32_t row_err = 0;
+  int32_t row_err = 0, qual_err = 0;
   bool dropped = false;
   // 1:N join: nodes up to the key are evaluated once, the rest once per match
   int n_matches = 1;
@@ -227,7 +227,7 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
   for (int n = 0; n < split && !dropped; ++n) {
     int32_t e = 0;
     vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
-    if (e && !row_err) row_err = e;
+    if (e) { int32_t& dst = (p.exprs[n].aux & kAuxInQual) ? qual_err : row_err; if (!dst) dst = e; }
     for (int j = 0; j < p.n_joins; ++j) {
       const DJoin& jn = p.joins[j];
       if (jn.key_expr != n) continue;
@@ -270,8 +270,9 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
     for (int n = split; n < p.n_exprs; ++n) {
       int32_t e = 0;
       vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
-      if (e && !row_err) row_err = e;
+      if (e) { int32_t& dst = (p.exprs[n].aux & kAuxInQual) ? qual_err : row_err; if (!dst) dst = e; }
     }
+    if (qual_err) { my_err = my_err > 0 ? my_err : qual_err; continue; }   // an error inside a qual: raised whether or not the row passes
     bool pass = true;
     for (int f = 0; f < p.n_filters; ++f) pass = pass && (vals[p.filters[f]].i > 0);
     if (!pass) continue;
@@ -313,7 +314,7 @@ __device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint
   constexpr DPlan sp = Shape::get();
   const DPlan& rp = args.plan;  // literals, key ranges, entry count
   int64_t rowid[HDK_B200_MAX_JOINS];
-  int32_t row_err = 0;
+  int32_t row_err = 0, qual_err = 0;
   bool alive = true;
   auto load_outer = [&](int c, int) -> uint64_t { return raw[c]; };
   auto load_inner = [&](int j, int c, int w) -> uint64_t {
@@ -326,7 +327,8 @@ __device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint
     if constexpr (sp.exprs[n].op == HDK_B200_OP_CONST) e.imm = rp.exprs[n].imm;  // literals are run-time; widths / units are structure
     int32_t err = 0;
     vals[n] = eval_node(sp, e, vals, err, load_outer, load_inner);
-    if (err && !row_err) row_err = err;
+    if constexpr ((sp.exprs[n].aux & kAuxInQual) != 0) { if (err && !qual_err) qual_err = err; }
+    else { if (err && !row_err) row_err = err; }
     static_for<0, sp.n_joins>([&](auto J) {
       constexpr int j = decltype(J)::value;
       constexpr DPlan sp = Shape::get();
@@ -366,6 +368,7 @@ __device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint
     });
   });
   if (!alive) return false;
+  if (qual_err) { my_err = my_err > 0 ? my_err : qual_err; return false; }   // raised whether or not the row passes
   bool pass = true;
   static_for<0, sp.n_filters>([&](auto F) {
     constexpr DPlan sp = Shape::get();

@@ -328,7 +328,7 @@ static void detect_direct_keys(const DPlan& p, ShuffleArgs* a) {
     if (e.op != HDK_B200_OP_COL || e.a != 0 || e.kind != HDK_B200_INT) return;
     a->key_col[k] = e.b;
     a->key_w[k] = uint8_t(e.imm.i);
-    a->key_days[k] = uint8_t(e.aux == 1);
+    a->key_days[k] = uint8_t(e.aux & 1);
   }
   a->direct = 1;
 }

@@ -392,7 +392,9 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
     def can_raise(e: ir.Expr) -> bool:
         """Does evaluating e possibly raise a row error (division by zero, checked integer overflow)?"""
         if e not in raises_memo:
-            own = isinstance(e, ir.BinOp) and (e.op == "/" or (e.overflow_check and not e.type.is_fp))
+            own = (isinstance(e, ir.BinOp) and (e.op == "/" or (e.overflow_check and not e.type.is_fp))) or \
+                  (isinstance(e, ir.Cast) and not e.type.is_fp and not e.arg.type.is_fp and e.arg.type.width > e.type.width) or \
+                  (isinstance(e, ir.UMinus) and not e.type.is_fp and not e.arg.type.nullable)
             raises_memo[e] = own or any(can_raise(c) for c in e.children())
         return raises_memo[e]
 
@@ -435,9 +437,9 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
             op = {"+": abi.OP_ADD, "-": abi.OP_SUB, "*": abi.OP_MUL, "/": abi.OP_DIV}[e.op]
             n = emit(op, a, b, 1 if (e.overflow_check and not e.type.is_fp) else 0, e.type, guard=g)
         elif isinstance(e, ir.UMinus):
-            n = emit(abi.OP_UMINUS, lower(e.arg, guard), t=e.type)
+            n = emit(abi.OP_UMINUS, lower(e.arg, guard), t=e.type, guard=g)
         elif isinstance(e, ir.Cast):
-            n = emit(abi.OP_CAST, lower(e.arg, guard), t=e.type)
+            n = emit(abi.OP_CAST, lower(e.arg, guard), t=e.type, guard=g)
         elif isinstance(e, ir.ExtractYear):
             at = e.arg.type
             units = at.unit if at.kind == "timestamp" else 1

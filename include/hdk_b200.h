@@ -97,7 +97,9 @@ enum hdk_b200_op {
   HDK_B200_OP_MUL = 4,
   HDK_B200_OP_DIV = 5,     /* int: ERR_DIV_BY_ZERO on zero divisor; fp: IEEE */
   HDK_B200_OP_CAST = 6,    /* a → type.  fp→int rounds half away from zero (QE/CastIR.cpp:529-541,        */
-                           /* RuntimeFunctions.cpp:309-345); int→fp exact convert; int→int re-sentinels     */
+                           /* RuntimeFunctions.cpp:309-345); int→fp exact convert; int→int re-sentinels;    */
+                           /* narrowing int→int raises ERR_OVERFLOW_OR_UNDERFLOW outside (min, max] of the  */
+                           /* target (codegenCastBetweenIntTypesOverflowChecks, CastIR.cpp:405-462)         */
   HDK_B200_OP_EXTRACT_YEAR = 7, /* a = timestamp in seconds after ival-division: ival = units per second   */
                            /* (1, 1000, 1e6, 1e9) (QE/DateTimeIR.cpp:281-320, Utils/ExtractFromTime.cpp:260-271) */
   HDK_B200_OP_LT = 8,

@@ -413,6 +413,35 @@ def test_case_expressions_on_gpu(oracle_mod, torch):
         assert int(prep["err"].item()) == code, text
 
 
+def test_overflow_and_underflow_on_gpu(oracle_mod, torch):
+    """Select.OverflowAndUnderFlow (ArrowBasedExecuteTest.cpp:7210-7300), integer cases: checked + - *, unary minus of the
+    type minimum, narrowing casts.  An error inside a qual is raised whether or not the row passes; results otherwise
+    byte-identical to the oracle's."""
+    from tests.test_sqlite_oracle import OVERFLOW_OK_QUERIES, OVERFLOW_THROW_QUERIES, reference_test_table
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    st = util.make_storage(reference_test_table(), fragment_size=2)
+    for text in OVERFLOW_OK_QUERIES + OVERFLOW_THROW_QUERIES:
+        ex = Executor(st)
+        pq = ex.plan(sql.parse(text, st.tables))
+        prep = ex.prepare(pq)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        code = int(prep["err"].item())
+        if text in OVERFLOW_THROW_QUERIES:
+            assert code == 7, text
+        else:
+            assert code == 0, text
+            check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), pq.plan.n_keys)
+    # the façade turns the code into an exception, like the reference's run_multiple_agg
+    import hdk_b200.hdk as hdk_mod
+    from hdk_b200.executor import QueryError
+    h = hdk_mod.init()
+    h.import_arrow(reference_test_table()["test"], "test", fragment_size=2)
+    with pytest.raises(QueryError):
+        h.sql("SELECT COUNT(*) FROM test WHERE ofq + 1 > 0").to_arrow()
+
+
 def test_group_by_boundaries_and_null_on_gpu(oracle_mod, torch):
     """GroupByBoundariesAndNull (ArrowBasedExecuteTest.cpp:2845-2866) on the device: keys at INT32_MAX / 127 / 32767 / 2^62
     with NULL keys, single and composite, buffers byte-identical to the oracle's."""
