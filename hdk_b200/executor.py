@@ -359,7 +359,7 @@ class Executor:
         rows = 0
         for k, key_col in enumerate(key_cols):
             ci = inner.columns[key_col]
-            lo, hi, _ = inner.col_stats(key_col)
+            lo, hi, _ = inner.join_key_range(key_col)
             if lo is None or ci.type.is_fp:
                 raise planner.UnsupportedPlan("join key without an integer range")
             chunks = (abi.JoinChunk * len(inner.fragments))()
@@ -417,7 +417,7 @@ class Executor:
             return self.join_tables[cache_key]
         torch = self.ctx.torch
         ci = inner.columns[key_col]
-        lo, hi, has_nulls = inner.col_stats(key_col)
+        lo, hi, has_nulls = inner.join_key_range(key_col)
         if lo is None or ci.type.is_fp:
             raise planner.UnsupportedPlan("join key without an integer range")
         entries = hi - lo + 1
@@ -462,7 +462,8 @@ class Executor:
         if len(frs) == 1:
             return self.ctx.chunk(frs[0], cname)
         if cname not in jt.inner_columns_dev:
-            jt.inner_columns_dev[cname] = self.ctx.torch.cat([self.ctx.chunk(f, cname) for f in frs])
+            jt.inner_columns_dev[cname] = self.ctx.torch.cat([self.ctx.chunk(f, cname) for f in frs]) if frs else \
+                self.ctx.torch.zeros(8, dtype=self.ctx.torch.uint8, device=self.ctx.device)   # empty table: never addressed
         return jt.inner_columns_dev[cname]
 
     def _slot_ordered_column(self, jt: JoinTable, cname: str):
@@ -554,7 +555,7 @@ class Executor:
             pj.one_to_many = int(jt.hash_type == "OneToMany")
             pj.min_key, pj.max_key, pj.entry_count = jt.min_key, jt.max_key, jt.entry_count
             pj.payload_by_slot = 0
-            if self.config.join_payload_by_slot and jt.hash_type == "OneToOne":
+            if self.config.join_payload_by_slot and jt.hash_type == "OneToOne" and pq.inner_columns[j]:
                 # a one-to-one table has no duplicate keys: as many non-NULL keys as entries ⇒ every slot is occupied
                 pj.payload_by_slot = 2 if jt.dense else 1
             if pj.payload_by_slot:

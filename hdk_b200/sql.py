@@ -320,7 +320,14 @@ class _Parser:
         table, alias = self._table_ref()
         self.scopes.append((alias, table, 0))
         joins_raw = []
-        while self.peek() in (("kw", "join"), ("kw", "inner")):
+        while self.peek() in (("kw", "join"), ("kw", "inner"), ("op", ",")):
+            if self.accept("op", ","):
+                # implicit join: FROM a, b WHERE a.x = b.x — the equalities against b's columns are taken out of the WHERE
+                # clause below (what the reference's join-qual extraction does, QE/RelAlgExecutor / RelAlgOptimizer)
+                t2, a2 = self._table_ref()
+                self.scopes.append((a2, t2, len(joins_raw) + 1))
+                joins_raw.append((t2, None))
+                continue
             if self.accept("kw", "inner"):
                 pass
             self.eat("kw", "join")
@@ -409,8 +416,27 @@ class _Parser:
                 return out
             return [c]
 
+        strip_cast = lambda x: x.arg if isinstance(x, ir.Cast) else x  # noqa: E731
+
+        def max_table(e):
+            return max([e.table] if isinstance(e, ir.ColumnRef) else [0] + [max_table(c) for c in e.children()])
+
         for t2, cond in joins_raw:
             jidx = len(joins) + 1
+            if cond is None:
+                # comma join: WHERE conjuncts `inner column of this table = expression over earlier tables`
+                mine, rest = [], []
+                for c in quals:
+                    ok = False
+                    if isinstance(c, ir.Cmp) and c.op == "=":
+                        l, r = strip_cast(c.lhs), strip_cast(c.rhs)
+                        ok = (isinstance(r, ir.ColumnRef) and r.table == jidx and max_table(l) < jidx) or \
+                             (isinstance(l, ir.ColumnRef) and l.table == jidx and max_table(r) < jidx)
+                    (mine if ok else rest).append(c)
+                if not mine:
+                    raise UnsupportedPlan("cross join: no equality between the comma-joined table and the tables before it")
+                quals = rest
+                cond = mine[0] if len(mine) == 1 else ir.Logic("and", tuple(mine))
             pairs = []
             for c in conjuncts(cond):
                 if not (isinstance(c, ir.Cmp) and c.op == "="):

@@ -69,6 +69,15 @@ class Table:
             hi = s.max if hi is None else max(hi, s.max)
         return lo, hi, hn
 
+    def join_key_range(self, column: str):
+        """col_stats for the build side of a join: a table without any non-NULL key (empty, or all NULL) builds a table of
+        one empty slot — no probe can match, the inner join yields nothing (the reference reaches the same result through
+        an invalid ExpressionRange → HashJoinFail → loop join over zero rows)."""
+        lo, hi, hn = self.col_stats(column)
+        if lo is None and not self.columns[column].type.is_fp:
+            lo = hi = 0
+        return lo, hi, hn
+
 
 def _arrow_type_to_sql(t: pa.DataType, nullable: bool):
     """→ (SqlType, numpy dtype, phys width)"""

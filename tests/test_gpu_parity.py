@@ -442,6 +442,25 @@ def test_overflow_and_underflow_on_gpu(oracle_mod, torch):
         h.sql("SELECT COUNT(*) FROM test WHERE ofq + 1 > 0").to_arrow()
 
 
+def test_reference_join_fixtures_on_gpu(oracle_mod, torch):
+    """Joins_ImplicitJoins / Joins_InnerJoin_* / Select.Empty / BigintGroupByColCompactionTest shapes over the reference's
+    fixtures (tests/test_sqlite_oracle.py::JOIN_FIXTURE_QUERIES) through the façade: empty tables and tables that fit one
+    fragment of two rows, chained joins, a baseline join table, ORDER BY on the device — rows vs SQLite."""
+    import hdk_b200.hdk as hdk_mod
+    from tests.test_sqlite_oracle import JOIN_FIXTURE_QUERIES, reference_join_tables
+    tables = reference_join_tables()
+    h = hdk_mod.init()
+    for name, t in tables.items():
+        h.import_arrow(t, name, fragment_size=2)
+    for text in JOIN_FIXTURE_QUERIES:
+        got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+        exp = util.sqlite_rows(tables, text, 0)
+        if "ORDER BY" in text:
+            util.assert_rows_equal(got, exp, rel=1e-9)
+        else:
+            util.assert_rows_equal(sorted(got, key=repr), sorted(exp, key=repr), rel=1e-9)
+
+
 def test_group_by_boundaries_and_null_on_gpu(oracle_mod, torch):
     """GroupByBoundariesAndNull (ArrowBasedExecuteTest.cpp:2845-2866) on the device: keys at INT32_MAX / 127 / 32767 / 2^62
     with NULL keys, single and composite, buffers byte-identical to the oracle's."""

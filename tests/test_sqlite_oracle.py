@@ -318,3 +318,79 @@ def test_overflow_and_underflow_raise(oracle_mod, text):
     for kind in ("port", "reference"):
         _, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
         assert err == 7, (kind, text)
+
+
+def reference_join_tables():
+    """`test` + the reference's join fixtures: test_inner (:958-968), hash_join_test (:928-939), join_test
+    (ArrowBasedExecuteTest.cpp createJoinTestTable), and the empty table of Select.Empty."""
+    tables = reference_test_table()
+    nn = lambda n, t: pa.field(n, t, nullable=False)   # noqa: E731
+    tables["test_inner"] = pa.table([pa.array([7], pa.int32()), pa.array([43], pa.int32()), pa.array(["foo"])],
+                                    schema=pa.schema([nn("x", pa.int32()), pa.field("y", pa.int32()), pa.field("str", pa.string())]))
+    tables["hash_join_test"] = pa.table([pa.array([7, 8, 9], pa.int32()), pa.array(["foo", "bar", "the"]),
+                                         pa.array([1001, 5000000000, 1002], pa.int64())],
+                                        schema=pa.schema([nn("x", pa.int32()), pa.field("str", pa.string()), pa.field("t", pa.int64())]))
+    tables["join_test"] = pa.table([pa.array([7, 8, 9], pa.int32()), pa.array([43, None, None], pa.int32()),
+                                    pa.array(["foo", "bar", "baz"]), pa.array(["foo", "foo", "bar"])],
+                                   schema=pa.schema([nn("x", pa.int32()), pa.field("y", pa.int32()), pa.field("str", pa.string()),
+                                                     pa.field("dup_str", pa.string())]))
+    tables["emptytab"] = pa.table({"x": pa.array([], pa.int32()), "y": pa.array([], pa.int32()), "t": pa.array([], pa.int64()),
+                                   "f": pa.array([], pa.float32()), "d": pa.array([], pa.float64())})
+    tables["bigint_groupby_col_compaction_test"] = pa.table({"c": pa.array(
+        [-6312639302689611776, -6312639302689611776, -6312639302689611776, -6336283200715718656, -6312639302689603584], pa.int64())})
+    return tables
+
+
+# Select.Joins_ImplicitJoins (:9311-9340), Joins_InnerJoin_* (:9540-9640) inside the subset: 1:1 perfect tables, a key range
+# too wide for one (test.t = hash_join_test.t → baseline join table), chains whose key comes from an inner table, a NULL-able
+# composite key, filters / group keys / aggregates on inner columns; Select.Empty (:8900-8950); BigintGroupByColCompactionTest
+# (:8866-8884: 64-bit keys 2^13 apart → baseline hash)
+JOIN_FIXTURE_QUERIES = [
+    "SELECT COUNT(*) FROM test, test_inner WHERE test.x = test_inner.x",
+    "SELECT COUNT(*) FROM test, hash_join_test WHERE test.t = hash_join_test.t",
+    "SELECT test_inner.x, COUNT(*) AS n FROM test, test_inner WHERE test.x = test_inner.x GROUP BY test_inner.x ORDER BY n",
+    "SELECT COUNT(*) FROM test JOIN test_inner ON test.x = test_inner.x",
+    "SELECT count(*) FROM test AS a JOIN hash_join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.x = c.x",
+    "SELECT count(*) FROM test AS a JOIN hash_join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.x = c.x "
+    "JOIN join_test AS d ON c.x = d.x",
+    "SELECT SUM(a.x), b.str FROM test AS a JOIN hash_join_test AS b ON a.x = b.x WHERE a.y = 43 GROUP BY b.str",
+    "SELECT count(*) FROM test AS a JOIN hash_join_test AS b ON a.x = b.x WHERE a.y < 43",
+    "SELECT b.x, SUM(a.t), MIN(b.t), MAX(b.t), AVG(a.d) FROM test a JOIN hash_join_test b ON a.x = b.x GROUP BY b.x",
+    "SELECT COUNT(*) FROM test a JOIN join_test b ON a.x = b.x AND a.y = b.y",
+    "SELECT a.x, COUNT(*) FROM test a JOIN join_test b ON a.y = b.y GROUP BY a.x",
+    "SELECT b.dup_str, COUNT(*), SUM(a.z) FROM test a JOIN join_test b ON a.x = b.x GROUP BY b.dup_str",
+    "SELECT COUNT(*) FROM test a JOIN hash_join_test b ON a.x = b.x WHERE b.t > 1001 AND a.f < 1.25",
+    "SELECT COUNT(*) FROM test a, join_test b, hash_join_test c WHERE a.x = b.x AND b.x = c.x AND a.y = b.y AND c.t < 2000 AND a.z > 100",
+    "SELECT COUNT(*), SUM(x), MIN(t), MAX(f), AVG(d), SUM(d), MIN(y) FROM emptytab",
+    "SELECT x, COUNT(*) FROM emptytab GROUP BY x",
+    "SELECT COUNT(*), SUM(y), MIN(t), MAX(f), AVG(d) FROM test WHERE x > 8",
+    "SELECT COUNT(*), SUM(test.y) FROM test JOIN emptytab ON test.x = emptytab.x",
+    "SELECT c FROM bigint_groupby_col_compaction_test GROUP BY c ORDER BY c",
+    "SELECT c, COUNT(*) FROM bigint_groupby_col_compaction_test GROUP BY c ORDER BY c DESC",
+]
+
+
+def decode_with_dictionaries(st, pq, buf):
+    from hdk_b200.executor import ResultSet
+    tabs = [st.get_table(pq.unit.table)] + [st.get_table(j.inner_table) for j in pq.unit.joins]
+    dicts = {i: tabs[e.table].columns[e.column].dictionary for i, e in enumerate(pq.unit.target_exprs)
+             if isinstance(getattr(e, "column", None), str) and e.type.kind == "dict"}
+    return [tuple(r.values()) for r in ResultSet(pq, buf, dicts).to_arrow().to_pylist()]
+
+
+@pytest.mark.parametrize("text", JOIN_FIXTURE_QUERIES)
+@pytest.mark.parametrize("kind", ["port", "reference"])
+def test_reference_join_fixtures_vs_sqlite(oracle_mod, text, kind):
+    tables = reference_join_tables()
+    st = util.make_storage(tables, fragment_size=2)
+    pq = util.plan_sql(st, text)
+    buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
+    assert err == 0
+    got = decode_with_dictionaries(st, pq, buf)
+    exp = util.sqlite_rows(tables, text, 0)
+    if "ORDER BY" in text:
+        util.assert_rows_equal(got, exp, rel=1e-9)
+    else:
+        util.assert_rows_equal(sorted(got, key=repr), sorted(exp, key=repr), rel=1e-9)
+    if "bigint_groupby" in text:
+        assert pq.qmd.hash_type == 1 and len(got) == 3      # baseline hash, three groups (ArrowBasedExecuteTest.cpp:8875)

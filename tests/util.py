@@ -44,7 +44,7 @@ def oracle_inputs(oracle, st, pq):
             keep = []
             for k, kcname in enumerate(key_cols):
                 ci = inner.columns[kcname]
-                lo, hi, _ = inner.col_stats(kcname)
+                lo, hi, _ = inner.join_key_range(kcname)
                 jc = oracle.make_join_column([f.chunks[kcname] for f in inner.fragments], ci.phys_width)
                 keep.append(jc)
                 jcs[k] = jc
@@ -59,7 +59,7 @@ def oracle_inputs(oracle, st, pq):
             inner_cols.append([np.concatenate([f.chunks[c] for f in inner.fragments]) for c in pq.inner_columns[j]])
             _KEEP.append(keep)
             continue
-        lo, hi, _ = inner.col_stats(js.inner_key_column)
+        lo, hi, _ = inner.join_key_range(js.inner_key_column)
         ci = inner.columns[js.inner_key_column]
         E = hi - lo + 1
         chunks = [f.chunks[js.inner_key_column] for f in inner.fragments]
