@@ -311,6 +311,8 @@ class ResultSet:
                 tbl = tbl.take(idx)
         if unit.limit is not None:
             tbl = tbl.slice(0, unit.limit)
+        if unit.n_hidden:
+            tbl = tbl.select(list(range(len(names) - unit.n_hidden)))
         return tbl
 
 

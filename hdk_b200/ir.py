@@ -388,3 +388,4 @@ class ExecutionUnit:
     joins: List[JoinSpec] = field(default_factory=list)
     order_by: List[tuple] = field(default_factory=list)   # (target index, is_desc, nulls_first) — hdk::ir::OrderEntry
     limit: Optional[int] = None
+    n_hidden: int = 0                   # trailing targets that only serve ORDER BY and are dropped from the answer

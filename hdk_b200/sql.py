@@ -371,6 +371,7 @@ class _Parser:
                 if not self.accept("op", ","):
                     break
         order = []
+        n_hidden = 0
         if self.accept("kw", "order"):
             self.eat("kw", "by")
             while True:
@@ -385,8 +386,14 @@ class _Parser:
                         key = e.value - 1
                     elif e in targets:
                         key = targets.index(e)
+                    elif e in groupby:
+                        # ordered by a group key the query does not project: carried as a trailing hidden target
+                        targets.append(e)
+                        names.append(f"__order_by_{len(targets)}")
+                        n_hidden += 1
+                        key = len(targets) - 1
                     else:
-                        raise UnsupportedPlan("ORDER BY expression must be a select item")
+                        raise UnsupportedPlan("ORDER BY expression must be a select item or a group key")
                 desc = False
                 if self.accept("kw", "desc"):
                     desc = True
@@ -457,7 +464,7 @@ class _Parser:
                 n = e.column if isinstance(e, ir.ColumnRef) else f"EXPR${i}"
             final_names.append(n)
         order = [(final_names.index(k) if isinstance(k, str) else k, d, nf) for k, d, nf in order]
-        return ir.ExecutionUnit(table, groupby, targets, final_names, quals, joins, order, limit)
+        return ir.ExecutionUnit(table, groupby, targets, final_names, quals, joins, order, limit, n_hidden)
 
     def _table_ref(self):
         name = self.eat("id")[1]

@@ -461,6 +461,24 @@ def test_reference_join_fixtures_on_gpu(oracle_mod, torch):
             util.assert_rows_equal(sorted(got, key=repr), sorted(exp, key=repr), rel=1e-9)
 
 
+@pytest.mark.parametrize("bigint_count", [False, True])
+def test_group_by_perfect_hash_on_gpu(oracle_mod, torch, bigint_count):
+    """Select.GroupByPerfectHash (ArrowBasedExecuteTest.cpp:8637-8709) through the façade: keys of every integer width,
+    nullable keys, CASE keys with a NULL arm, a key projected twice, ORDER BY (on the device) with NULLS FIRST, ordering
+    by a key that is not projected; rows in order vs SQLite, with COUNT as int32 and as int64."""
+    import hdk_b200.hdk as hdk_mod
+    from tests.test_sqlite_oracle import GROUP_BY_PERFECT_HASH_QUERIES, logical_size_tables, sqlite_text
+    tables = logical_size_tables()
+    h = hdk_mod.init(bigint_count=bigint_count)
+    for name, t in tables.items():
+        h.import_arrow(t, name, fragment_size=4)
+    for text in GROUP_BY_PERFECT_HASH_QUERIES:
+        res = h.sql(text)
+        assert res.result_set.sorted_on_device
+        got = [tuple(r.values()) for r in res.to_arrow().to_pylist()]
+        util.assert_rows_equal(got, util.sqlite_rows(tables, sqlite_text(text), 0), rel=1e-6)
+
+
 def test_group_by_boundaries_and_null_on_gpu(oracle_mod, torch):
     """GroupByBoundariesAndNull (ArrowBasedExecuteTest.cpp:2845-2866) on the device: keys at INT32_MAX / 127 / 32767 / 2^62
     with NULL keys, single and composite, buffers byte-identical to the oracle's."""

@@ -394,3 +394,81 @@ def test_reference_join_fixtures_vs_sqlite(oracle_mod, text, kind):
         util.assert_rows_equal(sorted(got, key=repr), sorted(exp, key=repr), rel=1e-9)
     if "bigint_groupby" in text:
         assert pq.qmd.hash_type == 1 and len(got) == 3      # baseline hash, three groups (ArrowBasedExecuteTest.cpp:8875)
+
+
+_LOGICAL_SIZE_ROWS = """2002,-57,7,0,73,32767,22,127,1.5,NULL,11.5,-21.6
+1001,63,6,NULL,77,-32767,21,NULL,1.6,1.1,11.6,NULL
+3003,63,5,2,79,NULL,23,125,1.5,-1.3,11.5,22.3
+3003,NULL,4,6,78,0,20,126,1.7,-1.5,11.7,22.5
+2002,NULL,4,NULL,75,-112,-13,-125,2.5,-2.3,22.5,-23.5
+1001,-57,6,2,77,NULL,-14,-126,2.6,NULL,22.6,23.7
+1001,63,7,0,78,-32767,-15,NULL,2.7,2.7,22.7,NULL
+1001,-57,5,6,79,32767,-12,-127,2.6,-2.4,22.6,-23.4
+3003,63,5,2,79,-32767,4,NULL,3.6,3.3,32.6,-33.3
+2002,-57,7,4,76,32767,2,-1,3.5,-3.7,32.5,33.7
+3003,NULL,4,NULL,77,NULL,3,-2,3.7,NULL,32.7,-33.5
+1001,-57,6,0,73,2345,1,-3,3.4,32.4,32.5,NULL
+1001,63,6,4,77,0,12,-3,4.5,4.3,11.6,NULL
+3003,-57,4,2,78,32767,16,-1,4.6,4.1,11.5,22.3
+2002,63,7,6,75,-32767,13,-2,4.7,-4.1,22.7,-33.3
+2002,NULL,5,NULL,76,NULL,15,NULL,4.4,NULL,22.5,-23.4"""
+
+
+def logical_size_tables():
+    """`logical_size_test` (ArrowBasedExecuteTest.cpp:732-786: every integer width, nullable and not, four fragments of four
+    rows) next to `test`."""
+    names = ["big_int", "big_int_null", "id", "id_null", "small_int", "small_int_null", "tiny_int", "tiny_int_null",
+             "float_not_null", "float_null", "double_not_null", "double_null"]
+    types = [pa.int64(), pa.int64(), pa.int32(), pa.int32(), pa.int16(), pa.int16(), pa.int8(), pa.int8(),
+             pa.float32(), pa.float32(), pa.float64(), pa.float64()]
+    rows = [[None if v == "NULL" else (float(v) if "." in v else int(v)) for v in line.split(",")]
+            for line in _LOGICAL_SIZE_ROWS.split("\n")]
+    schema = pa.schema([pa.field(n, t, nullable=n.endswith("_null")) for n, t in zip(names, types)])
+    tables = reference_test_table()
+    tables["logical_size_test"] = pa.table([pa.array([r[i] for r in rows], type=t) for i, t in enumerate(types)], schema=schema)
+    return tables
+
+
+# Select.GroupByPerfectHash (ArrowBasedExecuteTest.cpp:8637-8709), run with bigint_count off and on like the reference.
+# `test` columns the reduced fixture does not carry are replaced by ones of the same type (fn/ff → f, dn → d, smallint_nulls → z).
+_PH_KEYS = [
+    ("big_int_null", "SUM(float_null), COUNT(*)"), ("id", "AVG(big_int_null), COUNT(*)"),
+    ("id_null", "MAX(tiny_int), MIN(tiny_int)"), ("small_int", "SUM(cast (id as double)), SUM(double_not_null)"),
+    ("tiny_int", "COUNT(small_int_null), COUNT(*)"), ("tiny_int_null", "AVG(small_int), COUNT(tiny_int)"),
+    ("case when id = 6 then -17 when id = 5 then 33 else NULL end", "COUNT(*), AVG(small_int_null)"),
+    ("case when id = 5 then NULL when id = 6 then -57 else cast(61 as tinyint) end", "AVG(big_int), SUM(tiny_int)"),
+    ("case when float_not_null > 2 then -3 when float_null < 4 then 87 else NULL end", "MAX(id), COUNT(*)"),
+]
+GROUP_BY_PERFECT_HASH_QUERIES = [
+    "SELECT COUNT(*) FROM test GROUP BY x ORDER BY x DESC",
+    "SELECT y, COUNT(*) FROM test GROUP BY y ORDER BY y DESC",
+    "SELECT str, COUNT(*) FROM test GROUP BY str ORDER BY str DESC",
+    "SELECT COUNT(*), z FROM test where x = 7 GROUP BY z ORDER BY z DESC",
+    "SELECT z as z0, z as z1, COUNT(*) FROM test GROUP BY z0, z1 ORDER BY z0 DESC",
+    "SELECT x, COUNT(y), SUM(y), AVG(y), MIN(y), MAX(y) FROM test GROUP BY x ORDER BY x DESC",
+    "SELECT y, SUM(f), AVG(d), MAX(f) from test GROUP BY y ORDER BY y DESC",
+    "SELECT str, x FROM test GROUP BY x, str ORDER BY str, x",
+    "SELECT str, x, MAX(z), AVG(y), COUNT(ofd) FROM test GROUP BY x, str ORDER BY str, x",
+    "SELECT str, x, MAX(z), COUNT(ofd), COUNT(*) as cnt FROM test GROUP BY x, str ORDER BY cnt, str",
+    "SELECT x, str, z, SUM(d), MAX(d), AVG(d) FROM test GROUP BY x, str, z ORDER BY str, z, x",
+    "SELECT x, SUM(d), str, MAX(d), z, AVG(d), COUNT(*) FROM test GROUP BY z, x, str ORDER BY str, z, x",
+] + [f"SELECT {k}, {a} FROM logical_size_test GROUP BY {k} ORDER BY {k} ASC NULLS FIRST" for k, a in _PH_KEYS]
+
+
+def sqlite_text(text):
+    """c(query + " NULLS FIRST;", query + ";", dt): SQLite's ascending order already puts NULLs first"""
+    return text.replace(" NULLS FIRST", "")
+
+
+@pytest.mark.parametrize("text", GROUP_BY_PERFECT_HASH_QUERIES)
+@pytest.mark.parametrize("bigint_count", [False, True])
+def test_group_by_perfect_hash_vs_sqlite(oracle_mod, text, bigint_count):
+    from hdk_b200 import planner
+    tables = logical_size_tables()
+    st = util.make_storage(tables, fragment_size=4)
+    pq = util.plan_sql(st, text, cfg=planner.Config(bigint_count=bigint_count))
+    assert pq.qmd.hash_type == 0                                   # "small ranged to force perfect hash"
+    for kind in ("port", "reference"):
+        buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
+        assert err == 0
+        util.assert_rows_equal(decode_with_dictionaries(st, pq, buf), util.sqlite_rows(tables, sqlite_text(text), 0), rel=1e-6)
