@@ -172,52 +172,74 @@ struct CompactArgs {
   unsigned long long* row_count;
 };
 
-__global__ void compact_kernel(const __grid_constant__ CompactArgs a) {
+// one decoded 8-byte cell of target t of entry e (ResultSet::getTargetValueFromBufferRowwise / Colwise + pair_to_double)
+__device__ __forceinline__ int64_t compact_cell(const CompactArgs& a, const DLayout& L, uint64_t E, uint64_t e, int t) {
+  int8_t* buf = const_cast<int8_t*>(a.buf);
+  if (a.agg[t] == HDK_B200_AGG_AVG) {
+    const DSlot& s0 = L.slots[a.slot[t]];
+    const DSlot& s1 = L.slots[a.slot[t] + 1];
+    const int64_t sum = rd_slot(slot_ptr(L, buf, e, s0), a.float_arg[t] ? 4 : s0.padded);
+    const int64_t cnt = rd_slot(slot_ptr(L, buf, e, s1), s1.padded);
+    if (cnt == 0) return __double_as_longlong(2.2250738585072014e-308);  // NULL_DOUBLE
+    const double dividend = a.float_arg[t] ? double(__int_as_float(int32_t(sum))) : a.sum_is_fp[t] ? __longlong_as_double(sum) : double(sum);
+    return __double_as_longlong(dividend / double(cnt));
+  }
+  int64_t raw;
+  if (a.slot[t] >= 0) {
+    const DSlot& s = L.slots[a.slot[t]];
+    const bool f4 = a.float_arg[t] != 0;
+    raw = rd_slot(slot_ptr(L, buf, e, s), f4 ? 4 : s.padded);
+    if (f4) raw = __double_as_longlong(double(__int_as_float(int32_t(raw))));
+  } else {
+    const int k = a.key_index[t];
+    if (L.columnar) raw = reinterpret_cast<const int64_t*>(a.buf)[uint64_t(k) * E + e];
+    else if (L.key_width == 4) raw = reinterpret_cast<const int32_t*>(a.buf + e * L.row_bytes)[k];
+    else raw = reinterpret_cast<const int64_t*>(a.buf + e * L.row_bytes)[k];
+  }
+  if (!a.chosen_is_fp[t] && int_null_of(a.chosen_width[t]) == resize_int(raw, a.chosen_width[t])) raw = int_null_of(a.type_width[t]);
+  return raw;
+}
+
+constexpr int kCompactThreads = 256;
+constexpr int kCompactItems = 4;     // entries per thread per iteration: one reservation per 1024 entries
+
+__global__ void __launch_bounds__(kCompactThreads) compact_kernel(const __grid_constant__ CompactArgs a) {
   const DLayout& L = a.layout;
   const uint64_t E = L.entry_count;
-  const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
-  const int lane = threadIdx.x & 31;
-  for (uint64_t base = blockIdx.x * uint64_t(blockDim.x); base < E; base += step) {   // whole warps iterate together
-    const uint64_t e = base + threadIdx.x;
-    const bool keep = e < E && !entry_is_empty(L, a.buf, E, e);
-    // one reservation per warp: output positions = warp base + rank among the warp's non-empty entries
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    unsigned long long wbase = 0;
-    if (lane == 0 && m) wbase = atomicAdd(a.row_count, (unsigned long long)__popc(m));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (!keep) continue;
-    const unsigned long long r = wbase + __popc(m & ((1u << lane) - 1u));
-    for (int t = 0; t < a.n_targets; ++t) {
-      int64_t cell;
-      if (a.agg[t] == HDK_B200_AGG_AVG) {
-        const DSlot& s0 = L.slots[a.slot[t]];
-        const DSlot& s1 = L.slots[a.slot[t] + 1];
-        const int64_t sum = rd_slot(slot_ptr(L, const_cast<int8_t*>(a.buf), e, s0), a.float_arg[t] ? 4 : s0.padded);
-        const int64_t cnt = rd_slot(slot_ptr(L, const_cast<int8_t*>(a.buf), e, s1), s1.padded);
-        double d;
-        if (cnt == 0) d = 2.2250738585072014e-308;  // NULL_DOUBLE
-        else {
-          const double dividend = a.float_arg[t] ? double(__int_as_float(int32_t(sum))) : a.sum_is_fp[t] ? __longlong_as_double(sum) : double(sum);
-          d = dividend / double(cnt);
-        }
-        cell = __double_as_longlong(d);
-      } else {
-        int64_t raw;
-        if (a.slot[t] >= 0) {
-          const DSlot& s = L.slots[a.slot[t]];
-          const bool f4 = a.float_arg[t] != 0;
-          raw = rd_slot(slot_ptr(L, const_cast<int8_t*>(a.buf), e, s), f4 ? 4 : s.padded);
-          if (f4) raw = __double_as_longlong(double(__int_as_float(int32_t(raw))));
-        } else {
-          const int k = a.key_index[t];
-          if (L.columnar) raw = reinterpret_cast<const int64_t*>(a.buf)[uint64_t(k) * E + e];
-          else if (L.key_width == 4) raw = reinterpret_cast<const int32_t*>(a.buf + e * L.row_bytes)[k];
-          else raw = reinterpret_cast<const int64_t*>(a.buf + e * L.row_bytes)[k];
-        }
-        if (!a.chosen_is_fp[t] && int_null_of(a.chosen_width[t]) == resize_int(raw, a.chosen_width[t])) raw = int_null_of(a.type_width[t]);
-        cell = raw;
-      }
-      a.out_cols[t][r] = cell;
+  const uint64_t step = uint64_t(gridDim.x) * (kCompactThreads * kCompactItems);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ unsigned int warp_cnt[kCompactThreads / 32];
+  __shared__ unsigned long long cta_base;
+  for (uint64_t base = blockIdx.x * uint64_t(kCompactThreads * kCompactItems); base < E; base += step) {   // whole CTAs iterate together
+    // One reservation per CTA iteration: a single counter retires about one atomic per ns, so per-warp reservations bound
+    // the kernel at 2e8 entries.  Row = CTA base + non-empty entries of earlier warps + of earlier items / lanes of this warp.
+    bool keep[kCompactItems];
+    unsigned m[kCompactItems];
+    unsigned mine = 0;
+#pragma unroll
+    for (int j = 0; j < kCompactItems; ++j) {
+      const uint64_t e = base + uint64_t(j) * kCompactThreads + threadIdx.x;
+      keep[j] = e < E && !entry_is_empty(L, a.buf, E, e);
+      m[j] = __ballot_sync(0xffffffffu, keep[j]);
+      mine += __popc(m[j]);
+    }
+    if (lane == 0) warp_cnt[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned total = 0;
+      for (int w = 0; w < kCompactThreads / 32; ++w) { const unsigned c = warp_cnt[w]; warp_cnt[w] = total; total += c; }
+      cta_base = total ? atomicAdd(a.row_count, (unsigned long long)total) : 0ull;
+    }
+    __syncthreads();
+    unsigned long long wbase = cta_base + warp_cnt[warp];
+    __syncthreads();     // warp_cnt / cta_base are rewritten by the next iteration
+#pragma unroll
+    for (int j = 0; j < kCompactItems; ++j) {
+      const unsigned long long r = wbase + __popc(m[j] & ((1u << lane) - 1u));
+      wbase += __popc(m[j]);
+      if (!keep[j]) continue;
+      const uint64_t e = base + uint64_t(j) * kCompactThreads + threadIdx.x;
+      for (int t = 0; t < a.n_targets; ++t) a.out_cols[t][r] = compact_cell(a, L, E, e, t);
     }
   }
 }
@@ -282,7 +304,7 @@ int hdk_b200_compact_result(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, 
   a.row_count = reinterpret_cast<unsigned long long*>(row_count);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   HB_CUDA(cudaMemsetAsync(row_count, 0, sizeof(uint64_t), st));
-  compact_kernel<<<grid_for_r(qmd->entry_count, 128), 128, 0, st>>>(a);
+  compact_kernel<<<int(std::min<uint64_t>(148 * 8, (uint64_t(qmd->entry_count) + kCompactThreads * kCompactItems - 1) / (kCompactThreads * kCompactItems))), kCompactThreads, 0, st>>>(a);
   HB_LAUNCH_CHECK();
   return HDK_B200_OK;
 }
