@@ -187,4 +187,25 @@ __device__ __forceinline__ int64_t baseline_join_probe(const int8_t* table, int6
   return slot ? int64_t(*slot) : -1;
 }
 
+// position of the key in the composite-key dictionary of a one-to-many baseline table, or -1
+// (get_composite_key_index_{32,64}, JHT/Runtime/JoinHashTableQueryRuntime.cpp:130-171); the table is read-only here
+template <typename T>
+__device__ __forceinline__ int64_t baseline_dict_index(const int8_t* dict, int64_t E, const int64_t* key64, int kc) {
+  const T empty = sizeof(T) == 4 ? T(HDK_B200_EMPTY_KEY_32) : T(HDK_B200_EMPTY_KEY_64);
+  T key[HDK_B200_MAX_KEYS];
+  for (int i = 0; i < kc; ++i) key[i] = T(key64[i]);
+  const uint32_t h0 = murmur1_dev(key, kc * int(sizeof(T))) % uint32_t(E);
+  uint32_t h = h0;
+  do {
+    const T* row = reinterpret_cast<const T*>(dict) + size_t(h) * kc;
+    const T first = __ldg(row);
+    if (first == empty) return -1;
+    bool match = first == key[0];
+    for (int i = 1; i < kc && match; ++i) match = __ldg(row + i) == key[i];
+    if (match) return int64_t(h);
+    h = h + 1 == uint32_t(E) ? 0 : h + 1;
+  } while (h != h0);
+  return -1;
+}
+
 }  // namespace hb

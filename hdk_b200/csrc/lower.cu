@@ -172,7 +172,7 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
     p.join_entry_count[j] = s.entry_count;
     if (s.n_key_exprs < 0 || s.n_key_exprs > HDK_B200_MAX_KEYS) { set_error("join %d: bad n_key_exprs", j); return HDK_B200_E_INVALID; }
     if (s.n_key_exprs > 0) {
-      if (s.one_to_many || s.payload_by_slot) { set_error("join %d: the fused baseline probe is one-to-one", j); return HDK_B200_E_UNSUPPORTED; }
+      if (s.payload_by_slot) { set_error("join %d: payload_by_slot is a perfect-table layout", j); return HDK_B200_E_INVALID; }
       if (s.key_width != 4 && s.key_width != 8) { set_error("join %d: key_width must be 4 or 8", j); return HDK_B200_E_INVALID; }
       d.n_key_exprs = uint8_t(s.n_key_exprs);
       d.key_width = uint8_t(s.key_width);

@@ -231,10 +231,24 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
     for (int j = 0; j < p.n_joins; ++j) {
       const DJoin& jn = p.joins[j];
       if (jn.key_expr != n) continue;
-      if (jn.n_key_exprs) {   // composite / wide-range key: baseline join table, one-to-one layout
+      if (jn.n_key_exprs) {   // composite / wide-range key: baseline join table
         int64_t k64[HDK_B200_MAX_KEYS];
         for (int i = 0; i < jn.n_key_exprs; ++i) k64[i] = vals[jn.key_exprs[i]].i;
         const int8_t* tbl = reinterpret_cast<const int8_t*>(args.join_hash_tables[j]);
+        if (jn.one_to_many) {
+          // composite-key dictionary, then offsets | counts | payload indexed by the key's position in it
+          // (BaselineJoinHashTable one-to-many layout; HashJoin::codegenMatchingSet)
+          const int64_t E = p.join_entry_count[j];
+          const int64_t slot = jn.key_width == 4 ? baseline_dict_index<int32_t>(tbl, E, k64, jn.n_key_exprs)
+                                                 : baseline_dict_index<int64_t>(tbl, E, k64, jn.n_key_exprs);
+          if (slot < 0) { dropped = true; break; }
+          const int32_t* otm = reinterpret_cast<const int32_t*>(tbl + size_t(E) * size_t(jn.n_key_exprs) * size_t(jn.key_width));
+          const int32_t off = __ldg(otm + slot);
+          if (off < 0) { dropped = true; break; }
+          n_matches = __ldg(otm + E + slot);
+          match_ids = otm + 2 * E + off;
+          continue;
+        }
         const int64_t rid = jn.key_width == 4 ? baseline_join_probe<int32_t>(tbl, p.join_entry_count[j], k64, jn.n_key_exprs)
                                               : baseline_join_probe<int64_t>(tbl, p.join_entry_count[j], k64, jn.n_key_exprs);
         if (rid < 0) { dropped = true; break; }

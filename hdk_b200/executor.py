@@ -383,9 +383,9 @@ class Executor:
         return jcs, tis, rows, keep
 
     def build_baseline_join_table(self, inner: Table, key_cols, key_width: int) -> JoinTable:
-        """BaselineJoinHashTable::reify (JHT/BaselineJoinHashTable.cpp:256-259: 2 x tuples entries) in the one-to-one
-        layout E x (components ‖ row id).  A duplicate composite key would need the one-to-many layout, which the fused
-        probe does not read: UnsupportedPlan, never a silent wrong answer."""
+        """BaselineJoinHashTable::reify (JHT/BaselineJoinHashTable.cpp:256-259: 2 x tuples entries): the one-to-one
+        layout E x (components ‖ row id) first; a duplicate composite key (err = -1, NeedsOneToManyHash) rebuilds as the
+        one-to-many layout — composite-key dictionary E x components, then offsets | counts | payload."""
         cache_key = (inner.name, tuple(key_cols), key_width)
         if cache_key in self.join_tables:
             return self.join_tables[cache_key]
@@ -401,11 +401,23 @@ class Executor:
         _lib.check(self.lib.hdk_b200_fill_baseline_hash_join_buff_on_device(buf.data_ptr(), entries, -1, 0, n, 1, err.data_ptr(), jcs, tis,
                                                                             key_width, st), "fill_baseline_hash_join_buff")
         code = int(err.item())
+        hash_type = "BaselineOneToOne"
         if code == -1:
-            raise planner.UnsupportedPlan("duplicate composite join keys: the one-to-many baseline table is not read by the fused probe")
+            dict_bytes = entries * n * key_width
+            buf = torch.empty(dict_bytes + (2 * entries + rows) * 4, dtype=torch.uint8, device=self.ctx.device)
+            err.zero_()
+            _lib.check(self.lib.hdk_b200_init_baseline_hash_join_buff_on_device(buf.data_ptr(), entries, n, 0, -1, key_width, st),
+                       "init_baseline_hash_join_buff")
+            _lib.check(self.lib.hdk_b200_fill_baseline_hash_join_buff_on_device(buf.data_ptr(), entries, -1, 0, n, 0, err.data_ptr(),
+                                                                                jcs, tis, key_width, st), "fill_baseline_hash_join_buff")
+            _lib.check(self.lib.hdk_b200_fill_one_to_many_baseline_hash_table_on_device(buf.data_ptr() + dict_bytes, buf.data_ptr(),
+                                                                                        entries, -1, n, jcs, tis, key_width, st),
+                       "fill_one_to_many_baseline_hash_table")
+            code = int(err.item())
+            hash_type = "BaselineOneToMany"
         if code != 0:
             raise QueryError(code, "baseline join table build failed")
-        jt = JoinTable(buf, "BaselineOneToOne", 0, 0, entries, inner, {})
+        jt = JoinTable(buf, hash_type, 0, 0, entries, inner, {})
         jt.key_width, jt.n_keys = key_width, n
         self.join_tables[cache_key] = jt
         return jt
@@ -550,7 +562,7 @@ class Executor:
             inner_t = self.storage.get_table(js.inner_table)
             if pj.n_key_exprs >= 1:     # the planner chose a baseline join table (composite or wide-range key)
                 jt = self.build_baseline_join_table(inner_t, js.inner_key_columns[:pj.n_key_exprs], pj.key_width)
-                pj.one_to_many, pj.payload_by_slot, pj.entry_count = 0, 0, jt.entry_count
+                pj.one_to_many, pj.payload_by_slot, pj.entry_count = int(jt.hash_type == "BaselineOneToMany"), 0, jt.entry_count
                 joins.append(jt)
                 continue
             jt = self.build_join_table(inner_t, js.inner_key_column)

@@ -47,6 +47,9 @@ def _bind(lib):
     lib.oracle_fill_one_to_many_hash_table.argtypes = [vp, i64, i32, C.POINTER(abi.JoinColumn),
                                                        C.POINTER(abi.JoinColumnTypeInfo), i64]
     lib.oracle_init_baseline_hash_join_buff.argtypes = [vp, i64, C.c_size_t, C.c_int, i32, C.c_int]
+    lib.oracle_fill_one_to_many_baseline_hash_table.restype = C.c_int
+    lib.oracle_fill_one_to_many_baseline_hash_table.argtypes = [vp, vp, i64, i32, C.c_size_t, C.POINTER(abi.JoinColumn),
+                                                                C.POINTER(abi.JoinColumnTypeInfo), C.c_int]
     lib.oracle_fill_baseline_hash_join_buff.restype = C.c_int
     lib.oracle_fill_baseline_hash_join_buff.argtypes = [vp, i64, i32, C.c_int, C.c_size_t, C.c_int,
                                                         C.POINTER(abi.JoinColumn),

@@ -420,3 +420,29 @@ extern "C" inline int64_t baseline_hash_join_idx_64(const int8_t* hash_buff, con
                                                     const size_t key_bytes, const size_t entry_count) {
   return orc_baseline_probe<int64_t>(hash_buff, key, key_bytes, entry_count);
 }
+
+/* get_composite_key_index_{32,64} (JHT/Runtime/JoinHashTableQueryRuntime.cpp:130-171): index of the key in the
+ * composite-key dictionary of a one-to-many baseline table (entries = the key components only), or -1 */
+template <typename T>
+static inline int64_t orc_composite_key_index(const T* key, const size_t kc, const T* dict, const size_t entry_count) {
+  if (!entry_count) return -1;
+  const T empty = sizeof(T) == 4 ? T(ORC_EMPTY_KEY_32) : T(ORC_EMPTY_KEY_64);
+  const uint32_t h = MurmurHash1(key, int(kc * sizeof(T)), 0) % entry_count;
+  if (std::memcmp(dict + size_t(h) * kc, key, kc * sizeof(T)) == 0) return h;
+  uint32_t hp = (h + 1) % entry_count;
+  while (hp != h) {
+    const T* row = dict + size_t(hp) * kc;
+    if (std::memcmp(row, key, kc * sizeof(T)) == 0) return hp;
+    if (row[0] == empty) return -1;
+    hp = (hp + 1) % entry_count;
+  }
+  return -1;
+}
+extern "C" inline int64_t get_composite_key_index_32(const int32_t* key, const size_t kc, const int32_t* dict,
+                                                     const size_t entry_count) {
+  return orc_composite_key_index<int32_t>(key, kc, dict, entry_count);
+}
+extern "C" inline int64_t get_composite_key_index_64(const int64_t* key, const size_t kc, const int64_t* dict,
+                                                     const size_t entry_count) {
+  return orc_composite_key_index<int64_t>(key, kc, dict, entry_count);
+}

@@ -479,6 +479,32 @@ def test_group_by_perfect_hash_on_gpu(oracle_mod, torch, bigint_count):
         util.assert_rows_equal(got, util.sqlite_rows(tables, sqlite_text(text), 0), rel=1e-6)
 
 
+def test_one_to_many_joins_on_gpu(oracle_mod, torch):
+    """Duplicate build-side keys: the perfect one-to-many table and the baseline one (composite-key dictionary + offsets |
+    counts | payload), probed per row by the fused kernel with a loop over the matching set.  GPU buffer vs the oracle's
+    row function (which restates the loop) and the rows vs SQLite."""
+    import hdk_b200.hdk as hdk_mod
+    from tests.test_sqlite_oracle import ONE_TO_MANY_JOIN_QUERIES, one_to_many_tables
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables = one_to_many_tables()
+    st = util.make_storage(tables, fragment_size=700)
+    h = hdk_mod.init()
+    for name, t in tables.items():
+        h.import_arrow(t, name, fragment_size=700)
+    for text in ONE_TO_MANY_JOIN_QUERIES:
+        ex = Executor(st)
+        pq = ex.plan(sql.parse(text, st.tables))
+        prep = ex.prepare(pq)
+        assert pq.plan.joins[0].one_to_many == 1
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0, text
+        check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), pq.plan.n_keys)
+        got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+        util.assert_rows_equal(sorted(got, key=repr), sorted(util.sqlite_rows(tables, text, 0), key=repr), rel=1e-9)
+
+
 def test_group_by_boundaries_and_null_on_gpu(oracle_mod, torch):
     """GroupByBoundariesAndNull (ArrowBasedExecuteTest.cpp:2845-2866) on the device: keys at INT32_MAX / 127 / 32767 / 2^62
     with NULL keys, single and composite, buffers byte-identical to the oracle's."""

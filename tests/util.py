@@ -53,7 +53,19 @@ def oracle_inputs(oracle, st, pq):
             buf = np.empty(E * (kc + 1) * kw, dtype=np.uint8)
             L.oracle_init_baseline_hash_join_buff(buf.ctypes.data, E, kc, 1, -1, kw)
             rc = L.oracle_fill_baseline_hash_join_buff(buf.ctypes.data, E, -1, 0, kc, 1, jcs, tis, kw)
-            assert rc == 0, "oracle baseline join tables in these tests are one-to-one"
+            pj.one_to_many = 0
+            if rc == -1:
+                # duplicate composite keys: dictionary without payload, then offsets | counts | payload behind it
+                # (BaselineJoinHashTable one-to-many layout)
+                dict_bytes = E * kc * kw
+                buf = np.empty(dict_bytes + (2 * E + rows) * 4, dtype=np.uint8)
+                L.oracle_init_baseline_hash_join_buff(buf.ctypes.data, E, kc, 0, -1, kw)
+                assert L.oracle_fill_baseline_hash_join_buff(buf.ctypes.data, E, -1, 0, kc, 0, jcs, tis, kw) == 0
+                assert L.oracle_fill_one_to_many_baseline_hash_table(buf.ctypes.data + dict_bytes, buf.ctypes.data, E, -1, kc,
+                                                                     jcs, tis, kw) == 0
+                pj.one_to_many = 1
+            else:
+                assert rc == 0
             pj.entry_count = E
             join_tables.append(buf)
             inner_cols.append([np.concatenate([f.chunks[c] for f in inner.fragments]) for c in pq.inner_columns[j]])
@@ -69,9 +81,16 @@ def oracle_inputs(oracle, st, pq):
         buf = np.empty(E, dtype=np.int32)
         L.oracle_init_hash_join_buff(buf.ctypes.data, E, -1)
         rc = L.oracle_fill_hash_join_buff(buf.ctypes.data, -1, 0, C.byref(jc), C.byref(ti), 1)
-        assert rc == 0, "oracle join tables in these tests are one-to-one"
+        one_to_many = 0
+        if rc == -1:    # NeedsOneToManyHash: offsets | counts | payload
+            rows = sum(f.num_rows for f in inner.fragments)
+            buf = np.empty(2 * E + rows, dtype=np.int32)
+            L.oracle_fill_one_to_many_hash_table(buf.ctypes.data, E, -1, C.byref(jc), C.byref(ti), 1)
+            one_to_many = 1
+        else:
+            assert rc == 0
         pj = pq.plan.joins[j]
-        pj.one_to_many, pj.min_key, pj.max_key, pj.entry_count = 0, lo, hi, E
+        pj.one_to_many, pj.payload_by_slot, pj.min_key, pj.max_key, pj.entry_count = one_to_many, 0, lo, hi, E
         join_tables.append(buf)
         inner_cols.append([np.concatenate([f.chunks[c] for f in inner.fragments]) for c in pq.inner_columns[j]])
     return frs, join_tables, inner_cols
