@@ -504,6 +504,8 @@ def test_one_to_many_joins_vs_sqlite(oracle_mod, text, kind):
     st = util.make_storage(tables, fragment_size=700)
     pq = util.plan_sql(st, text)
     buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
-    assert err == 0 and pq.plan.joins[0].one_to_many == 1
+    assert err == 0
+    util.oracle_inputs(oracle_mod, st, pq)            # (describes the host-built tables in pq.plan)
+    assert pq.plan.joins[0].one_to_many == 1
     got = decode_with_dictionaries(st, pq, buf)
     util.assert_rows_equal(sorted(got, key=repr), sorted(util.sqlite_rows(tables, text, 0), key=repr), rel=1e-9)

@@ -97,8 +97,14 @@ def oracle_inputs(oracle, st, pq):
 
 
 def run_oracle(oracle, st, pq, kind="port", n_threads=2, per_fragment=True):
-    frs, jt, ic = oracle_inputs(oracle, st, pq)
-    buf, err = oracle.run_query(pq, frs, jt, ic, n_threads=n_threads, kind=kind, per_fragment=per_fragment)
+    """The oracle over its own host-built join tables.  oracle_inputs describes those tables in the plan's join PODs
+    (layout, entry count, no slot-ordered payload), so it works on a copy: `pq` may already be prepared for the GPU,
+    whose join tables are laid out differently."""
+    import copy
+    pq2 = copy.copy(pq)
+    pq2.plan = abi.Plan.from_buffer_copy(pq.plan)
+    frs, jt, ic = oracle_inputs(oracle, st, pq2)
+    buf, err = oracle.run_query(pq2, frs, jt, ic, n_threads=n_threads, kind=kind, per_fragment=per_fragment)
     return buf, err
 
 
