@@ -293,6 +293,16 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
             raise UnsupportedPlan("floating-point group keys")
     columnar = cfg.enable_columnar_output if output_columnar is None else output_columnar
     infos = [get_target_info(t, unit.groupby_exprs, cfg.bigint_count) for t in unit.target_exprs]
+    if non_grouped:
+        # NonGroupedAggregate: every aggregate over an argument skips NULLs and starts from the NULL sentinel, whatever the
+        # argument's declared nullability, so that no input row ⇒ NULL (TargetExprCodegenBuilder::operator(),
+        # QE/TargetExprBuilder.cpp:546-552; init_agg_val_vec, QE/OutputBufferInitialization.cpp:56-59)
+        for ti in infos:
+            if ti.is_agg and ti.arg is not None:
+                ti.skip_null_val = True
+                ti.arg_type = ti.arg_type.with_nullable(True)
+                if ti.agg != abi.AGG_COUNT:
+                    ti.type = ti.type.with_nullable(True)
 
     cri = get_col_range_info(unit, col_stats, cfg)
     if force_hash_type is not None and force_hash_type != cri.hash_type:
@@ -334,7 +344,9 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
             q.entry_count = max(cri.bucketed_cardinality(), 1)
             q.min_val, q.max_val, q.bucket, q.has_nulls = cri.min, cri.max, cri.bucket, int(cri.has_nulls)
         key_targets_have_slots = True
-        padded = min_slot_size
+        # slots narrower than 8 bytes make the reference retry without compaction when there is no GROUP BY
+        # (CompilationRetryNoCompaction, QE/TargetExprBuilder.cpp:520-526)
+        padded = 8 if non_grouped else min_slot_size
     else:
         q.keyless = 0
         q.target_idx_for_key = -1
@@ -399,6 +411,14 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
         return raises_memo[e]
 
     BOOL_NN, BOOL_N = ir.SqlType("bool", 1, False), ir.SqlType("bool", 1, True)
+    unsafe_memo = {}
+
+    def unsafe_division(e: ir.Expr) -> bool:
+        """contains_unsafe_division (QE/LogicalIR.cpp:26-53): a division whose divisor is not a non-zero literal"""
+        if e not in unsafe_memo:
+            own = isinstance(e, ir.BinOp) and e.op == "/" and not (isinstance(e.rhs, ir.Const) and e.rhs.value not in (None, 0, 0.0))
+            unsafe_memo[e] = own or any(unsafe_division(c) for c in e.children())
+        return unsafe_memo[e]
 
     def both(g: Optional[int], c: int) -> int:
         return c if g is None else emit(abi.OP_AND, g, c, t=BOOL_N)
@@ -470,9 +490,20 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
             if e.op == "not":
                 n = emit(abi.OP_NOT, lower(e.args[0], guard), t=e.type)
             else:
-                n = lower(e.args[0], guard)
-                for x in e.args[1:]:
-                    n = emit(abi.OP_AND if e.op == "and" else abi.OP_OR, n, lower(x, guard), t=e.type)
+                # codegenLogicalShortCircuit (QE/LogicalIR.cpp:193-298): an operand with an unsafe division is generated
+                # behind the other one and only runs when that one does not already decide the result
+                # (false AND …, true OR …, NULL).  Here: safe operands first, each unsafe one guarded by what precedes it.
+                args = [x for x in e.args if not unsafe_division(x)] + [x for x in e.args if unsafe_division(x)]
+                n = None
+                for x in args:
+                    if n is None:
+                        n = lower(x, guard)
+                        continue
+                    g_x = guard
+                    if unsafe_division(x):
+                        decided = n if e.op == "and" else emit(abi.OP_NOT, n, t=BOOL_N)   # runs when n is TRUE / FALSE
+                        g_x = both(guard, decided)
+                    n = emit(abi.OP_AND if e.op == "and" else abi.OP_OR, n, lower(x, g_x), t=e.type)
         elif isinstance(e, ir.IsNull):
             n = emit(abi.OP_IS_NULL, lower(e.arg, guard), t=e.type)
         else:
@@ -506,8 +537,16 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
     if len(unit.quals) > abi.MAX_FILTERS:
         raise UnsupportedPlan("too many filters")
     p.n_filters = len(unit.quals)
-    for i, f in enumerate(unit.quals):
+    # quals with an unsafe division are deferred behind the others and only run for rows those accept
+    # (should_defer_eval, QE/LogicalIR.cpp:57-74; Executor::compileBody's primary / deferred quals)
+    primary = [f for f in unit.quals if not unsafe_division(f)]
+    deferred = [f for f in unit.quals if unsafe_division(f)]
+    passed = None
+    for i, f in enumerate(primary):
         p.filters[i] = lower(f)
+        passed = both(passed, p.filters[i]) if deferred else None
+    for i, f in enumerate(deferred):
+        p.filters[len(primary) + i] = lower(f, passed)
     p.n_keys = len(unit.groupby_exprs)
     for i, g in enumerate(unit.groupby_exprs):
         k = p.keys[i]

@@ -98,13 +98,14 @@ def _ptr(a):
 class Fragments:
     """Host chunks laid out like ColumnFetcher hands them to a kernel: col_buffers[frag][col]."""
 
-    def __init__(self, frags):
-        # frags: list of list of contiguous numpy arrays (one per plan column)
+    def __init__(self, frags, num_rows=None):
+        # frags: list of list of contiguous numpy arrays (one per plan column); num_rows: rows per fragment (needed when
+        # the query reads no column at all, e.g. SELECT COUNT(*) FROM t WHERE 1 = 1 — fragment metadata in the reference)
         self.frags = [[np.ascontiguousarray(c) for c in f] for f in frags]
         self.n_frag = len(self.frags)
         self.n_cols = len(self.frags[0]) if self.frags else 0
-        self.ptrs = np.array([c.ctypes.data for f in self.frags for c in f], dtype=np.uint64)
-        self.num_rows = np.array([len(f[0]) if f else 0 for f in self.frags], dtype=np.int64)
+        self.ptrs = np.array([c.ctypes.data for f in self.frags for c in f] or [0], dtype=np.uint64)
+        self.num_rows = np.array([len(f[0]) if f else 0 for f in self.frags] if num_rows is None else list(num_rows), dtype=np.int64)
 
 
 def run_query(planned, frags: Fragments, join_tables=None, inner_cols=None, n_threads=1, kind="port",

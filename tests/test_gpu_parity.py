@@ -505,6 +505,28 @@ def test_one_to_many_joins_on_gpu(oracle_mod, torch):
         util.assert_rows_equal(sorted(got, key=repr), sorted(util.sqlite_rows(tables, text, 0), key=repr), rel=1e-9)
 
 
+def test_reference_simple_aggregation_and_short_circuit_on_gpu(oracle_mod, torch):
+    """The harvested Select.FilterAndSimpleAggregation / FilterAndMultipleAggregation / In queries (constant-only quals that
+    read no column, aggregates over zero passing rows, narrowing casts inside quals …), the short-circuit cases and the
+    divisions that must raise — through the façade, rows vs SQLite, error code vs the reference's behaviour."""
+    import hdk_b200.hdk as hdk_mod
+    from hdk_b200.executor import QueryError
+    from tests.test_sqlite_oracle import DIV_BY_ZERO_QUERIES, REFERENCE_SIMPLE_QUERIES, SHORT_CIRCUIT_QUERIES, reference_test_table
+    tables = reference_test_table()
+    h = hdk_mod.init()
+    h.import_arrow(tables["test"], "test", fragment_size=2)
+    for text in REFERENCE_SIMPLE_QUERIES + SHORT_CIRCUIT_QUERIES:
+        got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+        exp = util.sqlite_rows(tables, text, 0)
+        if "ORDER BY" not in text:
+            got, exp = sorted(got, key=repr), sorted(exp, key=repr)
+        util.assert_rows_equal(got, exp, rel=1e-6)
+    for text in DIV_BY_ZERO_QUERIES:
+        with pytest.raises(QueryError) as ei:
+            h.sql(text).to_arrow()
+        assert ei.value.code == 1, text
+
+
 def test_group_by_boundaries_and_null_on_gpu(oracle_mod, torch):
     """GroupByBoundariesAndNull (ArrowBasedExecuteTest.cpp:2845-2866) on the device: keys at INT32_MAX / 127 / 32767 / 2^62
     with NULL keys, single and composite, buffers byte-identical to the oracle's."""

@@ -28,7 +28,7 @@ _KEEP = []   # ctypes temporaries referenced by JoinColumn structs
 def oracle_inputs(oracle, st, pq):
     """Fragments + host-built join tables / inner columns for the oracle (and query_host)."""
     outer = st.get_table(pq.unit.table)
-    frs = oracle.Fragments([[fr.chunks[c] for c in pq.columns] for fr in outer.fragments])
+    frs = oracle.Fragments([[fr.chunks[c] for c in pq.columns] for fr in outer.fragments], [fr.num_rows for fr in outer.fragments])
     join_tables, inner_cols = [], []
     for j, js in enumerate(pq.unit.joins):
         inner = st.get_table(js.inner_table)
