@@ -216,11 +216,11 @@ class ResultSet:
                 if is_fp:
                     v = raw.astype(np.int32).view(np.float32).astype(np.float64) if f4 else raw.view(np.float64)
                     null = np.float64(np.float32(abi.FLT_MIN)) if chosen.width == 4 else abi.DBL_MIN
-                    col = np.ma.array(v, mask=(v == null))
+                    col = np.ma.array(v, mask=(v == null) & chosen.nullable)     # ResultSet::isNull: a NOT NULL type never is
                 else:
                     w = chosen.width
                     trunc = raw if w == 8 else raw.astype({1: np.int8, 2: np.int16, 4: np.int32}[w]).astype(np.int64)
-                    col = np.ma.array(raw, mask=(trunc == abi.int_null(w)))
+                    col = np.ma.array(raw, mask=(trunc == abi.int_null(w)) & chosen.nullable)
             cols.append(col[valid])
         self._cols = cols
         return cols
@@ -240,9 +240,9 @@ class ResultSet:
             elif chosen.is_fp and ti.agg != abi.AGG_COUNT:
                 v = c.view(np.float64)
                 null = np.float64(np.float32(abi.FLT_MIN)) if (ti.float_argument_input or chosen.width == 4) else abi.DBL_MIN
-                cols.append(np.ma.array(v, mask=(v == null)))
+                cols.append(np.ma.array(v, mask=(v == null) & chosen.nullable))
             else:
-                cols.append(np.ma.array(c, mask=(c == abi.int_null(ti.type.width))))
+                cols.append(np.ma.array(c, mask=(c == abi.int_null(ti.type.width)) & chosen.nullable))
         rs._cols = cols
         return rs
 
@@ -261,7 +261,8 @@ class ResultSet:
             else:
                 width = ti.type.width
             d = self.dictionaries.get(t) if (not ti.is_agg and ti.type.kind == "dict") else None
-            out.append(dict(column=t, is_fp=int(is_fp), type_width=width, nullable=1, is_desc=int(bool(desc)),
+            nullable = 1 if ti.agg == abi.AGG_AVG else int(chosen.nullable)
+            out.append(dict(column=t, is_fp=int(is_fp), type_width=width, nullable=nullable, is_desc=int(bool(desc)),
                             nulls_first=int(bool(nulls_first)), dictionary=d))
         return out
 

@@ -527,6 +527,27 @@ def test_reference_simple_aggregation_and_short_circuit_on_gpu(oracle_mod, torch
         assert ei.value.code == 1, text
 
 
+def test_reference_harvested_queries_on_gpu(oracle_mod, torch):
+    """The 170-odd queries harvested from the reference's Select.* tests (tests/test_sqlite_oracle.py) through the façade
+    on the device: rows (in order where the query orders them) vs SQLite."""
+    import hdk_b200.hdk as hdk_mod
+    from tests.test_sqlite_oracle import REFERENCE_HARVESTED_QUERIES, harvested_tables
+    tables = harvested_tables()
+    h = hdk_mod.init()
+    for name, t in tables.items():
+        h.import_arrow(t, name, fragment_size=2)
+    for name, queries in REFERENCE_HARVESTED_QUERIES.items():
+        for text in queries:
+            got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+            exp = util.sqlite_rows(tables, text, 0)
+            if "ORDER BY" not in text.upper():
+                got, exp = sorted(got, key=repr), sorted(exp, key=repr)
+            try:
+                util.assert_rows_equal(got, exp, rel=1e-6)
+            except AssertionError as e:
+                raise AssertionError(f"{name}: {text}: {e}")
+
+
 def test_group_by_boundaries_and_null_on_gpu(oracle_mod, torch):
     """GroupByBoundariesAndNull (ArrowBasedExecuteTest.cpp:2845-2866) on the device: keys at INT32_MAX / 127 / 32767 / 2^62
     with NULL keys, single and composite, buffers byte-identical to the oracle's."""

@@ -655,3 +655,253 @@ def test_unsafe_divisions_short_circuit_like_the_reference(oracle_mod):
             util.assert_rows_equal(decode_with_dictionaries(st, pq, buf), util.sqlite_rows(tables, text, 0))
     for text in DIV_BY_ZERO_QUERIES:
         assert util.run_oracle(oracle_mod, st, util.plan_sql(st, text))[1] == 1, text
+
+
+# Every other query of the reference's Select.* tests (ArrowBasedExecuteTest.cpp) that the SQL subset accepts over the reduced
+# fixtures — harvested verbatim, grouped by the test they come from.  (Select.ReturnNullFromDivByZero runs under
+# Config::exec.codegen.null_div_by_zero, which is not implemented: division by zero always raises.)
+REFERENCE_HARVESTED_QUERIES = {
+    'FloatAndDoubleTests': [
+        'SELECT MIN(f) FROM test',
+        'SELECT MAX(f) FROM test',
+        'SELECT AVG(f) FROM test',
+        'SELECT MIN(d) FROM test',
+        'SELECT MAX(d) FROM test',
+        'SELECT AVG(d) FROM test',
+        'SELECT SUM(f) FROM test',
+        'SELECT SUM(d) FROM test',
+        'SELECT SUM(f + d) FROM test',
+        'SELECT AVG(x * f) FROM test',
+        'SELECT AVG(z - 200) FROM test',
+        'SELECT SUM(CAST(x AS FLOAT)) FROM test',
+        'SELECT SUM(CAST(x AS FLOAT)) FROM test GROUP BY z',
+        'SELECT AVG(CAST(x AS FLOAT)) FROM test',
+        'SELECT AVG(CAST(x AS FLOAT)) FROM test GROUP BY y',
+        'SELECT COUNT(*) FROM test WHERE f > 1.0 AND f < 1.2',
+        'SELECT COUNT(*) FROM test WHERE f > 1.101 AND f < 1.299',
+        'SELECT COUNT(*) FROM test WHERE f > 1.201 AND f < 1.4',
+        'SELECT COUNT(*) FROM test WHERE f > 1.0 AND f < 1.2 AND d > 2.0 AND d < 2.4',
+        'SELECT COUNT(*) FROM test WHERE f > 1.0 AND f < 1.2 OR (d > 2.0 AND d < 3.0)',
+        'SELECT SUM(x + y) FROM test WHERE f > 1.0 AND f < 1.2',
+        'SELECT SUM(x + y) FROM test WHERE d + f > 3.0 AND d + f < 4.0',
+        'SELECT SUM(f + d) FROM test WHERE x - y = -35',
+        'SELECT SUM(f + d) FROM test WHERE x + y + 1 = 50',
+        'SELECT SUM(f * d + 15) FROM test WHERE x + y + 1 = 50',
+        'SELECT MIN(x), AVG(x * y), MAX(y + 7), AVG(x * f + 15), COUNT(*) FROM test WHERE x + y > 47 AND x + y < 51',
+    ],
+    'GroupBy': [
+        'SELECT x, y, COUNT(*) FROM test GROUP BY x, y',
+        'SELECT x, COUNT(x) FROM test GROUP BY x',
+        'SELECT x, y, COUNT(x) FROM test GROUP BY x,y',
+    ],
+    'FilterAndGroupBy': [
+        'SELECT MIN(x + y) FROM test WHERE x + y > 47 AND x + y < 53 GROUP BY x, y',
+        'SELECT MIN(x + y) FROM test WHERE x + y > 47 AND x + y < 53 GROUP BY x + 1, x + y',
+        'SELECT x, y, COUNT(*) FROM test GROUP BY x, y',
+        'SELECT str, MIN(y) FROM test WHERE y IS NOT NULL GROUP BY str ORDER BY str DESC',
+        'SELECT y, AVG(CASE WHEN x BETWEEN 6 AND 7 THEN x END) FROM test GROUP BY y ORDER BY y',
+        'SELECT CASE WHEN x > 8 THEN 100000000 ELSE 42 END AS c, COUNT(*) FROM test GROUP BY c',
+        'SELECT COUNT(*) FROM test WHERE CAST((CAST(x AS FLOAT) - 1) * 0.2 AS INT) = 1',
+        'SELECT CAST(CAST(d/2 AS FLOAT) AS INTEGER) AS key, COUNT(*) FROM test GROUP BY key',
+        'SELECT str, SUM(y - y) FROM test GROUP BY str ORDER BY str ASC',
+        'SELECT str, SUM(y - y) FROM test WHERE y - y IS NOT NULL GROUP BY str ORDER BY str ASC',
+        'SELECT x, SUM(z) FROM test WHERE z IS NOT NULL GROUP BY x ORDER BY x',
+    ],
+    'OrderBy': [
+        'SELECT ufd, COUNT(*) n FROM test GROUP BY ufd, str ORDER BY ufd, n',
+        'SELECT str, COUNT(*) n FROM test WHERE x < 0 GROUP BY str ORDER BY n DESC LIMIT 5',
+    ],
+    'GroupByPushDownFilterIntoExprRange': [
+        'SELECT x, COUNT(*) AS n FROM test WHERE x > 7 GROUP BY x ORDER BY x',
+        'SELECT y, COUNT(*) AS n FROM test WHERE y < 43 GROUP BY y ORDER BY n DESC',
+        'SELECT z, COUNT(*) AS n FROM test WHERE z <= 43 AND y > 10 GROUP BY z ORDER BY n DESC',
+        'SELECT t, SUM(y) AS sum_y FROM test WHERE t < 2000 GROUP BY t ORDER BY t DESC',
+        'SELECT t, SUM(y) AS sum_y FROM test WHERE t < 2000 GROUP BY t ORDER BY sum_y',
+        'SELECT t + x, AVG(x) AS avg_x FROM test WHERE z <= 50 and t < 2000 GROUP BY t + x ORDER BY avg_x DESC',
+    ],
+    'GroupByExprNoFilterNoAggregate': [
+        'SELECT x + y AS a FROM test GROUP BY a ORDER BY a',
+    ],
+    'Case': [
+        'SELECT SUM(CASE WHEN x BETWEEN 6 AND 7 THEN 1 WHEN x BETWEEN 8 AND 9 THEN 2 ELSE 3 END) FROM test',
+        'SELECT SUM(CASE WHEN x BETWEEN 6 AND 7 THEN 1 END) FROM test',
+        'SELECT SUM(CASE WHEN x BETWEEN 6 AND 7 THEN 1 WHEN x BETWEEN 8 AND 9 THEN 2 ELSE 3 END) FROM test WHERE CASE WHEN y BETWEEN 42 AND 43 THEN 5 ELSE 4 END > 4',
+        'SELECT CASE WHEN x + y > 50 THEN 77 ELSE 88 END AS foo, COUNT(*) FROM test GROUP BY foo ORDER BY foo',
+        'SELECT y AS key0, SUM(CASE WHEN x > 7 THEN x / (x - 7) ELSE 99 END) FROM test GROUP BY key0 ORDER BY key0',
+        "SELECT COUNT(CASE WHEN str = 'foo' THEN 1 END) FROM test",
+        "SELECT COUNT(CASE WHEN str = 'foo' THEN 1 ELSE NULL END) FROM test",
+        'SELECT x, AVG(CASE WHEN y BETWEEN 41 AND 42 THEN y END) FROM test GROUP BY x ORDER BY x',
+        'SELECT x, SUM(CASE WHEN y BETWEEN 41 AND 42 THEN y END) FROM test GROUP BY x ORDER BY x',
+        'SELECT x, COUNT(CASE WHEN y BETWEEN 41 AND 42 THEN y END) FROM test GROUP BY x ORDER BY x',
+        'SELECT x, COUNT(case when y = 42 then 1 else 0 end) AS n1, COUNT(*) AS n2 FROM test GROUP BY x ORDER BY n2 DESC',
+    ],
+    'Strings': [
+        'SELECT str, COUNT(*) FROM test where str IS NOT NULL GROUP BY str ORDER BY str',
+        'SELECT COUNT(*) FROM test WHERE str IS NULL',
+        'SELECT COUNT(*) FROM test WHERE str IS NOT NULL',
+        "SELECT COUNT(*) FROM test WHERE str = 'bar'",
+        "SELECT COUNT(*) FROM test WHERE 'bar' = str",
+        "SELECT COUNT(*) FROM test WHERE str <> 'bar'",
+        "SELECT COUNT(*) FROM test WHERE 'bar' <> str",
+        "SELECT COUNT(*) FROM test WHERE str = 'foo' OR str = 'bar'",
+        'SELECT COUNT(*) FROM test WHERE str <> str',
+    ],
+    'StringCompare': [
+        "SELECT COUNT(*) FROM test WHERE str = 'ba'",
+        "SELECT COUNT(*) FROM test WHERE str <> 'ba'",
+    ],
+    'ReturnNullFromDivByZero': [
+        'SELECT COUNT(*) FROM test WHERE x = x OR  y / (x - x) = y',
+    ],
+    'ConstantFolding': [
+        'SELECT COUNT(*) FROM test WHERE 3.0+8 < 30',
+        'SELECT COUNT(*) FROM test WHERE 3.0*8 > 30.01',
+        'SELECT COUNT(*) FROM test WHERE 3.0*8 > 30.0001',
+        'SELECT COUNT(*) FROM test WHERE t > 0 AND t = t',
+        'SELECT COUNT(*) FROM test WHERE t > 0 AND t <> t',
+        'SELECT COUNT(*) FROM test WHERE t > 0 OR t = t',
+        'SELECT COUNT(*) FROM test WHERE t > 0 OR t <> t',
+        'SELECT COUNT(*) FROM test where (604=575) OR (33.0<>12 AND 2.0001e+4>20000.9) OR (NOT t>=t OR f<>f OR (x=x AND x-x=0))',
+    ],
+    'OverflowAndUnderFlow': [
+        'SELECT COUNT(*) FROM test WHERE z + 32600 > 0',
+        'SELECT COUNT(*) FROM test WHERE z + 32666 > 0',
+        'SELECT COUNT(*) FROM test WHERE -32670 - z < 0',
+        'SELECT COUNT(*) FROM test WHERE (z + 16333) * 2 > 0',
+        'SELECT COUNT(*) FROM test WHERE t + 9223372036854774000 > 0',
+        'select count(*) from test where (t*123456 > 9681668.33071388567)',
+        'select count(*) from test where (x*12345678 < 9681668.33071388567)',
+        'select count(*) from test where (z*12345678 < 9681668.33071388567)',
+    ],
+    'ExpressionRewrite': [
+        'SELECT count(*) from test where f/2.0 >= 0.6',
+        'SELECT count(*) from test where d/0.5 < 5.0',
+    ],
+    'OrRewrite': [
+        "SELECT COUNT(*) FROM test WHERE str = 'foo' OR str = 'bar' OR str = 'baz' OR str = 'foo' OR str = 'bar' OR str = 'baz' OR str = 'foo' OR str = 'bar' OR str = 'baz' OR str = 'baz' OR str = 'foo' OR str = 'bar' OR str = 'baz'",
+        'SELECT COUNT(*) FROM test WHERE x = 7 OR x = 8 OR x = 7 OR x = 8 OR x = 7 OR x = 8 OR x = 7 OR x = 8 OR x = 7 OR x = 8 OR x = 7 OR x = 8',
+    ],
+    'GroupByPerfectHash': [
+        'SELECT COUNT(*) FROM test GROUP BY x ORDER BY x DESC',
+        'SELECT y, COUNT(*) FROM test GROUP BY y ORDER BY y DESC',
+        'SELECT str, COUNT(*) FROM test GROUP BY str ORDER BY str DESC',
+        'SELECT COUNT(*), z FROM test where x = 7 GROUP BY z ORDER BY z DESC',
+        'SELECT z as z0, z as z1, COUNT(*) FROM test GROUP BY z0, z1 ORDER BY z0 DESC',
+        'SELECT x, COUNT(y), SUM(y), AVG(y), MIN(y), MAX(y) FROM test GROUP BY x ORDER BY x DESC',
+        'SELECT str, x FROM test GROUP BY x, str ORDER BY str, x',
+    ],
+    'Empty': [
+        'SELECT COUNT(*) FROM emptytab',
+        'SELECT SUM(x) FROM emptytab',
+        'SELECT SUM(y) FROM emptytab',
+        'SELECT SUM(t) FROM emptytab',
+        'SELECT SUM(f) FROM emptytab',
+        'SELECT SUM(d) FROM emptytab',
+        'SELECT MIN(x) FROM emptytab',
+        'SELECT MIN(y) FROM emptytab',
+        'SELECT MIN(t) FROM emptytab',
+        'SELECT MIN(f) FROM emptytab',
+        'SELECT MIN(d) FROM emptytab',
+        'SELECT MAX(x) FROM emptytab',
+        'SELECT MAX(y) FROM emptytab',
+        'SELECT MAX(t) FROM emptytab',
+        'SELECT MAX(f) FROM emptytab',
+        'SELECT MAX(d) FROM emptytab',
+        'SELECT AVG(x) FROM emptytab',
+        'SELECT AVG(y) FROM emptytab',
+        'SELECT AVG(t) FROM emptytab',
+        'SELECT AVG(f) FROM emptytab',
+        'SELECT AVG(d) FROM emptytab',
+        'SELECT COUNT(*) FROM test WHERE x > 8',
+        'SELECT SUM(x) FROM test WHERE x > 8',
+        'SELECT SUM(f) FROM test WHERE x > 8',
+        'SELECT SUM(d) FROM test WHERE x > 8',
+    ],
+    'Joins_ImplicitJoins': [
+        'SELECT COUNT(*) FROM test, test_inner WHERE test.x = test_inner.x',
+        'SELECT COUNT(*) FROM test, hash_join_test WHERE test.t = hash_join_test.t',
+        'SELECT test_inner.x, COUNT(*) AS n FROM test, test_inner WHERE test.x = test_inner.x GROUP BY test_inner.x ORDER BY n',
+        'SELECT COUNT(*) FROM test, test_inner WHERE test.str = test_inner.str',
+        'SELECT test.str, COUNT(*) FROM test, test_inner WHERE test.str = test_inner.str GROUP BY test.str',
+        'SELECT test_inner.str, COUNT(*) FROM test, test_inner WHERE test.str = test_inner.str GROUP BY test_inner.str',
+        'SELECT a.x, b.str FROM test a, join_test b WHERE a.str = b.str GROUP BY a.x, b.str ORDER BY a.x, b.str',
+        'SELECT COUNT(1) FROM test a, join_test b, test_inner c WHERE a.str = b.str AND b.x = c.x',
+        "SELECT COUNT(*) FROM test a, join_test b, test_inner c WHERE a.x = b.x AND a.y = b.x AND a.x = c.x AND c.str = 'foo'",
+        'SELECT COUNT(*) FROM test a, test b WHERE a.x = b.x AND a.y = b.y',
+        'SELECT SUM(b.y) FROM test a, test b WHERE a.x = b.x AND a.y = b.y',
+        'SELECT COUNT(*) FROM test a, test b WHERE a.x = b.x AND a.str = b.str',
+    ],
+    'Joins_InnerJoin_TwoTables': [
+        'SELECT COUNT(*) FROM test JOIN test_inner ON test.x = test_inner.x',
+        'SELECT COUNT(*) FROM test a JOIN join_test b ON a.str = b.dup_str',
+        'SELECT a.x FROM test a JOIN join_test b ON a.str = b.dup_str GROUP BY a.x ORDER BY a.x',
+    ],
+    'Joins_InnerJoin_AtLeastThreeTables': [
+        'SELECT count(*) FROM test AS a JOIN join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str',
+        'SELECT count(*) FROM test AS a JOIN join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str JOIN join_test AS d ON c.x = d.x',
+        'SELECT a.y, count(*) FROM test AS a JOIN join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str GROUP BY a.y',
+        'SELECT count(*) FROM test AS a JOIN hash_join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str',
+        'SELECT count(*) FROM test AS a JOIN hash_join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str JOIN hash_join_test AS d ON c.x = d.x',
+        'SELECT count(*) FROM test AS a JOIN hash_join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str JOIN join_test AS d ON c.x = d.x',
+        'SELECT count(*) FROM test AS a JOIN join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str JOIN hash_join_test AS d ON c.x = d.x',
+        'SELECT COUNT(1) FROM test AS a JOIN join_test AS b ON a.x = b.x JOIN test_inner AS c ON a.t = c.x',
+    ],
+    'Joins_InnerJoin_Filters': [
+        'SELECT count(*) FROM test AS a JOIN join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str WHERE a.y < 43',
+        'SELECT SUM(a.x), b.str FROM test AS a JOIN join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str WHERE a.y = 43 group by b.str',
+        'SELECT count(*) FROM test AS a JOIN hash_join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str WHERE a.y < 43',
+        'SELECT SUM(a.x), b.str FROM test AS a JOIN hash_join_test AS b ON a.x = b.x JOIN test_inner AS c ON b.str = c.str WHERE a.y = 43 group by b.str',
+        "SELECT COUNT(*) FROM test a JOIN join_test b ON a.x = b.x JOIN test_inner c ON c.str = a.str WHERE c.str = 'foo'",
+        'SELECT COUNT(*) FROM test t1 JOIN test t2 ON t1.x = t2.x WHERE t1.y > t2.y',
+    ],
+    'Joins_MultiCompositeColumns': [
+        "SELECT COUNT(*) FROM test a JOIN join_test b ON a.x = b.x AND a.y = b.x JOIN test_inner c ON a.x = c.x WHERE c.str <> 'foo'",
+    ],
+    'Joins_BuildHashTable': [
+        'SELECT COUNT(*) FROM test, join_test WHERE test.str = join_test.dup_str',
+    ],
+    'Joins_OneOuterExpression': [
+        'SELECT COUNT(*) FROM test, test_inner WHERE test.x - 1 = test_inner.x',
+        'SELECT COUNT(*) FROM test, test_inner WHERE test.x + 0 = test_inner.x',
+        'SELECT COUNT(*) FROM test, test_inner WHERE test.x + 1 = test_inner.x',
+    ],
+    'Joins_MultipleOuterExpressions': [
+        'SELECT COUNT(*) FROM test, test_inner WHERE test.x - 1 = test_inner.x AND test.str = test_inner.str',
+        'SELECT COUNT(*) FROM test, test_inner WHERE test.x + 0 = test_inner.x AND test.str = test_inner.str',
+        'SELECT COUNT(*) FROM test, test_inner WHERE test.str = test_inner.str AND test.x + 0 = test_inner.x',
+        'SELECT COUNT(*) FROM test, test_inner WHERE test.x + 1 = test_inner.x AND test.str = test_inner.str',
+        'SELECT COUNT(*) FROM test, test_inner WHERE test.x + 0 = test_inner.x AND test_inner.str = test.str',
+    ],
+    'WatchdogTest': [
+        'SELECT x, SUM(f) AS n FROM test GROUP BY x ORDER BY n DESC LIMIT 5',
+        "SELECT COUNT(*) FROM test WHERE str = 'abcdefghijklmnopqrstuvwxyzabcdefghijklmnopqrstuvwxyz'",
+    ],
+    'LogicalSizedColumns': [
+        'SELECT MIN(tiny_int), MAX(tiny_int), MIN(tiny_int_null), MAX(tiny_int_null), COUNT(tiny_int), SUM(tiny_int), AVG(tiny_int) FROM logical_size_test',
+        'SELECT id, COUNT(tiny_int), COUNT(tiny_int_null), MAX(tiny_int), MIN(TINY_INT),SUM(tiny_int), SUM(tiny_int_null), AVG(tiny_int), AVG(tiny_int_null) FROM logical_size_test GROUP BY id ORDER BY id',
+        'SELECT id, COUNT(small_int_null), COUNT(small_int), SUM(small_int_null), SUM(small_int), AVG(small_int_null), AVG(small_int) FROM logical_size_test GROUP BY id ORDER BY id',
+        'SELECT id, MAX(tiny_int), MAX(small_int_null), MAX(big_int), MAX(tiny_int_null),MAX(id_null), MAX(small_int) FROM logical_size_test GROUP BY id ORDER BY id',
+        'SELECT id, MIN(tiny_int), MIN(small_int_null), MIN(big_int_null), MIN(tiny_int_null),MIN(big_int), MIN(small_int) FROM logical_size_test GROUP BY id ORDER BY id',
+        'SELECT id, MAX(big_int_null), COUNT(small_int_null), COUNT(tiny_int) FROM logical_size_test GROUP BY id ORDER BY id',
+    ],
+}
+
+
+def harvested_tables():
+    tables = reference_join_tables()
+    tables["logical_size_test"] = logical_size_tables()["logical_size_test"]
+    return tables
+
+
+@pytest.mark.parametrize("name", sorted(REFERENCE_HARVESTED_QUERIES))
+def test_reference_harvested_queries_vs_sqlite(oracle_mod, name):
+    tables = harvested_tables()
+    st = util.make_storage(tables, fragment_size=2)
+    for text in REFERENCE_HARVESTED_QUERIES[name]:
+        pq = util.plan_sql(st, text)
+        buf, err = util.run_oracle(oracle_mod, st, pq, kind="reference")
+        assert err == 0, text
+        got, exp = decode_with_dictionaries(st, pq, buf), util.sqlite_rows(tables, text, 0)
+        if "ORDER BY" not in text.upper():
+            got, exp = sorted(got, key=repr), sorted(exp, key=repr)
+        util.assert_rows_equal(got, exp, rel=1e-6)
