@@ -70,7 +70,11 @@ __device__ __forceinline__ void for_each_elem(const JoinCol& c, F&& f) {
     for (uint64_t i = start; i < chunk.num_elems; i += step) {
       int64_t elem = join_decode(chunk.col_buff, i, c.elem_sz, c.column_type, c.null_val);
       if (elem == c.null_val) {
-        if (c.uses_bw_eq) elem = c.translated_null_val; else continue;
+        if (c.uses_bw_eq) elem = c.translated_null_val; else continue;   // (the translated NULL has its own entry past max_val)
+      } else if (elem < c.min_val || elem > c.max_val) {
+        // outside the declared range the element would index outside the table (the reference trusts its metadata and
+        // would write out of bounds): ignored here
+        continue;
       }
       f(elem, chunk.row_id + i);
     }

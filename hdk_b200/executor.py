@@ -379,8 +379,8 @@ class Executor:
             dchunks = self.ctx.upload(host_chunks)
             keep.append(dchunks)
             jcs[k] = abi.JoinColumn(dchunks.data_ptr(), len(host_chunks), len(inner.fragments), row, ci.phys_width)
-            tis[k] = abi.JoinColumnTypeInfo(ci.phys_width, lo, hi, abi.int_null(ci.phys_width), 0, 0,
-                                            abi.SMALL_DATE if ci.type.date_in_days else abi.SIGNED)
+            # (a days-encoded date key joins on its stored days on both sides, ir.join_key_for: plain SIGNED elements)
+            tis[k] = abi.JoinColumnTypeInfo(ci.phys_width, lo, hi, abi.int_null(ci.phys_width), 0, 0, abi.SIGNED)
         return jcs, tis, rows, keep
 
     def build_baseline_join_table(self, inner: Table, key_cols, key_width: int) -> JoinTable:
@@ -451,8 +451,7 @@ class Executor:
         host_chunks = np.frombuffer(bytes(chunks), dtype=np.uint8)
         dchunks = self.ctx.upload(host_chunks)
         jc = abi.JoinColumn(dchunks.data_ptr(), len(host_chunks), len(inner.fragments), row, ci.phys_width)
-        ti = abi.JoinColumnTypeInfo(ci.phys_width, lo, hi, abi.int_null(ci.phys_width), 0, 0,
-                                    abi.SMALL_DATE if ci.type.date_in_days else abi.SIGNED)
+        ti = abi.JoinColumnTypeInfo(ci.phys_width, lo, hi, abi.int_null(ci.phys_width), 0, 0, abi.SIGNED)
         st = self.ctx.stream_ptr()
         buf = torch.empty(entries * 4, dtype=torch.uint8, device=self.ctx.device)
         err = torch.zeros(1, dtype=torch.int32, device=self.ctx.device)

@@ -55,8 +55,12 @@ class QueryNode:
         rhs_cols = lhs_cols if rhs_cols is None else ([rhs_cols] if isinstance(rhs_cols, str) else list(rhs_cols))
         if len(lhs_cols) != len(rhs_cols) or not lhs_cols:
             raise ValueError("join: left and right key lists differ in length")
-        spec = ir.JoinSpec(rhs.table_name, self.ref(lhs_cols[0]), rhs_cols[0],
-                           [(self.ref(lc), rc) for lc, rc in zip(lhs_cols[1:], rhs_cols[1:])])   # > 1 column: baseline join table
+        inner_t = self._hdk.storage.get_table(rhs.table_name)
+        try:
+            keys = [(ir.join_key_for(self.ref(lc), inner_t.columns[rc].type), rc) for lc, rc in zip(lhs_cols, rhs_cols)]
+        except NotImplementedError as ex:
+            raise planner.UnsupportedPlan(str(ex))
+        spec = ir.JoinSpec(rhs.table_name, keys[0][0], rhs_cols[0], keys[1:])   # > 1 column: baseline join table
         return QueryNode(self._hdk, self.table_name, self._quals, self._joins + [spec])
 
     def _parse_expr(self, text: str) -> ir.Expr:

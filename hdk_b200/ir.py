@@ -224,6 +224,23 @@ def make_case(arms, else_: Optional[Expr]) -> Expr:
     return Case(tuple((c, conv(v)) for c, v in arms), conv(else_) if else_ is not None else Const(None, t), t)
 
 
+def join_key_for(outer: Expr, inner_type: SqlType) -> Expr:
+    """The probe-side expression of one equi-join component.  The join table is built over the inner column's stored
+    values; a days-encoded date column stores days while its expressions decode to seconds, so a date = date component
+    probes with the outer column's stored days too.  Any other pairing with a days-encoded column is refused, and so are
+    dictionary-encoded keys (two dictionaries: the ids are unrelated)."""
+    if inner_type.kind == "dict" or outer.type.kind == "dict":
+        raise NotImplementedError("join on dictionary-encoded columns needs a dictionary translation")
+    if inner_type.date_in_days or outer.type.date_in_days:
+        if isinstance(outer, ColumnRef) and outer.type.date_in_days and inner_type.date_in_days and outer.phys_width == 4:
+            return ColumnRef(outer.table, outer.column, SqlType("int", 4, outer.type.nullable), outer.phys_width)
+        raise NotImplementedError("join of a days-encoded date column with anything but another one")
+    if (inner_type.kind == "timestamp" or outer.type.kind == "timestamp") and \
+            (inner_type.kind, inner_type.unit) != (outer.type.kind, outer.type.unit):
+        raise NotImplementedError("join of timestamps of different precision")
+    return outer
+
+
 def make_binop(op: str, lhs: Expr, rhs: Expr) -> Expr:
     t = common_numeric_type(lhs.type, rhs.type)
     lhs, rhs = cast_to(lhs, t), cast_to(rhs, t)

@@ -138,7 +138,19 @@ class _Parser:
 
     def _equals(self, op, lhs, rhs):
         lhs, rhs = self._coerce_temporal(lhs, rhs)
+        literal = lambda e: isinstance(e, ir.Const) and isinstance(e.value, str)   # noqa: E731
+        if not (literal(lhs) or literal(rhs)):
+            if lhs.type.kind == "dict" and rhs.type.kind == "dict" and not (
+                    isinstance(lhs, ir.ColumnRef) and isinstance(rhs, ir.ColumnRef) and (lhs.table, lhs.column) == (rhs.table, rhs.column)):
+                # ids of two dictionaries are unrelated; the reference translates one dictionary into the other
+                # (StringDictionaryTranslationMgr) — out of scope here, and never compared by id
+                raise UnsupportedPlan("comparison of two dictionary-encoded columns needs a dictionary translation")
+            if (lhs.type.kind == "dict") != (rhs.type.kind == "dict"):
+                raise UnsupportedPlan("comparison of a dictionary-encoded column with a non-string expression")
         lhs, rhs = self._coerce_dict_literal(lhs, rhs, op)
+        unit_of = lambda t: t.unit if t.kind == "timestamp" else (1 if t.kind == "date" else None)   # noqa: E731
+        if unit_of(lhs.type) and unit_of(rhs.type) and unit_of(lhs.type) != unit_of(rhs.type):
+            raise UnsupportedPlan("comparison of temporal values of different precision")
         return ir.make_cmp(op, lhs, rhs)
 
     def cmp_expr(self):
@@ -456,7 +468,10 @@ class _Parser:
                     outer, inner = rhs, lhs
                 else:
                     raise UnsupportedPlan("join condition must compare an outer expression with an inner column")
-                pairs.append((outer, inner.column))
+                try:
+                    pairs.append((ir.join_key_for(outer, inner.type), inner.column))
+                except NotImplementedError as ex:
+                    raise UnsupportedPlan(str(ex))
             joins.append(ir.JoinSpec(t2, pairs[0][0], pairs[0][1], pairs[1:]))
         final_names = []
         for i, (e, n) in enumerate(zip(targets, names)):

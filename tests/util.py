@@ -148,7 +148,9 @@ def sqlite_rows(tables, text, n_keys):
     for name, t in tables.items():
         cols = t.column_names
         con.execute(f"CREATE TABLE {name} ({', '.join(cols)})")
-        data = list(zip(*[t.column(c).to_pylist() for c in cols]))
+        # temporal columns go in as the text the reference's own SQLite side holds ('2014-12-13 22:23:15[.fff]', '1999-09-09')
+        data = list(zip(*[(t.column(c).cast(pa.string()) if pa.types.is_temporal(t.column(c).type) else t.column(c)).to_pylist()
+                          for c in cols]))
         con.executemany(f"INSERT INTO {name} VALUES ({', '.join('?' * len(cols))})", data)
     rows = [tuple(r) for r in con.execute(text).fetchall()]
     keyf = lambda r: tuple((0, 0) if x is None else (1, x) for x in r[:n_keys])  # noqa: E731
