@@ -71,7 +71,7 @@ __device__ __forceinline__ V eval_node(const DPlan& p, const DExpr& e, const V* 
       const V a = vals[e.a], b = vals[e.b];
       if (v_is_null(ta, a) || v_is_null(tb, b)) { r = v_null(e); break; }
       if (e.kind == HDK_B200_FP) {
-        if (e.op == HDK_B200_OP_DIV && b.f == 0.0) { err = HDK_B200_ERR_DIV_BY_ZERO; break; }
+        if (e.op == HDK_B200_OP_DIV && b.f == 0.0) { if (e.aux & 2) r = v_null(e); else err = HDK_B200_ERR_DIV_BY_ZERO; break; }
         if (e.width == 4) {
           const float x = float(a.f), y = float(b.f);
           r.f = double(e.op == HDK_B200_OP_ADD ? x + y : e.op == HDK_B200_OP_SUB ? x - y : e.op == HDK_B200_OP_MUL ? x * y : x / y);
@@ -82,7 +82,7 @@ __device__ __forceinline__ V eval_node(const DPlan& p, const DExpr& e, const V* 
         int64_t lo;
         bool ovf = false;
         if (e.op == HDK_B200_OP_DIV) {
-          if (b.i == 0) { err = HDK_B200_ERR_DIV_BY_ZERO; break; }
+          if (b.i == 0) { if (e.aux & 2) r = v_null(e); else err = HDK_B200_ERR_DIV_BY_ZERO; break; }
           lo = (a.i == INT64_MIN && b.i == -1) ? INT64_MIN : a.i / b.i;
           ovf = (a.i == INT64_MIN && b.i == -1);
         } else if (e.op == HDK_B200_OP_ADD) {

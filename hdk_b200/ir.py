@@ -90,6 +90,7 @@ class BinOp(Expr):
     rhs: Expr
     type: SqlType
     overflow_check: bool = True
+    null_on_zero: bool = False      # division under Config.null_div_by_zero: NULL instead of ERR_DIV_BY_ZERO (safe_div_*)
 
     def children(self):
         return (self.lhs, self.rhs)
@@ -241,6 +242,32 @@ def join_key_for(outer: Expr, inner_type: SqlType) -> Expr:
     return outer
 
 
+def with_null_div_by_zero(e: Expr) -> Expr:
+    """The expression under Config::exec.codegen.null_div_by_zero (QE/ArithmeticIR.cpp:587-597): every division yields NULL
+    for a zero divisor (safe_div_*), so it and everything computed from it become nullable."""
+    import dataclasses
+
+    def rebuild(x):
+        if isinstance(x, tuple):
+            return tuple(rebuild(y) for y in x)
+        if not isinstance(x, Expr) or not dataclasses.is_dataclass(x):
+            return x
+        kw = {f.name: rebuild(getattr(x, f.name)) for f in dataclasses.fields(x) if f.name != "type"}
+        kids = [v for v in kw.values() if isinstance(v, Expr)] + \
+               [z for v in kw.values() if isinstance(v, tuple) for y in v for z in (y if isinstance(y, tuple) else (y,)) if isinstance(z, Expr)]
+        t = x.type
+        if isinstance(x, BinOp) and x.op == "/":
+            kw["null_on_zero"] = True
+            t = t.with_nullable(True)
+        elif isinstance(x, AggExpr):
+            if x.agg != "count" and kids:
+                t = t.with_nullable(t.nullable or kids[0].type.nullable)
+        elif not isinstance(x, (ColumnRef, Const, IsNull)):
+            t = t.with_nullable(t.nullable or any(k.type.nullable for k in kids))
+        return type(x)(**kw, type=t)
+    return rebuild(e)
+
+
 def make_binop(op: str, lhs: Expr, rhs: Expr) -> Expr:
     t = common_numeric_type(lhs.type, rhs.type)
     lhs, rhs = cast_to(lhs, t), cast_to(rhs, t)
@@ -346,6 +373,11 @@ def expr_range(e: Expr, col_stats) -> Range:
         if e.op == "*":
             c = [a.lo * b.lo, a.lo * b.hi, a.hi * b.lo, a.hi * b.hi]
             return Range(kind, min(c), max(c), hn)
+        if e.op == "/" and kind == "int" and a.kind == "int" and b.kind == "int" and b.lo * b.hi > 0:
+            # ExpressionRange::div (QE/ExpressionRange.cpp:199-218): only when the divisor's interval excludes 0
+            tdiv = lambda x, y: abs(x) // abs(y) * (1 if (x >= 0) == (y >= 0) else -1)   # noqa: E731  (C truncation)
+            c = [tdiv(a.lo, b.lo), tdiv(a.lo, b.hi), tdiv(a.hi, b.lo), tdiv(a.hi, b.hi)]
+            return Range(kind, min(c), max(c), hn or e.null_on_zero)
         return Range("invalid")
     if isinstance(e, Case):
         # the union of the arms' ranges; a NULL arm only adds has_nulls (getExpressionRange(CaseExpr), ExpressionRange.cpp)

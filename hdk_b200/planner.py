@@ -33,6 +33,8 @@ class Config:
     join_payload_by_slot: bool = True
     # perfect join tables up to this many entries (PerfectJoinHashTable.cpp:139-151); beyond: baseline join table
     max_perfect_join_entries: int = (1 << 31) // 4
+    # Config::exec.codegen.null_div_by_zero: a zero divisor yields NULL instead of ERR_DIV_BY_ZERO
+    null_div_by_zero: bool = False
 
 
 class UnsupportedPlan(Exception):
@@ -283,6 +285,12 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
                 output_columnar: Optional[bool] = None) -> PlannedQuery:
     # Non-grouped aggregates (SELECT COUNT(*), SUM(x) ... without GROUP BY; the reference's
     # QueryDescriptionType::NonGroupedAggregate) run as the degenerate group-by: zero keys, one keyless entry.
+    if cfg.null_div_by_zero:
+        f = ir.with_null_div_by_zero
+        unit = ir.ExecutionUnit(unit.table, [f(g) for g in unit.groupby_exprs], [f(t) for t in unit.target_exprs], unit.target_names,
+                                [f(q) for q in unit.quals],
+                                [ir.JoinSpec(j.inner_table, f(j.outer_key), j.inner_key_column, [(f(o), c) for o, c in j.more_keys])
+                                 for j in unit.joins], unit.order_by, unit.limit, unit.n_hidden)
     non_grouped = not unit.groupby_exprs
     if non_grouped and any(not isinstance(t, ir.AggExpr) for t in unit.target_exprs):
         raise UnsupportedPlan("a query without GROUP BY may only select aggregates")
@@ -404,7 +412,7 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
     def can_raise(e: ir.Expr) -> bool:
         """Does evaluating e possibly raise a row error (division by zero, checked integer overflow)?"""
         if e not in raises_memo:
-            own = (isinstance(e, ir.BinOp) and (e.op == "/" or (e.overflow_check and not e.type.is_fp))) or \
+            own = (isinstance(e, ir.BinOp) and ((e.op == "/" and not e.null_on_zero) or (e.overflow_check and not e.type.is_fp))) or \
                   (isinstance(e, ir.Cast) and not e.type.is_fp and not e.arg.type.is_fp and e.arg.type.width > e.type.width) or \
                   (isinstance(e, ir.UMinus) and not e.type.is_fp and not e.arg.type.nullable)
             raises_memo[e] = own or any(can_raise(c) for c in e.children())
@@ -416,7 +424,8 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
     def unsafe_division(e: ir.Expr) -> bool:
         """contains_unsafe_division (QE/LogicalIR.cpp:26-53): a division whose divisor is not a non-zero literal"""
         if e not in unsafe_memo:
-            own = isinstance(e, ir.BinOp) and e.op == "/" and not (isinstance(e.rhs, ir.Const) and e.rhs.value not in (None, 0, 0.0))
+            own = isinstance(e, ir.BinOp) and e.op == "/" and not e.null_on_zero and \
+                not (isinstance(e.rhs, ir.Const) and e.rhs.value not in (None, 0, 0.0))
             unsafe_memo[e] = own or any(unsafe_division(c) for c in e.children())
         return unsafe_memo[e]
 
@@ -455,7 +464,7 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
         elif isinstance(e, ir.BinOp):
             a, b = lower(e.lhs, guard), lower(e.rhs, guard)
             op = {"+": abi.OP_ADD, "-": abi.OP_SUB, "*": abi.OP_MUL, "/": abi.OP_DIV}[e.op]
-            n = emit(op, a, b, 1 if (e.overflow_check and not e.type.is_fp) else 0, e.type, guard=g)
+            n = emit(op, a, b, (1 if (e.overflow_check and not e.type.is_fp) else 0) | (2 if e.null_on_zero else 0), e.type, guard=g)
         elif isinstance(e, ir.UMinus):
             n = emit(abi.OP_UMINUS, lower(e.arg, guard), t=e.type, guard=g)
         elif isinstance(e, ir.Cast):

@@ -95,7 +95,8 @@ enum hdk_b200_op {
   HDK_B200_OP_ADD = 2,
   HDK_B200_OP_SUB = 3,
   HDK_B200_OP_MUL = 4,
-  HDK_B200_OP_DIV = 5,     /* int: ERR_DIV_BY_ZERO on zero divisor; fp: IEEE */
+  HDK_B200_OP_DIV = 5,     /* ERR_DIV_BY_ZERO on a zero divisor; with aux bit 1 (value 2) NULL instead:       */
+                           /* safe_div_* under Config null_div_by_zero (QE/ArithmeticIR.cpp:587-597)        */
   HDK_B200_OP_CAST = 6,    /* a → type.  fp→int rounds half away from zero (QE/CastIR.cpp:529-541,        */
                            /* RuntimeFunctions.cpp:309-345); int→fp exact convert; int→int re-sentinels;    */
                            /* narrowing int→int raises ERR_OVERFLOW_OR_UNDERFLOW outside (min, max] of the  */

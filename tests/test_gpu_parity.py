@@ -548,6 +548,21 @@ def test_reference_harvested_queries_on_gpu(oracle_mod, torch):
                 raise AssertionError(f"{name}: {text}: {e}")
 
 
+def test_null_div_by_zero_on_gpu(oracle_mod, torch):
+    """Config null_div_by_zero (Select.ReturnNullFromDivByZero): NULL instead of ERR_DIV_BY_ZERO, rows vs SQLite."""
+    import hdk_b200.hdk as hdk_mod
+    from tests.test_sqlite_oracle import NULL_DIV_BY_ZERO_QUERIES, reference_test_table, sqlite_text
+    tables = reference_test_table()
+    h = hdk_mod.init(null_div_by_zero=True)
+    h.import_arrow(tables["test"], "test", fragment_size=2)
+    for text in NULL_DIV_BY_ZERO_QUERIES:
+        got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+        exp = util.sqlite_rows(tables, sqlite_text(text), 0)
+        if "ORDER BY" not in text:
+            got, exp = sorted(got, key=repr), sorted(exp, key=repr)
+        util.assert_rows_equal(got, exp, rel=1e-9)
+
+
 def test_group_by_boundaries_and_null_on_gpu(oracle_mod, torch):
     """GroupByBoundariesAndNull (ArrowBasedExecuteTest.cpp:2845-2866) on the device: keys at INT32_MAX / 127 / 32767 / 2^62
     with NULL keys, single and composite, buffers byte-identical to the oracle's."""

@@ -673,8 +673,8 @@ def test_unsafe_divisions_short_circuit_like_the_reference(oracle_mod):
 
 # Every other query of the reference's Select.* tests (ArrowBasedExecuteTest.cpp) that the SQL subset accepts over the
 # fixtures — harvested verbatim, grouped by the test they come from.  (Select.ReturnNullFromDivByZero runs under
-# Config::exec.codegen.null_div_by_zero, which is not implemented: division by zero always raises.  Comparisons and joins
-# between two dictionary-encoded columns are refused: they need the reference's dictionary translation.)
+# Config::exec.codegen.null_div_by_zero: see NULL_DIV_BY_ZERO_QUERIES.  Comparisons and joins between two
+# dictionary-encoded columns are refused: they need the reference's dictionary translation.)
 REFERENCE_HARVESTED_QUERIES = {
     'FilterAndSimpleAggregation': [
         'SELECT COUNT(smallint_nulls), COUNT(*), COUNT(fn) FROM test',
@@ -941,3 +941,33 @@ def test_reference_harvested_queries_vs_sqlite(oracle_mod, name):
         if "ORDER BY" not in text.upper():
             got, exp = sorted(got, key=repr), sorted(exp, key=repr)
         util.assert_rows_equal(got, exp, rel=1e-6)
+
+
+# Select.ReturnNullFromDivByZero (ArrowBasedExecuteTest.cpp: the three reference queries first) under
+# Config::exec.codegen.null_div_by_zero: a zero divisor yields NULL (safe_div_*, QE/ArithmeticIR.cpp:587-597), which then
+# behaves like any NULL — as a group key, inside aggregates, in a qual
+NULL_DIV_BY_ZERO_QUERIES = [
+    "SELECT COUNT(*) FROM test GROUP BY y / (x - x)",
+    "SELECT COUNT(*) n FROM test GROUP BY z, y / (x - x) ORDER BY n ASC",
+    "SELECT COUNT(*) FROM test WHERE y / (x - x) = 0",
+    "SELECT x, SUM(y / (x - 7)), COUNT(y / (x - 7)), AVG(d / (x - 7)) FROM test GROUP BY x",
+    "SELECT y / (x - 7) AS k, COUNT(*) FROM test GROUP BY k ORDER BY k NULLS FIRST",
+    "SELECT COUNT(*), SUM(CASE WHEN y / (x - 7) > 40 THEN 1 ELSE 0 END) FROM test",
+]
+
+
+@pytest.mark.parametrize("text", NULL_DIV_BY_ZERO_QUERIES)
+def test_null_div_by_zero_vs_sqlite(oracle_mod, text):
+    from hdk_b200 import planner
+    tables = reference_test_table()
+    st = util.make_storage(tables, fragment_size=2)
+    pq = util.plan_sql(st, text, cfg=planner.Config(null_div_by_zero=True))
+    for kind in ("port", "reference"):
+        buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
+        assert err == 0
+        got, exp = decode_with_dictionaries(st, pq, buf), util.sqlite_rows(tables, sqlite_text(text), 0)
+        if "ORDER BY" not in text:
+            got, exp = sorted(got, key=repr), sorted(exp, key=repr)
+        util.assert_rows_equal(got, exp, rel=1e-9)
+    # without the option the same division raises
+    assert util.run_oracle(oracle_mod, st, util.plan_sql(st, text))[1] == 1
