@@ -27,6 +27,7 @@ __device__ __forceinline__ void wr_slot(int8_t* p, int w, int64_t v) {
 }
 
 __device__ __forceinline__ bool entry_is_empty(const DLayout& L, const int8_t* buf, uint64_t E, uint64_t e) {
+  if (L.key_count == 0) return false;   // NonGroupedAggregate: the one entry always counts (ResultSetStorage.cpp:440-443)
   if (L.keyless) {
     const DSlot& s = L.slots[L.target_idx_for_key];
     const int8_t* p = L.columnar ? buf + s.col_off + e * s.padded : buf + e * L.row_bytes + s.off;

@@ -204,8 +204,12 @@ def get_keyless_info(infos: List[TargetInfo], col_stats) -> tuple:
             elif ti.agg == abi.AGG_MIN:
                 init = get_agg_initial_val(ti.agg, ti.compact_type, 4 if ti.float_argument_input else 8)
                 if r.kind == "fp":
+                    # Deviation, on purpose: the reference (MemoryLayoutBuilder.cpp:339-348) takes a nullable MIN whose values
+                    # all lie below the NULL sentinel (DBL_MIN / FLT_MIN, tiny positive numbers — i.e. all-negative data) as
+                    # the emptiness marker without looking at has_nulls, and then loses every group whose values are all
+                    # NULL: the slot still holds its initial value.  It guards MAX against exactly this (:368-373).
                     init_f = struct.unpack("<d", struct.pack("<q", init))[0]
-                    found = r.hi < init_f
+                    found = r.hi < init_f and not r.has_nulls
                 elif r.kind == "int":
                     found = r.hi < init
             elif ti.agg == abi.AGG_MAX:

@@ -1,0 +1,133 @@
+"""Differential fuzzing of the row evaluator, the reference's way (same SQL on SQLite, SQLiteComparator.cpp:66-170): random
+aggregate queries — arithmetic over every integer width and fp32 / fp64, three-valued logic, IN / BETWEEN / IS NULL / CASE
+(with and without ELSE), dictionary literals, expression group keys — over the reference's `test` fixture.  CPU: the oracle
+(reference runtime) vs SQLite; GPU: the CUDA path through the façade vs SQLite.  Queries whose arithmetic overflows are
+skipped (SQLite promotes to REAL, the reference raises ERR_OVERFLOW_OR_UNDERFLOW)."""
+import random
+
+import pytest
+
+from tests import util
+
+INT = ["x", "w", "y", "z", "t", "fx", "u", "smallint_nulls", "ofd"]
+FP = ["f", "d", "dn", "ff", "fn"]
+
+
+class Gen:
+    def __init__(self, seed):
+        self.r = random.Random(seed)
+
+    def iexpr(self, d=0):
+        r, p = self.r, self.r.random()
+        if d > 2 or p < 0.35:
+            return r.choice(INT)
+        if p < 0.5:
+            return f"({r.randint(-50, 50)})"
+        if p < 0.8:
+            return f"({self.iexpr(d + 1)} {r.choice('+-*')} {self.iexpr(d + 1)})"
+        if p < 0.9:
+            return f"(-({self.iexpr(d + 1)}))"
+        if r.random() < 0.7:
+            return f"CASE WHEN {self.bexpr(d + 1)} THEN {self.iexpr(d + 1)} ELSE {self.iexpr(d + 1)} END"
+        return f"CASE WHEN {self.bexpr(d + 1)} THEN {self.iexpr(d + 1)} END"
+
+    def fexpr(self, d=0):
+        r, p = self.r, self.r.random()
+        if d > 2 or p < 0.4:
+            return r.choice(FP)
+        if p < 0.5:
+            return f"({r.uniform(-5, 5):.2f})"
+        if p < 0.85:
+            return f"({self.fexpr(d + 1)} {r.choice('+-*')} {r.choice([self.fexpr, self.iexpr])(d + 1)})"
+        return f"CASE WHEN {self.bexpr(d + 1)} THEN {self.fexpr(d + 1)} ELSE {self.fexpr(d + 1)} END"
+
+    def bexpr(self, d=0):
+        r, p = self.r, self.r.random()
+        if d > 2 or p < 0.45:
+            e = r.choice([self.iexpr, self.fexpr])
+            return f"{e(d + 1)} {r.choice(['<', '<=', '>', '>=', '=', '<>'])} {e(d + 1)}"
+        if p < 0.55:
+            return f"{r.choice(INT + FP)} IS {'NOT ' if r.random() < 0.5 else ''}NULL"
+        if p < 0.65:
+            vals = ", ".join(str(r.randint(-10, 110)) for _ in range(r.randint(1, 4)))
+            return f"{r.choice(INT)} {'NOT ' if r.random() < 0.3 else ''}IN ({vals})"
+        if p < 0.72:
+            return f"{r.choice(INT)} BETWEEN {r.randint(-100, 50)} AND {r.randint(0, 1100)}"
+        if p < 0.8:
+            return f"str {r.choice(['=', '<>'])} '{r.choice(['foo', 'bar', 'baz', 'nope'])}'"
+        if p < 0.9:
+            return f"NOT ({self.bexpr(d + 1)})"
+        return f"({self.bexpr(d + 1)} {r.choice(['AND', 'OR'])} {self.bexpr(d + 1)})"
+
+    def query(self):
+        r = self.r
+        aggs = []
+        for _ in range(r.randint(1, 3)):
+            a = r.choice(["COUNT", "SUM", "MIN", "MAX", "AVG"])
+            e = r.choice([self.iexpr, self.fexpr])() if a != "COUNT" or r.random() < 0.5 else "*"
+            aggs.append(f"{a}({e})")
+        keys = r.sample(["x", "z", "y", "w", "str", "fx", "smallint_nulls", f"CASE WHEN {self.bexpr(1)} THEN 1 ELSE 0 END", "(x + w)"],
+                        r.randint(0, 2))
+        q = f"SELECT {', '.join(keys + aggs)} FROM test"
+        if r.random() < 0.7:
+            q += f" WHERE {self.bexpr()}"
+        if keys:
+            q += " GROUP BY " + ", ".join(str(i + 1) for i in range(len(keys)))
+        return q
+
+
+def queries(seed, n):
+    g = Gen(seed)
+    return [g.query() for _ in range(n)]
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_fuzz_oracle_vs_sqlite(oracle_mod, seed):
+    from hdk_b200 import planner
+    from tests.test_sqlite_oracle import decode_with_dictionaries, reference_test_table
+    tables = reference_test_table()
+    st = util.make_storage(tables, fragment_size=3)
+    compared = 0
+    for text in queries(seed, 150):
+        try:
+            pq = util.plan_sql(st, text)
+        except planner.UnsupportedPlan:
+            continue
+        buf, err = util.run_oracle(oracle_mod, st, pq, kind="reference")
+        if err != 0:
+            continue
+        got = sorted(decode_with_dictionaries(st, pq, buf), key=repr)
+        exp = sorted(util.sqlite_rows(tables, text, 0), key=repr)
+        try:
+            util.assert_rows_equal(got, exp, rel=1e-5)
+        except AssertionError as e:
+            raise AssertionError(f"{text}: {e}")
+        compared += 1
+    assert compared > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_fuzz_gpu_vs_sqlite(seed):
+    import hdk_b200.hdk as hdk_mod
+    from hdk_b200 import planner
+    from hdk_b200.executor import QueryError
+    from tests.test_sqlite_oracle import reference_test_table
+    tables = reference_test_table()
+    h = hdk_mod.init()
+    h.import_arrow(tables["test"], "test", fragment_size=3)
+    compared = 0
+    for text in queries(seed, 150):
+        try:
+            got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+        except planner.UnsupportedPlan:
+            continue
+        except QueryError:
+            continue
+        exp = util.sqlite_rows(tables, text, 0)
+        try:
+            util.assert_rows_equal(sorted(got, key=repr), sorted(exp, key=repr), rel=1e-5)
+        except AssertionError as e:
+            raise AssertionError(f"{text}: {e}")
+        compared += 1
+    assert compared > 100
