@@ -131,3 +131,122 @@ def test_fuzz_gpu_vs_sqlite(seed):
             raise AssertionError(f"{text}: {e}")
         compared += 1
     assert compared > 100
+
+
+# ---- joins: one-to-one and one-to-many perfect tables, composite keys (baseline tables, both layouts), two-join chains whose
+# second key comes from the fact or from the first inner table; NULL-able keys on both sides
+def join_tables(seed):
+    import numpy as np
+    import pyarrow as pa
+    rng = np.random.default_rng(seed)
+    n, m = 400, 60
+    fact = pa.table({"a": rng.integers(0, 30, n).astype(np.int32),
+                     "b": pa.array(rng.integers(0, 4, n).astype(np.int16), mask=rng.random(n) < 0.1),
+                     "c": pa.array(rng.integers(-5, 5, n).astype(np.int64), mask=rng.random(n) < 0.05),
+                     "v": rng.integers(-100, 100, n).astype(np.int64), "f": np.round(rng.normal(0, 10, n), 2)})
+    d1 = pa.table({"a": pa.array(rng.permutation(80)[:m].astype(np.int32)), "b": rng.integers(0, 4, m).astype(np.int16),
+                   "w": rng.integers(0, 9, m).astype(np.int32),
+                   "g": pa.array(rng.integers(0, 3, m).astype(np.int8), mask=rng.random(m) < 0.1)})
+    d2 = pa.table({"a": rng.integers(0, 35, m).astype(np.int32),
+                   "b": pa.array(rng.integers(0, 5, m).astype(np.int16), mask=rng.random(m) < 0.1),
+                   "h": rng.integers(0, 4, m).astype(np.int32), "x": np.round(rng.normal(5, 2, m), 1)})
+    d3 = pa.table({"c": pa.array(np.arange(-6, 6).astype(np.int64)), "p": rng.integers(0, 3, 12).astype(np.int32)})
+    return {"fact": fact, "d1": d1, "d2": d2, "d3": d3}
+
+
+def join_queries(seed, n):
+    r = random.Random(seed)
+
+    def one():
+        joins, cols, fcols = [], ["f0.a", "f0.b", "f0.c", "f0.v"], ["f0.f"]
+        p = r.random()
+        if p < 0.35:
+            joins.append("JOIN d1 j1 ON f0.a = j1.a" if r.random() < 0.6 else "JOIN d1 j1 ON f0.a = j1.a AND f0.b = j1.b")
+            cols += ["j1.w", "j1.g"]
+        elif p < 0.7:
+            joins.append("JOIN d2 j1 ON f0.a = j1.a" if r.random() < 0.5 else "JOIN d2 j1 ON f0.b = j1.b AND f0.a = j1.a")
+            cols += ["j1.h"]
+            fcols += ["j1.x"]
+        else:
+            joins.append("JOIN d1 j1 ON f0.a = j1.a")
+            joins.append("JOIN d3 j2 ON f0.c = j2.c" if r.random() < 0.5 else "JOIN d3 j2 ON j1.w - 4 = j2.c")
+            cols += ["j1.w", "j1.g", "j2.p"]
+
+        def ie(d=0):
+            q = r.random()
+            if d > 1 or q < 0.5:
+                return r.choice(cols)
+            if q < 0.6:
+                return f"({r.randint(-9, 9)})"
+            return f"({ie(d + 1)} {r.choice('+-*')} {ie(d + 1)})"
+
+        def be(d=0):
+            q = r.random()
+            if d > 1 or q < 0.6:
+                return f"{ie(1)} {r.choice(['<', '<=', '>', '=', '<>'])} {ie(1)}"
+            if q < 0.7:
+                return f"{r.choice(cols)} IS NOT NULL"
+            if q < 0.8:
+                return f"{r.choice(fcols)} > {r.uniform(-5, 8):.1f}"
+            return f"({be(d + 1)} {r.choice(['AND', 'OR'])} {be(d + 1)})"
+
+        aggs = []
+        for _ in range(r.randint(1, 3)):
+            a = r.choice(["COUNT", "SUM", "MIN", "MAX", "AVG"])
+            e = "*" if a == "COUNT" and r.random() < 0.5 else (r.choice(fcols) if r.random() < 0.3 else ie())
+            aggs.append(f"{a}({e})")
+        keys = r.sample(cols, r.randint(0, 2))
+        s = f"SELECT {', '.join(keys + aggs)} FROM fact f0 {' '.join(joins)}"
+        if r.random() < 0.6:
+            s += f" WHERE {be()}"
+        if keys:
+            s += " GROUP BY " + ", ".join(str(i + 1) for i in range(len(keys)))
+        return s
+    return [one() for _ in range(n)]
+
+
+def test_fuzz_joins_oracle_vs_sqlite(oracle_mod):
+    from hdk_b200 import planner
+    from tests.test_sqlite_oracle import decode_with_dictionaries
+    tables = join_tables(21)
+    st = util.make_storage(tables, fragment_size=90)
+    compared = 0
+    for text in join_queries(21, 150):
+        try:
+            pq = util.plan_sql(st, text)
+        except planner.UnsupportedPlan:
+            continue
+        buf, err = util.run_oracle(oracle_mod, st, pq, kind="reference")
+        if err != 0:
+            continue
+        try:
+            util.assert_rows_equal(sorted(decode_with_dictionaries(st, pq, buf), key=repr), sorted(util.sqlite_rows(tables, text, 0), key=repr),
+                                   rel=1e-6)
+        except AssertionError as e:
+            raise AssertionError(f"{text}: {e}")
+        compared += 1
+    assert compared > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_fuzz_joins_gpu_vs_sqlite(seed):
+    import hdk_b200.hdk as hdk_mod
+    from hdk_b200 import planner
+    from hdk_b200.executor import QueryError
+    tables = join_tables(seed)
+    h = hdk_mod.init()
+    for name, t in tables.items():
+        h.import_arrow(t, name, fragment_size=90)
+    compared = 0
+    for text in join_queries(seed, 150):
+        try:
+            got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+        except (planner.UnsupportedPlan, QueryError):
+            continue
+        try:
+            util.assert_rows_equal(sorted(got, key=repr), sorted(util.sqlite_rows(tables, text, 0), key=repr), rel=1e-6)
+        except AssertionError as e:
+            raise AssertionError(f"{text}: {e}")
+        compared += 1
+    assert compared > 100
