@@ -192,3 +192,46 @@ def test_limit_prefilter_keeps_every_row_of_the_answer(oracle_mod, order, top_n)
     full, part = full.cpu().numpy().astype(np.int64), part.cpu().numpy().astype(np.int64)
     assert len(np.unique(part)) == len(part)
     assert key_rows(cols, meta, order, part[:top_n]) == key_rows(cols, meta, order, full[:top_n])
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_fuzz_order_by_limit_vs_sqlite(seed):
+    """Random ORDER BY lists (1-3 targets: group keys incl. dictionary strings and NULL-able keys, COUNT / SUM / MIN / AVG
+    results; ASC / DESC; NULLS FIRST / LAST) with and without LIMIT over the reference's `test` and `logical_size_test` fixtures:
+    the sequence of ORDER BY tuples must equal SQLite's (rows that tie on every ORDER BY target may come in any order)."""
+    import random
+    import hdk_b200.hdk as hdk_mod
+    from tests import util
+    from tests.test_sqlite_oracle import harvested_tables
+    tables = harvested_tables()
+    h = hdk_mod.init()
+    for name in ("test", "logical_size_test"):
+        h.import_arrow(tables[name], name, fragment_size=4)
+    r = random.Random(seed)
+    shapes = [("test", ["x", "z", "str", "fx", "smallint_nulls", "w", "ss"], ["COUNT(*)", "SUM(y)", "MIN(fn)", "AVG(dn)", "MAX(t)", "SUM(u)"]),
+              ("logical_size_test", ["id", "id_null", "small_int_null", "tiny_int", "big_int_null"],
+               ["COUNT(*)", "SUM(float_null)", "AVG(big_int_null)", "MIN(tiny_int_null)", "MAX(double_null)"])]
+    compared = 0
+    for _ in range(60):
+        table, keys, aggs = r.choice(shapes)
+        ks = r.sample(keys, r.randint(1, 2))
+        ags = r.sample(aggs, r.randint(1, 3))
+        names = [f"k{i}" for i in range(len(ks))] + [f"a{i}" for i in range(len(ags))]
+        sel = ", ".join(f"{e} AS {n}" for e, n in zip(ks + ags, names))
+        order = r.sample(range(len(names)), r.randint(1, min(3, len(names))))
+        clause = ", ".join(f"{names[i]} {r.choice(['ASC', 'DESC'])} NULLS {r.choice(['FIRST', 'LAST'])}" for i in order)
+        text = f"SELECT {sel} FROM {table} GROUP BY {', '.join(names[:len(ks)])} ORDER BY {clause}"
+        if r.random() < 0.5:
+            text += f" LIMIT {r.randint(1, 6)}"
+        res = h.sql(text)
+        assert res.result_set.sorted_on_device
+        got = [tuple(row.values()) for row in res.to_arrow().to_pylist()]
+        exp = util.sqlite_rows(tables, text, 0)
+        try:
+            util.assert_rows_equal([tuple(g[i] for i in order) for g in got], [tuple(e[i] for i in order) for e in exp], rel=1e-6)
+            if "LIMIT" not in text:
+                util.assert_rows_equal(sorted(got, key=repr), sorted(exp, key=repr), rel=1e-6)
+        except AssertionError as e:
+            raise AssertionError(f"{text}: {e}")
+        compared += 1
+    assert compared == 60
