@@ -371,7 +371,9 @@ class _Parser:
                 self.aliases[n.lower()] = e
         quals = []
         if self.accept("kw", "where"):
+            visible, self.aliases = self.aliases, {}       # select-list aliases are not visible in WHERE
             quals = _split_conjuncts(self.expr())
+            self.aliases = visible
         groupby = []
         if self.accept("kw", "group"):
             self.eat("kw", "by")

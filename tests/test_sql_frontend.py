@@ -98,3 +98,9 @@ def test_case_lowering_guards_only_what_can_raise(st):
 def test_unsupported_sql_is_rejected(st, text):
     with pytest.raises((planner.UnsupportedPlan, SyntaxError, KeyError, ValueError)):
         util.plan_sql(st, text)
+
+
+def test_select_aliases_are_not_visible_in_where(st):
+    # `x` in WHERE is the table's column, not the select-list alias of `a`; in GROUP BY / ORDER BY the alias wins
+    u = sql.parse("SELECT a AS x, COUNT(*) AS n FROM t WHERE x > 3 GROUP BY x ORDER BY x", st.tables)
+    assert u.quals[0].lhs.column == "x" and u.groupby_exprs[0].column == "a" and u.order_by[0][0] == 0
