@@ -107,14 +107,18 @@ def test_fuzz_oracle_vs_sqlite(oracle_mod, seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed", [11, 12, 13])
-def test_fuzz_gpu_vs_sqlite(seed):
+@pytest.mark.parametrize("seed,config", [(11, {}), (12, {}), (13, {}), (14, {"enable_columnar_output": True}),
+                                         (15, {"baseline_threshold": 1}), (16, {"baseline_threshold": 1, "enable_columnar_output": True}),
+                                         (17, {"bigint_count": True})])
+def test_fuzz_gpu_vs_sqlite(seed, config):
+    """(config: the planner options that pick the buffer layout — columnar output, baseline hash for every multi-key
+    group-by, 64-bit COUNT — so that the generic kernel, finalize and the result decoding are fuzzed on each of them)"""
     import hdk_b200.hdk as hdk_mod
     from hdk_b200 import planner
     from hdk_b200.executor import QueryError
     from tests.test_sqlite_oracle import reference_test_table
     tables = reference_test_table()
-    h = hdk_mod.init()
+    h = hdk_mod.init(**config)
     h.import_arrow(tables["test"], "test", fragment_size=3)
     compared = 0
     for text in queries(seed, 150):
