@@ -852,6 +852,35 @@ def test_reduce_on_device_matches_oracle(oracle_mod, L, env, torch, idx):
     check_against_oracle(oracle_mod, st, pq, bufs[0].cpu().numpy(), nk)
 
 
+def test_reduce_of_non_grouped_partials_never_skips_an_entry(oracle_mod, L, torch):
+    """An aggregate without GROUP BY has one entry that always counts (ResultSetStorage::isEmptyEntry :440-443): a partial
+    whose MIN argument was all NULL still carries its SUM / COUNT into hdk_b200_reduce."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    from tests.test_sqlite_oracle import reference_test_table
+    tables = reference_test_table()
+    st = util.make_storage(tables, fragment_size=3)           # the first fragments hold dn = NULL only
+    ex = Executor(st)
+    text = "SELECT MIN(dn), SUM(smallint_nulls), COUNT(smallint_nulls), AVG(smallint_nulls) FROM test"
+    pq = ex.plan(sql.parse(text, st.tables))
+    frags = st.get_table("test").fragments
+    bufs = []
+    for part in (frags[:2], frags[2:]):
+        prep = ex.prepare(pq, fragments=part)
+        ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0
+        bufs.append(prep["out"].clone())
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for a, b in ((0, 1), (1, 0)):
+        this = bufs[a].clone()
+        assert L.hdk_b200_reduce(C.byref(pq.plan), C.byref(pq.qmd), this.data_ptr(), bufs[b].data_ptr(), 1, err.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        check_against_oracle(oracle_mod, st, pq, this.cpu().numpy(), 0)
+    got = util.result_columns(oracle_mod, pq, this.cpu().numpy())
+    assert [c[0] for c in got] == [-2002.4, 327675, 15, 21845.0]
+
+
 @pytest.mark.parametrize("idx", [0, 3, 7, 8, 11, 12, 13])
 def test_compact_result_matches_iteration(oracle_mod, L, env, torch, idx):
     from hdk_b200.executor import Executor
