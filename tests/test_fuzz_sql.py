@@ -254,3 +254,60 @@ def test_fuzz_joins_gpu_vs_sqlite(seed):
             raise AssertionError(f"{text}: {e}")
         compared += 1
     assert compared > 100
+
+
+# ---- larger tables: many ragged fragments, group counts from 3 to 60,000 (every accumulation strategy of the generic kernel:
+# per-thread bins, per-CTA shared table, global work table, baseline hash), NULLs in keys and arguments
+def large_table(seed, n=180_000):
+    import numpy as np
+    import pyarrow as pa
+    rng = np.random.default_rng(seed)
+    nul = lambda a, p: pa.array(a, mask=rng.random(n) < p)   # noqa: E731
+    return {"big": pa.table({
+        "k3": rng.integers(0, 3, n).astype(np.int8), "k40": nul(rng.integers(-20, 20, n).astype(np.int16), 0.02),
+        "k900": rng.integers(100, 1000, n).astype(np.int32), "k60k": nul(rng.integers(0, 60000, n).astype(np.int32), 0.01),
+        "wide": rng.integers(-(1 << 40), 1 << 40, n).astype(np.int64) // 1000 * 1000,
+        "i": nul(rng.integers(-1000, 1000, n).astype(np.int32), 0.05), "j": rng.integers(0, 100, n).astype(np.int64),
+        "f": nul(np.round(rng.normal(0, 100, n), 3), 0.03), "g": rng.random(n).astype(np.float32)})}
+
+
+def large_queries(seed, n):
+    r = random.Random(seed)
+    out = []
+    for _ in range(n):
+        keys = r.choice([["k3"], ["k40"], ["k900"], ["k60k"], ["k3", "k40"], ["k40", "k900"], ["wide"], ["k900", "k3", "k40"], []])
+        aggs = r.sample(["COUNT(*)", "COUNT(i)", "SUM(i)", "SUM(j)", "MIN(i)", "MAX(j)", "AVG(f)", "SUM(f)", "MIN(f)", "MAX(g)", "AVG(g)", "SUM(i * j)",
+                         "SUM(CASE WHEN j > 50 THEN i ELSE 0 END)", "MIN(f + g)"], r.randint(1, 5))
+        text = f"SELECT {', '.join(keys + aggs)} FROM big"
+        if r.random() < 0.6:
+            text += " WHERE " + r.choice(["i > 0", "j < 70 AND f IS NOT NULL", "k40 IN (1, 2, 3, 5, 8) OR g > 0.9", "f < 50.5 AND i <> 7", "k60k < 30000",
+                                          "NOT (j BETWEEN 10 AND 20)", "k3 = 1 AND g <= 0.25"])
+        if keys:
+            text += " GROUP BY " + ", ".join(keys)
+        out.append((text, len(keys)))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,config", [(41, {}), (42, {"enable_columnar_output": True}), (43, {"baseline_threshold": 1})])
+def test_fuzz_large_tables_gpu_vs_oracle(oracle_mod, seed, config):
+    import torch
+    from hdk_b200 import planner, sql
+    from hdk_b200.executor import Executor
+    from tests.test_gpu_parity import check_against_oracle
+    tables = large_table(seed)
+    st = util.make_storage(tables, fragment_size=23_456)
+    strategies = set()
+    for text, nk in large_queries(seed, 30):
+        ex = Executor(st, planner.Config(**config))
+        pq = ex.plan(sql.parse(text, st.tables), 262144)
+        prep = ex.prepare(pq)
+        info = ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0, text
+        strategies.add(int(info.strategy))
+        try:
+            check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+        except AssertionError as e:
+            raise AssertionError(f"{text} [strategy {info.strategy}]: {e}")
+    assert len(strategies) >= 3
