@@ -63,7 +63,7 @@ def test_device_sort_vs_reference_comparator(oracle_mod, order):
         np.testing.assert_array_equal(out[c].cpu().numpy(), np.ascontiguousarray(cols[c]).view(np.int64)[perm[:9]])
 
 
-@pytest.mark.parametrize("n", [0, 1, 31, 2047, 2048, 2049, 2048 * 592 + 1, 3_000_017])
+@pytest.mark.parametrize("n", [0, 1, 31, 2047, 2049, 3071, 3072, 3073, 3072 * 592 + 1, 3_000_017])
 def test_device_sort_edge_sizes(n):
     import torch
     rng = np.random.default_rng(n)
