@@ -512,11 +512,16 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
                     if n is None:
                         n = lower(x, guard)
                         continue
-                    g_x = guard
                     if unsafe_division(x):
-                        decided = n if e.op == "and" else emit(abi.OP_NOT, n, t=BOOL_N)   # runs when n is TRUE / FALSE
-                        g_x = both(guard, decided)
-                    n = emit(abi.OP_AND if e.op == "and" else abi.OP_OR, n, lower(x, g_x), t=e.type)
+                        decided = n if e.op == "and" else emit(abi.OP_NOT, n, t=BOOL_N)   # x runs when n is TRUE / FALSE
+                        nx = lower(x, both(guard, decided))
+                        # where x does not run the reference's phi yields n itself: FALSE / TRUE, or NULL when n is NULL
+                        # (nullcheck_fail_bb) — not NULL AND x.  NULL in x's place gives exactly that through AND / OR.
+                        null_bool = emit(abi.OP_CONST, t=BOOL_N, ival=abi.int_null(1))
+                        nx = emit(abi.OP_CASE, decided, nx, t=BOOL_N, ival=null_bool)
+                    else:
+                        nx = lower(x, guard)
+                    n = emit(abi.OP_AND if e.op == "and" else abi.OP_OR, n, nx, t=BOOL_N if unsafe_division(x) else e.type)
         elif isinstance(e, ir.IsNull):
             n = emit(abi.OP_IS_NULL, lower(e.arg, guard), t=e.type)
         else:

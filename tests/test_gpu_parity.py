@@ -525,6 +525,9 @@ def test_reference_simple_aggregation_and_short_circuit_on_gpu(oracle_mod, torch
         with pytest.raises(QueryError) as ei:
             h.sql(text).to_arrow()
         assert ei.value.code == 1, text
+    from tests.test_sqlite_oracle import SHORT_CIRCUIT_NULL_QUERIES
+    for text in SHORT_CIRCUIT_NULL_QUERIES:       # a NULL on the safe side decides: the whole AND / OR is NULL
+        assert [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()] == [(0,)], text
 
 
 def test_reference_harvested_queries_on_gpu(oracle_mod, torch):

@@ -651,6 +651,11 @@ SHORT_CIRCUIT_QUERIES = [
     "SELECT COUNT(*) FROM test WHERE NOT (x = 7 OR y / (x - 7) < 40) AND z > 0",
     "SELECT x, SUM(y / (x - 7)) FROM test WHERE x > 7 GROUP BY x",
 ]
+SHORT_CIRCUIT_NULL_QUERIES = [
+    "SELECT COUNT(*) FROM test WHERE NOT (u > 0 AND y / (x - 7) > 40)",
+    "SELECT COUNT(*) FROM test WHERE NOT (u > 0 AND y / (x - 7) < 40)",
+    "SELECT COUNT(*) FROM test WHERE NOT (u > 0 OR y / (x - 7) > 40)",
+]
 DIV_BY_ZERO_QUERIES = [
     "SELECT COUNT(*) FROM test WHERE y / (x - 7) < 44",
     "SELECT x, SUM(y / (x - 7)) FROM test GROUP BY x",
@@ -669,6 +674,14 @@ def test_unsafe_divisions_short_circuit_like_the_reference(oracle_mod):
             util.assert_rows_equal(decode_with_dictionaries(st, pq, buf), util.sqlite_rows(tables, text, 0))
     for text in DIV_BY_ZERO_QUERIES:
         assert util.run_oracle(oracle_mod, st, util.plan_sql(st, text))[1] == 1, text
+    # Where the unsafe side does not run, the short-circuit's phi yields the other side itself — NULL when that one is NULL
+    # (nullcheck_fail_bb, QE/LogicalIR.cpp:237-296), not `NULL AND x`: with u NULL everywhere all three are NULL → NOT NULL
+    # → no row passes (plain three-valued logic, and SQLite, would let the x = 8 rows of the second query through).
+    for text in SHORT_CIRCUIT_NULL_QUERIES:
+        pq = util.plan_sql(st, text)
+        for kind in ("port", "reference"):
+            buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
+            assert err == 0 and decode_with_dictionaries(st, pq, buf) == [(0,)], text
 
 
 # Every other query of the reference's Select.* tests (ArrowBasedExecuteTest.cpp) that the SQL subset accepts over the
