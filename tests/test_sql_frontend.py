@@ -104,3 +104,22 @@ def test_select_aliases_are_not_visible_in_where(st):
     # `x` in WHERE is the table's column, not the select-list alias of `a`; in GROUP BY / ORDER BY the alias wins
     u = sql.parse("SELECT a AS x, COUNT(*) AS n FROM t WHERE x > 3 GROUP BY x ORDER BY x", st.tables)
     assert u.quals[0].lhs.column == "x" and u.groupby_exprs[0].column == "a" and u.order_by[0][0] == 0
+
+
+def test_builder_api_join_agg_sort_units():
+    """The pyhdk-shaped builder (python/pyhdk/hdk.py:1606-1992 agg / join / sort): units are built without touching a GPU."""
+    import hdk_b200.hdk as hdk_mod
+    h = hdk_mod.init()
+    h.import_arrow(pa.table({"a": np.arange(10, dtype=np.int32), "b": np.arange(10, dtype=np.int64) % 3, "v": np.arange(10.0)}), "t")
+    h.import_arrow(pa.table({"a": np.arange(5, dtype=np.int32), "b": np.arange(5, dtype=np.int64) % 3, "w": np.arange(5, dtype=np.int32)}), "d")
+    t, d = h.scan("t"), h.scan("d")
+    n = t.join(d, "a").agg(["w"], s="sum(v)", c="count").sort(("s", "desc", "first"), "w")
+    assert n.unit.joins[0].inner_key_columns == ["a"] and n.unit.target_names == ["w", "s", "c"]
+    assert n.unit.order_by == [(1, True, True), (0, False, False)]            # NULLs last unless asked otherwise (hdk.py:1687-1689)
+    n2 = t.join(d, ["a", "b"]).agg("w", {"m": "min(v)"})
+    assert n2.unit.joins[0].inner_key_columns == ["a", "b"]
+    stats = lambda ti, c: [h.storage.get_table("t"), h.storage.get_table("d")][ti].col_stats(c)   # noqa: E731
+    pq = planner.build_query(n2.unit, stats, 10, h.config)
+    assert pq.plan.n_joins == 1 and pq.plan.joins[0].n_key_exprs == 2         # composite key → baseline join table
+    with pytest.raises(planner.UnsupportedPlan):
+        t.join(d, "a", how="left")
