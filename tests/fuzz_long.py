@@ -1,7 +1,7 @@
 """Long-running differential fuzz on the CPU: random aggregate and join queries (generators of tests/test_fuzz_sql.py) through the
 planner and the oracle against SQLite, for a range of seeds — the tests run a few seeds, this runs as many as asked:
 
-    python tools/fuzz_sql.py 200 208        # seeds 200..207, ~1900 comparisons in ~2 min
+    python tests/fuzz_long.py 200 208        # seeds 200..207, ~1900 comparisons in ~2 min
 
 Prints every mismatch with the query.  fp32 columns mixed with double arithmetic can differ from SQLite in the 5th digit
 (float * float is a float in the reference, a double in SQLite)."""
