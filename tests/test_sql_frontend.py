@@ -123,3 +123,32 @@ def test_builder_api_join_agg_sort_units():
     assert pq.plan.n_joins == 1 and pq.plan.joins[0].n_key_exprs == 2         # composite key → baseline join table
     with pytest.raises(planner.UnsupportedPlan):
         t.join(d, "a", how="left")
+
+
+def test_join_key_typing_rules(st):
+    """ir.join_key_for: what may be joined on stored values, and what is refused rather than compared wrongly."""
+    days = ir.SqlType("date", 8, True, date_in_days=True)
+    ts_s, ts_ms = ir.SqlType("timestamp", 8, True, unit=1), ir.SqlType("timestamp", 8, True, unit=1000)
+    i32, dic = ir.SqlType("int", 4, True), ir.SqlType("dict", 4, True)
+    col = lambda t, w=4: ir.ColumnRef(0, "c", t, w)   # noqa: E731
+    k = ir.join_key_for(col(days), days)
+    assert isinstance(k, ir.ColumnRef) and k.type.kind == "int" and not k.type.date_in_days       # probes with the stored days
+    assert ir.join_key_for(col(i32), i32) == col(i32)
+    assert ir.join_key_for(col(ts_s, 8), ts_s) == col(ts_s, 8)
+    for outer, inner in ((col(days), i32), (col(i32), days), (col(dic), dic), (col(ts_s, 8), ts_ms), (col(i32), ts_s)):
+        with pytest.raises(NotImplementedError):
+            ir.join_key_for(outer, inner)
+
+
+def test_null_div_by_zero_makes_dependents_nullable(st):
+    u = sql.parse("SELECT a, SUM(x / b), COUNT(*), MIN(CASE WHEN x / b > 1 THEN f ELSE 0.5 END) FROM t WHERE NOT (x / b = 2) GROUP BY a", st.tables)
+    e = ir.with_null_div_by_zero(u.target_exprs[1])
+    assert e.arg.null_on_zero and e.arg.type.nullable and e.type.nullable
+    assert not ir.with_null_div_by_zero(u.target_exprs[2]).type.nullable                           # COUNT(*) stays NOT NULL
+    q = ir.with_null_div_by_zero(u.quals[0])
+    assert q.type.nullable and q.args[0].type.nullable and q.args[0].lhs.null_on_zero
+    c = ir.with_null_div_by_zero(u.target_exprs[3])
+    assert c.arg.arms[0][0].type.nullable                                                          # the WHEN became nullable
+    pq = util.plan_sql(st, "SELECT a, SUM(x / b) FROM t GROUP BY a", cfg=planner.Config(null_div_by_zero=True))
+    div = [pq.plan.exprs[i] for i in range(pq.plan.n_exprs) if pq.plan.exprs[i].op == abi.OP_DIV]
+    assert div and all(d.aux & 2 and d.type.nullable and d.guard == 0 for d in div)
