@@ -342,7 +342,7 @@ def expr_range(e: Expr, col_stats) -> Range:
             return Range("int", int(lo) * 86400, int(hi) * 86400, hn)
         return Range("int", int(lo), int(hi), hn)
     if isinstance(e, Const):
-        if e.value is None:
+        if e.value is None or isinstance(e.value, str):
             return Range("invalid")
         return Range("fp" if e.type.is_fp else "int", e.value, e.value, False)
     if isinstance(e, Cast):

@@ -462,6 +462,8 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
                 t = e.type.with_nullable(True)
                 n = emit(abi.OP_CONST, t=t, ival=0 if t.is_fp else abi.int_null(t.width),
                          fval=abi.fp_null(t.width) if t.is_fp else 0.0)
+            elif isinstance(e.value, str):
+                raise UnsupportedPlan("string literal outside a comparison with a dictionary-encoded column")
             else:
                 n = emit(abi.OP_CONST, t=e.type.with_nullable(False),
                          ival=0 if e.type.is_fp else int(e.value), fval=float(e.value))
