@@ -259,7 +259,10 @@ class _Parser:
                 return ir.make_agg("count", None, self.bigint_count)
             arg = self.expr()
             self.eat("op", ")")
-            return ir.make_agg(t[1], arg, self.bigint_count)
+            try:
+                return ir.make_agg(t[1], arg, self.bigint_count)
+            except NotImplementedError as ex:
+                raise UnsupportedPlan(str(ex))
         if t == ("kw", "null"):
             self.i += 1
             return ir.Const(None, ir.SqlType("int", 4, True))       # only meaningful as a CASE value, which retypes it

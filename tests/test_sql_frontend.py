@@ -95,6 +95,7 @@ def test_case_lowering_guards_only_what_can_raise(st):
     "SELECT d.w, COUNT(*) FROM t JOIN d ON t.a < d.a GROUP BY d.w",     # non-equi join
     "SELECT a, SUM(x) OVER (PARTITION BY a) FROM t",                    # window function
     "SELECT 'lit' AS k, COUNT(*) FROM t GROUP BY k",                    # string literal as a group key
+    "SELECT a, MIN(s) FROM t GROUP BY a",                               # MIN over a dictionary-encoded string (reference: throws)
 ])
 def test_unsupported_sql_is_rejected(st, text):
     with pytest.raises((planner.UnsupportedPlan, SyntaxError, KeyError, ValueError)):
