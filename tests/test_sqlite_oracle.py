@@ -984,3 +984,26 @@ def test_null_div_by_zero_vs_sqlite(oracle_mod, text):
         util.assert_rows_equal(got, exp, rel=1e-9)
     # without the option the same division raises
     assert util.run_oracle(oracle_mod, st, util.plan_sql(st, text))[1] == 1
+
+
+# ASSERT_EQ(<literal>, v<…>(run_simple_agg("…"))) of the reference's tests that fall inside the subset: the expected values are
+# the reference's own, not SQLite's (mixed int / fp comparisons, a NOT NULL column holding the sentinel pattern, EXTRACT on
+# timestamps and days-encoded dates, date literals)
+REFERENCE_KNOWN_ANSWERS = [
+    (5, "SELECT COUNT(*) FROM test WHERE x > 7.1"),
+    (10, "SELECT COUNT(*) FROM test WHERE y > 42.5"),
+    (10, "SELECT COUNT(*) FROM test WHERE ufd > -2147483648.0"),
+    (15, "SELECT COUNT(*) FROM test WHERE ofd > -2147483648"),
+    (20140, "SELECT MAX(EXTRACT(YEAR FROM m) * 10) FROM test"),
+    (1999, "SELECT MAX(EXTRACT(YEAR FROM o)) FROM test"),
+    (0, "SELECT COUNT(*) FROM test where DATE '2017-05-30' = DATE '2017-05-31' OR DATE '2017-05-31' = DATE '2017-05-30'"),
+]
+
+
+@pytest.mark.parametrize("expected,text", REFERENCE_KNOWN_ANSWERS)
+def test_reference_known_answers(oracle_mod, expected, text):
+    st = util.make_storage(reference_test_table(), fragment_size=2)
+    pq = util.plan_sql(st, text)
+    for kind in ("port", "reference"):
+        buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
+        assert err == 0 and decode_with_dictionaries(st, pq, buf) == [(expected,)]
