@@ -105,4 +105,7 @@ def lib():
 def check(rc, what=""):
     if rc != 0:
         msg = lib().hdk_b200_last_error().decode(errors="replace")
+        if rc == abi.E_UNSUPPORTED:     # a plan shape outside the hot path reads the same whether the planner or the library refuses it
+            from .planner import UnsupportedPlan
+            raise UnsupportedPlan(f"{what}: {msg}")
         raise HdkB200Error(f"{what} failed with code {rc}: {msg}")

@@ -218,8 +218,13 @@ class PeerRows:
         return torch.as_tensor(_DevMem(self.local_ptrs[c].value, max(rows, 1) * self.widths[c]), device=self.device)[: rows * self.widths[c]]
 
     def close(self):
+        """Collective: every rank unmaps its peers' buffers, THEN (after a barrier) frees its own — freeing memory a
+        slower peer still has IPC-mapped is undefined behaviour (cudaIpcOpenMemHandle contract)."""
         for p in self.opened:
             self.lib.hdk_b200_peer_close(p)
+        self.opened = []
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
         for p in self.local_ptrs:
             self.lib.hdk_b200_peer_free(p)
-        self.opened, self.local_ptrs = [], []
+        self.local_ptrs = []

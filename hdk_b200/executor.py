@@ -387,7 +387,7 @@ class Executor:
         """BaselineJoinHashTable::reify (JHT/BaselineJoinHashTable.cpp:256-259: 2 x tuples entries): the one-to-one
         layout E x (components ‖ row id) first; a duplicate composite key (err = -1, NeedsOneToManyHash) rebuilds as the
         one-to-many layout — composite-key dictionary E x components, then offsets | counts | payload."""
-        cache_key = (inner.name, tuple(key_cols), key_width)
+        cache_key = (inner.name, id(inner), tuple(key_cols), key_width)   # id(): a table re-imported under the same name is another table
         if cache_key in self.join_tables:
             return self.join_tables[cache_key]
         torch = self.ctx.torch
@@ -427,7 +427,7 @@ class Executor:
         """HashJoin::getInstance → PerfectJoinHashTable::reify (JHT/PerfectJoinHashTable.cpp:90-383):
         one-to-one first; a duplicate key (err = -1) rebuilds as one-to-many (NeedsOneToManyHash); a key range too wide
         for a perfect table (TooManyHashEntries, :139-151) falls back to the baseline table like HashJoin::getInstance."""
-        cache_key = (inner.name, key_col)
+        cache_key = (inner.name, id(inner), key_col)
         if cache_key in self.join_tables:
             return self.join_tables[cache_key]
         torch = self.ctx.torch
@@ -839,7 +839,13 @@ class Executor:
             code = int(prep["err"].item())   # blocking copy of the error code = the reference's only sync
             if code < 0 and pq.qmd.hash_type == abi.BASELINE_HASH:
                 cur = pq.qmd.entry_count
-                guess = min(max(cur * 4, 2 * min(outer.num_rows, cur * 8)), max(2 * outer.num_rows, 16))
+                # groups <= rows the kernel aggregates: the outer rows, or with a one-to-many join up to the join's
+                # output cardinality (bounded here by outer rows x inner rows, and by what a uint32 entry count holds)
+                bound = outer.num_rows
+                if any(pq.plan.joins[j].one_to_many for j in range(pq.plan.n_joins)):
+                    inner_rows = max([self.storage.get_table(j.inner_table).num_rows for j in unit.joins] or [1])
+                    bound = min(outer.num_rows * max(inner_rows, 1), (1 << 31) - 1)
+                guess = min(max(cur * 4, 2 * min(bound, cur * 8)), max(2 * bound, 16))
                 if guess <= cur:
                     raise QueryError(code, "ran out of slots in the group-by buffer")
                 continue

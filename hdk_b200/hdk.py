@@ -60,7 +60,8 @@ class QueryNode:
             keys = [(ir.join_key_for(self.ref(lc), inner_t.columns[rc].type), rc) for lc, rc in zip(lhs_cols, rhs_cols)]
         except NotImplementedError as ex:
             raise planner.UnsupportedPlan(str(ex))
-        spec = ir.JoinSpec(rhs.table_name, keys[0][0], rhs_cols[0], keys[1:])   # > 1 column: baseline join table
+        spec = ir.JoinSpec(rhs.table_name, keys[0][0], rhs_cols[0], keys[1:],   # > 1 column: baseline join table
+                           [inner_t.columns[rc].type for rc in rhs_cols])
         return QueryNode(self._hdk, self.table_name, self._quals, self._joins + [spec])
 
     def _parse_expr(self, text: str) -> ir.Expr:

@@ -232,6 +232,10 @@ def join_key_for(outer: Expr, inner_type: SqlType) -> Expr:
     dictionary-encoded keys (two dictionaries: the ids are unrelated)."""
     if inner_type.kind == "dict" or outer.type.kind == "dict":
         raise NotImplementedError("join on dictionary-encoded columns needs a dictionary translation")
+    if inner_type.is_fp or outer.type.is_fp:
+        # the reference refuses to hash-join on a floating-point key (HashJoinFail → loop join, outside the hot path);
+        # probing with the raw bits of a double would silently match nothing
+        raise NotImplementedError("hash join on a floating-point key")
     if inner_type.date_in_days or outer.type.date_in_days:
         if isinstance(outer, ColumnRef) and outer.type.date_in_days and inner_type.date_in_days and outer.phys_width == 4:
             return ColumnRef(outer.table, outer.column, SqlType("int", 4, outer.type.nullable), outer.phys_width)
@@ -421,6 +425,7 @@ class JoinSpec:
     outer_key: Expr
     inner_key_column: str
     more_keys: List[tuple] = field(default_factory=list)
+    inner_key_types: List[SqlType] = field(default_factory=list)   # types of the inner key columns (all components)
 
     @property
     def outer_keys(self):

@@ -293,7 +293,8 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
         f = ir.with_null_div_by_zero
         unit = ir.ExecutionUnit(unit.table, [f(g) for g in unit.groupby_exprs], [f(t) for t in unit.target_exprs], unit.target_names,
                                 [f(q) for q in unit.quals],
-                                [ir.JoinSpec(j.inner_table, f(j.outer_key), j.inner_key_column, [(f(o), c) for o, c in j.more_keys])
+                                [ir.JoinSpec(j.inner_table, f(j.outer_key), j.inner_key_column, [(f(o), c) for o, c in j.more_keys],
+                                             j.inner_key_types)
                                  for j in unit.joins], unit.order_by, unit.limit, unit.n_hidden)
     non_grouped = not unit.groupby_exprs
     if non_grouped and any(not isinstance(t, ir.AggExpr) for t in unit.target_exprs):
@@ -552,8 +553,11 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
             p.joins[j].n_key_exprs = len(nodes)
             for i, nd in enumerate(nodes):
                 p.joins[j].key_exprs[i] = nd
-            # getKeyComponentWidth: 8 as soon as one component is wider than 4 bytes
-            p.joins[j].key_width = 8 if any(k.type.width > 4 for k in js.outer_keys) else 4
+            # BaselineJoinHashTable::getKeyComponentWidth (JHT/BaselineJoinHashTable.cpp:502-509): 8 as soon as one INNER
+            # key column is wider than 4 bytes (the table is built over the inner values: a narrower width would truncate
+            # them and alias e.g. 2^32 + 5 with 5); a wide outer expression needs 8 too, for the same reason on the probe
+            inner_wide = any(t.width > 4 for t in js.inner_key_types)
+            p.joins[j].key_width = 8 if (inner_wide or any(k.type.width > 4 for k in js.outer_keys)) else 4
     if len(unit.quals) > abi.MAX_FILTERS:
         raise UnsupportedPlan("too many filters")
     p.n_filters = len(unit.quals)

@@ -278,7 +278,7 @@ class _Parser:
                 self.eat("kw", "then")
                 arms.append((c, self.expr()))
             if not arms:
-                raise SyntaxError("CASE without WHEN")
+                raise UnsupportedPlan("CASE without WHEN")
             if self.accept("kw", "else"):
                 else_ = self.expr()
             self.eat("kw", "end")
@@ -400,6 +400,8 @@ class _Parser:
                     self.i = save
                     e = self.expr()
                     if isinstance(e, ir.Const) and isinstance(e.value, int):
+                        if not 1 <= e.value <= len(targets) - n_hidden:
+                            raise UnsupportedPlan(f"ORDER BY ordinal {e.value} is not a select item")
                         key = e.value - 1
                     elif e in targets:
                         key = targets.index(e)
@@ -465,7 +467,14 @@ class _Parser:
             for c in conjuncts(cond):
                 if not (isinstance(c, ir.Cmp) and c.op == "="):
                     raise UnsupportedPlan("only (conjunctions of) equi-join conditions are on the hot path")
-                strip = lambda x: x.arg if isinstance(x, ir.Cast) else x  # noqa: E731
+                # the implicit widening Cast the comparison puts on the narrower side is dropped (both sides are compared
+                # as integers of the join table's key width); any other Cast — narrowing, int <-> fp — changes the value
+                # and stays part of the outer expression (or refuses the plan on the inner side)
+                def strip(x):
+                    if isinstance(x, ir.Cast) and not x.type.is_fp and not x.arg.type.is_fp and x.type.width >= x.arg.type.width \
+                            and x.type.kind == x.arg.type.kind:
+                        return x.arg
+                    return x
                 lhs, rhs = strip(c.lhs), strip(c.rhs)
                 if isinstance(rhs, ir.ColumnRef) and rhs.table == jidx:
                     outer, inner = lhs, rhs
@@ -474,10 +483,10 @@ class _Parser:
                 else:
                     raise UnsupportedPlan("join condition must compare an outer expression with an inner column")
                 try:
-                    pairs.append((ir.join_key_for(outer, inner.type), inner.column))
+                    pairs.append((ir.join_key_for(outer, inner.type), inner.column, inner.type))
                 except NotImplementedError as ex:
                     raise UnsupportedPlan(str(ex))
-            joins.append(ir.JoinSpec(t2, pairs[0][0], pairs[0][1], pairs[1:]))
+            joins.append(ir.JoinSpec(t2, pairs[0][0], pairs[0][1], [(o, c) for o, c, _ in pairs[1:]], [t for _, _, t in pairs]))
         final_names = []
         for i, (e, n) in enumerate(zip(targets, names)):
             if n is None:

@@ -17,7 +17,7 @@ def _oracle_frs(oracle, st, pq):
 CASES = [
     ("taxi_q1", "taxi", "q1", 1), ("taxi_q2", "taxi", "q2", 1), ("taxi_q3", "taxi", "q3", 2), ("taxi_q4", "taxi", "q4", 3),
     ("c1_int64", "c1", "int", 1), ("c1_fp64", "c1", "fp", 1), ("tpch_q1", "lineitem", None, 2), ("star_join_sum", "star", None, 1),
-    ("tpch_q6", "lineitem", "q6", 0),
+    ("tpch_q6", "lineitem", "q6", 0), ("composite_key_sum_count", "c4", None, 2),
 ]
 
 

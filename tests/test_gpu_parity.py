@@ -284,6 +284,19 @@ def test_fused_baseline_join_probe(oracle_mod, L, torch, text, nk):
     util.assert_rows_equal(got, util.sqlite_rows(tables, text + " ORDER BY " + order, nk), rel=1e-9)
 
 
+def test_int32_outer_key_against_wide_int64_inner_key(oracle_mod, torch):
+    """the baseline join table is built over the inner values at the INNER columns' width — an int64 inner
+    2^32 + 35 must not alias with an int32 outer 35 (the GPU build used to truncate to 4 bytes)."""
+    import hdk_b200.hdk as hdkmod
+    tables = util.wide_inner_key_tables()
+    text, nk = util.WIDE_INNER_KEY_QUERY
+    h = hdkmod.init()
+    for name, tb in tables.items():
+        h.import_arrow(tb, name, fragment_size=701 if name == "t" else 100000)
+    got = [tuple(r.values()) for r in h.sql(text + " ORDER BY 1").to_arrow().to_pylist()]
+    util.assert_rows_equal(got, util.sqlite_rows(tables, text + " ORDER BY 1", nk))
+
+
 @pytest.mark.parametrize("text", util.NON_GROUPED_QUERIES)
 def test_non_grouped_aggregates(oracle_mod, torch, text):
     """Aggregates without GROUP BY on the GPU: buffer byte-identical to the oracle's where there is no fp sum, one row

@@ -154,3 +154,42 @@ def test_null_div_by_zero_makes_dependents_nullable(st):
     pq = util.plan_sql(st, "SELECT a, SUM(x / b) FROM t GROUP BY a", cfg=planner.Config(null_div_by_zero=True))
     div = [pq.plan.exprs[i] for i in range(pq.plan.n_exprs) if pq.plan.exprs[i].op == abi.OP_DIV]
     assert div and all(d.aux & 2 and d.type.nullable and d.guard == 0 for d in div)
+
+
+def test_baseline_join_key_width_follows_the_inner_columns():
+    """BaselineJoinHashTable::getKeyComponentWidth (JHT/BaselineJoinHashTable.cpp:502-509): 8 bytes per component as soon
+    as one INNER key column is wider than 4 bytes — an int32 outer column probing an int64 inner column must not build
+    a 4-byte table (2^32 + 5 would alias with 5)."""
+    n = 40
+    t = pa.table({"a": np.arange(n, dtype=np.int32) % 7, "b": np.arange(n, dtype=np.int32) % 3, "x": np.arange(n, dtype=np.int64)})
+    d = pa.table({"w": np.array([0, 1, 2, 3, 2**32 + 5, 5, 6], dtype=np.int64), "b": np.arange(7, dtype=np.int32) % 3,
+                  "g": np.arange(7, dtype=np.int32)})
+    st2 = util.make_storage({"t": t, "d": d}, fragment_size=16)
+    pq = util.plan_sql(st2, "SELECT d.g, COUNT(*) FROM t JOIN d ON t.a = d.w AND t.b = d.b GROUP BY d.g")
+    assert pq.plan.joins[0].n_key_exprs == 2 and pq.plan.joins[0].key_width == 8
+    # narrow on both sides stays at 4
+    pq = util.plan_sql(st2, "SELECT d.g, COUNT(*) FROM t JOIN d ON t.a = d.g AND t.b = d.b GROUP BY d.g")
+    assert pq.plan.joins[0].n_key_exprs == 2 and pq.plan.joins[0].key_width == 4
+
+
+@pytest.mark.parametrize("text", [
+    "SELECT d.w, COUNT(*) FROM t JOIN d ON t.f = d.a GROUP BY d.w",              # floating-point outer join key
+    "SELECT d.w, COUNT(*) FROM t JOIN d ON CAST(t.x AS INT) = d.a GROUP BY d.w AND 1 = 1",
+    "SELECT a, COUNT(*) FROM t GROUP BY a ORDER BY 0",                          # ORDER BY ordinal out of range
+    "SELECT a, COUNT(*) FROM t GROUP BY a ORDER BY 3",
+    "SELECT a, SUM(CASE ELSE 1 END) FROM t GROUP BY a",                         # CASE without WHEN
+])
+def test_refused_as_unsupported_plan(st, text):
+    """Refusals must surface as UnsupportedPlan (the façade's "not on the hot path"), not as IndexError / a silently wrong
+    answer: fp join keys (the reference refuses to hash-join on them), ORDER BY ordinals outside the select list."""
+    with pytest.raises((planner.UnsupportedPlan, SyntaxError)):
+        util.plan_sql(st, text)
+
+
+def test_fp_join_key_is_unsupported_plan(st):
+    with pytest.raises(planner.UnsupportedPlan):
+        util.plan_sql(st, "SELECT d.w, COUNT(*) FROM t JOIN d ON t.f = d.a GROUP BY d.w")
+    with pytest.raises(planner.UnsupportedPlan):
+        util.plan_sql(st, "SELECT a, COUNT(*) FROM t GROUP BY a ORDER BY 0")
+    with pytest.raises(planner.UnsupportedPlan):
+        util.plan_sql(st, "SELECT a, COUNT(*) FROM t GROUP BY a ORDER BY 3")

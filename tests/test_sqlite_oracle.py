@@ -81,6 +81,22 @@ def test_baseline_join_probe_in_row_function_vs_sqlite(oracle_mod, text, nk):
         assert err2 == 0 and np.array_equal(buf, buf2)
 
 
+def test_int32_outer_key_against_wide_int64_inner_key_vs_sqlite(oracle_mod):
+    """Key component width of a baseline join table comes from the INNER columns (BaselineJoinHashTable.cpp:502-509):
+    inner 2^32 + 35 must not match outer 35."""
+    tables = util.wide_inner_key_tables()
+    st = util.make_storage(tables, fragment_size={"t": 701, "dim": 100000})
+    text, nk = util.WIDE_INNER_KEY_QUERY
+    pq = util.plan_sql(st, text)
+    assert pq.plan.joins[0].key_width == 8
+    buf, err = util.run_oracle(oracle_mod, st, pq, kind="port")
+    assert err == 0
+    got = util.sort_rows(util.result_columns(oracle_mod, pq, buf), nk)
+    exp = util.sqlite_rows(tables, text + " ORDER BY 1", nk)
+    util.assert_rows_equal(got, exp)
+    assert sum(r[1] for r in got) < tables["t"].num_rows          # outer values 30..49 only exist as 2^32 + v on the inner side
+
+
 @pytest.mark.parametrize("text", util.NON_GROUPED_QUERIES)
 def test_non_grouped_aggregates_vs_sqlite(oracle_mod, text):
     """Aggregates without GROUP BY (the reference's NonGroupedAggregate) run as the degenerate group-by — zero keys,

@@ -96,13 +96,16 @@ def oracle_inputs(oracle, st, pq):
     return frs, join_tables, inner_cols
 
 
-def run_oracle(oracle, st, pq, kind="port", n_threads=2, per_fragment=True):
-    """The oracle over its own host-built join tables.  oracle_inputs describes those tables in the plan's join PODs
+def run_oracle(oracle, st, pq, kind=None, n_threads=2, per_fragment=True):
+    """The oracle over its own host-built join tables.  kind=None: the reference's own runtime (oracle/_ref, compiled from
+    the reference's sources) when it is present — it travels to the GPU box — else the port pinned to it on the CPU.  oracle_inputs describes those tables in the plan's join PODs
     (layout, entry count, no slot-ordered payload), so it works on a copy: `pq` may already be prepared for the GPU,
     whose join tables are laid out differently."""
     import copy
     pq2 = copy.copy(pq)
     pq2.plan = abi.Plan.from_buffer_copy(pq.plan)
+    if kind is None:
+        kind = "reference" if oracle.ref_available() else "port"
     frs, jt, ic = oracle_inputs(oracle, st, pq2)
     buf, err = oracle.run_query(pq2, frs, jt, ic, n_threads=n_threads, kind=kind, per_fragment=per_fragment)
     return buf, err
@@ -187,3 +190,17 @@ NON_GROUPED_QUERIES = [
     "SELECT SUM(f * (1 - f)), MIN(f), MAX(x) FROM t",
     "SELECT SUM(t.x), COUNT(*) FROM t JOIN dim ON t.a = dim.a AND t.b = dim.b WHERE dim.w > 500",
 ]
+
+
+def wide_inner_key_tables(seed=5, n=3000):
+    """An int32 outer key joined to an int64 inner column holding values >= 2^32 whose low halves collide with real outer
+    values (and one whose low half is EMPTY_KEY_32): a 4-byte join table would alias them."""
+    rng = np.random.default_rng(seed)
+    t = pa.table({"a": rng.integers(0, 50, n).astype(np.int32), "b": rng.integers(0, 4, n).astype(np.int32), "x": rng.integers(-100, 100, n)})
+    w = np.concatenate([np.arange(0, 30, dtype=np.int64), 2**32 + np.arange(30, 50, dtype=np.int64), [2**32 + 2**31 - 1, 2**33 + 7]])
+    b = np.arange(len(w), dtype=np.int32) % 4
+    dim = pa.table({"w": w, "b": b, "g": (np.arange(len(w)) % 6).astype(np.int32)})
+    return {"t": t, "dim": dim}
+
+
+WIDE_INNER_KEY_QUERY = ("SELECT dim.g, COUNT(*), SUM(t.x) FROM t JOIN dim ON t.a = dim.w AND t.b = dim.b GROUP BY dim.g", 1)
