@@ -70,7 +70,7 @@ def test_static_shape_parity(oracle_mod, name, kind, sub, nk):
     util.assert_rows_equal(util.sort_rows(util.result_columns(oracle_mod, pq, got), nk), exp)
     util.assert_rows_equal(util.sort_rows(util.result_columns(oracle_mod, pq, gen), nk), exp)
     has_fp_sum = any(ti.agg in (abi.AGG_SUM, abi.AGG_AVG) and ti.arg_type is not None and ti.arg_type.is_fp for ti in pq.infos)
-    if not has_fp_sum:
+    if not has_fp_sum and pq.qmd.hash_type == abi.PERFECT_HASH:   # (baseline hash: colliding keys may settle in either order)
         assert np.array_equal(got, obuf) and np.array_equal(gen, obuf)
 
 
