@@ -28,7 +28,7 @@ EXPORTS = [
     "hdk_b200_init_chunk_stats_on_device",
     "hdk_b200_materialize_nulls_on_device", "hdk_b200_peer_alloc", "hdk_b200_peer_open", "hdk_b200_peer_close",
     "hdk_b200_peer_free", "hdk_b200_exchange_bytes", "hdk_b200_exchange_init", "hdk_b200_launch_exchange", "hdk_b200_query_host", "hdk_b200_last_error", "hdk_b200_abi_version",
-    "hdk_b200_device_count", "hdk_b200_launch_count",
+    "hdk_b200_device_count", "hdk_b200_launch_count", "hdk_b200_launch_scratch_bytes", "hdk_b200_debug_set",
 ]
 
 
@@ -81,6 +81,8 @@ def _bind(lib):
         "hdk_b200_abi_version": (ci, []),
         "hdk_b200_device_count": (ci, []),
         "hdk_b200_launch_count": (u64, []),
+        "hdk_b200_launch_scratch_bytes": (ci, [P, Q, u64, C.POINTER(sz)]),
+        "hdk_b200_debug_set": (ci, [C.c_char_p, ci]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -100,6 +102,11 @@ def lib():
         if _lib.hdk_b200_abi_version() != abi.ABI_VERSION:
             raise HdkB200Error("libhdk_b200.so ABI version mismatch; rebuild")
     return _lib
+
+
+def debug_set(name: str, value: int):
+    """hdk_b200_debug_set: process-wide debug / tuning knobs ("force_generic", "force_strategy", "partitioned_aggregation")."""
+    check(lib().hdk_b200_debug_set(name.encode(), int(value)), f"debug_set({name})")
 
 
 def check(rc, what=""):

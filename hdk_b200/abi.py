@@ -28,7 +28,7 @@ INT, FP = 0, 1
 
 AGG_NONE, AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX, AGG_AVG = range(6)
 PERFECT_HASH, BASELINE_HASH = 0, 1
-STRATEGY_THREAD_PRIVATE, STRATEGY_CTA_SHARED, STRATEGY_GLOBAL, STRATEGY_BASELINE = range(4)
+STRATEGY_THREAD_PRIVATE, STRATEGY_CTA_SHARED, STRATEGY_GLOBAL, STRATEGY_BASELINE, STRATEGY_REGISTER, STRATEGY_PARTITIONED = range(6)
 SMALL_DATE, SIGNED, UNSIGNED, DOUBLE = range(4)
 
 

@@ -1,8 +1,10 @@
 // hdk_b200/csrc/api.cu — C-ABI entry points of the launch path (include/hdk_b200.h).
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
 #include "common.cuh"
+#include "partagg.cuh"
 #include "scan.cuh"
 
 namespace hb {
@@ -10,6 +12,26 @@ int init_group_by_buffer(const Lowered& lw, int64_t* buf, cudaStream_t stream);
 }
 
 extern "C" {
+
+// Should this baseline-hash launch run radix-partitioned (partagg.cu)?  Eligible plan, row count known, and either forced
+// or a table far beyond L2 (the per-row global probe then costs a random DRAM sector and several global atomics).
+static bool wants_partitioned(const hb::Lowered& lw, uint64_t total_rows, size_t* need) {
+  *need = 0;
+  if (lw.plan.hash_type != HDK_B200_BASELINE_HASH || hb::g_debug.partitioned == 0 || total_rows == 0) return false;
+  if (hb::partagg_scratch_bytes(lw, total_rows, need) != HDK_B200_OK) return false;
+  if (hb::g_debug.partitioned == 1) return true;
+  const size_t table_bytes = size_t(lw.plan.entry_count) * (lw.layout.row_bytes + size_t(lw.plan.n_acc) * 8);
+  return table_bytes > (size_t(48) << 20) && total_rows >= (1u << 20);
+}
+
+int hdk_b200_launch_scratch_bytes(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, uint64_t total_rows, size_t* scratch_bytes) {
+  hb::Lowered lw;
+  if (int rc = hb::lower_plan(plan, qmd, &lw)) return rc;
+  size_t need = 0;
+  const bool pa = wants_partitioned(lw, total_rows, &need);
+  if (scratch_bytes) *scratch_bytes = pa ? std::max(need, lw.work_table_bytes) : lw.work_table_bytes;
+  return HDK_B200_OK;
+}
 
 int hdk_b200_init_work_table(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, int64_t* work_table, void* stream) {
   hb::Lowered lw;
@@ -53,6 +75,9 @@ int hdk_b200_launch(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, const hd
   }
   int64_t* work = static_cast<int64_t*>(scratch);
   if (qmd->hash_type == HDK_B200_BASELINE_HASH) {
+    size_t need = 0;
+    if (wants_partitioned(lw, params->total_rows_hint, &need) && scratch_bytes >= need)
+      return hb::launch_partagg(lw, params, scratch, scratch_bytes, st, info);
     // keys are claimed in the caller-initialised buffer, aggregates accumulate in the entry-major work table,
     // finalize encodes the slots of the claimed entries
     if (int rc = hb::init_work_table(lw, work, st)) return rc;

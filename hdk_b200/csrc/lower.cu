@@ -11,11 +11,13 @@
 #include <string>
 
 #include "common.cuh"
+#include "partagg.cuh"
 
 namespace hb {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launch_count = 0;
+DebugKnobs g_debug = {0, -1, -1, 0, 0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -410,6 +412,18 @@ __attribute__((visibility("default"))) int hdk_b200_internal_dump_shape(const hd
 }
 
 const char* hdk_b200_last_error(void) { return hb::last_error(); }
+
+int hdk_b200_debug_set(const char* name, int value) {
+  if (!name) { hb::set_error("null knob name"); return HDK_B200_E_INVALID; }
+  const std::string n(name);
+  if (n == "force_generic") hb::g_debug.force_generic = value != 0;
+  else if (n == "force_strategy") hb::g_debug.force_strategy = value;
+  else if (n == "partitioned_aggregation") hb::g_debug.partitioned = value;
+  else if (n == "partitioned_table_slots") hb::g_debug.pa_slots = value;
+  else if (n == "partitioned_partitions") hb::g_debug.pa_partitions = value;
+  else { hb::set_error("unknown debug knob '%s'", name); return HDK_B200_E_INVALID; }
+  return HDK_B200_OK;
+}
 int hdk_b200_abi_version(void) { return HDK_B200_ABI_VERSION; }
 uint64_t hdk_b200_launch_count(void) { return hb::g_launch_count; }
 int hdk_b200_device_count(void) {

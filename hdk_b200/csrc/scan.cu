@@ -24,73 +24,14 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "accum.cuh"
 #include "baseline.cuh"
 #include "device_utils.cuh"
 #include "eval.cuh"
+#include "partagg.cuh"
 #include "scan.cuh"
 
 namespace hb {
-
-// Is the accumulator's argument NULL for this row?  mode 1: the argument's own sentinel; mode 2: the
-// reference's COUNT(int64) quirk (see lower.cu)
-__device__ __forceinline__ bool acc_arg_is_null(const DPlan& p, const DAcc& a, const V* vals) {
-  if (!a.arg_nullable) return false;
-  const DExpr& t = p.exprs[a.arg];
-  const V v = vals[a.arg];
-  if (t.kind == HDK_B200_FP) return v.f == fp_null_of(t.width);
-  if (v.i == int_null_of(t.width)) return true;
-  return a.arg_nullable == 2 && int32_t(v.i) == INT32_MIN;
-}
-
-__device__ __forceinline__ int64_t acc_identity(uint8_t kind) {
-  return (kind == ACC_MIN_I || kind == ACC_MIN_F) ? INT64_MAX : (kind == ACC_MAX_I || kind == ACC_MAX_F) ? INT64_MIN : 0;
-}
-
-// value contributed by this row to accumulator `a` (as an int64 cell / double bits)
-__device__ __forceinline__ int64_t acc_input(const DPlan& p, const DAcc& a, const V* vals) {
-  switch (a.kind) {
-    case ACC_CNT_ALL: case ACC_CNT_NN: return 1;
-    case ACC_SUM_I: case ACC_MIN_I: case ACC_MAX_I: return vals[a.arg].i;
-    case ACC_SUM_F: return vals[a.arg].i;  // bits of the double
-    default: return f64_order_encode(vals[a.arg].f);  // MIN_F / MAX_F
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// accumulator updates
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bin_update_private(uint8_t kind, uint8_t* bin, int64_t x) {
-  switch (kind) {
-    case ACC_CNT_ALL: case ACC_CNT_NN: *reinterpret_cast<uint32_t*>(bin) += 1u; break;
-    case ACC_SUM_I: *reinterpret_cast<int64_t*>(bin) += x; break;
-    case ACC_SUM_F: *reinterpret_cast<double*>(bin) += __longlong_as_double(x); break;
-    case ACC_MIN_I: case ACC_MIN_F: { int64_t* b = reinterpret_cast<int64_t*>(bin); *b = min(*b, x); break; }
-    default: { int64_t* b = reinterpret_cast<int64_t*>(bin); *b = max(*b, x); break; }
-  }
-}
-__device__ __forceinline__ void bin_update_shared_atomic(uint8_t kind, uint8_t* bin, int64_t x) {
-  switch (kind) {
-    case ACC_CNT_ALL: case ACC_CNT_NN: atomicAdd(reinterpret_cast<uint32_t*>(bin), 1u); break;
-    case ACC_SUM_I: atomicAdd(reinterpret_cast<unsigned long long*>(bin), static_cast<unsigned long long>(x)); break;
-    case ACC_SUM_F: atomicAdd(reinterpret_cast<double*>(bin), __longlong_as_double(x)); break;
-    // 64-bit shared atomics are CAS loops (SASS ATOMS.CAST.SPIN.64): look first, a bin only ever moves towards x
-    case ACC_MIN_I: case ACC_MIN_F:
-      if (x < *reinterpret_cast<volatile int64_t*>(bin)) atomicMin(reinterpret_cast<long long*>(bin), static_cast<long long>(x));
-      break;
-    default:
-      if (x > *reinterpret_cast<volatile int64_t*>(bin)) atomicMax(reinterpret_cast<long long*>(bin), static_cast<long long>(x));
-      break;
-  }
-}
-__device__ __forceinline__ void cell_update_global(uint8_t kind, int64_t* cell, int64_t x) {
-  switch (kind) {
-    case ACC_CNT_ALL: case ACC_CNT_NN: case ACC_SUM_I:
-      atomicAdd(reinterpret_cast<unsigned long long*>(cell), static_cast<unsigned long long>(x)); break;
-    case ACC_SUM_F: atomicAdd(reinterpret_cast<double*>(cell), __longlong_as_double(x)); break;
-    case ACC_MIN_I: case ACC_MIN_F: atomicMin(reinterpret_cast<long long*>(cell), static_cast<long long>(x)); break;
-    default: atomicMax(reinterpret_cast<long long*>(cell), static_cast<long long>(x)); break;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
@@ -985,7 +926,7 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
 
   // pre-compiled shape for this plan?  (its iteration granularity shapes the tile size)
   const StaticEntry* stat = nullptr;
-  if (!(ko && ko->literalsOffset == 0xB200F0FFu)) {  // test hook: force the generic kernel
+  if (!g_debug.force_generic) {  // (hdk_b200_debug_set("force_generic", 1): tests run the interpreter on the benchmark shapes)
     const uint64_t sig = plan_signature(p);
     for (int i = 0; kStaticShapes[i].name; ++i)
       if (kStaticShapes[i].sig == sig) { stat = &kStaticShapes[i]; break; }
@@ -1075,10 +1016,9 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   Geo geo{};
   bool have = false;
   int forced = -1;
-  if (!baseline && ko && ko->sharedMemBytes == 0xB200F001u) forced = HDK_B200_STRATEGY_THREAD_PRIVATE;  // test hooks
-  if (!baseline && ko && ko->sharedMemBytes == 0xB200F002u) forced = HDK_B200_STRATEGY_CTA_SHARED;
-  if (!baseline && ko && ko->sharedMemBytes == 0xB200F003u) forced = HDK_B200_STRATEGY_GLOBAL;
-  if (!baseline && ko && ko->sharedMemBytes == 0xB200F005u) forced = HDK_B200_STRATEGY_REGISTER;
+  if (!baseline && g_debug.force_strategy >= 0 && g_debug.force_strategy <= HDK_B200_STRATEGY_REGISTER &&
+      g_debug.force_strategy != HDK_B200_STRATEGY_BASELINE)
+    forced = g_debug.force_strategy;   // hdk_b200_debug_set("force_strategy", s): tests / tuning
   if (baseline) have = best(HDK_B200_STRATEGY_BASELINE, &geo);
   else if (forced == HDK_B200_STRATEGY_REGISTER && !(stat && stat->fn[forced] && E <= size_t(kRegGroups))) have = false;
   else if (forced >= 0) have = best(forced, &geo);

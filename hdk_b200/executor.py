@@ -584,7 +584,9 @@ class Executor:
         kp.groupby_buf = bufptr.data_ptr()
         kp.error_codes = err.data_ptr()
         scratch_bytes = C.c_size_t(0)
-        _lib.check(self.lib.hdk_b200_plan_check(C.byref(pq.plan), C.byref(pq.qmd), C.byref(scratch_bytes)), "plan_check")
+        # (what the launch wants for this many rows: a large baseline-hash group-by stages one packed record per row there)
+        _lib.check(self.lib.hdk_b200_launch_scratch_bytes(C.byref(pq.plan), C.byref(pq.qmd), int(kp.total_rows_hint),
+                                                          C.byref(scratch_bytes)), "launch_scratch_bytes")
         scratch = self.ctx.get_scratch(scratch_bytes.value)
         keep += [bufptr, scratch]
         return dict(kp=kp, keep=keep, out=out, err=err, scratch=scratch, scratch_bytes=scratch_bytes.value)

@@ -296,12 +296,22 @@ enum hdk_b200_strategy {
   HDK_B200_STRATEGY_CTA_SHARED = 1,     /* per-CTA table in shared memory, shared atomics */
   HDK_B200_STRATEGY_GLOBAL = 2,         /* perfect hash straight into the global work table */
   HDK_B200_STRATEGY_BASELINE = 3,       /* open addressing in the global group-by buffer */
-  HDK_B200_STRATEGY_REGISTER = 4        /* <= 8 groups, pre-compiled shapes: every thread keeps all groups' accumulators in registers */
+  HDK_B200_STRATEGY_REGISTER = 4,       /* <= 8 groups, pre-compiled shapes: every thread keeps all groups' accumulators in registers */
+  HDK_B200_STRATEGY_PARTITIONED = 5     /* baseline hash, large tables: rows radix-partitioned by key hash, every partition      */
+                                        /* aggregated in shared memory, groups written straight into the reference layout        */
 };
 
 /* Validate a plan/descriptor pair and report the scratch (device) bytes the
  * launch needs.  Host-only, no CUDA calls. */
 HDK_B200_API int hdk_b200_plan_check(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, size_t* scratch_bytes);
+
+/* Scratch bytes hdk_b200_launch wants for `total_rows` input rows (sum of NUM_ROWS; 0 = unknown): at least what
+ * hdk_b200_plan_check reports.  Large baseline-hash group-bys (QE/RelAlgExecutor.cpp:691-838 is the reference's own,
+ * CPU-only, partitioned aggregation) run radix-partitioned when the caller provides this much scratch and states
+ * params->total_rows_hint: one packed record per row (keys + aggregate arguments) is staged in the scratch area.
+ * With less scratch the launch falls back to probing the global table per row — same results, slower. */
+HDK_B200_API int hdk_b200_launch_scratch_bytes(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, uint64_t total_rows,
+                                               size_t* scratch_bytes);
 
 /* Bytes of the group-by buffer for this descriptor:
  * QueryMemoryDescriptor::getBufferSizeBytes (QueryMemoryDescriptor.cpp:457-481). */
@@ -654,6 +664,13 @@ HDK_B200_API int hdk_b200_query_host(const hdk_b200_plan* plan, const hdk_b200_q
                         int8_t* out_buffer, int device, hdk_b200_launch_info* info);
 
 /* ---- misc ------------------------------------------------------------------ */
+/* Process-wide debug / tuning knobs (tests, tools/): never needed for correct results.
+ *   "force_generic"            1 = never dispatch to a pre-compiled plan shape (run the interpreting kernel)
+ *   "force_strategy"           -1 = library picks; HDK_B200_STRATEGY_* = accumulation strategy of perfect-hash launches
+ *   "partitioned_aggregation"  -1 = library picks; 0 = never; 1 = whenever the plan is eligible and the scratch suffices
+ *   "partitioned_table_slots"  0 = library picks; else the slots of the per-CTA shared table (tests force partition splits)
+ *   "partitioned_partitions"   0 = library picks; else the number of partitions */
+HDK_B200_API int hdk_b200_debug_set(const char* name, int value);
 HDK_B200_API const char* hdk_b200_last_error(void);
 HDK_B200_API int hdk_b200_abi_version(void);
 HDK_B200_API int hdk_b200_device_count(void);

@@ -289,10 +289,31 @@ def large_queries(seed, n):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,config", [(41, {}), (42, {"enable_columnar_output": True}), (43, {"baseline_threshold": 1})])
+@pytest.mark.parametrize("seed,config", [(41, {}), (42, {"enable_columnar_output": True}), (43, {"baseline_threshold": 1}),
+                                         (44, {"baseline_threshold": 1, "partitioned": (0, 0)}),
+                                         (45, {"baseline_threshold": 1, "partitioned": (512, 7)}),
+                                         (46, {"baseline_threshold": 1, "enable_columnar_output": True, "partitioned": (0, 40), "generic": 1})])
 def test_fuzz_large_tables_gpu_vs_oracle(oracle_mod, seed, config):
+    """("partitioned": (table slots, partitions) — baseline-hash plans run through the radix-partitioned aggregation;
+    "generic": its interpreter passes even where the plan is a direct one)"""
+    from hdk_b200 import _lib
+    config = dict(config)
+    pa, generic = config.pop("partitioned", None), config.pop("generic", 0)
+    if pa is not None:
+        _lib.debug_set("partitioned_aggregation", 1)
+        _lib.debug_set("partitioned_table_slots", pa[0])
+        _lib.debug_set("partitioned_partitions", pa[1])
+        _lib.debug_set("force_generic", generic)
+    try:
+        _fuzz_large_tables(oracle_mod, seed, config, pa is not None)
+    finally:
+        for k, v in (("partitioned_aggregation", -1), ("partitioned_table_slots", 0), ("partitioned_partitions", 0), ("force_generic", 0)):
+            _lib.debug_set(k, v)
+
+
+def _fuzz_large_tables(oracle_mod, seed, config, want_partitioned):
     import torch
-    from hdk_b200 import planner, sql
+    from hdk_b200 import abi, planner, sql
     from hdk_b200.executor import Executor
     from tests.test_gpu_parity import check_against_oracle
     tables = large_table(seed)
@@ -311,3 +332,4 @@ def test_fuzz_large_tables_gpu_vs_oracle(oracle_mod, seed, config):
         except AssertionError as e:
             raise AssertionError(f"{text} [strategy {info.strategy}]: {e}")
     assert len(strategies) >= 3
+    assert (abi.STRATEGY_PARTITIONED in strategies) == want_partitioned

@@ -58,9 +58,12 @@ def test_static_shape_parity(oracle_mod, name, kind, sub, nk):
         assert info.strategy == 4, "TPC-H Q1 (6 groups, 11 accumulators) should keep its accumulators in registers"
     got = prep["out"].cpu().numpy().copy()
     # the same plan on the generic kernel
-    ko = abi.KernelOptions()
-    ko.literalsOffset = 0xB200F0FF
-    info2 = ex.launch(pq, prep, ko)
+    from hdk_b200 import _lib
+    _lib.debug_set("force_generic", 1)
+    try:
+        info2 = ex.launch(pq, prep)
+    finally:
+        _lib.debug_set("force_generic", 0)
     torch.cuda.synchronize()
     assert info2.variant == 0
     gen = prep["out"].cpu().numpy().copy()
@@ -104,10 +107,46 @@ def test_register_strategy_few_groups(oracle_mod, sub):
     util.assert_rows_equal(util.sort_rows(util.result_columns(oracle_mod, pq, got), 1), exp)
     if sub == "int":
         assert np.array_equal(got, obuf)
-    for hook in (0xB200F001, 0xB200F002, 0xB200F005):
-        ko = abi.KernelOptions()
-        ko.sharedMemBytes = hook
-        i2 = ex.launch(pq, prep, ko)
+    from hdk_b200 import _lib
+    for strategy in (0, 1, 4):
+        _lib.debug_set("force_strategy", strategy)
+        try:
+            i2 = ex.launch(pq, prep)
+        finally:
+            _lib.debug_set("force_strategy", -1)
         torch.cuda.synchronize()
-        assert i2.strategy == {0xB200F001: 0, 0xB200F002: 1, 0xB200F005: 4}[hook]
+        assert i2.strategy == strategy
         util.assert_rows_equal(util.sort_rows(util.result_columns(oracle_mod, pq, prep["out"].cpu().numpy()), 1), exp)
+
+
+@pytest.mark.parametrize("generic,slots,partitions", [(0, 0, 0), (1, 0, 0), (0, 1024, 2), (0, 0, 3000)])
+def test_c4_partitioned_aggregation(oracle_mod, generic, slots, partitions):
+    """Config 4's shape through the radix-partitioned aggregation (what runs at BASELINE.json's size, where the 2e8-entry
+    table is far beyond L2): direct passes (plain columns, no interpreter) and the interpreting ones, against the oracle."""
+    import torch
+    import benchdata
+    from hdk_b200 import _lib, sql
+    from hdk_b200.executor import Executor
+    from hdk_b200.storage import ArrowStorage
+    dev = torch.device("cuda", 0)
+    st = ArrowStorage()
+    benchdata.make_c4(st, dev, 400_003, 60_000, fragment_rows=90_001, keep_host=True)
+    knobs = (("partitioned_aggregation", 1, -1), ("force_generic", generic, 0), ("partitioned_table_slots", slots, 0),
+             ("partitioned_partitions", partitions, 0))
+    for k, v, _ in knobs:
+        _lib.debug_set(k, v)
+    try:
+        ex = Executor(st)
+        pq = ex.plan(sql.parse(benchdata.C4_QUERY, st.tables), 131072)
+        prep = ex.prepare(pq)
+        info = ex.launch(pq, prep)
+        torch.cuda.synchronize()
+    finally:
+        for k, _, v in knobs:
+            _lib.debug_set(k, v)
+    assert int(prep["err"].item()) == 0
+    assert info.strategy == abi.STRATEGY_PARTITIONED and info.variant == (0 if generic else 1)
+    got = prep["out"].cpu().numpy()
+    obuf, oerr = util.run_oracle(oracle_mod, st, pq, n_threads=4)
+    assert oerr == 0
+    util.assert_rows_equal(util.sort_rows(util.result_columns(oracle_mod, pq, got), 2), util.sort_rows(util.result_columns(oracle_mod, pq, obuf), 2))

@@ -163,29 +163,29 @@ def test_every_query_with_columnar_output(oracle_mod, env, torch, idx):
     check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
 
 
-@pytest.mark.parametrize("strategy", [0xB200F001, 0xB200F002, 0xB200F003])
+@pytest.mark.parametrize("strategy", [0, 1, 2])
 @pytest.mark.parametrize("text,nk", [(QUERIES[2][0], 1), (QUERIES[3][0], 1), (QUERIES[4][0], 2), (QUERIES[7][0], 1), (QUERIES[8][0], 1)])
 def test_every_accumulation_strategy(oracle_mod, env, torch, strategy, text, nk):
     """THREAD_PRIVATE / CTA_SHARED / GLOBAL must agree with the oracle on the same plan."""
     from hdk_b200.executor import Executor
     tables, st = env
     ex = Executor(st)
-    from hdk_b200 import sql
+    from hdk_b200 import _lib, sql
     unit = sql.parse(text, st.tables)
     pq = ex.plan(unit)
     prep = ex.prepare(pq)
-    ko = abi.KernelOptions()
-    ko.sharedMemBytes = strategy
-    from hdk_b200._lib import HdkB200Error
+    _lib.debug_set("force_strategy", strategy)
     try:
-        info = ex.launch(pq, prep, ko)
-    except HdkB200Error as e:
+        info = ex.launch(pq, prep)
+    except (_lib.HdkB200Error, planner.UnsupportedPlan) as e:
         if "does not fit" in str(e):
             pytest.skip("forced strategy does not fit in shared memory for this plan")
         raise
+    finally:
+        _lib.debug_set("force_strategy", -1)
     torch.cuda.synchronize()
     assert int(prep["err"].item()) == 0
-    assert info.strategy == {0xB200F001: 0, 0xB200F002: 1, 0xB200F003: 2}[strategy]
+    assert info.strategy == strategy
     check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
 
 
@@ -1046,6 +1046,61 @@ def test_baseline_region_pass_does_not_change_results(oracle_mod, env, torch, id
         torch.cuda.synchronize()
         assert int(prep["err"].item()) == 0
         check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+
+
+@pytest.fixture
+def partitioned():
+    """Force the radix-partitioned baseline-hash aggregation (partagg.cu) whatever the table size; knobs reset afterwards."""
+    from hdk_b200 import _lib
+
+    def set_(slots=0, partitions=0, generic=0):
+        _lib.debug_set("partitioned_aggregation", 1)
+        _lib.debug_set("partitioned_table_slots", slots)
+        _lib.debug_set("partitioned_partitions", partitions)
+        _lib.debug_set("force_generic", generic)
+    yield set_
+    for k, v in (("partitioned_aggregation", -1), ("partitioned_table_slots", 0), ("partitioned_partitions", 0), ("force_generic", 0)):
+        _lib.debug_set(k, v)
+
+
+@pytest.mark.parametrize("slots,partitions", [(0, 0), (128, 3), (256, 1), (0, 700)])
+@pytest.mark.parametrize("idx", [12, 13, 14, 15])
+def test_partitioned_aggregation_matches_oracle(oracle_mod, env, torch, partitioned, idx, slots, partitions):
+    """Baseline-hash group-bys through the partitioned path: count → offsets → scatter of packed records → per-partition
+    aggregation in shared memory → entries written in the reference layout (row-wise 8- and 4-byte keys, columnar; filters;
+    every aggregate kind).  Tiny shared tables / a single partition force the split-by-more-hash-bits path."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    text, nk, kw = QUERIES[idx]
+    partitioned(slots, partitions)
+    ex = Executor(st, kw.get("cfg"))
+    pq = ex.plan(sql.parse(text, st.tables), kw.get("max_groups_buffer_entry_count"), kw.get("output_columnar"))
+    assert pq.qmd.hash_type == abi.BASELINE_HASH
+    prep = ex.prepare(pq)
+    info = ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    assert info.strategy == abi.STRATEGY_PARTITIONED
+    check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+
+
+def test_partitioned_aggregation_out_of_slots(env, torch, partitioned):
+    """More groups than entries: the reference's get_group_value returns NULL → ERR_OUT_OF_SLOTS (negative code); the
+    partitioned path reports the same when the groups do not fit the buffer, and hdk.sql's retry ladder then succeeds."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    partitioned()
+    ex = Executor(st)
+    text, nk, kw = QUERIES[13]
+    pq = ex.plan(sql.parse(text, st.tables), 64)
+    prep = ex.prepare(pq)
+    ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == -abi.ERR_OUT_OF_SLOTS
+    rs = ex.execute_work_unit(sql.parse(text, st.tables))
+    assert rs.row_count() > 64
 
 
 @pytest.mark.parametrize("P", [1, 5, 40])

@@ -39,9 +39,8 @@ def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label="", forc
     times, tot = [], []
     info = None
     ko = None
-    if force is not None:   # test hook of hdk_b200_launch: force an accumulation strategy
-        ko = abi.KernelOptions()
-        ko.sharedMemBytes = 0xB200F001 + force
+    if force is not None:   # hdk_b200_debug_set: force an accumulation strategy
+        _lib.debug_set("force_strategy", force)
         label += f" [forced strategy {force}]"
     for i in range(reps + 2):
         torch.cuda.synchronize()
@@ -56,6 +55,8 @@ def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label="", forc
         if i >= 2:
             times.append(e1.elapsed_time(e2))
             tot.append(e0.elapsed_time(e2))
+    if force is not None:
+        _lib.debug_set("force_strategy", -1)
     err = int(prep["err"].item())
     ms = sum(times) / len(times)
     gbs = bytes_per_row * rows / (ms * 1e-3) / 1e9
