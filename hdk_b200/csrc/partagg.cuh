@@ -12,20 +12,51 @@ struct PaField {
   int16_t expr;     // plan node whose value the field holds
   uint8_t words;    // 1: the value fits 32 bits (sign-extended on read); 2: 64 bits (int64, or the bits of a double)
   uint8_t off;      // first word inside the record
-  int8_t col;       // plain outer column feeding the field, or -1 (needs the interpreter)
-  uint8_t colw;     // physical width of that column
-  uint8_t is_fp;
-  uint8_t pad;
 };
 
 struct PaLayout {
-  int32_t n_keys, n_fields, rec_words, key_words, key_width;
-  int32_t direct;                 // no filters, every field is a plain outer column, few fields: no interpreter
+  int32_t ok;                     // the plan can run partitioned (baseline hash, no joins, record fits)
+  int32_t n_keys, n_fields, rec_words, key_words;
   PaField f[kPaMaxFields];        // keys first (the first key_words words of a record are its key)
   int8_t acc_field[kMaxAcc];      // field holding accumulator a's argument, -1 for COUNT(*)
 };
 
-int partagg_layout(const Lowered& lw, PaLayout* out);
+// Record layout of a plan: a function of the plan's STRUCTURE only, so that pre-compiled shapes know it at compile time.
+__host__ __device__ constexpr PaLayout pa_layout_of(const DPlan& p) {
+  PaLayout L{};
+  if (p.hash_type != HDK_B200_BASELINE_HASH || p.n_joins != 0 || p.n_keys < 1) return L;
+  L.n_keys = p.n_keys;
+  int off = 0, nf = 0;
+  for (int k = 0; k < p.n_keys; ++k) {
+    const DExpr& e = p.exprs[p.keys[k].expr];
+    L.f[nf].expr = int16_t(p.keys[k].expr);
+    L.f[nf].words = uint8_t(e.width == 8 ? 2 : 1);
+    L.f[nf].off = uint8_t(off);
+    off += L.f[nf].words;
+    ++nf;
+  }
+  L.key_words = off;
+  for (int a = 0; a < p.n_acc; ++a) {
+    L.acc_field[a] = -1;
+    if (p.accs[a].arg < 0) continue;
+    for (int i = p.n_keys; i < nf; ++i)
+      if (L.f[i].expr == p.accs[a].arg) L.acc_field[a] = int8_t(i);
+    if (L.acc_field[a] >= 0) continue;
+    if (nf >= kPaMaxFields) return L;
+    const DExpr& e = p.exprs[p.accs[a].arg];
+    L.f[nf].expr = int16_t(p.accs[a].arg);
+    L.f[nf].words = uint8_t((e.kind == HDK_B200_FP || e.width == 8) ? 2 : 1);
+    L.f[nf].off = uint8_t(off);
+    off += L.f[nf].words;
+    L.acc_field[a] = int8_t(nf++);
+  }
+  if (off > 64) return L;
+  L.n_fields = nf;
+  L.rec_words = off;
+  L.ok = 1;
+  return L;
+}
+
 int partagg_scratch_bytes(const Lowered& lw, uint64_t total_rows, size_t* bytes);
 int launch_partagg(const Lowered& lw, const hdk_b200_kernel_params* params, void* scratch, size_t scratch_bytes, cudaStream_t st,
                    hdk_b200_launch_info* info);

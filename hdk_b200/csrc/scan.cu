@@ -30,6 +30,7 @@
 #include "eval.cuh"
 #include "partagg.cuh"
 #include "scan.cuh"
+#include "shape.cuh"
 
 namespace hb {
 
@@ -41,28 +42,6 @@ struct StageHeader {          // written by the producer, read by consumers
   uint32_t aligned;           // every column slice of the tile starts on a 16-byte boundary (vector loads allowed)
   uint32_t col_off[HDK_B200_MAX_COLS];  // byte offset (from dynamic smem base) of element 0 of column c
 };
-
-// ---- plan shapes -----------------------------------------------------------------------------
-// The generic kernel interprets the device plan at run time.  For the plan shapes listed in
-// static_shapes.inc (generated at build time from the named configs by tools/gen_static_shapes.py)
-// the SAME row code is instantiated with the plan's structure as a compile-time constant, so the
-// expression switch, type checks and accumulator dispatch fold away and `vals[]` lives in registers.
-// Literal values, key ranges and entry counts stay run-time parameters in both cases.
-struct GenericShape {
-  static constexpr bool is_static = false;
-  static constexpr int rows_per_iter = 1;
-  __host__ __device__ static constexpr DPlan get() { return DPlan{}; }
-};
-template <int ID>
-struct StaticShape;
-
-template <int I, int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (I < N) {
-    f(std::integral_constant<int, I>{});
-    static_for<I + 1, N>(f);
-  }
-}
 
 __device__ __forceinline__ uint64_t lds_elem(const uint8_t* ptr, int w) {
   return w == 8 ? *reinterpret_cast<const uint64_t*>(ptr) : w == 4 ? uint64_t(*reinterpret_cast<const uint32_t*>(ptr))
@@ -806,17 +785,6 @@ scan_kernel(const __grid_constant__ ScanArgs args) {
     }
   }
 }
-
-// ---- pre-compiled plan shapes ------------------------------------------------------------------
-#define HB_STATIC_SHAPE(ID, SIG, NAME, RPI, ...)                                 \
-  template <>                                                                    \
-  struct StaticShape<ID> {                                                       \
-    static constexpr bool is_static = true;                                      \
-    static constexpr int rows_per_iter = RPI;                                    \
-    __host__ __device__ static constexpr DPlan get() { return DPlan __VA_ARGS__; } \
-  };
-#include "static_shapes.inc"
-#undef HB_STATIC_SHAPE
 
 typedef void (*ScanKernelFn)(const ScanArgs);
 struct StaticEntry {
