@@ -48,7 +48,6 @@ constexpr int kPaThreads = 512;
 constexpr int kPaMaxTileRows = 4096;         // rows regrouped per tile (ranks fit 16 bits, destinations 8)
 constexpr int kPaCountRows = 8;              // rows per thread per tile of the count pass
 constexpr int kAggThreads = 1024;
-constexpr int kAggChunkRows = 2048;          // records staged per cp.async chunk
 constexpr uint32_t kEmptyId = 0xffffffffu;
 
 struct PaArgs {
@@ -72,28 +71,40 @@ struct PaArgs {
   int32_t* error_codes;
 };
 
-// MurmurHash64A over the 64-bit widened key values (the reference's partition hash, QE/RowFuncBuilder.cpp:516-577),
-// computed incrementally so that the keys need not sit in an array
+// Hash of the (cast) key values: 32 x 32 → 64-bit multiply mixing (the scheme of wyhash32: xor the key's halves into two
+// 32-bit lanes, multiply the lanes, take the product's halves as the new lanes — three instructions per step).  The
+// reference's partitioned aggregation hashes with MurmurHash64A (QE/RowFuncBuilder.cpp:516-577; shuffle.cu keeps it for
+// the multi-GPU exchange); inside one GPU any deterministic function of the key serves, and this one costs a third of
+// the instructions — it is evaluated four times per row (count, two scatter levels, aggregation).
+// Bits: upper half → partition (range reduction of its top bits) and fingerprint / split bits (its low bits);
+// lower half → bucket of the shared table (top bits) and further split bits (low bits).
 struct KeyHasher {
-  uint64_t h;
-  __device__ __forceinline__ explicit KeyHasher(int n_keys) : h(uint64_t(n_keys) * 8 * 0xc6a4a7935bd1e995ULL) {}
-  __device__ __forceinline__ void add(int64_t key) {
-    const uint64_t m = 0xc6a4a7935bd1e995ULL;
-    uint64_t k = uint64_t(key) * m;
-    k ^= k >> 47;
-    k *= m;
-    h ^= k;
-    h *= m;
+  uint32_t a, b;
+  __device__ __forceinline__ void mix() {
+    const uint64_t c = uint64_t(a ^ 0x53c5ca59u) * uint64_t(b ^ 0x74743c1bu);
+    a = uint32_t(c);
+    b = uint32_t(c >> 32);
   }
-  __device__ __forceinline__ uint64_t finish() const {
-    const uint64_t m = 0xc6a4a7935bd1e995ULL;
-    uint64_t x = h;
-    x ^= x >> 47;
-    x *= m;
-    x ^= x >> 47;
-    return x;
+  __device__ __forceinline__ explicit KeyHasher(int n_keys) : a(0x9E3779B9u + uint32_t(n_keys)), b(0x85EBCA6Bu) { mix(); }
+  __device__ __forceinline__ void add(int64_t key) {
+    a ^= uint32_t(uint64_t(key));
+    b ^= uint32_t(uint64_t(key) >> 32);
+    mix();
+  }
+  // each half of the result is lane ^ lane: the upper half of a product alone is far from uniform (measured: partition
+  // sizes with a standard deviation 20 x Poisson's when it fed the range reduction directly)
+  __device__ __forceinline__ uint64_t finish() {
+    mix();
+    mix();
+    const uint32_t hi = a ^ b;
+    mix();
+    return (uint64_t(hi) << 32) | (a ^ b);
   }
 };
+__device__ __forceinline__ uint32_t pa_fingerprint(uint64_t h) { return (uint32_t(h >> 32) & 0xffu) << 24; }
+// bits that decide the sub-pass of a split partition: independent of the partition (top of the upper half) and of the
+// bucket (top of the lower half)
+__device__ __forceinline__ uint32_t pa_split_bits(uint64_t h) { return ((uint32_t(h >> 40) & 0xffu) | ((uint32_t(h) & 0x3ffu) << 8)); }
 __device__ __forceinline__ uint32_t pa_partition(uint64_t h, uint32_t P) { return __umulhi(uint32_t(h >> 32), P); }
 __device__ __forceinline__ int64_t pa_key_cast(int64_t v, int key_width) { return key_width == 4 ? int64_t(int32_t(v)) : v; }
 
@@ -255,12 +266,25 @@ __global__ void __launch_bounds__(kPaThreads, 2) pa_count_kernel(const __grid_co
       constexpr DPlan sp = Shape::get();
       static_for<0, sp.n_cols>([&](auto Cc) { cptr[decltype(Cc)::value] = cols[decltype(Cc)::value]; });
     }
+    if constexpr (Shape::is_static) {
+      // all rows of the thread are evaluated before any is hashed: their loads are in flight together
+      PaVals<Shape> v[kPaCountRows];
+      bool ok[kPaCountRows];
 #pragma unroll
-    for (int r = 0; r < kPaCountRows; ++r) {
-      const uint64_t pos = row0 + uint64_t(r) * kPaThreads + tid;
-      if (pos >= rows) continue;
-      if (!pa_eval_row<Shape, false>(a.plan, Shape::is_static ? cptr : cols, pos, vals.v, err)) continue;
-      atomicAdd(&hist[pa_partition(pa_hash_vals<Shape>(a.lay, a.key_width, vals.v), a.P)], 1u);
+      for (int r = 0; r < kPaCountRows; ++r) {
+        const uint64_t pos = row0 + uint64_t(r) * kPaThreads + tid;
+        ok[r] = pos < rows && pa_eval_row<Shape, false>(a.plan, cptr, pos < rows ? pos : row0, v[r].v, err);
+      }
+#pragma unroll
+      for (int r = 0; r < kPaCountRows; ++r)
+        if (ok[r]) atomicAdd(&hist[pa_partition(pa_hash_vals<Shape>(a.lay, a.key_width, v[r].v), a.P)], 1u);
+    } else {
+      for (int r = 0; r < kPaCountRows; ++r) {
+        const uint64_t pos = row0 + uint64_t(r) * kPaThreads + tid;
+        if (pos >= rows) continue;
+        if (!pa_eval_row<Shape, false>(a.plan, cols, pos, vals.v, err)) continue;
+        atomicAdd(&hist[pa_partition(pa_hash_vals<Shape>(a.lay, a.key_width, vals.v), a.P)], 1u);
+      }
     }
   }
   __syncthreads();
@@ -297,8 +321,11 @@ __global__ void __launch_bounds__(1024) pa_offsets_kernel(const uint32_t* counts
 }
 
 // ---- pass 3: scatter (level 1 from the columns, level 2 from level 1's records) ---------------------------------------
-// Shared memory of a tile of R rows: the regrouped records (R x rec_words words), per row its destination and its rank
-// inside the destination's run, per regrouped position its destination; per destination the run start, the reservation.
+// A tile of R rows is regrouped by destination in shared memory, then written out run by run.  Every run is placed in
+// the staging area at a word offset CONGRUENT (mod 4) to the global word offset it was reserved at, each in its own
+// 16-byte-aligned slot: the copy-out then moves whole 16-byte vectors (LDS.128 → STG.128), word by word only at the
+// two ends of a run.  Shared memory: the staging area, per vector its destination, per row its destination and its rank
+// inside the destination's run, per destination the run's staging start / length and its global offset.
 template <class Shape, int kLevel>
 __global__ void __launch_bounds__(kPaThreads, 2) pa_scatter_kernel(const __grid_constant__ PaArgs a) {
   extern __shared__ __align__(16) uint8_t dsm[];
@@ -307,14 +334,17 @@ __global__ void __launch_bounds__(kPaThreads, 2) pa_scatter_kernel(const __grid_
   const uint32_t n_src = kLevel == 1 ? a.num_fragments : a.F1;
   int RW;
   if constexpr (Shape::is_static) RW = pa_layout_of(Shape::get()).rec_words; else RW = L.rec_words;
-  uint32_t* stage = reinterpret_cast<uint32_t*>(dsm);                                    // [R * RW]
-  long long* delta = reinterpret_cast<long long*>(stage + ((size_t(R) * RW + 3) & ~size_t(3)));   // [n_dest] words: global - local
+  const uint32_t stage_words = (R * uint32_t(RW) + 8u * a.n_dest + 3u) & ~3u;
+  uint32_t* stage = reinterpret_cast<uint32_t*>(dsm);                                    // [stage_words]
+  long long* delta = reinterpret_cast<long long*>(stage + stage_words);                  // [n_dest] global word - staging word
   uint32_t* hist = reinterpret_cast<uint32_t*>(delta + a.n_dest);                        // [n_dest]
-  uint32_t* run_start = hist + a.n_dest;                                                 // [n_dest + 1]
-  uint32_t* tile_prefix = run_start + a.n_dest + 1;                                      // [n_src + 1]
+  uint32_t* run_ws = hist + a.n_dest;                                                    // [n_dest] first staging word of the run
+  uint32_t* run_len = run_ws + a.n_dest;                                                 // [n_dest] records in the run
+  uint32_t* slot_ps = run_len + a.n_dest;                                                // [n_dest + 1] staging slots (multiples of 4 words)
+  uint32_t* tile_prefix = slot_ps + a.n_dest + 1;                                        // [n_src + 1]
   uint16_t* rank_of_row = reinterpret_cast<uint16_t*>(tile_prefix + n_src + 1);          // [R]  0xffff = dropped
   uint8_t* dest_of_row = reinterpret_cast<uint8_t*>(rank_of_row + R);                    // [R]
-  uint8_t* dest_of_pos = dest_of_row + R;                                                // [R]
+  uint8_t* dest_of_vec = dest_of_row + ((R + 3u) & ~3u);                                 // [stage_words / 4]  0xff = padding
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) {
     uint32_t acc = 0;
@@ -348,88 +378,172 @@ __global__ void __launch_bounds__(kPaThreads, 2) pa_scatter_kernel(const __grid_
     } else {
       recs = a.src_recs + (a.base[size_t(src) << a.F2_log2] + row0) * uint64_t(RW);
     }
-    // ---- A: destination of every row and its rank inside the destination's run
-    for (uint32_t i = tid; i < n_tile; i += kPaThreads) {
-      uint64_t h;
-      bool ok = true;
-      if constexpr (kLevel == 1) {
-        int32_t e = 0;
-        ok = pa_eval_row<Shape, false>(a.plan, Shape::is_static ? cptr : cols, row0 + i, vals.v, e);
-        h = ok ? pa_hash_vals<Shape>(L, a.key_width, vals.v) : 0;
+    // ---- A: destination of every row and its rank inside the destination's run (kBatch rows per thread at a time: their
+    //         loads are in flight together)
+    constexpr int kBatch = 4;
+    for (uint32_t i0 = 0; i0 < n_tile; i0 += kPaThreads * kBatch) {
+      uint64_t h[kBatch];
+      bool ok[kBatch];
+      if constexpr (kLevel == 1 && Shape::is_static) {
+        PaVals<Shape> v[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const uint32_t i = i0 + uint32_t(b) * kPaThreads + tid;
+          int32_t e = 0;
+          ok[b] = i < n_tile && pa_eval_row<Shape, false>(a.plan, cptr, row0 + (i < n_tile ? i : 0), v[b].v, e);
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) h[b] = pa_hash_vals<Shape>(L, a.key_width, v[b].v);
+      } else if constexpr (kLevel == 1) {
+        for (int b = 0; b < kBatch; ++b) {
+          const uint32_t i = i0 + uint32_t(b) * kPaThreads + tid;
+          int32_t e = 0;
+          ok[b] = i < n_tile && pa_eval_row<Shape, false>(a.plan, cols, row0 + i, vals.v, e);
+          h[b] = ok[b] ? pa_hash_vals<Shape>(L, a.key_width, vals.v) : 0;
+        }
       } else {
-        h = pa_hash_record<Shape>(L, recs + size_t(i) * RW);
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const uint32_t i = i0 + uint32_t(b) * kPaThreads + tid;
+          ok[b] = i < n_tile;
+          h[b] = pa_hash_record<Shape>(L, recs + size_t(ok[b] ? i : 0) * RW);
+        }
       }
-      uint32_t d = 0;
-      uint32_t rank = 0xffffu;
-      if (ok) {
-        const uint32_t p = pa_partition(h, a.P);
-        d = kLevel == 1 ? (p >> a.F2_log2) : (p & F2_mask);
-        rank = atomicAdd(&hist[d], 1u);
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const uint32_t i = i0 + uint32_t(b) * kPaThreads + tid;
+        if (i >= n_tile) continue;
+        uint32_t d = 0, rank = 0xffffu;
+        if (ok[b]) {
+          const uint32_t p = pa_partition(h[b], a.P);
+          d = kLevel == 1 ? (p >> a.F2_log2) : (p & F2_mask);
+          rank = atomicAdd(&hist[d], 1u);
+        }
+        dest_of_row[i] = uint8_t(d);
+        rank_of_row[i] = uint16_t(rank);
       }
-      dest_of_row[i] = uint8_t(d);
-      rank_of_row[i] = uint16_t(rank);
     }
     __syncthreads();
-    // ---- run starts (exclusive scan of the histogram: one warp, contiguous chunks) and one reservation per destination
-    if (tid < 32) {
+    // ---- one reservation per destination; the run's staging slot holds it at the same offset (mod 4 words) as in global memory
+    for (uint32_t d = tid; d < a.n_dest; d += kPaThreads) {
+      const uint32_t n = hist[d];
+      unsigned long long gword = 0;
+      if (n) {
+        // level 1 writes into the region of its destination's first final partition; level 2 into the final partition
+        const uint32_t cidx = kLevel == 1 ? d : ((src << a.F2_log2) | d);
+        const uint32_t pidx = kLevel == 1 ? (d << a.F2_log2) : cidx;
+        gword = (a.base[pidx] + atomicAdd(a.cursor + cidx, n)) * uint64_t(RW);
+      }
+      run_len[d] = n;
+      run_ws[d] = uint32_t(gword & 3u);                       // offset inside the slot, completed below
+      delta[d] = static_cast<long long>(gword);
+      hist[d] = 0;
+    }
+    for (uint32_t q = tid; q < stage_words / 16; q += kPaThreads) reinterpret_cast<uint32_t*>(dest_of_vec)[q] = 0xffffffffu;
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of the slot sizes: one warp, contiguous chunks
       const uint32_t chunk = (a.n_dest + 31) / 32, lo = min(uint32_t(lane) * chunk, a.n_dest), hi = min(lo + chunk, a.n_dest);
       uint32_t sum = 0;
-      for (uint32_t i = lo; i < hi; ++i) sum += hist[i];
+      for (uint32_t i = lo; i < hi; ++i) sum += run_len[i] ? ((run_len[i] * uint32_t(RW) + run_ws[i] + 3u) & ~3u) : 0u;
       uint32_t incl = sum;
       for (int dd = 1; dd < 32; dd <<= 1) {
         const uint32_t o = __shfl_up_sync(0xffffffffu, incl, dd);
         if (lane >= dd) incl += o;
       }
       uint32_t run = incl - sum;
-      for (uint32_t i = lo; i < hi; ++i) { run_start[i] = run; run += hist[i]; }
-      if (lane == 31) run_start[a.n_dest] = incl;
+      for (uint32_t i = lo; i < hi; ++i) {
+        slot_ps[i] = run;
+        run += run_len[i] ? ((run_len[i] * uint32_t(RW) + run_ws[i] + 3u) & ~3u) : 0u;
+      }
+      if (lane == 31) slot_ps[a.n_dest] = incl;
     }
     __syncthreads();
     for (uint32_t d = tid; d < a.n_dest; d += kPaThreads) {
-      const uint32_t n = hist[d];
-      if (n) {
-        // level 1 writes into the region of its destination's first final partition; level 2 into the final partition
-        const uint32_t cidx = kLevel == 1 ? d : ((src << a.F2_log2) | d);
-        const uint32_t pidx = kLevel == 1 ? (d << a.F2_log2) : cidx;
-        const unsigned long long g = a.base[pidx] + atomicAdd(a.cursor + cidx, n);
-        delta[d] = (static_cast<long long>(g) - static_cast<long long>(run_start[d])) * RW;
-      }
-      hist[d] = 0;
-    }
-    // ---- B: records into their regrouped position
-    for (uint32_t i = tid; i < n_tile; i += kPaThreads) {
-      const uint32_t rank = rank_of_row[i];
-      if (rank == 0xffffu) continue;
-      const uint32_t d = dest_of_row[i];
-      const uint32_t pos = run_start[d] + rank;
-      uint32_t* dst = stage + size_t(pos) * RW;
-      if constexpr (kLevel == 1) {
-        if (pa_eval_row<Shape, true>(a.plan, Shape::is_static ? cptr : cols, row0 + i, vals.v, my_err)) {
-          pa_write_record<Shape>(L, a.key_width, vals.v, dst);
-        } else {
-          // an error in a key / aggregate argument of a row that passes: reported (my_err), the query fails; keep the
-          // slot's words defined
-          for (int w = 0; w < RW; ++w) dst[w] = 0;
-        }
-      } else {
-        const uint32_t* rec = recs + size_t(i) * RW;
-        if constexpr (Shape::is_static) {
-          constexpr int SRW = pa_layout_of(Shape::get()).rec_words;
-#pragma unroll
-          for (int w = 0; w < SRW; ++w) dst[w] = rec[w];
-        } else {
-          for (int w = 0; w < RW; ++w) dst[w] = rec[w];
-        }
-      }
-      dest_of_pos[pos] = uint8_t(d);
+      const uint32_t ws = slot_ps[d] + run_ws[d];
+      run_ws[d] = ws;
+      delta[d] -= static_cast<long long>(ws);
     }
     __syncthreads();
-    // ---- copy the runs out: consecutive threads, consecutive words
-    const uint32_t n_words = run_start[a.n_dest] * uint32_t(RW);
-    for (uint32_t w = tid; w < n_words; w += kPaThreads) {
-      uint32_t i;
-      if constexpr (Shape::is_static) i = w / uint32_t(pa_layout_of(Shape::get()).rec_words); else i = w / uint32_t(RW);
-      a.dst_recs[delta[dest_of_pos[i]] + static_cast<long long>(w)] = stage[w];
+    // ---- B: records into their regrouped position
+    for (uint32_t i0 = 0; i0 < n_tile; i0 += kPaThreads * kBatch) {
+      uint32_t* dst[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const uint32_t i = i0 + uint32_t(b) * kPaThreads + tid;
+        dst[b] = nullptr;
+        if (i < n_tile) {
+          const uint32_t rank = rank_of_row[i];
+          if (rank != 0xffffu) {
+            const uint32_t d = dest_of_row[i];
+            const uint32_t w = run_ws[d] + rank * uint32_t(RW);
+            dst[b] = stage + w;
+            for (uint32_t q = w >> 2; q <= (w + uint32_t(RW) - 1u) >> 2; ++q) dest_of_vec[q] = uint8_t(d);
+          }
+        }
+      }
+      if constexpr (kLevel == 1 && Shape::is_static) {
+        PaVals<Shape> v[kBatch];
+        bool ok[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const uint32_t i = i0 + uint32_t(b) * kPaThreads + tid;
+          ok[b] = dst[b] != nullptr && pa_eval_row<Shape, true>(a.plan, cptr, row0 + (dst[b] ? i : 0), v[b].v, my_err);
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          if (!dst[b]) continue;
+          if (ok[b]) pa_write_record<Shape>(L, a.key_width, v[b].v, dst[b]);
+          else for (int w = 0; w < RW; ++w) dst[b][w] = 0;
+        }
+      } else if constexpr (kLevel == 1) {
+        for (int b = 0; b < kBatch; ++b) {
+          if (!dst[b]) continue;
+          const uint32_t i = i0 + uint32_t(b) * kPaThreads + tid;
+          // (an error in a key / aggregate argument of a row that passes is reported through my_err and fails the query;
+          //  its slot's words stay defined)
+          if (pa_eval_row<Shape, true>(a.plan, cols, row0 + i, vals.v, my_err)) pa_write_record<Shape>(L, a.key_width, vals.v, dst[b]);
+          else for (int w = 0; w < RW; ++w) dst[b][w] = 0;
+        }
+      } else if constexpr (Shape::is_static) {
+        constexpr int SRW = pa_layout_of(Shape::get()).rec_words;
+        uint32_t wv[kBatch][SRW];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const uint32_t* rec = recs + size_t(dst[b] ? i0 + uint32_t(b) * kPaThreads + tid : 0) * SRW;
+#pragma unroll
+          for (int w = 0; w < SRW; ++w) wv[b][w] = rec[w];
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          if (!dst[b]) continue;
+#pragma unroll
+          for (int w = 0; w < SRW; ++w) dst[b][w] = wv[b][w];
+        }
+      } else {
+        for (int b = 0; b < kBatch; ++b) {
+          if (!dst[b]) continue;
+          const uint32_t* rec = recs + size_t(i0 + uint32_t(b) * kPaThreads + tid) * RW;
+          for (int w = 0; w < RW; ++w) dst[b][w] = rec[w];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- copy out: one 16-byte vector per thread and step, consecutive threads consecutive vectors
+    const uint32_t n_vec = slot_ps[a.n_dest] >> 2;
+    for (uint32_t q = tid; q < n_vec; q += kPaThreads) {
+      const uint32_t d = dest_of_vec[q];
+      if (d == 0xffu) continue;
+      const uint4 v = reinterpret_cast<const uint4*>(stage)[q];
+      const uint32_t w = q << 2, ws = run_ws[d], we = ws + run_len[d] * uint32_t(RW);
+      uint32_t* out = a.dst_recs + (delta[d] + static_cast<long long>(w));
+      if (w >= ws && w + 4 <= we) {
+        *reinterpret_cast<uint4*>(out) = v;
+      } else {
+        if (w >= ws && w < we) out[0] = v.x;
+        if (w + 1 >= ws && w + 1 < we) out[1] = v.y;
+        if (w + 2 >= ws && w + 2 < we) out[2] = v.z;
+        if (w + 3 >= ws && w + 3 < we) out[3] = v.w;
+      }
     }
     __syncthreads();
   }
@@ -437,11 +551,15 @@ __global__ void __launch_bounds__(kPaThreads, 2) pa_scatter_kernel(const __grid_
 }
 
 // ---- pass 4: per-partition aggregation in shared memory ---------------------------------------------------------------
+constexpr int kAggWarps = kAggThreads / 32;
+constexpr int kAggIlp = 2;                       // records per lane in flight
+constexpr int kAggWarpChunk = 32 * kAggIlp;      // records per warp and cp.async chunk
+
 struct PaAggArgs {
   DPlan plan;
   DLayout layout;
   PaLayout lay;
-  uint32_t P, T;                    // partitions, shared-table slots
+  uint32_t P, NB;                   // partitions, buckets (of 4 slots) of the shared table
   const uint32_t* counts;           // records actually written per partition
   const unsigned long long* base;
   const uint32_t* recs;
@@ -449,8 +567,8 @@ struct PaAggArgs {
   unsigned long long* out_cursor;   // entries of the group-by buffer handed out so far
   int64_t* const* groupby_buf;
   int32_t* error_codes;
-  uint32_t off_chunks;              // byte offset of the two record chunks inside dynamic shared memory
-  uint32_t chunk_words;             // words per chunk buffer (incl. alignment slack)
+  uint32_t off_chunks;              // byte offset of the warps' record chunks inside dynamic shared memory
+  uint32_t chunk_words;             // words per chunk buffer (incl. alignment slack); every warp owns two
   uint32_t acc_off[kMaxAcc];        // byte offset of accumulator a's cells (ids at 0)
 };
 
@@ -480,6 +598,12 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds_volatile_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))) : "memory");
+  return v;
+}
 
 // one accumulator update of one record (kind / argument type are compile-time constants for pre-compiled shapes)
 __device__ __forceinline__ void pa_accumulate(const DPlan& p, const PaLayout& F, int k, const DAcc acc, const uint32_t* rec, uint8_t* cell) {
@@ -500,6 +624,13 @@ __device__ __forceinline__ void pa_accumulate(const DPlan& p, const PaLayout& F,
   }
 }
 
+// The shared table: NB buckets of four 32-bit ids (one 16-byte vector), accumulator cells beside them indexed by slot
+// (= 4 x bucket + position).  An id is the index of the group's representative record inside the partition, with an
+// 8-bit fingerprint of the key hash in its top byte when the partition has < 2^24 records.  A record reads its bucket
+// with one LDS.128, compares the four fingerprints at once, verifies a match against the representative's key words in
+// global memory (L2), claims the first empty slot with one 32-bit CAS when nothing matches, and moves to the next
+// bucket only when the bucket is full: at load 0.6 about one bucket probe per record, the warp's slowest record two or
+// three — against seven slot probes with linear probing over single slots.
 template <class Shape>
 __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __grid_constant__ PaAggArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
@@ -510,8 +641,8 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
   const DPlan& p = a.plan;
   const PaLayout& F = a.lay;
   const DLayout& L = a.layout;
-  const uint32_t T = a.T;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t NB = a.NB, T = NB * 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int RW, KW;
   if constexpr (Shape::is_static) { RW = pa_layout_of(Shape::get()).rec_words; KW = pa_layout_of(Shape::get()).key_words; }
   else { RW = F.rec_words; KW = F.key_words; }
@@ -525,7 +656,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
   for (uint32_t s = tid; s < T; s += kAggThreads) reset_slot(s);
   int8_t* const buf = reinterpret_cast<int8_t*>(a.groupby_buf[0]);
   const uint64_t E = L.entry_count;
-  uint32_t* chunk_buf[2] = {reinterpret_cast<uint32_t*>(sm + a.off_chunks), reinterpret_cast<uint32_t*>(sm + a.off_chunks) + a.chunk_words};
+  uint32_t* const my_chunks = reinterpret_cast<uint32_t*>(sm + a.off_chunks) + size_t(warp) * 2 * a.chunk_words;
   for (;;) {
     __syncthreads();
     if (tid == 0) s_part = atomicAdd(a.work_counter, 1u);
@@ -536,18 +667,21 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
     if (n == 0) continue;
     const uint64_t first_word = a.base[part] * uint64_t(RW);
     const uint32_t* rows = a.recs + first_word;
-    const int row_bits = n < (1u << 24) - 1 ? 24 : 32;      // spare bits of the id word hold a fingerprint of the key hash
-    const uint32_t row_mask = row_bits == 32 ? 0xffffffffu : (1u << row_bits) - 1u;
-    const uint32_t n_chunks = (n + kAggChunkRows - 1) / kAggChunkRows;
-    // chunk c = records [c * kAggChunkRows, ...): copied from the 16-byte aligned address at or below its first word
+    const bool has_fp = n < (1u << 24) - 1;                 // spare bits of the id word hold a fingerprint of the key hash
+    const uint32_t row_mask = has_fp ? 0x00ffffffu : 0xffffffffu;
+    // this warp's slice of the partition, streamed in chunks of kAggWarpChunk records
+    const uint32_t w_lo = uint32_t(uint64_t(n) * warp / kAggWarps), w_hi = uint32_t(uint64_t(n) * (warp + 1) / kAggWarps);
+    const uint32_t n_chunks = (w_hi - w_lo + kAggWarpChunk - 1) / kAggWarpChunk;
+    // a chunk is copied from the 16-byte aligned address at or below its first word
     auto issue_chunk = [&](uint32_t c) {
-      const uint64_t w0 = first_word + uint64_t(c) * kAggChunkRows * RW;
-      const uint32_t nrec = min(uint32_t(kAggChunkRows), n - c * kAggChunkRows);
+      const uint32_t r0 = w_lo + c * kAggWarpChunk;
+      const uint64_t w0 = first_word + uint64_t(r0) * RW;
+      const uint32_t nrec = min(uint32_t(kAggWarpChunk), w_hi - r0);
       const uint64_t wa = w0 & ~uint64_t(3);
       const uint32_t pieces = uint32_t((w0 - wa) + uint64_t(nrec) * RW + 3) / 4;
       const uint32_t* src = a.recs + wa;
-      uint32_t* dst = chunk_buf[c & 1];
-      for (uint32_t i = tid; i < pieces; i += kAggThreads) cp_async16(dst + 4 * i, src + 4 * i);
+      uint32_t* dst = my_chunks + (c & 1) * a.chunk_words;
+      for (uint32_t i = lane; i < pieces; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
     };
     if (tid == 0) { s_stack[0][0] = 1; s_stack[0][1] = 0; s_top = 1; }
     for (;;) {
@@ -556,67 +690,124 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
       const uint32_t mod = s_stack[s_top - 1][0], rem = s_stack[s_top - 1][1];
       __syncthreads();
       if (tid == 0) { --s_top; s_overflow = 0; s_ngroups = 0; s_emitted = 0; }
-      issue_chunk(0);
-      cp_async_commit();
       __syncthreads();
-      // ---- insert + accumulate, chunk by chunk (the next chunk streams in meanwhile)
+      // ---- insert + accumulate: every warp on its own, no CTA barrier inside (the next chunk streams in meanwhile)
+      if (n_chunks) issue_chunk(0);
+      cp_async_commit();
       for (uint32_t c = 0; c < n_chunks; ++c) {
         if (c + 1 < n_chunks) issue_chunk(c + 1);
         cp_async_commit();
         cp_async_wait<1>();
-        __syncthreads();
-        const uint32_t c0 = c * kAggChunkRows;
-        const uint32_t nrec = min(uint32_t(kAggChunkRows), n - c0);
-        const uint32_t* cbase = chunk_buf[c & 1] + uint32_t((first_word + uint64_t(c0) * RW) & 3u);
-        if (!s_overflow)
-        for (uint32_t j = tid; j < nrec; j += kAggThreads) {
-          const uint32_t* rec = cbase + size_t(j) * RW;
-          const uint32_t i = c0 + j;
-          const uint64_t h = pa_hash_record<Shape>(F, rec);
-          if (mod > 1 && (uint32_t(h >> 13) & (mod - 1)) != rem) continue;
-          const uint32_t fp = row_bits == 32 ? 0u : (uint32_t(h >> 45) & 0xffu) << 24;
-          const uint32_t mine = fp | i;
-          uint32_t slot = __umulhi(uint32_t(h), T);
-          uint32_t probes = 0;
-          bool lost = false;
-          for (;;) {
-            uint32_t id = *reinterpret_cast<volatile uint32_t*>(ids + slot);
-            if (id == kEmptyId) {
-              id = atomicCAS(ids + slot, kEmptyId, mine);
-              if (id == kEmptyId) break;      // claimed: this record represents the group
-            }
-            if ((id & ~row_mask) == fp) {     // same fingerprint: compare with the representative's key words
-              const uint32_t* rep = rows + uint64_t(id & row_mask) * RW;
-              bool eq = true;
-              if constexpr (Shape::is_static) {
-                constexpr int SKW = pa_layout_of(Shape::get()).key_words;
-                uint32_t rk[SKW];
+        __syncwarp();
+        const uint32_t r0 = w_lo + c * kAggWarpChunk;
+        const uint32_t nrec = min(uint32_t(kAggWarpChunk), w_hi - r0);
+        const uint32_t* cbase = my_chunks + (c & 1) * a.chunk_words + uint32_t((first_word + uint64_t(r0) * RW) & 3u);
+        const bool overflow_now = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(&s_overflow), 0) != 0;
+        // Two records per lane, every lane runs the same number of steps: the probe loop is warp-synchronous — all lanes
+        // iterate until the warp's last record has found its slot — so the warp never splits into groups that execute
+        // the body at different times (measured with a per-lane loop: 10 of 32 lanes active on average).
+        const uint32_t* rec[kAggIlp];
+        uint32_t bucket[kAggIlp], slot[kAggIlp], mine[kAggIlp], fp[kAggIlp], probes[kAggIlp], excl[kAggIlp];
+        bool act[kAggIlp], pend[kAggIlp];
 #pragma unroll
-                for (int w = 0; w < SKW; ++w) rk[w] = __ldg(rep + w);
+        for (int u = 0; u < kAggIlp; ++u) {
+          const uint32_t j = uint32_t(u) * 32 + lane;
+          act[u] = j < nrec && !overflow_now;
+          rec[u] = cbase + size_t(act[u] ? j : 0) * RW;
+          const uint64_t h = pa_hash_record<Shape>(F, rec[u]);
+          if (mod > 1 && (pa_split_bits(h) & (mod - 1)) != rem) act[u] = false;
+          fp[u] = has_fp ? pa_fingerprint(h) : 0u;
+          mine[u] = fp[u] | (r0 + j);
+          bucket[u] = __umulhi(uint32_t(h), NB);
+          slot[u] = 0;
+          probes[u] = 0;
+          excl[u] = 0;
+          pend[u] = act[u];
+        }
+        bool any_pend = false;
 #pragma unroll
-                for (int w = 0; w < SKW; ++w) eq = eq && rk[w] == rec[w];
-              } else {
-                for (int w = 0; w < KW && eq; ++w) eq = __ldg(rep + w) == rec[w];
-              }
-              if (eq) break;
+        for (int u = 0; u < kAggIlp; ++u) any_pend = any_pend || pend[u];
+        while (__any_sync(0xffffffffu, any_pend)) {
+          uint32_t cand[kAggIlp];     // position (0-3) of the slot to verify, 4 = none
+          uint32_t empty[kAggIlp];    // position of the first empty slot, 4 = none
+          uint32_t cand_id[kAggIlp];
+#pragma unroll
+          for (int u = 0; u < kAggIlp; ++u) {
+            cand[u] = empty[u] = 4;
+            cand_id[u] = 0;
+            if (!pend[u]) continue;
+            const uint4 q = lds_volatile_v4(ids + size_t(bucket[u]) * 4);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int s = 3; s >= 0; --s) {
+              if (w[s] == kEmptyId) empty[u] = s;
+              else if ((w[s] & ~row_mask) == fp[u] && !((excl[u] >> s) & 1u)) { cand[u] = s; cand_id[u] = w[s]; }
             }
-            slot = slot + 1 == T ? 0 : slot + 1;
-            if (++probes >= T) { lost = true; break; }
           }
-          if (lost) { s_overflow = 1; break; }
+          // a slot with the record's fingerprint: compare with the representative's key words (both records' loads in flight)
+          if constexpr (Shape::is_static) {
+            constexpr int SKW = pa_layout_of(Shape::get()).key_words;
+            uint32_t rk[kAggIlp][SKW];
+#pragma unroll
+            for (int u = 0; u < kAggIlp; ++u) {
+              const uint32_t* rep = rows + uint64_t(cand[u] < 4 ? (cand_id[u] & row_mask) : 0u) * RW;
+#pragma unroll
+              for (int w = 0; w < SKW; ++w) rk[u][w] = cand[u] < 4 ? __ldg(rep + w) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kAggIlp; ++u) {
+              if (cand[u] == 4) continue;
+              bool eq = true;
+#pragma unroll
+              for (int w = 0; w < SKW; ++w) eq = eq && rk[u][w] == rec[u][w];
+              if (eq) { pend[u] = false; slot[u] = bucket[u] * 4 + cand[u]; }
+              else excl[u] |= 1u << cand[u];
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < kAggIlp; ++u) {
+              if (cand[u] == 4) continue;
+              const uint32_t* rep = rows + uint64_t(cand_id[u] & row_mask) * RW;
+              bool eq = true;
+              for (int w = 0; w < KW && eq; ++w) eq = __ldg(rep + w) == rec[u][w];
+              if (eq) { pend[u] = false; slot[u] = bucket[u] * 4 + cand[u]; }
+              else excl[u] |= 1u << cand[u];
+            }
+          }
+          any_pend = false;
+#pragma unroll
+          for (int u = 0; u < kAggIlp; ++u) {
+            if (pend[u] && cand[u] == 4) {
+              if (empty[u] < 4) {
+                // nothing in the bucket matches: claim its first empty slot; on a lost race look at the bucket again
+                // (the winner may hold this record's key)
+                const uint32_t s = bucket[u] * 4 + empty[u];
+                if (atomicCAS(ids + s, kEmptyId, mine[u]) == kEmptyId) { pend[u] = false; slot[u] = s; }
+              } else {
+                bucket[u] = bucket[u] + 1 == NB ? 0 : bucket[u] + 1;
+                excl[u] = 0;
+                if (++probes[u] >= NB) { pend[u] = false; act[u] = false; s_overflow = 1; }
+              }
+            }
+            any_pend = any_pend || pend[u];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kAggIlp; ++u) {
+          if (!act[u]) continue;
           if constexpr (Shape::is_static) {
             constexpr DPlan sp = Shape::get();
             static_for<0, sp.n_acc>([&](auto A) {
               constexpr int k = decltype(A)::value;
               constexpr DPlan sp = Shape::get();
               constexpr PaLayout SL = pa_layout_of(Shape::get());
-              pa_accumulate(sp, SL, k, sp.accs[k], rec, sm + a.acc_off[k] + size_t(slot) * sp.accs[k].bytes);
+              pa_accumulate(sp, SL, k, sp.accs[k], rec[u], sm + a.acc_off[k] + size_t(slot[u]) * sp.accs[k].bytes);
             });
           } else {
-            for (int k = 0; k < p.n_acc; ++k) pa_accumulate(p, F, k, p.accs[k], rec, sm + a.acc_off[k] + size_t(slot) * p.accs[k].bytes);
+            for (int k = 0; k < p.n_acc; ++k) pa_accumulate(p, F, k, p.accs[k], rec[u], sm + a.acc_off[k] + size_t(slot[u]) * p.accs[k].bytes);
           }
         }
-        __syncthreads();   // every thread is done with this chunk buffer before chunk c + 2 lands in it
+        __syncwarp();   // every lane is done with this chunk buffer before chunk c + 2 lands in it
       }
       cp_async_wait<0>();
       __syncthreads();
@@ -624,7 +815,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
         // the groups of this sub-pass do not fit: forget them and split the sub-pass by two more hash bits
         for (uint32_t s = tid; s < T; s += kAggThreads) reset_slot(s);
         if (tid == 0) {
-          if (mod >= (1u << 18) || s_top + 4 > 64) {
+          if (mod >= (1u << 16) || s_top + 4 > 64) {
             record_error(a.error_codes, -HDK_B200_ERR_OUT_OF_SLOTS);
           } else {
             for (uint32_t j = 0; j < 4; ++j) { s_stack[s_top][0] = mod * 4; s_stack[s_top][1] = rem + j * mod; ++s_top; }
@@ -713,9 +904,9 @@ static int partagg_geometry(const Lowered& lw, const PaLayout& L, uint64_t total
   int dev = 0, max_smem = 0;
   HB_CUDA(cudaGetDevice(&dev));
   HB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  // ---- aggregation: two record chunks + the table
-  g->chunk_words = uint32_t(pa_align(size_t(kAggChunkRows) * L.rec_words + 8, 4));
-  const size_t chunk_bytes = size_t(g->chunk_words) * 4 * 2;
+  // ---- aggregation: per warp two record chunks, then the table (buckets of four ids + the accumulator cells)
+  g->chunk_words = uint32_t(pa_align(size_t(kAggWarpChunk) * L.rec_words + 8, 4));
+  const size_t chunk_bytes = size_t(g->chunk_words) * 4 * 2 * kAggWarps;
   size_t per_slot = 4;
   for (int a = 0; a < p.n_acc; ++a) per_slot += p.accs[a].bytes;
   const size_t budget = size_t(max_smem) - 2048;
@@ -730,9 +921,10 @@ static int partagg_geometry(const Lowered& lw, const PaLayout& L, uint64_t total
   g->off_chunks = uint32_t(off);
   g->agg_smem = off + chunk_bytes;
   // ---- partitions.  The caller sizes the table at 2 x the estimated number of groups (QE/RelAlgExecutor.cpp:1553-1557):
-  // aim at half-full shared tables for that estimate; a partition that still overflows is split by further hash bits
+  // aim at 60 % full shared tables for that estimate; a partition that still overflows is split by further hash bits
   const uint64_t groups_est = std::max<uint64_t>(1, std::min<uint64_t>(uint64_t(p.entry_count) / 2 + 1, total_rows));
-  uint64_t P = (groups_est + T / 2 - 1) / (T / 2);
+  const uint64_t per_part = std::max<uint64_t>(1, uint64_t(T) * 6 / 10);   // buckets of four tolerate a load of 0.6
+  uint64_t P = (groups_est + per_part - 1) / per_part;
   // enough partitions to occupy the GPU even with few groups, as long as they keep a few thousand rows each
   P = std::max<uint64_t>(P, std::min<uint64_t>(uint64_t(sm_count()) * 8, total_rows / 4096));
   if (g_debug.pa_partitions > 0) P = uint64_t(g_debug.pa_partitions);
@@ -743,23 +935,20 @@ static int partagg_geometry(const Lowered& lw, const PaLayout& L, uint64_t total
   g->F1 = F1;
   g->F2_log2 = f2;
   g->P = F1 << f2;
-  // ---- scatter tiles: R rows x (record + rank + 2 destination bytes)
-  const size_t per_dest = 8 + 4 + 4;
-  for (int lvl = 0; lvl < 2; ++lvl) {
-    const size_t n_src = lvl == 0 ? num_fragments : F1;
-    const size_t n_dest = lvl == 0 ? F1 : (size_t(1) << f2);
-    const size_t fixed = n_dest * per_dest + 8 + (n_src + 1) * 4 + 64;
-    const size_t room = (size_t(max_smem) / 2 > fixed + 4096 ? size_t(max_smem) / 2 : size_t(max_smem)) - 1024 - fixed;   // two CTAs per SM when they fit
-    size_t R = room / (size_t(L.rec_words) * 4 + 4);
-    R = std::min<size_t>(R, kPaMaxTileRows) / kPaThreads * kPaThreads;
-    if (R < size_t(kPaThreads)) { set_error("partitioned aggregation: records too wide for a scatter tile"); return HDK_B200_E_UNSUPPORTED; }
-    if (lvl == 0) g->tile_rows = uint32_t(R); else g->tile_rows = std::min<uint32_t>(g->tile_rows, uint32_t(R));
+  // ---- scatter tiles: R rows x (record + rank + destination) + per destination (slot padding, descriptors) + per vector a byte
+  auto scatter_bytes = [&](size_t R, size_t n_src, size_t n_dest) {
+    const size_t stage_words = (R * L.rec_words + 8 * n_dest + 3) & ~size_t(3);
+    return stage_words * 4 + n_dest * (8 + 4 + 4 + 4 + 4) + 4 + (n_src + 1) * 4 + R * 2 + ((R + 3) & ~size_t(3)) + stage_words / 4 + 64;
+  };
+  g->tile_rows = 0;
+  for (size_t R = kPaMaxTileRows; R >= size_t(kPaThreads); R -= kPaThreads) {
+    const size_t need = std::max(scatter_bytes(R, num_fragments, F1), scatter_bytes(R, F1, size_t(1) << f2));
+    // two CTAs per SM when the tile stays at least half the maximum, else one
+    if (need + 1024 <= size_t(max_smem) / 2 || (R <= kPaMaxTileRows / 2 && need + 1024 <= size_t(max_smem))) { g->tile_rows = uint32_t(R); break; }
   }
-  for (int lvl = 0; lvl < 2; ++lvl) {
-    const size_t n_src = lvl == 0 ? num_fragments : F1;
-    const size_t n_dest = lvl == 0 ? F1 : (size_t(1) << f2);
-    g->scatter_smem[lvl] = pa_align(size_t(g->tile_rows) * L.rec_words * 4, 16) + n_dest * per_dest + 8 + (n_src + 1) * 4 + size_t(g->tile_rows) * 4 + 64;
-  }
+  if (!g->tile_rows) { set_error("partitioned aggregation: records too wide for a scatter tile"); return HDK_B200_E_UNSUPPORTED; }
+  g->scatter_smem[0] = scatter_bytes(g->tile_rows, num_fragments, F1);
+  g->scatter_smem[1] = scatter_bytes(g->tile_rows, F1, size_t(1) << f2);
   // header: counts u32[P] | cursor2 u32[P] | cursor1 u32[F1] | base u64[P + 1] | work counter, out cursor
   g->header_bytes = pa_align(size_t(g->P) * 8 + size_t(F1) * 4 + 8 + (size_t(g->P) + 1) * 8 + 64, 256);
   g->rec_bytes = pa_align(size_t(total_rows) * L.rec_words * 4 + 64, 256);
@@ -870,7 +1059,7 @@ int launch_partagg(const Lowered& lw, const hdk_b200_kernel_params* params, void
   ag.layout = lw.layout;
   ag.lay = L;
   ag.P = g.P;
-  ag.T = g.T;
+  ag.NB = g.T / 4;
   ag.counts = cursor2;
   ag.base = base;
   ag.recs = two_level ? recs_b : recs_a;
