@@ -76,8 +76,18 @@ int hdk_b200_launch(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, const hd
   int64_t* work = static_cast<int64_t*>(scratch);
   if (qmd->hash_type == HDK_B200_BASELINE_HASH) {
     size_t need = 0;
-    if (wants_partitioned(lw, params->total_rows_hint, &need) && scratch_bytes >= need)
-      return hb::launch_partagg(lw, params, scratch, scratch_bytes, st, info);
+    if (wants_partitioned(lw, params->total_rows_hint, &need) && scratch_bytes >= need) {
+      const int* fallback = nullptr;
+      int64_t* fwork = nullptr;
+      if (int rc = hb::launch_partagg(lw, params, scratch, scratch_bytes, st, info, &fallback, &fwork)) return rc;
+      // hot keys (a partition too heavy for one CTA): the partitioned kernels stood down, the global-table path below
+      // does the work; otherwise these three launches return at once
+      if (int rc = hb::init_work_table(lw, fwork, st, fallback)) return rc;
+      if (int rc = hb::launch_baseline_scan(lw, ko, params, fwork, st, nullptr, fallback)) return rc;
+      if (int rc = hb::launch_finalize(lw, fwork, nullptr, params->groupby_buf, st, fallback)) return rc;
+      if (info) info->n_launches += 3;
+      return HDK_B200_OK;
+    }
     // keys are claimed in the caller-initialised buffer, aggregates accumulate in the entry-major work table,
     // finalize encodes the slots of the claimed entries
     if (int rc = hb::init_work_table(lw, work, st)) return rc;

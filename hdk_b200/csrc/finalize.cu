@@ -174,6 +174,7 @@ struct FinalizeArgs {
   const unsigned long long* flags; // [n_peers] flags of this epoch's parity
   int32_t* error_codes;
   AccKinds kinds;
+  const int* run_if;               // when set: nothing happens unless *run_if != 0
   int8_t* buf;                     // direct pointer, or
   int64_t* const* buf_indirect;    // GROUPBY_BUF-style device array of pointers ([0] is used)
 };
@@ -209,6 +210,7 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
   const DLayout& L = a.layout;
   const uint64_t E = a.entry_count;
   const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+  if (a.run_if && *a.run_if == 0) return;
   int8_t* const buf = a.buf ? a.buf : reinterpret_cast<int8_t*>(a.buf_indirect[0]);
   if (kMerged) {
     // wait until every rank has published its table of this epoch (flags are written after a system-wide fence)
@@ -285,8 +287,9 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
 }
 
 int launch_finalize(const Lowered& lw, const int64_t* work_table, int64_t* groups_buffer, int64_t* const* groups_buffer_indirect,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const int* run_if) {
   FinalizeArgs a{};
+  a.run_if = run_if;
   a.buf_indirect = groups_buffer_indirect;
   a.layout = lw.layout;
   for (int k = 0; k < lw.plan.n_keys; ++k) a.keys[k] = lw.plan.keys[k];

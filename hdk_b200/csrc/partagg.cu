@@ -69,6 +69,7 @@ struct PaArgs {
   uint32_t* cursor;                // this pass's cursors: level 1 [F1] (or [P] when it is the only level), level 2 [P]
   uint32_t* dst_recs;
   int32_t* error_codes;
+  const int* skewed;               // set by the offsets kernel: a partition is too heavy for one CTA, the fallback path runs instead
 };
 
 // Hash of the (cast) key values: 32 x 32 → 64-bit multiply mixing (the scheme of wyhash32: xor the key's halves into two
@@ -101,7 +102,8 @@ struct KeyHasher {
     return (uint64_t(hi) << 32) | (a ^ b);
   }
 };
-__device__ __forceinline__ uint32_t pa_fingerprint(uint64_t h) { return (uint32_t(h >> 32) & 0xffu) << 24; }
+// 7 bits: an id whose top byte is 0xff is always the EMPTY id
+__device__ __forceinline__ uint32_t pa_fingerprint(uint64_t h) { return (uint32_t(h >> 32) & 0x7fu) << 24; }
 // bits that decide the sub-pass of a split partition: independent of the partition (top of the upper half) and of the
 // bucket (top of the lower half)
 __device__ __forceinline__ uint32_t pa_split_bits(uint64_t h) { return ((uint32_t(h >> 40) & 0xffu) | ((uint32_t(h) & 0x3ffu) << 8)); }
@@ -293,12 +295,16 @@ __global__ void __launch_bounds__(kPaThreads, 2) pa_count_kernel(const __grid_co
 }
 
 // ---- pass 2: exclusive scan of the partition counters (one CTA) -------------------------------------------------------
-__global__ void __launch_bounds__(1024) pa_offsets_kernel(const uint32_t* counts, unsigned long long* base, uint32_t P) {
+// Also the skew check: hashing spreads the GROUPS evenly, so a partition with far more rows than the others holds hot keys.
+// One CTA aggregates a partition; a partition beyond `heavy_rows` would serialise the launch on one SM, so the whole
+// launch falls back to the global-table probe (whose atomics spread a hot key's rows over all SMs): *skewed = 1.
+__global__ void __launch_bounds__(1024) pa_offsets_kernel(const uint32_t* counts, unsigned long long* base, uint32_t P, uint32_t heavy_rows,
+                                                          int* skewed) {
   __shared__ unsigned long long warp_tot[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t chunk = (P + 1023) / 1024, lo = min(uint32_t(tid) * chunk, P), hi = min(lo + chunk, P);
   unsigned long long sum = 0;
-  for (uint32_t i = lo; i < hi; ++i) sum += counts[i];
+  for (uint32_t i = lo; i < hi; ++i) { sum += counts[i]; if (counts[i] > heavy_rows) *skewed = 1; }
   unsigned long long incl = sum;
   for (int d = 1; d < 32; d <<= 1) {
     const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -342,10 +348,10 @@ __global__ void __launch_bounds__(kPaThreads, 2) pa_scatter_kernel(const __grid_
   uint32_t* run_len = run_ws + a.n_dest;                                                 // [n_dest] records in the run
   uint32_t* slot_ps = run_len + a.n_dest;                                                // [n_dest + 1] staging slots (multiples of 4 words)
   uint32_t* tile_prefix = slot_ps + a.n_dest + 1;                                        // [n_src + 1]
-  uint16_t* rank_of_row = reinterpret_cast<uint16_t*>(tile_prefix + n_src + 1);          // [R]  0xffff = dropped
-  uint8_t* dest_of_row = reinterpret_cast<uint8_t*>(rank_of_row + R);                    // [R]
-  uint8_t* dest_of_vec = dest_of_row + ((R + 3u) & ~3u);                                 // [stage_words / 4]  0xff = padding
+  uint32_t* row_info = tile_prefix + n_src + 1;                                          // [R]  rank | destination << 16; rank 0xffff = dropped
+  uint8_t* dest_of_vec = reinterpret_cast<uint8_t*>(row_info + R);                       // [stage_words / 4]  0xff = padding
   const int tid = threadIdx.x, lane = tid & 31;
+  if (*a.skewed) return;
   if (tid == 0) {
     uint32_t acc = 0;
     tile_prefix[0] = 0;
@@ -419,8 +425,7 @@ __global__ void __launch_bounds__(kPaThreads, 2) pa_scatter_kernel(const __grid_
           d = kLevel == 1 ? (p >> a.F2_log2) : (p & F2_mask);
           rank = atomicAdd(&hist[d], 1u);
         }
-        dest_of_row[i] = uint8_t(d);
-        rank_of_row[i] = uint16_t(rank);
+        row_info[i] = rank | (d << 16);
       }
     }
     __syncthreads();
@@ -472,12 +477,15 @@ __global__ void __launch_bounds__(kPaThreads, 2) pa_scatter_kernel(const __grid_
         const uint32_t i = i0 + uint32_t(b) * kPaThreads + tid;
         dst[b] = nullptr;
         if (i < n_tile) {
-          const uint32_t rank = rank_of_row[i];
+          const uint32_t info = row_info[i], rank = info & 0xffffu;
           if (rank != 0xffffu) {
-            const uint32_t d = dest_of_row[i];
+            const uint32_t d = info >> 16;
             const uint32_t w = run_ws[d] + rank * uint32_t(RW);
             dst[b] = stage + w;
-            for (uint32_t q = w >> 2; q <= (w + uint32_t(RW) - 1u) >> 2; ++q) dest_of_vec[q] = uint8_t(d);
+            const uint32_t q0 = w >> 2, q1 = (w + uint32_t(RW) - 1u) >> 2;
+            dest_of_vec[q0] = uint8_t(d);
+            dest_of_vec[q1] = uint8_t(d);
+            for (uint32_t q = q0 + 1; q < q1; ++q) dest_of_vec[q] = uint8_t(d);
           }
         }
       }
@@ -567,6 +575,7 @@ struct PaAggArgs {
   unsigned long long* out_cursor;   // entries of the group-by buffer handed out so far
   int64_t* const* groupby_buf;
   int32_t* error_codes;
+  const int* skewed;
   uint32_t off_chunks;              // byte offset of the warps' record chunks inside dynamic shared memory
   uint32_t chunk_words;             // words per chunk buffer (incl. alignment slack); every warp owns two
   uint32_t acc_off[kMaxAcc];        // byte offset of accumulator a's cells (ids at 0)
@@ -598,25 +607,28 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ uint4 lds_volatile_v4(const void* p) {
+__device__ __forceinline__ uint4 lds_volatile_v4(uint32_t saddr) {
   uint4 v;
-  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))) : "memory");
+  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
   return v;
 }
+// bit 7 of every byte of x that is zero, exact for the lowest such byte (a borrow can only flag bytes above a zero byte)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) { return (x - 0x01010101u) & ~x & 0x80808080u; }
 
 // one accumulator update of one record (kind / argument type are compile-time constants for pre-compiled shapes)
 __device__ __forceinline__ void pa_accumulate(const DPlan& p, const PaLayout& F, int k, const DAcc acc, const uint32_t* rec, uint8_t* cell) {
   if (acc.kind == ACC_CNT_ALL) { atomicAdd(reinterpret_cast<uint32_t*>(cell), 1u); return; }
   const int64_t v = pa_field_value(rec, F.f[F.acc_field[k]]);
+  bool is_null = false;
   if (acc.arg_nullable) {
     const DExpr& te = p.exprs[acc.arg];
-    const bool is_null = te.kind == HDK_B200_FP ? __longlong_as_double(v) == fp_null_of(te.width)
-                                                : (v == int_null_of(te.width) || (acc.arg_nullable == 2 && int32_t(v) == INT32_MIN));
-    if (is_null) return;
+    is_null = te.kind == HDK_B200_FP ? __longlong_as_double(v) == fp_null_of(te.width)
+                                     : (v == int_null_of(te.width) || (acc.arg_nullable == 2 && int32_t(v) == INT32_MIN));
   }
+  // a COUNT(arg) cell counts the NULL rows (rare: no atomic for most rows); the emit step turns it into rows - NULLs
+  if (acc.kind == ACC_CNT_NN) { if (is_null) atomicAdd(reinterpret_cast<uint32_t*>(cell), 1u); return; }
+  if (is_null) return;
   switch (acc.kind) {
-    case ACC_CNT_NN: atomicAdd(reinterpret_cast<uint32_t*>(cell), 1u); break;
     case ACC_SUM_I: smem_add_i64(cell, v); break;
     case ACC_SUM_F: atomicAdd(reinterpret_cast<double*>(cell), __longlong_as_double(v)); break;
     case ACC_MIN_I: case ACC_MAX_I: bin_update_shared_atomic(acc.kind, cell, v); break;
@@ -643,6 +655,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
   const DLayout& L = a.layout;
   const uint32_t NB = a.NB, T = NB * 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (*a.skewed) return;
   int RW, KW;
   if constexpr (Shape::is_static) { RW = pa_layout_of(Shape::get()).rec_words; KW = pa_layout_of(Shape::get()).key_words; }
   else { RW = F.rec_words; KW = F.key_words; }
@@ -657,6 +670,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
   int8_t* const buf = reinterpret_cast<int8_t*>(a.groupby_buf[0]);
   const uint64_t E = L.entry_count;
   uint32_t* const my_chunks = reinterpret_cast<uint32_t*>(sm + a.off_chunks) + size_t(warp) * 2 * a.chunk_words;
+  const uint32_t ids_saddr = static_cast<uint32_t>(__cvta_generic_to_shared(ids));
   for (;;) {
     __syncthreads();
     if (tid == 0) s_part = atomicAdd(a.work_counter, 1u);
@@ -736,12 +750,24 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
             cand[u] = empty[u] = 4;
             cand_id[u] = 0;
             if (!pend[u]) continue;
-            const uint4 q = lds_volatile_v4(ids + size_t(bucket[u]) * 4);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            const uint4 q = lds_volatile_v4(ids_saddr + bucket[u] * 16u);
+            if (has_fp) {
+              // the four top bytes in one word: fingerprint matches and empties found with byte arithmetic
+              const uint32_t tb = __byte_perm(__byte_perm(q.x, q.y, 0x0073), __byte_perm(q.z, q.w, 0x0073), 0x5410);
+              const uint32_t zm = zero_bytes((tb ^ ((fp[u] >> 24) * 0x01010101u)) | excl[u]);   // excl: 0xff in verified-unequal bytes
+              const uint32_t ze = zero_bytes(~tb);
+              if (zm) {
+                cand[u] = (__ffs(zm) - 1) >> 3;
+                cand_id[u] = cand[u] == 0 ? q.x : cand[u] == 1 ? q.y : cand[u] == 2 ? q.z : q.w;
+              }
+              if (ze) empty[u] = (__ffs(ze) - 1) >> 3;
+            } else {
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int s = 3; s >= 0; --s) {
-              if (w[s] == kEmptyId) empty[u] = s;
-              else if ((w[s] & ~row_mask) == fp[u] && !((excl[u] >> s) & 1u)) { cand[u] = s; cand_id[u] = w[s]; }
+              for (int s = 3; s >= 0; --s) {
+                if (w[s] == kEmptyId) empty[u] = s;
+                else if (!((excl[u] >> (8 * s)) & 1u)) { cand[u] = s; cand_id[u] = w[s]; }
+              }
             }
           }
           // a slot with the record's fingerprint: compare with the representative's key words (both records' loads in flight)
@@ -761,7 +787,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
 #pragma unroll
               for (int w = 0; w < SKW; ++w) eq = eq && rk[u][w] == rec[u][w];
               if (eq) { pend[u] = false; slot[u] = bucket[u] * 4 + cand[u]; }
-              else excl[u] |= 1u << cand[u];
+              else excl[u] |= 0xffu << (8 * cand[u]);
             }
           } else {
 #pragma unroll
@@ -771,7 +797,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
               bool eq = true;
               for (int w = 0; w < KW && eq; ++w) eq = __ldg(rep + w) == rec[u][w];
               if (eq) { pend[u] = false; slot[u] = bucket[u] * 4 + cand[u]; }
-              else excl[u] |= 1u << cand[u];
+              else excl[u] |= 0xffu << (8 * cand[u]);
             }
           }
           any_pend = false;
@@ -854,8 +880,10 @@ __global__ void __launch_bounds__(kAggThreads, 1) pa_aggregate_kernel(const __gr
             else reinterpret_cast<int64_t*>(row)[k] = kv;
           }
           auto cell = [&](int k) -> int64_t {
-            return p.accs[k].bytes == 4 ? int64_t(reinterpret_cast<const uint32_t*>(sm + a.acc_off[k])[s])
-                                        : reinterpret_cast<const int64_t*>(sm + a.acc_off[k])[s];
+            if (p.accs[k].bytes == 8) return reinterpret_cast<const int64_t*>(sm + a.acc_off[k])[s];
+            const int64_t c = int64_t(reinterpret_cast<const uint32_t*>(sm + a.acc_off[k])[s]);
+            // (accumulator 0 is always the group's row count, lower.cu)
+            return p.accs[k].kind == ACC_CNT_NN ? int64_t(reinterpret_cast<const uint32_t*>(sm + a.acc_off[0])[s]) - c : c;
           };
           for (int si = 0; si < L.slot_count; ++si) {
             const DSlot& sl = L.slots[si];
@@ -897,6 +925,7 @@ struct PaGeometry {
   uint32_t off_chunks, chunk_words;
   uint32_t acc_off[kMaxAcc];
   size_t header_bytes, rec_bytes, total_bytes;
+  uint32_t heavy_rows;
 };
 
 static int partagg_geometry(const Lowered& lw, const PaLayout& L, uint64_t total_rows, uint32_t num_fragments, PaGeometry* g) {
@@ -938,7 +967,7 @@ static int partagg_geometry(const Lowered& lw, const PaLayout& L, uint64_t total
   // ---- scatter tiles: R rows x (record + rank + destination) + per destination (slot padding, descriptors) + per vector a byte
   auto scatter_bytes = [&](size_t R, size_t n_src, size_t n_dest) {
     const size_t stage_words = (R * L.rec_words + 8 * n_dest + 3) & ~size_t(3);
-    return stage_words * 4 + n_dest * (8 + 4 + 4 + 4 + 4) + 4 + (n_src + 1) * 4 + R * 2 + ((R + 3) & ~size_t(3)) + stage_words / 4 + 64;
+    return stage_words * 4 + n_dest * (8 + 4 + 4 + 4 + 4) + 4 + (n_src + 1) * 4 + R * 4 + stage_words / 4 + 64;
   };
   g->tile_rows = 0;
   for (size_t R = kPaMaxTileRows; R >= size_t(kPaThreads); R -= kPaThreads) {
@@ -952,7 +981,14 @@ static int partagg_geometry(const Lowered& lw, const PaLayout& L, uint64_t total
   // header: counts u32[P] | cursor2 u32[P] | cursor1 u32[F1] | base u64[P + 1] | work counter, out cursor
   g->header_bytes = pa_align(size_t(g->P) * 8 + size_t(F1) * 4 + 8 + (size_t(g->P) + 1) * 8 + 64, 256);
   g->rec_bytes = pa_align(size_t(total_rows) * L.rec_words * 4 + 64, 256);
-  g->total_bytes = g->header_bytes + g->rec_bytes * (f2 ? 2 : 1) + 256;
+  // (the fallback's work table lives where the records would: only one of the two paths runs)
+  g->total_bytes = g->header_bytes + std::max(g->rec_bytes * (f2 ? 2 : 1), pa_align(lw.work_table_bytes, 256)) + 256;
+  // heavy partition: more rows than one SM can take without stretching the launch (a quarter of an even share of the
+  // SMs' work) and far beyond the average
+  const uint64_t avg = total_rows / g->P + 1;
+  uint64_t heavy = std::max<uint64_t>(8 * avg + 65536, total_rows / (uint64_t(sm_count()) * 4));
+  if (g_debug.pa_heavy_rows > 0) heavy = uint64_t(g_debug.pa_heavy_rows);
+  g->heavy_rows = uint32_t(std::min<uint64_t>(heavy, 0xffffffffu));
   return HDK_B200_OK;
 }
 
@@ -990,7 +1026,7 @@ static const PaKernels kPaStatic[] = {
 #undef HB_STATIC_SHAPE
 
 int launch_partagg(const Lowered& lw, const hdk_b200_kernel_params* params, void* scratch, size_t scratch_bytes, cudaStream_t st,
-                   hdk_b200_launch_info* info) {
+                   hdk_b200_launch_info* info, const int** fallback_flag, int64_t** fallback_work) {
   const PaLayout L = pa_layout_of(lw.plan);
   if (!L.ok) { set_error("plan shape not eligible for partitioned aggregation"); return HDK_B200_E_UNSUPPORTED; }
   const uint64_t total_rows = params->total_rows_hint;
@@ -1025,6 +1061,10 @@ int launch_partagg(const Lowered& lw, const hdk_b200_kernel_params* params, void
   a.base = base;
   unsigned int* work_counter = reinterpret_cast<unsigned int*>(base + g.P + 1);
   unsigned long long* out_cursor = reinterpret_cast<unsigned long long*>(work_counter + 2);
+  int* skewed = reinterpret_cast<int*>(out_cursor + 1);
+  a.skewed = skewed;
+  *fallback_flag = skewed;
+  *fallback_work = reinterpret_cast<int64_t*>(s + g.header_bytes);
   uint32_t* recs_a = reinterpret_cast<uint32_t*>(s + g.header_bytes);               // level 1 output
   uint32_t* recs_b = reinterpret_cast<uint32_t*>(s + g.header_bytes + g.rec_bytes);   // level 2 output
   a.error_codes = params->error_codes;
@@ -1033,7 +1073,7 @@ int launch_partagg(const Lowered& lw, const hdk_b200_kernel_params* params, void
   HB_CUDA(cudaFuncSetAttribute(kern.count, cudaFuncAttributeMaxDynamicSharedMemorySize, int(count_smem)));
   kern.count<<<sm_count() * (count_smem > 100 * 1024 ? 1 : 2), kPaThreads, count_smem, st>>>(a);
   HB_LAUNCH_CHECK();
-  pa_offsets_kernel<<<1, 1024, 0, st>>>(a.counts, base, g.P);
+  pa_offsets_kernel<<<1, 1024, 0, st>>>(a.counts, base, g.P, g.heavy_rows, skewed);
   HB_LAUNCH_CHECK();
   // level 1: fragments → F1 destinations (the final partitions themselves when one level suffices)
   a.n_dest = g.F1;
@@ -1067,6 +1107,7 @@ int launch_partagg(const Lowered& lw, const hdk_b200_kernel_params* params, void
   ag.out_cursor = out_cursor;
   ag.groupby_buf = params->groupby_buf;
   ag.error_codes = params->error_codes;
+  ag.skewed = skewed;
   ag.off_chunks = g.off_chunks;
   ag.chunk_words = g.chunk_words;
   for (int k = 0; k < lw.plan.n_acc; ++k) ag.acc_off[k] = g.acc_off[k];

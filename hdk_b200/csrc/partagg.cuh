@@ -58,8 +58,11 @@ __host__ __device__ constexpr PaLayout pa_layout_of(const DPlan& p) {
 }
 
 int partagg_scratch_bytes(const Lowered& lw, uint64_t total_rows, size_t* bytes);
+// Enqueues the partitioned path.  *fallback_flag (device int) is raised by it when a partition is too heavy for one CTA
+// (hot keys): its remaining kernels then do nothing and the caller's global-table path, enqueued behind with
+// run_if = *fallback_flag and its work table at *fallback_work (inside `scratch`), does the launch's work instead.
 int launch_partagg(const Lowered& lw, const hdk_b200_kernel_params* params, void* scratch, size_t scratch_bytes, cudaStream_t st,
-                   hdk_b200_launch_info* info);
+                   hdk_b200_launch_info* info, const int** fallback_flag, int64_t** fallback_work);
 
 // process-wide debug / tuning overrides (hdk_b200_debug_set)
 struct DebugKnobs {
@@ -68,6 +71,7 @@ struct DebugKnobs {
   int partitioned;          // -1 auto, 0 never, 1 whenever the plan is eligible and the scratch area suffices
   int pa_slots;             // 0 auto, else slots of the per-CTA shared table of the partitioned aggregation (tests: force splits)
   int pa_partitions;        // 0 auto, else the number of partitions
+  int pa_heavy_rows;        // 0 auto, else the partition size beyond which the launch falls back to the global-table probe
 };
 extern DebugKnobs g_debug;
 

@@ -493,6 +493,7 @@ template <int kStrategy, class Shape, int G = kRegGroups>
 __global__ void __launch_bounds__(kStrategy == HDK_B200_STRATEGY_REGISTER ? kRegThreads : kThreads, kStrategy == HDK_B200_STRATEGY_REGISTER ? 1 : 2)
 scan_kernel(const __grid_constant__ ScanArgs args) {
   extern __shared__ __align__(128) uint8_t smem[];
+  if (args.run_if && *args.run_if == 0) return;
   const DPlan& p = args.plan;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -829,20 +830,21 @@ static const StaticEntry kStaticShapes[] = {
 // ---------------------------------------------------------------------------------------------
 // accumulator-major [n_acc][E] for perfect hash (merge classes are contiguous for the all-reduce),
 // entry-major [E][n_acc] for baseline hash (one entry's cells share a sector)
-__global__ void init_work_table_kernel(int64_t* w, uint64_t E, int n_acc, bool entry_major, const __grid_constant__ AccKinds kinds) {
+__global__ void init_work_table_kernel(int64_t* w, uint64_t E, int n_acc, bool entry_major, const __grid_constant__ AccKinds kinds, const int* run_if) {
+  if (run_if && *run_if == 0) return;
   const uint64_t n = uint64_t(n_acc) * E;
   for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
     w[i] = acc_identity(kinds.kind[entry_major ? i % uint64_t(n_acc) : i / E]);
 }
 
-int init_work_table(const Lowered& lw, int64_t* work_table, cudaStream_t stream) {
+int init_work_table(const Lowered& lw, int64_t* work_table, cudaStream_t stream, const int* run_if) {
   AccKinds kinds{};
   for (int a = 0; a < lw.plan.n_acc; ++a) kinds.kind[a] = lw.plan.accs[a].kind;
   const uint64_t n = uint64_t(lw.plan.n_acc) * lw.plan.entry_count;
   const int block = 256;
   const int grid = int(std::min<uint64_t>((n + block - 1) / block, uint64_t(sm_count()) * 8));
   init_work_table_kernel<<<std::max(grid, 1), block, 0, stream>>>(work_table, lw.plan.entry_count, lw.plan.n_acc,
-                                                                  lw.plan.hash_type == HDK_B200_BASELINE_HASH, kinds);
+                                                                  lw.plan.hash_type == HDK_B200_BASELINE_HASH, kinds, run_if);
   HB_LAUNCH_CHECK();
   return HDK_B200_OK;
 }
@@ -854,7 +856,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
                             int64_t* work_table, bool baseline, cudaStream_t stream, hdk_b200_launch_info* info,
-                            const ExchangeTargets* xchg = nullptr) {
+                            const ExchangeTargets* xchg = nullptr, const int* run_if = nullptr) {
   const DPlan& p = lw.plan;
   if (params->num_fragments > kMaxFragments) { set_error("more than %d fragments per launch", kMaxFragments); return HDK_B200_E_UNSUPPORTED; }
   ScanArgs a{};
@@ -868,6 +870,7 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   a.error_codes = params->error_codes;
   a.layout = lw.layout;
   a.groupby_buf = params->groupby_buf;
+  a.run_if = run_if;
   if (xchg) {
     a.n_peers = xchg->n_peers;
     a.n_cells = uint64_t(p.n_acc) * p.entry_count;
@@ -1089,8 +1092,8 @@ int launch_scan_exchange(const Lowered& lw, const hdk_b200_kernel_options* ko, c
   return launch_scan_impl(lw, ko, params, work_table, false, stream, info, &x);
 }
 int launch_baseline_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
-                         int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info) {
-  return launch_scan_impl(lw, ko, params, work_table, true, stream, info);
+                         int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info, const int* run_if) {
+  return launch_scan_impl(lw, ko, params, work_table, true, stream, info, nullptr, run_if);
 }
 
 }  // namespace hb

@@ -24,6 +24,7 @@ struct ScanArgs {
   int64_t* work_table;                // [n_acc * entry_count]            (perfect hash)
   int64_t* const* groupby_buf;        // GROUPBY_BUF device array, [0] used  (baseline hash)
   int32_t* error_codes;
+  const int* run_if;                  // when set: the kernel does nothing unless *run_if != 0 (fallback path of the partitioned aggregation)
   uint32_t num_fragments;
   uint32_t tile_rows;
   uint32_t stage_bytes;
@@ -42,11 +43,11 @@ struct ScanArgs {
   uint32_t col_region_off[HDK_B200_MAX_COLS];       // from a stage's base
 };
 
-int init_work_table(const Lowered& lw, int64_t* work_table, cudaStream_t stream);
+int init_work_table(const Lowered& lw, int64_t* work_table, cudaStream_t stream, const int* run_if = nullptr);
 int launch_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
                 int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info);
 int launch_finalize(const Lowered& lw, const int64_t* work_table, int64_t* groups_buffer, int64_t* const* groups_buffer_indirect,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const int* run_if = nullptr);
 // exchange variants (peer.cu)
 struct ExchangeTargets {
   uint32_t n_peers;
@@ -60,6 +61,6 @@ int launch_scan_exchange(const Lowered& lw, const hdk_b200_kernel_options* ko, c
 int launch_finalize_exchange(const Lowered& lw, const int64_t* slots, const unsigned long long* flags, uint32_t n_peers, uint64_t epoch,
                              int32_t* error_codes, int64_t* const* groups_buffer_indirect, cudaStream_t stream);
 int launch_baseline_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
-                         int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info);
+                         int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info, const int* run_if = nullptr);
 
 }  // namespace hb

@@ -669,7 +669,9 @@ HDK_B200_API int hdk_b200_query_host(const hdk_b200_plan* plan, const hdk_b200_q
  *   "force_strategy"           -1 = library picks; HDK_B200_STRATEGY_* = accumulation strategy of perfect-hash launches
  *   "partitioned_aggregation"  -1 = library picks; 0 = never; 1 = whenever the plan is eligible and the scratch suffices
  *   "partitioned_table_slots"  0 = library picks; else the slots of the per-CTA shared table (tests force partition splits)
- *   "partitioned_partitions"   0 = library picks; else the number of partitions */
+ *   "partitioned_partitions"   0 = library picks; else the number of partitions
+ *   "partitioned_heavy_rows"   0 = library picks; else the partition size (rows) beyond which a partitioned launch falls
+ *                              back to the global-table probe (hot keys) */
 HDK_B200_API int hdk_b200_debug_set(const char* name, int value);
 HDK_B200_API const char* hdk_b200_last_error(void);
 HDK_B200_API int hdk_b200_abi_version(void);

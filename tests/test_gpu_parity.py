@@ -1059,7 +1059,8 @@ def partitioned():
         _lib.debug_set("partitioned_partitions", partitions)
         _lib.debug_set("force_generic", generic)
     yield set_
-    for k, v in (("partitioned_aggregation", -1), ("partitioned_table_slots", 0), ("partitioned_partitions", 0), ("force_generic", 0)):
+    for k, v in (("partitioned_aggregation", -1), ("partitioned_table_slots", 0), ("partitioned_partitions", 0), ("force_generic", 0),
+                 ("partitioned_heavy_rows", 0)):
         _lib.debug_set(k, v)
 
 
@@ -1083,6 +1084,33 @@ def test_partitioned_aggregation_matches_oracle(oracle_mod, env, torch, partitio
     assert int(prep["err"].item()) == 0
     assert info.strategy == abi.STRATEGY_PARTITIONED
     check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+
+
+@pytest.mark.parametrize("heavy_rows", [1, 3000, 0])
+def test_partitioned_aggregation_hot_keys_fall_back(oracle_mod, torch, partitioned, heavy_rows):
+    """Hot keys: hashing spreads groups, not rows — a partition holding a hot key would serialise the launch on one CTA.
+    The offsets kernel raises a device flag when a partition exceeds the limit, the partitioned kernels stand down and the
+    global-table path enqueued behind them does the work.  heavy_rows = 1: every launch falls back; 3000: only because of
+    the hot key; 0 (library default): no fallback at this size.  Same answer every time."""
+    from hdk_b200 import _lib, sql
+    from hdk_b200.executor import Executor
+    rng = np.random.default_rng(77)
+    n = 120_000
+    k = rng.integers(0, 40_000, n) * 1_000_003
+    k[rng.random(n) < 0.4] = 123_456_789_012          # 40 % of the rows share one key
+    t = pa.table({"k": k, "j": rng.integers(0, 7, n).astype(np.int32), "v": pa.array(rng.integers(-50, 50, n), mask=rng.random(n) < 0.05),
+                  "f": rng.normal(0, 10, n)})
+    st = util.make_storage({"t": t}, fragment_size=25_001)
+    partitioned()
+    _lib.debug_set("partitioned_heavy_rows", heavy_rows)
+    ex = Executor(st)
+    pq = ex.plan(sql.parse("SELECT k, j, COUNT(*), SUM(v), MIN(f), MAX(v), AVG(f) FROM t GROUP BY k, j", st.tables), 400_000)
+    assert pq.qmd.hash_type == abi.BASELINE_HASH
+    prep = ex.prepare(pq)
+    info = ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0 and info.strategy == abi.STRATEGY_PARTITIONED
+    check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), 2)
 
 
 def test_partitioned_aggregation_out_of_slots(env, torch, partitioned):

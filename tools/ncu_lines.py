@@ -10,7 +10,8 @@ import sys
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", f"regex:{kern}"],
+    sel = ["--kernel-id", kern] if kern.startswith(":") else ["--kernel-name", f"regex:{kern}"]   # ":::3" = third launch
+    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + sel,
                                   text=True, stderr=subprocess.DEVNULL)
     fname, hdr, data = "", None, []
     for r in csv.reader(io.StringIO(raw)):
