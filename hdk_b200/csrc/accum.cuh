@@ -46,10 +46,25 @@ __device__ __forceinline__ void bin_update_private(uint8_t kind, uint8_t* bin, i
     default: { int64_t* b = reinterpret_cast<int64_t*>(bin); *b = max(*b, x); break; }
   }
 }
+// 64-bit integer SUM in shared memory with native 32-bit atomics: add the low half, carry into the high half.  Every
+// carry is added exactly once by the thread whose addition produced it, additions commute, so the cell ends up exact
+// modulo 2^64 whatever the interleaving (a 64-bit shared atomicAdd is a CAS loop: SASS ATOMS.CAST.SPIN.64).
+__device__ __forceinline__ void smem_add_i64(uint8_t* cell, int64_t x) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(cell);
+  const uint32_t lo = uint32_t(uint64_t(x)), hi = uint32_t(uint64_t(x) >> 32);
+  uint32_t carry = 0;
+  if (lo) {
+    const uint32_t old = atomicAdd(w, lo);
+    carry = (old + lo) < old ? 1u : 0u;
+  }
+  const uint32_t h = hi + carry;
+  if (h) atomicAdd(w + 1, h);
+}
+
 __device__ __forceinline__ void bin_update_shared_atomic(uint8_t kind, uint8_t* bin, int64_t x) {
   switch (kind) {
     case ACC_CNT_ALL: case ACC_CNT_NN: atomicAdd(reinterpret_cast<uint32_t*>(bin), 1u); break;
-    case ACC_SUM_I: atomicAdd(reinterpret_cast<unsigned long long*>(bin), static_cast<unsigned long long>(x)); break;
+    case ACC_SUM_I: smem_add_i64(bin, x); break;
     case ACC_SUM_F: atomicAdd(reinterpret_cast<double*>(bin), __longlong_as_double(x)); break;
     // 64-bit shared atomics are CAS loops (SASS ATOMS.CAST.SPIN.64): look first, a bin only ever moves towards x
     case ACC_MIN_I: case ACC_MIN_F:

@@ -581,21 +581,6 @@ struct PaAggArgs {
   uint32_t acc_off[kMaxAcc];        // byte offset of accumulator a's cells (ids at 0)
 };
 
-// 64-bit integer SUM in shared memory with native 32-bit atomics: add the low half, carry into the high half.  Every
-// carry is added exactly once by the thread whose addition produced it, additions commute, so the cell ends up exact
-// modulo 2^64 whatever the interleaving (a 64-bit shared atomicAdd is a CAS loop: SASS ATOMS.CAST.SPIN.64).
-__device__ __forceinline__ void smem_add_i64(uint8_t* cell, int64_t x) {
-  uint32_t* w = reinterpret_cast<uint32_t*>(cell);
-  const uint32_t lo = uint32_t(uint64_t(x)), hi = uint32_t(uint64_t(x) >> 32);
-  uint32_t carry = 0;
-  if (lo) {
-    const uint32_t old = atomicAdd(w, lo);
-    carry = (old + lo) < old ? 1u : 0u;
-  }
-  const uint32_t h = hi + carry;
-  if (h) atomicAdd(w + 1, h);
-}
-
 __device__ __forceinline__ void pa_store_slot(int8_t* p, int bytes, int padded, int64_t v) {
   if (padded == 8) *reinterpret_cast<int64_t*>(p) = bytes == 8 ? v : int64_t(uint32_t(v));
   else *reinterpret_cast<int32_t*>(p) = int32_t(v);

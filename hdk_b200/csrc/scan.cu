@@ -22,6 +22,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "accum.cuh"
@@ -854,6 +857,30 @@ int init_work_table(const Lowered& lw, int64_t* work_table, cudaStream_t stream,
 // ---------------------------------------------------------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// launch geometry per (plan shape, entry count, fragment count, input size class, device, forced choices): per-device
+// cache, nothing query-specific in it (literals, pointers and key ranges travel in the arguments of every launch)
+struct GeoKey {
+  uint64_t sig, entries;
+  uint32_t n_frag, hint_bucket, dev, baseline, force_generic, force_strategy, grid_x;
+  bool operator==(const GeoKey& o) const {
+    return sig == o.sig && entries == o.entries && n_frag == o.n_frag && hint_bucket == o.hint_bucket && dev == o.dev && baseline == o.baseline &&
+           force_generic == o.force_generic && force_strategy == o.force_strategy && grid_x == o.grid_x;
+  }
+};
+struct GeoEntry {
+  GeoKey key;
+  ScanArgs a;            // only the geometry fields are used
+  ScanKernelFn kern;
+  int grid, block, variant, strategy;
+  size_t smem_bytes;
+};
+static std::mutex g_geo_mutex;
+static std::vector<GeoEntry> g_geo_cache;
+static const char* geo_env() {   // tuning hook (tools/sweep_geo.py), read once
+  static const char* env = getenv("HDK_B200_GEO");
+  return env;
+}
+
 static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
                             int64_t* work_table, bool baseline, cudaStream_t stream, hdk_b200_launch_info* info,
                             const ExchangeTargets* xchg = nullptr, const int* run_if = nullptr) {
@@ -881,6 +908,30 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
 
   int dev = 0;
   HB_CUDA(cudaGetDevice(&dev));
+  // ---- launch geometry of an earlier launch of the same shape?  (the search below queries occupancy and sets function
+  //      attributes: not something to repeat per launch of a 100 µs query)
+  const uint64_t total_hint = params->total_rows_hint;
+  int hint_bucket = 0;
+  while ((total_hint >> hint_bucket) > 1) ++hint_bucket;
+  GeoKey key{plan_signature(p), uint64_t(p.entry_count), a.num_fragments, uint32_t(hint_bucket), uint32_t(dev), baseline ? 1u : 0u,
+             uint32_t(g_debug.force_generic), uint32_t(g_debug.force_strategy + 1), ko ? ko->gridDimX : 0u};
+  {
+    std::lock_guard<std::mutex> lock(g_geo_mutex);
+    for (const GeoEntry& ge : g_geo_cache)
+      if (ge.key == key && !geo_env()) {
+        a.consumer_threads = ge.a.consumer_threads; a.n_stages = ge.a.n_stages; a.tile_rows = ge.a.tile_rows; a.off_bins = ge.a.off_bins;
+        a.off_stages = ge.a.off_stages; a.off_tile_prefix = ge.a.off_tile_prefix; a.stage_bytes = ge.a.stage_bytes; a.full_iters = ge.a.full_iters;
+        memcpy(a.acc_bin_off, ge.a.acc_bin_off, sizeof(a.acc_bin_off));
+        memcpy(a.col_region_off, ge.a.col_region_off, sizeof(a.col_region_off));
+        ge.kern<<<ge.grid, ge.block, ge.smem_bytes, stream>>>(a);
+        HB_LAUNCH_CHECK();
+        if (info) {
+          info->variant = ge.variant; info->strategy = ge.strategy; info->grid = ge.grid; info->block = ge.block;
+          info->smem_bytes = int(ge.smem_bytes); info->n_accumulators = p.n_acc; info->tile_rows = int(ge.a.tile_rows);
+        }
+        return HDK_B200_OK;
+      }
+  }
   int max_smem = 0;
   HB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 
@@ -923,7 +974,7 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
     if (strategy == HDK_B200_STRATEGY_REGISTER) bins = size_t(kRegGroups) * kMaxAcc * 4;   // NULL-row counters of COUNT(arg)
     const size_t off_stages = align_up(fixed_bytes + bins, 128);
     // each resident CTA costs its dynamic shared memory + 1 KB reserved by the driver
-    const size_t budget = std::min<size_t>(size_t(sm_smem) / ctas - 1024, size_t(max_smem));
+    const size_t budget = std::min<size_t>(size_t(sm_smem) / ctas - 1024, size_t(max_smem) - 1024);
     if (off_stages >= budget) return false;
     const size_t per_stage = std::min<size_t>((budget - off_stages) / stages, 72 * 1024);
     // a whole number of full-tile iterations (nct * iter_rows rows each); every column slice is then a multiple of 16 bytes
@@ -961,7 +1012,7 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
             ScanKernelFn k = stat->reg_fn[E <= 2 ? 0 : E <= 4 ? 1 : E <= 6 ? 2 : 3];
             const size_t smem_need = g.off_stages + size_t(stages) * align_up(size_t(g.tile_rows) * row_bytes + 48 * size_t(p.n_cols), 128);
             int occ = 0;
-            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::min<size_t>(smem_need + 4096, size_t(max_smem)))) != cudaSuccess ||
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024) != cudaSuccess ||
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, nct + 32, smem_need) != cudaSuccess || occ < ctas) {
               cudaGetLastError();
               continue;
@@ -1006,7 +1057,7 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
     if (!have) have = best(HDK_B200_STRATEGY_GLOBAL, &geo);
   }
   // tuning hook (tools/sweep_geo.py): HDK_B200_GEO="strategy,consumer_threads,ctas_per_sm,stages,tile_rows" overrides the search
-  if (const char* env = getenv("HDK_B200_GEO")) {
+  if (const char* env = geo_env()) {
     int es = 0, en = 0, ec = 0, est = 0, et = 0;
     if (sscanf(env, "%d,%d,%d,%d,%d", &es, &en, &ec, &est, &et) == 5 && en >= 32 && en <= kConsumerWarps * 32 && en % 32 == 0 &&
         est >= 1 && est <= kStages && et >= 32 && es >= 0 && es <= HDK_B200_STRATEGY_REGISTER &&
@@ -1045,7 +1096,7 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   }
   a.stage_bytes = uint32_t(align_up(so, 128));
   const size_t smem_bytes = a.off_stages + size_t(a.stage_bytes) * geo.stages;
-  if (smem_bytes > size_t(max_smem)) { set_error("stage ring does not fit in shared memory (%zu > %d)", smem_bytes, max_smem); return HDK_B200_E_UNSUPPORTED; }
+  if (smem_bytes > size_t(max_smem) - 1024) { set_error("stage ring does not fit in shared memory (%zu > %d)", smem_bytes, max_smem - 1024); return HDK_B200_E_UNSUPPORTED; }
   const int block = geo.nct + 32;
   int grid = sm_count() * geo.ctas;
   if (ko && ko->gridDimX) grid = int(ko->gridDimX);
@@ -1063,11 +1114,18 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
     const uint32_t per_iter = uint32_t(geo.nct) * uint32_t(stat->iter_rows);
     a.full_iters = (geo.tile_rows % per_iter == 0 && geo.tile_rows % 16 == 0) ? geo.tile_rows / per_iter : 0;
   }
-  HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+  HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024));   // (a cap, never lowered: cached geometries of the same kernel stay launchable)
   if (!(ko && ko->gridDimX)) {   // persistent grid = what is actually resident (registers can allow fewer CTAs than planned)
     int occ = 0;
     HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem_bytes));
     grid = sm_count() * std::max(1, std::min(occ, geo.ctas));
+  }
+  if (!geo_env()) {
+    std::lock_guard<std::mutex> lock(g_geo_mutex);
+    if (g_geo_cache.size() >= 256) g_geo_cache.clear();
+    GeoEntry ge{};
+    ge.key = key; ge.a = a; ge.kern = kern; ge.grid = grid; ge.block = block; ge.smem_bytes = smem_bytes; ge.variant = variant; ge.strategy = strategy;
+    g_geo_cache.push_back(ge);
   }
   kern<<<grid, block, smem_bytes, stream>>>(a);
   HB_LAUNCH_CHECK();

@@ -56,6 +56,8 @@ class Table:
     columns: Dict[str, ColumnInfo]
     fragments: List[Fragment]
     num_rows: int
+    shard: Optional[tuple] = None     # (rank, world): this process holds fragments i with i % world == rank of a table spread over
+                                      # the ranks of a process group (one process per GPU); None = the whole table is here
 
     def col_stats(self, column: str):
         lo = hi = None
@@ -197,7 +199,7 @@ class ArrowStorage:
                     stats[cname] = _stats(v, ci.type)
                 frags.append(Fragment(fid, rows, off, fid % self.n_devices, chunks, stats))
             fid += 1
-        t = Table(name, cols, frags, sum(f.num_rows for f in frags))
+        t = Table(name, cols, frags, sum(f.num_rows for f in frags), shard)
         self.tables[name] = t
         return t
 
@@ -274,13 +276,13 @@ class ArrowStorage:
                 frags.append(fr)
                 kept += 1
             fid += 1
-        t = Table(name, cols, frags, sum(f.num_rows for f in frags))
+        t = Table(name, cols, frags, sum(f.num_rows for f in frags), shard)
         self.tables[name] = t
         return t
 
-    def add_device_table(self, name: str, columns: Dict[str, ColumnInfo], fragments: List[Fragment]) -> Table:
+    def add_device_table(self, name: str, columns: Dict[str, ColumnInfo], fragments: List[Fragment], shard: Optional[tuple] = None) -> Table:
         """Register fragments whose chunks already live on the device (synthetic benchmarks)."""
-        t = Table(name, columns, fragments, sum(f.num_rows for f in fragments))
+        t = Table(name, columns, fragments, sum(f.num_rows for f in fragments), shard)
         self.tables[name] = t
         return t
 
