@@ -350,6 +350,14 @@ class Executor:
         self.region_bytes = 12 << 20                   # target size of one region (a fraction of L2)
         self.partition_over_peer_memory = True    # execute_partitioned: scatter straight into the owners' buffers (else NCCL all-to-all)
         self._peer_rows = {}
+        # Under torch.distributed (one process per GPU) a query over a SHARDED table (Table.shard) runs across all ranks and
+        # returns the merged result on every rank: perfect hash = partials merged inside the kernels over peer memory (or
+        # NCCL all-reduce), baseline hash = rows re-partitioned by key hash, join build sides built once and broadcast.
+        self.distributed = True
+        self.broadcast_join_build = True          # False: every rank builds its own copy (what the reference does per device)
+        self._exchanges = {}                      # PeerExchange per work-table shape
+        self._peer_ok = None
+        self._global_stats = {}
         self.lib = _lib.lib()
         self.join_tables: Dict[tuple, JoinTable] = {}
         self.last_launch_info = None
@@ -390,6 +398,17 @@ class Executor:
         cache_key = (inner.name, id(inner), tuple(key_cols), key_width)   # id(): a table re-imported under the same name is another table
         if cache_key in self.join_tables:
             return self.join_tables[cache_key]
+        if self._broadcasts_build(inner):
+            from . import distributed as D
+            jt = self._build_baseline_join_table_local(inner, key_cols, key_width) if D.rank() == 0 else None
+            jt = self._broadcast_join_table(jt, inner)
+            self.join_tables[cache_key] = jt
+            return jt
+        jt = self._build_baseline_join_table_local(inner, key_cols, key_width)
+        self.join_tables[cache_key] = jt
+        return jt
+
+    def _build_baseline_join_table_local(self, inner: Table, key_cols, key_width: int) -> JoinTable:
         torch = self.ctx.torch
         jcs, tis, rows, keep = self._join_columns(inner, key_cols)
         entries = 2 * max(rows, 1)
@@ -420,7 +439,28 @@ class Executor:
             raise QueryError(code, "baseline join table build failed")
         jt = JoinTable(buf, hash_type, 0, 0, entries, inner, {})
         jt.key_width, jt.n_keys = key_width, n
-        self.join_tables[cache_key] = jt
+        return jt
+
+    def _broadcasts_build(self, inner: Table) -> bool:
+        """Build side built once (rank 0) and broadcast?  Only for a table every rank holds in full (not sharded): the
+        reference rebuilds the table on every device (JHT/PerfectJoinHashTable.cpp:331-339)."""
+        from . import distributed as D
+        return bool(self.distributed and self.broadcast_join_build and inner.shard is None and D.is_dist() and D.world() > 1)
+
+    def _broadcast_join_table(self, jt: Optional[JoinTable], inner: Table) -> JoinTable:
+        """rank 0's table → every rank (NCCL broadcast of the buffer; the few scalars travel as an object)."""
+        import torch.distributed as dist
+
+        from . import distributed as D
+        meta = [None]
+        if D.rank() == 0:
+            meta = [(jt.hash_type, jt.min_key, jt.max_key, jt.entry_count, jt.dense, jt.key_width, jt.n_keys, int(jt.buffer.numel()))]
+        dist.broadcast_object_list(meta, src=0)
+        hash_type, lo, hi, entries, dense, kw, nk, nbytes = meta[0]
+        buf = D.broadcast_tensor(jt.buffer if D.rank() == 0 else None, nbytes, self.ctx.device)
+        if D.rank() != 0:
+            jt = JoinTable(buf, hash_type, lo, hi, entries, inner, {})
+            jt.dense, jt.key_width, jt.n_keys = dense, kw, nk
         return jt
 
     def build_join_table(self, inner: Table, key_col: str) -> JoinTable:
@@ -430,6 +470,17 @@ class Executor:
         cache_key = (inner.name, id(inner), key_col)
         if cache_key in self.join_tables:
             return self.join_tables[cache_key]
+        if self._broadcasts_build(inner):
+            from . import distributed as D
+            jt = self._build_join_table_local(inner, key_col) if D.rank() == 0 else None
+            jt = self._broadcast_join_table(jt, inner)
+            self.join_tables[cache_key] = jt
+            return jt
+        jt = self._build_join_table_local(inner, key_col)
+        self.join_tables[cache_key] = jt
+        return jt
+
+    def _build_join_table_local(self, inner: Table, key_col: str) -> JoinTable:
         torch = self.ctx.torch
         ci = inner.columns[key_col]
         lo, hi, has_nulls = inner.join_key_range(key_col)
@@ -466,7 +517,6 @@ class Executor:
             hash_type = "OneToMany"
         jt = JoinTable(buf, hash_type, lo, hi, entries, inner, {})
         jt.dense = hash_type == "OneToOne" and not has_nulls and row == entries
-        self.join_tables[cache_key] = jt
         return jt
 
     def _linear_inner_column(self, jt: JoinTable, cname: str):
@@ -488,25 +538,61 @@ class Executor:
         if cname in jt.by_slot:
             return jt.by_slot[cname]
         torch = self.ctx.torch
-        src = self._linear_inner_column(jt, cname)
         width = jt.inner_table.columns[cname].phys_width
         out = torch.empty(max(jt.entry_count, 1) * width, dtype=torch.uint8, device=self.ctx.device)
         if jt.bitmap is None:
             jt.bitmap = torch.empty((jt.entry_count + 31) // 32 + 1, dtype=torch.int32, device=self.ctx.device)
-        _lib.check(self.lib.hdk_b200_gather_join_payload_on_device(jt.buffer.data_ptr(), jt.entry_count, src.data_ptr(), width,
-                                                                   out.data_ptr(), jt.bitmap.data_ptr(), self.ctx.stream_ptr()),
-                   "gather_join_payload")
+        bcast = self._broadcasts_build(jt.inner_table)
+        if bcast:
+            from . import distributed as D
+        if not bcast or D.rank() == 0:
+            src = self._linear_inner_column(jt, cname)
+            _lib.check(self.lib.hdk_b200_gather_join_payload_on_device(jt.buffer.data_ptr(), jt.entry_count, src.data_ptr(), width,
+                                                                       out.data_ptr(), jt.bitmap.data_ptr(), self.ctx.stream_ptr()),
+                       "gather_join_payload")
+        if bcast:
+            import torch.distributed as dist
+            dist.broadcast(out, src=0)
+            dist.broadcast(jt.bitmap, src=0)
         jt.by_slot[cname] = out
         return out
 
     # -- one work unit ---------------------------------------------------------------------
+    def _runs_distributed(self, table: Table) -> bool:
+        from . import distributed as D
+        return bool(self.distributed and table.shard is not None and D.is_dist() and D.world() > 1)
+
+    def _global_col_stats(self, table: Table, col: str):
+        """Chunk statistics over ALL ranks' shards of a table (they pick perfect vs baseline hash and the key ranges, so
+        every rank must plan with the same ones).  Collective; cached per table object."""
+        import torch.distributed as dist
+        key = (id(table), col)
+        if key not in self._global_stats:
+            gathered = [None] * dist.get_world_size()
+            dist.all_gather_object(gathered, table.col_stats(col))
+            los = [g[0] for g in gathered if g[0] is not None]
+            his = [g[1] for g in gathered if g[1] is not None]
+            self._global_stats[key] = (min(los) if los else None, max(his) if his else None, any(g[2] for g in gathered), table)
+        return self._global_stats[key][:3]
+
+    def _global_num_rows(self, table: Table) -> int:
+        import torch.distributed as dist
+        key = (id(table), None)
+        if key not in self._global_stats:
+            gathered = [None] * dist.get_world_size()
+            dist.all_gather_object(gathered, int(table.num_rows))
+            self._global_stats[key] = (sum(gathered), None, None, table)
+        return self._global_stats[key][0]
+
     def _col_stats(self, unit: ir.ExecutionUnit):
         tables = [self.storage.get_table(unit.table)] + [self.storage.get_table(j.inner_table) for j in unit.joins]
-        return lambda tidx, col: tables[tidx].col_stats(col)
+        return lambda tidx, col: (self._global_col_stats(tables[tidx], col) if self._runs_distributed(tables[tidx])
+                                  else tables[tidx].col_stats(col))
 
     def plan(self, unit: ir.ExecutionUnit, max_groups_buffer_entry_count=None, output_columnar=None) -> planner.PlannedQuery:
         outer = self.storage.get_table(unit.table)
-        pq = planner.build_query(unit, self._col_stats(unit), outer.num_rows, self.config,
+        n_rows = self._global_num_rows(outer) if self._runs_distributed(outer) else outer.num_rows
+        pq = planner.build_query(unit, self._col_stats(unit), n_rows, self.config,
                                  max_groups_buffer_entry_count=max_groups_buffer_entry_count,
                                  output_columnar=output_columnar)
         return pq
@@ -659,6 +745,7 @@ class Executor:
         publish to every rank + wait / merge / finalize, no NCCL call.  `xchg`: distributed.PeerExchange of this plan."""
         st = self.ctx.stream_ptr()
         info = abi.LaunchInfo()
+        prep["err"].zero_()
         need = prep["scratch_bytes"] + 80
         if prep["scratch"].numel() < need:
             prep["scratch"] = self.ctx.get_scratch(need)
@@ -829,11 +916,159 @@ class Executor:
         _lib.check(self.lib.hdk_b200_gather_rows(in_ptrs, out_ptrs, T, perm.data_ptr(), n_out, self.ctx.stream_ptr()), "gather_rows")
         return out
 
+    # -- one query across all ranks (one process per GPU) ------------------------------------------------------------
+    def _exchange_for(self, pq):
+        """PeerExchange buffers for this plan's work table, shared by every plan of the same shape (collective on first
+        use).  None when peer memory is not available on this box: the caller falls back to NCCL all-reduce."""
+        import torch.distributed as dist
+
+        from . import distributed as D
+        wl = self.work_table_layout(pq)
+        key = (int(wl.n_cells), int(wl.sum_i64_cells), int(wl.sum_cells), int(wl.min_cells), int(wl.max_cells))
+        if self._peer_ok is False:
+            return None
+        if key not in self._exchanges:
+            ok, x = 1, None
+            try:
+                x = D.PeerExchange(self.lib, pq.plan, pq.qmd, self.ctx.device)
+            except Exception:      # every rank must take the same path
+                ok = 0
+            flag = self.ctx.torch.tensor([ok], dtype=self.ctx.torch.int32, device=self.ctx.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self._peer_ok = False
+                return None
+            self._peer_ok = True
+            self._exchanges[key] = x
+        return self._exchanges[key]
+
+    def _agree_on_error(self, err):
+        """One in-band code for all ranks: a positive (persistent) code wins over a negative (out of slots) one."""
+        import torch.distributed as dist
+        t = self.ctx.torch
+        v = int(err.item())
+        both = t.tensor([max(v, 0), max(-v, 0)], dtype=t.int32, device=self.ctx.device)
+        dist.all_reduce(both, op=dist.ReduceOp.MAX)
+        pos, neg = int(both[0].item()), int(both[1].item())
+        return pos if pos else -neg
+
+    def _gather_rows(self, cols, n: int):
+        """Compacted result rows of every rank, concatenated on every rank: device int64 [T, total]."""
+        import torch.distributed as dist
+        t = self.ctx.torch
+        W = dist.get_world_size()
+        counts = [None] * W
+        dist.all_gather_object(counts, int(n))
+        m = max(max(counts), 1)
+        T = cols.shape[0]
+        mine = t.zeros((T, m), dtype=t.int64, device=self.ctx.device)
+        mine[:, :n] = cols[:, :n]
+        parts = [t.empty_like(mine) for _ in range(W)]
+        dist.all_gather(parts, mine)
+        return t.cat([p_[:, :c] for p_, c in zip(parts, counts)], dim=1), sum(counts)
+
+    def _execute_distributed(self, unit: ir.ExecutionUnit, output_columnar=None) -> ResultSet:
+        """Executor::executeWorkUnitImpl across devices (QE/Execute.cpp:2656-2805 creates one kernel per device and
+        reduceMultiDeviceResultSets merges on the host, :1224-1336; partitioned aggregation is RelAlgExecutor.cpp:691-838).
+        Here every rank scans its shard; what merges them is picked from the plan:
+          perfect hash  → neutral partial tables merged inside the kernels over peer memory (NCCL all-reduce as fallback)
+          baseline hash → rows re-partitioned by key hash (count → scatter straight into the owners' buffers), aggregated
+                          by their owner, the disjoint results gathered
+          joins         → the build side is built once on rank 0 and broadcast (build_join_table)
+        Every rank returns the same merged ResultSet."""
+        from . import distributed as D
+        torch = self.ctx.torch
+        outer = self.storage.get_table(unit.table)
+        tables = [outer] + [self.storage.get_table(j.inner_table) for j in unit.joins]
+        dicts = {t: tables[e.table].columns[e.column].dictionary for t, e in enumerate(unit.target_exprs)
+                 if isinstance(e, ir.ColumnRef) and e.type.kind == "dict"}
+        guess = None
+        n_global = self._global_num_rows(outer)
+        for attempt in range(8):
+            pq = self.plan(unit, guess, output_columnar)
+            if pq.qmd.hash_type == abi.PERFECT_HASH:
+                prep = self.prepare(pq)
+                xchg = self._exchange_for(pq)
+                if xchg is not None:
+                    info = self.launch_exchange(pq, prep, xchg)
+                else:
+                    info = self.execute_sharded(pq, prep)
+                code = self._agree_on_error(prep["err"])
+                if code != 0:
+                    raise QueryError(code, {1: "division by zero", 7: "overflow or underflow", 1004: "a peer's partial table never arrived",
+                                            1003: "group key outside the range of the perfect-hash layout"}.get(code, "runtime error"))
+                if unit.order_by:
+                    cols, n = self.compact_on_device(pq, prep["out"], to_host=False)
+                    order = ResultSet(pq, np.zeros(0, dtype=np.uint8), dicts).order_entries()
+                    rs = ResultSet.from_compact(pq, self.sort_on_device(cols, n, order, unit.limit).cpu().numpy(), dicts)
+                    rs.sorted_on_device = True
+                else:
+                    rs = ResultSet(pq, prep["out"].cpu().numpy(), dicts)
+                rs.launch_info = info
+                return rs
+            if unit.joins:
+                raise planner.UnsupportedPlan("partitioned aggregation of joined plans is not supported")
+            out, n_recv, code, info = self._partitioned_on_device(pq)
+            if code < 0:
+                cur = pq.qmd.entry_count
+                guess = min(max(cur * 4, 2 * min(n_global, cur * 8)), max(2 * n_global, 16))
+                if guess <= cur:
+                    raise QueryError(code, "ran out of slots in the group-by buffer")
+                continue
+            if code != 0:
+                raise QueryError(code, {1: "division by zero", 7: "overflow or underflow"}.get(code, "runtime error"))
+            cols, n = self.compact_on_device(pq, out, to_host=False)
+            order = ResultSet(pq, np.zeros(0, dtype=np.uint8), dicts).order_entries() if unit.order_by else None
+            if order and unit.limit is not None:       # each owner's first `limit` rows are enough for the global first `limit`
+                top = self.sort_on_device(cols, n, order, unit.limit)
+                cols, n = top, top.shape[1]
+            allc, total = self._gather_rows(cols, n)
+            if order:
+                allc = self.sort_on_device(allc, total, order, unit.limit)
+            rs = ResultSet.from_compact(pq, allc.cpu().numpy(), dicts)
+            rs.sorted_on_device = bool(order)
+            rs.launch_info = info
+            return rs
+        raise QueryError(-abi.ERR_OUT_OF_SLOTS, "ran out of slots after retries")
+
+    def _partitioned_on_device(self, pq):
+        """The shuffle of execute_partitioned with everything left on the device: (this rank's group-by buffer over the keys it
+        owns, rows received, error code agreed by all ranks, launch info)."""
+        from . import distributed as D
+        torch = self.ctx.torch
+        W = D.world()
+        prep = self.prepare(pq)
+        outer = self.storage.get_table(pq.unit.table)
+        widths = [outer.columns[c].phys_width for c in pq.columns]
+        counts = torch.zeros(W, dtype=torch.int64, device=self.ctx.device)
+        _lib.check(self.lib.hdk_b200_shuffle_count(C.byref(pq.plan), C.byref(prep["kp"]), W, counts.data_ptr(), self.ctx.stream_ptr()),
+                   "shuffle_count")
+        if self.partition_over_peer_memory and self._peer_ok is not False:
+            frag, n_recv = self._exchange_rows_over_peer_memory(pq, prep, counts, widths)
+        else:
+            from .storage import ChunkStats, Fragment
+            n_local = int(counts.sum().item())
+            offsets = torch.cumsum(counts, 0) - counts
+            cursors = torch.zeros(W, dtype=torch.int64, device=self.ctx.device)
+            send_cols = [torch.empty(max(n_local, 1) * w, dtype=torch.uint8, device=self.ctx.device) for w in widths]
+            ptrs = torch.tensor([t.data_ptr() for t in send_cols], dtype=torch.int64, device=self.ctx.device)
+            _lib.check(self.lib.hdk_b200_shuffle_scatter(C.byref(pq.plan), C.byref(prep["kp"]), W, offsets.data_ptr(), cursors.data_ptr(),
+                                                         ptrs.data_ptr(), self.ctx.stream_ptr()), "shuffle_scatter")
+            recv_cols, n_recv = D.all_to_all_rows(send_cols, counts, widths)
+            frag = Fragment(0, n_recv, 0, 0, {}, {c: ChunkStats(None, None, False) for c in pq.columns},
+                            {c: t[: n_recv * w] for c, t, w in zip(pq.columns, recv_cols, widths)})
+        prep2 = self.prepare(pq, fragments=[frag])
+        info = self.launch(pq, prep2)
+        code = self._agree_on_error(prep2["err"])
+        return prep2["out"], n_recv, code, info
+
     def execute_work_unit(self, unit: ir.ExecutionUnit, output_columnar=None, ko=None) -> ResultSet:
         """Executor::executeWorkUnit with the out-of-slots retry of RelAlgExecutor::executeWorkUnit
         (QE/RelAlgExecutor.cpp:1544-1566: on ERR_OUT_OF_SLOTS re-run with 2 × the cardinality estimate)."""
         guess = None
         outer = self.storage.get_table(unit.table)
+        if self._runs_distributed(outer):
+            return self._execute_distributed(unit, output_columnar)
         for attempt in range(8):
             pq = self.plan(unit, guess, output_columnar)
             prep = self.prepare(pq)

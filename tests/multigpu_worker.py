@@ -91,8 +91,39 @@ def main():
     dist.all_reduce(tot)
     assert int(tot.item()) == n
     dist.barrier()
+    # (3) the public API: hdk.sql() over a sharded table picks the multi-GPU strategy itself (perfect hash → merge over peer
+    #     memory, baseline hash → key-hash shuffle, join → build once + broadcast) and returns the merged result on every
+    #     rank — the shapes of the five named configs against SQLite on the union of all shards
+    import hdk_b200.hdk as hdk_mod
+    t2 = t.append_column("ts", pa.array((rng.integers(1230768000, 1467331200, n) * 1000).astype("datetime64[ms]")))
+    h = hdk_mod.init(device=local)
+    h.import_arrow(t2, "t", fragment_size=10_000, shard=(rank, world))
+    h.import_arrow(dim, "dim")
+    tables = {"t": t2, "dim": dim}
+    api_queries = [
+        ("SELECT k, COUNT(*), SUM(v), MIN(v), MAX(v) FROM t GROUP BY k", 1),                                                  # config 1
+        ("SELECT s, AVG(f) FROM t GROUP BY s", 1),                                                                            # taxi Q2
+        ("SELECT s, EXTRACT(YEAR FROM ts) AS y, COUNT(*) FROM t GROUP BY s, y", 2),                                           # taxi Q3
+        ("SELECT s, SUM(f), SUM(f * (1 - f / 1000)), AVG(f), COUNT(*) FROM t WHERE k <= 400 GROUP BY s", 1),                  # TPC-H Q1 shape
+        ("SELECT big, s, SUM(v), COUNT(*) FROM t GROUP BY big, s", 2),                                                        # config 4
+        ("SELECT dim.attr, SUM(t.f), COUNT(*) FROM t JOIN dim ON t.fk = dim.pk GROUP BY dim.attr", 1),                        # config 5
+        ("SELECT big, COUNT(*) AS c, SUM(v) AS sv FROM t GROUP BY big ORDER BY c DESC, big LIMIT 7", 0),                      # baseline + top-k
+    ]
+    for text, nk in api_queries:
+        order = (" ORDER BY " + ", ".join(str(i + 1) for i in range(nk))) if nk else ""
+        got = [tuple(r.values()) for r in h.sql(text + order).to_arrow().to_pylist()]
+        text_sqlite = text.replace("EXTRACT(YEAR FROM ts)", "CAST(strftime('%Y', ts) AS INT)")
+        exp = util.sqlite_rows(tables, text_sqlite + order, nk)
+        if nk == 0:
+            exp = [tuple(r) for r in exp]
+            got_s, exp_s = got, sorted(exp, key=lambda r: (-r[1], r[0]))
+            util.assert_rows_equal(got_s, exp_s, rel=1e-9)
+        else:
+            util.assert_rows_equal(got, exp, rel=1e-9)
+    strategies = h.executor._peer_ok
+    dist.barrier()
     if rank == 0:
-        print(f"MULTIGPU OK world={world}")
+        print(f"MULTIGPU OK world={world} (hdk.sql across ranks: {len(api_queries)} queries, peer memory {'on' if strategies else 'off'})")
     dist.destroy_process_group()
 
 

@@ -15,6 +15,6 @@ def test_two_rank_sharded_and_partitioned_group_by():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29531", os.path.join(ROOT, "tests", "multigpu_worker.py")], capture_output=True, text=True, timeout=600)
+                        "--master-port", "29531", os.path.join(ROOT, "tests", "multigpu_worker.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTIGPU OK world=2" in r.stdout
