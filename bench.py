@@ -241,102 +241,44 @@ def _quiet_stdout():
     os.dup2(2, 1)
 
 
-def main():
-    _quiet_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=1_100_000_000, help="rows per GPU (weak scaling)")
-    ap.add_argument("--cpu-sample-rows", type=int, default=48_000_000)
-    ap.add_argument("--cpu-repeats", type=int, default=0, help="0 = repeat until ~10 s of CPU work")
-    ap.add_argument("--e2e-rows", type=int, default=128_000_000)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--merge", choices=["p2p", "nccl"], default="p2p",
-                    help="N > 1: merge partial tables inside the kernels over peer memory (default) or with NCCL all-reduce")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+class TaxiRun:
+    """Q1-Q4 over one taxi-shaped table sharded over the ranks: plans, buffers, merge path, one step."""
 
-    import torch
-    import torch.distributed as dist
-    import benchdata
-    from hdk_b200 import _lib, abi, distributed as D, sql
-    from hdk_b200.executor import Executor
-    from hdk_b200.storage import ArrowStorage
+    def __init__(self, st, ex, device, world, merge, torch, dist, D, L):
+        import benchdata
+        from hdk_b200 import abi, sql
+        self.ex, self.device, self.world, self.torch, self.dist, self.D, self.L = ex, device, world, torch, dist, D, L
+        self.qnames = ["q1", "q2", "q3", "q4"]
+        self.pqs, self.preps, self.layouts, self.xchg = {}, {}, {}, {}
+        for q in self.qnames:
+            pq = ex.plan(sql.parse(benchdata.TAXI_QUERIES[q], st.tables))     # (statistics are global: Executor._global_col_stats)
+            assert pq.qmd.hash_type == abi.PERFECT_HASH
+            self.pqs[q] = pq
+            self.preps[q] = ex.prepare(pq)
+            self.preps[q]["scratch"] = torch.empty(self.preps[q]["scratch_bytes"] + 128, dtype=torch.uint8, device=device)  # one work table per query
+            self.layouts[q] = ex.work_table_layout(pq)
+        self.merge = merge if world > 1 else "none"
+        if self.merge == "p2p":
+            ok = 1
+            try:
+                for q in self.qnames:
+                    self.xchg[q] = D.PeerExchange(L, self.pqs[q].plan, self.pqs[q].qmd, device)
+            except Exception as e:   # no peer access on this box: every rank must take the same path
+                print(f"[bench] peer exchange unavailable: {e}", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self.merge = "nccl"
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.gpus != world:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    L = _lib.lib()
-
-    # ---- data: this rank's shard, generated on the device, resident in HBM before timing
-    st = ArrowStorage()
-    t_gen = time.perf_counter()
-    benchdata.make_taxi(st, device, args.rows, rank=rank)
-    torch.cuda.synchronize()
-    gen_s = time.perf_counter() - t_gen
-    ex = Executor(st, device=local_rank)
-    qnames = ["q1", "q2", "q3", "q4"]
-    plans = {}
-    for q in qnames:
-        plans[q] = sql.parse(benchdata.TAXI_QUERIES[q], st.tables)
-    # global statistics so that all ranks agree on the perfect-hash ranges
-    if world > 1:
-        tab = st.get_table("trips")
-        for cname, ci in tab.columns.items():
-            lo, hi, hn = tab.col_stats(cname)
-            tt = torch.tensor([float(lo), -float(hi)], dtype=torch.float64, device=device)
-            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
-            glo, ghi = tt[0].item(), -tt[1].item()
-            for f in tab.fragments:
-                f.stats[cname].min = glo if ci.type.is_fp else int(glo)
-                f.stats[cname].max = ghi if ci.type.is_fp else int(ghi)
-    pqs, preps, layouts = {}, {}, {}
-    for q in qnames:
-        pq = ex.plan(plans[q])
-        assert pq.qmd.hash_type == abi.PERFECT_HASH
-        pqs[q] = pq
-        preps[q] = ex.prepare(pq)
-        preps[q]["scratch"] = torch.empty(max(preps[q]["scratch_bytes"], 8), dtype=torch.uint8, device=device)  # one work table per query
-        layouts[q] = ex.work_table_layout(pq)
-    stream_ptr = ex.ctx.stream_ptr()
-
-    # multi-GPU merge of the partial tables: the library's own exchange over peer memory (NVLink stores + flags inside
-    # the scan / finalize kernels, hdk_b200_launch_exchange) or, as the fallback / comparison, NCCL all-reduce
-    merge = args.merge if world > 1 else "none"
-    xchg = {}
-    if merge == "p2p":
-        ok = 1
-        try:
-            for q in qnames:
-                preps[q]["scratch"] = torch.empty(preps[q]["scratch_bytes"] + 128, dtype=torch.uint8, device=device)
-                xchg[q] = D.PeerExchange(L, pqs[q].plan, pqs[q].qmd, device)
-        except Exception as e:   # no peer access on this box: every rank must take the same path
-            print(f"[bench] peer exchange unavailable on rank {rank}: {e}", file=sys.stderr)
-            ok = 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            merge = "nccl"
-
-    def run_query(q, ev=None):
-        pq, prep = pqs[q], preps[q]
-        if merge == "p2p":
+    def run_query(self, q, ev=None):
+        from hdk_b200 import _lib, abi
+        pq, prep, ex, L = self.pqs[q], self.preps[q], self.ex, self.L
+        stream_ptr = ex.ctx.stream_ptr()
+        if self.merge == "p2p":
             if ev is not None:
                 ev[0].record()
-            info = ex.launch_exchange(pq, prep, xchg[q])
+            info = ex.launch_exchange(pq, prep, self.xchg[q])
             if ev is not None:
                 ev[1].record()
             return info
@@ -348,66 +290,206 @@ def main():
                                              stream_ptr, C.byref(info)), "launch_partial")
         if ev is not None:
             ev[1].record()
-        wl = layouts[q]
-        D.allreduce_work_table(prep["scratch"], wl.n_cells, wl.sum_i64_cells, wl.sum_cells, wl.min_cells, wl.max_cells)
+        wl = self.layouts[q]
+        self.D.allreduce_work_table(prep["scratch"], wl.n_cells, wl.sum_i64_cells, wl.sum_cells, wl.min_cells, wl.max_cells)
         ex.finalize(pq, prep)
         return info
 
-    def step(evs=None):
-        infos = {}
-        for q in qnames:
-            infos[q] = run_query(q, evs[q] if evs else None)
+    def step(self, evs=None):
+        return {q: self.run_query(q, evs[q] if evs else None) for q in self.qnames}
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def errors(self):
+        return max(abs(int(self.preps[q]["err"].item())) for q in self.qnames)
+
+    def warm(self, n):
+        """warm-up steps; a peer flag that never arrived is reported in band (1004): fall back to NCCL on every rank"""
+        torch, dist = self.torch, self.dist
+        for _ in range(n):
+            infos = self.step()
+        self.barrier()
+        if self.merge == "p2p":
+            bad = torch.tensor([self.errors()], dtype=torch.int32, device=self.device)
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if int(bad.item()) != 0:
+                print(f"[bench] peer exchange reported {int(bad.item())}; using NCCL all-reduce", file=sys.stderr)
+                self.merge = "nccl"
+                for q in self.qnames:
+                    self.preps[q]["err"].zero_()
+                for _ in range(n):
+                    infos = self.step()
+                self.barrier()
+        assert self.errors() == 0, "in-band error"
         return infos
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def timed(self, steps, sampler=None, with_kernel_events=False):
+        torch = self.torch
+        kev = [{q: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for q in self.qnames}
+               for _ in range(steps)] if with_kernel_events else None
+        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        if sampler:
+            sampler.mark(True)
+        e_start.record()
+        for s in range(steps):
+            self.step(kev[s] if kev else None)
+        e_end.record()
+        self.barrier()
+        if sampler:
+            sampler.mark(False)
+        assert self.errors() == 0, "in-band error inside the timed region"
+        tt = torch.tensor([e_start.elapsed_time(e_end)], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+        return tt.item(), kev
 
-    for _ in range(max(args.warmup, 3)):
-        infos = step()
-    barrier()
-    if merge == "p2p":
-        # a peer flag that never arrived is reported in band (1004): fall back to NCCL on every rank rather than fail
-        bad = torch.tensor([max(int(preps[q]["err"].item()) for q in qnames)], dtype=torch.int32, device=device)
-        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-        if int(bad.item()) != 0:
-            print(f"[bench] peer exchange reported {int(bad.item())}; using NCCL all-reduce", file=sys.stderr)
-            merge = "nccl"
-            for q in qnames:
-                preps[q]["err"].zero_()
-            for _ in range(max(args.warmup, 3)):
-                infos = step()
-            barrier()
-    for q in qnames:
-        assert int(preps[q]["err"].item()) == 0, f"{q}: in-band error"
+    def parity_check(self, tab, total_rows):
+        """The merged results of the last step against size-independent properties (the reference's own
+        multi-fragment / partitioned tests compare with SQLite, PartitionedGroupByTest.cpp:80-139):
+        sum of Q1 counts == rows over all ranks; Q2's AVG per passenger_count == all-reduced torch sums / counts (1e-9);
+        Q3 summed over the years == those counts; Q4 summed over the distances == Q3; every rank holds identical bytes."""
+        torch, dist, ex, dev = self.torch, self.dist, self.ex, self.device
+        cols = {}
+        for q in self.qnames:
+            c, n = ex.compact_on_device(self.pqs[q], self.preps[q]["out"], to_host=False)
+            cols[q] = c[:, :n]
+        problems = []
+        if int(cols["q1"][1].sum()) != total_rows:
+            problems.append(f"sum of Q1 counts {int(cols['q1'][1].sum())} != {total_rows} rows")
+        exp = torch.zeros(2, 10, dtype=torch.float64, device=dev)
+        for f in tab.fragments:
+            pc = f.device_chunks["passenger_count"].view(torch.int16).to(torch.int64)
+            exp[0].scatter_add_(0, pc, f.device_chunks["total_amount"].view(torch.float64))
+            exp[1] += torch.bincount(pc, minlength=10).to(torch.float64)
+        if self.world > 1:
+            dist.all_reduce(exp)
+        o2 = torch.argsort(cols["q2"][0])
+        present = exp[1] > 0
+        if not torch.equal(cols["q2"][0][o2], torch.nonzero(present).flatten()):
+            problems.append("Q2 group keys")
+        elif not torch.allclose(cols["q2"][1][o2].view(torch.float64), (exp[0] / exp[1])[present], rtol=1e-9, atol=0):
+            problems.append("Q2 AVG(total_amount) per passenger_count beyond 1e-9")
+        m3 = torch.zeros(10, dtype=torch.int64, device=dev).scatter_add_(0, cols["q3"][0], cols["q3"][2])
+        if not torch.equal(m3, exp[1].to(torch.int64)):
+            problems.append("Q3 summed over the years != rows per passenger_count")
+        k3 = cols["q3"][0] * 10000 + cols["q3"][1]
+        k4 = cols["q4"][0] * 10000 + cols["q4"][1]
+        u3, inv3 = torch.unique(k3, return_inverse=True)
+        pos = torch.searchsorted(u3, k4)
+        if int(pos.max()) >= u3.numel() or not torch.equal(u3[pos], k4):
+            problems.append("Q4 has a (passenger_count, year) Q3 lacks")
+        else:
+            m4 = torch.zeros(u3.numel(), dtype=torch.int64, device=dev).scatter_add_(0, pos, cols["q4"][3])
+            c3 = torch.zeros(u3.numel(), dtype=torch.int64, device=dev).scatter_add_(0, inv3, cols["q3"][2])
+            if not torch.equal(m4, c3):
+                problems.append("Q4 summed over the distances != Q3")
+        if self.world > 1:
+            for q in self.qnames:
+                b = self.preps[q]["out"]
+                d = b[: b.numel() // 8 * 8].view(torch.int64).sum().reshape(1)
+                lo, hi = d.clone(), d.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                if int(lo.item()) != int(hi.item()):
+                    problems.append(f"{q}: ranks hold different merged buffers")
+        bad = torch.tensor([len(problems)], dtype=torch.int32, device=dev)
+        if self.world > 1:
+            dist.all_reduce(bad)
+        if int(bad.item()) == 0:
+            return "ok"
+        return "FAILED: " + ("; ".join(problems) if problems else "on another rank")
+
+    def close(self):
+        for x in self.xchg.values():
+            x.close()
+
+
+def measure_pcie(torch, device, nbytes=1 << 30, reps=3):
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = None
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        e0.record()
+        dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return nbytes / (best * 1e-3) / 1e9
+
+
+def main():
+    _quiet_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=1_100_000_000, help="rows per GPU (weak scaling)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=48_000_000)
+    ap.add_argument("--cpu-repeats", type=int, default=0, help="0 = repeat until ~10 s of CPU work")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows per GPU of the end-to-end leg (0 = the whole table at N = 1, a host-RAM-bounded share at N > 1)")
+    ap.add_argument("--e2e-host-gb", type=float, default=72.0, help="pinned host memory the end-to-end legs of all ranks may use together")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the other named configs (C1, TPC-H Q1, C4, C5; at N > 1: C4 and C5 across ranks)")
+    ap.add_argument("--per-config-scale", type=float, default=1.0, help="N = 1: scale of the other configs' row counts (1.0 = BASELINE.json's sizes)")
+    ap.add_argument("--multi-scale", type=float, default=0.25, help="N > 1: rows per GPU of C4 / C5 as a fraction of BASELINE.json's totals")
+    ap.add_argument("--merge", choices=["p2p", "nccl"], default="p2p",
+                    help="N > 1: merge partial tables inside the scan / finalize kernels over peer memory (default) or with NCCL all-reduce")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import benchdata
+    from hdk_b200 import _lib, abi, distributed as D, sql
+    from hdk_b200.executor import Executor
+    from hdk_b200.storage import ArrowStorage, Fragment
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    L = _lib.lib()
+    warmup = max(args.warmup, 3)
+
+    # ---- data: this rank's shard, generated on the device, resident in HBM before timing
+    st = ArrowStorage()
+    t_gen = time.perf_counter()
+    tab = benchdata.make_taxi(st, device, args.rows, rank=rank)
+    tab.shard = (rank, world)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t_gen
+    ex = Executor(st, device=local_rank)
+    run = TaxiRun(st, ex, device, world, args.merge, torch, dist, D, L)
+    qnames = run.qnames
+    infos = run.warm(warmup)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    kernel_events = [{q: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for q in qnames}
-                     for _ in range(args.steps)]
     launches0 = L.hdk_b200_launch_count()
-    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    sampler.mark(True)
-    e_start.record()
-    for s in range(args.steps):
-        step(kernel_events[s])
-    e_end.record()
-    barrier()
-    sampler.mark(False)
+    elapsed_ms, kernel_events = run.timed(args.steps, sampler if rank == 0 else None, with_kernel_events=True)
     launches = L.hdk_b200_launch_count() - launches0
-    for q in qnames:
-        assert int(preps[q]["err"].item()) == 0, f"{q}: in-band error {int(preps[q]['err'].item())} inside the timed region"
     clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = e_start.elapsed_time(e_end)
-    tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    elapsed_ms = tt.item()
-    rows_rank = st.get_table("trips").num_rows
+    rows_rank = tab.num_rows
     value = 4.0 * rows_rank * world * args.steps / (elapsed_ms * 1e-3)
+    parity = run.parity_check(tab, rows_rank * world)
 
     # per-query scan-kernel durations (CUDA events on the launching stream, inside the timed region)
     peak, peak_src = measured_peak()
@@ -418,7 +500,7 @@ def main():
         gbs = bytes_alg / (ms * 1e-3) / 1e9
         per_query[q] = {"scan_kernel_ms": ms, "rows_per_s": rows_rank / (ms * 1e-3), "bytes_per_row": benchdata.TAXI_BYTES_PER_ROW[q],
                         "achieved_gbs": gbs, "frac_of_measured_peak": gbs / peak, "frac_of_nominal_8TBs": gbs / NOMINAL_HBM_GBS,
-                        "strategy": int(infos[q].strategy), "entry_count": int(pqs[q].qmd.entry_count),
+                        "strategy": int(infos[q].strategy), "entry_count": int(run.pqs[q].qmd.entry_count),
                         "grid": int(infos[q].grid), "smem_bytes": int(infos[q].smem_bytes)}
     dominant = max(qnames, key=lambda q: per_query[q]["scan_kernel_ms"])
     dq = per_query[dominant]
@@ -441,29 +523,55 @@ def main():
                 (sum(per_query[q]["scan_kernel_ms"] for q in qnames) * 1e-3) / peak}
 
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64/f64", "data": "synthetic",
         "config": {"workload": "NYC-taxi-shaped synthetic table, taxi benchmark Q1-Q4 (BASELINE.json configs[1])",
                    "rows_per_gpu": rows_rank, "total_rows": rows_rank * world, "fragment_rows": benchdata.FRAGMENT_ROWS,
                    "queries": 4, "parallelism": f"fragments sharded per GPU x{world}; perfect-hash partials merged " +
                    ({"p2p": "inside the scan / finalize kernels over peer memory (NVLink stores + flags, no NCCL on the data path)",
-                     "nccl": "by NCCL all-reduce", "none": "locally (one GPU)"}[merge]),
-                   "merge": merge,
+                     "nccl": "by NCCL all-reduce", "none": "locally (one GPU)"}[run.merge]),
+                   "merge": run.merge,
                    "l2": "inputs (4.4-19.8 GB per query) are larger than the 126 MB L2", "data_gen_s": gen_s},
-        "roofline": roofline, "per_query": per_query, "gpu_launches": int(launches),
+        "roofline": roofline, "per_query": per_query, "gpu_launches": int(launches), "parity_check": parity,
     }
     if rank == 0:
         out["clocks"] = clocks
+    run.close()
 
-    # ---- e2e: the public API (Executor.execute_work_unit = what hdk.sql() runs) with HOST-resident chunks:
-    #      every query copies its columns from pinned host memory, launches, reads the result back and decodes it
+    # ---- strong scaling (north_star: "scales at least 6x from 1 to 8 GPUs on the billion-row configs"): the SAME 1.1 B-row
+    #      table spread over the N GPUs, same queries, same merge
+    if world > 1:
+        del run, ex
+        st.drop_table("trips")
+        del tab, st
+        torch.cuda.empty_cache()
+        st_s = ArrowStorage()
+        rows_s = args.rows // world
+        tab_s = benchdata.make_taxi(st_s, device, rows_s, rank=rank)
+        tab_s.shard = (rank, world)
+        ex_s = Executor(st_s, device=local_rank)
+        run_s = TaxiRun(st_s, ex_s, device, world, args.merge, torch, dist, D, L)
+        run_s.warm(warmup)
+        ms_s, _ = run_s.timed(args.steps)
+        out["strong_scaling"] = {"total_rows": rows_s * world, "rows_per_gpu": rows_s, "ms_per_step": ms_s / args.steps,
+                                 "value": 4.0 * rows_s * world * args.steps / (ms_s * 1e-3), "unit": UNIT, "merge": run_s.merge,
+                                 "parity_check": run_s.parity_check(tab_s, rows_s * world),
+                                 "note": "fixed total size: divide by the N = 1 line's `value` (same box) for the speed-up"}
+        run_s.close()
+        st, tab, ex = st_s, tab_s, ex_s
+        del run_s
+
+    # ---- e2e: the public API with HOST-resident chunks.  Executor.execute_streamed = one pass over the table's fragments for
+    #      Q1-Q4, the H2D copy of fragment f + 1 (pinned memory, copy stream) overlapping the kernels of fragment f; results
+    #      merged across ranks (N > 1), read back and decoded.  PCIe is its roof: reported beside it.
     if not args.no_e2e:
-        e2e_rows = min(args.e2e_rows, rows_rank)
-        tab = st.get_table("trips")
+        host_budget = int(args.e2e_host_gb * 1e9)
+        bytes_per_row = 30                     # the five taxi columns
+        e2e_rows = args.e2e_rows or min(tab.num_rows, host_budget // (bytes_per_row * world))
+        e2e_rows = min(e2e_rows, tab.num_rows)
         n_frag = max(1, (e2e_rows + benchdata.FRAGMENT_ROWS - 1) // benchdata.FRAGMENT_ROWS)
         st2 = ArrowStorage()
-        from hdk_b200.storage import Fragment
         frs = []
         for f in tab.fragments[:n_frag]:
             pinned = {c: torch.empty(d.numel(), dtype=torch.uint8).pin_memory() for c, d in f.device_chunks.items()}
@@ -473,24 +581,27 @@ def main():
             nf.pinned = pinned
             frs.append(nf)
         torch.cuda.synchronize()
-        st2.add_device_table("trips", tab.columns, frs)
+        st2.add_device_table("trips", tab.columns, frs, shard=(rank, world))
+        st.drop_table("trips")
+        del tab
+        torch.cuda.empty_cache()
         ex2 = Executor(st2, device=local_rank, hot_data=False)
-        units = {q: sql.parse(benchdata.TAXI_QUERIES[q], st2.tables) for q in qnames}
+        units = [sql.parse(benchdata.TAXI_QUERIES[q].split(" ORDER BY")[0], st2.tables) for q in qnames]
         e2e_rows = sum(f.num_rows for f in frs)
+        pcie = measure_pcie(torch, device)
 
         def e2e_step():
             d2h = 0
-            with ex2.ctx.batch():   # the four queries of a step share one host → device copy of each column they read
-                for q in qnames:
-                    rs = ex2.execute_work_unit(units[q])
-                    rs.row_count()
-                    d2h += rs.buffer.nbytes + 4
+            for rs in ex2.execute_streamed(units):
+                rs.row_count()
+                d2h += rs.buffer.nbytes + 4
             return d2h
-        for _ in range(2):
-            e2e_step()
-        barrier()
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         ex2.ctx.h2d_bytes = 0
-        k = max(2, min(args.steps, 5))
+        k = 3
         t0 = time.perf_counter()
         d2h = 0
         for _ in range(k):
@@ -500,10 +611,38 @@ def main():
         tt = torch.tensor([dt], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        out["e2e"] = {"value": 4.0 * e2e_rows * world * k / tt.item(), "unit": UNIT, "h2d_bytes_per_step": ex2.ctx.h2d_bytes // k,
-                      "d2h_bytes_per_step": int(d2h), "rows_per_gpu": e2e_rows, "steps": k,
-                      "path": "Executor.execute_work_unit (hdk.sql) x Q1-Q4 per step: pinned host chunks -> H2D (each referenced column once per step) -> init+scan+finalize -> D2H buffer + error code -> ResultSet decode"}
+        h2d = ex2.ctx.h2d_bytes // k
+        out["e2e"] = {"value": 4.0 * e2e_rows * world * k / tt.item(), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": int(d2h), "rows_per_gpu": e2e_rows, "total_rows": e2e_rows * world, "steps": k,
+                      "pcie_gbs": pcie, "h2d_gbs_per_gpu": h2d / (tt.item() / k) / 1e9, "frac_of_pcie": h2d / (tt.item() / k) / 1e9 / pcie,
+                      "whole_table": bool(e2e_rows == args.rows),
+                      "path": "Executor.execute_streamed (what hdk.sql runs per query, here Q1-Q4 sharing one pass): per fragment, pinned host chunks -> H2D on a copy "
+                              "stream (each referenced column once) overlapping the previous fragment's scan kernels -> " +
+                              ("work tables merged across ranks (NCCL all-reduce) -> " if world > 1 else "") +
+                              "finalize -> D2H buffer + error code -> ResultSet decode",
+                      "note": "PCIe-bound: pcie_gbs = measured pinned H2D copy bandwidth of this GPU (1 GiB, best of 3); N > 1: the ranks share the host's "
+                              "memory and PCIe complex" + ("" if e2e_rows == args.rows else f"; rows per GPU bounded by --e2e-host-gb {args.e2e_host_gb:g} of pinned host memory")}
         del ex2, st2, frs
+        torch.cuda.empty_cache()
+    else:
+        st.drop_table("trips")
+        del tab
+        torch.cuda.empty_cache()
+
+    # ---- the other named configs
+    if not args.no_per_config:
+        import benchcfg
+        try:
+            if world == 1:
+                out["per_config"] = benchcfg.per_config_single_gpu(device, peak, cpu=not args.no_cpu_baseline, scale=args.per_config_scale)
+            else:
+                out["per_config"] = {
+                    "c4_baseline_hash": benchcfg.multi_c4(device, rank, world, int(1_000_000_000 * args.multi_scale),
+                                                          int(100_000_000 * args.multi_scale) * world),
+                    "c5_star_join": benchcfg.multi_c5(device, rank, world, int(2_000_000_000 * args.multi_scale))}
+        except Exception as e:   # never lose the headline line to a side measurement
+            import traceback
+            out["per_config"] = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1500:]}
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -1062,6 +1062,92 @@ class Executor:
         code = self._agree_on_error(prep2["err"])
         return prep2["out"], n_recv, code, info
 
+    def execute_streamed(self, units: List[ir.ExecutionUnit]) -> List[ResultSet]:
+        """Several perfect-hash queries over ONE host-resident table in a single pass over its fragments, the copy of
+        fragment f + 1 overlapping the kernels of fragment f (Executor::fetchChunks per fragment, QE/ExecutionKernel.cpp:
+        205-228, with the reference's one-kernel-per-fragment dispatch): a copy stream uploads each referenced column of a
+        fragment once into one of two staging sets, the compute stream scans it for every query into that query's neutral
+        work table (hdk_b200_launch_partial accumulates), the tables are finalised at the end — merged across ranks first
+        when the table is sharded.  Host chunks should be pinned (Fragment.pinned) for the copies to be asynchronous."""
+        from . import distributed as D
+        torch = self.ctx.torch
+        dev = self.ctx.device
+        outer = self.storage.get_table(units[0].table)
+        dist_run = self._runs_distributed(outer)
+        pqs = []
+        for u in units:
+            if u.table != units[0].table or u.joins:
+                raise planner.UnsupportedPlan("execute_streamed: plain group-bys over one table")
+            pq = self.plan(u)
+            if pq.qmd.hash_type != abi.PERFECT_HASH:
+                raise planner.UnsupportedPlan("execute_streamed: perfect-hash plans")
+            pqs.append(pq)
+        cols = sorted({c for pq in pqs for c in pq.columns})
+        width = {c: outer.columns[c].phys_width for c in cols}
+        frags = outer.fragments
+        max_rows = max([f.num_rows for f in frags] or [1])
+        st = getattr(self, "_stream_state", None)
+        if st is None or st["cols"] != cols or st["max_rows"] < max_rows:
+            st = dict(cols=cols, max_rows=max_rows, copy=torch.cuda.Stream(device=dev),
+                      stage=[{c: torch.empty(max_rows * width[c], dtype=torch.uint8, device=dev) for c in cols} for _ in range(2)],
+                      ready=[torch.cuda.Event() for _ in range(2)], done=[torch.cuda.Event() for _ in range(2)])
+            self._stream_state = st
+        compute = torch.cuda.current_stream(dev)
+        preps = []
+        for pq in pqs:
+            nbytes = self.lib.hdk_b200_buffer_size_bytes(C.byref(pq.qmd))
+            sb = C.c_size_t(0)
+            _lib.check(self.lib.hdk_b200_plan_check(C.byref(pq.plan), C.byref(pq.qmd), C.byref(sb)), "plan_check")
+            work = torch.empty(max(sb.value, 8), dtype=torch.uint8, device=dev)
+            out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            err = torch.zeros(1, dtype=torch.int32, device=dev)
+            kps = []
+            for slot in range(2):
+                ptrs = torch.tensor([st["stage"][slot][c].data_ptr() for c in pq.columns], dtype=torch.int64, device=dev)
+                kps.append(ptrs)
+            _lib.check(self.lib.hdk_b200_init_work_table(C.byref(pq.plan), C.byref(pq.qmd), work.data_ptr(), compute.cuda_stream), "init_work_table")
+            preps.append(dict(work=work, out=out, err=err, ptrs=kps, scratch=work))
+        rows_dev = torch.tensor([f.num_rows for f in frags] or [0], dtype=torch.int64, device=dev)
+        info = abi.LaunchInfo()
+        for fi, f in enumerate(frags):
+            slot = fi & 1
+            with torch.cuda.stream(st["copy"]):
+                if fi >= 2:
+                    st["copy"].wait_event(st["done"][slot])          # the kernels of fragment fi - 2 are done with this staging set
+                for c in cols:
+                    src = f.pinned[c] if getattr(f, "pinned", None) else torch.from_numpy(np.ascontiguousarray(f.chunks[c]).view(np.uint8).reshape(-1))
+                    st["stage"][slot][c][: src.numel()].copy_(src, non_blocking=True)
+                    self.ctx.h2d_bytes += src.numel()
+                st["ready"][slot].record(st["copy"])
+            compute.wait_event(st["ready"][slot])
+            for pq, prep in zip(pqs, preps):
+                kp = abi.KernelParams()
+                kp.col_buffers = prep["ptrs"][slot].data_ptr()
+                kp.num_fragments = 1
+                kp.num_rows = rows_dev.data_ptr() + 8 * fi
+                kp.num_tables = 1
+                kp.error_codes = prep["err"].data_ptr()
+                kp.total_rows_hint = f.num_rows
+                _lib.check(self.lib.hdk_b200_launch_partial(C.byref(pq.plan), C.byref(pq.qmd), None, C.byref(kp), prep["work"].data_ptr(),
+                                                            compute.cuda_stream, C.byref(info)), "launch_partial")
+            st["done"][slot].record(compute)
+        results = []
+        for pq, prep in zip(pqs, preps):
+            if dist_run:
+                wl = self.work_table_layout(pq)
+                D.allreduce_work_table(prep["work"], wl.n_cells, wl.sum_i64_cells, wl.sum_cells, wl.min_cells, wl.max_cells)
+                code = self._agree_on_error(prep["err"])
+            _lib.check(self.lib.hdk_b200_finalize(C.byref(pq.plan), C.byref(pq.qmd), prep["work"].data_ptr(), prep["out"].data_ptr(),
+                                                  compute.cuda_stream), "finalize")
+            if not dist_run:
+                code = int(prep["err"].item())
+            if code != 0:
+                raise QueryError(code, "runtime error")
+            rs = ResultSet(pq, prep["out"].cpu().numpy(), {})
+            rs.launch_info = info
+            results.append(rs)
+        return results
+
     def execute_work_unit(self, unit: ir.ExecutionUnit, output_columnar=None, ko=None) -> ResultSet:
         """Executor::executeWorkUnit with the out-of-slots retry of RelAlgExecutor::executeWorkUnit
         (QE/RelAlgExecutor.cpp:1544-1566: on ERR_OUT_OF_SLOTS re-run with 2 × the cardinality estimate)."""
