@@ -615,13 +615,13 @@ def main():
         out["e2e"] = {"value": 4.0 * e2e_rows * world * k / tt.item(), "unit": UNIT, "h2d_bytes_per_step": h2d,
                       "d2h_bytes_per_step": int(d2h), "rows_per_gpu": e2e_rows, "total_rows": e2e_rows * world, "steps": k,
                       "pcie_gbs": pcie, "h2d_gbs_per_gpu": h2d / (tt.item() / k) / 1e9, "frac_of_pcie": h2d / (tt.item() / k) / 1e9 / pcie,
-                      "whole_table": bool(e2e_rows == args.rows),
+                      "whole_table": bool(e2e_rows * world >= args.rows),
                       "path": "Executor.execute_streamed (what hdk.sql runs per query, here Q1-Q4 sharing one pass): per fragment, pinned host chunks -> H2D on a copy "
                               "stream (each referenced column once) overlapping the previous fragment's scan kernels -> " +
                               ("work tables merged across ranks (NCCL all-reduce) -> " if world > 1 else "") +
                               "finalize -> D2H buffer + error code -> ResultSet decode",
                       "note": "PCIe-bound: pcie_gbs = measured pinned H2D copy bandwidth of this GPU (1 GiB, best of 3); N > 1: the ranks share the host's "
-                              "memory and PCIe complex" + ("" if e2e_rows == args.rows else f"; rows per GPU bounded by --e2e-host-gb {args.e2e_host_gb:g} of pinned host memory")}
+                              "memory and PCIe complex" + ("" if e2e_rows * world >= args.rows else f"; rows per GPU bounded by --e2e-host-gb {args.e2e_host_gb:g} of pinned host memory")}
         del ex2, st2, frs
         torch.cuda.empty_cache()
     else:

@@ -161,3 +161,25 @@ def test_reduce_and_launch_with_buffers_beyond_4_gib(oracle_mod):
     exp = util.sort_rows(util.result_columns(oracle_mod, pq_small, obuf), 2)
     got = [tuple(r.values()) for r in rows_whole.to_pylist()]
     util.assert_rows_equal(got, exp)
+
+
+@pytest.mark.parametrize("config", ["c1", "c3", "c5", "c4"])
+def test_other_configs_at_baseline_size(config):
+    """BASELINE.json configs[0], [2], [4], [3] at their full sizes on one GPU (TPC-H Q1 on 600 M lineitem rows, the star join
+    on 2 B x 10 M rows, the composite-key group-by on 1 B rows / 100 M groups — through the radix-partitioned aggregation),
+    checked through size-independent properties (benchcfg.check_*): conservation of rows, per-group results against
+    independent torch reductions of the same columns (integers bit-exact, fp64 within 1e-9), checksum of keys x counts
+    modulo 2^64, no key in two entries."""
+    import torch
+    import benchcfg
+    free, _ = torch.cuda.mem_get_info()
+    if config == "c4" and free < 90e9:
+        pytest.skip("needs ~75 GB of device memory")
+    out = benchcfg.per_config_single_gpu(torch.device("cuda", 0), 6537.0, reps=1, cpu=False, only=(config,))
+    assert out, "nothing ran"
+    for name, d in out.items():
+        assert d["parity_check"].startswith("ok"), f"{name}: {d['parity_check']}"
+        assert d["precompiled_shape"], name
+    if config == "c4":
+        from hdk_b200 import abi
+        assert out["c4_baseline_hash"]["strategy"] == abi.STRATEGY_PARTITIONED

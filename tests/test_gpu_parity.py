@@ -1048,6 +1048,48 @@ def test_baseline_region_pass_does_not_change_results(oracle_mod, env, torch, id
         check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
 
 
+RING_STRESS = r"""
+import sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch
+from tests import util
+from tests.test_gpu_parity import QUERIES, gen_tables, check_against_oracle
+from oracle import oracle
+from hdk_b200 import sql
+from hdk_b200.executor import Executor
+tables = gen_tables()
+st = util.make_storage(tables, fragment_size={{"t": 7001, "dim": 100000, "dim_many": 100000}})
+n = 0
+for idx in (0, 2, 3, 4, 7, 16):
+    text, nk, kw = QUERIES[idx]
+    ex = Executor(st, kw.get("cfg"))
+    pq = ex.plan(sql.parse(text, st.tables), kw.get("max_groups_buffer_entry_count"), kw.get("output_columnar"))
+    prep = ex.prepare(pq)
+    info = ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    assert info.tile_rows == {tile}, info.tile_rows
+    check_against_oracle(oracle, st, pq, prep["out"].cpu().numpy(), nk)
+    n += 1
+print("RING STRESS OK", n)
+"""
+
+
+@pytest.mark.parametrize("geo,tile", [("1,32,1,1,32", 32), ("2,64,2,1,64", 64), ("1,32,3,2,96", 96)])
+def test_stage_ring_with_one_stage_and_tiny_tiles(geo, tile):
+    """The TMA producer / consumer ring at its most fragile: ONE stage (every tile waits for the previous one to be released)
+    and tiles of one or two warps' worth of rows, thousands of mbarrier phase flips per CTA.  HDK_B200_GEO (tuning hook,
+    read once per process) forces the geometry, so the queries run in a child process; results against the oracle.
+    profiles/ holds the compute-sanitizer racecheck / memcheck logs of this very script."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HDK_B200_GEO=geo)
+    r = subprocess.run([sys.executable, "-c", RING_STRESS.format(root=root, tile=tile)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "RING STRESS OK 6" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 @pytest.fixture
 def partitioned():
     """Force the radix-partitioned baseline-hash aggregation (partagg.cu) whatever the table size; knobs reset afterwards."""
