@@ -63,13 +63,14 @@ struct DAcc {           // 4 bytes
   uint8_t bytes;        // bin width inside shared memory: 4 (counters) or 8
 };
 
-struct DKey {           // 40 bytes
+struct DKey {           // 48 bytes
   int64_t min_val;
   int64_t null_translated;  // max + (bucket ? bucket : 1)
   int64_t mult;             // Π cardinality of the previous keys
   int64_t card;             // this key's bucketed cardinality (incl. the NULL bin)
   int32_t expr;
   uint8_t has_nulls, width, pad0, pad1;
+  int64_t bucket;           // > 1: the key is (value - min) / bucket (ExpressionRange buckets: a DATE key counts days, 86400 s each)
 };
 
 struct DJoin {          // 48 bytes

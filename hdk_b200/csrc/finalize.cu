@@ -188,6 +188,9 @@ __device__ __forceinline__ void store_slot(int8_t* p, int bytes, int padded, int
   }
 }
 
+// key value of bin `comp` (the NULL bin holds max + bucket = the translated NULL, as the reference writes it)
+__device__ __forceinline__ int64_t key_of(const DKey& ky, int64_t comp) { return ky.min_val + comp * (ky.bucket ? ky.bucket : 1); }
+
 // merge of one accumulator cell over the ranks' partial tables (kMerged) or the plain work-table cell
 template <bool kMerged>
 __device__ __forceinline__ int64_t work_cell(const FinalizeArgs& a, int acc, uint64_t e) {
@@ -239,7 +242,7 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
       for (int k = 0; k < a.n_keys; ++k) comp[k] = a.n_keys == 1 ? int64_t(e) : int64_t((e / uint64_t(a.keys[k].mult)) % uint64_t(a.keys[k].card));
     if (!L.keyless && !a.baseline) {
       for (int k = 0; k < a.n_keys; ++k) {
-        const int64_t kv = empty ? HDK_B200_EMPTY_KEY_64 : a.keys[k].min_val + comp[k];
+        const int64_t kv = empty ? HDK_B200_EMPTY_KEY_64 : key_of(a.keys[k], comp[k]);
         if (L.columnar) reinterpret_cast<int64_t*>(buf + size_t(k) * ((8 * E + 7) & ~uint64_t(7)))[e] = kv;
         else reinterpret_cast<int64_t*>(row)[k] = kv;
       }
@@ -254,7 +257,7 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
           case SLOT_KEY: {
             const DKey& ky = a.keys[sl.key_index];
             const bool is_null = ky.has_nulls && comp[sl.key_index] == ky.card - 1;
-            v = is_null ? int_null_of(sl.key_width) : ky.min_val + comp[sl.key_index];
+            v = is_null ? int_null_of(sl.key_width) : key_of(ky, comp[sl.key_index]);
             break;
           }
           case SLOT_COUNT: v = work_cell<kMerged>(a, sl.acc, e); break;
@@ -273,6 +276,14 @@ __global__ void finalize_kernel(const __grid_constant__ FinalizeArgs a) {
           }
         }
       }
+      // Keyless + columnar, reference quirk: get_columnar_group_bin_offset (QE/GroupByRuntime.cpp:233-246, picked by
+      // RowFuncBuilder::codegenSingleColumnPerfectHash, QE/RowFuncBuilder.cpp:604-607) is handed the buffer's FIRST column
+      // — a slot column when there is no key column — and stores the row's (translated) key there while the cell still
+      // reads EMPTY_KEY_64.  Only an 8-byte MIN over a NOT NULL int64 starts at that pattern (INT64_MAX): the key then
+      // takes part in the minimum.  Reproduced so that the buffer stays the reference's, byte for byte.
+      if (s == 0 && !empty && L.columnar && L.keyless && a.n_keys == 1 && sl.padded == 8 && sl.init_val == HDK_B200_EMPTY_KEY_64 &&
+          sl.op == SLOT_MIN && !sl.is_fp)
+        v = min(v, key_of(a.keys[0], comp[0]));
       store_slot(p, sl.bytes, sl.padded, v);
     }
     if (!L.columnar && !a.baseline) {

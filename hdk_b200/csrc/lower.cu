@@ -202,8 +202,9 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
     d.null_translated = s.max_val + (s.bucket ? s.bucket : 1);
     d.mult = mult;
     d.card = s.cardinality;
+    d.bucket = s.bucket > 1 ? s.bucket : 0;
     if (q->hash_type == HDK_B200_PERFECT_HASH) {
-      if (s.bucket > 1) { set_error("bucketed perfect-hash keys are not supported"); return HDK_B200_E_UNSUPPORTED; }
+      if (s.bucket < 0) { set_error("key %d: negative bucket", k); return HDK_B200_E_INVALID; }
       if (s.cardinality <= 0) { set_error("key %d: bad cardinality", k); return HDK_B200_E_INVALID; }
       mult *= s.cardinality;
     }
@@ -223,7 +224,6 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
     if (q->keyless) { set_error("baseline hash cannot be keyless"); return HDK_B200_E_INVALID; }
     if (q->output_columnar && q->key_width != 8) { set_error("columnar baseline needs 8-byte keys"); return HDK_B200_E_INVALID; }
   } else { set_error("unknown hash type"); return HDK_B200_E_UNSUPPORTED; }
-  if (q->keyless && q->output_columnar) { set_error("keyless columnar output is not supported"); return HDK_B200_E_UNSUPPORTED; }
 
   // ---- layout
   L.entry_count = q->entry_count;

@@ -225,7 +225,9 @@ __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const 
         const DKey& ky = p.keys[k];
         int64_t v = vals[ky.expr].i;
         if (ky.has_nulls && v == int_null_of(ky.width)) v = ky.null_translated;
-        h += (v - ky.min_val) * ky.mult;
+        int64_t term = v - ky.min_val;
+        if (ky.bucket) term /= ky.bucket;   // (get_group_value_fast / perfect_key_hash divide by the bucket)
+        h += term * ky.mult;
       }
       idx = uint32_t(h);
       if (idx >= p.entry_count) { my_err = my_err > 0 ? my_err : 1003; continue; }  // key outside the range the layout was built for
@@ -321,7 +323,9 @@ __device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint
       const DKey& ky = rp.keys[k];
       int64_t v = vals[sp.keys[k].expr].i;
       if (sp.keys[k].has_nulls && v == int_null_of(sp.keys[k].width)) v = ky.null_translated;
-      if constexpr (k == 0) h = v - ky.min_val; else h += (v - ky.min_val) * ky.mult;
+      int64_t term = v - ky.min_val;
+      if (ky.bucket) term /= ky.bucket;     // run-time property of the key range (uniform branch, not taken for plain keys)
+      if constexpr (k == 0) h = term; else h += term * ky.mult;
     });
     idx = uint32_t(h);
     max_idx = max(max_idx, idx);   // a key outside the range the layout was built for is reported once per tile (error 1003)

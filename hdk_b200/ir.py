@@ -347,7 +347,9 @@ def expr_range(e: Expr, col_stats) -> Range:
         if e.type.is_fp:
             return Range("fp", float(lo), float(hi), hn)
         if e.type.date_in_days:
-            return Range("int", int(lo) * 86400, int(hi) * 86400, hn)
+            # a DATE column's range counts in days: bucket = 86400 s (getExpressionRange(ColumnVar), QE/ExpressionRange.cpp:
+            # 553-558 → get_conservative_datetrunc_bucket(kDay)); GROUP BY a date is then a perfect hash over the days
+            return Range("int", int(lo) * 86400, int(hi) * 86400, hn, 86400)
         return Range("int", int(lo), int(hi), hn)
     if isinstance(e, Const):
         if e.value is None or isinstance(e.value, str):

@@ -341,10 +341,9 @@ def build_query(unit: ir.ExecutionUnit, col_stats: Callable, total_tuples: int, 
             q.keyless, columnar = 1, False      # one entry, nothing to key; the row is always part of the result
             q.output_columnar = 0
             tidx = tidx if keyless else 0
-        if columnar and q.keyless:
-            # keyless + columnar drives get_columnar_group_bin_offset over a slot column in the
-            # reference (QE/RowFuncBuilder.cpp:604-607); we keep keys in that case.
-            q.keyless = 0
+        # (keyless + columnar is a layout the reference produces — MemoryLayoutBuilder.cpp:864-880 does not look at the
+        #  columnar hint — with its quirk that get_columnar_group_bin_offset then writes into the first SLOT column,
+        #  QE/RowFuncBuilder.cpp:604-607; finalize.cu reproduces it)
         q.target_idx_for_key = tidx
         q.key_width = 8
         if non_grouped:

@@ -1048,6 +1048,27 @@ def test_baseline_region_pass_does_not_change_results(oracle_mod, env, torch, id
         check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
 
 
+@pytest.mark.parametrize("text,nk,columnar,vs_sqlite", util.LAYOUT_QUERIES)
+def test_keyless_columnar_and_bucketed_layouts(oracle_mod, torch, text, nk, columnar, vs_sqlite):
+    """Keyless + columnar buffers (incl. the reference's key-in-the-first-slot-column quirk) and bucketed perfect-hash keys
+    (DATE group keys: one bin per day) on the GPU: byte-identical to the oracle where there is no fp sum."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables = util.layout_tables()
+    st = util.make_storage(tables, fragment_size=1700)
+    ex = Executor(st)
+    pq = ex.plan(sql.parse(text, st.tables), None, columnar)
+    prep = ex.prepare(pq)
+    ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), max(nk, 1))
+    # and the result side on the device (compaction of non-empty entries)
+    cols, n = ex.compact_on_device(pq, prep["out"], to_host=False)
+    obuf, _ = util.run_oracle(oracle_mod, st, pq)
+    assert n == len(util.result_columns(oracle_mod, pq, obuf)[0])
+
+
 RING_STRESS = r"""
 import sys
 sys.path.insert(0, {root!r})

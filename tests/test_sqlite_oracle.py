@@ -1023,3 +1023,41 @@ def test_reference_known_answers(oracle_mod, expected, text):
     for kind in ("port", "reference"):
         buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
         assert err == 0 and decode_with_dictionaries(st, pq, buf) == [(expected,)]
+
+
+@pytest.mark.parametrize("text,nk,columnar,vs_sqlite", util.LAYOUT_QUERIES)
+def test_keyless_columnar_and_bucketed_layouts(oracle_mod, text, nk, columnar, vs_sqlite):
+    """Layouts the reference produces and round 1 refused: keyless + columnar (MemoryLayoutBuilder.cpp:864-880 decides keyless
+    without looking at the columnar hint; the row function then calls get_columnar_group_bin_offset on the first slot
+    column, RowFuncBuilder.cpp:604-607) and bucketed perfect-hash keys (a DATE column's range counts days,
+    ExpressionRange.cpp:553-558).  The restatement and the reference runtime must agree byte for byte, and with SQLite
+    where SQLite can answer (the key-in-the-MIN-slot quirk is the reference's own)."""
+    tables = util.layout_tables()
+    st = util.make_storage(tables, fragment_size=1700)
+    pq = util.plan_sql(st, text, output_columnar=columnar)
+    from hdk_b200 import abi
+    assert pq.qmd.hash_type == abi.PERFECT_HASH and pq.qmd.output_columnar == int(columnar)
+    if columnar and " d" not in text.split("FROM")[0]:
+        assert pq.qmd.keyless == 1
+    if "GROUP BY d" in text:
+        assert pq.plan.keys[0].bucket == 86400 and pq.qmd.entry_count < (400 if nk == 1 else 400 * 70)
+    buf, err = util.run_oracle(oracle_mod, st, pq, kind="port")
+    assert err == 0
+    if oracle_mod.ref_available():
+        buf2, err2 = util.run_oracle(oracle_mod, st, pq, kind="reference")
+        assert err2 == 0 and np.array_equal(buf, buf2)
+    got = util.sort_rows(util.result_columns(oracle_mod, pq, buf), max(nk, 1))
+    if vs_sqlite:
+        order = ", ".join(str(i + 1) for i in range(nk))
+        exp = util.sqlite_rows(tables, text + " ORDER BY " + order, nk)
+        # SQLite holds the date as text ('2021-03-04'); the result column is seconds since the epoch
+        import datetime
+        conv = lambda r: tuple((int((datetime.date.fromisoformat(x) - datetime.date(1970, 1, 1)).days) * 86400 if isinstance(x, str) else x) for x in r)  # noqa: E731
+        exp = sorted([conv(r) for r in exp], key=lambda r: tuple((0, 0) if x is None else (1, x) for x in r[:nk]))
+        util.assert_rows_equal(got, exp, rel=1e-9)
+    else:
+        # every group's MIN(pos) came out as min(key, MIN(pos)): the keys 10..69 are below every pos only sometimes
+        k = tables["t"].column("k").to_numpy()
+        pos = tables["t"].column("pos").to_numpy()
+        exp = sorted((int(min(kk, pos[k == kk].min())), int((k == kk).sum()), int(pos[k == kk].sum())) for kk in np.unique(k))
+        assert sorted(got) == exp

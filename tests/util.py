@@ -204,3 +204,29 @@ def wide_inner_key_tables(seed=5, n=3000):
 
 
 WIDE_INNER_KEY_QUERY = ("SELECT dim.g, COUNT(*), SUM(t.x) FROM t JOIN dim ON t.a = dim.w AND t.b = dim.b GROUP BY dim.g", 1)
+
+
+def layout_tables(seed=9, n=6000):
+    """Inputs of the layout tests: an int key (keyless + columnar layouts), a DATE key (bucketed perfect hash: one bin per
+    day) with NULLs, NOT NULL and nullable int64 arguments."""
+    import datetime
+    rng = np.random.default_rng(seed)
+    d0 = (datetime.date(2021, 3, 1) - datetime.date(1970, 1, 1)).days
+    t = pa.table({"k": rng.integers(10, 70, n).astype(np.int32),
+                  "d": pa.array((d0 + rng.integers(0, 200, n)).astype("datetime64[D]"), mask=rng.random(n) < 0.03),
+                  "pos": rng.integers(1, 5000, n),
+                  "v": pa.array(rng.integers(-1000, 1000, n), mask=rng.random(n) < 0.1),
+                  "f": rng.normal(0, 5, n)})
+    fields = [pa.field(f.name, f.type, nullable=(f.name != "pos")) for f in t.schema]
+    return {"t": pa.table([t.column(f.name) for f in fields], schema=pa.schema(fields))}
+
+
+LAYOUT_QUERIES = [
+    # (text, n_keys, columnar, compare with SQLite?)
+    ("SELECT k, COUNT(*), SUM(v), MIN(f) FROM t GROUP BY k", 1, True, True),                     # keyless + columnar
+    ("SELECT k, AVG(f), MAX(pos) FROM t WHERE v > -500 GROUP BY k", 1, True, True),              # keyless on AVG's count slot
+    ("SELECT MIN(pos), COUNT(*), SUM(pos) FROM t GROUP BY k", 0, True, False),                   # the key lands in the MIN slot (reference quirk)
+    ("SELECT d, COUNT(*), SUM(pos), MIN(v) FROM t GROUP BY d", 1, False, True),                  # DATE key: bucket = one day
+    ("SELECT d, k, COUNT(*), AVG(f) FROM t GROUP BY d, k", 2, False, True),                      # bucketed key inside a multi-key perfect hash
+    ("SELECT d, COUNT(*), MAX(f) FROM t WHERE k < 40 GROUP BY d", 1, True, True),                # bucketed + columnar
+]
