@@ -29,6 +29,7 @@ EXPORTS = [
     "hdk_b200_materialize_nulls_on_device", "hdk_b200_peer_alloc", "hdk_b200_peer_open", "hdk_b200_peer_close",
     "hdk_b200_peer_free", "hdk_b200_exchange_bytes", "hdk_b200_exchange_init", "hdk_b200_launch_exchange", "hdk_b200_query_host", "hdk_b200_last_error", "hdk_b200_abi_version",
     "hdk_b200_device_count", "hdk_b200_launch_count", "hdk_b200_launch_scratch_bytes", "hdk_b200_debug_set",
+    "hdk_b200_jit_get_stats", "hdk_b200_jit_wait",
 ]
 
 
@@ -83,6 +84,8 @@ def _bind(lib):
         "hdk_b200_launch_count": (u64, []),
         "hdk_b200_launch_scratch_bytes": (ci, [P, Q, u64, C.POINTER(sz)]),
         "hdk_b200_debug_set": (ci, [C.c_char_p, ci]),
+        "hdk_b200_jit_get_stats": (ci, [C.POINTER(abi.JitStats)]),
+        "hdk_b200_jit_wait": (ci, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -107,6 +110,13 @@ def lib():
 def debug_set(name: str, value: int):
     """hdk_b200_debug_set: process-wide debug / tuning knobs ("force_generic", "force_strategy", "partitioned_aggregation")."""
     check(lib().hdk_b200_debug_set(name.encode(), int(value)), f"debug_set({name})")
+
+
+def jit_stats() -> dict:
+    """hdk_b200_jit_get_stats as a dict (shapes compiled / failed / pending, launches on run-time compiled kernels, compile ms)."""
+    st = abi.JitStats()
+    check(lib().hdk_b200_jit_get_stats(C.byref(st)), "jit_get_stats")
+    return {f: getattr(st, f) for f, _ in abi.JitStats._fields_}
 
 
 def check(rc, what=""):

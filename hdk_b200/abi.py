@@ -91,6 +91,14 @@ class KernelParams(C.Structure):
                 ("inner_col_buffers", C.c_void_p), ("total_rows_hint", C.c_uint64)]
 
 
+class JitStats(C.Structure):
+    _fields_ = [("shapes_compiled", C.c_uint64), ("shapes_failed", C.c_uint64), ("shapes_pending", C.c_uint64), ("launches", C.c_uint64),
+                ("last_compile_ms", C.c_double), ("total_compile_ms", C.c_double), ("available", C.c_int)]
+
+
+VARIANT_JIT = 1000
+
+
 class KernelOptions(C.Structure):
     _fields_ = [("gridDimX", C.c_uint), ("gridDimY", C.c_uint), ("gridDimZ", C.c_uint), ("blockDimX", C.c_uint),
                 ("blockDimY", C.c_uint), ("blockDimZ", C.c_uint), ("sharedMemBytes", C.c_uint),

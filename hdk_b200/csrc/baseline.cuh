@@ -6,7 +6,9 @@
 //   claim          CAS on the first key component; the winner publishes the rest; others wait until
 //                  the rest is published, then compare                      (QE/cuda_mapd_rt.cu:176-236, 240-321)
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <type_traits>
+#endif
 
 #include "common.cuh"
 

@@ -1,7 +1,19 @@
 // hdk_b200/csrc/common.cuh — shared device/host definitions of the sm_100a hot-path library.
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation (jit.cu): no host headers; fixed-width types and limits from libcu++
+#include <cuda/std/cstdint>
+#include <cuda/std/climits>
+#include <cuda/std/type_traits>
+#include <cuda/std/utility>
+using cuda::std::int8_t; using cuda::std::int16_t; using cuda::std::int32_t; using cuda::std::int64_t;
+using cuda::std::uint8_t; using cuda::std::uint16_t; using cuda::std::uint32_t; using cuda::std::uint64_t; using cuda::std::uintptr_t;
+namespace std { using cuda::std::integral_constant; using cuda::std::conditional; }
+#define HDK_B200_NO_STD_HEADERS 1
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "../../include/hdk_b200.h"
 
@@ -10,6 +22,7 @@ namespace hb {
 // ---------------------------------------------------------------------------------------
 // error handling (host)
 // ---------------------------------------------------------------------------------------
+#ifndef __CUDACC_RTC__
 void set_error(const char* fmt, ...);
 extern unsigned long long g_launch_count;
 #define HB_CUDA(expr)                                                                    \
@@ -27,6 +40,7 @@ extern unsigned long long g_launch_count;
   } while (0)
 
 int sm_count();
+#endif
 
 // ---------------------------------------------------------------------------------------
 // device plan: the C-ABI plan lowered to a compact, kernel-parameter-sized form
@@ -144,8 +158,10 @@ struct Lowered {
   size_t stage_row_bytes;  // Σ physical widths of the outer columns
 };
 
+#ifndef __CUDACC_RTC__
 int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, Lowered* out);
 uint64_t plan_signature(const DPlan& p);
+#endif
 
 // ---------------------------------------------------------------------------------------
 // small device helpers

@@ -1,7 +1,9 @@
 // hdk_b200/csrc/device_utils.cuh — PTX wrappers: mbarrier, TMA bulk copy (cp.async.bulk), cache policy.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 namespace hb {
 

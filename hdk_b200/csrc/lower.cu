@@ -17,7 +17,7 @@ namespace hb {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launch_count = 0;
-DebugKnobs g_debug = {0, -1, -1, 0, 0, 0};
+DebugKnobs g_debug = {0, -1, -1, 0, 0, 0, 1};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -372,8 +372,10 @@ uint64_t plan_signature(const DPlan& p) {
   return h;
 }
 
-// C++ aggregate initialiser of the structural part of a DPlan (consumed by static_shapes.inc)
-static int dump_shape(const DPlan& p, char* out, size_t cap) {
+// C++ aggregate initialiser of the structural part of a DPlan (consumed by static_shapes.inc and by jit.cu)
+int dump_shape_text(const DPlan& p, char* out, size_t cap);
+static int dump_shape(const DPlan& p, char* out, size_t cap) { return dump_shape_text(p, out, cap); }
+int dump_shape_text(const DPlan& p, char* out, size_t cap) {
   std::string s = "{";
   auto add = [&](const char* fmt, ...) { char b[256]; va_list ap; va_start(ap, fmt); vsnprintf(b, sizeof(b), fmt, ap); va_end(ap); s += b; };
   add("%d, %d, %d, %d, %d, %d, 0u, %d,\n  {", p.n_exprs, p.n_filters, p.n_keys, p.n_joins, p.n_acc, p.n_cols, p.hash_type);
@@ -422,6 +424,7 @@ int hdk_b200_debug_set(const char* name, int value) {
   else if (n == "partitioned_table_slots") hb::g_debug.pa_slots = value;
   else if (n == "partitioned_partitions") hb::g_debug.pa_partitions = value;
   else if (n == "partitioned_heavy_rows") hb::g_debug.pa_heavy_rows = value;
+  else if (n == "jit") hb::g_debug.jit = value;
   else { hb::set_error("unknown debug knob '%s'", name); return HDK_B200_E_INVALID; }
   return HDK_B200_OK;
 }

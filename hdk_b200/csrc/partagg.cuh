@@ -72,6 +72,7 @@ struct DebugKnobs {
   int pa_slots;             // 0 auto, else slots of the per-CTA shared table of the partitioned aggregation (tests: force splits)
   int pa_partitions;        // 0 auto, else the number of partitions
   int pa_heavy_rows;        // 0 auto, else the partition size beyond which the launch falls back to the global-table probe
+  int jit;                  // run-time specialisation of plan shapes without pre-compiled kernels: 0 off, 1 in the background, 2 before the launch
 };
 extern DebugKnobs g_debug;
 

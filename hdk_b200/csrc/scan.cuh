@@ -43,6 +43,23 @@ struct ScanArgs {
   uint32_t col_region_off[HDK_B200_MAX_COLS];       // from a stage's base
 };
 
+#ifndef __CUDACC_RTC__
+typedef void (*ScanKernelFn)(const ScanArgs);
+struct StaticEntry {   // the kernels of one plan shape: pre-compiled (static_shapes.inc) or compiled at run time (jit.cu)
+  uint64_t sig;
+  const char* name;
+  int iter_rows;       // rows per consumer thread per iteration of the full-tile loop
+  ScanKernelFn fn[5];  // THREAD_PRIVATE, CTA_SHARED, GLOBAL, BASELINE, REGISTER (8 groups)
+  ScanKernelFn reg_fn[4];  // REGISTER kernels for <= 2, 4, 6, 8 groups
+};
+// Run-time specialisation (jit.cu): the kernels of a plan shape without a pre-compiled entry, compiled with NVRTC from the
+// same scan_kernel.cuh.  `wait`: compile now if needed (else the compile runs on a worker thread and nullptr is returned
+// until it is done — the caller launches the interpreting kernel meanwhile).  nullptr also when NVRTC is unavailable.
+const StaticEntry* jit_scan_kernels(const DPlan& p, uint64_t sig, bool wait);
+int dump_shape_text(const DPlan& p, char* out, size_t cap);
+struct JitStats { unsigned long long compiled, failed, launches, pending; double last_compile_ms, total_compile_ms; };
+extern JitStats g_jit_stats;
+
 int init_work_table(const Lowered& lw, int64_t* work_table, cudaStream_t stream, const int* run_if = nullptr);
 int launch_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
                 int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info);
@@ -62,5 +79,7 @@ int launch_finalize_exchange(const Lowered& lw, const int64_t* slots, const unsi
                              int32_t* error_codes, int64_t* const* groups_buffer_indirect, cudaStream_t stream);
 int launch_baseline_scan(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,
                          int64_t* work_table, cudaStream_t stream, hdk_b200_launch_info* info, const int* run_if = nullptr);
+
+#endif
 
 }  // namespace hb

@@ -1,7 +1,9 @@
 // hdk_b200/csrc/shape.cuh — plan shapes: the compile-time structure of a lowered plan.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <type_traits>
 #include <utility>
+#endif
 
 #include "common.cuh"
 
@@ -37,7 +39,9 @@ __device__ __forceinline__ void static_for(F&& f) {
     static constexpr int rows_per_iter = RPI;                                    \
     __host__ __device__ static constexpr DPlan get() { return DPlan __VA_ARGS__; } \
   };
+#ifndef HB_JIT   // (a run-time compiled translation unit defines its own single shape)
 #include "static_shapes.inc"
+#endif
 #undef HB_STATIC_SHAPE
 
 }  // namespace hb

@@ -19,8 +19,10 @@
 #ifndef HDK_B200_H
 #define HDK_B200_H
 
+#ifndef HDK_B200_NO_STD_HEADERS /* (the library's own run-time compiled kernels get these types from libcu++) */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -290,6 +292,8 @@ typedef struct hdk_b200_launch_info {
   int32_t n_accumulators;
   int32_t tile_rows;     /* rows per staged tile */
 } hdk_b200_launch_info;
+
+#define HDK_B200_VARIANT_JIT 1000 /* hdk_b200_launch_info.variant: kernels specialised for the plan's shape at run time */
 
 enum hdk_b200_strategy {
   HDK_B200_STRATEGY_THREAD_PRIVATE = 0, /* per-thread bins in shared memory, no atomics */
@@ -663,6 +667,25 @@ HDK_B200_API int hdk_b200_query_host(const hdk_b200_plan* plan, const hdk_b200_q
                         const size_t* inner_col_bytes,
                         int8_t* out_buffer, int device, hdk_b200_launch_info* info);
 
+/* ============================================================================
+ * Run-time specialisation.  The reference compiles EVERY work unit (Executor::compileWorkUnit, QE/NativeCodegen.cpp:
+ * 1403-1560) and caches the native code by plan; here the fused kernel is a template over the plan's structure
+ * (expression DAG, key / aggregate kinds, column widths — never literals, key ranges or entry counts): the named configs'
+ * shapes are instantiated at build time, any other supported plan is instantiated by NVRTC (libnvrtc, loaded on demand)
+ * from the same source the first time its shape is launched and cached by structural signature for the life of the
+ * process.  While a shape compiles in the background its launches run the interpreting kernel — same results.
+ * Without libnvrtc everything runs on the interpreting kernel.
+ * ==========================================================================*/
+typedef struct hdk_b200_jit_stats {
+  uint64_t shapes_compiled, shapes_failed, shapes_pending;
+  uint64_t launches;                 /* launches that ran run-time compiled kernels */
+  double last_compile_ms, total_compile_ms;
+  int available;                     /* libnvrtc found and usable */
+} hdk_b200_jit_stats;
+HDK_B200_API int hdk_b200_jit_get_stats(hdk_b200_jit_stats* out);
+/* block until no shape is being compiled (tests, benchmarks) */
+HDK_B200_API int hdk_b200_jit_wait(void);
+
 /* ---- misc ------------------------------------------------------------------ */
 /* Process-wide debug / tuning knobs (tests, tools/): never needed for correct results.
  *   "force_generic"            1 = never dispatch to a pre-compiled plan shape (run the interpreting kernel)
@@ -671,7 +694,9 @@ HDK_B200_API int hdk_b200_query_host(const hdk_b200_plan* plan, const hdk_b200_q
  *   "partitioned_table_slots"  0 = library picks; else the slots of the per-CTA shared table (tests force partition splits)
  *   "partitioned_partitions"   0 = library picks; else the number of partitions
  *   "partitioned_heavy_rows"   0 = library picks; else the partition size (rows) beyond which a partitioned launch falls
- *                              back to the global-table probe (hot keys) */
+ *                              back to the global-table probe (hot keys)
+ *   "jit"                      run-time specialisation (see hdk_b200_jit_*): 0 off, 1 compile in the background (default
+ *                              when NVRTC is present), 2 compile before the first launch of a shape */
 HDK_B200_API int hdk_b200_debug_set(const char* name, int value);
 HDK_B200_API const char* hdk_b200_last_error(void);
 HDK_B200_API int hdk_b200_abi_version(void);
