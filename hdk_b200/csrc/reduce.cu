@@ -310,4 +310,62 @@ int hdk_b200_compact_result(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, 
   return HDK_B200_OK;
 }
 
+// ---- Arrow buffers of one result column (ArrowResultSetConverter::convertToArrow, omniscidb/ResultSet/
+//      ArrowResultSetConverter.cpp: value buffer of the Arrow type + validity bitmap, LSB first) ----------------------------
+namespace hb {
+struct ArrowColArgs {
+  const int64_t* cells;
+  uint64_t n;
+  int32_t cells_fp, out_fp, out_width, nullable;
+  int64_t null_int;
+  double null_fp;
+  int8_t* values;
+  uint32_t* validity;
+  unsigned long long* null_count;
+};
+__global__ void __launch_bounds__(256) arrow_column_kernel(const __grid_constant__ ArrowColArgs a) {
+  const uint64_t n32 = (a.n + 31) / 32 * 32;    // whole validity words: every lane of a warp votes
+  unsigned long long nulls = 0;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n32; i += uint64_t(gridDim.x) * blockDim.x) {
+    bool valid = false;
+    if (i < a.n) {
+      const int64_t c = a.cells[i];
+      valid = !a.nullable || (a.cells_fp ? __longlong_as_double(c) != a.null_fp : c != a.null_int);
+      if (a.out_fp) {
+        const double d = valid ? __longlong_as_double(c) : 0.0;
+        if (a.out_width == 4) reinterpret_cast<float*>(a.values)[i] = float(d);
+        else reinterpret_cast<double*>(a.values)[i] = d;
+      } else {
+        const int64_t v = valid ? c : 0;      // Arrow leaves NULL slots unspecified: zero keeps the buffers deterministic
+        if (a.out_width == 8) reinterpret_cast<int64_t*>(a.values)[i] = v;
+        else if (a.out_width == 4) reinterpret_cast<int32_t*>(a.values)[i] = int32_t(v);
+        else if (a.out_width == 2) reinterpret_cast<int16_t*>(a.values)[i] = int16_t(v);
+        else a.values[i] = int8_t(v);
+      }
+      nulls += !valid;
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && a.validity) a.validity[i / 32] = word;
+  }
+  for (int d = 16; d; d >>= 1) nulls += __shfl_xor_sync(0xffffffffu, nulls, d);
+  if ((threadIdx.x & 31) == 0 && nulls && a.null_count) atomicAdd(a.null_count, nulls);
+}
+}  // namespace hb
+
+int hdk_b200_arrow_column_on_device(const int64_t* cells, uint64_t n_rows, int cells_are_fp, int out_is_fp, int out_width, int nullable,
+                                    int64_t null_int, double null_fp, int8_t* values, uint32_t* validity, uint64_t* null_count,
+                                    void* stream) {
+  if ((!cells && n_rows) || !values || (out_width != 1 && out_width != 2 && out_width != 4 && out_width != 8) ||
+      (out_is_fp && out_width < 4) || (out_is_fp && !cells_are_fp)) { set_error("bad argument"); return HDK_B200_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (null_count) HB_CUDA(cudaMemsetAsync(null_count, 0, sizeof(uint64_t), st));
+  if (!n_rows) return HDK_B200_OK;
+  hb::ArrowColArgs a{cells, n_rows, cells_are_fp, out_is_fp, out_width, nullable, null_int, null_fp, values, validity,
+                     reinterpret_cast<unsigned long long*>(null_count)};
+  const int grid = int(std::min<uint64_t>(uint64_t(hb::sm_count()) * 8, (n_rows + 255) / 256));
+  hb::arrow_column_kernel<<<grid, 256, 0, st>>>(a);
+  HB_LAUNCH_CHECK();
+  return HDK_B200_OK;
+}
+
 }  // extern "C"

@@ -136,6 +136,9 @@ class ResultSet:
         small results; large results go through hdk_b200_compact_result on the device."""
         if self._cols is not None:
             return self._cols
+        if getattr(self, "_dev_cells", None) is not None:
+            self._cols = ResultSet.from_compact(self.planned, self._dev_cells.cpu().numpy(), self.dictionaries)._cols
+            return self._cols
         pq, q, p = self.planned, self.planned.qmd, self.planned.plan
         E = q.entry_count
         buf = self.buffer
@@ -246,6 +249,68 @@ class ResultSet:
         rs._cols = cols
         return rs
 
+    @classmethod
+    def from_compact_device(cls, planned: planner.PlannedQuery, cells_dev, dictionaries, executor) -> "ResultSet":
+        """Result set over compacted cells that STAY on the device (torch int64 [n_targets, rows]): to_arrow() builds the
+        typed Arrow value buffers and validity bitmaps there (hdk_b200_arrow_column_on_device) and copies only those;
+        Python-side access (row_count, _decode) copies the cells lazily."""
+        rs = cls(planned, np.zeros(0, dtype=np.uint8), dictionaries)
+        rs._dev_cells, rs._executor = cells_dev, executor
+        return rs
+
+    def _arrow_from_device(self) -> pa.Table:
+        """ArrowResultSetConverter::convertToArrowTable (omniscidb/ResultSet/ArrowResultSetConverter.cpp) without the host loop
+        over rows: per target one kernel writes the Arrow value buffer + validity bitmap, pa.Array.from_buffers wraps them."""
+        ex, cells = self._executor, self._dev_cells
+        torch, lib, st = ex.ctx.torch, ex.lib, ex.ctx.stream_ptr()
+        n = int(cells.shape[1])
+        unit = self.planned.unit
+        arrays, names = [], []
+        words = (n + 31) // 32
+        for t, ti in enumerate(self.planned.infos):
+            chosen, typ = ti.compact_type, ti.type
+            post = None
+            if ti.agg == abi.AGG_AVG:
+                spec = (1, 1, 8, 1, 0, abi.DBL_MIN, pa.float64())
+            elif chosen.is_fp and ti.agg != abi.AGG_COUNT:
+                f4 = ti.float_argument_input or chosen.width == 4
+                null_fp = float(np.float64(np.float32(abi.FLT_MIN))) if f4 else abi.DBL_MIN
+                narrow = ti.agg in (abi.AGG_SUM, abi.AGG_MIN, abi.AGG_MAX) and typ.is_fp and typ.width == 4
+                spec = (1, 1, 4 if narrow else 8, int(chosen.nullable), 0, null_fp, pa.float32() if narrow else pa.float64())
+            else:
+                null_int = abi.int_null(ti.type.width)
+                if not ti.is_agg and typ.kind == "dict" and self.dictionaries.get(t) is not None:
+                    w, pt, post = 4, pa.int32(), "dict"
+                elif not ti.is_agg and typ.kind == "dict":
+                    w, pt = 4, pa.int32()
+                elif not ti.is_agg and typ.kind == "timestamp":
+                    w, pt, post = 8, pa.int64(), "timestamp"
+                elif ti.agg == abi.AGG_COUNT:
+                    w = 4 if typ.width == 4 else 8
+                    pt = pa.int32() if w == 4 else pa.int64()
+                else:
+                    w = 8 if (ti.is_agg and ti.agg == abi.AGG_SUM) else typ.width
+                    pt = {1: pa.int8(), 2: pa.int16(), 4: pa.int32(), 8: pa.int64()}[w]
+                spec = (0, 0, w, int(chosen.nullable), null_int, 0.0, pt)
+            cells_fp, out_fp, w, nullable, null_int, null_fp, pt = spec
+            values = torch.empty(max(n, 1) * w, dtype=torch.uint8, device=ex.ctx.device)
+            validity = torch.empty(max(words, 1), dtype=torch.int32, device=ex.ctx.device) if nullable else None
+            nulls = torch.zeros(1, dtype=torch.int64, device=ex.ctx.device)
+            _lib.check(lib.hdk_b200_arrow_column_on_device(cells[t].data_ptr(), n, cells_fp, out_fp, w, nullable, null_int, null_fp,
+                                                           values.data_ptr(), validity.data_ptr() if nullable else None, nulls.data_ptr(), st),
+                       "arrow_column_on_device")
+            null_count = int(nulls.item()) if nullable else 0
+            vbuf = pa.py_buffer(values[: n * w].cpu().numpy())
+            bbuf = pa.py_buffer(validity[:words].cpu().numpy()) if (nullable and null_count) else None
+            arr = pa.Array.from_buffers(pt, n, [bbuf, vbuf], null_count)
+            if post == "dict":
+                arr = pa.DictionaryArray.from_arrays(arr, pa.array(self.dictionaries[t], type=pa.string())).cast(pa.string())
+            elif post == "timestamp":
+                arr = arr.cast(pa.timestamp({1: "s", 1000: "ms", 1000000: "us", 1000000000: "ns"}[typ.unit]))
+            arrays.append(arr)
+            names.append(unit.target_names[t])
+        return pa.table(arrays, names=names)
+
     def order_entries(self) -> list:
         """One dict per ORDER BY item, typed the way the compacted 8-byte cells are (and the way `from_compact` reads them)."""
         out = []
@@ -272,9 +337,16 @@ class ResultSet:
 
     def to_arrow(self) -> pa.Table:
         """ArrowResultSetConverter::convertToArrowTable (omniscidb/ResultSet/ArrowResultSetConverter.cpp)."""
+        unit = self.planned.unit
+        if getattr(self, "_dev_cells", None) is not None and (self.sorted_on_device or not unit.order_by):
+            tbl = self._arrow_from_device()
+            if unit.limit is not None:
+                tbl = tbl.slice(0, unit.limit)
+            if unit.n_hidden:
+                tbl = tbl.select(list(range(tbl.num_columns - unit.n_hidden)))
+            return tbl
         cols = self._decode()
         arrays, names = [], []
-        unit = self.planned.unit
         for t, (ti, col) in enumerate(zip(self.planned.infos, cols)):
             mask = np.ma.getmaskarray(col)
             data = np.ma.getdata(col)
@@ -1184,12 +1256,13 @@ class Executor:
                 # ORDER BY [LIMIT]: compact, sort and cut on the device; only the rows of the answer travel
                 cols, n = self.compact_on_device(pq, prep["out"], to_host=False)
                 order = ResultSet(pq, np.zeros(0, dtype=np.uint8), dicts).order_entries()
-                cells = self.sort_on_device(cols, n, order, unit.limit).cpu().numpy()
-                rs = ResultSet.from_compact(pq, cells, dicts)
+                rs = ResultSet.from_compact_device(pq, self.sort_on_device(cols, n, order, unit.limit), dicts, self)
                 rs.sorted_on_device = True
             elif prep["out"].numel() > self.compact_threshold_bytes:
-                # large (baseline-hash) buffers: drop the empty entries and finalise AVG on the device, copy rows only
-                rs = ResultSet.from_compact(pq, self.compact_on_device(pq, prep["out"]), dicts)
+                # large (baseline-hash) buffers: drop the empty entries and finalise AVG on the device; the rows stay there
+                # until somebody asks for them (to_arrow builds the Arrow buffers on the device)
+                cols, n = self.compact_on_device(pq, prep["out"], to_host=False)
+                rs = ResultSet.from_compact_device(pq, cols[:, :n], dicts, self)
             else:
                 rs = ResultSet(pq, prep["out"].cpu().numpy(), dicts)
             rs.launch_info = info

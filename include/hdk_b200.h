@@ -592,6 +592,16 @@ HDK_B200_API int hdk_b200_compact_result(const hdk_b200_plan* plan, const hdk_b2
                             int64_t* const* out_cols /* DEVICE array [n_targets] of int64[entry_count] */,
                             uint64_t* row_count /* DEVICE */, void* stream);
 
+/* Arrow buffers of one result column from its compacted 8-byte cells, on the device (ArrowResultSetConverter::
+ * convertToArrowTable, omniscidb/ResultSet/ArrowResultSetConverter.cpp — there a host loop over ResultSet rows): the value
+ * buffer of the Arrow type (int8/16/32/64, float, double: out_width bytes per row, NULL slots zeroed) and the validity
+ * bitmap (bit i = row i is not NULL, LSB first, ceil(n_rows / 32) words; may be NULL when the column is not nullable).
+ * A cell is NULL when it equals null_int (integers) / null_fp (cells holding doubles) — the sentinels
+ * hdk_b200_compact_result normalises to.  *null_count (DEVICE, optional) receives the number of NULLs. */
+HDK_B200_API int hdk_b200_arrow_column_on_device(const int64_t* cells, uint64_t n_rows, int cells_are_fp, int out_is_fp, int out_width,
+                                                 int nullable, int64_t null_int, double null_fp, int8_t* values, uint32_t* validity,
+                                                 uint64_t* null_count, void* stream);
+
 /* ============================================================================
  * ORDER BY / LIMIT over the compacted result, on the device ("next" row: top-k / ORDER BY over aggregated results).
  * Replaces sortResultSet (QE/ResultSetSort.cpp:752-851): the permutation it leaves in the ResultSet

@@ -564,6 +564,34 @@ def test_reference_harvested_queries_on_gpu(oracle_mod, torch):
                 raise AssertionError(f"{name}: {text}: {e}")
 
 
+def test_arrow_buffers_built_on_device_equal_host_conversion(oracle_mod, torch):
+    """ResultSet → Arrow on the device (hdk_b200_arrow_column_on_device: typed value buffers + validity bitmaps from the
+    compacted cells) against the host conversion of the same group-by buffer (ArrowResultSetConverter restated in
+    ResultSet.to_arrow): identical schema, values and NULLs for every harvested query — every integer width, fp32 / fp64,
+    dictionary strings, timestamps, dates, AVG, COUNT under both bigint_count settings, ORDER BY … LIMIT."""
+    import hdk_b200.hdk as hdk_mod
+    from tests.test_sqlite_oracle import REFERENCE_HARVESTED_QUERIES, harvested_tables
+    tables = harvested_tables()
+    h = hdk_mod.init()
+    for name, t in tables.items():
+        h.import_arrow(t, name, fragment_size=3)
+    n_dev = 0
+    for name, queries in REFERENCE_HARVESTED_QUERIES.items():
+        for text in queries:
+            h.executor.compact_threshold_bytes = 1 << 40
+            host = h.sql(text).to_arrow()
+            h.executor.compact_threshold_bytes = 0
+            rs = h.sql(text)
+            dev = rs.to_arrow()
+            n_dev += getattr(rs.result_set, "_dev_cells", None) is not None
+            assert host.schema.equals(dev.schema), f"{text}: {host.schema} vs {dev.schema}"
+            if "ORDER BY" not in text.upper():
+                order = [(c, "ascending") for c in host.column_names]
+                host, dev = host.sort_by(order), dev.sort_by(order)
+            assert [tuple(map(repr, r.values())) for r in host.to_pylist()] == [tuple(map(repr, r.values())) for r in dev.to_pylist()], text
+    assert n_dev > 100
+
+
 def test_null_div_by_zero_on_gpu(oracle_mod, torch):
     """Config null_div_by_zero (Select.ReturnNullFromDivByZero): NULL instead of ERR_DIV_BY_ZERO, rows vs SQLite."""
     import hdk_b200.hdk as hdk_mod
