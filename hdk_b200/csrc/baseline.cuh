@@ -3,8 +3,12 @@
 //
 //   hash           key_hash = MurmurHash3_x86_32 over the key bytes, seed 0  (QE/GroupByRuntime.cpp:24-29)
 //   probe          h % E, linear probing, NULL ⇒ out of slots                (QE/GroupByRuntime.cpp:31-54, 90-112)
-//   claim          CAS on the first key component; the winner publishes the rest; others wait until
-//                  the rest is published, then compare                      (QE/cuda_mapd_rt.cu:176-236, 240-321)
+//   claim          the reference's protocol (QE/cuda_mapd_rt.cu:176-236, 240-321): CAS on the first key component; the
+//                  winner publishes the rest; others wait until the rest is published, then compare.  Here a key that
+//                  fits one atomic is claimed WHOLE — two 4-byte components with one 64-bit CAS, two 8-byte components of
+//                  a 16-byte aligned row with one atom.cas.b128 — so there is no half-published entry and nobody waits;
+//                  the reference protocol remains for wider keys and the columnar layout, its wait backs off
+//                  (__nanosleep) and is bounded (kClaimTimedOut instead of a hang).
 #pragma once
 #ifndef __CUDACC_RTC__
 #include <type_traits>
@@ -66,13 +70,68 @@ __device__ __forceinline__ uint64_t murmur64a_keys(const int64_t* keys, int key_
 template <typename T>
 __device__ __forceinline__ T ld_volatile(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
 
-// Find or claim the entry for `keys` (row-wise layout).  Returns the entry index or -1 (table full).
+constexpr int64_t kClaimTimedOut = -2;   // a winner never published the rest of its key (→ error HDK_B200_ERR_CLAIM_TIMEOUT)
+
+// wait until a claimed entry's component is published: poll, back off, give up after ~1 s
+template <typename T>
+__device__ __forceinline__ bool wait_published(const T* p, T empty, T* out) {
+  T v = ld_volatile(p);
+  for (uint32_t spins = 0; v == empty; ++spins) {
+    if (spins >= (1u << 22)) return false;
+    if (spins >= 16) __nanosleep(spins < 1024 ? 32 : 256);
+    v = ld_volatile(p);
+  }
+  *out = v;
+  return true;
+}
+
+// 16-byte compare-and-swap (sm_90+): returns the old value
+__device__ __forceinline__ void cas_b128(void* addr, uint64_t cmp_lo, uint64_t cmp_hi, uint64_t val_lo, uint64_t val_hi, uint64_t& old_lo,
+                                         uint64_t& old_hi) {
+  asm volatile(
+      "{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+      "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(old_lo), "=l"(old_hi)
+      : "l"(cmp_lo), "l"(cmp_hi), "l"(val_lo), "l"(val_hi), "l"(addr)
+      : "memory");
+}
+
+// Find or claim the entry for `keys` (row-wise layout).  Returns the entry index, -1 (table full) or kClaimTimedOut.
 template <typename T>
 __device__ __forceinline__ int64_t baseline_claim_rowwise(int8_t* buf, uint32_t row_bytes, uint32_t E, const int64_t* keys,
                                                           int key_count, uint32_t h0) {
   const T empty = sizeof(T) == 4 ? T(HDK_B200_EMPTY_KEY_32) : T(HDK_B200_EMPTY_KEY_64);
   using U = typename std::conditional<sizeof(T) == 4, unsigned int, unsigned long long>::type;
   uint32_t h = h0;
+  if (sizeof(T) == 4 && key_count == 2) {
+    // two 4-byte components: the whole key is one 64-bit word of the (8-byte aligned) row
+    const unsigned long long e64 = (unsigned long long)uint32_t(HDK_B200_EMPTY_KEY_32) * 0x100000001ull;
+    const unsigned long long mine = (unsigned long long)uint32_t(keys[0]) | ((unsigned long long)uint32_t(keys[1]) << 32);
+    do {
+      unsigned long long* row = reinterpret_cast<unsigned long long*>(buf + size_t(h) * row_bytes);
+      unsigned long long cur = ld_volatile(row);
+      if (cur == e64) cur = atomicCAS(row, e64, mine);
+      if (cur == e64 || cur == mine) return h;
+      h = h + 1 == E ? 0 : h + 1;
+    } while (h != h0);
+    return -1;
+  }
+  if (sizeof(T) == 8 && key_count == 2 && (row_bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0) {
+    // two 8-byte components of a 16-byte aligned row: one 128-bit CAS.  A half only ever holds EMPTY or its final value,
+    // so a plain look that shows both halves equal to the key is a match; anything with an EMPTY half is settled by the CAS.
+    const uint64_t e = uint64_t(HDK_B200_EMPTY_KEY_64), k0 = uint64_t(keys[0]), k1 = uint64_t(keys[1]);
+    do {
+      uint64_t* row = reinterpret_cast<uint64_t*>(buf + size_t(h) * row_bytes);
+      uint64_t c0 = ld_volatile(row), c1 = ld_volatile(row + 1);
+      if (c0 == e || c1 == e) {
+        cas_b128(row, e, e, k0, k1, c0, c1);
+        if (c0 == e && c1 == e) return h;   // claimed
+      }
+      if (c0 == k0 && c1 == k1) return h;
+      h = h + 1 == E ? 0 : h + 1;
+    } while (h != h0);
+    return -1;
+  }
   do {
     T* row = reinterpret_cast<T*>(buf + size_t(h) * row_bytes);
     const T k0 = T(keys[0]);
@@ -86,8 +145,7 @@ __device__ __forceinline__ int64_t baseline_claim_rowwise(int8_t* buf, uint32_t 
       bool match = true;
       for (int i = 1; i < key_count && match; ++i) {
         T v;
-        while ((v = ld_volatile(row + i)) == empty) {
-        }
+        if (!wait_published(row + i, empty, &v)) return kClaimTimedOut;
         match = v == T(keys[i]);
       }
       if (match) return h;
@@ -97,7 +155,8 @@ __device__ __forceinline__ int64_t baseline_claim_rowwise(int8_t* buf, uint32_t 
   return -1;
 }
 
-// columnar layout: 8-byte key columns, component i at buf64[i * E + h]
+// columnar layout: 8-byte key columns, component i at buf64[i * E + h] (components of one entry lie E words apart: no
+// packed claim)
 __device__ __forceinline__ int64_t baseline_claim_columnar(int64_t* buf64, uint32_t E, const int64_t* keys, int key_count,
                                                            uint32_t h0) {
   uint32_t h = h0;
@@ -115,8 +174,7 @@ __device__ __forceinline__ int64_t baseline_claim_columnar(int64_t* buf64, uint3
       bool match = true;
       for (int i = 1; i < key_count && match; ++i) {
         int64_t v;
-        while ((v = ld_volatile(buf64 + size_t(i) * E + h)) == HDK_B200_EMPTY_KEY_64) {
-        }
+        if (!wait_published(buf64 + size_t(i) * E + h, int64_t(HDK_B200_EMPTY_KEY_64), &v)) return kClaimTimedOut;
         match = v == keys[i];
       }
       if (match) return h;
@@ -167,8 +225,7 @@ __device__ __forceinline__ T* baseline_slot(int8_t* hash_buff, int64_t E, const 
       bool match = true;
       for (int i = 1; i < kc && match; ++i) {
         T v;
-        while ((v = *reinterpret_cast<volatile T*>(row + i)) == empty) {
-        }
+        if (!wait_published(row + i, empty, &v)) return nullptr;   // (a winner that never publishes: treated as a miss / full table)
         match = v == key[i];
       }
       if (match) return row + kc;

@@ -226,16 +226,38 @@ static void compile_entry(JitEntry* je) {
   g_cv.notify_all();
 }
 
+// Process exit while a compile is in flight: the detached worker would still be inside NVRTC / the CUDA runtime when their
+// static state is torn down (observed: SIGSEGV at interpreter exit of a short script).  An atexit handler — registered at
+// the first background request, i.e. after the CUDA runtime's own, so it runs before them — drops the queue and waits
+// for the compile in flight (<= a few seconds).
+bool g_shutdown = false;
+int g_busy = 0;
+static void jit_shutdown() {
+  std::unique_lock<std::mutex> lock(g_mutex);
+  g_shutdown = true;
+  g_jit_stats.pending -= g_queue.size();
+  g_queue.clear();
+  g_cv.notify_all();
+  g_cv.wait(lock, [] { return g_busy == 0; });
+}
+
 static void worker() {
   for (;;) {
     JitEntry* je = nullptr;
     {
       std::unique_lock<std::mutex> lock(g_mutex);
-      g_cv.wait(lock, [] { return !g_queue.empty(); });
+      g_cv.wait(lock, [] { return g_shutdown || !g_queue.empty(); });
+      if (g_shutdown) return;
       je = g_queue.front();
       g_queue.pop_front();
+      ++g_busy;
     }
     compile_entry(je);
+    {
+      std::lock_guard<std::mutex> lock(g_mutex);
+      --g_busy;
+    }
+    g_cv.notify_all();
   }
 }
 
@@ -264,6 +286,7 @@ const StaticEntry* jit_scan_kernels(const DPlan& p, uint64_t sig, bool wait) {
       g_queue.push_back(je);
       if (!g_worker_started) {
         g_worker_started = true;
+        std::atexit(jit_shutdown);
         std::thread(worker).detach();
       }
       g_cv.notify_all();

@@ -164,7 +164,6 @@ int lower_plan(const hdk_b200_plan* plan, const hdk_b200_qmd* q, Lowered* out) {
   for (int j = 0; j < plan->n_joins; ++j) {
     const hdk_b200_join& s = plan->joins[j];
     if (s.key_expr < 0 || s.key_expr >= plan->n_exprs) { set_error("bad join key node"); return HDK_B200_E_INVALID; }
-    if (s.one_to_many && (plan->n_joins != 1)) { set_error("one-to-many probe is supported for a single join only"); return HDK_B200_E_UNSUPPORTED; }
     DJoin& d = p.joins[j];
     d.min_key = s.min_key; d.max_key = s.max_key; d.null_val = s.null_val;
     d.key_expr = s.key_expr; d.key_nullable = uint8_t(s.key_nullable); d.one_to_many = uint8_t(s.one_to_many);

@@ -138,7 +138,7 @@ __global__ void reduce_baseline_kernel(const __grid_constant__ ReduceArgs a) {
     const int64_t dst = L.columnar ? baseline_claim_columnar(reinterpret_cast<int64_t*>(a.this_buf), L.entry_count, keys, L.key_count, h0)
                         : L.key_width == 4 ? baseline_claim_rowwise<int32_t>(a.this_buf, L.row_bytes, L.entry_count, keys, L.key_count, h0)
                                            : baseline_claim_rowwise<int64_t>(a.this_buf, L.row_bytes, L.entry_count, keys, L.key_count, h0);
-    if (dst < 0) { record_error(a.error_codes, -HDK_B200_ERR_OUT_OF_SLOTS); continue; }
+    if (dst < 0) { record_error(a.error_codes, dst == kClaimTimedOut ? HDK_B200_ERR_CLAIM_TIMEOUT : -HDK_B200_ERR_OUT_OF_SLOTS); continue; }
     // keys are unique inside `that`, so exactly one thread touches the destination entry's slots;
     // a freshly claimed entry still holds the init values, so reducing into it equals a copy
     for (int s = 0; s < L.slot_count; ++s) {

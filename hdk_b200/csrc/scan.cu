@@ -138,6 +138,10 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   a.layout = lw.layout;
   a.groupby_buf = params->groupby_buf;
   a.run_if = run_if;
+  // nesting order of the join probes: by key node (a chained join's key comes after the inner columns it reads, hence after
+  // the key of the join that supplies them); stable for joins sharing a key node
+  for (int j = 0; j < p.n_joins; ++j) a.join_order[j] = uint8_t(j);
+  std::stable_sort(a.join_order, a.join_order + p.n_joins, [&](uint8_t x, uint8_t y) { return p.joins[x].key_expr < p.joins[y].key_expr; });
   if (xchg) {
     a.n_peers = xchg->n_peers;
     a.n_cells = uint64_t(p.n_acc) * p.entry_count;
@@ -157,7 +161,11 @@ static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko
   // none yet — the interpreting kernel runs, and with the JIT on the specialised ones are being built meanwhile
   const uint64_t sig = plan_signature(p);
   const StaticEntry* stat = nullptr;
-  if (!g_debug.force_generic) {  // (hdk_b200_debug_set("force_generic", 1): tests run the interpreter on the benchmark shapes)
+  // (a one-to-many join loops over its matching set: only the interpreting kernel nests those loops, and no pre-compiled
+  //  shape has one)
+  bool one_to_many = false;
+  for (int j = 0; j < p.n_joins; ++j) one_to_many = one_to_many || p.joins[j].one_to_many;
+  if (!g_debug.force_generic && !one_to_many) {  // (hdk_b200_debug_set("force_generic", 1): tests run the interpreter on the benchmark shapes)
     for (int i = 0; kStaticShapes[i].name; ++i)
       if (kStaticShapes[i].sig == sig) { stat = &kStaticShapes[i]; break; }
     if (!stat && g_debug.jit) stat = jit_scan_kernels(p, sig, g_debug.jit == 2);

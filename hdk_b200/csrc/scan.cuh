@@ -39,6 +39,7 @@ struct ScanArgs {
   unsigned long long* ticket;         // CTAs-done counter behind the work table, zeroed with it
   int64_t* peer_slot[HDK_B200_MAX_PEERS];              // slot `my_rank` of peer p's exchange buffer (this epoch's parity)
   unsigned long long* peer_flag[HDK_B200_MAX_PEERS];   // flag `my_rank` of peer p
+  uint8_t join_order[HDK_B200_MAX_JOINS];           // joins by key node: the order in which the interpreting kernel nests their probes
   uint32_t acc_bin_off[kMaxAcc];                    // from off_bins
   uint32_t col_region_off[HDK_B200_MAX_COLS];       // from a stage's base
 };

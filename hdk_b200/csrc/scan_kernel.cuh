@@ -107,115 +107,144 @@ __device__ __forceinline__ int64_t baseline_entry(const ScanArgs& args, int n_ke
 }
 
 // ---- one row, run-time plan --------------------------------------------------------------------
+// probe of join j with the key node(s) just evaluated: false on a miss (inner join: the row, or this combination of
+// matches, is dropped).  One-to-one tables give one inner row id; one-to-many tables the matching set (ids != nullptr).
+__device__ __forceinline__ bool probe_join_generic(const ScanArgs& args, int j, const V* vals, int64_t& rid, int32_t& n_matches,
+                                                   const int32_t*& ids) {
+  const DPlan& p = args.plan;
+  const DJoin& jn = p.joins[j];
+  n_matches = 1;
+  ids = nullptr;
+  if (jn.n_key_exprs) {   // composite / wide-range key: baseline join table
+    int64_t k64[HDK_B200_MAX_KEYS];
+    for (int i = 0; i < jn.n_key_exprs; ++i) k64[i] = vals[jn.key_exprs[i]].i;
+    const int8_t* tbl = reinterpret_cast<const int8_t*>(args.join_hash_tables[j]);
+    const int64_t E = p.join_entry_count[j];
+    if (jn.one_to_many) {
+      // composite-key dictionary, then offsets | counts | payload indexed by the key's position in it
+      // (BaselineJoinHashTable one-to-many layout; HashJoin::codegenMatchingSet)
+      const int64_t slot = jn.key_width == 4 ? baseline_dict_index<int32_t>(tbl, E, k64, jn.n_key_exprs)
+                                             : baseline_dict_index<int64_t>(tbl, E, k64, jn.n_key_exprs);
+      if (slot < 0) return false;
+      const int32_t* otm = reinterpret_cast<const int32_t*>(tbl + size_t(E) * size_t(jn.n_key_exprs) * size_t(jn.key_width));
+      const int32_t off = __ldg(otm + slot);
+      if (off < 0) return false;
+      n_matches = __ldg(otm + E + slot);
+      ids = otm + 2 * E + off;
+      return n_matches > 0;
+    }
+    rid = jn.key_width == 4 ? baseline_join_probe<int32_t>(tbl, E, k64, jn.n_key_exprs) : baseline_join_probe<int64_t>(tbl, E, k64, jn.n_key_exprs);
+    return rid >= 0;
+  }
+  // hash_join_idx[_nullable] (QE/GroupByRuntime.cpp:298-329)
+  const int64_t key = vals[jn.key_expr].i;
+  if ((jn.key_nullable && key == jn.null_val) || key < jn.min_key || key > jn.max_key) return false;
+  const int32_t* table = reinterpret_cast<const int32_t*>(args.join_hash_tables[j]);
+  const int64_t slot = key - jn.min_key;
+  if (jn.one_to_many) {
+    // offsets | counts | payload (JHT/PerfectJoinHashTable.cpp:861-886)
+    const int64_t E = p.join_entry_count[j];
+    const int32_t off = __ldg(table + slot);
+    if (off < 0) return false;
+    n_matches = __ldg(table + E + slot);
+    ids = table + 2 * E + off;
+    return n_matches > 0;
+  }
+  if (jn.by_slot) {
+    // presence bitmap + slot-ordered inner columns (hdk_b200_gather_join_payload_on_device)
+    if (jn.by_slot == 1 && !((__ldg(reinterpret_cast<const uint32_t*>(table) + (slot >> 5)) >> (slot & 31)) & 1u)) return false;
+    rid = slot;   // (by_slot == 2: every slot of [min_key, max_key] is occupied, no bitmap)
+    return true;
+  }
+  rid = __ldg(table + slot);
+  return rid >= 0;
+}
+
+// The joins of a plan are nested loops (the reference's JoinLoop nest, QE/IRCodegen.cpp: a Singleton loop for a one-to-one
+// table, a Set loop over HashJoin::codegenMatchingSet's (offset, count) for a one-to-many table).  Level l evaluates the
+// nodes between the key of join l-1 and the key of join l (joins taken by key node: args.join_order), then probes join l;
+// the innermost level evaluates the rest, filters and accumulates once per combination of matches.  Iterative: cur[l] is
+// the position inside level l's matching set, a finished level advances the nearest outer one that has matches left.
 template <int kStrategy>
 __device__ __forceinline__ void process_row_generic(const ScanArgs& args, const uint8_t* smem, const uint32_t* col_off, uint32_t r,
                                                     uint8_t* bins, int tid, V* vals, int32_t& my_err) {
   const DPlan& p = args.plan;
+  const int J = p.n_joins;
   int64_t rowid[HDK_B200_MAX_JOINS];
+  int32_t n_matches[HDK_B200_MAX_JOINS], cur[HDK_B200_MAX_JOINS];
+  const int32_t* match_ids[HDK_B200_MAX_JOINS];
+  int32_t row_err_at[HDK_B200_MAX_JOINS + 1], qual_err_at[HDK_B200_MAX_JOINS + 1];   // first error up to and including a level
   auto load_outer = [&](int c, int w) -> uint64_t { return lds_elem(smem + col_off[c] + size_t(r) * w, w); };
   auto load_inner = [&](int j, int c, int w) -> uint64_t {
     return ldg_elem(reinterpret_cast<const uint8_t*>(args.inner_col_buffers[j * HDK_B200_MAX_COLS + c]) + size_t(rowid[j]) * w, w);
   };
-  int32_t row_err = 0, qual_err = 0;
-  bool dropped = false;
-  // 1:N join: nodes up to the key are evaluated once, the rest once per match
-  int n_matches = 1;
-  const int32_t* match_ids = nullptr;
-  int split = p.n_exprs;
-  if (p.n_joins == 1 && p.joins[0].one_to_many) split = p.joins[0].key_expr + 1;
-  for (int n = 0; n < split && !dropped; ++n) {
-    int32_t e = 0;
-    vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
-    if (e) { int32_t& dst = (p.exprs[n].aux & kAuxInQual) ? qual_err : row_err; if (!dst) dst = e; }
-    for (int j = 0; j < p.n_joins; ++j) {
-      const DJoin& jn = p.joins[j];
-      if (jn.key_expr != n) continue;
-      if (jn.n_key_exprs) {   // composite / wide-range key: baseline join table
-        int64_t k64[HDK_B200_MAX_KEYS];
-        for (int i = 0; i < jn.n_key_exprs; ++i) k64[i] = vals[jn.key_exprs[i]].i;
-        const int8_t* tbl = reinterpret_cast<const int8_t*>(args.join_hash_tables[j]);
-        if (jn.one_to_many) {
-          // composite-key dictionary, then offsets | counts | payload indexed by the key's position in it
-          // (BaselineJoinHashTable one-to-many layout; HashJoin::codegenMatchingSet)
-          const int64_t E = p.join_entry_count[j];
-          const int64_t slot = jn.key_width == 4 ? baseline_dict_index<int32_t>(tbl, E, k64, jn.n_key_exprs)
-                                                 : baseline_dict_index<int64_t>(tbl, E, k64, jn.n_key_exprs);
-          if (slot < 0) { dropped = true; break; }
-          const int32_t* otm = reinterpret_cast<const int32_t*>(tbl + size_t(E) * size_t(jn.n_key_exprs) * size_t(jn.key_width));
-          const int32_t off = __ldg(otm + slot);
-          if (off < 0) { dropped = true; break; }
-          n_matches = __ldg(otm + E + slot);
-          match_ids = otm + 2 * E + off;
-          continue;
+  int lvl = 0;
+  for (;;) {
+    bool dead = false;
+    for (; lvl <= J; ++lvl) {
+      const int n0 = lvl == 0 ? 0 : p.joins[args.join_order[lvl - 1]].key_expr + 1;
+      const int n1 = lvl == J ? p.n_exprs : p.joins[args.join_order[lvl]].key_expr + 1;
+      if (lvl > 0 && match_ids[lvl - 1]) rowid[args.join_order[lvl - 1]] = __ldg(match_ids[lvl - 1] + cur[lvl - 1]);
+      int32_t row_err = lvl ? row_err_at[lvl - 1] : 0, qual_err = lvl ? qual_err_at[lvl - 1] : 0;
+      for (int n = n0; n < n1; ++n) {
+        int32_t e = 0;
+        vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
+        if (e) { int32_t& dst = (p.exprs[n].aux & kAuxInQual) ? qual_err : row_err; if (!dst) dst = e; }
+      }
+      row_err_at[lvl] = row_err;
+      qual_err_at[lvl] = qual_err;
+      if (lvl < J) {
+        cur[lvl] = 0;
+        const int j = args.join_order[lvl];
+        if (!probe_join_generic(args, j, vals, rowid[j], n_matches[lvl], match_ids[lvl])) { dead = true; break; }
+      }
+    }
+    if (!dead) {
+      const int32_t row_err = row_err_at[J], qual_err = qual_err_at[J];
+      bool pass = true;
+      for (int f = 0; f < p.n_filters; ++f) pass = pass && (vals[p.filters[f]].i > 0);
+      if (qual_err) {
+        my_err = my_err > 0 ? my_err : qual_err;   // an error inside a qual: raised whether or not the row passes
+      } else if (pass && row_err) {
+        my_err = my_err > 0 ? my_err : row_err;
+      } else if (pass) {
+        uint32_t idx = 0;
+        bool have = true;
+        if (kStrategy == HDK_B200_STRATEGY_BASELINE) {
+          const int64_t entry = baseline_entry(args, p.n_keys, [&](int k) { return p.keys[k].expr; }, vals);
+          if (entry == kClaimTimedOut) { my_err = my_err > 0 ? my_err : HDK_B200_ERR_CLAIM_TIMEOUT; have = false; }
+          else if (entry < 0) { if (my_err <= 0) my_err = -HDK_B200_ERR_OUT_OF_SLOTS; have = false; }
+          idx = uint32_t(entry);
+        } else {
+          int64_t h = 0;
+          for (int k = 0; k < p.n_keys; ++k) {
+            const DKey& ky = p.keys[k];
+            int64_t v = vals[ky.expr].i;
+            if (ky.has_nulls && v == int_null_of(ky.width)) v = ky.null_translated;
+            int64_t term = v - ky.min_val;
+            if (ky.bucket) term /= ky.bucket;   // (get_group_value_fast / perfect_key_hash divide by the bucket)
+            h += term * ky.mult;
+          }
+          idx = uint32_t(h);
+          if (idx >= p.entry_count) { my_err = my_err > 0 ? my_err : 1003; have = false; }  // key outside the range the layout was built for
         }
-        const int64_t rid = jn.key_width == 4 ? baseline_join_probe<int32_t>(tbl, p.join_entry_count[j], k64, jn.n_key_exprs)
-                                              : baseline_join_probe<int64_t>(tbl, p.join_entry_count[j], k64, jn.n_key_exprs);
-        if (rid < 0) { dropped = true; break; }
-        rowid[j] = rid;
-        continue;
-      }
-      // hash_join_idx[_nullable] (QE/GroupByRuntime.cpp:298-329)
-      const int64_t key = vals[n].i;
-      if ((jn.key_nullable && key == jn.null_val) || key < jn.min_key || key > jn.max_key) { dropped = true; break; }
-      const int32_t* table = reinterpret_cast<const int32_t*>(args.join_hash_tables[j]);
-      const int64_t slot = key - jn.min_key;
-      if (jn.one_to_many) {
-        // offsets | counts | payload (JHT/PerfectJoinHashTable.cpp:861-886)
-        const int64_t E = p.join_entry_count[j];
-        const int32_t off = __ldg(table + slot);
-        if (off < 0) { dropped = true; break; }
-        n_matches = __ldg(table + E + slot);
-        match_ids = table + 2 * E + off;
-      } else if (jn.by_slot) {
-        // presence bitmap + slot-ordered inner columns (hdk_b200_gather_join_payload_on_device)
-        if (jn.by_slot == 1 && !((__ldg(reinterpret_cast<const uint32_t*>(table) + (slot >> 5)) >> (slot & 31)) & 1u)) { dropped = true; break; }
-        rowid[j] = slot;   // (by_slot == 2: every slot of [min_key, max_key] is occupied, no bitmap)
-      } else {
-        const int32_t idx = __ldg(table + slot);
-        if (idx < 0) { dropped = true; break; }
-        rowid[j] = idx;
+        if (have) {
+          for (int a = 0; a < p.n_acc; ++a) {
+            const DAcc acc = p.accs[a];
+            // shared-memory bins of a CNT_NN accumulator count the NULL rows (rare) instead of the non-NULL ones;
+            // the flush converts: non-null = rows - nulls.  The global work table always holds non-null counts.
+            const bool count_nulls = acc.kind == ACC_CNT_NN && kStrategy != HDK_B200_STRATEGY_GLOBAL && kStrategy != HDK_B200_STRATEGY_BASELINE;
+            if (acc_arg_is_null(p, acc, vals) != count_nulls) continue;
+            accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(p, acc, vals));
+          }
+        }
       }
     }
-  }
-  if (dropped) return;
-  for (int mi = 0; mi < n_matches; ++mi) {
-    if (match_ids) rowid[0] = __ldg(match_ids + mi);
-    for (int n = split; n < p.n_exprs; ++n) {
-      int32_t e = 0;
-      vals[n] = eval_node(p, p.exprs[n], vals, e, load_outer, load_inner);
-      if (e) { int32_t& dst = (p.exprs[n].aux & kAuxInQual) ? qual_err : row_err; if (!dst) dst = e; }
-    }
-    if (qual_err) { my_err = my_err > 0 ? my_err : qual_err; continue; }   // an error inside a qual: raised whether or not the row passes
-    bool pass = true;
-    for (int f = 0; f < p.n_filters; ++f) pass = pass && (vals[p.filters[f]].i > 0);
-    if (!pass) continue;
-    if (row_err) { my_err = my_err > 0 ? my_err : row_err; continue; }
-    uint32_t idx;
-    if (kStrategy == HDK_B200_STRATEGY_BASELINE) {
-      const int64_t entry = baseline_entry(args, p.n_keys, [&](int k) { return p.keys[k].expr; }, vals);
-      if (entry < 0) { if (my_err <= 0) my_err = -HDK_B200_ERR_OUT_OF_SLOTS; continue; }
-      idx = uint32_t(entry);
-    } else {
-      int64_t h = 0;
-      for (int k = 0; k < p.n_keys; ++k) {
-        const DKey& ky = p.keys[k];
-        int64_t v = vals[ky.expr].i;
-        if (ky.has_nulls && v == int_null_of(ky.width)) v = ky.null_translated;
-        int64_t term = v - ky.min_val;
-        if (ky.bucket) term /= ky.bucket;   // (get_group_value_fast / perfect_key_hash divide by the bucket)
-        h += term * ky.mult;
-      }
-      idx = uint32_t(h);
-      if (idx >= p.entry_count) { my_err = my_err > 0 ? my_err : 1003; continue; }  // key outside the range the layout was built for
-    }
-    for (int a = 0; a < p.n_acc; ++a) {
-      const DAcc acc = p.accs[a];
-      // shared-memory bins of a CNT_NN accumulator count the NULL rows (rare) instead of the non-NULL ones;
-      // the flush converts: non-null = rows - nulls.  The global work table always holds non-null counts.
-      const bool count_nulls = acc.kind == ACC_CNT_NN && kStrategy != HDK_B200_STRATEGY_GLOBAL && kStrategy != HDK_B200_STRATEGY_BASELINE;
-      if (acc_arg_is_null(p, acc, vals) != count_nulls) continue;
-      accumulate_one<kStrategy>(args, bins, tid, a, acc, idx, acc_input(p, acc, vals));
-    }
+    // next combination: advance the innermost level that was probed and has matches left
+    int l = (dead ? lvl : J) - 1;
+    while (l >= 0 && ++cur[l] >= n_matches[l]) --l;
+    if (l < 0) break;
+    lvl = l + 1;
   }
 }
 
@@ -308,6 +337,7 @@ __device__ __forceinline__ bool eval_row_static(const ScanArgs& args, const uint
     if (idx >= rp.entry_count) return false;
   } else {
     const int64_t entry = baseline_entry(args, sp.n_keys, [&](int k) { constexpr DPlan sp = Shape::get(); return sp.keys[k].expr; }, vals);
+    if (entry == kClaimTimedOut) { my_err = my_err > 0 ? my_err : HDK_B200_ERR_CLAIM_TIMEOUT; return false; }
     if (entry < 0) { if (my_err <= 0) my_err = -HDK_B200_ERR_OUT_OF_SLOTS; return false; }
     idx = uint32_t(entry);
   }

@@ -1068,7 +1068,8 @@ class Executor:
                 code = self._agree_on_error(prep["err"])
                 if code != 0:
                     raise QueryError(code, {1: "division by zero", 7: "overflow or underflow", 1004: "a peer's partial table never arrived",
-                                            1003: "group key outside the range of the perfect-hash layout"}.get(code, "runtime error"))
+                                            1003: "group key outside the range of the perfect-hash layout",
+                                        1005: "baseline hash: a claimed entry was never published"}.get(code, "runtime error"))
                 if unit.order_by:
                     cols, n = self.compact_on_device(pq, prep["out"], to_host=False)
                     order = ResultSet(pq, np.zeros(0, dtype=np.uint8), dicts).order_entries()
@@ -1246,7 +1247,8 @@ class Executor:
                 continue
             if code != 0:
                 raise QueryError(code, {1: "division by zero", 7: "overflow or underflow",
-                                        1003: "group key outside the range of the perfect-hash layout"}.get(code, "runtime error"))
+                                        1003: "group key outside the range of the perfect-hash layout",
+                                        1005: "baseline hash: a claimed entry was never published"}.get(code, "runtime error"))
             dicts = {}
             tables = [outer] + [self.storage.get_table(j.inner_table) for j in unit.joins]
             for t, e in enumerate(unit.target_exprs):

@@ -565,6 +565,7 @@ HDK_B200_API int hdk_b200_shuffle_scatter_to(const hdk_b200_plan* plan, const hd
 #define HDK_B200_MAX_PEERS 16
 #define HDK_B200_IPC_HANDLE_BYTES 64
 #define HDK_B200_ERR_PEER_TIMEOUT 1004 /* a peer's flag did not arrive (in-band error code, positive = persistent) */
+#define HDK_B200_ERR_CLAIM_TIMEOUT 1005 /* baseline hash: a claimed entry's key was never published (bounded wait of the claim protocol) */
 HDK_B200_API int hdk_b200_peer_alloc(size_t bytes, void** dev_ptr, uint8_t handle[HDK_B200_IPC_HANDLE_BYTES]);
 HDK_B200_API int hdk_b200_peer_open(const uint8_t handle[HDK_B200_IPC_HANDLE_BYTES], void** dev_ptr);
 HDK_B200_API int hdk_b200_peer_close(void* dev_ptr);

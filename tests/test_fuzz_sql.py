@@ -138,7 +138,7 @@ def test_fuzz_gpu_vs_sqlite(seed, config):
 
 
 # ---- joins: one-to-one and one-to-many perfect tables, composite keys (baseline tables, both layouts), two-join chains whose
-# second key comes from the fact or from the first inner table; NULL-able keys on both sides
+# second key comes from the fact or from the first inner table, two one-to-many tables per plan; NULL-able keys on both sides
 def join_tables(seed):
     import numpy as np
     import pyarrow as pa
@@ -171,10 +171,17 @@ def join_queries(seed, n):
             joins.append("JOIN d2 j1 ON f0.a = j1.a" if r.random() < 0.5 else "JOIN d2 j1 ON f0.b = j1.b AND f0.a = j1.a")
             cols += ["j1.h"]
             fcols += ["j1.x"]
-        else:
+        elif p < 0.87:
             joins.append("JOIN d1 j1 ON f0.a = j1.a")
             joins.append("JOIN d3 j2 ON f0.c = j2.c" if r.random() < 0.5 else "JOIN d3 j2 ON j1.w - 4 = j2.c")
             cols += ["j1.w", "j1.g", "j2.p"]
+        else:
+            # two one-to-many tables in one plan (nested matching sets): both keyed by the fact table, or the second
+            # chained behind an inner column of the first
+            joins.append("JOIN d2 j1 ON f0.a = j1.a")
+            joins.append("JOIN d2 j2 ON f0.b = j2.b" if r.random() < 0.5 else "JOIN d2 j2 ON j1.h = j2.b")
+            cols += ["j1.h", "j2.h", "j2.a"]
+            fcols += ["j2.x"]
 
         def ie(d=0):
             q = r.random()

@@ -513,7 +513,11 @@ def one_to_many_tables():
     dim = pa.table({"a": rng.integers(0, 45, m).astype(np.int32),
                     "b": pa.array(rng.integers(0, 6, m).astype(np.int64), mask=rng.random(m) < 0.1),
                     "w": rng.integers(0, 7, m).astype(np.int32), "g": rng.integers(0, 4, m).astype(np.int16)})
-    return {"fact": fact, "dim": dim}
+    # a second dimension with duplicate keys (joined to the fact table or chained behind `dim`) and a unique one
+    dim2 = pa.table({"k": rng.integers(0, 7, 20).astype(np.int32), "z": rng.integers(-5, 5, 20).astype(np.int32),
+                     "h": rng.integers(0, 3, 20).astype(np.int16)})
+    uniq = pa.table({"k": rng.permutation(8)[:6].astype(np.int32), "u": rng.integers(0, 100, 6).astype(np.int64)})
+    return {"fact": fact, "dim": dim, "dim2": dim2, "uniq": uniq}
 
 
 # duplicate keys on the build side: NeedsOneToManyHash → offsets | counts | payload (JHT/PerfectJoinHashTable.cpp:861-886), and
@@ -524,6 +528,15 @@ ONE_TO_MANY_JOIN_QUERIES = [
     "SELECT d.g, COUNT(*), SUM(f.v), MIN(d.w), MAX(d.w) FROM fact f JOIN dim d ON f.a = d.a AND f.b = d.b GROUP BY d.g",
     "SELECT COUNT(*), SUM(d.w) FROM fact f JOIN dim d ON f.a = d.a AND f.b = d.b WHERE d.w > 2 AND f.v < 50",
     "SELECT f.a, COUNT(*), AVG(d.w) FROM fact f JOIN dim d ON f.b = d.b AND f.a = d.a GROUP BY f.a",
+]
+# several one-to-many joins in one plan: the matching sets nest (the reference's JoinLoop nest, one Set loop per such join) —
+# two on the fact table, one chained behind the other's inner column, mixed with a one-to-one table, a filter between levels
+MULTI_ONE_TO_MANY_JOIN_QUERIES = [
+    "SELECT d.g, e.h, COUNT(*), SUM(f.v), SUM(d.w), SUM(e.z) FROM fact f JOIN dim d ON f.a = d.a JOIN dim2 e ON f.b = e.k GROUP BY d.g, e.h",
+    "SELECT e.h, COUNT(*), SUM(f.v * e.z), MIN(d.w), MAX(e.z) FROM fact f JOIN dim d ON f.a = d.a JOIN dim2 e ON d.w = e.k GROUP BY e.h",
+    "SELECT d.g, COUNT(*), SUM(u.u), SUM(e.z) FROM fact f JOIN dim d ON f.a = d.a JOIN uniq u ON d.w = u.k JOIN dim2 e ON f.b = e.k "
+    "WHERE d.w < 6 AND e.z <> 0 GROUP BY d.g",
+    "SELECT COUNT(*), SUM(d.w + e.z) FROM fact f JOIN dim d ON f.a = d.a AND f.b = d.b JOIN dim2 e ON d.g = e.h WHERE f.v > -50",
 ]
 
 
@@ -537,6 +550,20 @@ def test_one_to_many_joins_vs_sqlite(oracle_mod, text, kind):
     assert err == 0
     util.oracle_inputs(oracle_mod, st, pq)            # (describes the host-built tables in pq.plan)
     assert pq.plan.joins[0].one_to_many == 1
+    got = decode_with_dictionaries(st, pq, buf)
+    util.assert_rows_equal(sorted(got, key=repr), sorted(util.sqlite_rows(tables, text, 0), key=repr), rel=1e-9)
+
+
+@pytest.mark.parametrize("text", MULTI_ONE_TO_MANY_JOIN_QUERIES)
+@pytest.mark.parametrize("kind", ["port", "reference"])
+def test_several_one_to_many_joins_vs_sqlite(oracle_mod, text, kind):
+    tables = one_to_many_tables()
+    st = util.make_storage(tables, fragment_size=700)
+    pq = util.plan_sql(st, text)
+    buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
+    assert err == 0
+    util.oracle_inputs(oracle_mod, st, pq)
+    assert sum(pq.plan.joins[j].one_to_many for j in range(pq.plan.n_joins)) >= 2
     got = decode_with_dictionaries(st, pq, buf)
     util.assert_rows_equal(sorted(got, key=repr), sorted(util.sqlite_rows(tables, text, 0), key=repr), rel=1e-9)
 
