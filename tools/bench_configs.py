@@ -29,7 +29,12 @@ def peak():
     return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
 
 
+ITERS = None   # --iters: total launches per query (profiling runs: 2 = one warm-up + one measured)
+
+
 def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label="", force=None):
+    if ITERS:
+        reps = max(ITERS - 2, 0)
     unit = sql.parse(text, ex.storage.tables)
     pq = ex.plan(unit, guess)
     prep = ex.prepare(pq)
@@ -42,6 +47,7 @@ def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label="", forc
     if force is not None:   # hdk_b200_debug_set: force an accumulation strategy
         _lib.debug_set("force_strategy", force)
         label += f" [forced strategy {force}]"
+    warm = 2 if reps else 1
     for i in range(reps + 2):
         torch.cuda.synchronize()
         e0.record()
@@ -52,7 +58,7 @@ def time_query(ex, text, bytes_per_row, rows, reps=5, guess=None, label="", forc
         info = ex.launch(pq, prep, ko)
         e2.record()
         torch.cuda.synchronize()
-        if i >= 2:
+        if i >= warm:
             times.append(e1.elapsed_time(e2))
             tot.append(e0.elapsed_time(e2))
     if force is not None:
@@ -140,7 +146,10 @@ def main():
     ap.add_argument("--force", action="store_true", help="also time the GLOBAL strategy where it is an alternative")
     ap.add_argument("--cpu", action="store_true", help="also time the reference's CPU path (oracle/_ref) on a host slice of each config")
     ap.add_argument("--cpu-rows", type=int, default=8_000_000)
+    ap.add_argument("--iters", type=int, default=0, help="total launches per query (0 = the per-config defaults); 2 for ncu captures")
     args = ap.parse_args()
+    global ITERS
+    ITERS = args.iters
     dev = torch.device("cuda", 0)
     only = args.only.split(",")
     out = []

@@ -23,7 +23,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 def main():
     rep = sys.argv[1]
     pat = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None
-    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True)
+    # (a .csv argument is the `--page raw --csv` export itself: reports too big to pull from the GPU box are exported there)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True)
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -31,7 +32,7 @@ def main():
         name = r[idx["Kernel Name"]]
         if pat and not pat.search(name):
             continue
-        print("====", name[:90])
+        print("====", name[:90], r[idx["Demangled Name"]][:120] if "Demangled Name" in idx else "")
         for w in WANT:
             if w in idx:
                 print(f"  {w:70s} {r[idx[w]]:>16s} {units[idx[w]]}")
