@@ -186,7 +186,9 @@ def per_config_single_gpu(device, peak, reps=5, cpu=True, only=("c1", "c3", "c4"
             pq, prep, ms_all, ms, info = time_launch(ex, text, 20)
             out[name] = _entry(name, 10_000_000, 12, ms, ms_all, peak, info, pq, check_c1(ex, pq, prep, st, col),
                                {"workload": "BASELINE.json configs[0]: 10 M rows, int32 key with 1 K distinct values: " + text,
-                                "note": "launch bound: 120 MB of input is 18 µs at the HBM peak; three launches (init, scan, finalize)"})
+                                "note": "not HBM-bound: 120 MB of input is 18 µs at the HBM peak; the scan kernel sits on the SM's shared-memory pipe "
+                                        "(COUNT + SUM + MIN + MAX into 1000 bins = 40 shared wavefronts per 32 rows = 43 µs of pipe time per launch, "
+                                        "profiles/README.md round 2) + three launches (init, scan, finalize)"})
         if cpu:
             out["c1_int64"]["cpu_baseline"] = cpu_sample(lambda s, n: benchdata.make_c1(s, device, rows=n, keep_host=True), benchdata.C1_QUERY, 10_000_000)
         del ex, st
@@ -217,7 +219,12 @@ def per_config_single_gpu(device, peak, reps=5, cpu=True, only=("c1", "c3", "c4"
         pq, prep, ms_all, ms, info = time_launch(ex, benchdata.C5_QUERY, reps)
         out["c5_star_join"] = _entry("c5_star_join", rows, benchdata.C5_BYTES_PER_ROW, ms, ms_all, peak, info, pq, check_c5(ex, pq, prep, st, dim_rows),
                                      {"workload": "BASELINE.json configs[4]: 2 B-row fact x 10 M-row dimension star join + group-by SUM (x scale)",
-                                      "join_build_ms_first_call": build_ms, "dim_rows": dim_rows})
+                                      "join_build_ms_first_call": build_ms, "dim_rows": dim_rows,
+                                      "second_roof": {"bound": "l1tex request rate (one random gather per row = 1.0 SM cycle per row, measured: "
+                                                               "profiles/r2_gather_accum.log)", "gather_only_floor_ms": rows / (148 * 1.965e9) * 1e3,
+                                                      "frac_of_gather_roof": rows / (148 * 1.965e9) * 1e3 / ms},
+                                      "note": "not HBM-bound: ncu counts 1.02 gather sectors + 0.92 shared wavefronts per row through the same "
+                                              "L1TEX pipe (profiles/README.md round 2)"})
         if cpu:
             out["c5_star_join"]["cpu_baseline"] = cpu_sample(lambda s, n: benchdata.make_star(s, device, n, dim_rows, fragment_rows=1_000_000, keep_host=True),
                                                              benchdata.C5_QUERY, cpu_rows)

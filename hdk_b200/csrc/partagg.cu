@@ -7,7 +7,7 @@
 // the key — QE/RowFuncBuilder.cpp:516-577 — so that every partition aggregates on its own).  Here the same idea runs
 // INSIDE one GPU, down to partitions whose groups fit a CTA's shared memory:
 //
-//   1. count      every row's key → partition = key hash range-reduced to P = F1 x F2 (<= 32768); per-CTA shared histogram
+//   1. count      every row's key → partition = key hash range-reduced to P = F1 x F2 (<= 255 x 128); per-CTA shared histogram
 //   2. offsets    exclusive scan of the P counters (one CTA)
 //   3. scatter    one or two passes, each splitting <= 256 ways.  A row that passes the filters becomes a packed RECORD
 //                 (key values ‖ aggregate arguments, 4-byte words).  A CTA regroups a tile of 4096 rows by destination
@@ -41,9 +41,9 @@
 
 namespace hb {
 
-constexpr uint32_t kPaMaxPartitions = 32768;
+constexpr uint32_t kPaMaxPartitions = 255 * 128;   // <= 255 level-1 destinations x <= 128 level-2 destinations
 constexpr uint32_t kPaMaxFragments = 4096;
-constexpr uint32_t kPaFanout = 256;          // destinations of one scatter pass
+constexpr uint32_t kPaFanout = 255;          // destinations of one scatter pass (a tile's per-vector destination is a byte, 0xff = padding)
 constexpr int kPaThreads = 512;
 constexpr int kPaMaxTileRows = 4096;         // rows regrouped per tile (ranks fit 16 bits, destinations 8)
 constexpr int kPaCountRows = 8;              // rows per thread per tile of the count pass
@@ -944,7 +944,7 @@ static int partagg_geometry(const Lowered& lw, const PaLayout& L, uint64_t total
   if (g_debug.pa_partitions > 0) P = uint64_t(g_debug.pa_partitions);
   P = std::max<uint64_t>(1, std::min<uint64_t>(P, kPaMaxPartitions));
   uint32_t f2 = 0;
-  while ((P >> f2) > kPaFanout) ++f2;                         // F2 = 2^f2 final partitions per level-1 destination
+  while (((P + (uint64_t(1) << f2) - 1) >> f2) > kPaFanout) ++f2;   // F2 = 2^f2 final partitions per level-1 destination; F1 = ceil(P / F2) <= 255
   const uint32_t F1 = uint32_t((P + (uint64_t(1) << f2) - 1) >> f2);
   g->F1 = F1;
   g->F2_log2 = f2;

@@ -146,10 +146,13 @@ def main():
     ap.add_argument("--force", action="store_true", help="also time the GLOBAL strategy where it is an alternative")
     ap.add_argument("--cpu", action="store_true", help="also time the reference's CPU path (oracle/_ref) on a host slice of each config")
     ap.add_argument("--cpu-rows", type=int, default=8_000_000)
+    ap.add_argument("--pa-partitions", type=int, default=0, help="force the partition count of the partitioned aggregation (0 = auto)")
     ap.add_argument("--iters", type=int, default=0, help="total launches per query (0 = the per-config defaults); 2 for ncu captures")
     args = ap.parse_args()
     global ITERS
     ITERS = args.iters
+    if args.pa_partitions:
+        _lib.debug_set("partitioned_partitions", args.pa_partitions)
     dev = torch.device("cuda", 0)
     only = args.only.split(",")
     out = []
