@@ -388,7 +388,14 @@ int dump_shape_text(const DPlan& p, char* out, size_t cap) {
   s += "},\n  {";
   for (int i = 0; i < p.n_keys; ++i) add("{0, 0, 0, 0, %d, %d, %d, 0, 0}%s", p.keys[i].expr, p.keys[i].has_nulls, p.keys[i].width, i + 1 < p.n_keys ? ", " : "");
   s += "},\n  {";
-  for (int i = 0; i < p.n_joins; ++i) add("{0, 0, 0, %d, %d, %d, 0, 0}%s", p.joins[i].key_expr, p.joins[i].key_nullable, p.joins[i].one_to_many, i + 1 < p.n_joins ? ", " : "");
+  for (int i = 0; i < p.n_joins; ++i) {
+    // (baseline join tables — composite / wide-range keys — probe with their component nodes: part of the structure; the
+    //  component width stays a run-time property like the key range)
+    const DJoin& j = p.joins[i];
+    add("{0, 0, 0, %d, %d, %d, 0, 0, %d, 0, 0, 0, {", j.key_expr, j.key_nullable, j.one_to_many, j.n_key_exprs);
+    for (int k = 0; k < HDK_B200_MAX_KEYS; ++k) add("%d%s", k < j.n_key_exprs ? j.key_exprs[k] : 0, k + 1 < HDK_B200_MAX_KEYS ? ", " : "");
+    add("}, 0}%s", i + 1 < p.n_joins ? ", " : "");
+  }
   s += "},\n  {";
   for (int i = 0; i < p.n_acc; ++i) add("{%d, %d, %d, %d}%s", p.accs[i].kind, p.accs[i].arg, p.accs[i].arg_nullable, p.accs[i].bytes, i + 1 < p.n_acc ? ", " : "");
   s += "},\n  {";

@@ -103,3 +103,63 @@ def test_jit_fuzz_vs_sqlite(jit_sync):
         compared += 1
     st_ = jit_sync.jit_stats()
     assert compared > 12 and st_["shapes_failed"] == 0 and st_["launches"] >= compared
+
+
+def test_harvested_reference_queries_run_specialised(jit_sync):
+    """The queries harvested from the reference's own Select.* tests (tests/test_sqlite_oracle.py) with every plan shape
+    compiled at run time BEFORE its launch ("jit" = 2), rows vs SQLite: the specialised kernels, not the interpreter, give
+    the reference's answers.  Every 5th query by default (a compile costs ~2 s of host time per new shape);
+    HDK_B200_JIT_FULL=1 runs all of them (the log of such a run is profiles/r2_jit_harvested_full.log)."""
+    import os
+    import hdk_b200.hdk as hdk_mod
+    from hdk_b200 import planner
+    from tests.test_sqlite_oracle import REFERENCE_HARVESTED_QUERIES, harvested_tables
+    tables = harvested_tables()
+    h = hdk_mod.init()
+    for name, t in tables.items():
+        h.import_arrow(t, name, fragment_size=2)
+    texts = [q for qs in REFERENCE_HARVESTED_QUERIES.values() for q in qs]
+    stride = 1 if os.environ.get("HDK_B200_JIT_FULL") else 5
+    before = jit_sync.jit_stats()
+    specialised = interpreted = 0
+    for text in texts[::stride]:
+        res = h.sql(text)
+        got = [tuple(r.values()) for r in res.to_arrow().to_pylist()]
+        exp = util.sqlite_rows(tables, text, 0)
+        if "ORDER BY" not in text.upper():
+            got, exp = sorted(got, key=repr), sorted(exp, key=repr)
+        try:
+            util.assert_rows_equal(got, exp, rel=1e-6)
+        except AssertionError as e:
+            raise AssertionError(f"{text}: {e}")
+        info = res.launch_info
+        if info is not None and info.variant > 0:
+            specialised += 1
+        else:
+            interpreted += 1      # one-to-many joins and queries that read no column stay on the interpreter / launch nothing
+    after = jit_sync.jit_stats()
+    print(f"harvested queries: {specialised} specialised, {interpreted} interpreted, "
+          f"{after['shapes_compiled'] - before['shapes_compiled']} shapes compiled in {after['total_compile_ms'] - before['total_compile_ms']:.0f} ms")
+    assert after["shapes_failed"] == before["shapes_failed"]
+    assert specialised >= 0.8 * (specialised + interpreted)
+
+
+@pytest.mark.parametrize("text,nk", util.COMPOSITE_JOIN_QUERIES + [(util.NON_GROUPED_QUERIES[3], 0)])
+def test_jit_kernels_probe_baseline_join_tables(oracle_mod, jit_sync, text, nk):
+    """Run-time specialised kernels over BASELINE join tables (composite keys; a single key whose range is too wide for a
+    perfect table): the table kind and its component nodes are structure of the plan shape.  (Found by running every harvested
+    query specialised: the shape text once left the components out and the kernel probed the table as a perfect one.)"""
+    import torch
+    from hdk_b200 import sql
+    from hdk_b200.executor import Executor
+    from tests.test_gpu_parity import check_against_oracle
+    st = util.make_storage(util.composite_join_tables(), fragment_size=1300)
+    ex = Executor(st)
+    pq = ex.plan(sql.parse(text, st.tables))
+    prep = ex.prepare(pq)
+    info = ex.launch(pq, prep)
+    torch.cuda.synchronize()
+    assert int(prep["err"].item()) == 0
+    assert any(pq.plan.joins[j].n_key_exprs > 0 for j in range(pq.plan.n_joins))
+    assert info.variant == abi.VARIANT_JIT
+    check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), max(nk, 1))
