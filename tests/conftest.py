@@ -36,10 +36,11 @@ def oracle_mod():
 @pytest.fixture(autouse=True, scope="session")
 def _deterministic_kernels():
     """Run-time specialisation compiles in the background by default: which kernel a launch gets would then depend on timing.
-    The suite pins it off; the JIT tests switch it to "compile before the launch" themselves."""
+    The suite pins it off; the JIT tests switch it to "compile before the launch" themselves.  HDK_B200_TEST_JIT=2 runs the
+    whole suite with every plan shape specialised before its launch instead (slow: ~2 s of NVRTC per new shape)."""
     try:
         from hdk_b200 import _lib
-        _lib.debug_set("jit", 0)
+        _lib.debug_set("jit", int(os.environ.get("HDK_B200_TEST_JIT", "0")))
     except Exception:      # library not built: the tests that need it fail on their own
         pass
     yield
