@@ -29,7 +29,7 @@ EXPORTS = [
     "hdk_b200_materialize_nulls_on_device", "hdk_b200_peer_alloc", "hdk_b200_peer_open", "hdk_b200_peer_close",
     "hdk_b200_peer_free", "hdk_b200_exchange_bytes", "hdk_b200_exchange_init", "hdk_b200_launch_exchange", "hdk_b200_query_host", "hdk_b200_last_error", "hdk_b200_abi_version",
     "hdk_b200_device_count", "hdk_b200_launch_count", "hdk_b200_launch_scratch_bytes", "hdk_b200_debug_set",
-    "hdk_b200_jit_get_stats", "hdk_b200_jit_wait", "hdk_b200_arrow_column_on_device",
+    "hdk_b200_jit_get_stats", "hdk_b200_jit_wait", "hdk_b200_jit_shutdown", "hdk_b200_arrow_column_on_device",
 ]
 
 
@@ -86,6 +86,7 @@ def _bind(lib):
         "hdk_b200_debug_set": (ci, [C.c_char_p, ci]),
         "hdk_b200_jit_get_stats": (ci, [C.POINTER(abi.JitStats)]),
         "hdk_b200_jit_wait": (ci, []),
+        "hdk_b200_jit_shutdown": (ci, []),
         "hdk_b200_arrow_column_on_device": (ci, [vp, u64, ci, ci, ci, ci, i64, C.c_double, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -105,6 +106,10 @@ def lib():
         _lib = _bind(C.CDLL(LIB_PATH))
         if _lib.hdk_b200_abi_version() != abi.ABI_VERSION:
             raise HdkB200Error("libhdk_b200.so ABI version mismatch; rebuild")
+        # the run-time compiler's worker thread must not outlive the libraries it uses: stop it at interpreter exit, ahead of
+        # every C-level exit handler (hdk_b200_jit_shutdown waits for the compile in flight, a few seconds at most)
+        import atexit
+        atexit.register(_lib.hdk_b200_jit_shutdown)
     return _lib
 
 

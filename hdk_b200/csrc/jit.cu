@@ -106,7 +106,11 @@ static Nvrtc& nvrtc() {
   return n;
 }
 
-enum { kCompiling = 0, kReady = 1, kFailed = 2 };
+// kCompiled: the cubin exists but is not loaded yet.  The worker thread only runs NVRTC (host code); everything that touches
+// the CUDA runtime — cudaLibraryLoadData, cudaLibraryGetKernel — happens on the next launching thread that asks for the
+// shape (load_entry), so no CUDA call of ours can race the runtime's teardown at process exit.
+enum { kCompiling = 0, kReady = 1, kFailed = 2, kCompiled = 3 };
+struct JitWant { int strategy, g, slot; bool reg; };
 struct JitEntry {
   int state = kCompiling;
   StaticEntry e{};
@@ -114,7 +118,11 @@ struct JitEntry {
   DPlan plan;
   uint64_t sig = 0;
   int dev = 0;
+  int iter_rows = 1;
   std::string name;
+  std::vector<char> cubin;
+  std::vector<JitWant> wants;
+  std::vector<std::string> lowered;   // mangled kernel names, parallel to wants
 };
 
 // (never destroyed: the detached worker may still wait on them when the process exits)
@@ -123,6 +131,7 @@ std::condition_variable& g_cv = *new std::condition_variable;
 std::map<uint64_t, JitEntry*>& g_table = *new std::map<uint64_t, JitEntry*>;
 std::deque<JitEntry*>& g_queue = *new std::deque<JitEntry*>;
 bool g_worker_started = false;
+constexpr size_t kMaxShapes = 4096;   // loaded cubins kept for the life of the process (~100 KB of device code each)
 constexpr size_t kMaxQueue = 16;   // shapes waiting beyond this are simply not specialised (they keep running interpreted)
 
 static bool wants_registers(const DPlan& p) {   // = shape_wants_registers (scan.cu)
@@ -141,8 +150,7 @@ static void compile_entry(JitEntry* je) {
   std::string src = "#define HB_JIT 1\n#include \"scan_kernel.cuh\"\nnamespace hb {\ntemplate <> struct StaticShape<1000> {\n"
                     "  static constexpr bool is_static = true;\n  static constexpr int rows_per_iter = " + std::to_string(rpi) + ";\n"
                     "  __host__ __device__ static constexpr DPlan get() { return DPlan " + std::string(shape.data()) + "; }\n};\n}\n";
-  struct Want { int strategy, g, slot; bool reg; };
-  std::vector<Want> wants;
+  std::vector<JitWant> wants;
   if (p.hash_type == HDK_B200_BASELINE_HASH) {
     wants.push_back({HDK_B200_STRATEGY_BASELINE, 8, HDK_B200_STRATEGY_BASELINE, false});
   } else {
@@ -157,7 +165,7 @@ static void compile_entry(JitEntry* je) {
   std::vector<std::string> exprs;
   if (ok) ok = n.create(&prog, src.c_str(), "hdk_b200_jit.cu", int(texts.size()), texts.data(), names.data()) == NVRTC_SUCCESS;
   if (ok) {
-    for (const Want& w : wants) {
+    for (const JitWant& w : wants) {
       exprs.push_back("hb::scan_kernel<" + std::to_string(w.strategy) + ", hb::StaticShape<1000>, " + std::to_string(w.g) + ">");
       ok = ok && n.add_name(prog, exprs.back().c_str()) == NVRTC_SUCCESS;
     }
@@ -178,25 +186,11 @@ static void compile_entry(JitEntry* je) {
     ok = n.cubin_size(prog, &cs) == NVRTC_SUCCESS && cs > 0;
     if (ok) { cubin.resize(cs); ok = n.cubin(prog, cubin.data()) == NVRTC_SUCCESS; }
   }
-  StaticEntry e{};
-  cudaLibrary_t lib = nullptr;
-  if (ok) {
-    ok = cudaSetDevice(je->dev) == cudaSuccess &&
-         cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess;
-    for (size_t i = 0; ok && i < wants.size(); ++i) {
-      const char* lowered = nullptr;
-      cudaKernel_t k = nullptr;
-      ok = n.lowered(prog, exprs[i].c_str(), &lowered) == NVRTC_SUCCESS && cudaLibraryGetKernel(&k, lib, lowered) == cudaSuccess;
-      if (!ok) break;
-      ScanKernelFn fn = reinterpret_cast<ScanKernelFn>(k);
-      if (wants[i].reg) {
-        e.reg_fn[wants[i].slot] = fn;
-        if (wants[i].g == 8) e.fn[HDK_B200_STRATEGY_REGISTER] = fn;
-      } else {
-        e.fn[wants[i].slot] = fn;
-      }
-    }
-    if (!ok) cudaGetLastError();
+  std::vector<std::string> lowered;
+  for (size_t i = 0; ok && i < wants.size(); ++i) {
+    const char* name = nullptr;
+    ok = n.lowered(prog, exprs[i].c_str(), &name) == NVRTC_SUCCESS && name;
+    if (ok) lowered.push_back(name);
   }
   if (prog) n.destroy(&prog);
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -206,14 +200,11 @@ static void compile_entry(JitEntry* je) {
       int mw = 1;
       for (int c = 0; c < p.n_cols; ++c) mw = p.col_width[c] > mw ? p.col_width[c] : mw;
       const int vw = 16 / mw;                                   // = shape_iter_rows<Shape>() (scan_kernel.cuh)
-      e.iter_rows = rpi > vw ? rpi / vw * vw : vw;
-      e.sig = je->sig;
-      je->name = "jit_" + std::to_string(je->sig);
-      e.name = je->name.c_str();
-      je->e = e;
-      je->lib = lib;
-      je->state = kReady;
-      ++g_jit_stats.compiled;
+      je->iter_rows = rpi > vw ? rpi / vw * vw : vw;
+      je->cubin.swap(cubin);
+      je->wants = wants;
+      je->lowered.swap(lowered);
+      je->state = kCompiled;
     } else {
       je->state = kFailed;
       ++g_jit_stats.failed;
@@ -221,15 +212,52 @@ static void compile_entry(JitEntry* je) {
     }
     g_jit_stats.last_compile_ms = ms;
     g_jit_stats.total_compile_ms += ms;
-    --g_jit_stats.pending;
+    --g_jit_stats.pending;   // (pending = queued or compiling; a compiled shape is loaded by the next launch that asks for it)
   }
   g_cv.notify_all();
 }
 
-// Process exit while a compile is in flight: the detached worker would still be inside NVRTC / the CUDA runtime when their
-// static state is torn down (observed: SIGSEGV at interpreter exit of a short script).  An atexit handler — registered at
-// the first background request, i.e. after the CUDA runtime's own, so it runs before them — drops the queue and waits
-// for the compile in flight (<= a few seconds).
+// second half, on a launching thread (g_mutex held, the thread's current device is je->dev): load the cubin, look the kernels up
+static void load_entry(JitEntry* je) {
+  StaticEntry e{};
+  cudaLibrary_t lib = nullptr;
+  bool ok = cudaLibraryLoadData(&lib, je->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess;
+  for (size_t i = 0; ok && i < je->wants.size(); ++i) {
+    cudaKernel_t k = nullptr;
+    ok = cudaLibraryGetKernel(&k, lib, je->lowered[i].c_str()) == cudaSuccess;
+    if (!ok) break;
+    ScanKernelFn fn = reinterpret_cast<ScanKernelFn>(k);
+    const JitWant& w = je->wants[i];
+    if (w.reg) {
+      e.reg_fn[w.slot] = fn;
+      if (w.g == 8) e.fn[HDK_B200_STRATEGY_REGISTER] = fn;
+    } else {
+      e.fn[w.slot] = fn;
+    }
+  }
+  if (!ok) cudaGetLastError();
+  std::vector<char>().swap(je->cubin);
+  if (ok) {
+    e.iter_rows = je->iter_rows;
+    e.sig = je->sig;
+    je->name = "jit_" + std::to_string(je->sig);
+    e.name = je->name.c_str();
+    je->e = e;
+    je->lib = lib;
+    je->state = kReady;
+    ++g_jit_stats.compiled;
+  } else {
+    je->state = kFailed;
+    ++g_jit_stats.failed;
+  }
+}
+
+// Process exit while a compile is in flight: the detached worker would still be inside NVRTC when static state it uses is
+// torn down (observed: SIGSEGV at interpreter exit of short scripts; NVRTC loads libnvrtc-builtins lazily, so its
+// destructors can be registered AFTER any handler of ours and run before it).  hdk_b200_jit_shutdown() drops the queue and
+// waits for the compile in flight (<= a few seconds): a host calls it before it exits — the Python binding registers it with
+// `atexit`, which runs ahead of every C-level exit handler; std::atexit keeps a best-effort copy for other hosts.  The worker
+// never calls the CUDA runtime (see kCompiled), so it cannot race the runtime's own teardown either.
 bool g_shutdown = false;
 int g_busy = 0;
 static void jit_shutdown() {
@@ -270,8 +298,10 @@ const StaticEntry* jit_scan_kernels(const DPlan& p, uint64_t sig, bool wait) {
   std::unique_lock<std::mutex> lock(g_mutex);
   auto it = g_table.find(sig);
   JitEntry* je = it == g_table.end() ? nullptr : it->second;
+  if (je && !same_plan_shape(je->plan, p)) return nullptr;   // signature collision: this shape stays on the interpreter
   if (!je) {
-    if (!wait && g_queue.size() >= kMaxQueue) return nullptr;
+    if (!wait && (g_shutdown || g_queue.size() >= kMaxQueue)) return nullptr;
+    if (g_table.size() >= kMaxShapes) return nullptr;         // the cache is full: further shapes stay on the interpreter
     je = new JitEntry();
     je->plan = p;
     je->sig = sig;
@@ -294,6 +324,7 @@ const StaticEntry* jit_scan_kernels(const DPlan& p, uint64_t sig, bool wait) {
     }
   }
   if (je->state == kCompiling && wait) g_cv.wait(lock, [je] { return je->state != kCompiling; });
+  if (je->state == kCompiled && je->dev == dev) load_entry(je);
   if (je->state != kReady) return nullptr;
   ++g_jit_stats.launches;
   return &je->e;
@@ -314,6 +345,11 @@ int hdk_b200_jit_get_stats(hdk_b200_jit_stats* out) {
   out->last_compile_ms = hb::g_jit_stats.last_compile_ms;
   out->total_compile_ms = hb::g_jit_stats.total_compile_ms;
   out->available = ok ? 1 : 0;
+  return HDK_B200_OK;
+}
+
+int hdk_b200_jit_shutdown(void) {
+  hb::jit_shutdown();
   return HDK_B200_OK;
 }
 

@@ -371,6 +371,37 @@ uint64_t plan_signature(const DPlan& p) {
   return h;
 }
 
+// Field-by-field equality of what plan_signature hashes: the run-time kernel cache compares a hit with the shape it was
+// compiled for, so a 64-bit signature collision degrades to the interpreter instead of running another shape's kernel.
+bool same_plan_shape(const DPlan& a, const DPlan& b) {
+  if (a.n_exprs != b.n_exprs || a.n_filters != b.n_filters || a.n_keys != b.n_keys || a.n_joins != b.n_joins || a.n_acc != b.n_acc ||
+      a.n_cols != b.n_cols || a.hash_type != b.hash_type)
+    return false;
+  for (int i = 0; i < a.n_exprs; ++i) {
+    const DExpr &x = a.exprs[i], &y = b.exprs[i];
+    if (x.op != y.op || x.a != y.a || x.b != y.b || x.aux != y.aux || x.kind != y.kind || x.width != y.width || x.nullable != y.nullable ||
+        x.guard != y.guard)
+      return false;
+    if ((x.op == HDK_B200_OP_COL || x.op == HDK_B200_OP_EXTRACT_YEAR || x.op == HDK_B200_OP_CASE) && x.imm.i != y.imm.i) return false;
+  }
+  for (int i = 0; i < a.n_filters; ++i)
+    if (a.filters[i] != b.filters[i]) return false;
+  for (int i = 0; i < a.n_keys; ++i)
+    if (a.keys[i].expr != b.keys[i].expr || a.keys[i].has_nulls != b.keys[i].has_nulls || a.keys[i].width != b.keys[i].width) return false;
+  for (int i = 0; i < a.n_joins; ++i) {
+    const DJoin &x = a.joins[i], &y = b.joins[i];
+    if (x.key_expr != y.key_expr || x.key_nullable != y.key_nullable || x.one_to_many != y.one_to_many || x.n_key_exprs != y.n_key_exprs) return false;
+    for (int k = 0; k < x.n_key_exprs; ++k)
+      if (x.key_exprs[k] != y.key_exprs[k]) return false;
+  }
+  for (int i = 0; i < a.n_acc; ++i)
+    if (a.accs[i].kind != b.accs[i].kind || a.accs[i].arg != b.accs[i].arg || a.accs[i].arg_nullable != b.accs[i].arg_nullable || a.accs[i].bytes != b.accs[i].bytes)
+      return false;
+  for (int i = 0; i < a.n_cols; ++i)
+    if (a.col_width[i] != b.col_width[i]) return false;
+  return true;
+}
+
 // C++ aggregate initialiser of the structural part of a DPlan (consumed by static_shapes.inc and by jit.cu)
 int dump_shape_text(const DPlan& p, char* out, size_t cap);
 static int dump_shape(const DPlan& p, char* out, size_t cap) { return dump_shape_text(p, out, cap); }

@@ -58,6 +58,7 @@ struct StaticEntry {   // the kernels of one plan shape: pre-compiled (static_sh
 // until it is done — the caller launches the interpreting kernel meanwhile).  nullptr also when NVRTC is unavailable.
 const StaticEntry* jit_scan_kernels(const DPlan& p, uint64_t sig, bool wait);
 int dump_shape_text(const DPlan& p, char* out, size_t cap);
+bool same_plan_shape(const DPlan& a, const DPlan& b);
 struct JitStats { unsigned long long compiled, failed, launches, pending; double last_compile_ms, total_compile_ms; };
 extern JitStats g_jit_stats;
 

@@ -108,6 +108,21 @@ __device__ __forceinline__ int row_partition(const ShuffleArgs& a, const int8_t*
   return partition_of_keys(a, keys, p.n_keys);
 }
 
+// Lanes of the warp whose row goes to the same partition as this lane's (0 for a dropped row, part < 0).  MATCH.ANY costs
+// over two SM cycles per row (tools/micro/gather_accum_bench.cu: the match_any variants); with the handful of partitions of a
+// multi-GPU exchange one ballot per partition is several times cheaper.  All 32 lanes must call it.
+__device__ __forceinline__ unsigned warp_peers(int part, uint32_t n_partitions) {
+  if (n_partitions <= 16) {
+    unsigned mine = 0;
+    for (uint32_t q = 0; q < n_partitions; ++q) {
+      const unsigned m = __ballot_sync(0xffffffffu, part == int(q));
+      if (part == int(q)) mine = m;
+    }
+    return mine;
+  }
+  return __match_any_sync(0xffffffffu, part);
+}
+
 __global__ void shuffle_scatter_kernel(const __grid_constant__ ShuffleArgs a) {
   V vals[HDK_B200_MAX_EXPRS];
   const DPlan& p = a.plan;
@@ -121,7 +136,7 @@ __global__ void shuffle_scatter_kernel(const __grid_constant__ ShuffleArgs a) {
     for (uint64_t pos = start; pos < rows_padded; pos += step) {
       const int part = pos < rows ? row_partition(a, cols, pos, vals) : -1;
       // warp-aggregated reservation: one atomic per distinct partition per warp
-      const unsigned peers = __match_any_sync(0xffffffffu, part);
+      const unsigned peers = warp_peers(part, a.n_partitions);
       if (part < 0) continue;
       const int leader = __ffs(peers) - 1;
       const int rank = __popc(peers & ((1u << lane) - 1));
@@ -225,7 +240,7 @@ __global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __g
       if (a.n_partitions > 32) {   // many partitions: lanes rarely meet, MATCH.ANY would cost one round per distinct value
         if (part[r] >= 0) atomicAdd(&hist[part[r]], 1u);
       } else {                     // warp-aggregated histogram update
-        const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+        const unsigned peers = warp_peers(part[r], a.n_partitions);
         if (part[r] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[part[r]], (unsigned)__popc(peers));
       }
     }
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __g
     if constexpr (kStaged) {
 #pragma unroll
       for (int r = 0; r < kShufRowsPerThread; ++r) {
-        const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+        const unsigned peers = warp_peers(part[r], a.n_partitions);
         if (part[r] < 0) continue;
         const int leader = __ffs(peers) - 1;
         unsigned int start = 0;
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __g
     } else {
 #pragma unroll
     for (int r = 0; r < kShufRowsPerThread; ++r) {
-      const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+      const unsigned peers = warp_peers(part[r], a.n_partitions);
       if (part[r] < 0) continue;
       const int leader = __ffs(peers) - 1;
       unsigned int start = 0;
@@ -395,7 +410,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) scatter_big_tile_kernel(const 
         if (many) {   // many partitions: lanes rarely meet, MATCH.ANY would cost one round per distinct value
           if (part[r] >= 0) atomicAdd(&hist[part[r]], 1u);
         } else {
-          const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+          const unsigned peers = warp_peers(part[r], a.n_partitions);
           if (part[r] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[part[r]], (unsigned)__popc(peers));
         }
       }
@@ -427,7 +442,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) scatter_big_tile_kernel(const 
         if (many) {
           if (part[r] >= 0) lp = run_start[part[r]] + atomicAdd(&hist[part[r]], 1u);
         } else {
-          const unsigned peers = __match_any_sync(0xffffffffu, part[r]);
+          const unsigned peers = warp_peers(part[r], a.n_partitions);
           if (part[r] >= 0) {
             const int leader = __ffs(peers) - 1;
             unsigned int start = 0;

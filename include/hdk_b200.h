@@ -694,6 +694,10 @@ typedef struct hdk_b200_jit_stats {
   int available;                     /* libnvrtc found and usable */
 } hdk_b200_jit_stats;
 HDK_B200_API int hdk_b200_jit_get_stats(hdk_b200_jit_stats* out);
+/* Stop run-time specialisation: drops the shapes still queued and returns once no compile is in flight (a few seconds at most).
+ * Call it before the process exits (the compile runs on a worker thread that must not outlive the libraries it uses); later
+ * launches of shapes without kernels keep running interpreted. */
+HDK_B200_API int hdk_b200_jit_shutdown(void);
 /* block until no shape is being compiled (tests, benchmarks) */
 HDK_B200_API int hdk_b200_jit_wait(void);
 

@@ -18,6 +18,9 @@ from tests import util  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    if os.environ.get("HDK_B200_TEST_JIT"):
+        from hdk_b200 import _lib
+        _lib.debug_set("jit", int(os.environ["HDK_B200_TEST_JIT"]))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rng = np.random.default_rng(7)
