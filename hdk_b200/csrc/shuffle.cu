@@ -237,6 +237,10 @@ __global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __g
     for (int r = 0; r < kShufRowsPerThread; ++r) {
       const uint64_t pos = row0 + uint64_t(r) * kShufThreads + tid;      // coalesced: consecutive threads, consecutive rows
       part[r] = pos < rows ? (a.direct ? row_partition_direct(a, kbase, pos) : row_partition(a, cols, pos, vals)) : -1;
+    }
+    // (a loop of its own: the key loads of all the thread's rows are in flight together, no warp vote between them)
+#pragma unroll
+    for (int r = 0; r < kShufRowsPerThread; ++r) {
       if (a.n_partitions > 32) {   // many partitions: lanes rarely meet, MATCH.ANY would cost one round per distinct value
         if (part[r] >= 0) atomicAdd(&hist[part[r]], 1u);
       } else {                     // warp-aggregated histogram update
@@ -407,6 +411,11 @@ __global__ void __launch_bounds__(kBigThreads, 1) scatter_big_tile_kernel(const 
       if (uint32_t(r) < ba.rpt) {
         const uint64_t pos = row0 + uint64_t(r) * kBigThreads + tid;
         if (pos < rows) part[r] = a.direct ? row_partition_direct(a, kbase, pos) : row_partition(a, cols, pos, vals);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kBigMaxRpt; ++r) {
+      if (uint32_t(r) < ba.rpt) {
         if (many) {   // many partitions: lanes rarely meet, MATCH.ANY would cost one round per distinct value
           if (part[r] >= 0) atomicAdd(&hist[part[r]], 1u);
         } else {
