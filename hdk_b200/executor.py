@@ -24,6 +24,12 @@ from . import _lib, abi, ir, planner, sql
 from .storage import ArrowStorage, Table
 
 
+# in-band error codes of a launch (ERROR_CODE; > 0 persistent): the reference's (QE/ErrorHandling.h ERR_DIV_BY_ZERO,
+# ERR_OVERFLOW_OR_UNDERFLOW) and the library's own (include/hdk_b200.h)
+ERROR_TEXT = {1: "division by zero", 7: "overflow or underflow", 1003: "group key outside the range of the perfect-hash layout",
+              1004: "a peer's partial table never arrived", 1005: "baseline hash: a claimed entry was never published"}
+
+
 class QueryError(RuntimeError):
     """In-band query error (QE/Execute.h:1019-1031 error codes)."""
 
@@ -1067,9 +1073,7 @@ class Executor:
                     info = self.execute_sharded(pq, prep)
                 code = self._agree_on_error(prep["err"])
                 if code != 0:
-                    raise QueryError(code, {1: "division by zero", 7: "overflow or underflow", 1004: "a peer's partial table never arrived",
-                                            1003: "group key outside the range of the perfect-hash layout",
-                                        1005: "baseline hash: a claimed entry was never published"}.get(code, "runtime error"))
+                    raise QueryError(code, ERROR_TEXT.get(code, "runtime error"))
                 if unit.order_by:
                     cols, n = self.compact_on_device(pq, prep["out"], to_host=False)
                     order = ResultSet(pq, np.zeros(0, dtype=np.uint8), dicts).order_entries()
@@ -1089,7 +1093,7 @@ class Executor:
                     raise QueryError(code, "ran out of slots in the group-by buffer")
                 continue
             if code != 0:
-                raise QueryError(code, {1: "division by zero", 7: "overflow or underflow"}.get(code, "runtime error"))
+                raise QueryError(code, ERROR_TEXT.get(code, "runtime error"))
             cols, n = self.compact_on_device(pq, out, to_host=False)
             order = ResultSet(pq, np.zeros(0, dtype=np.uint8), dicts).order_entries() if unit.order_by else None
             if order and unit.limit is not None:       # each owner's first `limit` rows are enough for the global first `limit`
@@ -1246,9 +1250,7 @@ class Executor:
                     raise QueryError(code, "ran out of slots in the group-by buffer")
                 continue
             if code != 0:
-                raise QueryError(code, {1: "division by zero", 7: "overflow or underflow",
-                                        1003: "group key outside the range of the perfect-hash layout",
-                                        1005: "baseline hash: a claimed entry was never published"}.get(code, "runtime error"))
+                raise QueryError(code, ERROR_TEXT.get(code, "runtime error"))
             dicts = {}
             tables = [outer] + [self.storage.get_table(j.inner_table) for j in unit.joins]
             for t, e in enumerate(unit.target_exprs):
