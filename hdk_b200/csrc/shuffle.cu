@@ -170,6 +170,7 @@ struct ScatterToArgs {
   ShuffleArgs base;
   int8_t* const* dest_cols;        // [n_partitions * n_cols]
   const uint64_t* dest_offsets;    // [n_partitions]
+  uint32_t off_part_of_pos, off_dest_ptrs;   // staged kernel: byte offsets inside dynamic shared memory (behind the staging area)
 };
 
 __device__ __forceinline__ void tile_of(const ShuffleArgs& a, uint64_t tile, const uint32_t* frag_tile_prefix, uint32_t& frag, uint64_t& row0) {
@@ -212,6 +213,13 @@ __global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __g
     }
   }
   for (uint32_t i = tid; i < a.n_partitions; i += kShufThreads) hist[i] = 0;
+  // staged: the tile position → partition map and the destination column pointers live in shared memory, so the copy-out
+  // below is one flat loop over the tile's elements without a dependent global load per (partition, column)
+  uint8_t* part_of_pos = staging + sa.off_part_of_pos;
+  int8_t** dest_s = reinterpret_cast<int8_t**>(staging + sa.off_dest_ptrs);
+  if constexpr (kStaged) {
+    for (uint32_t i = tid; i < a.n_partitions * uint32_t(p.n_cols); i += kShufThreads) dest_s[i] = sa.dest_cols[i];
+  }
   __syncthreads();
   const uint32_t total_tiles = frag_tile_prefix[a.num_fragments];
   V vals[HDK_B200_MAX_EXPRS];
@@ -264,41 +272,63 @@ __global__ void __launch_bounds__(kShufThreads, 4) shuffle_tile_kernel(const __g
     }
     __syncthreads();
     if constexpr (kStaged) {
+      // position of every row of the thread inside the staged tile (rows grouped by partition)
+      uint32_t lp[kShufRowsPerThread];
 #pragma unroll
       for (int r = 0; r < kShufRowsPerThread; ++r) {
         const unsigned peers = warp_peers(part[r], a.n_partitions);
+        lp[r] = 0xffffffffu;
         if (part[r] < 0) continue;
         const int leader = __ffs(peers) - 1;
         unsigned int start = 0;
         if (lane == leader) start = atomicAdd(&hist[part[r]], (unsigned)__popc(peers));
         start = __shfl_sync(peers, start, leader);
-        const uint32_t lp = run_start[part[r]] + start + __popc(peers & ((1u << lane) - 1u));   // position inside the tile
-        const uint64_t pos = row0 + uint64_t(r) * kShufThreads + tid;
+        lp[r] = run_start[part[r]] + start + __popc(peers & ((1u << lane) - 1u));
+        part_of_pos[lp[r]] = uint8_t(part[r]);
+      }
+      // column by column: the loads of all the thread's rows are in flight together, then their stores
 #pragma unroll
-        for (int c = 0; c < kHoist; ++c) {
-          if (c >= p.n_cols) break;
-          const int w = p.col_width[c];
-          copy_elem(staging + stage_col_off[c] + size_t(lp) * w, cbase[c] + pos * w, w);
+      for (int c = 0; c < kHoist; ++c) {
+        if (c >= p.n_cols) break;
+        const int w = p.col_width[c];
+        uint64_t v[kShufRowsPerThread];
+#pragma unroll
+        for (int r = 0; r < kShufRowsPerThread; ++r) {
+          const int8_t* src = cbase[c] + (row0 + uint64_t(r) * kShufThreads + tid) * w;
+          v[r] = 0;
+          if (lp[r] != 0xffffffffu)
+            v[r] = w == 8 ? *reinterpret_cast<const uint64_t*>(src) : w == 4 ? uint64_t(*reinterpret_cast<const uint32_t*>(src))
+                   : w == 2 ? uint64_t(*reinterpret_cast<const uint16_t*>(src)) : uint64_t(*reinterpret_cast<const uint8_t*>(src));
         }
-        for (int c = kHoist; c < p.n_cols; ++c) {
-          const int w = p.col_width[c];
-          copy_elem(staging + stage_col_off[c] + size_t(lp) * w, cols[c] + pos * w, w);
+        uint8_t* sc = staging + stage_col_off[c];
+#pragma unroll
+        for (int r = 0; r < kShufRowsPerThread; ++r) {
+          if (lp[r] == 0xffffffffu) continue;
+          uint8_t* dst = sc + size_t(lp[r]) * w;
+          if (w == 8) *reinterpret_cast<uint64_t*>(dst) = v[r];
+          else if (w == 4) *reinterpret_cast<uint32_t*>(dst) = uint32_t(v[r]);
+          else if (w == 2) *reinterpret_cast<uint16_t*>(dst) = uint16_t(v[r]);
+          else *dst = uint8_t(v[r]);
         }
       }
+      for (int c = kHoist; c < p.n_cols; ++c) {
+        const int w = p.col_width[c];
+#pragma unroll
+        for (int r = 0; r < kShufRowsPerThread; ++r)
+          if (lp[r] != 0xffffffffu) copy_elem(staging + stage_col_off[c] + size_t(lp[r]) * w, cols[c] + (row0 + uint64_t(r) * kShufThreads + tid) * w, w);
+      }
       __syncthreads();
-      // copy the runs out: consecutive threads, consecutive elements of one partition's run
+      // copy the runs out: the staged tile is ordered by partition, so consecutive threads write consecutive elements of a
+      // partition's run (whole 128-byte lines per warp except where a run ends)
+      const uint32_t n_tile = run_start[a.n_partitions];
       for (int c = 0; c < p.n_cols; ++c) {
         const int w = p.col_width[c];
         const uint8_t* sc = staging + stage_col_off[c];
-        for (uint32_t pr = 0; pr < a.n_partitions; ++pr) {
-          const uint32_t n = run_start[pr + 1] - run_start[pr];
-          if (!n) continue;
-          int8_t* out = sa.dest_cols[size_t(pr) * p.n_cols + c] + base[pr] * w;
-          const uint8_t* src = sc + size_t(run_start[pr]) * w;
-          if (w == 8) { for (uint32_t i = tid; i < n; i += kShufThreads) reinterpret_cast<uint64_t*>(out)[i] = reinterpret_cast<const uint64_t*>(src)[i]; }
-          else if (w == 4) { for (uint32_t i = tid; i < n; i += kShufThreads) reinterpret_cast<uint32_t*>(out)[i] = reinterpret_cast<const uint32_t*>(src)[i]; }
-          else if (w == 2) { for (uint32_t i = tid; i < n; i += kShufThreads) reinterpret_cast<uint16_t*>(out)[i] = reinterpret_cast<const uint16_t*>(src)[i]; }
-          else { for (uint32_t i = tid; i < n; i += kShufThreads) out[i] = int8_t(src[i]); }
+#pragma unroll 4
+        for (uint32_t i = tid; i < n_tile; i += kShufThreads) {
+          const uint32_t pr = part_of_pos[i];
+          int8_t* out = dest_s[pr * uint32_t(p.n_cols) + uint32_t(c)] + (base[pr] + (i - run_start[pr])) * w;
+          copy_elem(out, sc + size_t(i) * w, w);
         }
       }
       __syncthreads();
@@ -539,6 +569,16 @@ static int lower_for_shuffle(const hdk_b200_plan* plan, Lowered* lw) {
 
 using namespace hb;
 
+// the staged small-tile scatter: dynamic shared memory = staging area | tile position → partition bytes | destination pointers
+static int launch_staged_scatter(ScatterToArgs& sa, const Lowered& lw, uint32_t n_partitions, size_t staging, cudaStream_t st) {
+  sa.off_part_of_pos = uint32_t((staging + 15) & ~size_t(15));
+  sa.off_dest_ptrs = uint32_t((sa.off_part_of_pos + size_t(kTileRows) + 15) & ~size_t(15));
+  const size_t dyn = sa.off_dest_ptrs + size_t(n_partitions) * size_t(lw.plan.n_cols) * sizeof(void*);
+  HB_CUDA(cudaFuncSetAttribute(shuffle_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn)));
+  shuffle_tile_kernel<true, true><<<sm_count() * 3, kShufThreads, dyn, st>>>(sa);
+  return HDK_B200_OK;
+}
+
 extern "C" {
 
 int hdk_b200_shuffle_count(const hdk_b200_plan* plan, const hdk_b200_kernel_params* params, uint32_t n_partitions,
@@ -618,8 +658,7 @@ int hdk_b200_region_scatter_to(const hdk_b200_plan* plan, const hdk_b200_qmd* qm
   }
   const size_t staging = size_t(kTileRows) * lw.stage_row_bytes;
   if (n_regions <= kStagedMaxPartitions && staging <= 96 * 1024) {
-    HB_CUDA(cudaFuncSetAttribute(shuffle_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(staging)));
-    shuffle_tile_kernel<true, true><<<sm_count() * 3, kShufThreads, staging, st>>>(sa);
+    if (int rc = launch_staged_scatter(sa, lw, n_regions, staging, st)) return rc;
   } else {
     shuffle_tile_kernel<true><<<sm_count() * 4, kShufThreads, 0, st>>>(sa);
   }
@@ -655,8 +694,7 @@ int hdk_b200_shuffle_scatter_to(const hdk_b200_plan* plan, const hdk_b200_kernel
   bool staged = n_partitions >= 4 && n_partitions <= kStagedMaxPartitions && staging <= 96 * 1024;
   if (const char* env = getenv("HDK_B200_SCATTER_STAGED")) staged = env[0] == '1' && n_partitions <= kStagedMaxPartitions && staging <= 96 * 1024;   // tuning hook
   if (staged) {
-    HB_CUDA(cudaFuncSetAttribute(shuffle_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(staging)));
-    shuffle_tile_kernel<true, true><<<sm_count() * 3, kShufThreads, staging, st>>>(sa);
+    if (int rc = launch_staged_scatter(sa, lw, n_partitions, staging, st)) return rc;
   } else {
     shuffle_tile_kernel<true><<<sm_count() * 4, kShufThreads, 0, st>>>(sa);
   }
