@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kPaThreads, 2) pa_count_kernel(const __grid_co
 // One CTA aggregates a partition; a partition beyond `heavy_rows` would serialise the launch on one SM, so the whole
 // launch falls back to the global-table probe (whose atomics spread a hot key's rows over all SMs): *skewed = 1.
 __global__ void __launch_bounds__(1024) pa_offsets_kernel(const uint32_t* counts, unsigned long long* base, uint32_t P, uint32_t heavy_rows,
-                                                          int* skewed) {
+                                                          unsigned long long capacity_rows, int* skewed) {
   __shared__ unsigned long long warp_tot[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t chunk = (P + 1023) / 1024, lo = min(uint32_t(tid) * chunk, P), hi = min(lo + chunk, P);
@@ -323,7 +323,12 @@ __global__ void __launch_bounds__(1024) pa_offsets_kernel(const uint32_t* counts
   __syncthreads();
   unsigned long long run = warp_tot[warp] + incl - sum;
   for (uint32_t i = lo; i < hi; ++i) { base[i] = run; run += counts[i]; }
-  if (hi == P && lo < P) base[P] = run;   // the thread owning the last counter also writes the total
+  if (hi == P && lo < P) {   // the thread owning the last counter also writes the total
+    base[P] = run;
+    // more rows than the caller's total_rows_hint sized the record area for: stand down as well (the fallback path does
+    // not depend on the hint)
+    if (run > capacity_rows) *skewed = 1;
+  }
 }
 
 // ---- pass 3: scatter (level 1 from the columns, level 2 from level 1's records) ---------------------------------------
@@ -1058,7 +1063,7 @@ int launch_partagg(const Lowered& lw, const hdk_b200_kernel_params* params, void
   HB_CUDA(cudaFuncSetAttribute(kern.count, cudaFuncAttributeMaxDynamicSharedMemorySize, int(count_smem)));
   kern.count<<<sm_count() * (count_smem > 100 * 1024 ? 1 : 2), kPaThreads, count_smem, st>>>(a);
   HB_LAUNCH_CHECK();
-  pa_offsets_kernel<<<1, 1024, 0, st>>>(a.counts, base, g.P, g.heavy_rows, skewed);
+  pa_offsets_kernel<<<1, 1024, 0, st>>>(a.counts, base, g.P, g.heavy_rows, total_rows, skewed);
   HB_LAUNCH_CHECK();
   // level 1: fragments → F1 destinations (the final partitions themselves when one level suffices)
   a.n_dest = g.F1;

@@ -268,7 +268,8 @@ typedef struct hdk_b200_kernel_params {
   const int8_t* const* inner_col_buffers;
   /* -- extension: sum of NUM_ROWS when the host knows it (the reference fills NUM_ROWS from a host vector,
    *    QE/QueryExecutionContext.cpp:789-964), 0 = unknown.  Only sizes tiles so that small inputs still give
-   *    every resident CTA several tiles; results never depend on it. */
+   *    every resident CTA several tiles, and the record area of the partitioned baseline-hash path (a launch that finds
+   *    more rows than the hint falls back to the per-row probe); results never depend on it. */
   uint64_t total_rows_hint;
 } hdk_b200_kernel_params;
 

@@ -1211,6 +1211,27 @@ def test_partitioned_aggregation_hot_keys_fall_back(oracle_mod, torch, partition
     check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), 2)
 
 
+def test_partitioned_aggregation_with_an_undersized_row_hint(oracle_mod, env, torch, partitioned):
+    """kernel_params.total_rows_hint sizes the record area of the partitioned path.  A caller that understates it must not
+    get records written past the area: the offsets kernel compares the counted rows with the capacity and the launch stands
+    down to the per-row probe — same answer as ever ("results never depend on it", include/hdk_b200.h)."""
+    from hdk_b200.executor import Executor
+    from hdk_b200 import sql
+    tables, st = env
+    partitioned()
+    text, nk, kw = QUERIES[13]
+    for understate in (3, 1000):
+        ex = Executor(st)
+        pq = ex.plan(sql.parse(text, st.tables), kw.get("max_groups_buffer_entry_count"))
+        prep = ex.prepare(pq)
+        true_rows = int(prep["kp"].total_rows_hint)
+        prep["kp"].total_rows_hint = max(true_rows // understate, 1)
+        info = ex.launch(pq, prep)
+        torch.cuda.synchronize()
+        assert int(prep["err"].item()) == 0 and info.strategy == abi.STRATEGY_PARTITIONED
+        check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), nk)
+
+
 def test_partitioned_aggregation_out_of_slots(env, torch, partitioned):
     """More groups than entries: the reference's get_group_value returns NULL → ERR_OUT_OF_SLOTS (negative code); the
     partitioned path reports the same when the groups do not fit the buffer, and hdk.sql's retry ladder then succeeds."""
