@@ -17,7 +17,7 @@ namespace hb {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launch_count = 0;
-DebugKnobs g_debug = {0, -1, -1, 0, 0, 0, 1};
+DebugKnobs g_debug = {0, -1, -1, 0, 0, 0, 1, 0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -462,6 +462,7 @@ int hdk_b200_debug_set(const char* name, int value) {
   else if (n == "partitioned_partitions") hb::g_debug.pa_partitions = value;
   else if (n == "partitioned_heavy_rows") hb::g_debug.pa_heavy_rows = value;
   else if (n == "jit") hb::g_debug.jit = value;
+  else if (n == "geo_env_refresh") hb::g_debug.geo_env_refresh = value;
   else { hb::set_error("unknown debug knob '%s'", name); return HDK_B200_E_INVALID; }
   return HDK_B200_OK;
 }

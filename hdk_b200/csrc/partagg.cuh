@@ -73,6 +73,7 @@ struct DebugKnobs {
   int pa_partitions;        // 0 auto, else the number of partitions
   int pa_heavy_rows;        // 0 auto, else the partition size beyond which the launch falls back to the global-table probe
   int jit;                  // run-time specialisation of plan shapes without pre-compiled kernels: 0 off, 1 in the background, 2 before the launch
+  int geo_env_refresh;      // 1: read HDK_B200_GEO on every launch instead of once per process (tools/sweep_geo.py)
 };
 extern DebugKnobs g_debug;
 

@@ -116,9 +116,9 @@ struct GeoEntry {
 };
 static std::mutex g_geo_mutex;
 static std::vector<GeoEntry> g_geo_cache;
-static const char* geo_env() {   // tuning hook (tools/sweep_geo.py), read once
+static const char* geo_env() {   // tuning hook (tools/sweep_geo.py), read once unless the sweep asks for every launch
   static const char* env = getenv("HDK_B200_GEO");
-  return env;
+  return g_debug.geo_env_refresh ? getenv("HDK_B200_GEO") : env;
 }
 
 static int launch_scan_impl(const Lowered& lw, const hdk_b200_kernel_options* ko, const hdk_b200_kernel_params* params,

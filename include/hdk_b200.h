@@ -712,7 +712,9 @@ HDK_B200_API int hdk_b200_jit_wait(void);
  *   "partitioned_heavy_rows"   0 = library picks; else the partition size (rows) beyond which a partitioned launch falls
  *                              back to the global-table probe (hot keys)
  *   "jit"                      run-time specialisation (see hdk_b200_jit_*): 0 off, 1 compile in the background (default
- *                              when NVRTC is present), 2 compile before the first launch of a shape */
+ *                              when NVRTC is present), 2 compile before the first launch of a shape
+ *   "geo_env_refresh"          1 = read the HDK_B200_GEO tuning override on every launch instead of once per process
+ *                              (tools/sweep_geo.py) */
 HDK_B200_API int hdk_b200_debug_set(const char* name, int value);
 HDK_B200_API const char* hdk_b200_last_error(void);
 HDK_B200_API int hdk_b200_abi_version(void);

@@ -30,7 +30,8 @@ UNIT_SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e
 
 def main():
     rep, tag = sys.argv[1], sys.argv[2]
-    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True)
+    # (a .csv argument is the `ncu -i … --page raw --csv` export made on the GPU box, for reports too big to pull)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True)
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -51,7 +52,10 @@ def main():
             tot += float(r[idx[m]].replace(",", "")) * UNIT_SCALE.get(units[idx[m]], 1.0)
         traffic[f"q{i + 1}"] = tot
     traffic["_source"] = f"{os.path.basename(rep)}: dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full, 1.1B rows)"
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    merged = json.load(open(tpath)) if os.path.exists(tpath) else {}     # keep the other configs' keys (tools/profile_configs.py)
+    merged.update(traffic)
+    json.dump(merged, open(tpath, "w"), indent=1)
     print("wrote", out, "and profiles/traffic.json", traffic)
 
 

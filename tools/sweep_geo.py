@@ -45,6 +45,8 @@ def main():
     ap.add_argument("--geos", default="", help="semicolon-separated explicit geometries; default: a built-in grid")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
+    from hdk_b200 import _lib
+    _lib.debug_set("geo_env_refresh", 1)     # the library reads HDK_B200_GEO once per process otherwise
     st = ArrowStorage()
     benchdata.make_taxi(st, dev, args.rows)
     ex = Executor(st)
