@@ -48,3 +48,31 @@ def test_b200kernel_shim_compiles():
         r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), src],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_header_compiles_as_plain_c_and_declares_the_round2_entry_points():
+    """The drop-in boundary is a C ABI: include/hdk_b200.h must compile as C99 (no C++ in the signatures), and the entry
+    points INTEGRATION.md §1b / §3b tell a maintainer to call must be declared with the argument lists the document shows."""
+    src_text = r'''
+#include "hdk_b200.h"
+static int use(const hdk_b200_plan* plan, const hdk_b200_qmd* qmd, const int64_t* cells, int8_t* values, uint32_t* validity,
+               uint64_t* null_count, void* stream) {
+  size_t scratch = 0;
+  hdk_b200_jit_stats st;
+  int rc = hdk_b200_launch_scratch_bytes(plan, qmd, (uint64_t)1000000, &scratch);
+  rc |= hdk_b200_arrow_column_on_device(cells, (uint64_t)10, 0, 0, 8, 1, INT64_MIN, 0.0, values, validity, null_count, stream);
+  rc |= hdk_b200_debug_set("jit", 2);
+  rc |= hdk_b200_jit_get_stats(&st);
+  rc |= hdk_b200_jit_wait();
+  rc |= hdk_b200_jit_shutdown();
+  return rc + (HDK_B200_ERR_CLAIM_TIMEOUT == 1005) + (HDK_B200_ERR_PEER_TIMEOUT == 1004);
+}
+int main(void) { return use(0, 0, 0, 0, 0, 0, 0) ? 0 : 1; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "abi.c")
+        with open(src, "w") as f:
+            f.write(src_text)
+        r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
