@@ -114,7 +114,7 @@ def main():
     ]
     for text, nk in api_queries:
         order = (" ORDER BY " + ", ".join(str(i + 1) for i in range(nk))) if nk else ""
-        got = [tuple(r.values()) for r in h.sql(text + order).to_arrow().to_pylist()]
+        got = util.arrow_rows(h.sql(text + order).to_arrow())
         text_sqlite = text.replace("EXTRACT(YEAR FROM ts)", "CAST(strftime('%Y', ts) AS INT)")
         exp = util.sqlite_rows(tables, text_sqlite + order, nk)
         if nk == 0:

@@ -123,7 +123,7 @@ def test_fuzz_gpu_vs_sqlite(seed, config):
     compared = 0
     for text in queries(seed, 150):
         try:
-            got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+            got = util.arrow_rows(h.sql(text).to_arrow())
         except planner.UnsupportedPlan:
             continue
         except QueryError:
@@ -252,7 +252,7 @@ def test_fuzz_joins_gpu_vs_sqlite(seed):
     compared = 0
     for text in join_queries(seed, 150):
         try:
-            got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+            got = util.arrow_rows(h.sql(text).to_arrow())
         except (planner.UnsupportedPlan, QueryError):
             continue
         try:

@@ -159,7 +159,7 @@ def test_reduce_and_launch_with_buffers_beyond_4_gib(oracle_mod):
     obuf, oerr = util.run_oracle(oracle_mod, st, pq_small)
     assert oerr == 0
     exp = util.sort_rows(util.result_columns(oracle_mod, pq_small, obuf), 2)
-    got = [tuple(r.values()) for r in rows_whole.to_pylist()]
+    got = util.arrow_rows(rows_whole)
     util.assert_rows_equal(got, exp)
 
 

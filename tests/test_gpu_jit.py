@@ -92,7 +92,7 @@ def test_jit_fuzz_vs_sqlite(jit_sync):
     compared = 0
     for text in queries(31, 24):
         try:
-            got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+            got = util.arrow_rows(h.sql(text).to_arrow())
         except (planner.UnsupportedPlan, QueryError):
             continue
         exp = util.sqlite_rows(tables, text, 0)
@@ -124,7 +124,7 @@ def test_harvested_reference_queries_run_specialised(jit_sync):
     specialised = interpreted = 0
     for text in texts[::stride]:
         res = h.sql(text)
-        got = [tuple(r.values()) for r in res.to_arrow().to_pylist()]
+        got = util.arrow_rows(res.to_arrow())
         exp = util.sqlite_rows(tables, text, 0)
         if "ORDER BY" not in text.upper():
             got, exp = sorted(got, key=repr), sorted(exp, key=repr)

@@ -280,7 +280,7 @@ def test_fused_baseline_join_probe(oracle_mod, L, torch, text, nk):
         h.import_arrow(tb, name, fragment_size=1201 if name == "t" else 100000)
     order = ", ".join(str(i + 1) for i in range(nk))
     res = h.sql(text + " ORDER BY " + order).to_arrow()
-    got = [tuple(r.values()) for r in res.to_pylist()]
+    got = util.arrow_rows(res)
     util.assert_rows_equal(got, util.sqlite_rows(tables, text + " ORDER BY " + order, nk), rel=1e-9)
 
 
@@ -293,7 +293,7 @@ def test_int32_outer_key_against_wide_int64_inner_key(oracle_mod, torch):
     h = hdkmod.init()
     for name, tb in tables.items():
         h.import_arrow(tb, name, fragment_size=701 if name == "t" else 100000)
-    got = [tuple(r.values()) for r in h.sql(text + " ORDER BY 1").to_arrow().to_pylist()]
+    got = util.arrow_rows(h.sql(text + " ORDER BY 1").to_arrow())
     util.assert_rows_equal(got, util.sqlite_rows(tables, text + " ORDER BY 1", nk))
 
 
@@ -319,7 +319,7 @@ def test_non_grouped_aggregates(oracle_mod, torch, text):
     h = hdkmod.init()
     for name, tb in tables.items():
         h.import_arrow(tb, name, fragment_size=1201 if name == "t" else 100000)
-    got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+    got = util.arrow_rows(h.sql(text).to_arrow())
     assert len(got) == 1
     util.assert_rows_equal(got, util.sqlite_rows(tables, text, 0), rel=1e-9)
 
@@ -466,7 +466,7 @@ def test_reference_join_fixtures_on_gpu(oracle_mod, torch):
     for name, t in tables.items():
         h.import_arrow(t, name, fragment_size=2)
     for text in JOIN_FIXTURE_QUERIES:
-        got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+        got = util.arrow_rows(h.sql(text).to_arrow())
         exp = util.sqlite_rows(tables, text, 0)
         if "ORDER BY" in text:
             util.assert_rows_equal(got, exp, rel=1e-9)
@@ -488,7 +488,7 @@ def test_group_by_perfect_hash_on_gpu(oracle_mod, torch, bigint_count):
     for text in GROUP_BY_PERFECT_HASH_QUERIES:
         res = h.sql(text)
         assert res.result_set.sorted_on_device
-        got = [tuple(r.values()) for r in res.to_arrow().to_pylist()]
+        got = util.arrow_rows(res.to_arrow())
         util.assert_rows_equal(got, util.sqlite_rows(tables, sqlite_text(text), 0), rel=1e-6)
 
 
@@ -517,7 +517,7 @@ def test_one_to_many_joins_on_gpu(oracle_mod, torch):
         torch.cuda.synchronize()
         assert int(prep["err"].item()) == 0, text
         check_against_oracle(oracle_mod, st, pq, prep["out"].cpu().numpy(), pq.plan.n_keys)
-        got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+        got = util.arrow_rows(h.sql(text).to_arrow())
         util.assert_rows_equal(sorted(got, key=repr), sorted(util.sqlite_rows(tables, text, 0), key=repr), rel=1e-9)
 
 
@@ -532,7 +532,7 @@ def test_reference_simple_aggregation_and_short_circuit_on_gpu(oracle_mod, torch
     h = hdk_mod.init()
     h.import_arrow(tables["test"], "test", fragment_size=2)
     for text in REFERENCE_SIMPLE_QUERIES + SHORT_CIRCUIT_QUERIES:
-        got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+        got = util.arrow_rows(h.sql(text).to_arrow())
         exp = util.sqlite_rows(tables, text, 0)
         if "ORDER BY" not in text:
             got, exp = sorted(got, key=repr), sorted(exp, key=repr)
@@ -543,7 +543,7 @@ def test_reference_simple_aggregation_and_short_circuit_on_gpu(oracle_mod, torch
         assert ei.value.code == 1, text
     from tests.test_sqlite_oracle import SHORT_CIRCUIT_NULL_QUERIES
     for text in SHORT_CIRCUIT_NULL_QUERIES:       # a NULL on the safe side decides: the whole AND / OR is NULL
-        assert [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()] == [(0,)], text
+        assert util.arrow_rows(h.sql(text).to_arrow()) == [(0,)], text
 
 
 def test_reference_harvested_queries_on_gpu(oracle_mod, torch):
@@ -557,7 +557,7 @@ def test_reference_harvested_queries_on_gpu(oracle_mod, torch):
         h.import_arrow(t, name, fragment_size=2)
     for name, queries in REFERENCE_HARVESTED_QUERIES.items():
         for text in queries:
-            got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+            got = util.arrow_rows(h.sql(text).to_arrow())
             exp = util.sqlite_rows(tables, text, 0)
             if "ORDER BY" not in text.upper():
                 got, exp = sorted(got, key=repr), sorted(exp, key=repr)
@@ -593,7 +593,7 @@ def test_arrow_buffers_built_on_device_equal_host_conversion(oracle_mod, torch):
                 host, dev = host.sort_by(order), dev.sort_by(order)
             # (two executions: fp64 sums are accumulated with atomics in an order that differs from run to run)
             try:
-                util.assert_rows_equal([tuple(r.values()) for r in dev.to_pylist()], [tuple(r.values()) for r in host.to_pylist()], rel=1e-9)
+                util.assert_rows_equal(util.arrow_rows(dev), util.arrow_rows(host), rel=1e-9)
             except AssertionError as e:
                 raise AssertionError(f"{text}: {e}")
     assert n_dev > 100
@@ -607,7 +607,7 @@ def test_null_div_by_zero_on_gpu(oracle_mod, torch):
     h = hdk_mod.init(null_div_by_zero=True)
     h.import_arrow(tables["test"], "test", fragment_size=2)
     for text in NULL_DIV_BY_ZERO_QUERIES:
-        got = [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()]
+        got = util.arrow_rows(h.sql(text).to_arrow())
         exp = util.sqlite_rows(tables, sqlite_text(text), 0)
         if "ORDER BY" not in text:
             got, exp = sorted(got, key=repr), sorted(exp, key=repr)
@@ -647,7 +647,7 @@ def test_executor_sql_end_to_end_vs_sqlite(env, torch):
     for text, nk in [("SELECT s, COUNT(*) AS c, SUM(w) AS sw, AVG(f) AS af FROM t GROUP BY s ORDER BY s", 1),
                      ("SELECT k, MIN(v) AS mn, MAX(v) AS mx FROM t WHERE w > 10 GROUP BY k ORDER BY k", 1)]:
         res = h.sql(text).to_arrow()
-        got = [tuple(r.values()) for r in res.to_pylist()]
+        got = util.arrow_rows(res)
         exp = util.sqlite_rows({"t": tables["t"].select(["k", "s", "v", "w", "f"])}, text, nk)
         util.assert_rows_equal(got, exp)
 

@@ -173,7 +173,7 @@ def test_order_by_limit_through_the_facade_vs_sqlite(oracle_mod):
     for q in queries:
         res = hdk.sql(q)
         assert res.result_set.sorted_on_device
-        got = [tuple(r.values()) for r in res.to_arrow().to_pylist()]
+        got = util.arrow_rows(res.to_arrow())
         exp = util.sqlite_rows({"t": t}, q, 0)
         util.assert_rows_equal(got, exp, rel=1e-9)
 

@@ -108,7 +108,7 @@ def test_non_grouped_aggregates_vs_sqlite(oracle_mod, text):
     assert pq.qmd.key_count == 0 and pq.qmd.entry_count == 1 and pq.qmd.keyless == 1
     buf, err = util.run_oracle(oracle_mod, st, pq, kind="port")
     assert err == 0
-    got = [tuple(r.values()) for r in ResultSet(pq, buf).to_arrow().to_pylist()]
+    got = util.arrow_rows(ResultSet(pq, buf).to_arrow())
     assert len(got) == 1
     util.assert_rows_equal(got, util.sqlite_rows(tables, text, 0), rel=1e-9)
 
@@ -194,7 +194,7 @@ def test_filter_and_group_by_vs_sqlite(oracle_mod, text, nk):
     assert err == 0
     dicts = {t: st.get_table("test").columns[e.column].dictionary for t, e in enumerate(pq.unit.target_exprs)
              if getattr(e, "column", None) and e.type.kind == "dict"}
-    got = [tuple(r.values()) for r in ResultSet(pq, buf, dicts).to_arrow().to_pylist()]
+    got = util.arrow_rows(ResultSet(pq, buf, dicts).to_arrow())
     exp = util.sqlite_rows(tables, text, nk)
     keyf = lambda r: tuple((0, 0) if x is None else (1, x) for x in r)   # noqa: E731
     util.assert_rows_equal(sorted(got, key=keyf), sorted(exp, key=keyf), rel=1e-6)
@@ -245,7 +245,7 @@ def test_case_expressions_vs_sqlite(oracle_mod, text, nk, kind):
     pq = util.plan_sql(st, text)
     buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
     assert err == 0
-    got = [tuple(r.values()) for r in ResultSet(pq, buf, {}).to_arrow().to_pylist()]
+    got = util.arrow_rows(ResultSet(pq, buf, {}).to_arrow())
     exp = util.sqlite_rows(tables, text, nk)
     keyf = lambda r: tuple((0, 0) if x is None else (1, x) for x in r)   # noqa: E731
     util.assert_rows_equal(sorted(got, key=keyf), sorted(exp, key=keyf), rel=1e-9)
@@ -334,7 +334,7 @@ def test_overflow_and_underflow_no_error(oracle_mod, text, kind):
     pq = util.plan_sql(st, text)
     buf, err = util.run_oracle(oracle_mod, st, pq, kind=kind)
     assert err == 0
-    got = [tuple(r.values()) for r in ResultSet(pq, buf, {}).to_arrow().to_pylist()]
+    got = util.arrow_rows(ResultSet(pq, buf, {}).to_arrow())
     exp = util.sqlite_rows(tables, text, 0)
     if "ORDER BY" in text:          # ordered on the COUNT only: compare the ordered counts and the row sets
         assert [r[-1] for r in got] == [r[-1] for r in exp]
@@ -405,7 +405,7 @@ def decode_with_dictionaries(st, pq, buf):
     tabs = [st.get_table(pq.unit.table)] + [st.get_table(j.inner_table) for j in pq.unit.joins]
     dicts = {i: tabs[e.table].columns[e.column].dictionary for i, e in enumerate(pq.unit.target_exprs)
              if isinstance(getattr(e, "column", None), str) and e.type.kind == "dict"}
-    return [tuple(r.values()) for r in ResultSet(pq, buf, dicts).to_arrow().to_pylist()]
+    return util.arrow_rows(ResultSet(pq, buf, dicts).to_arrow())
 
 
 @pytest.mark.parametrize("text", JOIN_FIXTURE_QUERIES)

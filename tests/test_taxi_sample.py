@@ -66,4 +66,4 @@ def test_taxi_sample_known_answers_gpu(text):
     import hdk_b200.hdk as hdk_mod
     h = hdk_mod.init()
     h.import_arrow(trips_table(), "trips", fragment_size=7)
-    check(text, [tuple(r.values()) for r in h.sql(text).to_arrow().to_pylist()])
+    check(text, util.arrow_rows(h.sql(text).to_arrow()))

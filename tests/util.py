@@ -144,6 +144,13 @@ def assert_rows_equal(got, exp, rel=1e-9, float_cols=()):
                 assert a == b, f"row {r} col {c}: {a} vs {b}"
 
 
+def arrow_rows(table):
+    """Rows of an Arrow table as tuples, column by column (Table.to_pylist() makes dicts: two result columns of the same
+    name — `SELECT j1.h, j2.h …` — would collapse into one)."""
+    cols = [c.to_pylist() for c in table.columns]
+    return [tuple(r) for r in zip(*cols)] if cols else []
+
+
 def sqlite_rows(tables, text, n_keys):
     """The reference's own differential oracle: the same SQL on SQLite
     (omniscidb/Tests/ArrowSQLRunner/SQLiteComparator.cpp:66-170)."""
